@@ -1,0 +1,165 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY.
+
+CPU restatement of pyoomph's assembly path (generated-format C plugin + restated host driver), used as the
+checker in tests/, in __graft_entry__.smoke() and as bench.py's CPU baseline.  Nothing under pyoomph_b200/
+imports this package; the product path never executes it.
+
+Parity status: the reference cannot be built or imported in this environment (GiNaC/CLN are not
+vendored) and ships no golden vectors for this path.  What IS pinned against the reference's
+own code: Gauss tables and Lagrange shape functions (against oomph-lib sources compiled into oracle/_ref), the
+plugin ABI headers and accumulate macros (same generated C compiled against /root/reference/src/jitbridge*.h,
+bit-identical results).  The geometry/derivation logic is pinned only by patch, finite-difference and invariance
+tests => "parity unpinned" at the Jacobian level.
+"""
+from __future__ import annotations
+
+import ctypes
+import hashlib
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+from .emit_c import emit_plugin_source
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "_build")
+REF_BUILD = os.path.join(HERE, "_ref")
+REFERENCE_SRC = "/root/reference/src"
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int_p) if a is not None else None
+
+
+def cpu_flags(fast_math: bool = False):
+    """SystemCCompiler flags (/root/reference/pyoomph/generic/ccompiler.py:214-220, :233)."""
+    fl = ["-O3", "-fPIC", "-march=native"]
+    if fast_math:
+        fl.append("-ffast-math")
+    return fl
+
+
+def build_plugin(code, name: str, *, reference_headers: bool = False, fast_math: bool = False, force: bool = False) -> str:
+    """Emit the generated-format C for `code`, compile it with the restated driver, return the .so path.
+
+    reference_headers=True compiles the same sources against the reference's own jitbridge.h/jitbridge_hang.h
+    where they lie (outputs only into oracle/_ref/)."""
+    src = emit_plugin_source(code)
+    outdir = REF_BUILD if reference_headers else BUILD
+    os.makedirs(outdir, exist_ok=True)
+    driver = open(os.path.join(HERE, "driver.c")).read()
+    hdrs = open(os.path.join(HERE, "oracle_jit.h")).read() + open(os.path.join(HERE, "oracle_jit_hang.h")).read()
+    tag = hashlib.sha1((src + driver + hdrs + str(fast_math)).encode()).hexdigest()[:12]
+    cfile = os.path.join(outdir, "%s_%s.c" % (name, tag))
+    sofile = os.path.join(outdir, "%s_%s%s.so" % (name, tag, "_ref" if reference_headers else ""))
+    if os.path.exists(sofile) and not force:
+        return sofile
+    with open(cfile, "w") as f:
+        f.write(src)
+    cmd = ["gcc", "-std=gnu99"] + cpu_flags(fast_math) + ["-fopenmp", "-shared", "-I", HERE]
+    if reference_headers:
+        if not os.path.isdir(REFERENCE_SRC):
+            raise RuntimeError("reference tree not present")
+        cmd += ["-DORACLE_USE_REFERENCE_HEADERS", "-I", REFERENCE_SRC]
+    cmd += [os.path.join(HERE, "driver.c"), cfile, "-o", sofile, "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle plugin compilation failed:\n" + r.stderr[-4000:])
+    return sofile
+
+
+class OracleProblem:
+    """One mesh + one element class, assembled the reference's way on the CPU."""
+
+    def __init__(self, code, mesh, dofmap, node_val: np.ndarray, *, node_pos_hist: Optional[np.ndarray] = None,
+                 node_lagr: Optional[np.ndarray] = None, name: str = "plugin", reference_headers: bool = False,
+                 fast_math: bool = False, so_path: Optional[str] = None):
+        self.code, self.mesh, self.dofmap = code, mesh, dofmap
+        so = so_path or build_plugin(code, name, reference_headers=reference_headers, fast_math=fast_math)
+        self.lib = ctypes.CDLL(so)
+        L = self.lib
+        L.oracle_create.restype = ctypes.c_void_p
+        L.oracle_assemble.restype = ctypes.c_double
+        L.oracle_nnz.restype = ctypes.c_int64
+        L.oracle_element.restype = ctypes.c_int
+        self.dim = mesh.dim
+        self.elem_nodes = np.ascontiguousarray(mesh.elem_nodes, dtype=np.int32)
+        node_val = np.ascontiguousarray(node_val, dtype=np.float64)
+        if node_val.ndim == 2:
+            node_val = node_val[None]
+        self.T = node_val.shape[0]
+        pos = mesh.node_pos[None] if node_pos_hist is None else node_pos_hist
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        lagr = np.ascontiguousarray(mesh.node_pos if node_lagr is None else node_lagr, dtype=np.float64)
+        self.node_eqn = np.ascontiguousarray(dofmap.node_eqn, dtype=np.int32)
+        self.pos_eqn = None if dofmap.pos_eqn is None else np.ascontiguousarray(dofmap.pos_eqn, dtype=np.int32)
+        self.n_dof = dofmap.n_dof
+        self.h = ctypes.c_void_p(L.oracle_create(self.dim, mesh.n_elem, _ip(self.elem_nodes), mesh.n_node,
+                                                 node_val.shape[2], self.T, pos.shape[0], _dp(pos), _dp(lagr),
+                                                 _dp(node_val), _ip(self.node_eqn), _ip(self.pos_eqn), self.n_dof))
+        self.maxdof = mesh.elem_nodes.shape[1] * (self.dim + node_val.shape[2])
+
+    def set_params(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        self.lib.oracle_set_params(self.h, _dp(v), len(v))
+
+    def set_steady(self):
+        z = np.zeros(7)
+        self.lib.oracle_set_time(self.h, 1, 0, 0, _dp(z), _dp(z), _dp(z), _dp(z), _dp(z), _dp(z))
+
+    def set_unsteady(self, t: float, dt: float, dtprev: float, unsteady_steps_done: int, ntstorage: int = 3):
+        w1, w2, z = np.zeros(7), np.zeros(7), np.zeros(7)
+        self.lib.oracle_bdf_weights(ctypes.c_double(dt), ctypes.c_double(dtprev), _dp(w1), _dp(w2))
+        tt = np.zeros(7); tt[0] = t; tt[1] = t - dt; tt[2] = t - dt - dtprev
+        dd = np.zeros(7); dd[0] = dt; dd[1] = dtprev
+        self.lib.oracle_set_time(self.h, 0, unsteady_steps_done, ntstorage, _dp(tt), _dp(dd), _dp(w1), _dp(w2), _dp(z), _dp(z))
+        return w1, w2
+
+    def update_values(self, t: int, node_val=None, node_pos=None):
+        nv = None if node_val is None else np.ascontiguousarray(node_val, dtype=np.float64)
+        npos = None if node_pos is None else np.ascontiguousarray(node_pos, dtype=np.float64)
+        self.lib.oracle_update_values(self.h, t, _dp(nv), _dp(npos))
+
+    def element(self, e: int, which: int = 0, param: int = -1, flag: int = 1):
+        n = self.maxdof
+        R, J, M = np.zeros(n), np.zeros(n * n), np.zeros(n * n)
+        eq = np.zeros(n, dtype=np.int32)
+        nd = self.lib.oracle_element(self.h, e, which, param, flag, _dp(R), _dp(J), _dp(M), _ip(eq))
+        # the routine used jacobian_size = ndof
+        return R[:nd].copy(), J[:nd * nd].reshape(nd, nd).copy(), M[:nd * nd].reshape(nd, nd).copy(), eq[:nd].copy()
+
+    def assemble(self, which: int = 0, param: int = -1, flag: int = 1, nthreads: int = 1):
+        """Returns residual and (row_start, col_index, value) per matrix in the reference's vectors_of_pairs
+        order (columns in first-touch order, exact zeros dropped)."""
+        res = np.zeros(self.n_dof)
+        self.lib.oracle_assemble(self.h, which, param, flag, _dp(res), nthreads)
+        mats = []
+        for m in range(0 if flag == 0 else (1 if flag == 1 else 2)):
+            nnz = int(self.lib.oracle_nnz(self.h, m))
+            rs = np.zeros(self.n_dof + 1, dtype=np.int32)
+            ci = np.zeros(nnz, dtype=np.int32)
+            va = np.zeros(nnz)
+            self.lib.oracle_get_csr(self.h, m, _ip(rs), _ip(ci), _dp(va))
+            mats.append((rs, ci, va))
+        return res, mats
+
+    def point_shapes(self, e: int, ipt: int, flag: int = 1):
+        nn, d = self.mesh.elem_nodes.shape[1], self.dim
+        w = np.zeros(3); sh = np.zeros(nn); dx = np.zeros((nn, d)); dX = np.zeros((nn, d))
+        wd = np.zeros((d, nn)); dd = np.zeros((nn, d, nn, d))
+        self.lib.oracle_point_shapes(self.h, e, ipt, flag, _dp(w), _dp(sh), _dp(dx), _dp(dX), _dp(wd), _dp(dd))
+        return w, sh, dx, dX, wd, dd
+
+    def close(self):
+        if self.h:
+            self.lib.oracle_free(self.h)
+            self.h = None

@@ -1,0 +1,822 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY.  Never linked into, imported by, or executed from the product path
+ * (only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it).
+ *
+ * CPU restatement of the host side of pyoomph's element assembly, i.e. everything around the generated
+ * routine, following the reference file by file:
+ *   - element-local data tables            /root/reference/src/elements.cpp:2713-2990 (fill_element_info)
+ *   - per-assembly shape buffer prep       src/elements.cpp:4577-4646 (prepare_shape_buffer_for_integration),
+ *                                          :4510-4562 (Pos space aliases the dominant space)
+ *   - per-Gauss-point geometry and shapes  src/elements.cpp:4564-4575, :3593-4300 (fill_shape_info_at_s)
+ *   - moving-mesh derivative tensors       src/elements.cpp:3051-3155 (fill_shape_info_at_s_dNodalPos_helper)
+ *   - shape functions / node order         oomph-lib/include/shape.h:604-650, Qelements.cc:348-377, :621-660,
+ *                                          src/elements.cpp:9274-9306, :11163-11210 (C1 on vertex nodes)
+ *   - Gauss rules (literal tables, incl. the mistyped knots of Gauss<2,3>)  oomph-lib/include/integral.cc:84-102, :169-207
+ *   - element wrapper                      src/elements.cpp:5054-5127 (fill_in_generic_residual_contribution_jit)
+ *   - global loop + vectors_of_pairs CSR   oomph-lib/include/problem.cc:5459-5659, Numerical_zero 0.0 (:110)
+ *   - local equation order                 oomph-lib/include/elements.cc:694-699 (nodal values, then solid positions)
+ *   - time-stepper weight selection        src/elements.cpp:4583-4632 (_degr rule)
+ * It is compiled together with one generated-format plugin (oracle/emit_c.py) into one shared object.
+ * Parity status: the restated tables/shape functions are pinned against the reference's own oomph-lib
+ * sources compiled into oracle/_ref (tests/test_oracle_ref.py); the geometry/assembly logic has no golden
+ * vectors in the reference and is pinned by patch / finite-difference / invariance tests only.
+ */
+#define JIT_ELEMENT_SHARED_LIB
+#include "oracle_jit.h"
+#include <math.h>
+#include <stdint.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+extern void JIT_ELEMENT_init(JITFuncSpec_Table_FiniteElement_t *functable);
+
+/* ------------------------------------------------------------------ quadrature tables (verbatim literals) */
+#define K3 0.774596669241483
+#define K3T 0.774596662941483 /* sic, integral.cc:87-93 */
+static const double Gauss23_knot[9][2] = {{-K3, -K3}, {-K3, 0.0}, {-K3, K3T}, {0.0, -K3}, {0.0, 0.0}, {0.0, K3T}, {K3T, -K3}, {K3T, 0.0}, {K3T, K3T}};
+static const double Gauss23_weight[9] = {(25.0 / 81.0), (40.0 / 81.0), (25.0 / 81.0), (40.0 / 81.0), (64.0 / 81.0), (40.0 / 81.0), (25.0 / 81.0), (40.0 / 81.0), (25.0 / 81.0)};
+#define K33 0.77459666924148
+static double Gauss33_knot[27][3];
+static const double Gauss33_weight[27] = {
+    0.17146776406035, 0.27434842249657, 0.17146776406035, 0.27434842249657, 0.43895747599451, 0.27434842249657, 0.17146776406035,
+    0.27434842249657, 0.17146776406035, 0.27434842249657, 0.43895747599451, 0.27434842249657, 0.43895747599451, 0.70233196159122,
+    0.43895747599451, 0.27434842249657, 0.43895747599451, 0.27434842249657, 0.17146776406035, 0.27434842249657, 0.17146776406035,
+    0.27434842249657, 0.43895747599451, 0.27434842249657, 0.17146776406035, 0.27434842249657, 0.17146776406035};
+static void init_tables(void)
+{
+  static int done = 0;
+  if (done) return;
+  const double k[3] = {-K33, 0, K33};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      for (int l = 0; l < 3; l++)
+      {
+        Gauss33_knot[9 * i + 3 * j + l][0] = k[i];
+        Gauss33_knot[9 * i + 3 * j + l][1] = k[j];
+        Gauss33_knot[9 * i + 3 * j + l][2] = k[l];
+      }
+  done = 1;
+}
+
+void oracle_gauss(int dim, int ipt, double *knot, double *weight)
+{
+  init_tables();
+  if (dim == 2) { knot[0] = Gauss23_knot[ipt][0]; knot[1] = Gauss23_knot[ipt][1]; *weight = Gauss23_weight[ipt]; }
+  else { for (int i = 0; i < 3; i++) knot[i] = Gauss33_knot[ipt][i]; *weight = Gauss33_weight[ipt]; }
+}
+
+/* ------------------------------------------------------------------ shape functions */
+static void lag3(double s, double *p) { p[0] = 0.5 * s * (s - 1.0); p[1] = 1.0 - s * s; p[2] = 0.5 * s * (s + 1.0); }
+static void dlag3(double s, double *p) { p[0] = s - 0.5; p[1] = -2.0 * s; p[2] = s + 0.5; }
+static void lag2(double s, double *p) { p[0] = 0.5 * (1.0 - s); p[1] = 0.5 * (1.0 + s); }
+static void dlag2(double s, double *p) { (void)s; p[0] = -0.5; p[1] = 0.5; }
+
+/* psi[n], dpsi[n][dim]; order = 3 (C2) or 2 (C1) */
+void oracle_dshape_local(int dim, int order, const double *s, double *psi, double *dpsi)
+{
+  double P[3][3], D[3][3];
+  for (int a = 0; a < dim; a++)
+  {
+    if (order == 3) { lag3(s[a], P[a]); dlag3(s[a], D[a]); }
+    else { lag2(s[a], P[a]); dlag2(s[a], D[a]); }
+  }
+  int index = 0;
+  if (dim == 2)
+  {
+    for (int i = 0; i < order; i++)
+      for (int j = 0; j < order; j++)
+      {
+        dpsi[index * 2 + 0] = P[1][i] * D[0][j];
+        dpsi[index * 2 + 1] = D[1][i] * P[0][j];
+        psi[index] = P[1][i] * P[0][j];
+        ++index;
+      }
+  }
+  else
+  {
+    for (int i = 0; i < order; i++)
+      for (int j = 0; j < order; j++)
+        for (int k = 0; k < order; k++)
+        {
+          dpsi[index * 3 + 0] = P[2][i] * P[1][j] * D[0][k];
+          dpsi[index * 3 + 1] = P[2][i] * D[1][j] * P[0][k];
+          dpsi[index * 3 + 2] = D[2][i] * P[1][j] * P[0][k];
+          psi[index] = P[2][i] * P[1][j] * P[0][k];
+          ++index;
+        }
+  }
+}
+
+/* ------------------------------------------------------------------ problem data */
+#define MAXN 27
+#define MAXD 3
+#define NTW 7
+
+typedef struct
+{
+  int dim, nnode, nnode_C1, n_int;
+  int c1_nodes[8];
+} EType;
+
+typedef struct { int col; double val; } Pair;
+typedef struct { Pair *p; int n, cap; } Row;
+
+typedef struct
+{
+  EType et;
+  int n_elem, n_node, nval, T, n_dof, n_pos_hist;
+  const int *elem_nodes; /* [n_elem][nnode] */
+  double *pos;           /* [node][dim][T]   oomph Data layout: value-major, history contiguous */
+  double *lagr;          /* [node][dim] */
+  double *val;           /* [node][nval][T] */
+  const int *node_eqn;   /* [node][nval] */
+  const int *pos_eqn;    /* [node][dim] or NULL */
+  JITFuncSpec_Table_FiniteElement_t *ft;
+  double *params;
+  double t[NTW], dt[NTW];
+  double wBDF1[NTW], wBDF2[NTW], wNM2[NTW], wNM2_d2t[NTW];
+  int steady, unsteady_steps_done, ntstorage;
+  /* CSR result of the last assembly, per matrix (0: Jacobian, 1: mass matrix) */
+  int *row_start[2], *col_index[2];
+  double *value[2];
+  int64_t nnz[2];
+} Oracle;
+
+/* per-thread assembly state = the reference's global shape buffer + _currently_assembled_element
+ * (src/elements.cpp:34,251) */
+typedef struct
+{
+  Oracle *o;
+  JITElementInfo_t ei;
+  JITShapeInfo_t si;
+  int elem;
+  int node_of[MAXN];
+  int eqn_of_local[MAXN * (MAXD + 16)];
+  JITHangInfo_t nohang[MAXN];
+  /* backing storage */
+  double **coord_ptr[MAXN], **data_ptr[MAXN];
+  double *coord_slots[MAXN][2 * MAXD], *data_slots[MAXN][32];
+  int *eqn_ptr[MAXN], *poseqn_ptr[MAXN];
+  int eqn_slots[MAXN][32], poseqn_slots[MAXN][MAXD];
+} ThreadState;
+
+static __thread ThreadState *TS = NULL;
+
+static void *xcalloc(size_t n, size_t s)
+{
+  void *p = calloc(n ? n : 1, s);
+  if (!p) { fprintf(stderr, "oracle: out of memory\n"); abort(); }
+  return p;
+}
+
+static double **alloc2(int a, int b)
+{
+  double **p = (double **)xcalloc(a, sizeof(double *));
+  for (int i = 0; i < a; i++) p[i] = (double *)xcalloc(b, sizeof(double));
+  return p;
+}
+static double ****alloc4(int a, int b, int c, int d)
+{
+  double ****p = (double ****)xcalloc(a, sizeof(double ***));
+  for (int i = 0; i < a; i++)
+  {
+    p[i] = (double ***)xcalloc(b, sizeof(double **));
+    for (int j = 0; j < b; j++) p[i][j] = alloc2(c, d);
+  }
+  return p;
+}
+
+static void check_size(unsigned long long a, unsigned long long b, char *what)
+{
+  if (a != b) { fprintf(stderr, "oracle: compiler size mismatch for %s\n", what); abort(); }
+}
+
+/* ------------------------------------------------------------------ geometry at one Gauss point
+ * restates BulkElementBase::fill_shape_info_at_s for el_dim == nodal_dim in {2,3} (src/elements.cpp:3593) */
+static void fill_shape_info_at_s(ThreadState *ts, const double *s, double weight, unsigned flag,
+                                 const JITFuncSpec_RequiredShapes_FiniteElement_t *req)
+{
+  (void)req; /* everything is filled; the reference skips unrequired spaces, values are identical */
+  Oracle *o = ts->o;
+  const int dim = o->et.dim, nn = o->et.nnode;
+  JITShapeInfo_t *si = &ts->si;
+  double psi[MAXN], dpsids[MAXN * MAXD];
+  oracle_dshape_local(dim, 3, s, psi, dpsids);
+  double t[MAXD][MAXD], TL[MAXD][MAXD]; /* tangents t(a,i) Eulerian and Lagrangian */
+  memset(t, 0, sizeof(t));
+  memset(TL, 0, sizeof(TL));
+  for (int l = 0; l < nn; l++)
+  {
+    for (int i = 0; i < dim; i++)
+      for (int j = 0; j < dim; j++) t[j][i] += ts->ei.nodal_coords[l][i][0] * dpsids[l * dim + j];
+    for (int i = 0; i < dim; i++)
+      for (int j = 0; j < dim; j++) TL[j][i] += ts->ei.nodal_coords[l][dim + i][0] * dpsids[l * dim + j];
+  }
+  double gg[MAXD][MAXD], ggL[MAXD][MAXD], aup[MAXD][MAXD], detE = 0, detL = 0;
+  const int require_dxdshape = (flag && o->ft->moving_nodes && !o->ft->fd_position_jacobian);
+  for (int pass = 0; pass < 2; pass++)
+  {
+    double(*tt)[MAXD] = pass == 0 ? t : TL;
+    double(*g)[MAXD] = pass == 0 ? gg : ggL;
+    double amet[MAXD][MAXD], up[MAXD][MAXD], det_a;
+    for (int al = 0; al < dim; al++)
+      for (int be = 0; be < dim; be++)
+      {
+        amet[al][be] = 0.0;
+        for (int i = 0; i < dim; i++) amet[al][be] += tt[al][i] * tt[be][i];
+      }
+    if (dim == 2)
+    {
+      det_a = amet[0][0] * amet[1][1] - amet[0][1] * amet[1][0];
+      up[0][0] = amet[1][1] / det_a;
+      up[0][1] = -amet[0][1] / det_a;
+      up[1][0] = -amet[1][0] / det_a;
+      up[1][1] = amet[0][0] / det_a;
+      for (int b = 0; b < 2; b++)
+        for (int i = 0; i < dim; i++) g[b][i] = up[0][b] * tt[0][i] + up[1][b] * tt[1][i];
+    }
+    else
+    {
+      det_a = amet[0][0] * amet[1][1] * amet[2][2] + amet[0][1] * amet[1][2] * amet[2][0] + amet[0][2] * amet[1][0] * amet[2][1] - amet[0][0] * amet[1][2] * amet[2][1] - amet[0][1] * amet[1][0] * amet[2][2] - amet[0][2] * amet[1][1] * amet[2][0];
+      up[0][0] = (amet[1][1] * amet[2][2] - amet[1][2] * amet[2][1]) / det_a;
+      up[0][1] = -(amet[0][1] * amet[2][2] - amet[0][2] * amet[2][1]) / det_a;
+      up[0][2] = (amet[0][1] * amet[1][2] - amet[0][2] * amet[1][1]) / det_a;
+      up[1][0] = -(amet[1][0] * amet[2][2] - amet[1][2] * amet[2][0]) / det_a;
+      up[1][1] = (amet[0][0] * amet[2][2] - amet[0][2] * amet[2][0]) / det_a;
+      up[1][2] = -(amet[0][0] * amet[1][2] - amet[0][2] * amet[1][0]) / det_a;
+      up[2][0] = (amet[1][0] * amet[2][1] - amet[1][1] * amet[2][0]) / det_a;
+      up[2][1] = -(amet[0][0] * amet[2][1] - amet[0][1] * amet[2][0]) / det_a;
+      up[2][2] = (amet[0][0] * amet[1][1] - amet[0][1] * amet[1][0]) / det_a;
+      for (int b = 0; b < 3; b++)
+        for (int i = 0; i < dim; i++) g[b][i] = up[0][b] * tt[0][i] + up[1][b] * tt[1][i] + up[2][b] * tt[2][i];
+    }
+    if (pass == 0)
+    {
+      detE = sqrt(det_a);
+      memcpy(aup, up, sizeof(up));
+    }
+    else
+      detL = sqrt(det_a);
+  }
+
+  /* moving-mesh helper (src/elements.cpp:3051-3155): int_pt_weights_d_coords and DXdshape_il_jb */
+  static __thread double DX[MAXD][MAXN][MAXD][MAXD];
+  if (require_dxdshape)
+  {
+    double Tt[MAXN][MAXD][MAXD][MAXD], G[MAXN][MAXD][MAXD][MAXD];
+    for (int l = 0; l < nn; l++)
+      for (int i = 0; i < dim; i++)
+      {
+        double dshape_dx = 0.0;
+        for (int a = 0; a < dim; a++)
+          for (int b = 0; b < dim; b++) dshape_dx += aup[a][b] * dpsids[l * dim + b] * t[a][i];
+        si->int_pt_weights_d_coords[i][l] = dshape_dx * detE * weight;
+      }
+    for (int l = 0; l < nn; l++)
+      for (int c = 0; c < dim; c++)
+        for (int d = 0; d < dim; d++)
+          for (int j = 0; j < dim; j++) Tt[l][c][d][j] = dpsids[l * dim + c] * t[d][j] + dpsids[l * dim + d] * t[c][j];
+    for (int l = 0; l < nn; l++)
+      for (int a = 0; a < dim; a++)
+        for (int b = 0; b < dim; b++)
+          for (int j = 0; j < dim; j++)
+          {
+            double Gval = 0.0;
+            for (int c = 0; c < dim; c++)
+              for (int d = 0; d < dim; d++) Gval -= aup[a][c] * Tt[l][c][d][j] * aup[d][b];
+            G[l][a][b][j] = Gval;
+          }
+    for (int i = 0; i < dim; i++)
+      for (int l = 0; l < nn; l++)
+        for (int j = 0; j < dim; j++)
+          for (int b = 0; b < dim; b++)
+          {
+            double v = 0.0;
+            for (int a = 0; a < dim; a++)
+            {
+              if (i == j) v += aup[a][b] * dpsids[l * dim + a];
+              v += t[a][j] * G[l][a][b][i];
+            }
+            DX[i][l][j][b] = v;
+          }
+  }
+
+  /* spaces: C2 (dominant, aliased by Pos) and C1 on the vertex nodes */
+  for (int space = 0; space < 2; space++)
+  {
+    const int n = space == 0 ? nn : o->et.nnode_C1;
+    double p1[8], d1[8 * MAXD];
+    const double *P = psi, *D = dpsids;
+    if (space == 1)
+    {
+      oracle_dshape_local(dim, 2, s, p1, d1);
+      P = p1;
+      D = d1;
+    }
+    double *shape = space == 0 ? si->shape_C2 : si->shape_C1;
+    double **dx = space == 0 ? si->dx_shape_C2 : si->dx_shape_C1;
+    double **dX = space == 0 ? si->dX_shape_C2 : si->dX_shape_C1;
+    double **dS = space == 0 ? si->dS_shape_C2 : si->dS_shape_C1;
+    double ****dd = space == 0 ? si->d_dx_shape_dcoord_C2 : si->d_dx_shape_dcoord_C1;
+    for (int l = 0; l < n; l++)
+    {
+      shape[l] = P[l];
+      for (int i = 0; i < dim; i++)
+      {
+        dx[l][i] = 0.0;
+        for (int b = 0; b < dim; b++) dx[l][i] += gg[b][i] * D[l * dim + b];
+      }
+      for (int i = 0; i < dim; i++) dS[l][i] = D[l * dim + i];
+      for (int i = 0; i < dim; i++)
+      {
+        dX[l][i] = 0.0;
+        for (int b = 0; b < dim; b++) dX[l][i] += ggL[b][i] * D[l * dim + b];
+      }
+      if (require_dxdshape)
+        for (int i = 0; i < dim; i++)
+          for (int l2 = 0; l2 < nn; l2++)
+            for (int i2 = 0; i2 < dim; i2++)
+            {
+              dd[l][i][l2][i2] = 0.0;
+              for (int b = 0; b < dim; b++) dd[l][i][l2][i2] += DX[i2][l2][i][b] * D[l * dim + b];
+            }
+    }
+  }
+  si->int_pt_weight_unity = weight;
+  si->int_pt_weight = weight * detE;
+  si->int_pt_weight_Lagrangian = weight * detL;
+}
+
+/* callback installed into the function table (src/elements.cpp:60-63 -> :4564) */
+static void cb_fill_shape_buffer_for_point(unsigned ipt, JITFuncSpec_RequiredShapes_FiniteElement_t *req, int flag)
+{
+  ThreadState *ts = TS;
+  double s[MAXD], w;
+  oracle_gauss(ts->o->et.dim, (int)ipt, s, &w);
+  fill_shape_info_at_s(ts, s, w, (unsigned)flag, req);
+}
+
+/* ------------------------------------------------------------------ per-thread state */
+static ThreadState *ts_create(Oracle *o)
+{
+  ThreadState *ts = (ThreadState *)xcalloc(1, sizeof(ThreadState));
+  const int dim = o->et.dim, nn = o->et.nnode;
+  ts->o = o;
+  JITShapeInfo_t *si = &ts->si;
+  si->int_pt_weights_d_coords = alloc2(dim, nn);
+  si->shape_C2 = (double *)xcalloc(nn, sizeof(double));
+  si->dx_shape_C2 = alloc2(nn, dim);
+  si->dX_shape_C2 = alloc2(nn, dim);
+  si->dS_shape_C2 = alloc2(nn, dim);
+  si->d_dx_shape_dcoord_C2 = alloc4(nn, dim, nn, dim);
+  si->shape_C1 = (double *)xcalloc(8, sizeof(double));
+  si->dx_shape_C1 = alloc2(8, dim);
+  si->dX_shape_C1 = alloc2(8, dim);
+  si->dS_shape_C1 = alloc2(8, dim);
+  si->d_dx_shape_dcoord_C1 = alloc4(8, dim, nn, dim);
+  /* set_remaining_shapes_appropriately: Pos aliases C2 (src/elements.cpp:4534-4542) */
+  si->shape_Pos = si->shape_C2;
+  si->dx_shape_Pos = si->dx_shape_C2;
+  si->dX_shape_Pos = si->dX_shape_C2;
+  si->dS_shape_Pos = si->dS_shape_C2;
+  si->d_dx_shape_dcoord_Pos = si->d_dx_shape_dcoord_C2;
+  si->t = (double *)xcalloc(NTW, sizeof(double));
+  si->dt = (double *)xcalloc(NTW, sizeof(double));
+  si->timestepper_weights_dt_BDF1 = (double *)xcalloc(NTW, sizeof(double));
+  si->timestepper_weights_dt_BDF2 = (double *)xcalloc(NTW, sizeof(double));
+  si->timestepper_weights_dt_Newmark2 = (double *)xcalloc(NTW, sizeof(double));
+  si->timestepper_weights_d2t_Newmark2 = (double *)xcalloc(NTW, sizeof(double));
+  si->hanginfo_C1 = ts->nohang;
+  si->hanginfo_C2 = ts->nohang;
+  si->hanginfo_Pos = ts->nohang;
+  for (int l = 0; l < nn; l++)
+  {
+    ts->coord_ptr[l] = ts->coord_slots[l];
+    ts->data_ptr[l] = ts->data_slots[l];
+    ts->eqn_ptr[l] = ts->eqn_slots[l];
+    ts->poseqn_ptr[l] = ts->poseqn_slots[l];
+  }
+  ts->ei.nodal_coords = ts->coord_ptr;
+  ts->ei.nodal_data = ts->data_ptr;
+  ts->ei.nodal_local_eqn = ts->eqn_ptr;
+  ts->ei.pos_local_eqn = ts->poseqn_ptr;
+  ts->ei.nnode = nn;
+  ts->ei.nnode_C2 = nn;
+  ts->ei.nnode_C1 = o->et.nnode_C1;
+  ts->ei.nodal_dim = dim;
+  return ts;
+}
+
+/* fill_element_info (src/elements.cpp:2713): pointer tables + local equation numbers.
+ * Local order: nodal values node by node, then positions node by node (oomph elements.cc:694-699). */
+static void bind_element(ThreadState *ts, int e)
+{
+  Oracle *o = ts->o;
+  const int dim = o->et.dim, nn = o->et.nnode, nC2 = (int)o->ft->numfields_C2, nC1 = (int)o->ft->numfields_C1;
+  const int *en = o->elem_nodes + (size_t)e * nn;
+  ts->elem = e;
+  int nloc = 0;
+  for (int l = 0; l < nn; l++)
+  {
+    const int node = en[l];
+    ts->node_of[l] = node;
+    for (int i = 0; i < dim; i++)
+    {
+      ts->coord_slots[l][i] = o->pos + ((size_t)node * dim + i) * o->n_pos_hist;
+      ts->coord_slots[l][dim + i] = o->lagr + (size_t)node * dim + i;
+    }
+    for (int f = 0; f < nC2; f++) ts->data_slots[l][f] = o->val + ((size_t)node * o->nval + f) * o->T;
+  }
+  for (int l = 0; l < o->et.nnode_C1; l++)
+  {
+    const int node = en[o->et.c1_nodes[l]];
+    for (int f = nC2; f < nC2 + nC1; f++) ts->data_slots[l][f] = o->val + ((size_t)node * o->nval + f) * o->T;
+  }
+  /* local equations of nodal values in element-node order, value order */
+  for (int l = 0; l < nn; l++)
+    for (int f = 0; f < nC2 + nC1; f++) ts->eqn_slots[l][f] = -1;
+  for (int l = 0; l < nn; l++)
+  {
+    const int node = en[l];
+    int c1l = -1;
+    for (int k = 0; k < o->et.nnode_C1; k++)
+      if (o->et.c1_nodes[k] == l) c1l = k;
+    for (int f = 0; f < nC2 + nC1; f++)
+    {
+      const int g = o->node_eqn[(size_t)node * o->nval + f];
+      if (g < 0) continue;
+      if (f < nC2)
+      {
+        ts->eqn_slots[l][f] = nloc;
+        ts->eqn_of_local[nloc++] = g;
+      }
+      else if (c1l >= 0)
+      {
+        ts->eqn_slots[c1l][f] = nloc;
+        ts->eqn_of_local[nloc++] = g;
+      }
+    }
+  }
+  for (int l = 0; l < nn; l++)
+    for (int i = 0; i < dim; i++)
+    {
+      const int g = o->pos_eqn ? o->pos_eqn[(size_t)en[l] * dim + i] : -1;
+      ts->poseqn_slots[l][i] = -1;
+      if (g >= 0)
+      {
+        ts->poseqn_slots[l][i] = nloc;
+        ts->eqn_of_local[nloc++] = g;
+      }
+    }
+  ts->ei.ndof = nloc;
+}
+
+/* prepare_shape_buffer_for_integration (src/elements.cpp:4577-4646) */
+static void prepare_shape_buffer(ThreadState *ts)
+{
+  Oracle *o = ts->o;
+  JITShapeInfo_t *si = &ts->si;
+  si->n_int_pt = o->et.n_int;
+  if (o->steady)
+  {
+    si->timestepper_ntstorage = 0;
+    for (int i = 0; i < NTW; i++)
+    {
+      si->timestepper_weights_dt_BDF1[i] = 0;
+      si->timestepper_weights_dt_BDF2[i] = 0;
+      si->timestepper_weights_dt_Newmark2[i] = 0;
+      si->timestepper_weights_d2t_Newmark2[i] = 0;
+    }
+    si->timestepper_weights_dt_BDF2_degr = si->timestepper_weights_dt_BDF2;
+    si->timestepper_weights_dt_Newmark2_degr = si->timestepper_weights_dt_Newmark2;
+  }
+  else
+  {
+    si->timestepper_ntstorage = o->ntstorage;
+    for (int i = 0; i < NTW; i++)
+    {
+      si->timestepper_weights_dt_BDF1[i] = o->wBDF1[i];
+      si->timestepper_weights_dt_BDF2[i] = o->wBDF2[i];
+      si->timestepper_weights_dt_Newmark2[i] = o->wNM2[i];
+      si->timestepper_weights_d2t_Newmark2[i] = o->wNM2_d2t[i];
+    }
+    if (o->unsteady_steps_done == 0)
+    {
+      si->timestepper_weights_dt_BDF2_degr = si->timestepper_weights_dt_BDF1;
+      si->timestepper_weights_dt_Newmark2_degr = si->timestepper_weights_dt_BDF1;
+    }
+    else if (o->unsteady_steps_done <= 4)
+    {
+      si->timestepper_weights_dt_BDF2_degr = si->timestepper_weights_dt_BDF2;
+      si->timestepper_weights_dt_Newmark2_degr = si->timestepper_weights_dt_BDF2;
+    }
+    else
+    {
+      si->timestepper_weights_dt_BDF2_degr = si->timestepper_weights_dt_BDF2;
+      si->timestepper_weights_dt_Newmark2_degr = si->timestepper_weights_dt_Newmark2;
+    }
+  }
+  for (int i = 0; i < NTW; i++)
+  {
+    si->t[i] = o->t[i];
+    si->dt[i] = o->dt[i];
+  }
+}
+
+/* fill_in_generic_residual_contribution_jit (src/elements.cpp:5054-5127): R,J,M are caller-zeroed [ndof],[ndof^2] */
+static void element_rjm_bound(ThreadState *ts, int which, int param, unsigned flag, double *R, double *J, double *M)
+{
+  Oracle *o = ts->o;
+  TS = ts;
+  prepare_shape_buffer(ts);
+  ts->si.jacobian_size = ts->ei.ndof;
+  ts->si.mass_matrix_size = ts->ei.ndof;
+  JITFuncSpec_ResidualAndJacobian_FiniteElement func;
+  if (param >= 0)
+    func = o->ft->ParameterDerivative[which][param];
+  else if (o->steady && o->ft->ResidualAndJacobianSteady && o->ft->ResidualAndJacobianSteady[which])
+    func = o->ft->ResidualAndJacobianSteady[which];
+  else
+    func = o->ft->ResidualAndJacobian[which];
+  func(&ts->ei, &ts->si, R, J, M, flag);
+}
+
+static void element_rjm(ThreadState *ts, int e, int which, int param, unsigned flag, double *R, double *J, double *M)
+{
+  bind_element(ts, e);
+  element_rjm_bound(ts, which, param, flag, R, J, M);
+}
+
+/* ------------------------------------------------------------------ public C entry points (ctypes) */
+void *oracle_create(int dim, int n_elem, const int *elem_nodes, int n_node, int nval, int T, int n_pos_hist,
+                    const double *node_pos, const double *node_lagr, const double *node_val, const int *node_eqn,
+                    const int *pos_eqn, int n_dof)
+{
+  init_tables();
+  Oracle *o = (Oracle *)xcalloc(1, sizeof(Oracle));
+  static const int c1q[4] = {0, 2, 6, 8}, c1b[8] = {0, 2, 6, 8, 18, 20, 24, 26};
+  o->et.dim = dim;
+  o->et.nnode = dim == 2 ? 9 : 27;
+  o->et.nnode_C1 = dim == 2 ? 4 : 8;
+  o->et.n_int = dim == 2 ? 9 : 27;
+  memcpy(o->et.c1_nodes, dim == 2 ? c1q : c1b, sizeof(int) * o->et.nnode_C1);
+  o->n_elem = n_elem;
+  o->n_node = n_node;
+  o->nval = nval;
+  o->T = T;
+  o->n_pos_hist = n_pos_hist;
+  o->n_dof = n_dof;
+  o->elem_nodes = elem_nodes;
+  o->node_eqn = node_eqn;
+  o->pos_eqn = pos_eqn;
+  /* transpose [t][node][k] -> [node][k][t] (oomph Data keeps a value's history contiguous) */
+  o->pos = (double *)xcalloc((size_t)n_node * dim * n_pos_hist, sizeof(double));
+  for (int t = 0; t < n_pos_hist; t++)
+    for (size_t n = 0; n < (size_t)n_node; n++)
+      for (int i = 0; i < dim; i++) o->pos[(n * dim + i) * n_pos_hist + t] = node_pos[((size_t)t * n_node + n) * dim + i];
+  o->lagr = (double *)xcalloc((size_t)n_node * dim, sizeof(double));
+  memcpy(o->lagr, node_lagr, sizeof(double) * (size_t)n_node * dim);
+  o->val = (double *)xcalloc((size_t)n_node * nval * T, sizeof(double));
+  for (int t = 0; t < T; t++)
+    for (size_t n = 0; n < (size_t)n_node; n++)
+      for (int f = 0; f < nval; f++) o->val[(n * nval + f) * T + t] = node_val[((size_t)t * n_node + n) * nval + f];
+  o->ft = (JITFuncSpec_Table_FiniteElement_t *)xcalloc(1, sizeof(JITFuncSpec_Table_FiniteElement_t));
+  o->ft->check_compiler_size = check_size;
+  JIT_ELEMENT_init(o->ft);
+  o->ft->fill_shape_buffer_for_point = cb_fill_shape_buffer_for_point;
+  o->params = (double *)xcalloc(o->ft->numglobal_params + 1, sizeof(double));
+  for (unsigned k = 0; k < o->ft->numglobal_params; k++) o->ft->global_parameters[k] = &o->params[k];
+  o->steady = 1;
+  if ((int)o->ft->nodal_dim != dim) { fprintf(stderr, "oracle: plugin dimension mismatch\n"); abort(); }
+  return o;
+}
+
+int oracle_num_params(void *h) { return (int)((Oracle *)h)->ft->numglobal_params; }
+int oracle_num_residuals(void *h) { return (int)((Oracle *)h)->ft->num_res_jacs; }
+int oracle_moving_nodes(void *h) { return (int)((Oracle *)h)->ft->moving_nodes; }
+
+void oracle_set_params(void *h, const double *p, int n)
+{
+  Oracle *o = (Oracle *)h;
+  for (int k = 0; k < n && k < (int)o->ft->numglobal_params; k++) o->params[k] = p[k];
+}
+
+void oracle_set_time(void *h, int steady, int unsteady_steps_done, int ntstorage, const double *t, const double *dt,
+                     const double *wBDF1, const double *wBDF2, const double *wNM2, const double *wNM2_d2t)
+{
+  Oracle *o = (Oracle *)h;
+  o->steady = steady;
+  o->unsteady_steps_done = unsteady_steps_done;
+  o->ntstorage = ntstorage;
+  for (int i = 0; i < NTW; i++)
+  {
+    o->t[i] = t[i];
+    o->dt[i] = dt[i];
+    o->wBDF1[i] = wBDF1[i];
+    o->wBDF2[i] = wBDF2[i];
+    o->wNM2[i] = wNM2[i];
+    o->wNM2_d2t[i] = wNM2_d2t[i];
+  }
+}
+
+/* MultiTimeStepper::set_weights (src/timestepper.cpp:31-72), BDF part */
+void oracle_bdf_weights(double dt, double dtprev, double *wBDF1, double *wBDF2)
+{
+  for (int i = 0; i < NTW; i++) wBDF1[i] = wBDF2[i] = 0.0;
+  wBDF2[0] = 1.0 / dt + 1.0 / (dt + dtprev);
+  wBDF2[1] = -(dt + dtprev) / (dt * dtprev);
+  wBDF2[2] = dt / ((dt + dtprev) * dtprev);
+  wBDF1[0] = 1.0 / dt;
+  wBDF1[1] = -1.0 / dt;
+}
+
+/* update nodal values/positions at history level t from [node][k] arrays */
+void oracle_update_values(void *h, int t, const double *node_val, const double *node_pos)
+{
+  Oracle *o = (Oracle *)h;
+  if (node_val)
+    for (size_t n = 0; n < (size_t)o->n_node; n++)
+      for (int f = 0; f < o->nval; f++) o->val[(n * o->nval + f) * o->T + t] = node_val[n * o->nval + f];
+  if (node_pos)
+    for (size_t n = 0; n < (size_t)o->n_node; n++)
+      for (int i = 0; i < o->et.dim; i++) o->pos[(n * o->et.dim + i) * o->n_pos_hist + t] = node_pos[n * o->et.dim + i];
+}
+
+/* one element: dense R[ndof], J[ndof^2], M[ndof^2] in the oracle's (= oomph's) local order + global eqn map */
+int oracle_element(void *h, int e, int which, int param, unsigned flag, double *R, double *J, double *M, int *eqns)
+{
+  Oracle *o = (Oracle *)h;
+  ThreadState *ts = ts_create(o);
+  element_rjm(ts, e, which, param, flag, R, J, M);
+  const int n = (int)ts->ei.ndof;
+  for (int i = 0; i < n; i++) eqns[i] = ts->eqn_of_local[i];
+  free(ts); /* small leak of the shape tables: test-only entry point */
+  return n;
+}
+
+/* shape buffer of one Gauss point of one element, for the geometry tests */
+void oracle_point_shapes(void *h, int e, int ipt, unsigned flag, double *weights /*3*/, double *shape, double *dx_shape,
+                         double *dX_shape, double *w_dcoords, double *d_dx_dcoord)
+{
+  Oracle *o = (Oracle *)h;
+  ThreadState *ts = ts_create(o);
+  const int dim = o->et.dim, nn = o->et.nnode;
+  TS = ts;
+  bind_element(ts, e);
+  prepare_shape_buffer(ts);
+  cb_fill_shape_buffer_for_point((unsigned)ipt, NULL, (int)flag);
+  weights[0] = ts->si.int_pt_weight;
+  weights[1] = ts->si.int_pt_weight_Lagrangian;
+  weights[2] = ts->si.int_pt_weight_unity;
+  for (int l = 0; l < nn; l++)
+  {
+    shape[l] = ts->si.shape_C2[l];
+    for (int i = 0; i < dim; i++)
+    {
+      dx_shape[l * dim + i] = ts->si.dx_shape_C2[l][i];
+      dX_shape[l * dim + i] = ts->si.dX_shape_C2[l][i];
+      if (w_dcoords) w_dcoords[i * nn + l] = ts->si.int_pt_weights_d_coords[i][l];
+      if (d_dx_dcoord)
+        for (int l2 = 0; l2 < nn; l2++)
+          for (int i2 = 0; i2 < dim; i2++) d_dx_dcoord[((l * dim + i) * nn + l2) * dim + i2] = ts->si.d_dx_shape_dcoord_C2[l][i][l2][i2];
+    }
+  }
+  free(ts);
+}
+
+static void row_add(Row *r, int col, double v)
+{
+  for (int k = 0; k < r->n; k++)
+    if (r->p[k].col == col)
+    {
+      r->p[k].val += v;
+      return;
+    }
+  if (r->n == r->cap)
+  {
+    r->cap = r->cap ? 2 * r->cap : 32;
+    r->p = (Pair *)realloc(r->p, sizeof(Pair) * r->cap);
+  }
+  r->p[r->n].col = col;
+  r->p[r->n].val = v;
+  r->n++;
+}
+
+/* sparse_assemble_row_or_column_compressed_with_vectors_of_pairs (problem.cc:5332-5666).  flag: 0 residual only,
+ * 1 +Jacobian, 2 +mass matrix.  nthreads>1 splits the element range statically like First_el_for_assembly
+ * (problem.cc:5354) with one private matrix per range, merged in range order afterwards. */
+double oracle_assemble(void *h, int which, int param, unsigned flag, double *residuals, int nthreads)
+{
+  Oracle *o = (Oracle *)h;
+  const int nmat = flag == 0 ? 0 : (flag == 1 ? 1 : 2);
+  if (nthreads < 1) nthreads = 1;
+  for (int m = 0; m < 2; m++)
+  {
+    free(o->row_start[m]); free(o->col_index[m]); free(o->value[m]);
+    o->row_start[m] = o->col_index[m] = NULL; o->value[m] = NULL; o->nnz[m] = 0;
+  }
+  Row **rows = (Row **)xcalloc((size_t)nthreads * 2, sizeof(Row *));
+  double **res_t = (double **)xcalloc(nthreads, sizeof(double *));
+  for (int th = 0; th < nthreads; th++)
+  {
+    for (int m = 0; m < nmat; m++) rows[th * 2 + m] = (Row *)xcalloc(o->n_dof, sizeof(Row));
+    res_t[th] = th == 0 ? residuals : (double *)xcalloc(o->n_dof, sizeof(double));
+  }
+  memset(residuals, 0, sizeof(double) * o->n_dof);
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads)
+#endif
+  {
+#ifdef _OPENMP
+    const int th = omp_get_thread_num();
+#else
+    const int th = 0;
+#endif
+    ThreadState *ts = ts_create(o);
+    const int maxdof = o->et.nnode * (o->et.dim + o->nval);
+    double *R = (double *)xcalloc(maxdof, sizeof(double));
+    double *J = (double *)xcalloc((size_t)maxdof * maxdof, sizeof(double));
+    double *M = (double *)xcalloc((size_t)maxdof * maxdof, sizeof(double));
+    const int lo = (int)((int64_t)o->n_elem * th / nthreads), hi = (int)((int64_t)o->n_elem * (th + 1) / nthreads);
+    for (int e = lo; e < hi; e++)
+    {
+      bind_element(ts, e);
+      const int n = (int)ts->ei.ndof;
+      memset(R, 0, sizeof(double) * n);
+      if (nmat > 0) memset(J, 0, sizeof(double) * n * n);
+      if (nmat > 1) memset(M, 0, sizeof(double) * n * n);
+      element_rjm_bound(ts, which, param, flag, R, nmat > 0 ? J : NULL, nmat > 1 ? M : NULL);
+      for (int i = 0; i < n; i++)
+      {
+        const int eqn = ts->eqn_of_local[i];
+        res_t[th][eqn] += R[i];
+        for (int j = 0; j < n; j++)
+        {
+          const int unknown = ts->eqn_of_local[j];
+          for (int m = 0; m < nmat; m++)
+          {
+            const double value = (m == 0 ? J : M)[i * n + j];
+            if (fabs(value) > 0.0) row_add(&rows[th * 2 + m][eqn], unknown, value);
+          }
+        }
+      }
+    }
+    free(R); free(J); free(M); free(ts);
+  }
+  /* merge per-range results in range order (single range: no-op) */
+  for (int th = 1; th < nthreads; th++)
+  {
+    for (int i = 0; i < o->n_dof; i++) residuals[i] += res_t[th][i];
+    for (int m = 0; m < nmat; m++)
+      for (int i = 0; i < o->n_dof; i++)
+      {
+        Row *r = &rows[th * 2 + m][i];
+        for (int k = 0; k < r->n; k++) row_add(&rows[m][i], r->p[k].col, r->p[k].val);
+        free(r->p);
+      }
+    free(res_t[th]);
+    for (int m = 0; m < nmat; m++) free(rows[th * 2 + m]);
+  }
+  for (int m = 0; m < nmat; m++)
+  {
+    Row *rw = rows[m];
+    o->row_start[m] = (int *)xcalloc(o->n_dof + 1, sizeof(int));
+    for (int i = 0; i < o->n_dof; i++) o->row_start[m][i + 1] = o->row_start[m][i] + rw[i].n;
+    const int entries = o->row_start[m][o->n_dof];
+    o->nnz[m] = entries;
+    o->col_index[m] = (int *)xcalloc(entries, sizeof(int));
+    o->value[m] = (double *)xcalloc(entries, sizeof(double));
+    for (int i = 0; i < o->n_dof; i++)
+    {
+      int p = 0;
+      for (int j = o->row_start[m][i]; j < o->row_start[m][i + 1]; j++, p++)
+      {
+        o->col_index[m][j] = rw[i].p[p].col;
+        o->value[m][j] = rw[i].p[p].val;
+      }
+      free(rw[i].p);
+    }
+    free(rw);
+  }
+  free(rows);
+  free(res_t);
+  return (double)o->nnz[0];
+}
+
+int64_t oracle_nnz(void *h, int m) { return ((Oracle *)h)->nnz[m]; }
+void oracle_get_csr(void *h, int m, int *row_start, int *col_index, double *value)
+{
+  Oracle *o = (Oracle *)h;
+  memcpy(row_start, o->row_start[m], sizeof(int) * (o->n_dof + 1));
+  memcpy(col_index, o->col_index[m], sizeof(int) * o->nnz[m]);
+  memcpy(value, o->value[m], sizeof(double) * o->nnz[m]);
+}
+
+void oracle_free(void *h)
+{
+  Oracle *o = (Oracle *)h;
+  for (int m = 0; m < 2; m++) { free(o->row_start[m]); free(o->col_index[m]); free(o->value[m]); }
+  if (o->ft->clean_up) o->ft->clean_up(o->ft);
+  free(o->ft); free(o->pos); free(o->lagr); free(o->val); free(o->params);
+  free(o);
+}

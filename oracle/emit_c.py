@@ -1,0 +1,378 @@
+"""ORACLE -- TEST INFRASTRUCTURE ONLY (never imported by the product package).
+
+C emitter restating the *output format* of pyoomph's code generator for the assembly routines:
+  FiniteElementCode::write_code            /root/reference/src/codegen.cpp:4684-4811 (file skeleton)
+  write_generic_RJM                        src/codegen.cpp:3912-4109       (loop nest)
+  write_nodal_time_interpolation           src/codegen.cpp:1202-1292
+  write_spatial_interpolation (+COORDDIFF) src/codegen.cpp:1294-1448
+  write_generic_RJM_contribution           src/codegen.cpp:2015-2236
+  write_generic_RJM_jacobian_contribution  src/codegen.cpp:1883-2013
+  write_code_info (JIT_ELEMENT_init)       src/codegen.cpp:6398-7090
+
+The symbolic residual comes from the shared front end (pyoomph_b200.codegen.FiniteElementCode, the stand-in
+for pyoomph's GiNaC trees).  The Jacobian is derived HERE, independently of the product's coefficient-form
+derivation: like the reference it is the derivative of the complete residual expression with respect to the
+nodal value U^{l_shape} of one field (a Gateaux derivative through every shape expansion, the test-function
+gradients and the integration weight), printed as one expression per (test field, unknown field) and evaluated
+for every (l_test, l_shape) pair.  Moving-mesh terms use the reference's tensors
+(``d_dx_shape_dcoord_*``, ``int_pt_weights_d_coords``, COORDDIFF arrays), not the product's closed-form identity.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Dict, List, Optional, Tuple
+
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+
+from pyoomph_b200 import expressions as ex
+from pyoomph_b200.codegen import AtomInfo, FiniteElementCode, TestSlot
+
+EPS = sp.Symbol("ORACLE__eps", real=True)
+MM = sp.Symbol("ORACLE__partial_t_mass_matrix", real=True)
+
+
+class _CPrinter(C99CodePrinter):
+    def __init__(self, names: Dict[sp.Symbol, str]):
+        super().__init__({"precision": 17})
+        self.names = names
+
+    def _print_Symbol(self, expr):
+        if expr in self.names:
+            return self.names[expr]
+        return super()._print_Symbol(expr)
+
+    def _print_Float(self, expr):
+        return repr(float(expr))
+
+    def _print_Rational(self, expr):
+        return "(%d.0/%d.0)" % (expr.p, expr.q)
+
+    def _print_Integer(self, expr):
+        return "%d.0" % int(expr) if abs(int(expr)) < 2 ** 53 else super()._print_Integer(expr)
+
+    def _print_Pow(self, expr):
+        # integer exponents stay integers (the base rule above would print them as doubles)
+        if expr.exp.is_Integer:
+            e = int(expr.exp)
+            b = self.parenthesize(expr.base, sp.printing.precedence.PRECEDENCE["Pow"])
+            if e == -1:
+                return "1.0/%s" % b
+            return "pow(%s,%d.0)" % (self._print(expr.base), e)
+        return super()._print_Pow(expr)
+
+
+def _space_shape_name(code: FiniteElementCode, fieldname: str) -> str:
+    return {"C2": "C2", "C1": "C1", "Pos": "Pos"}[code.fields[fieldname].space]
+
+
+def _nodal_index_name(fieldname: str) -> str:
+    return "this_nodalind_" + fieldname
+
+
+class CEmitter:
+    def __init__(self, code: FiniteElementCode):
+        self.code = code
+        self.dim = code.nodal_dim
+
+    # ---- naming helpers ---------------------------------------------------------
+    def _data_array(self, field: str) -> str:
+        return "nodal_coords" if self.code.fields[field].space == "Pos" else "nodal_data"
+
+    def _eqn_str(self, field: str, l: str) -> str:
+        arr = "pos_local_eqn" if self.code.fields[field].space == "Pos" else "nodal_local_eqn"
+        return "eleminfo->%s[%s][%s]" % (arr, l, _nodal_index_name(field))
+
+    def _nnode_str(self, field: str) -> str:
+        s = self.code.fields[field].space
+        return "eleminfo->nnode" if s == "Pos" else "eleminfo->nnode_" + s
+
+    def _shape_str(self, field: str, deriv: str, l: str) -> str:
+        S = _space_shape_name(self.code, field)
+        if deriv == "d0":
+            return "shapeinfo->shape_%s[%s]" % (S, l)
+        return "shapeinfo->d%s_shape_%s[%s][%s]" % (deriv[1], S, l, deriv[2:])
+
+    def _dt_values_name(self, a: AtomInfo) -> str:
+        return "this_d%dt%d%s_%s" % (a.dt_order, a.past, a.scheme.replace("_degr", ""), a.field)
+
+    def _weights_name(self, a: AtomInfo) -> str:
+        return "shapeinfo->timestepper_weights_%s_%s" % ("dt" if a.dt_order == 1 else "d2t", a.scheme)
+
+    def _coorddiff_name(self, a: AtomInfo, j: int) -> str:
+        dts = "d%dt%d%s" % (a.dt_order, a.past, a.scheme.replace("_degr", "") if a.dt_order else "")
+        return "this_intrp_%s_d1x%s_COORDDIFF_%d_%s" % (dts, a.deriv[2:], j, a.field)
+
+    # ---- one routine ---------------------------------------------------------------------------
+    def routine(self, funcname: str, resname: str, res_index: int, parameter: Optional[str]) -> str:
+        code = self.code
+        E = code.atomize(code.residuals[resname])
+        if parameter is not None:
+            E = sp.diff(E, code._param_syms[parameter])
+        atoms = sorted([code._atom_syms[s] for s in E.free_symbols if s in code._atom_syms],
+                       key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
+        moving = code.coordinates_as_dofs
+        if moving:
+            # Eulerian-gradient atoms need all directions for nothing extra here (tensors do the work)
+            pass
+        tests = sorted([code._test_syms[s] for s in E.free_symbols if s in code._test_syms], key=lambda t: (t.field, t.deriv))
+        test_fields = []
+        for t in tests:
+            if t.field not in test_fields:
+                test_fields.append(t.field)
+        names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi"}
+        for a in atoms:
+            names[code.atom_symbol(a)] = "this_" + a.cname
+        for k, p in enumerate(code.global_params):
+            names[code._param_syms[p]] = "(*(my_func_table->global_parameters[%d]))" % k
+        for s in code._test_syms:
+            sl = code._test_syms[s]
+            names[s] = "testfunction[l_test]" if sl.deriv == "d0" else "d%s_testfunction[l_test][%s]" % (sl.deriv[1], sl.deriv[2:])
+        pr = _CPrinter(names)
+
+        o: List[str] = []
+        w = o.append
+        w("static void %s(const JITElementInfo_t * eleminfo, const JITShapeInfo_t * shapeinfo,double * residuals, double *jacobian, double *mass_matrix,unsigned flag)" % funcname)
+        w("{")
+        w("  int local_eqn, local_unknown;")
+        w("  unsigned nummaster,nummaster2;")
+        w("  double hang_weight,hang_weight2;")
+        w("  const double * t=shapeinfo->t;")
+        w("  const double * dt=shapeinfo->dt;")
+        w("  (void)t; (void)dt; (void)local_unknown; (void)nummaster2; (void)hang_weight2;")
+        idx_fields = sorted({a.field for a in atoms} | set(test_fields) |
+                            ({"coordinate_" + d for d in ex.DIRS[:self.dim]} if moving else set()))
+        for f in idx_fields:
+            w("  const unsigned %s = %d;" % (_nodal_index_name(f), code.fields[f].index))
+        w("  //START: Precalculate time derivatives of the necessary data")
+        dt_atoms: Dict[str, AtomInfo] = {}
+        for a in atoms:
+            if a.dt_order:
+                dt_atoms.setdefault(self._dt_values_name(a), a)
+        by_space: Dict[str, List[Tuple[str, AtomInfo]]] = {}
+        for nm, a in dt_atoms.items():
+            by_space.setdefault(code.fields[a.field].space, []).append((nm, a))
+        for space, lst in by_space.items():
+            rng = self._nnode_str(lst[0][1].field)
+            for nm, a in lst:
+                w("  double %s[%d];" % (nm, code.etype.nnode))
+            w("  for (unsigned int l_shape=0;l_shape<%s;l_shape++)" % rng)
+            w("  {")
+            for nm, a in lst:
+                w("    %s[l_shape]=0.0;" % nm)
+            w("    for (unsigned tindex=0;tindex<shapeinfo->timestepper_ntstorage;tindex++)")
+            w("    {")
+            for nm, a in lst:
+                w("      %s[l_shape] += %s[tindex]*eleminfo->%s[l_shape][%s][tindex];" % (
+                    nm, self._weights_name(a), self._data_array(a.field), _nodal_index_name(a.field)))
+            w("    }")
+            w("  }")
+        w("  //END: Precalculate time derivatives of the necessary data")
+        w("")
+        w("  //START: Spatial integration loop")
+        w("  for(unsigned ipt=0;ipt<shapeinfo->n_int_pt;ipt++)")
+        w("  {")
+        w("    my_func_table->fill_shape_buffer_for_point(ipt, &(my_func_table->shapes_required_ResJac[%d]), flag);" % res_index)
+        w("    const double dx = shapeinfo->int_pt_weight;")
+        w("    const double dX = shapeinfo->int_pt_weight_Lagrangian;")
+        w("    (void)dx; (void)dX;")
+        w("    //START: Interpolate all required fields")
+        for space in ("Pos", "C2", "C1"):
+            sat = [a for a in atoms if code.fields[a.field].space == space]
+            if not sat:
+                continue
+            rng = self._nnode_str(sat[0].field)
+            for a in sat:
+                w("    double this_%s=0.0;" % a.cname)
+            w("    for (unsigned int l_shape=0;l_shape<%s;l_shape++)" % rng)
+            w("    {")
+            for a in sat:
+                if a.dt_order:
+                    nd = "%s[l_shape]" % self._dt_values_name(a)
+                else:
+                    nd = "eleminfo->%s[l_shape][%s][%d]" % (self._data_array(a.field), _nodal_index_name(a.field), a.past)
+                w("      this_%s+= %s * %s;" % (a.cname, nd, self._shape_str(a.field, a.deriv, "l_shape")))
+            w("    }")
+            cd = [a for a in sat if moving and a.deriv.startswith("dx") and space != "Pos" and not a.past]
+            if cd:
+                for a in cd:
+                    for j in range(self.dim):
+                        w("    double %s[%d];" % (self._coorddiff_name(a, j), code.etype.nnode))
+                w("    if (flag)")
+                w("    {")
+                w("     for (unsigned int m=0;m<eleminfo->nnode;m++)")
+                w("     {")
+                for a in cd:
+                    for j in range(self.dim):
+                        w("        %s[m]=0.0;" % self._coorddiff_name(a, j))
+                w("        for (unsigned int l_shape=0;l_shape<%s;l_shape++)" % rng)
+                w("        {")
+                for a in cd:
+                    nd = ("%s[l_shape]" % self._dt_values_name(a)) if a.dt_order else \
+                        "eleminfo->nodal_data[l_shape][%s][0]" % _nodal_index_name(a.field)
+                    S = _space_shape_name(code, a.field)
+                    for j in range(self.dim):
+                        w("           %s[m]+=%s * shapeinfo->d_dx_shape_dcoord_%s[l_shape][%s][m][%d];" % (
+                            self._coorddiff_name(a, j), nd, S, a.deriv[2:], j))
+                w("        }")
+                w("     }")
+                w("    }")
+        w("    //END: Interpolate all required fields")
+        w("")
+        w("    //START: Contribution of the spaces")
+        w("    double _res_contrib,_J_contrib;")
+        for space in ("Pos", "C2", "C1"):
+            tf = [f for f in test_fields if code.fields[f].space == space]
+            if not tf:
+                continue
+            S = {"Pos": "Pos"}.get(space, space)
+            nn = "eleminfo->nnode" if space == "Pos" else "eleminfo->nnode_" + space
+            w("    {")
+            w("      double const * testfunction = shapeinfo->shape_%s;" % S)
+            w("      DX_SHAPE_FUNCTION_DECL(dx_testfunction) = shapeinfo->dx_shape_%s;" % S)
+            w("      DX_SHAPE_FUNCTION_DECL(dX_testfunction) = shapeinfo->dX_shape_%s;" % S)
+            w("      (void)testfunction; (void)dx_testfunction; (void)dX_testfunction;")
+            w("      for (unsigned int l_test=0;l_test<%s;l_test++)" % nn)
+            w("      {")
+            for F in tf:
+                other = {s: 0 for s, sl in code._test_syms.items() if sl.field != F}
+                var_part = E.xreplace(other)
+                if var_part == 0:
+                    continue
+                hang = "shapeinfo->hanginfo_%s" % S
+                w("        BEGIN_RESIDUAL_CONTINUOUS_SPACE(%s,%s, %s,%s,l_test)" % (
+                    self._eqn_str(F, "l_test"), pr.doprint(var_part), hang, _nodal_index_name(F)))
+                w("          ADD_TO_RESIDUAL_CONTINUOUS_SPACE()")
+                w("          BEGIN_JACOBIAN()")
+                for G in code.unknown_field_names():
+                    diffpart = self._gateaux(var_part, F, G, names)
+                    if diffpart == 0:
+                        continue
+                    mass_part = sp.diff(diffpart, MM)
+                    diffpart = diffpart.xreplace({MM: 0})
+                    Gs = _space_shape_name(code, G)
+                    w("            for (unsigned int l_shape=0;l_shape<%s;l_shape++)" % self._nnode_str(G))
+                    w("            {")
+                    w("              BEGIN_JACOBIAN_HANG(%s, %s,shapeinfo->hanginfo_%s,%s,l_shape)" % (
+                        self._eqn_str(G, "l_shape"), pr.doprint(diffpart), Gs, _nodal_index_name(G)))
+                    w("                ADD_TO_JACOBIAN_HANG_HANG()")
+                    if mass_part != 0:
+                        w("                ADD_TO_MASS_MATRIX_HANG_HANG(%s)" % pr.doprint(mass_part))
+                    w("              END_JACOBIAN_HANG()")
+                    w("            }")
+                w("          END_JACOBIAN()")
+                w("        END_RESIDUAL_CONTINUOUS_SPACE()")
+            w("      }")
+            w("    }")
+        w("    //END: Contribution of the spaces")
+        w("  }")
+        w("  //END: Spatial integration loop")
+        w("}")
+        w("")
+        return "\n".join(o)
+
+    def _gateaux(self, var_part: sp.Expr, F: str, G: str, names: Dict[sp.Symbol, str]) -> sp.Expr:
+        """d/d U_G^{l_shape} of the complete residual expression of test field F."""
+        code = self.code
+        var: Dict[sp.Symbol, sp.Expr] = {}
+
+        def csym(text: str) -> sp.Symbol:
+            s = sp.Symbol("C__" + text, real=True)
+            names[s] = text
+            return s
+
+        for s in list(var_part.free_symbols):
+            if s in code._atom_syms:
+                a = code._atom_syms[s]
+                if a.past:
+                    continue
+                if a.field == G:
+                    shp = csym(self._shape_str(G, a.deriv, "l_shape"))
+                    if a.dt_order == 0:
+                        var[s] = shp
+                    else:
+                        var[s] = (csym(self._weights_name(a) + "[0]") + (MM if a.dt_order == 1 else 0)) * shp
+                elif G.startswith("coordinate_") and a.deriv.startswith("dx") and code.fields[a.field].space != "Pos":
+                    j = ex.DIRS.index(G[-1])
+                    var[s] = csym(self._coorddiff_name(a, j) + "[l_shape]")
+        if G.startswith("coordinate_") and code.coordinates_as_dofs:
+            j = ex.DIRS.index(G[-1])
+            if var_part.has(ex.DX_EUL):
+                var[ex.DX_EUL] = csym("shapeinfo->int_pt_weights_d_coords[%d][l_shape]" % j)
+            for s, sl in code._test_syms.items():
+                if sl.field == F and sl.deriv.startswith("dx") and var_part.has(s):
+                    S = _space_shape_name(code, F)
+                    var[s] = csym("shapeinfo->d_dx_shape_dcoord_%s[l_test][%s][l_shape][%d]" % (S, sl.deriv[2:], j))
+        if not var:
+            return sp.Integer(0)
+        perturbed = var_part.xreplace({s: s + EPS * v for s, v in var.items()})
+        return sp.diff(perturbed, EPS).xreplace({EPS: 0})
+
+    # ---- whole plugin file -------------------------------------------------------------------
+    def emit(self) -> str:
+        code = self.code
+        o: List[str] = []
+        w = o.append
+        w("/* generated by oracle/emit_c.py in the format of pyoomph's FiniteElementCode::write_code -- TEST INFRASTRUCTURE */")
+        w("#define JIT_ELEMENT_SHARED_LIB")
+        w('#include "oracle_jit.h"')
+        w("static JITFuncSpec_Table_FiniteElement_t * my_func_table;")
+        w('#include "oracle_jit_hang.h"')
+        w("")
+        resnames = code.residual_names()
+        for i, rn in enumerate(resnames):
+            w(self.routine("ResidualAndJacobian%d" % i, rn, i, None))
+            for p in code.global_params:
+                w(self.routine("dResidual%ddParameter_%s" % (i, p), rn, i, p))
+        nC2 = len([f for f in code.nodal_fields() if f.space == "C2"])
+        nC1 = len([f for f in code.nodal_fields() if f.space == "C1"])
+        w("static void clean_up(JITFuncSpec_Table_FiniteElement_t *functable)")
+        w("{")
+        w(" free(functable->ResidualAndJacobian); free(functable->ResidualAndJacobianSteady); free(functable->shapes_required_ResJac);")
+        w(" free(functable->global_parameters);")
+        w(" for (unsigned i=0;i<functable->num_res_jacs;i++) { free(functable->ParameterDerivative[i]); free(functable->res_jac_names[i]); }")
+        w(" free(functable->ParameterDerivative); free(functable->res_jac_names); free(functable->dominant_space);")
+        w("}")
+        w("")
+        w("JIT_API void JIT_ELEMENT_init(JITFuncSpec_Table_FiniteElement_t *functable)")
+        w("{")
+        w(' functable->check_compiler_size(sizeof(double),8, "double");')
+        w(" functable->nodal_dim=%d;" % self.dim)
+        w(" functable->lagr_dim=%d;" % self.dim)
+        w(" functable->fd_jacobian=false; ")
+        w(" functable->fd_position_jacobian=false; ")
+        w(" functable->with_adaptivity=true; ")
+        w(" functable->numfields_C2=%d;" % nC2)
+        w(" functable->numfields_C1=%d;" % nC1)
+        w(" functable->numfields_Pos=%d;" % (2 * self.dim))
+        w(" functable->num_res_jacs=%d;" % len(resnames))
+        w(" functable->current_res_jac=0;")
+        w(" functable->res_jac_names=(char **)calloc(%d,sizeof(char*));" % max(1, len(resnames)))
+        for i, rn in enumerate(resnames):
+            w(' SET_INTERNAL_NAME(functable->res_jac_names[%d],"%s");' % (i, rn))
+        w(" functable->shapes_required_ResJac=(JITFuncSpec_RequiredShapes_FiniteElement_t *)calloc(%d,sizeof(JITFuncSpec_RequiredShapes_FiniteElement_t));" % max(1, len(resnames)))
+        w(" functable->numglobal_params=%d;" % len(code.global_params))
+        w(" functable->global_parameters=(double **)calloc(%d,sizeof(double*));" % max(1, len(code.global_params)))
+        w(" functable->ResidualAndJacobian=(JITFuncSpec_ResidualAndJacobian_FiniteElement *)calloc(%d,sizeof(JITFuncSpec_ResidualAndJacobian_FiniteElement));" % max(1, len(resnames)))
+        w(" functable->ResidualAndJacobianSteady=(JITFuncSpec_ResidualAndJacobian_FiniteElement *)calloc(%d,sizeof(JITFuncSpec_ResidualAndJacobian_FiniteElement));" % max(1, len(resnames)))
+        w(" functable->ParameterDerivative=(JITFuncSpec_ResidualAndJacobian_FiniteElement **)calloc(%d,sizeof(JITFuncSpec_ResidualAndJacobian_FiniteElement*));" % max(1, len(resnames)))
+        for i, rn in enumerate(resnames):
+            w(" functable->ResidualAndJacobian[%d]=&ResidualAndJacobian%d;" % (i, i))
+            # steady solves run the same routine with zeroed weights / ntstorage 0 (src/elements.cpp:4583-4596)
+            w(" functable->ResidualAndJacobianSteady[%d]=&ResidualAndJacobian%d;" % (i, i))
+            w(" functable->ParameterDerivative[%d]=(JITFuncSpec_ResidualAndJacobian_FiniteElement *)calloc(%d,sizeof(JITFuncSpec_ResidualAndJacobian_FiniteElement));" % (i, max(1, len(code.global_params))))
+            for k, p in enumerate(code.global_params):
+                w(" functable->ParameterDerivative[%d][%d]=&dResidual%ddParameter_%s;" % (i, k, i, p))
+        w(" functable->max_dt_order=%d;" % code.max_dt_order())
+        w(" functable->moving_nodes=%s;" % ("true" if code.coordinates_as_dofs else "false"))
+        w(" functable->integration_order=0;")
+        w(' SET_INTERNAL_NAME(functable->dominant_space,"C2");')
+        w(" functable->hessian_generated=false;")
+        w(" functable->clean_up=&clean_up;")
+        w(" my_func_table=functable;")
+        w("}")
+        return "\n".join(o) + "\n"
+
+
+def emit_plugin_source(code: FiniteElementCode) -> str:
+    return CEmitter(code).emit()

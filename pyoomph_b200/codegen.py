@@ -1,0 +1,464 @@
+"""Element-class code model: fields, spaces, residual bookkeeping and symbolic derivation.
+
+Host-side mirror of ``pyoomph::FiniteElementCode`` (/root/reference/src/codegen.cpp) and of the
+Python ``Equations`` front end (/root/reference/pyoomph/generic/codegen.py:1852).  The reference
+derives, per test field and per unknown field, a *full* expression ``GiNaC::diff(var_part, field)``
+(src/codegen.cpp:1956) that the generated C evaluates for every (l_test, l_shape) pair.  The B200
+design instead exploits that a weak form is linear in the test function and its gradient, and
+that every shape expansion enters through ``psi_l`` or ``d psi_l/dx``:
+
+    E  = sum_s  T_s[l_test] * R_s(point)                 s = (test field, test atom)
+    J  = sum_s sum_a T_s[l_test] * C_{s,(G,a)}(point) * S_a[l_shape]     a = shape atom of unknown G
+
+so the only problem-specific code is the *pointwise* evaluation of R_s and C_{s,(G,a)} (straight-line
+code after CSE); the (l_test,l_shape) contraction is a fixed register-tiled kernel.  Moving-mesh
+columns (src/codegen.cpp:8454-8586, src/elements.cpp:3051) fit the same form through
+``d(d psi_m/dx_d)/dX^l_j = -(d psi_m/dx_j)(d psi_l/dx_d)`` and ``d(dx)/dX^l_j = dx * d psi_l/dx_j``
+(valid for elements without co-dimension, which is all bulk elements).
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import sympy as sp
+from sympy.core.function import AppliedUndef
+
+from . import expressions as ex
+
+# ---------------------------------------------------------------------------------------------
+# Element types (src/elements.hpp:556-1377).  Node order = oomph QElement tensor-product order,
+# first local coordinate fastest (oomph-lib Qelements.cc:348-377); C1 nodes = vertices
+# (src/elements.cpp:8733, :10764).
+# ---------------------------------------------------------------------------------------------
+
+
+@dataclasses.dataclass(frozen=True)
+class ElementType:
+    name: str
+    nodal_dim: int
+    elem_dim: int
+    nnode: int               # nodes of the dominant (geometry) space
+    order: int               # 1D nodes per direction of the geometry space (3 = quadratic)
+    c1_nodes: Tuple[int, ...]  # element-local node numbers carrying the C1 space
+    n_int_pt: int            # default oomph integration scheme (integration_order==0)
+
+    @property
+    def nnode_C1(self):
+        return len(self.c1_nodes)
+
+
+ELEMENT_TYPES: Dict[str, ElementType] = {
+    "Quad2dC2": ElementType("Quad2dC2", 2, 2, 9, 3, (0, 2, 6, 8), 9),
+    "Brick3dC2": ElementType("Brick3dC2", 3, 3, 27, 3, (0, 2, 6, 8, 18, 20, 24, 26), 27),
+}
+
+SPACE_ORDER = ("C2TB", "C2", "C1TB", "C1")  # nodal_data index order (src/codegen.cpp:2367-2380)
+
+
+@dataclasses.dataclass
+class Field:
+    name: str
+    space: str          # "C2", "C1" or "Pos"
+    index: int = -1     # index into nodal_data / nodal_coords (src/codegen.cpp:2795-2835)
+
+
+@dataclasses.dataclass(frozen=True)
+class AtomInfo:
+    """One interpolated quantity at an integration point (a printed ShapeExpansion)."""
+    field: str
+    dt_order: int        # 0,1,2
+    scheme: str          # "", "BDF1", "BDF2", "Newmark2" (+"_degr")
+    deriv: str           # "d0", "dx0".."dx2", "dX0".."dX2"
+    past: int = 0        # history index (evaluate_in_past)
+
+    @property
+    def cname(self) -> str:
+        """Name in the reference's generated code (src/codegen.cpp:943-1032)."""
+        d = {"d0": "d0x"}.get(self.deriv, "d1" + self.deriv[1] + self.deriv[2:])
+        return "intrp_d%dt%d%s_%s_%s" % (self.dt_order, self.past, self.scheme if self.dt_order else "", d, self.field)
+
+
+@dataclasses.dataclass(frozen=True)
+class TestSlot:
+    field: str
+    deriv: str           # "d0", "dxN", "dXN"
+
+
+@dataclasses.dataclass
+class ResidualForm:
+    """Coefficient form of one generated routine (ResidualAndJacobian<i>, dResidual<i>dParameter_<p>)."""
+    name: str
+    slots: List[TestSlot]
+    R: List[sp.Expr]                                          # per slot, measure weights folded in
+    J: Dict[Tuple[int, str, str], sp.Expr]                    # (slot, unknown field, shape atom) -> coefficient
+    M: Dict[Tuple[int, str, str], sp.Expr]                    # mass-matrix coefficients (flag==2)
+    atoms: List[AtomInfo]                                     # point inputs needed
+    uses_dx: bool = True
+    uses_dX: bool = False
+
+    def unknown_fields(self) -> List[str]:
+        seen: List[str] = []
+        for (_, g, _a) in list(self.J.keys()) + list(self.M.keys()):
+            if g not in seen:
+                seen.append(g)
+        return seen
+
+
+class FiniteElementCode:
+    """Per-element-class code object (FiniteElementCode, src/codegen.hpp; FiniteElementCodeGenerator,
+    pyoomph/generic/codegen.py:60)."""
+
+    def __init__(self, element_type: str, equations: "Equations", *, default_timestepping_scheme: str = "BDF2",
+                 name: str = "domain"):
+        self.etype = ELEMENT_TYPES[element_type]
+        self.nodal_dim = self.etype.nodal_dim
+        self.name = name
+        self.default_timestepping_scheme = default_timestepping_scheme
+        self.fields: Dict[str, Field] = {}
+        self.vector_fields: Dict[str, List[str]] = {}
+        self.coordinates_as_dofs = False
+        self.global_params: List[str] = []
+        self._param_syms: Dict[str, sp.Symbol] = {}
+        self.residuals: Dict[str, sp.Expr] = {}
+        self._atom_syms: Dict[sp.Symbol, AtomInfo] = {}
+        self._atom_by_info: Dict[AtomInfo, sp.Symbol] = {}
+        self._test_syms: Dict[sp.Symbol, TestSlot] = {}
+        self.equations = equations
+        self._defining_fields = False
+        # position fields always exist (src/codegen.cpp:2816-2835)
+        for i, d in enumerate(ex.DIRS[:self.nodal_dim]):
+            self.fields["coordinate_" + d] = Field("coordinate_" + d, "Pos", i)
+        for i, d in enumerate(ex.DIRS[:self.nodal_dim]):
+            self.fields["lagrangian_" + d] = Field("lagrangian_" + d, "Pos", self.nodal_dim + i)
+        ex._Context.stack.append(self)
+        try:
+            equations._code = self
+            self._defining_fields = True
+            equations.define_fields()
+            self._defining_fields = False
+            self._index_fields()
+            equations.define_residuals()
+        finally:
+            ex._Context.stack.pop()
+        self._forms: Dict[str, ResidualForm] = {}
+
+    # -- field bookkeeping ---------------------------------------------------------------------
+    def define_scalar_field(self, name: str, space: str):
+        if space not in ("C2", "C1"):
+            raise RuntimeError("space %s is outside the scope of the CUDA assembly path (C2/C1 only)" % space)
+        if space == "C2" and self.etype.order < 3:
+            raise RuntimeError("C2 field on a first-order element")
+        self.fields[name] = Field(name, space)
+
+    def define_vector_field(self, name: str, space: str, dim: Optional[int] = None):
+        dim = dim or self.nodal_dim
+        comps = [name + "_" + d for d in ex.DIRS[:dim]]
+        for c in comps:
+            self.define_scalar_field(c, space)
+        self.vector_fields[name] = comps
+
+    def _index_fields(self):
+        idx = 0
+        for sp_name in SPACE_ORDER:
+            for f in self.fields.values():
+                if f.space == sp_name:
+                    f.index = idx
+                    idx += 1
+        self.n_nodal_values = idx
+
+    def nodal_fields(self) -> List[Field]:
+        return sorted([f for f in self.fields.values() if f.space != "Pos"], key=lambda f: f.index)
+
+    def _require_field(self, name: str):
+        if name.startswith("coordinate_") or name.startswith("lagrangian_"):
+            if name not in self.fields:
+                raise RuntimeError("no such position field " + name)
+            return
+        if name not in self.fields:
+            raise RuntimeError("field '%s' is not defined on element class '%s'" % (name, self.name))
+
+    def _global_param_symbol(self, name: str) -> sp.Symbol:
+        if name not in self._param_syms:
+            self._param_syms[name] = sp.Symbol("P__" + name, real=True)
+            self.global_params.append(name)
+        return self._param_syms[name]
+
+    def add_residual(self, expr, destination: str = ""):
+        expr = sp.sympify(expr)
+        self.residuals[destination] = self.residuals.get(destination, sp.Integer(0)) + expr
+
+    def residual_names(self) -> List[str]:
+        return list(self.residuals.keys())
+
+    def space_nodes(self, space: str) -> Tuple[int, ...]:
+        """Element-local node numbers of a space (src/elements.cpp:2870-2879)."""
+        if space in ("C2", "Pos"):
+            return tuple(range(self.etype.nnode))
+        if space == "C1":
+            return self.etype.c1_nodes
+        raise KeyError(space)
+
+    def dof_layout(self) -> List[Tuple[str, int]]:
+        """Local dof order used by this engine: for each element node in local order, position
+        dofs (if coordinates are dofs) then nodal values by index.  oomph's own local order is
+        nodal values then solid positions (oomph-lib elements.cc:694-699); the generated code never
+        depends on it, it only maps through *_local_eqn."""
+        out: List[Tuple[str, int]] = []
+        for l in range(self.etype.nnode):
+            if self.coordinates_as_dofs:
+                for d in ex.DIRS[:self.nodal_dim]:
+                    out.append(("coordinate_" + d, l))
+            for f in self.nodal_fields():
+                nodes = self.space_nodes(f.space)
+                if l in nodes:
+                    out.append((f.name, nodes.index(l)))
+        return out
+
+    # -- atomisation ---------------------------------------------------------------------------
+    def _time_scheme(self, dt_order: int) -> str:
+        # get_default_timestepping_scheme (pyoomph/generic/problem.py:750-757); dt^2 -> Newmark2
+        # (src/codegen.cpp:8245); first order default gets the _degr suffix (src/codegen.cpp:8116)
+        if dt_order == 2:
+            return "Newmark2"
+        s = self.default_timestepping_scheme
+        return s + "_degr" if s != "BDF1" else s
+
+    def _atom(self, info: AtomInfo) -> sp.Symbol:
+        if info not in self._atom_by_info:
+            s = sp.Symbol("A__%s__dt%d%s__%s__p%d" % (info.field, info.dt_order, info.scheme, info.deriv, info.past), real=True)
+            self._atom_by_info[info] = s
+            self._atom_syms[s] = info
+        return self._atom_by_info[info]
+
+    def _test_atom(self, slot: TestSlot) -> sp.Symbol:
+        s = sp.Symbol("Tst__%s__%s" % (slot.field, slot.deriv), real=True)
+        self._test_syms[s] = slot
+        return s
+
+    def _classify(self, d):
+        """Split a Derivative/AppliedUndef node into (kind, field, past, dt_order, eul_dirs, lag_dirs)."""
+        if isinstance(d, sp.Derivative):
+            base = d.expr
+            counts = {v: n for v, n in d.variable_count}
+        else:
+            base, counts = d, {}
+        nm = base.func.__name__
+        past = 0
+        if "__past" in nm:
+            nm, p = nm.split("__past")
+            past = int(p)
+        kind, field = nm[0], nm[3:]
+        dt = int(counts.get(ex.TIME, 0))
+        eul = [i for i, c in enumerate(ex.EUL) for _ in range(int(counts.get(c, 0)))]
+        lag = [i for i, c in enumerate(ex.LAG) for _ in range(int(counts.get(c, 0)))]
+        return kind, field, past, dt, eul, lag
+
+    def atomize(self, expr: sp.Expr) -> sp.Expr:
+        expr = sp.sympify(expr)
+        repl = {}
+        nodes = list(expr.atoms(sp.Derivative)) + list(expr.atoms(AppliedUndef))
+        for d in nodes:
+            base = d.expr if isinstance(d, sp.Derivative) else d
+            if not isinstance(base, AppliedUndef) or not base.func.__name__[:3] in ("F__", "T__"):
+                raise RuntimeError("cannot atomise " + str(d))
+            kind, field, past, dt, eul, lag = self._classify(d)
+            if len(eul) + len(lag) > 1:
+                raise RuntimeError("second spatial derivatives of C0 shape expansions are not available: " + str(d))
+            deriv = "d0" if not (eul or lag) else ("dx%d" % eul[0] if eul else "dX%d" % lag[0])
+            if kind == "T":
+                if dt or past:
+                    raise RuntimeError("time derivative of a test function")
+                repl[d] = self._test_atom(TestSlot(field, deriv))
+                continue
+            # position-space rules (src/codegen.cpp:8220-8230, :8285-8324, :8376-8399)
+            if field.startswith("coordinate_"):
+                i = ex.DIRS.index(field[-1])
+                if eul:
+                    if dt:
+                        raise RuntimeError("spatial derivative of the mesh velocity is not supported")
+                    repl[d] = sp.Integer(1 if eul[0] == i else 0)
+                    continue
+            if field.startswith("lagrangian_"):
+                i = ex.DIRS.index(field[-1])
+                if dt:
+                    repl[d] = sp.Integer(0)
+                    continue
+                if lag:
+                    repl[d] = sp.Integer(1 if lag[0] == i else 0)
+                    continue
+                if eul:
+                    raise RuntimeError("Eulerian derivative of Lagrangian coordinates is not supported")
+            if dt > 2:
+                raise RuntimeError("Too high dt order")
+            scheme = self._time_scheme(dt) if dt else ""
+            repl[d] = self._atom(AtomInfo(field, dt, scheme, deriv, past))
+        return expr.xreplace(repl)
+
+    # -- derivation ----------------------------------------------------------------------------
+    def unknown_field_names(self) -> List[str]:
+        out = []
+        if self.coordinates_as_dofs:
+            out += ["coordinate_" + d for d in ex.DIRS[:self.nodal_dim]]
+        out += [f.name for f in self.nodal_fields()]
+        return out
+
+    def derive(self, resname: str = "", parameter: Optional[str] = None) -> ResidualForm:
+        key = resname + ("|dP_" + parameter if parameter else "")
+        if key in self._forms:
+            return self._forms[key]
+        E = self.atomize(self.residuals[resname])
+        if parameter is not None:
+            E = sp.diff(E, self._param_syms[parameter])
+        form = self._coefficient_form(E, key)
+        self._forms[key] = form
+        return form
+
+    def _coefficient_form(self, E: sp.Expr, name: str) -> ResidualForm:
+        tests = sorted([s for s in E.free_symbols if s in self._test_syms], key=lambda s: s.name)
+        slots: List[TestSlot] = []
+        R: List[sp.Expr] = []
+        rest = E
+        for ts in tests:
+            coeff = sp.diff(E, ts)
+            if coeff.has(*tests):
+                raise RuntimeError("residual is not linear in the test functions")
+            slots.append(self._test_syms[ts])
+            R.append(coeff)
+            rest = rest - ts * coeff
+        if sp.simplify(sp.expand(rest)) != 0:
+            raise RuntimeError("residual has a part without test function: " + str(rest))
+        unknowns = set(self.unknown_field_names())
+        J: Dict[Tuple[int, str, str], sp.Expr] = {}
+        M: Dict[Tuple[int, str, str], sp.Expr] = {}
+
+        def add(dic, k, v):
+            if v != 0:
+                dic[k] = dic.get(k, sp.Integer(0)) + v
+
+        def slot_index(slot: TestSlot) -> int:
+            if slot not in slots:
+                slots.append(slot)
+                R.append(sp.Integer(0))
+            return slots.index(slot)
+
+        nslot0 = len(slots)
+        for si in range(nslot0):
+            Rs = R[si]
+            atoms = [s for s in Rs.free_symbols if s in self._atom_syms]
+            for a in atoms:
+                info = self._atom_syms[a]
+                if info.past or info.field not in unknowns:
+                    continue  # history values and non-dof data carry no Jacobian (src/codegen.cpp:8256)
+                c = sp.diff(Rs, a)
+                if info.dt_order == 0:
+                    add(J, (si, info.field, info.deriv), c)
+                else:
+                    w = sp.Symbol("W__%s__%d" % (info.scheme, info.dt_order), real=True)
+                    add(J, (si, info.field, info.deriv), w * c)
+                    if info.dt_order == 1:
+                        add(M, (si, info.field, info.deriv), c)  # __partial_t_mass_matrix (src/codegen.cpp:8260)
+            if self.coordinates_as_dofs:
+                RE = ex.DX_EUL * sp.diff(Rs, ex.DX_EUL)  # Eulerian-measure part
+                slot = slots[si]
+                for j, dj in enumerate(ex.DIRS[:self.nodal_dim]):
+                    Xj = "coordinate_" + dj
+                    # d(dx)/dX_j^l = dx * dpsi_l/dx_j   (int_pt_weights_d_coords, src/elements.cpp:3086)
+                    add(J, (si, Xj, "dx%d" % j), RE)
+                    # d(dpsi_m/dx_d)/dX_j^l = -dpsi_m/dx_j * dpsi_l/dx_d applied to every Eulerian gradient atom
+                    for a in atoms:
+                        info = self._atom_syms[a]
+                        if info.deriv.startswith("dx") and not info.past:
+                            aj = self._atom(dataclasses.replace(info, deriv="dx%d" % j))
+                            add(J, (si, Xj, info.deriv), -sp.diff(Rs, a) * aj)
+                    # ... and to the test-function gradient itself (src/codegen.cpp:8642)
+                    if slot.deriv.startswith("dx"):
+                        sj = slot_index(TestSlot(slot.field, "dx%d" % j))
+                        add(J, (sj, Xj, slot.deriv), -Rs)
+        used = set()
+        for e in list(R) + list(J.values()) + list(M.values()):
+            used |= {s for s in e.free_symbols if s in self._atom_syms}
+        atoms = sorted((self._atom_syms[s] for s in used), key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
+        allsyms = set().union(*[e.free_symbols for e in list(R) + list(J.values()) + list(M.values())]) if R else set()
+        return ResidualForm(name, slots, R, J, M, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=ex.DX_LAG in allsyms)
+
+    def atom_symbol(self, info: AtomInfo) -> sp.Symbol:
+        return self._atom(info)
+
+    def max_dt_order(self) -> int:
+        m = 0
+        for n in self.residual_names():
+            for a in self.derive(n).atoms:
+                m = max(m, a.dt_order)
+        return m
+
+    def history_levels(self) -> int:
+        """Number of nodal history values the routines read (T in SURVEY 8d)."""
+        t = 1
+        for n in self.residual_names():
+            for a in self.derive(n).atoms:
+                if a.dt_order == 1:
+                    t = max(t, 2 if a.scheme == "BDF1" else 3)
+                if a.dt_order == 2:
+                    t = max(t, 5)
+                t = max(t, a.past + 1)
+        return t
+
+
+# ---------------------------------------------------------------------------------------------
+# Equations front end (pyoomph/generic/codegen.py:1852 Equations)
+# ---------------------------------------------------------------------------------------------
+class Equations:
+    def __init__(self):
+        self._code: Optional[FiniteElementCode] = None
+        self._children: List["Equations"] = []
+
+    def get_current_code_generator(self) -> FiniteElementCode:
+        assert self._code is not None
+        return self._code
+
+    def get_nodal_dimension(self) -> int:
+        return self._code.nodal_dim
+
+    def define_fields(self):
+        pass
+
+    def define_residuals(self):
+        pass
+
+    def define_scalar_field(self, name: str, space: str, **_scaling):
+        self._code.define_scalar_field(name, space)
+
+    def define_vector_field(self, name: str, space: str, dim: Optional[int] = None, **_scaling):
+        self._code.define_vector_field(name, space, dim)
+
+    def activate_coordinates_as_dofs(self, coordinate_space: Optional[str] = None):
+        self._code.coordinates_as_dofs = True
+
+    def add_residual(self, expr, destination: str = ""):
+        self._code.add_residual(expr, destination)
+
+    def get_global_parameter(self, name: str):
+        return self._code._global_param_symbol(name)
+
+    def __add__(self, other: "Equations") -> "Equations":
+        return CombinedEquations([self, other])
+
+
+class CombinedEquations(Equations):
+    """``eqs_a + eqs_b`` (pyoomph/generic/codegen.py CombinedEquations)."""
+
+    def __init__(self, parts: Sequence[Equations]):
+        super().__init__()
+        self.parts: List[Equations] = []
+        for p in parts:
+            self.parts += p.parts if isinstance(p, CombinedEquations) else [p]
+
+    def define_fields(self):
+        for p in self.parts:
+            p._code = self._code
+            p.define_fields()
+
+    def define_residuals(self):
+        for p in self.parts:
+            p.define_residuals()

@@ -1,0 +1,113 @@
+"""Equation classes that define the BASELINE configs, written against the same front-end calls
+as the reference's own classes so the definitions read alike:
+
+* ``PoissonEquation``          /root/reference/pyoomph/equations/poisson.py:35-75
+* ``StokesEquations`` / ``NavierStokesEquations`` (Taylor-Hood)  pyoomph/equations/navier_stokes.py:148-344, :422-503
+* ``TransientHeatEquation``    partial_t(u) + Poisson part (config 3; cf. pyoomph/equations/advection_diffusion.py)
+* ``PseudoElasticMesh``        pyoomph/equations/ALE.py:97-146
+
+Scaling/non-dimensionalisation factors of the reference are all 1 here (no units in the configs).
+"""
+from __future__ import annotations
+
+from .codegen import Equations
+from .expressions import (Weak, contract, div, dot, grad, identity_matrix, material_derivative, partial_t,
+                          rational_num, sym, testfunction, trace, var, var_and_test, weak)
+
+
+class PoissonEquation(Equations):
+    """-div(coeff*grad(u)) = f  (poisson.py:35)."""
+
+    def __init__(self, name: str = "u", *, space: str = "C2", source=None, coefficient=1):
+        super().__init__()
+        self.name, self.space, self.source, self.coefficient = name, space, source, coefficient
+
+    def define_fields(self):
+        self.define_scalar_field(self.name, self.space)
+
+    def define_residuals(self):
+        u, u_test = var_and_test(self.name)
+        self.add_residual(weak(self.coefficient * grad(u), grad(u_test)))
+        if self.source is not None:
+            src = self.source() if callable(self.source) else self.source
+            self.add_residual(-weak(src, u_test))
+
+
+class TransientHeatEquation(PoissonEquation):
+    """partial_t(u) - div(coeff*grad(u)) = f, default time scheme of the problem (BDF2 for config 3)."""
+
+    def __init__(self, name: str = "u", *, space: str = "C2", source=None, coefficient=1, capacity=1):
+        super().__init__(name, space=space, source=source, coefficient=coefficient)
+        self.capacity = capacity
+
+    def define_residuals(self):
+        super().define_residuals()
+        u, u_test = var_and_test(self.name)
+        self.add_residual(weak(self.capacity * partial_t(u), u_test))
+
+
+class StokesEquations(Equations):
+    """Stokes flow, Taylor-Hood: velocity in C2, pressure in C1 (navier_stokes.py:148-344)."""
+
+    def __init__(self, *, dynamic_viscosity=1.0, bulkforce=None, velocity_name="velocity", pressure_name="pressure",
+                 pressure_sign_flip=False, pressure_factor=1):
+        super().__init__()
+        self.dynamic_viscosity = dynamic_viscosity
+        self.bulkforce = bulkforce
+        self.velocity_name, self.pressure_name = velocity_name, pressure_name
+        self.pressure_sign_flip, self.pressure_factor = pressure_sign_flip, pressure_factor
+
+    def define_fields(self):
+        self.define_vector_field(self.velocity_name, "C2")
+        self.define_scalar_field(self.pressure_name, "C1")
+
+    def define_stress_tensor(self):
+        u, p = var(self.velocity_name), var(self.pressure_name)
+        strain = sym(grad(u))
+        return 2 * self.dynamic_viscosity * strain - identity_matrix() * self.pressure_factor * p * (-1 if self.pressure_sign_flip else 1)
+
+    def define_residuals(self):
+        u, u_test = var_and_test(self.velocity_name)
+        p, p_test = var_and_test(self.pressure_name)
+        stress_tensor = self.define_stress_tensor()
+        Dv = grad(u_test)   # symmetric_test_function 'auto' resolves to the plain gradient for Cartesian TH
+        self.add_residual(weak(stress_tensor, Dv))
+        self.add_residual(weak(div(u), p_test))
+        if self.bulkforce is not None:
+            self.add_residual(-weak(self.bulkforce, u_test))
+
+
+class NavierStokesEquations(StokesEquations):
+    """Adds rho*(dt_factor*partial_t(u) + nonlinear_factor*(u.grad)u) (navier_stokes.py:422-503)."""
+
+    def __init__(self, *, dynamic_viscosity=1.0, mass_density=1.0, bulkforce=None, dt_factor=1, nonlinear_factor=1, **kw):
+        super().__init__(dynamic_viscosity=dynamic_viscosity, bulkforce=bulkforce, **kw)
+        self.mass_density, self.dt_factor, self.nonlinear_factor = mass_density, dt_factor, nonlinear_factor
+
+    def define_residuals(self):
+        super().define_residuals()
+        u, u_test = var_and_test(self.velocity_name)
+        rho = self.mass_density
+        self.add_residual(weak(rho * material_derivative(u, u, dt_factor=self.dt_factor, advection_factor=self.nonlinear_factor), u_test))
+
+
+class PseudoElasticMesh(Equations):
+    """Moving mesh as a linear-elastic pseudo solid in Lagrangian coordinates (ALE.py:97-146)."""
+
+    def __init__(self, E=1, nu=rational_num(3, 10)):
+        super().__init__()
+        self.E, self.nu = E, nu
+
+    def define_fields(self):
+        self.activate_coordinates_as_dofs()
+
+    def define_residuals(self):
+        E, nu = self.E, self.nu
+        mu = E / 2 / (1 + nu)
+        lmbda = E * nu / (1 + nu) / (1 - 2 * nu)
+        lmbda = 2 * mu * lmbda / (lmbda + 2 * mu)
+        eps = lambda v: sym(grad(v, lagrangian=True))
+        sigma = lambda v: lmbda * trace(eps(v)) * identity_matrix() + 2 * mu * eps(v)
+        x, x_test = var_and_test("mesh")
+        X = var("lagrangian")
+        self.add_residual(Weak(sigma(x - X), eps(x_test)))

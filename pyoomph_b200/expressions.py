@@ -1,0 +1,280 @@
+"""Symbolic weak-form vocabulary of the assembly hot path.
+
+Mirrors the subset of pyoomph's expression API that the five BASELINE configs use
+(/root/reference/pyoomph/expressions/generic.py: ``var`` :137, ``grad`` :355, ``weak`` :394,
+``Weak`` :429, ``mesh_velocity`` :497, ``partial_t`` :507, ``material_derivative`` :564,
+``testfunction`` :647, ``identity_matrix`` :826, ``vector`` :928, ``dot`` :982,
+``transpose`` :1043, ``subexpression`` :1058).  In pyoomph these build GiNaC trees inside the C++
+core (src/expressions.cpp); GiNaC is not available here, so sympy plays GiNaC's role: a field is
+an applied undefined function of the Eulerian coordinates, the Lagrangian coordinates and time,
+so that ``sympy.diff`` produces exactly the objects ``GiNaCShapeExpansion::derivative``
+(src/codegen.cpp:8190) produces: spatial/temporal derivatives of the shape expansion.
+
+Nothing in this module evaluates numbers; it only builds trees that ``codegen.FiniteElementCode``
+turns into the coefficient form the CUDA kernels (and, independently, the CPU oracle) consume.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple, Union
+
+import sympy as sp
+from sympy.core.function import AppliedUndef
+
+# Independent symbols (src/expressions.cpp global symbols x,y,z,X,Y,Z,t)
+EUL = sp.symbols("x y z", real=True)
+LAG = sp.symbols("X Y Z", real=True)
+TIME = sp.Symbol("t", real=True)
+# measures: Eulerian dx / Lagrangian dX  (GiNaCSpatialIntegralSymbol, src/codegen.cpp:7562)
+DX_EUL = sp.Symbol("M__dx", real=True)
+DX_LAG = sp.Symbol("M__dX", real=True)
+
+DIRS = ("x", "y", "z")
+
+ExpressionOrNum = Union[sp.Expr, sp.MatrixBase, float, int]
+
+
+class _Context:
+    """The code generator whose residuals are currently being defined (pyoomph::__current_code)."""
+    stack: List["object"] = []
+
+    @classmethod
+    def current(cls):
+        if not cls.stack:
+            raise RuntimeError("var()/testfunction() may only be used while an element code is being defined "
+                               "(inside Equations.define_residuals)")
+        return cls.stack[-1]
+
+
+def _args(ndim: int):
+    return tuple(EUL[:ndim]) + tuple(LAG[:ndim]) + (TIME,)
+
+
+class FieldFunction(sp.Function):
+    """Shape expansion  sum_l U^l psi_l  of a named field (ShapeExpansion, src/codegen.hpp)."""
+    is_real = True
+
+
+class TestFunctionSymbol(sp.Function):
+    """Test function psi_{l_test} of a named field (TestFunction, src/codegen.hpp)."""
+    is_real = True
+
+
+def _field(name: str) -> sp.Expr:
+    code = _Context.current()
+    code._require_field(name)
+    return sp.Function("F__" + name, real=True)(*_args(code.nodal_dim))
+
+
+def _test(name: str) -> sp.Expr:
+    code = _Context.current()
+    code._require_field(name)
+    return sp.Function("T__" + name, real=True)(*_args(code.nodal_dim))
+
+
+def _vector_components(code, name: str) -> Optional[List[str]]:
+    if name in ("mesh", "coordinate"):
+        return ["coordinate_" + d for d in DIRS[:code.nodal_dim]]
+    if name == "lagrangian":
+        return ["lagrangian_" + d for d in DIRS[:code.nodal_dim]]
+    if name in code.vector_fields:
+        return list(code.vector_fields[name])
+    return None
+
+
+_ALIASES = {"mesh_x": "coordinate_x", "mesh_y": "coordinate_y", "mesh_z": "coordinate_z"}
+
+
+def var(arg: Union[str, Sequence[str]]):
+    """Field value(s) by name; vector fields expand to a column of components (generic.py:137)."""
+    if not isinstance(arg, str):
+        return tuple(var(a) for a in arg)
+    code = _Context.current()
+    if arg == "time":
+        return TIME
+    comps = _vector_components(code, arg)
+    if comps is not None:
+        return sp.Matrix([_field(c) for c in comps])
+    return _field(_ALIASES.get(arg, arg))
+
+
+def testfunction(arg: Union[str, Sequence[str]]):
+    """Galerkin test function(s) of a field (generic.py:647)."""
+    if not isinstance(arg, str):
+        return tuple(testfunction(a) for a in arg)
+    code = _Context.current()
+    comps = _vector_components(code, arg)
+    if comps is not None:
+        return sp.Matrix([_test(c) for c in comps])
+    return _test(_ALIASES.get(arg, arg))
+
+
+def var_and_test(name: str):
+    return var(name), testfunction(name)
+
+
+def global_parameter(name: str) -> sp.Symbol:
+    """Problem-level parameter, printed as (*(my_func_table->global_parameters[k])) (src/expressions.cpp:95)."""
+    code = _Context.current()
+    return code._global_param_symbol(name)
+
+
+def _is_matrix(a) -> bool:
+    return isinstance(a, sp.MatrixBase)
+
+
+def _coords(lagrangian: bool):
+    code = _Context.current()
+    return (LAG if lagrangian else EUL)[:code.nodal_dim]
+
+
+def grad(arg: ExpressionOrNum, lagrangian: bool = False):
+    """Gradient: scalar -> column vector, vector -> matrix G[i,j]=d u_i / d x_j (generic.py:355).
+
+    Only the Cartesian coordinate system is built here; axisymmetric terms are added by the
+    equation classes that need them (see equations.AxisymmetricNavierStokes)."""
+    cs = _coords(lagrangian)
+    if _is_matrix(arg):
+        if arg.shape[1] != 1:
+            raise RuntimeError("grad of a rank-2 tensor is not supported")
+        return sp.Matrix(arg.shape[0], len(cs), lambda i, j: sp.diff(arg[i, 0], cs[j]))
+    arg = sp.sympify(arg)
+    return sp.Matrix([sp.diff(arg, c) for c in cs])
+
+
+def div(arg, lagrangian: bool = False):
+    cs = _coords(lagrangian)
+    if not _is_matrix(arg):
+        raise RuntimeError("div needs a vector")
+    if arg.shape[1] == 1:
+        return sum(sp.diff(arg[i, 0], cs[i]) for i in range(len(cs)))
+    return sp.Matrix([sum(sp.diff(arg[i, j], cs[j]) for j in range(len(cs))) for i in range(arg.shape[0])])
+
+
+def dot(a, b):
+    if _is_matrix(a) and _is_matrix(b):
+        if a.shape[1] == 1 and b.shape[1] == 1:
+            return sum(a[i, 0] * b[i, 0] for i in range(a.shape[0]))
+        if a.shape[1] == 1:  # v . M
+            return (a.T * b).T
+        return a * b
+    return a * b
+
+
+def contract(a, b):
+    """Full contraction of two equal-rank objects (generic.py:470)."""
+    if _is_matrix(a) != _is_matrix(b):
+        raise RuntimeError("cannot contract objects of different rank")
+    if _is_matrix(a):
+        if a.shape != b.shape:
+            raise RuntimeError("shape mismatch in contract: %s vs %s" % (a.shape, b.shape))
+        return sum(a[i, j] * b[i, j] for i in range(a.shape[0]) for j in range(a.shape[1]))
+    return sp.sympify(a) * sp.sympify(b)
+
+
+def double_dot(a, b):
+    return contract(a, b)
+
+
+def weak(a, b, *, lagrangian: bool = False):
+    """(a,b) = integral of contract(a,b) over the element, Eulerian dx unless lagrangian (generic.py:394)."""
+    return contract(a, b) * (DX_LAG if lagrangian else DX_EUL)
+
+
+def Weak(a, b):
+    """Lagrangian weak form (generic.py:429)."""
+    return weak(a, b, lagrangian=True)
+
+
+def transpose(a):
+    return a.T
+
+
+def sym(a):
+    return (a + a.T) / 2
+
+
+def trace(a):
+    return a.trace()
+
+
+def identity_matrix(dim: int = -1):
+    if dim < 0:
+        dim = _Context.current().nodal_dim
+    return sp.eye(dim)
+
+
+def vector(*args):
+    if len(args) == 1 and isinstance(args[0], (list, tuple)):
+        args = tuple(args[0])
+    return sp.Matrix([sp.sympify(a) for a in args])
+
+
+def matproduct(a, b):
+    return a * b
+
+
+def dyadic(a, b):
+    return a * b.T
+
+
+def subexpression(what):
+    """pyoomph wraps expensive terms for CSE (generic.py:1058); sympy.cse does that globally here."""
+    return what
+
+
+def rational_num(n, d=1):
+    return sp.Rational(n, d)
+
+
+def mesh_velocity():
+    """partial_t(var("mesh"), ALE=False) (generic.py:497)."""
+    return partial_t(var("mesh"), ALE=False)
+
+
+def partial_t(f, order: int = 1, ALE: Union[str, bool] = "auto"):
+    """Time derivative at fixed local coordinate, ALE-corrected on moving meshes (generic.py:507)."""
+    if isinstance(f, str):
+        f = var(f)
+    if order == 0:
+        return f
+    code = _Context.current()
+    d = (f.diff(TIME, order) if _is_matrix(f) else sp.diff(sp.sympify(f), TIME, order))
+    use_ale = (ALE is True) or (ALE == "auto" and code.coordinates_as_dofs)
+    if use_ale:
+        if order != 1:
+            raise ValueError("Currently, I can only take the first order time derivative with ALE")
+        d = d - directional_derivative(f, mesh_velocity())
+    return d
+
+
+def directional_derivative(f, direction):
+    """(direction . grad) f (generic.py:623)."""
+    g = grad(f)
+    if _is_matrix(f):
+        return g * direction
+    return dot(direction, g)
+
+
+def material_derivative(f, velocity, ALE: Union[str, bool] = "auto", dt_factor=1, advection_factor=1):
+    """dt_factor*partial_t(f) + advection_factor*(velocity.grad) f (generic.py:564)."""
+    if isinstance(f, str):
+        f = var(f)
+    if isinstance(velocity, str):
+        velocity = var(velocity)
+    return dt_factor * partial_t(f, ALE=ALE) + advection_factor * directional_derivative(f, velocity)
+
+
+def evaluate_in_past(expr, timestep_offset: int = 1):
+    """Replace every field by its history value (generic.py:1125); only integer offsets."""
+    expr = sp.sympify(expr) if not _is_matrix(expr) else expr
+    repl = {}
+    for f in expr.atoms(AppliedUndef):
+        nm = f.func.__name__
+        if nm.startswith("F__"):
+            repl[f] = sp.Function(nm + "__past%d" % int(timestep_offset), real=True)(*f.args)
+    return expr.xreplace(repl)
+
+
+# math vocabulary (A.2 of SURVEY: pow, libm functions)
+sqrt, exp, log, sin, cos, tan, tanh, atan2 = sp.sqrt, sp.exp, sp.log, sp.sin, sp.cos, sp.tan, sp.tanh, sp.atan2
+pi = sp.Symbol("Pi", real=True)  # jitbridge_hang.h:355 defines Pi as 3.14159265359 (truncated); kept symbolic

@@ -1,0 +1,175 @@
+"""Structured meshes generated directly in array form, with the reference's node/element/equation order.
+
+The reference builds these through Python triple loops and a kd-tree de-duplication
+(/root/reference/pyoomph/meshes/simplemeshes.py:224-305 RectangularQuadMesh, :456-540 CuboidBrickMesh,
+src/meshtemplate.cpp:1378-1398 add_node_unique), then converts every C1 template element to C2 in element
+order (src/meshtemplate.cpp:401-409 quads, :579-620 bricks).  That is O(minutes-hours) at the BASELINE
+sizes, so the same *ordering rules* are applied here with vectorised first-occurrence numbering:
+
+* elements: x outermost ... last coordinate innermost;
+* all vertex nodes precede all mid nodes; within each class nodes are numbered at first touch, visiting
+  elements in order and, inside an element, in the order the reference creates them;
+* element-local node layout = oomph tensor-product order (first local coordinate fastest);
+* equations: nodes in order; per node position dofs first, then nodal values by index, pinned ones skipped
+  (oomph-lib mesh.cc:686-708, nodes.cc:896-927, :3652-3659).  C1 fields own a (pinned, dummy) slot on
+  non-vertex nodes as well (src/elements.cpp:2235-2271).
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .codegen import FiniteElementCode
+
+
+@dataclasses.dataclass
+class StructuredMesh:
+    dim: int
+    N: Tuple[int, ...]
+    elem_nodes: np.ndarray           # [n_elem, nnode] int32, oomph local order
+    node_pos: np.ndarray             # [n_node, dim] float64
+    node_lattice: np.ndarray         # [n_node, dim] int32 position on the (2N+1)^dim lattice
+    boundaries: Dict[str, np.ndarray]  # name -> node indices
+    element_type: str
+
+    @property
+    def n_elem(self) -> int:
+        return self.elem_nodes.shape[0]
+
+    @property
+    def n_node(self) -> int:
+        return self.node_pos.shape[0]
+
+    def is_vertex(self) -> np.ndarray:
+        return np.all(self.node_lattice % 2 == 0, axis=1)
+
+
+def _first_occurrence_ids(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """ids by first occurrence in the flattened key stream; returns (ids shaped like keys, first index per id)."""
+    flat = keys.ravel()
+    uniq, first, inv = np.unique(flat, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size)
+    return rank[inv].reshape(keys.shape), first[order]
+
+
+def _structured(N: Sequence[int], size: Sequence[float], lower_left: Sequence[float]) -> StructuredMesh:
+    dim = len(N)
+    N = tuple(int(n) for n in N)
+    # element index grid, first coordinate outermost (simplemeshes.py:225/:233, :512-514)
+    grids = np.meshgrid(*[np.arange(n, dtype=np.int64) for n in N], indexing="ij")
+    eidx = np.stack([g.ravel() for g in grids], axis=1)          # [n_elem, dim]
+    n_elem = eidx.shape[0]
+    L = [2 * n + 1 for n in N]                                   # lattice extents
+
+    def lattice_key(lat):  # lat [..., dim]
+        k = lat[..., 0]
+        for d in range(1, dim):
+            k = k * L[d] + lat[..., d]
+        return k
+
+    # creation order inside an element, as lattice offsets in {0,1,2}^dim (x fastest in the oomph local index)
+    if dim == 2:
+        vert_order = [(0, 0), (2, 0), (0, 2), (2, 2)]            # n00,n10,n01,n11 (simplemeshes.py:234-240)
+        mid_order = [(1, 0), (0, 1), (1, 1), (2, 1), (1, 2)]     # meshtemplate.cpp:403-407
+    else:
+        vert_order = [(0, 0, 0), (2, 0, 0), (0, 2, 0), (2, 2, 0), (0, 0, 2), (2, 0, 2), (0, 2, 2), (2, 2, 2)]
+        # meshtemplate.cpp:583-617: local indices 1,3,4,5,7, 9,11,15,17, 19,21,22,23,25, 10,12,14,16,13
+        loc = [1, 3, 4, 5, 7, 9, 11, 15, 17, 19, 21, 22, 23, 25, 10, 12, 14, 16, 13]
+        mid_order = [(l % 3, (l // 3) % 3, l // 9) for l in loc]
+    base = 2 * eidx                                              # lattice origin of each element
+    vkeys = np.stack([lattice_key(base + np.array(o)) for o in vert_order], axis=1)
+    vid, vfirst = _first_occurrence_ids(vkeys)
+    n_vert = vfirst.size
+    mkeys = np.stack([lattice_key(base + np.array(o)) for o in mid_order], axis=1)
+    mid, mfirst = _first_occurrence_ids(mkeys)
+    n_node = n_vert + mfirst.size
+
+    # oomph local order: index = sum_d off_d * 3^d
+    nnode = 3 ** dim
+    elem_nodes = np.empty((n_elem, nnode), dtype=np.int32)
+    for k, o in enumerate(vert_order):
+        elem_nodes[:, sum(o[d] * 3 ** d for d in range(dim))] = vid[:, k]
+    for k, o in enumerate(mid_order):
+        elem_nodes[:, sum(o[d] * 3 ** d for d in range(dim))] = n_vert + mid[:, k]
+
+    # lattice coordinate of every node
+    node_lat = np.empty((n_node, dim), dtype=np.int32)
+    for k, o in enumerate(vert_order):
+        node_lat[vid[:, k]] = base + np.array(o)
+    for k, o in enumerate(mid_order):
+        node_lat[n_vert + mid[:, k]] = base + np.array(o)
+
+    # coordinates: vertices (i*size)/N + lower_left (simplemeshes.py:234); mid nodes by averaging the bracketing
+    # vertices the way the creating element does (0.5*(a+b), 0.25*(a+b+c+d))
+    def vcoord(i, d):
+        return (i * size[d]) / N[d] + lower_left[d]
+
+    node_pos = np.empty((n_node, dim), dtype=np.float64)
+    for d in range(dim):
+        lat = node_lat[:, d].astype(np.int64)
+        lo, hi = lat // 2, (lat + 1) // 2
+        a, b = vcoord(lo.astype(np.float64), d), vcoord(hi.astype(np.float64), d)
+        # odd lattice coordinate: average of the two bracketing vertices.  (The reference averages 4 vertices for
+        # centre nodes, 0.25*(a+b+c+d); on these uniform lattices that is the same number up to one ulp.)
+        node_pos[:, d] = np.where(lat % 2 == 1, 0.5 * (a + b), a)
+    names = [("left", "right"), ("bottom", "top"), ("back", "front")]
+    boundaries = {}
+    for d in range(dim):
+        boundaries[names[d][0]] = np.nonzero(node_lat[:, d] == 0)[0].astype(np.int64)
+        boundaries[names[d][1]] = np.nonzero(node_lat[:, d] == 2 * N[d])[0].astype(np.int64)
+    return StructuredMesh(dim, N, elem_nodes, node_pos, node_lat, boundaries, "Quad2dC2" if dim == 2 else "Brick3dC2")
+
+
+def RectangularQuadMesh(N=10, size=1.0, lower_left=(0.0, 0.0)) -> StructuredMesh:
+    """Q9 mesh of N[0] x N[1] elements (simplemeshes.py:111)."""
+    N = (N, N) if np.isscalar(N) else tuple(N)
+    size = (size, size) if np.isscalar(size) else tuple(size)
+    return _structured(N, [float(s) for s in size], [float(v) for v in lower_left])
+
+
+def CuboidBrickMesh(N=4, size=1.0, lower_left=(0.0, 0.0, 0.0)) -> StructuredMesh:
+    """Q27 mesh of N[0] x N[1] x N[2] elements (simplemeshes.py:456)."""
+    N = (N, N, N) if np.isscalar(N) else tuple(N)
+    size = (size, size, size) if np.isscalar(size) else tuple(size)
+    return _structured(N, [float(s) for s in size], [float(v) for v in lower_left])
+
+
+@dataclasses.dataclass
+class DofMap:
+    node_eqn: np.ndarray             # [n_node, nval] int32, -1 pinned
+    pos_eqn: Optional[np.ndarray]    # [n_node, dim] int32 or None
+    n_dof: int
+
+
+def assign_equation_numbers(mesh: StructuredMesh, code: FiniteElementCode,
+                            pinned: Optional[Dict[str, Iterable[int]]] = None,
+                            pinned_positions: Optional[Dict[str, Iterable[int]]] = None) -> DofMap:
+    """Global equation numbers in oomph's order (mesh.cc:686-708): node by node; positions first."""
+    nval = code.n_nodal_values
+    n_node, dim = mesh.n_node, mesh.dim
+    free = np.ones((n_node, nval), dtype=bool)
+    vertex = mesh.is_vertex()
+    for f in code.nodal_fields():
+        if f.space == "C1":
+            free[~vertex, f.index] = False     # dummy values on non-vertex nodes (src/elements.cpp:2235-2271)
+    for name, nodes in (pinned or {}).items():
+        free[np.asarray(list(nodes) if not isinstance(nodes, np.ndarray) else nodes, dtype=np.int64), code.fields[name].index] = False
+    if code.coordinates_as_dofs:
+        pfree = np.ones((n_node, dim), dtype=bool)
+        for name, nodes in (pinned_positions or {}).items():
+            d = "xyz".index(name[-1])
+            pfree[np.asarray(list(nodes) if not isinstance(nodes, np.ndarray) else nodes, dtype=np.int64), d] = False
+        allfree = np.concatenate([pfree, free], axis=1)
+    else:
+        pfree = None
+        allfree = free
+    flat = allfree.ravel()
+    eq = np.where(flat, np.cumsum(flat) - 1, -1).astype(np.int32).reshape(allfree.shape)
+    n_dof = int(flat.sum())
+    if pfree is not None:
+        return DofMap(np.ascontiguousarray(eq[:, dim:]), np.ascontiguousarray(eq[:, :dim]), n_dof)
+    return DofMap(np.ascontiguousarray(eq), None, n_dof)
