@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- element residual+Jacobian assemblies/s of the B200 assembly engine (BASELINE.json metric).
+
+One "step" = one full residual+Jacobian assembly (flag 1) of the workload mesh: gather -> generated batched kernels
+(one launch per colour) -> coloured scatter into the fixed CSR pattern.  Pattern/maps/colouring are setup and are
+not timed (DESIGN.md "Measurement"; the reference's Jacobian_setup_time includes its per-assembly pattern build).
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload ns_cavity|heat3d|poisson] [--n SIZE]
+
+Default workload: BASELINE configs[1], 2D Navier-Stokes lid-driven cavity, Taylor-Hood Q9/Q4, 1024x1024 elements.
+--impl reference times the CPU restatement of the reference path (oracle/, all host threads) on a bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "element Jacobian+residual assemblies/sec"
+UNIT = "elements/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(workload, n, seed=0):
+    from problems import smooth_field
+    from pyoomph_b200.codegen import FiniteElementCode
+    from pyoomph_b200.equations import NavierStokesEquations, PoissonEquation, TransientHeatEquation
+    from pyoomph_b200.meshes import CuboidBrickMesh, RectangularQuadMesh, assign_equation_numbers
+    from problems import poisson_source
+    if workload == "ns_cavity":
+        mesh = RectangularQuadMesh(n)
+        code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0), name="ns")
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "right", "bottom", "top")]))
+        pinned = {"velocity_x": wall, "velocity_y": wall, "pressure": np.array([0])}
+        unsteady = False
+        label = "2D Navier-Stokes lid-driven cavity, Taylor-Hood QUAD2, %dx%d elements, steady Newton step" % (n, n)
+    elif workload == "heat3d":
+        mesh = CuboidBrickMesh(n)
+        code = FiniteElementCode("Brick3dC2", TransientHeatEquation(), name="heat3d")
+        pinned = {"u": mesh.boundaries["left"]}
+        unsteady = True
+        label = "3D transient heat, C2 bricks %d^3, BDF2" % n
+    elif workload == "poisson":
+        mesh = RectangularQuadMesh(n)
+        code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")
+        pinned = {"u": np.concatenate([mesh.boundaries["left"], mesh.boundaries["right"]])}
+        unsteady = False
+        label = "2D Poisson QUAD2 %dx%d" % (n, n)
+    else:
+        raise SystemExit("unknown workload " + workload)
+    dofmap = assign_equation_numbers(mesh, code, pinned)
+    T, nval = code.history_levels(), code.n_nodal_values
+    vals = np.zeros((T, mesh.n_node, nval))
+    for t in range(T):
+        for f in range(nval):
+            vals[t, :, f] = smooth_field(mesh.node_pos, f + 3 * t, seed) * (1.0 - 0.05 * t)
+    return dict(kind=workload, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=None, unsteady=unsteady, params={}, label=label)
+
+
+def cpu_run(workload, n_sample, steps, warmup, threads):
+    """Reference path on the host cores: oracle plugin (gcc -O3 -march=native, SystemCCompiler flags) driven by the
+    restated serial element loop + vectors_of_pairs scatter, static element-range split over `threads`."""
+    from problems import make_oracle
+    pb = build_workload(workload, n_sample)
+    op = make_oracle(pb)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        op.assemble(flag=1, nthreads=threads)
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+    ne = pb["mesh"].n_elem
+    op.close()
+    return ne, float(np.mean(times))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="ns_cavity")
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    default_n = {"ns_cavity": 1024, "heat3d": 126, "poisson": 2048}[args.workload]
+    n = args.n or default_n
+    cores = os.cpu_count() or 1
+    sample_n = {"ns_cavity": 160, "heat3d": 14, "poisson": 256}[args.workload]
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ne, sec = cpu_run(args.workload, sample_n, max(1, min(args.steps, 5)), 1, cores)
+        val = ne / sec
+        wl = build_label(args.workload, n)
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl, "sample": "%d elements of the same element class per step" % ne},
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": "%s at %d^%d elements, oracle C plugin gcc -O3 -march=native, %d threads" % (args.workload, sample_n, 3 if args.workload == "heat3d" else 2, cores)},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    from pyoomph_b200.assembly import load_library
+    from problems import make_gpu
+    lib = load_library()
+    lib.pb2_host_alloc.restype = ctypes.c_void_p
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    device = local_rank
+
+    t_setup = time.time()
+    pb = build_workload(args.workload, n)
+    mesh = pb["mesh"]
+    if world > 1:
+        # element-block partition in mesh order (x-strips): contiguous element range per rank
+        lo, hi = mesh.n_elem * rank // world, mesh.n_elem * (rank + 1) // world
+        elements = np.arange(lo, hi)
+    else:
+        elements = None
+    from pyoomph_b200.assembly import B200Assembly
+    asm = B200Assembly(pb["code"], mesh, pb["dofmap"], name=pb["code"].name, device=device, elements=elements)
+    for t in range(pb["vals"].shape[0]):
+        asm.set_nodal_values(t, pb["vals"][t])
+    if pb["unsteady"]:
+        from problems import TIME
+        asm.set_unsteady(TIME["t"], TIME["dt"], TIME["dtprev"], TIME["unsteady_steps_done"])
+    t_setup = time.time() - t_setup
+    n_elem_rank = asm.n_elem
+    info = asm.info
+
+    def barrier():
+        lib.pb2_device_synchronize()
+        if dist is not None:
+            dist.barrier()
+        lib.pb2_device_synchronize()
+
+    # ---- device-resident timing (value)
+    for _ in range(max(3, args.warmup)):
+        asm.assemble(flag=1)
+    barrier()
+    sampler = ClockSampler(device)
+    sampler.start()
+    launches = 0
+    lib.pb2_event_record(0, None)
+    for _ in range(args.steps):
+        asm.assemble(flag=1)
+        launches += asm.launch_count()
+    lib.pb2_event_record(1, None)
+    ms = ctypes.c_float()
+    lib.pb2_event_elapsed_ms(0, 1, ctypes.byref(ms))
+    barrier()
+    clocks = sampler.stop()
+    ms_step = ms.value / args.steps
+    if dist is not None:
+        import torch
+        tt = torch.tensor([ms_step], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_step = float(tt.item())
+    total_elems = mesh.n_elem
+    value = total_elems / (ms_step * 1e-3)
+
+    # ---- end-to-end through the reference-facing call (host buffers, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        eq = pb["dofmap"].node_eqn
+        ndof, nnz = asm.n_dof, asm.nnz
+
+        def pinned(nelem):
+            ptr = lib.pb2_host_alloc(ctypes.c_size_t(nelem * 8))
+            if not ptr:
+                raise RuntimeError("pinned allocation failed")
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(nelem,))
+        h_dofs, h_res, h_jac = pinned(ndof), pinned(ndof), pinned(nnz)
+        h_dofs[:] = 0.0
+        h_dofs[eq[eq >= 0]] = pb["vals"][0][eq >= 0]
+        ksteps = max(1, min(args.steps, 5))
+        asm.assemble_host(h_dofs, 1, out=(h_res, h_jac, None))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            asm.assemble_host(h_dofs, 1, out=(h_res, h_jac, None))
+        barrier()
+        sec = (time.perf_counter() - t0) / ksteps
+        if dist is not None:
+            import torch
+            tt = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sec = float(tt.item())
+        e2e = {"value": total_elems / sec, "unit": UNIT, "h2d_bytes_per_step": int(ndof * 8), "d2h_bytes_per_step": int((ndof + nnz) * 8),
+               "ms_per_step": sec * 1e3, "steps": ksteps}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    b_el = float(info.alg_bytes_per_elem[1])
+    if not pb["unsteady"]:
+        b_el -= float(info.alg_bytes_per_hist_level) * (info.n_hist_val - 1)   # steady: history levels are not read
+    # dominant (only) kernel: the generated ResidualAndJacobian routine, one launch per colour
+    achieved = b_el * n_elem_rank / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "alg_bytes_per_element": b_el, "kernel": "pb2_%s_r0_f1" % pb["code"].name,
+                "launches_per_step": asm.num_launches(), "avg_launch_ms": ms_step / max(1, asm.num_launches())}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": pb["label"], "elements": int(total_elems), "dofs": int(asm.n_dof), "nnz": int(asm.nnz), "ndof_el": int(info.ndof_el),
+                       "colours": asm.num_colours(), "launches_per_step": asm.num_launches(), "cache": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2" % (b_el * n_elem_rank / 1e9),
+                       "setup_s": round(t_setup, 1), "parallelism": "element blocks x%d" % world},
+            "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches)}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        ne, sec = cpu_run(args.workload, sample_n, 2, 1, cores)
+        line["cpu_baseline"] = {"value": ne / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%s at sample size %d (%d elements), oracle C plugin gcc -O3 -march=native, %d threads, 2 assemblies" % (args.workload, sample_n, ne, cores)}
+        ne1, sec1 = cpu_run(args.workload, max(8, sample_n // 3), 1, 0, 1)
+        line["cpu_baseline"]["value_1core"] = ne1 / sec1
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def build_label(workload, n):
+    return {"ns_cavity": "2D Navier-Stokes lid-driven cavity, Taylor-Hood QUAD2, %dx%d elements, steady Newton step" % (n, n),
+            "heat3d": "3D transient heat, C2 bricks %d^3, BDF2" % n, "poisson": "2D Poisson QUAD2 %dx%d" % (n, n)}[workload]
+
+
+if __name__ == "__main__":
+    main()

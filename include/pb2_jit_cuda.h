@@ -1,0 +1,117 @@
+/* pb2_jit_cuda.h -- the GPU extension of pyoomph's generated-code plugin contract.
+ *
+ * pyoomph's CPU plugins export one symbol, JIT_ELEMENT_init(JITFuncSpec_Table_FiniteElement_t*)
+ * (/root/reference/src/jitbridge.h:499, emitted at src/codegen.cpp:6401), which fills a table of
+ * per-element function pointers (ResidualAndJacobian[i], ParameterDerivative[i][p], HessianVectorProduct[i],
+ * jitbridge.h:412,446-451) called once per element by the host (src/elements.cpp:5112).
+ *
+ * A CUDA plugin (compiled by nvcc for sm_100a from the code pyoomph_b200.cuda_emitter writes) exports, next
+ * to that, JIT_ELEMENT_init_cuda(pb2_cuda_table_t*): metadata of the element class plus *batched* launchers
+ * that run one routine over a whole colour of elements.  The per-Gauss-point host callback
+ * fill_shape_buffer_for_point (jitbridge.h:495) does not exist on this path: geometry is computed in-kernel.
+ * Everything is plain C: pointers and sizes only.
+ */
+#ifndef PB2_JIT_CUDA_H
+#define PB2_JIT_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB2_ABI_VERSION 4
+#define PB2_MAX_PARAMS 16
+#define PB2_NTW 7           /* time-stepper storage, MultiTimeStepper (src/timestepper.hpp:37-45) */
+#define PB2_MAX_FIELDS 16
+#define PB2_MAX_ROUTINES 64
+#define PB2_MAX_HVEC 4      /* vectors per Hessian-vector launch */
+
+/* what one launch writes (the `flag` of jitbridge.h:285 routines) */
+#define PB2_FLAG_RESIDUAL 0u
+#define PB2_FLAG_JACOBIAN 1u
+#define PB2_FLAG_MASS 2u
+
+/* residual position map encoding: >=0 accumulate at that position, <0 (but not SKIP) first touch: store at ~v */
+#define PB2_MAP_SKIP (-2147483647 - 1)
+
+/* time information = what prepare_shape_buffer_for_integration copies per element (src/elements.cpp:4577-4646);
+ * here it is one constant block per launch.  The *_degr aliases are resolved by the host. */
+typedef struct pb2_time_info
+{
+  double t[PB2_NTW], dt[PB2_NTW];
+  double w_dt_BDF1[PB2_NTW], w_dt_BDF2[PB2_NTW], w_dt_Newmark2[PB2_NTW], w_d2t_Newmark2[PB2_NTW];
+  double w_dt_BDF2_degr[PB2_NTW], w_dt_Newmark2_degr[PB2_NTW];
+  int ntstorage; /* 0 when steady: history sums are skipped (src/elements.cpp:4585) */
+  int pad_;
+} pb2_time_info;
+
+/* kernel argument block, passed by value (lands in the constant bank) */
+typedef struct pb2_kernel_args
+{
+  int n_elem;                 /* elements of this launch (one colour) */
+  int elem_begin;             /* first element of the launch in the colour-major element arrays */
+  const int *elem_nodes;      /* [n_elem_total][nnode]            element -> node, oomph local order */
+  const int *elem_eqn;        /* [n_elem_total][ndof_el]          local dof -> global equation, <0 pinned */
+  const int *elem_rowstart;   /* [n_elem_total][ndof_el]          CSR position of the first entry of each local row, <0 pinned */
+  const void *elem_off;       /* [n_elem_total][ndof_el*ndof_el]  (row,col) -> offset in that row | first-touch bit; all ones: skip */
+  int map_bits, pad0_;        /* 8 or 16 bits per elem_off entry */
+  const int *elem_res;        /* [n_elem_total][ndof_el]          residual position, same encoding */
+  const double *node_pos;     /* [n_hist_pos][n_node][dim] */
+  const double *node_lagr;    /* [n_node][dim] */
+  const double *node_val;     /* [n_hist_val][n_node][nval] */
+  long long n_node;
+  int n_hist_val, n_hist_pos;
+  double *residual;           /* [n_dof] */
+  double *jac_vals;           /* [nnz] */
+  double *mass_vals;          /* [nnz] */
+  const double *hvec;         /* [n_hvec][n_dof]   Hessian-vector inputs (or NULL) */
+  int n_hvec, pad_;
+  pb2_time_info ti;
+  double params[PB2_MAX_PARAMS]; /* global parameters (jitbridge.h:410) by value */
+} pb2_kernel_args;
+
+typedef struct pb2_class_info
+{
+  int abi_version;
+  char name[64];
+  int nodal_dim, elem_dim;
+  int nnode, nnode_C1;
+  int c1_nodes[8];
+  int n_int_pt;
+  int nval;                        /* nodal values per node (all continuous fields) */
+  int n_fields;
+  char field_names[PB2_MAX_FIELDS][48];
+  int field_space[PB2_MAX_FIELDS]; /* 2: C2, 1: C1 */
+  int field_index[PB2_MAX_FIELDS]; /* index into the nodal value record */
+  int moving_nodes;                /* coordinates are dofs */
+  int ndof_el;                     /* local dofs per element incl. pinned slots */
+  /* local dof layout: for dof k: node (element-local), kind 0: position dim `index`, 1: nodal value `index` */
+  int dof_node[160], dof_kind[160], dof_index[160];
+  int n_residuals;
+  char residual_names[8][48];
+  int n_params;
+  char param_names[PB2_MAX_PARAMS][48];
+  int n_hist_val, n_hist_pos;      /* history levels the kernels read */
+  int max_dt_order;
+  int elems_per_block, threads_per_block, smem_bytes;
+  int hessian_generated;
+  double alg_bytes_per_elem[3];    /* algorithmic bytes per element for flag 0,1,2 */
+  double flops_per_elem[3];        /* fp64 flops per element counted from the emitted code */
+  double alg_bytes_per_hist_level; /* part of alg_bytes per history level beyond the current one (not read when steady) */
+} pb2_class_info;
+
+typedef int (*pb2_launch_fn)(int residual_index, int param_index, unsigned flag, const pb2_kernel_args *args,
+                             void *cuda_stream);
+
+typedef struct pb2_cuda_table
+{
+  pb2_class_info info;
+  pb2_launch_fn launch_rjm;        /* ResidualAndJacobian<i> / dResidual<i>dParameter_<p> (param_index>=0) */
+  pb2_launch_fn launch_hessian;    /* HessianVectorProduct<i>: args->hvec, flag semantics of SURVEY A.5 */
+} pb2_cuda_table_t;
+
+typedef void (*JIT_ELEMENT_init_cuda_SPEC)(pb2_cuda_table_t *table);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,93 @@
+/* pyoomph_b200.h -- C-ABI of the B200 element-assembly engine (libpyoomph_b200.so).
+ *
+ * Plain pointers and sizes only; no C++/torch types.  Each entry point cites the reference interface it
+ * replaces (paths relative to /root/reference).  Every function returns 0 on success, non-zero on error with a
+ * message retrievable through pb2_last_error(); nothing falls back to the CPU.
+ *
+ * Call sequence (mirrors Problem.initialise -> assign equation numbers -> get_jacobian):
+ *   pb2_class_load        <- DynamicBulkElementCode ctor + CCompiler::get_init_func   src/problem.cpp:101-142, src/ccompiler.cpp:191-243
+ *   pb2_problem_create    <- fill_element_info + assign_eqn_numbers consumers         src/elements.cpp:2713, oomph mesh.cc:686
+ *   pb2_problem_set_*     <- nodal Data values / positions / history, Time, global parameters
+ *   pb2_problem_assemble  <- Problem::get_jacobian / get_residuals                    src/problem.cpp:902-968 -> oomph problem.cc:5332-5666
+ *   pb2_problem_fetch     <- the CSR triple handed to the linear solver               src/pybind/problem.cpp:572-602
+ */
+#ifndef PYOOMPH_B200_H
+#define PYOOMPH_B200_H
+
+#include <stddef.h>
+#include "pb2_jit_cuda.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb2_class pb2_class;
+typedef struct pb2_problem pb2_problem;
+
+/* mesh + numbering of one element class, host arrays (the data fill_element_info reads per element) */
+typedef struct pb2_mesh_desc
+{
+  long long n_elem, n_node;
+  const int *elem_nodes;   /* [n_elem][nnode] global node numbers in oomph local order */
+  const int *node_eqn;     /* [n_node][nval] global equation per nodal value, <0 pinned (Data::eqn_number) */
+  const int *pos_eqn;      /* [n_node][dim] equations of nodal positions (SolidNode), NULL if mesh is fixed */
+  long long n_dof;         /* global number of equations */
+  /* multi-GPU row blocks (oomph LinearAlgebraDistribution, problem.cc:6543): this rank assembles the given elements
+   * and owns rows [row_begin,row_end); pass 0,n_dof for a single GPU */
+  long long row_begin, row_end;
+} pb2_mesh_desc;
+
+int pb2_version(void);
+const char *pb2_last_error(void);
+
+/* load a compiled CUDA plugin (.so exporting JIT_ELEMENT_init_cuda).  Replaces dlopen+dlsym("JIT_ELEMENT_init")
+ * of src/ccompiler.cpp:191-243. */
+int pb2_class_load(const char *so_path, pb2_class **out);
+int pb2_class_get_info(const pb2_class *cls, pb2_class_info *out);
+void pb2_class_free(pb2_class *cls);
+
+/* build colouring, the fixed CSR pattern (columns ascending per row, like the "maps" assembly of
+ * src/problem.cpp:2200-2274) and the element->CSR position maps; upload everything to `device`. */
+int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_desc *mesh, pb2_problem **out);
+void pb2_problem_free(pb2_problem *p);
+
+/* pattern of the assembled matrix (host memory owned by the problem): CRDoubleMatrix row_start/column_index */
+int pb2_problem_pattern(pb2_problem *p, const int **row_start, const int **column_index, long long *nnz, long long *n_rows);
+int pb2_problem_num_colours(pb2_problem *p);
+int pb2_problem_num_launches(pb2_problem *p); /* kernel launches per assembly: chunks x colours */
+
+/* nodal data, host -> device.  t = history index (0 current). */
+int pb2_problem_set_nodal_values(pb2_problem *p, int t, const double *values /*[n_node][nval]*/);
+int pb2_problem_set_nodal_positions(pb2_problem *p, int t, const double *pos /*[n_node][dim]*/);
+int pb2_problem_set_lagrangian_positions(pb2_problem *p, const double *pos /*[n_node][dim]*/);
+/* Problem::set_dofs equivalent: scatter a global dof vector (host) into current nodal values / positions on the device */
+int pb2_problem_set_dofs(pb2_problem *p, const double *dofs /*[n_dof]*/);
+int pb2_problem_set_time(pb2_problem *p, const pb2_time_info *ti);
+int pb2_problem_set_parameters(pb2_problem *p, const double *values, int n);
+
+/* one assembly on the device; results stay in HBM.  flag: 0 residual, 1 +Jacobian, 2 +mass matrix (jitbridge.h:285).
+ * param_index >= 0 selects dResidual<i>dParameter_<p>.  `cuda_stream` may be NULL (default stream). */
+int pb2_problem_assemble(pb2_problem *p, int residual_index, int param_index, unsigned flag, void *cuda_stream);
+/* device pointers of the outputs (for GPU-side consumers) */
+int pb2_problem_device_outputs(pb2_problem *p, double **residual, double **jac_vals, double **mass_vals);
+/* copy results to host buffers (any may be NULL) */
+int pb2_problem_fetch(pb2_problem *p, double *residual, double *jac_vals, double *mass_vals);
+/* the reference-facing call: host dofs in, host residual/CSR values out, copies included */
+int pb2_problem_assemble_host(pb2_problem *p, int residual_index, int param_index, unsigned flag, const double *dofs,
+                              double *residual, double *jac_vals, double *mass_vals);
+/* number of kernel launches issued by the last assemble, and cumulative */
+long long pb2_problem_launch_count(pb2_problem *p);
+
+/* utilities for hosts without CUDA bindings of their own: pinned host buffers, event timing on a stream */
+void *pb2_host_alloc(size_t nbytes);
+void pb2_host_free(void *ptr);
+int pb2_event_record(int idx, void *cuda_stream);
+int pb2_event_elapsed_ms(int idx0, int idx1, float *ms);
+int pb2_device_synchronize(void);
+int pb2_device_count(int *n);
+int pb2_flush_l2(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

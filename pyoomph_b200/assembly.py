@@ -1,0 +1,298 @@
+"""Host-side assembler: the Python mirror of the reference interfaces for the assembly hot path.
+
+``B200Assembly`` implements the contract of pyoomph's ``CustomAssemblyBase``
+(/root/reference/pyoomph/generic/assembly.py:36-86): ``get_residuals_and_jacobian(require_jacobian, dparameter)``
+returns a float64 residual and a CSR matrix with int32 ``indptr``/``indices`` and float64 ``data``, which is exactly
+what ``Problem.get_custom_residuals_jacobian`` (pyoomph/generic/problem.py:1727-1745) hands to
+``CRDoubleMatrix::build`` (src/problem.cpp:965); ``invalidate_cache`` etc. keep their meaning.  Everything numeric
+happens in libpyoomph_b200.so through the C-ABI of include/pyoomph_b200.h; this module only marshals arrays.
+The library and the CUDA plugin are mandatory: a missing build raises, nothing is computed on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .ccompiler import BaseCCompiler, CudaCCompiler, build_core_library, get_ccompiler
+from .codegen import FiniteElementCode
+from .cuda_emitter import CudaEmitter
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PB2_NTW = 7
+PB2_MAX_PARAMS = 16
+PB2_MAX_FIELDS = 16
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+
+class TimeInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double * PB2_NTW) for n in
+                ("t", "dt", "w_dt_BDF1", "w_dt_BDF2", "w_dt_Newmark2", "w_d2t_Newmark2", "w_dt_BDF2_degr", "w_dt_Newmark2_degr")] + \
+               [("ntstorage", ctypes.c_int), ("pad_", ctypes.c_int)]
+
+
+class ClassInfo(ctypes.Structure):
+    _fields_ = [
+        ("abi_version", ctypes.c_int), ("name", ctypes.c_char * 64),
+        ("nodal_dim", ctypes.c_int), ("elem_dim", ctypes.c_int), ("nnode", ctypes.c_int), ("nnode_C1", ctypes.c_int),
+        ("c1_nodes", ctypes.c_int * 8), ("n_int_pt", ctypes.c_int), ("nval", ctypes.c_int), ("n_fields", ctypes.c_int),
+        ("field_names", (ctypes.c_char * 48) * PB2_MAX_FIELDS), ("field_space", ctypes.c_int * PB2_MAX_FIELDS),
+        ("field_index", ctypes.c_int * PB2_MAX_FIELDS), ("moving_nodes", ctypes.c_int), ("ndof_el", ctypes.c_int),
+        ("dof_node", ctypes.c_int * 160), ("dof_kind", ctypes.c_int * 160), ("dof_index", ctypes.c_int * 160),
+        ("n_residuals", ctypes.c_int), ("residual_names", (ctypes.c_char * 48) * 8),
+        ("n_params", ctypes.c_int), ("param_names", (ctypes.c_char * 48) * PB2_MAX_PARAMS),
+        ("n_hist_val", ctypes.c_int), ("n_hist_pos", ctypes.c_int), ("max_dt_order", ctypes.c_int),
+        ("elems_per_block", ctypes.c_int), ("threads_per_block", ctypes.c_int), ("smem_bytes", ctypes.c_int),
+        ("hessian_generated", ctypes.c_int),
+        ("alg_bytes_per_elem", ctypes.c_double * 3), ("flops_per_elem", ctypes.c_double * 3),
+        ("alg_bytes_per_hist_level", ctypes.c_double),
+    ]
+
+
+class MeshDesc(ctypes.Structure):
+    _fields_ = [("n_elem", ctypes.c_longlong), ("n_node", ctypes.c_longlong), ("elem_nodes", c_int_p),
+                ("node_eqn", c_int_p), ("pos_eqn", c_int_p), ("n_dof", ctypes.c_longlong),
+                ("row_begin", ctypes.c_longlong), ("row_end", ctypes.c_longlong)]
+
+
+_LIB = None
+
+
+def load_library() -> ctypes.CDLL:
+    """Load libpyoomph_b200.so (built in-tree by __graft_entry__.build / ccompiler.build_core_library)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = os.path.join(HERE, "libpyoomph_b200.so")
+    if not os.path.exists(path):
+        raise RuntimeError("libpyoomph_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+    L = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+    L.pb2_last_error.restype = ctypes.c_char_p
+    L.pb2_problem_launch_count.restype = ctypes.c_longlong
+    for fn in ("pb2_class_load", "pb2_class_get_info", "pb2_problem_create", "pb2_problem_pattern", "pb2_problem_set_nodal_values",
+               "pb2_problem_set_nodal_positions", "pb2_problem_set_lagrangian_positions", "pb2_problem_set_dofs",
+               "pb2_problem_set_time", "pb2_problem_set_parameters", "pb2_problem_assemble", "pb2_problem_device_outputs",
+               "pb2_problem_fetch", "pb2_problem_assemble_host", "pb2_problem_num_colours", "pb2_version"):
+        getattr(L, fn).restype = ctypes.c_int
+    _LIB = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise RuntimeError("pyoomph_b200: " + load_library().pb2_last_error().decode())
+
+
+def bdf_weights(dt: float, dtprev: float):
+    """MultiTimeStepper::set_weights, BDF part (/root/reference/src/timestepper.cpp:31-59)."""
+    w1, w2 = np.zeros(PB2_NTW), np.zeros(PB2_NTW)
+    w2[0] = 1.0 / dt + 1.0 / (dt + dtprev)
+    w2[1] = -(dt + dtprev) / (dt * dtprev)
+    w2[2] = dt / ((dt + dtprev) * dtprev)
+    w1[0] = 1.0 / dt
+    w1[1] = -1.0 / dt
+    return w1, w2
+
+
+class CustomAssemblyBase:
+    """Interface of pyoomph/generic/assembly.py:36 (hooks kept so that Problem.set_custom_assembler accepts it)."""
+
+    def __init__(self) -> None:
+        self.problem = None
+
+    def _set_problem(self, problem):
+        self.problem = problem
+
+    def has_custom_solve_routine(self) -> bool:
+        return False
+
+    def invalidate_cache(self) -> None:
+        pass
+
+    def actions_after_adapt(self) -> None:
+        self.invalidate_cache()
+
+    def actions_after_remeshing(self) -> None:
+        self.invalidate_cache()
+
+    def actions_after_equation_numbering(self) -> None:
+        self.invalidate_cache()
+
+    def actions_after_setting_initial_condition(self) -> None:
+        self.invalidate_cache()
+
+    def actions_after_successful_newton_solve(self) -> None:
+        pass
+
+    def initialize(self) -> None:
+        pass
+
+    def finalize(self) -> None:
+        pass
+
+    def get_residuals_and_jacobian(self, require_jacobian: bool, dparameter: Optional[str] = None):
+        raise RuntimeError("Must be implemented")
+
+
+class B200Assembly(CustomAssemblyBase):
+    """One element class on one mesh, assembled on one B200."""
+
+    def __init__(self, code: FiniteElementCode, mesh, dofmap, *, name: str = "elem", device: int = 0,
+                 compiler: Optional[CudaCCompiler] = None, emitter_options: Optional[dict] = None,
+                 elements: Optional[np.ndarray] = None):
+        super().__init__()
+        self.code, self.mesh, self.dofmap = code, mesh, dofmap
+        self.lib = load_library()
+        self.compiler = compiler or get_ccompiler("cuda")
+        self.emitter = CudaEmitter(code, name, **(emitter_options or {}))
+        self.plugin_path = self.compiler.compile_code(self.emitter.emit(), name)
+        self.cls = ctypes.c_void_p()
+        _check(self.lib.pb2_class_load(self.plugin_path.encode(), ctypes.byref(self.cls)))
+        self.info = ClassInfo()
+        _check(self.lib.pb2_class_get_info(self.cls, ctypes.byref(self.info)))
+        en = mesh.elem_nodes if elements is None else mesh.elem_nodes[elements]
+        self._elem_nodes = np.ascontiguousarray(en, dtype=np.int32)
+        self._node_eqn = np.ascontiguousarray(dofmap.node_eqn, dtype=np.int32)
+        self._pos_eqn = None if dofmap.pos_eqn is None else np.ascontiguousarray(dofmap.pos_eqn, dtype=np.int32)
+        md = MeshDesc(self._elem_nodes.shape[0], mesh.n_node, self._elem_nodes.ctypes.data_as(c_int_p),
+                      self._node_eqn.ctypes.data_as(c_int_p),
+                      None if self._pos_eqn is None else self._pos_eqn.ctypes.data_as(c_int_p), dofmap.n_dof, 0, dofmap.n_dof)
+        self.prob = ctypes.c_void_p()
+        _check(self.lib.pb2_problem_create(self.cls, device, ctypes.byref(md), ctypes.byref(self.prob)))
+        rs, ci = c_int_p(), c_int_p()
+        nnz, nrows = ctypes.c_longlong(), ctypes.c_longlong()
+        _check(self.lib.pb2_problem_pattern(self.prob, ctypes.byref(rs), ctypes.byref(ci), ctypes.byref(nnz), ctypes.byref(nrows)))
+        self.n_dof, self.nnz = int(nrows.value), int(nnz.value)
+        self.indptr = np.ctypeslib.as_array(rs, shape=(self.n_dof + 1,))
+        self.indices = np.ctypeslib.as_array(ci, shape=(max(self.nnz, 1),))[:self.nnz]
+        self.n_elem = self._elem_nodes.shape[0]
+        self.param_names = [self.info.param_names[i].value.decode() for i in range(self.info.n_params)]
+        self.residual_names = [self.info.residual_names[i].value.decode() for i in range(self.info.n_residuals)]
+        self._params = np.zeros(max(1, self.info.n_params))
+        self.set_nodal_positions(0, mesh.node_pos)
+        for t in range(1, self.info.n_hist_pos):
+            self.set_nodal_positions(t, mesh.node_pos)
+        self.set_lagrangian_positions(mesh.node_pos)
+        self.set_steady()
+        self._last_flag = -1
+
+    # ---- data ---------------------------------------------------------------------------------
+    @staticmethod
+    def _dp(a):
+        return a.ctypes.data_as(c_double_p)
+
+    def set_nodal_values(self, t: int, values: np.ndarray):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert v.shape == (self.mesh.n_node, self.info.nval)
+        _check(self.lib.pb2_problem_set_nodal_values(self.prob, t, self._dp(v)))
+
+    def set_nodal_positions(self, t: int, pos: np.ndarray):
+        v = np.ascontiguousarray(pos, dtype=np.float64)
+        _check(self.lib.pb2_problem_set_nodal_positions(self.prob, t, self._dp(v)))
+
+    def set_lagrangian_positions(self, pos: np.ndarray):
+        v = np.ascontiguousarray(pos, dtype=np.float64)
+        _check(self.lib.pb2_problem_set_lagrangian_positions(self.prob, self._dp(v)))
+
+    def set_dofs(self, dofs: np.ndarray):
+        v = np.ascontiguousarray(dofs, dtype=np.float64)
+        assert v.shape == (self.n_dof,)
+        _check(self.lib.pb2_problem_set_dofs(self.prob, self._dp(v)))
+
+    def set_parameters(self, **values: float):
+        for k, v in values.items():
+            self._params[self.param_names.index(k)] = v
+        _check(self.lib.pb2_problem_set_parameters(self.prob, self._dp(self._params), self.info.n_params))
+
+    def set_steady(self):
+        """oomph steady solve: all time weights zero, ntstorage 0 (src/elements.cpp:4583-4596)."""
+        self.ti = TimeInfo()
+        _check(self.lib.pb2_problem_set_time(self.prob, ctypes.byref(self.ti)))
+
+    def set_unsteady(self, t: float, dt: float, dtprev: float, unsteady_steps_done: int, ntstorage: int = 3):
+        """BDF weights + the _degr selection rule of prepare_shape_buffer_for_integration (src/elements.cpp:4611-4626)."""
+        ti = TimeInfo()
+        w1, w2 = bdf_weights(dt, dtprev)
+        ti.t[0], ti.t[1], ti.t[2] = t, t - dt, t - dt - dtprev
+        ti.dt[0], ti.dt[1] = dt, dtprev
+        for i in range(PB2_NTW):
+            ti.w_dt_BDF1[i], ti.w_dt_BDF2[i] = w1[i], w2[i]
+            degr = w1[i] if unsteady_steps_done == 0 else w2[i]
+            ti.w_dt_BDF2_degr[i] = degr
+            ti.w_dt_Newmark2_degr[i] = degr if unsteady_steps_done <= 4 else ti.w_dt_Newmark2[i]
+        ti.ntstorage = ntstorage
+        self.ti = ti
+        _check(self.lib.pb2_problem_set_time(self.prob, ctypes.byref(ti)))
+
+    # ---- assembly -----------------------------------------------------------------------------
+    def assemble(self, flag: int = 1, residual: str = "", parameter: Optional[str] = None, stream: int = 0):
+        """Device-resident assembly (results stay in HBM); use fetch() or device_outputs()."""
+        ri = self.residual_names.index(residual)
+        pi = -1 if parameter is None else self.param_names.index(parameter)
+        _check(self.lib.pb2_problem_assemble(self.prob, ri, pi, flag, ctypes.c_void_p(stream)))
+        self._last_flag = flag
+
+    def fetch(self, want_jacobian: bool = True, want_mass: bool = False):
+        res = np.empty(self.n_dof)
+        jac = np.empty(self.nnz) if want_jacobian else None
+        mass = np.empty(self.nnz) if want_mass else None
+        _check(self.lib.pb2_problem_fetch(self.prob, self._dp(res), None if jac is None else self._dp(jac),
+                                          None if mass is None else self._dp(mass)))
+        return res, jac, mass
+
+    def assemble_host(self, dofs: Optional[np.ndarray], flag: int = 1, residual: str = "", parameter: Optional[str] = None,
+                      out: Optional[Tuple[np.ndarray, Optional[np.ndarray], Optional[np.ndarray]]] = None):
+        """The reference-facing call: host dof vector in, host residual / CSR values out (copies included)."""
+        ri = self.residual_names.index(residual)
+        pi = -1 if parameter is None else self.param_names.index(parameter)
+        if out is None:
+            out = (np.empty(self.n_dof), np.empty(self.nnz) if flag >= 1 else None, np.empty(self.nnz) if flag >= 2 else None)
+        res, jac, mass = out
+        d = None if dofs is None else self._dp(np.ascontiguousarray(dofs, dtype=np.float64))
+        _check(self.lib.pb2_problem_assemble_host(self.prob, ri, pi, flag, d, self._dp(res),
+                                                  None if jac is None else self._dp(jac), None if mass is None else self._dp(mass)))
+        return out
+
+    def device_outputs(self):
+        r, j, m = c_double_p(), c_double_p(), c_double_p()
+        _check(self.lib.pb2_problem_device_outputs(self.prob, ctypes.byref(r), ctypes.byref(j), ctypes.byref(m)))
+        return (ctypes.cast(r, ctypes.c_void_p).value, ctypes.cast(j, ctypes.c_void_p).value, ctypes.cast(m, ctypes.c_void_p).value)
+
+    def launch_count(self) -> int:
+        return int(self.lib.pb2_problem_launch_count(self.prob))
+
+    def num_colours(self) -> int:
+        return int(self.lib.pb2_problem_num_colours(self.prob))
+
+    def num_launches(self) -> int:
+        """kernel launches per assembly = element chunks x colours"""
+        return int(self.lib.pb2_problem_num_launches(self.prob))
+
+    # ---- CustomAssemblyBase contract -----------------------------------------------------------
+    def get_residuals_and_jacobian(self, require_jacobian: bool, dparameter: Optional[str] = None):
+        if require_jacobian:
+            if dparameter:
+                raise RuntimeError("Cannot derive custom Jacobian with respect to a parameter yet")  # problem.py:1733
+            res, jac, _ = self.assemble_host(None, 1)
+            from scipy.sparse import csr_matrix
+            return res, csr_matrix((jac, self.indices, self.indptr), shape=(self.n_dof, self.n_dof))
+        res, _, _ = self.assemble_host(None, 0, parameter=dparameter)
+        return res
+
+    def close(self):
+        if getattr(self, "prob", None):
+            self.lib.pb2_problem_free(self.prob)
+            self.prob = None
+        if getattr(self, "cls", None):
+            self.lib.pb2_class_free(self.cls)
+            self.cls = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

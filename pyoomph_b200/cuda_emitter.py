@@ -1,0 +1,890 @@
+"""CUDA emission backend: element-class code model -> one .cu file of batched sm_100a kernels.
+
+This is the counterpart of ``FiniteElementCode::write_code`` (/root/reference/src/codegen.cpp:4684) and
+``write_generic_RJM`` (:3912) for the GPU.  Where the reference emits, per (test field, unknown field), one big
+expression evaluated inside ``for l_test { for l_shape {...} }`` with a host callback per Gauss point
+(src/codegen.cpp:3207-3238 -> src/elements.cpp:3593), this backend emits per routine ONE kernel with three
+phases per batch of elements (DESIGN.md "Kernel"):
+
+  phase 0  gather      element nodes -> shared memory (positions, nodal values, BDF/Newmark time combinations)
+  phase 1  points      one thread per (element, Gauss point): geometry (the restatement of
+                       fill_shape_info_at_s), field interpolation, and the problem-specific straight-line code
+                       for the pointwise coefficients R_s, C_{s,(G,a)} (sympy CSE of ResidualForm)
+  phase 2  contract    one thread per (element, test node, field group): register-tiled
+                       J[row][col] += T_b[l_test] * C * S_a[l_shape] with reference-element shape tables read
+                       from the constant bank, then a coloured, first-touch-aware scatter through the
+                       element -> CSR position map.
+
+No tensor cores: per-element work is small irregular fp64 contraction (BASELINE north_star).
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Dict, List, Optional, Tuple
+
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+
+from . import expressions as ex
+from .codegen import AtomInfo, FiniteElementCode, ResidualForm, TestSlot
+
+K3 = 0.774596669241483
+K3T = 0.774596662941483   # sic: oomph-lib integral.cc:87-93 (mistyped literal, kept for parity)
+K33 = 0.77459666924148
+
+
+def gauss_rule(dim: int):
+    """Literal oomph tables Gauss<2,3> (integral.cc:84-102) and Gauss<3,3> (:169-207)."""
+    if dim == 2:
+        kn = [(-K3, -K3), (-K3, 0.0), (-K3, K3T), (0.0, -K3), (0.0, 0.0), (0.0, K3T), (K3T, -K3), (K3T, 0.0), (K3T, K3T)]
+        w = [25.0 / 81.0, 40.0 / 81.0, 25.0 / 81.0, 40.0 / 81.0, 64.0 / 81.0, 40.0 / 81.0, 25.0 / 81.0, 40.0 / 81.0, 25.0 / 81.0]
+        return kn, w
+    k = [-K33, 0.0, K33]
+    kn = [(k[i], k[j], k[l]) for i in range(3) for j in range(3) for l in range(3)]
+    wa, wb, wc, wd = 0.17146776406035, 0.27434842249657, 0.43895747599451, 0.70233196159122
+    w1 = {0: 0, 1: 1, 2: 0}
+    w = []
+    for i in range(3):
+        for j in range(3):
+            for l in range(3):
+                w.append([wa, wb, wc, wd][w1[i] + w1[j] + w1[l]])
+    return kn, w
+
+
+def _lag(order: int, s: float):
+    # oomph-lib shape.h:604-650, same operation order
+    if order == 3:
+        return [0.5 * s * (s - 1.0), 1.0 - s * s, 0.5 * s * (s + 1.0)], [s - 0.5, -2.0 * s, s + 0.5]
+    return [0.5 * (1.0 - s), 0.5 * (1.0 + s)], [-0.5, 0.5]
+
+
+def shape_tables(dim: int, order: int, knots):
+    """psi[ipt][l], dpsi[ipt][l][b] in oomph's tensor-product order (Qelements.cc:348-377, :621-660)."""
+    psi, dpsi = [], []
+    for s in knots:
+        P, D = zip(*[_lag(order, s[a]) for a in range(dim)])
+        ps, ds = [], []
+        if dim == 2:
+            for i in range(order):
+                for j in range(order):
+                    ds.append((P[1][i] * D[0][j], D[1][i] * P[0][j]))
+                    ps.append(P[1][i] * P[0][j])
+        else:
+            for i in range(order):
+                for j in range(order):
+                    for k in range(order):
+                        ds.append((P[2][i] * P[1][j] * D[0][k], P[2][i] * D[1][j] * P[0][k], D[2][i] * P[1][j] * P[0][k]))
+                        ps.append(P[2][i] * P[1][j] * P[0][k])
+        psi.append(ps)
+        dpsi.append(ds)
+    return psi, dpsi
+
+
+class _CudaPrinter(C99CodePrinter):
+    def __init__(self, names):
+        super().__init__({"precision": 17})
+        self.names = names
+
+    def _print_Symbol(self, e):
+        return self.names.get(e, e.name)
+
+    def _print_Float(self, e):
+        return repr(float(e))
+
+    def _print_Rational(self, e):
+        return "(%d.0/%d.0)" % (e.p, e.q)
+
+    def _print_Integer(self, e):
+        return "%d.0" % int(e)
+
+    def _print_Pow(self, e):
+        if e.exp.is_Integer:
+            n = int(e.exp)
+            b = self.parenthesize(e.base, sp.printing.precedence.PRECEDENCE["Mul"])
+            if 1 < abs(n) <= 4:
+                s = "*".join([b] * abs(n))
+                return "(%s)" % s if n > 0 else "(1.0/(%s))" % s
+            if n == -1:
+                return "(1.0/%s)" % b
+            return "pow(%s,%d.0)" % (self._print(e.base), n)
+        return super()._print_Pow(e)
+
+
+@dataclasses.dataclass
+class RowGroup:
+    space: str
+    fields: List[str]
+    rows_per_thread: int
+    threads_per_elem: int
+    thread_off: int = 0      # first thread of the group in the block
+    nthreads: int = 0        # threads reserved (warp padded)
+
+
+@dataclasses.dataclass
+class RoutinePlan:
+    key: str                 # C identifier suffix
+    form: ResidualForm
+    res_index: int
+    param_index: int
+
+
+class CudaEmitter:
+    def __init__(self, code: FiniteElementCode, name: str = "elem", *, elems_per_block: Optional[int] = None,
+                 acc_max: int = 96, ipt_unroll: Optional[int] = None, table_source: Optional[str] = None):
+        self.code = code
+        self.name = name
+        self.et = code.etype
+        self.dim = code.nodal_dim
+        self.NN = self.et.nnode
+        self.NN1 = self.et.nnode_C1
+        self.NIPT = self.et.n_int_pt
+        self.layout = code.dof_layout()                      # [(field, space-local node)]
+        self.ndof = len(self.layout)
+        self.nval = code.n_nodal_values
+        import os
+        self.acc_max = int(os.environ.get("PB2_ACC_MAX", acc_max))
+        if elems_per_block is None and os.environ.get("PB2_EPB"):
+            elems_per_block = int(os.environ["PB2_EPB"])
+        self.min_blocks = int(os.environ.get("PB2_MINBLOCKS", "2" if self.dim == 2 else "1"))
+        self.table_source = table_source or ("const" if self.dim == 2 else "smem")
+        self.ipt_unroll = ipt_unroll if ipt_unroll is not None else (self.NIPT if self.dim == 2 else 1)
+        self.routines: List[RoutinePlan] = []
+        for i, rn in enumerate(code.residual_names()):
+            self.routines.append(RoutinePlan("r%d" % i, code.derive(rn), i, -1))
+            for k, p in enumerate(code.global_params):
+                self.routines.append(RoutinePlan("r%d_dp%d" % (i, k), code.derive(rn, p), i, k))
+        self.T_val = code.history_levels()
+        self.T_pos = self.T_val if code.coordinates_as_dofs else 1
+        self._plan_groups()
+        self.EPB = elems_per_block or self._default_epb()
+        self._layout_threads()
+
+    # ------------------------------------------------------------------ planning
+    def _col_index(self, field: str, lnode: int) -> int:
+        return self.layout.index((field, lnode))
+
+    def _nnode_space(self, space: str) -> int:
+        return self.NN if space in ("C2", "Pos") else self.NN1
+
+    def _plan_groups(self):
+        code = self.code
+        by_space: Dict[str, List[str]] = {}
+        for f in code.unknown_field_names():
+            by_space.setdefault(code.fields[f].space, []).append(f)
+        groups: List[RowGroup] = []
+        for space, fl in by_space.items():
+            nn = self._nnode_space(space)
+            # rows per thread: whole fields per group; RB>1 only for 3D single-field groups
+            per_field = self.ndof
+            maxf = max(1, self.acc_max // per_field)
+            for i in range(0, len(fl), maxf):
+                chunk = fl[i:i + maxf]
+                rb = 1
+                if self.dim == 3:
+                    for cand in (3,):
+                        if nn % cand == 0 and cand * len(chunk) * per_field <= self.acc_max:
+                            rb = cand
+                groups.append(RowGroup(space, chunk, rb, nn // rb))
+        self.groups = groups
+
+    def _default_epb(self) -> int:
+        tpe = sum(g.threads_per_elem for g in self.groups)
+        target_threads = 182 if self.dim == 2 else 192
+        return max(4, target_threads // max(1, tpe))
+
+    def _layout_threads(self):
+        off = 0
+        for g in self.groups:
+            g.thread_off = off
+            g.nthreads = ((self.EPB * g.threads_per_elem + 31) // 32) * 32
+            off += g.nthreads
+        self.NT = max(off, 64)
+
+    # ------------------------------------------------------------------ shared-memory plan of one routine
+    def _plan_smem(self, form: ResidualForm, what: int):
+        """Returns dict with element-local offsets (in doubles)."""
+        code, dim, NN = self.code, self.dim, self.NN
+        need_lagr = form.uses_dX or any(a.deriv.startswith("dX") for a in form.atoms) or \
+            any(k[2].startswith("dX") for k in list(form.J) + list(form.M)) or any(s.deriv.startswith("dX") for s in form.slots)
+        # nodal source arrays: (field, kind) kind = ("cur", past) | ("dt", order, scheme)
+        sources: List[Tuple[str, tuple]] = []
+        for a in form.atoms:
+            if a.field.startswith("lagrangian_"):
+                continue
+            kind = ("dt", a.dt_order, a.scheme) if a.dt_order else ("cur", a.past)
+            if a.field.startswith("coordinate_") and kind == ("cur", 0):
+                continue  # current positions are always staged
+            if (a.field, kind) not in sources:
+                sources.append((a.field, kind))
+        off = 0
+        plan = {"need_lagr": need_lagr, "sources": sources}
+        plan["xpos"] = off
+        off += NN * dim
+        if need_lagr:
+            plan["xlag"] = off
+            off += NN * dim
+        plan["src_off"] = {}
+        for (f, kind) in sources:
+            plan["src_off"][(f, kind)] = off
+            off += self._nnode_space(code.fields[f].space)
+        plan["EL0"] = off
+        # per-point block
+        poff = 0
+        plan["gg"] = poff
+        poff += dim * dim
+        if need_lagr:
+            plan["ggL"] = poff
+            poff += dim * dim
+        ncoef = len(form.slots)
+        jkeys = sorted(form.J.keys()) if what >= 1 else []
+        mkeys = sorted(form.M.keys()) if what >= 2 else []
+        plan["R_off"] = poff
+        plan["J_off"] = {k: poff + ncoef + i for i, k in enumerate(jkeys)}
+        plan["M_off"] = {k: poff + ncoef + len(jkeys) + i for i, k in enumerate(mkeys)}
+        poff += ncoef + len(jkeys) + len(mkeys)
+        plan["PB"] = poff
+        els = plan["EL0"] + self.NIPT * poff
+        nstage = self.ndof * self.ndof + self.ndof if what >= 1 else self.ndof
+        if what >= 2:
+            # the mass pass needs the point data again after the Jacobian pass was staged: no aliasing
+            plan["SJ_off"] = els
+            plan["stage_alias"] = False
+            els += nstage
+        else:
+            plan["SJ_off"] = 0
+            plan["stage_alias"] = True
+            els = max(els, nstage)
+        if els % 2 == 0:
+            els += 1          # odd stride: elements of one warp fall into different banks
+        plan["ELS"] = els
+        return plan
+
+    # ------------------------------------------------------------------ code pieces
+    def _w_name(self, scheme: str, order: int) -> str:
+        return "a.ti.w_%s_%s" % ("dt" if order == 1 else "d2t", scheme)
+
+    def _emit_tables(self, o: List[str]):
+        kn, w = gauss_rule(self.dim)
+        psi2, dpsi2 = shape_tables(self.dim, 3, kn)
+        psi1, dpsi1 = shape_tables(self.dim, 2, kn)
+
+        def arr(vals):
+            return ", ".join(repr(float(v)) for v in vals)
+        o.append("// reference-element tables at the oomph Gauss points (integral.cc literals, shape.h polynomials)")
+        o.append("__constant__ double c_w[%d] = {%s};" % (self.NIPT, arr(w)))
+        o.append("__constant__ double c_psi2[%d] = {%s};" % (self.NIPT * self.NN, arr(v for p in psi2 for v in p)))
+        o.append("__constant__ double c_dpsi2[%d] = {%s};" % (self.NIPT * self.NN * self.dim, arr(v for p in dpsi2 for l in p for v in l)))
+        o.append("__constant__ double c_psi1[%d] = {%s};" % (self.NIPT * self.NN1, arr(v for p in psi1 for v in p)))
+        o.append("__constant__ double c_dpsi1[%d] = {%s};" % (self.NIPT * self.NN1 * self.dim, arr(v for p in dpsi1 for l in p for v in l)))
+        o.append("__device__ const double g_tables[%d] = {%s};" % (self._tables_smem_size(), arr(
+            [v for p in psi2 for v in p] + [v for p in dpsi2 for l in p for v in l] + [v for p in psi1 for v in p] + [v for p in dpsi1 for l in p for v in l])))
+        o.append("__constant__ int c_c1node[%d] = {%s};" % (self.NN1, ", ".join(str(n) for n in self.et.c1_nodes)))
+        # row dof index of (field, space-local node)
+        for f in self.code.unknown_field_names():
+            nn = self._nnode_space(self.code.fields[f].space)
+            o.append("__constant__ int c_row_%s[%d] = {%s};" % (f, nn, ", ".join(str(self._col_index(f, l)) for l in range(nn))))
+        o.append("")
+
+    def _tables_smem_size(self) -> int:
+        """doubles of shape tables staged in shared memory (needed by phase 1 always, phase 2 in smem mode)."""
+        return self.NIPT * (self.NN * (1 + self.dim) + self.NN1 * (1 + self.dim))
+
+    def _emit_kernel(self, o: List[str], rp: RoutinePlan, what: int):
+        code, dim, NN, NN1, NIPT = self.code, self.dim, self.NN, self.NN1, self.NIPT
+        form = rp.form
+        plan = self._plan_smem(form, what)
+        ELS, EL0, PB = plan["ELS"], plan["EL0"], plan["PB"]
+        kname = "pb2_%s_%s_f%d" % (self.name, rp.key, what)
+        tab_n = self._tables_smem_size()
+        smem_doubles = tab_n + self.EPB * ELS
+        ND, ND2 = self.ndof, self.ndof * self.ndof
+        # staged scatter maps: rowstart[EPB][ND] + res[EPB][ND] ints, then the (8|16 bit) offset bytes
+        map_ints = 2 * self.EPB * ND
+        map_bytes = 2 * self.EPB * ND2 if what >= 1 else 0
+        self._kernel_smem[kname] = smem_doubles * 8 + map_ints * 4 + ((map_bytes + 15) // 16) * 16
+        w = o.append
+        T2 = "s_psi2" if self.table_source == "smem" else "c_psi2"
+        w("// %s  what=%d : %d slots, %d Jacobian coefficients, %d mass coefficients, element smem %d doubles" % (
+            form.name or "<default residual>", what, len(form.slots), len(form.J) if what else 0, len(form.M) if what > 1 else 0, ELS))
+        w("extern \"C\" __global__ void __launch_bounds__(%d, %d) %s(const pb2_kernel_args a)" % (self.NT, self.min_blocks, kname))
+        w("{")
+        w("  extern __shared__ double smem[];")
+        w("  double* const s_psi2 = smem;")
+        w("  double* const s_dpsi2 = s_psi2 + %d;" % (NIPT * NN))
+        w("  double* const s_psi1 = s_dpsi2 + %d;" % (NIPT * NN * dim))
+        w("  double* const s_dpsi1 = s_psi1 + %d;" % (NIPT * NN1))
+        w("  double* const s_el = smem + %d;" % tab_n)
+        w("  int* const s_rowstart = (int*)(smem + %d);" % (tab_n + self.EPB * ELS))
+        w("  int* const s_resmap = s_rowstart + %d;" % (self.EPB * self.ndof))
+        w("  unsigned char* const s_map = (unsigned char*)(s_resmap + %d);" % (self.EPB * self.ndof))
+        w("  const int tid = threadIdx.x;")
+        w("  for (int i = tid; i < %d; i += %d) smem[i] = g_tables[i];   // psi2 | dpsi2 | psi1 | dpsi1, once per persistent block" % (tab_n, self.NT))
+        w("  const int nbatch = (a.n_elem + %d - 1) / %d;" % (self.EPB, self.EPB))
+        w("  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x)")
+        w("  {")
+        w("    const int e0 = batch * %d;" % self.EPB)
+        w("    const int nel = min(%d, a.n_elem - e0);" % self.EPB)
+        w("    __syncthreads();")
+        # ---------------- phase 0
+        w("    // ---- phase 0: gather element data (fill_element_info's pointer tables become one staged copy)")
+        w("    for (int i = tid; i < nel * %d; i += %d)" % (NN, self.NT))
+        w("    {")
+        w("      const int el = i / %d, l = i - el * %d;" % (NN, NN))
+        w("      const long long node = a.elem_nodes[(long long)(a.elem_begin + e0 + el) * %d + l];" % NN)
+        w("      double* E = s_el + el * %d;" % ELS)
+        for d in range(dim):
+            w("      E[%d + l * %d + %d] = a.node_pos[node * %d + %d];" % (plan["xpos"], dim, d, dim, d))
+        if plan["need_lagr"]:
+            for d in range(dim):
+                w("      E[%d + l * %d + %d] = a.node_lagr[node * %d + %d];" % (plan["xlag"], dim, d, dim, d))
+        c1_sources = []
+        for (f, kind) in plan["sources"]:
+            fld = code.fields[f]
+            soff = plan["src_off"][(f, kind)]
+            if fld.space == "Pos":
+                dd = ex.DIRS.index(f[-1])
+                base = "a.node_pos"
+                stride, comp, nh = dim, dd, "a.n_hist_pos"
+            else:
+                base = "a.node_val"
+                stride, comp, nh = self.nval, fld.index, "a.n_hist_val"
+            if fld.space == "C1":
+                c1_sources.append((f, kind, soff, base, stride, comp))
+                continue
+            if kind[0] == "cur":
+                w("      E[%d + l] = %s[((long long)%d * a.n_node + node) * %d + %d];" % (soff, base, kind[1], stride, comp))
+            else:
+                wn = self._w_name(kind[2], kind[1])
+                w("      { double s = 0.0; for (int t = 0; t < a.ti.ntstorage; ++t) s += %s[t] * %s[((long long)t * a.n_node + node) * %d + %d]; E[%d + l] = s; }" % (
+                    wn, base, stride, comp, soff))
+        w("    }")
+        if c1_sources:
+            w("    for (int i = tid; i < nel * %d; i += %d)" % (NN1, self.NT))
+            w("    {")
+            w("      const int el = i / %d, l = i - el * %d;" % (NN1, NN1))
+            w("      const long long node = a.elem_nodes[(long long)(a.elem_begin + e0 + el) * %d + c_c1node[l]];" % NN)
+            w("      double* E = s_el + el * %d;" % ELS)
+            for (f, kind, soff, base, stride, comp) in c1_sources:
+                if kind[0] == "cur":
+                    w("      E[%d + l] = %s[((long long)%d * a.n_node + node) * %d + %d];" % (soff, base, kind[1], stride, comp))
+                else:
+                    wn = self._w_name(kind[2], kind[1])
+                    w("      { double s = 0.0; for (int t = 0; t < a.ti.ntstorage; ++t) s += %s[t] * %s[((long long)t * a.n_node + node) * %d + %d]; E[%d + l] = s; }" % (
+                        wn, base, stride, comp, soff))
+            w("    }")
+        w("    // scatter maps of the batch: issued together with the gather, consumed in phase 3 (no dependent global load there)")
+        w("    {")
+        w("      const long long eg0 = (long long)(a.elem_begin + e0);")
+        w("      for (int i = tid; i < nel * %d; i += %d) { s_rowstart[i] = __ldg(a.elem_rowstart + eg0 * %d + i); s_resmap[i] = __ldg(a.elem_res + eg0 * %d + i); }" % (self.ndof, self.NT, self.ndof, self.ndof))
+        if what >= 1:
+            nd2 = self.ndof * self.ndof
+            w("      const int mbytes = nel * %d * (a.map_bits >> 3);" % nd2)
+            w("      const unsigned char* __restrict__ gmap = (const unsigned char*)a.elem_off + eg0 * %d * (a.map_bits >> 3);" % nd2)
+            if nd2 % 4 == 0:
+                w("      for (int i = tid; i < (mbytes >> 2); i += %d) ((unsigned*)s_map)[i] = __ldg((const unsigned*)gmap + i);" % self.NT)
+            else:
+                w("      for (int i = tid; i < mbytes; i += %d) s_map[i] = __ldg(gmap + i);" % self.NT)
+        w("    }")
+        w("    __syncthreads();")
+        # ---------------- phase 1
+        w("    // ---- phase 1: one thread per (element, Gauss point): geometry + interpolation + pointwise coefficients")
+        w("    for (int i = tid; i < nel * %d; i += %d)" % (NIPT, self.NT))
+        w("    {")
+        w("      const int el = i / %d, ipt = i - el * %d;" % (NIPT, NIPT))
+        w("      double* E = s_el + el * %d;" % ELS)
+        w("      double* P = E + %d + ipt * %d;" % (EL0, PB))
+        w("      const double* ps2 = s_psi2 + ipt * %d; const double* dp2 = s_dpsi2 + ipt * %d;" % (NN, NN * dim))
+        w("      const double* ps1 = s_psi1 + ipt * %d; const double* dp1 = s_dpsi1 + ipt * %d;" % (NN1, NN1 * dim))
+        w("      (void)ps1; (void)dp1; (void)ps2;")
+        self._emit_geometry(o, plan, "xpos", "gg", "detE")
+        if plan["need_lagr"]:
+            self._emit_geometry(o, plan, "xlag", "ggL", "detL")
+        w("      const double dx = c_w[ipt] * detE;")
+        if plan["need_lagr"]:
+            w("      const double dX = c_w[ipt] * detL;")
+        # interpolation
+        names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "a.ti.t[0]", ex.pi: "3.14159265359"}
+        for k, p in enumerate(code.global_params):
+            names[code._param_syms[p]] = "a.params[%d]" % k
+        # local-derivative sums per (field, kind)
+        needed: Dict[Tuple[str, tuple], set] = {}
+        for at in form.atoms:
+            kind = ("dt", at.dt_order, at.scheme) if at.dt_order else ("cur", at.past)
+            needed.setdefault((at.field, kind), set()).add(at.deriv)
+        for (f, kind), derivs in needed.items():
+            fld = code.fields[f]
+            nn = self._nnode_space(fld.space)
+            ps, dp = ("ps1", "dp1") if fld.space == "C1" else ("ps2", "dp2")
+            if f.startswith("lagrangian_"):
+                srcexpr = "E[%d + l * %d + %d]" % (plan["xlag"], dim, ex.DIRS.index(f[-1]))
+            elif f.startswith("coordinate_") and kind == ("cur", 0):
+                srcexpr = "E[%d + l * %d + %d]" % (plan["xpos"], dim, ex.DIRS.index(f[-1]))
+            else:
+                srcexpr = "E[%d + l]" % plan["src_off"][(f, kind)]
+            tag = "%s_%s" % (f, "_".join(str(k) for k in kind))
+            want_val = "d0" in derivs
+            want_grad = any(d != "d0" for d in derivs)
+            decl = []
+            if want_val:
+                decl.append("v_%s = 0.0" % tag)
+            if want_grad:
+                decl += ["s%d_%s = 0.0" % (b, tag) for b in range(dim)]
+            w("      double %s;" % ", ".join(decl))
+            w("      #pragma unroll")
+            w("      for (int l = 0; l < %d; ++l) { const double u = %s;" % (nn, srcexpr))
+            if want_val:
+                w("        v_%s += u * %s[l];" % (tag, ps))
+            if want_grad:
+                for b in range(dim):
+                    w("        s%d_%s += u * %s[l * %d + %d];" % (b, tag, dp, dim, b))
+            w("      }")
+            for d in sorted(derivs):
+                at = AtomInfo(f, kind[1] if kind[0] == "dt" else 0, kind[2] if kind[0] == "dt" else "", d, kind[1] if kind[0] == "cur" else 0)
+                sym = code.atom_symbol(at)
+                cn = "A_%s_%s" % (tag, d)
+                names[sym] = cn
+                if d == "d0":
+                    w("      const double %s = v_%s;" % (cn, tag))
+                else:
+                    g = "gg" if d[1] == "x" else "ggL"
+                    i = int(d[2:])
+                    w("      const double %s = %s;" % (cn, " + ".join("%s%d%d * s%d_%s" % (g, b, i, b, tag) for b in range(dim))))
+        for sch in ("BDF1", "BDF2", "Newmark2", "BDF2_degr", "Newmark2_degr"):
+            names[sp.Symbol("W__%s__1" % sch, real=True)] = "a.ti.w_dt_%s[0]" % sch
+        names[sp.Symbol("W__Newmark2__2", real=True)] = "a.ti.w_d2t_Newmark2[0]"
+        # coefficients through CSE
+        exprs, targets = [], []
+        for si, r in enumerate(form.R):
+            exprs.append(r)
+            targets.append(plan["R_off"] + si)
+        if what >= 1:
+            for k in sorted(form.J.keys()):
+                exprs.append(form.J[k])
+                targets.append(plan["J_off"][k])
+        if what >= 2:
+            for k in sorted(form.M.keys()):
+                exprs.append(form.M[k])
+                targets.append(plan["M_off"][k])
+        repl, red = sp.cse(exprs, symbols=sp.numbered_symbols("cse"), optimizations="basic")
+        pr = _CudaPrinter(names)
+        for s, e in repl:
+            w("      const double %s = %s;" % (s.name, pr.doprint(e)))
+        for tgt, e in zip(targets, red):
+            w("      P[%d] = %s;" % (tgt, pr.doprint(e)))
+        self._flops_phase1 = sum(int(sp.count_ops(e)) for _, e in repl) + sum(int(sp.count_ops(e)) for e in red)
+        w("    }")
+        w("    __syncthreads();")
+        # ---------------- phase 2 + 3, once per output matrix ("J": residual + Jacobian, "M": mass matrix)
+        passes = [("J", form.J, plan["J_off"], "a.jac_vals", True)] if what >= 1 else [("R", {}, {}, None, True)]
+        if what >= 2:
+            passes.append(("M", form.M, plan["M_off"], "a.mass_vals", False))
+        nacc = max(self._group_nacc(form, g, coef) for g in self.groups for (_, coef, _, _, _) in passes)
+        w("    double acc[%d];" % max(1, nacc))
+        for pi_, (pname, coef, coff, target, with_res) in enumerate(passes):
+            w("    // ---- phase 2 (%s): register-tiled contraction over (l_test, l_shape)" % pname)
+            for g in self.groups:
+                self._emit_group_compute(o, rp, plan, g, pname, coef, coff, with_res)
+            if plan["stage_alias"]:
+                w("    __syncthreads();   // point data is dead from here on: the staging area aliases it")
+            w("    // ---- phase 3a (%s): element matrices -> shared memory, dense [row][col]" % pname)
+            for g in self.groups:
+                self._emit_group_stage(o, rp, plan, g, pname, coef, with_res, target is not None)
+            w("    __syncthreads();")
+            w("    // ---- phase 3b (%s): cooperative coloured scatter, consecutive threads = consecutive (row,col) entries" % pname)
+            self._emit_scatter(o, plan, target, with_res)
+            if pi_ + 1 < len(passes):
+                w("    __syncthreads();")
+        w("  }")
+        w("}")
+        w("")
+        return kname
+
+    def _emit_geometry(self, o: List[str], plan, src: str, gname: str, detname: str):
+        """Restates fill_shape_info_at_s for el_dim==nodal_dim (src/elements.cpp:3604-3626 tangents, :3677-3703 2D
+        metric/inverse, :3804-3836 3D) with the same operation order; stores gab_gai[b][i] to the point block."""
+        dim, NN = self.dim, self.NN
+        w = o.append
+        t = "t_" + gname
+        w("      double %s;" % ", ".join("%s%d%d = 0.0" % (t, a, i) for a in range(dim) for i in range(dim)))
+        w("      #pragma unroll")
+        w("      for (int l = 0; l < %d; ++l) {" % NN)
+        for i in range(dim):
+            for a in range(dim):
+                w("        %s%d%d += E[%d + l * %d + %d] * dp2[l * %d + %d];" % (t, a, i, plan[src], dim, i, dim, a))
+        w("      }")
+        for al in range(dim):
+            for be in range(dim):
+                terms = ["%s%d%d * %s%d%d" % (t, al, i, t, be, i) for i in range(dim)]
+                # amet += in order i=0.. starting from 0.0
+                w("      const double am_%s%d%d = %s;" % (gname, al, be, " + ".join(terms)))
+        am = lambda a, b: "am_%s%d%d" % (gname, a, b)
+        if dim == 2:
+            w("      const double det_%s = %s * %s - %s * %s;" % (gname, am(0, 0), am(1, 1), am(0, 1), am(1, 0)))
+            up = {(0, 0): "%s / det_%s" % (am(1, 1), gname), (0, 1): "-%s / det_%s" % (am(0, 1), gname),
+                  (1, 0): "-%s / det_%s" % (am(1, 0), gname), (1, 1): "%s / det_%s" % (am(0, 0), gname)}
+        else:
+            w("      const double det_%s = %s * %s * %s + %s * %s * %s + %s * %s * %s - %s * %s * %s - %s * %s * %s - %s * %s * %s;" % (
+                gname, am(0, 0), am(1, 1), am(2, 2), am(0, 1), am(1, 2), am(2, 0), am(0, 2), am(1, 0), am(2, 1),
+                am(0, 0), am(1, 2), am(2, 1), am(0, 1), am(1, 0), am(2, 2), am(0, 2), am(1, 1), am(2, 0)))
+            D = "det_" + gname
+            up = {
+                (0, 0): "(%s * %s - %s * %s) / %s" % (am(1, 1), am(2, 2), am(1, 2), am(2, 1), D),
+                (0, 1): "-(%s * %s - %s * %s) / %s" % (am(0, 1), am(2, 2), am(0, 2), am(2, 1), D),
+                (0, 2): "(%s * %s - %s * %s) / %s" % (am(0, 1), am(1, 2), am(0, 2), am(1, 1), D),
+                (1, 0): "-(%s * %s - %s * %s) / %s" % (am(1, 0), am(2, 2), am(1, 2), am(2, 0), D),
+                (1, 1): "(%s * %s - %s * %s) / %s" % (am(0, 0), am(2, 2), am(0, 2), am(2, 0), D),
+                (1, 2): "-(%s * %s - %s * %s) / %s" % (am(0, 0), am(1, 2), am(0, 2), am(1, 0), D),
+                (2, 0): "(%s * %s - %s * %s) / %s" % (am(1, 0), am(2, 1), am(1, 1), am(2, 0), D),
+                (2, 1): "-(%s * %s - %s * %s) / %s" % (am(0, 0), am(2, 1), am(0, 1), am(2, 0), D),
+                (2, 2): "(%s * %s - %s * %s) / %s" % (am(0, 0), am(1, 1), am(0, 1), am(1, 0), D),
+            }
+        for (al, be), e in up.items():
+            w("      const double up_%s%d%d = %s;" % (gname, al, be, e))
+        for b in range(dim):
+            for i in range(dim):
+                w("      const double %s%d%d = %s;" % (gname, b, i, " + ".join("up_%s%d%d * %s%d%d" % (gname, a_, b, t, a_, i) for a_ in range(dim))))
+                w("      P[%d] = %s%d%d;" % (plan[gname] + b * dim + i, gname, b, i))
+        w("      const double %s = sqrt(det_%s);" % (detname, gname))
+
+    def _group_pairs(self, form: ResidualForm, g: RowGroup, coef):
+        fields = [f for f in g.fields if any(s.field == f for s in form.slots)]
+        pairs: Dict[Tuple[str, str], List[Tuple[int, str]]] = {}
+        for (si, G, a_) in coef.keys():
+            F = form.slots[si].field
+            if F in fields:
+                pairs.setdefault((F, G), []).append((si, a_))
+        return fields, pairs
+
+    def _group_acc_layout(self, form: ResidualForm, g: RowGroup, coef):
+        """index of every accumulator of the group inside the kernel-wide acc[] array"""
+        fields, pairs = self._group_pairs(form, g, coef)
+        base: Dict[Tuple[str, str], int] = {}
+        n = 0
+        for F in fields:
+            base[(F, "__res")] = n
+            n += g.rows_per_thread
+            for G in self.code.unknown_field_names():
+                if (F, G) in pairs:
+                    base[(F, G)] = n
+                    n += g.rows_per_thread * self._nnode_space(self.code.fields[G].space)
+        return base, n
+
+    def _group_nacc(self, form, g, coef) -> int:
+        return self._group_acc_layout(form, g, coef)[1]
+
+    def _emit_group_compute(self, o: List[str], rp: RoutinePlan, plan, g: RowGroup, pname, coef, coff, with_res):
+        code, dim, NIPT = self.code, self.dim, self.NIPT
+        form = rp.form
+        ELS, EL0, PB = plan["ELS"], plan["EL0"], plan["PB"]
+        w = o.append
+        nn_g = self._nnode_space(g.space)
+        RB, TPE = g.rows_per_thread, g.threads_per_elem
+        fields, pairs = self._group_pairs(form, g, coef)
+        base, nacc = self._group_acc_layout(form, g, coef)
+        unknowns = code.unknown_field_names()
+        if not fields:
+            return
+        w("    if (tid >= %d && tid < %d)" % (g.thread_off, g.thread_off + g.nthreads))
+        w("    {")
+        w("      const int tl = tid - %d;" % g.thread_off)
+        w("      const int el = tl / %d, q = tl - el * %d;" % (TPE, TPE))
+        w("      if (el < nel)")
+        w("      {")
+        w("        const double* E = s_el + el * %d;" % ELS)
+        w("        #pragma unroll")
+        w("        for (int i = 0; i < %d; ++i) acc[i] = 0.0;" % nacc)
+        if self.ipt_unroll >= NIPT:
+            w("        #pragma unroll")
+        else:
+            w("        #pragma unroll %d" % self.ipt_unroll)
+        w("        for (int ipt = 0; ipt < %d; ++ipt)" % NIPT)
+        w("        {")
+        w("          const double* P = E + %d + ipt * %d;" % (EL0, PB))
+        need_x = any(s.deriv.startswith("dx") for s in form.slots if s.field in fields) or any(a_.startswith("dx") for (F, G), l in pairs.items() for (_, a_) in l)
+        need_X = any(s.deriv.startswith("dX") for s in form.slots if s.field in fields) or any(a_.startswith("dX") for (F, G), l in pairs.items() for (_, a_) in l)
+        if need_x:
+            w("          " + " ".join("const double gg%d%d = P[%d];" % (b, i, plan["gg"] + b * dim + i) for b in range(dim) for i in range(dim)))
+        if need_X:
+            w("          " + " ".join("const double ggL%d%d = P[%d];" % (b, i, plan["ggL"] + b * dim + i) for b in range(dim) for i in range(dim)))
+        w("          #pragma unroll")
+        w("          for (int k = 0; k < %d; ++k)" % RB)
+        w("          {")
+        w("            const int lt = q + k * %d;" % TPE)
+        sps, sdp = ("s_psi1", "s_dpsi1") if g.space == "C1" else ("s_psi2", "s_dpsi2")
+        w("            const double T_d0 = %s[ipt * %d + lt]; (void)T_d0;" % (sps, nn_g))
+        test_derivs = {s.deriv for s in form.slots if s.field in fields}
+        if any(d != "d0" for d in test_derivs):
+            for b in range(dim):
+                w("            const double Ts%d = %s[(ipt * %d + lt) * %d + %d];" % (b, sdp, nn_g, dim, b))
+        for d in sorted(test_derivs):
+            if d == "d0":
+                continue
+            gn = "gg" if d[1] == "x" else "ggL"
+            i = int(d[2:])
+            w("            const double T_%s = %s;" % (d, " + ".join("%s%d%d * Ts%d" % (gn, b, i, b) for b in range(dim))))
+        for F in fields:
+            fslots = [(si, s) for si, s in enumerate(form.slots) if s.field == F]
+            if with_res:
+                terms = ["T_%s * P[%d]" % (s.deriv, plan["R_off"] + si) for si, s in fslots if form.R[si] != 0]
+                if terms:
+                    expr = "acc[%d + k]" % base[(F, "__res")]
+                    for si, sl in fslots:
+                        if form.R[si] != 0:
+                            expr = "fma(T_%s, P[%d], %s)" % (sl.deriv, plan["R_off"] + si, expr)
+                    w("            acc[%d + k] = %s;" % (base[(F, "__res")], expr))
+            for G in unknowns:
+                if (F, G) not in pairs:
+                    continue
+                Gs = code.fields[G].space
+                nnG = self._nnode_space(Gs)
+                by_atom: Dict[str, List[int]] = {}
+                for (si, a_) in pairs[(F, G)]:
+                    by_atom.setdefault(a_, []).append(si)
+                for a_, sis in sorted(by_atom.items()):
+                    w("            const double W_%s_%s_%s = %s;" % (F, G, a_, " + ".join(
+                        "T_%s * P[%d]" % (form.slots[si].deriv, coff[(si, G, a_)]) for si in sis)))
+                have_s = False
+                sterms = {b: [] for b in range(dim)}
+                for a_ in sorted(by_atom):
+                    if a_ == "d0":
+                        continue
+                    gn = "gg" if a_[1] == "x" else "ggL"
+                    i = int(a_[2:])
+                    for b in range(dim):
+                        sterms[b].append("W_%s_%s_%s * %s%d%d" % (F, G, a_, gn, b, i))
+                    have_s = True
+                if have_s:
+                    for b in range(dim):
+                        w("            const double Ws%d_%s_%s = %s;" % (b, F, G, " + ".join(sterms[b])))
+                if Gs == "C1":
+                    tp, td = ("s_psi1", "s_dpsi1") if self.table_source == "smem" else ("c_psi1", "c_dpsi1")
+                else:
+                    tp, td = ("s_psi2", "s_dpsi2") if self.table_source == "smem" else ("c_psi2", "c_dpsi2")
+                parts = []
+                if "d0" in by_atom:
+                    parts.append(("W_%s_%s_d0" % (F, G), "%s[ipt * %d + c]" % (tp, nnG)))
+                if have_s:
+                    for b in range(dim):
+                        parts.append(("Ws%d_%s_%s" % (b, F, G), "%s[(ipt * %d + c) * %d + %d]" % (td, nnG, dim, b)))
+                accname = "acc[%d + k * %d + c]" % (base[(F, G)], nnG)
+                expr = accname
+                for (wn, tn) in parts:          # one DFMA per term, accumulated in place
+                    expr = "fma(%s, %s, %s)" % (wn, tn, expr)
+                w("            #pragma unroll")
+                w("            for (int c = 0; c < %d; ++c)" % nnG)
+                w("              %s = %s;" % (accname, expr))
+        w("          }")
+        w("        }")
+        w("      }")
+        w("    }")
+
+    def _emit_group_stage(self, o: List[str], rp: RoutinePlan, plan, g: RowGroup, pname, coef, with_res, with_matrix):
+        """accumulators -> dense element matrix/residual in shared memory (structurally empty blocks are zeros: the
+        fixed CSR pattern still owns those entries)"""
+        code = self.code
+        form = rp.form
+        w = o.append
+        ND = self.ndof
+        RB, TPE = g.rows_per_thread, g.threads_per_elem
+        fields, pairs = self._group_pairs(form, g, coef)
+        base, nacc = self._group_acc_layout(form, g, coef)
+        unknowns = code.unknown_field_names()
+        w("    if (tid >= %d && tid < %d)" % (g.thread_off, g.thread_off + g.nthreads))
+        w("    {")
+        w("      const int tl = tid - %d;" % g.thread_off)
+        w("      const int el = tl / %d, q = tl - el * %d;" % (TPE, TPE))
+        w("      if (el < nel)")
+        w("      {")
+        w("        double* SJ = s_el + el * %d + %d;" % (plan["ELS"], plan["SJ_off"]))
+        w("        #pragma unroll")
+        w("        for (int k = 0; k < %d; ++k)" % RB)
+        w("        {")
+        w("          const int lt = q + k * %d;" % TPE)
+        for F in g.fields:
+            w("          {")
+            w("            const int row = c_row_%s[lt];" % F)
+            if with_res:
+                roff = ND * ND if with_matrix else 0
+                if F in fields:
+                    w("            SJ[%d + row] = acc[%d + k];" % (roff, base[(F, "__res")]))
+                else:
+                    w("            SJ[%d + row] = 0.0;" % roff)
+            if with_matrix:
+                w("            double* srow = SJ + row * %d;" % ND)
+                for G in unknowns:
+                    nnG = self._nnode_space(code.fields[G].space)
+                    for c in range(nnG):
+                        col = self._col_index(G, c)
+                        if (F, G) in pairs:
+                            w("            srow[%d] = acc[%d + k * %d + %d];" % (col, base[(F, G)], nnG, c))
+                        else:
+                            w("            srow[%d] = 0.0;" % col)
+            w("          }")
+        w("        }")
+        w("      }")
+        w("    }")
+
+    def _emit_scatter(self, o: List[str], plan, target, with_res):
+        w = o.append
+        ND, ND2 = self.ndof, self.ndof * self.ndof
+        ELS, SJ = plan["ELS"], plan["SJ_off"]
+        w("    {")
+        if target is not None:
+            w("      if (a.map_bits == 8)")
+            w("        pb2_scatter_matrix<unsigned char, 0x80u, 0xFFu, %d, %d, %d>((const unsigned char*)s_map, s_rowstart, s_el + %d, %s, nel, tid);" % (
+                ND, ELS, self.NT, SJ, target))
+            w("      else")
+            w("        pb2_scatter_matrix<unsigned short, 0x8000u, 0xFFFFu, %d, %d, %d>((const unsigned short*)s_map, s_rowstart, s_el + %d, %s, nel, tid);" % (
+                ND, ELS, self.NT, SJ, target))
+        if with_res:
+            w("      for (int idx = tid; idx < nel * %d; idx += %d)" % (ND, self.NT))
+            w("      {")
+            w("        const int el = idx / %d, row = idx - el * %d;" % (ND, ND))
+            w("        pb2_put(a.residual, s_resmap[idx], s_el[el * %d + %d + row]);" % (ELS, SJ + (ND2 if target is not None else 0)))
+            w("      }")
+        w("    }")
+
+    # ------------------------------------------------------------------ whole file
+    def emit(self) -> str:
+        code = self.code
+        self._kernel_smem: Dict[str, int] = {}
+        o: List[str] = []
+        w = o.append
+        w("// generated by pyoomph_b200.cuda_emitter for element class '%s' (%s) -- sm_100a" % (self.name, self.et.name))
+        w("#include <cuda_runtime.h>")
+        w("#include <string.h>")
+        w('#include "pb2_jit_cuda.h"')
+        w("")
+        w("static __device__ __forceinline__ void pb2_put(double* __restrict__ dst, const int p, const double v)")
+        w("{")
+        w("  if (p >= 0) atomicAdd(dst + p, v);")
+        w("  else if (p != PB2_MAP_SKIP) dst[~p] = v;")
+        w("}")
+        w("// cooperative scatter of dense element matrices staged in shared memory (element stride ELS doubles) into the CSR")
+        w("// value array: entry idx of the batch <-> byte idx of the position map, so map reads are perfectly coalesced and")
+        w("// neighbouring lanes hit neighbouring columns of the same CSR row.")
+        w("template <typename MapT, unsigned FIRST, unsigned SKIP, int ND, int ELS, int NT>")
+        w("static __device__ __forceinline__ void pb2_scatter_matrix(const MapT* __restrict__ mp, const int* __restrict__ rowstart,")
+        w("                                                          const double* __restrict__ sj, double* __restrict__ vals, const int nel, const int tid)")
+        w("{")
+        w("  // all operands are in shared memory; stores and reductions are fire-and-forget (colouring => one add per entry and launch,")
+        w("  // stream order between launches => the summation order is fixed).  Lane <-> consecutive (row,col) entries of one element,")
+        w("  // so neighbouring lanes hit neighbouring columns of the same CSR row; the entry -> row split is loop invariant.")
+        w("  constexpr int ND2 = ND * ND, NJ = (ND2 + NT - 1) / NT;")
+        w("  int kj[NJ], rj[NJ];")
+        w("  #pragma unroll")
+        w("  for (int j = 0; j < NJ; ++j) { kj[j] = tid + j * NT; rj[j] = kj[j] / ND; }")
+        w("  #pragma unroll 2")
+        w("  for (int el = 0; el < nel; ++el)")
+        w("  {")
+        w("    const MapT* __restrict__ m = mp + el * ND2; const int* __restrict__ rs = rowstart + el * ND; const double* __restrict__ sv = sj + el * ELS;")
+        w("    #pragma unroll")
+        w("    for (int j = 0; j < NJ; ++j)")
+        w("    {")
+        w("      if (kj[j] < ND2)")
+        w("      {")
+        w("        const unsigned code = (unsigned)m[kj[j]];")
+        w("        const int r0 = rs[rj[j]];")
+        w("        const double v = sv[kj[j]];")
+        w("        if (code != SKIP && r0 >= 0)")
+        w("        {")
+        w("          double* dst = vals + (r0 + (int)(code & (FIRST - 1u)));")
+        w("          if (code & FIRST) *dst = v; else atomicAdd(dst, v);")
+        w("        }")
+        w("      }")
+        w("    }")
+        w("  }")
+        w("}")
+        w("")
+        self._emit_tables(o)
+        kernels: Dict[Tuple[str, int], str] = {}
+        for rp in self.routines:
+            for what in (0, 1, 2):
+                kernels[(rp.key, what)] = self._emit_kernel(o, rp, what)
+        # host side: launchers + table
+        w("static int pb2_launch_rjm(int residual_index, int param_index, unsigned flag, const pb2_kernel_args* args, void* stream)")
+        w("{")
+        w("  if (flag > 2u) return 1;")
+        w("  if (args->n_elem <= 0) return 0;")
+        w("  const int nbatch = (args->n_elem + %d - 1) / %d;" % (self.EPB, self.EPB))
+        w("  void (*kern)(const pb2_kernel_args) = 0; size_t smem = 0;")
+        for rp in self.routines:
+            for what in (0, 1, 2):
+                kn = kernels[(rp.key, what)]
+                w("  if (residual_index == %d && param_index == %d && flag == %du) { kern = %s; smem = %d; }" % (
+                    rp.res_index, rp.param_index, what, kn, self._kernel_smem[kn]))
+        w("  if (!kern) return 2;")
+        w("  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+        w("  if (err != cudaSuccess) return 100 + (int)err;")
+        w("  static int grid_cap = 0;")
+        w("  if (!grid_cap) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); grid_cap = sms > 0 ? sms : 148; }")
+        w("  int per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, %d, smem);" % self.NT)
+        w("  if (per_sm < 1) per_sm = 1;")
+        w("  const int grid = nbatch < grid_cap * per_sm ? nbatch : grid_cap * per_sm;   // persistent blocks, one wave")
+        w("  kern<<<grid, %d, smem, (cudaStream_t)stream>>>(*args);" % self.NT)
+        w("  err = cudaGetLastError();")
+        w("  return err == cudaSuccess ? 0 : 100 + (int)err;")
+        w("}")
+        w("")
+        w('extern "C" void JIT_ELEMENT_init_cuda(pb2_cuda_table_t* table)')
+        w("{")
+        w("  memset(table, 0, sizeof(*table));")
+        w("  pb2_class_info* ci = &table->info;")
+        w("  ci->abi_version = PB2_ABI_VERSION;")
+        w('  strncpy(ci->name, "%s", sizeof(ci->name) - 1);' % self.name)
+        w("  ci->nodal_dim = %d; ci->elem_dim = %d; ci->nnode = %d; ci->nnode_C1 = %d; ci->n_int_pt = %d;" % (
+            self.dim, self.et.elem_dim, self.NN, self.NN1, self.NIPT))
+        for i, n in enumerate(self.et.c1_nodes):
+            w("  ci->c1_nodes[%d] = %d;" % (i, n))
+        w("  ci->nval = %d;" % self.nval)
+        nf = code.nodal_fields()
+        w("  ci->n_fields = %d;" % len(nf))
+        for i, f in enumerate(nf):
+            w('  strncpy(ci->field_names[%d], "%s", 47); ci->field_space[%d] = %d; ci->field_index[%d] = %d;' % (
+                i, f.name, i, 2 if f.space == "C2" else 1, i, f.index))
+        w("  ci->moving_nodes = %d;" % (1 if code.coordinates_as_dofs else 0))
+        w("  ci->ndof_el = %d;" % self.ndof)
+        for k, (f, l) in enumerate(self.layout):
+            fld = code.fields[f]
+            node = l if fld.space != "C1" else self.et.c1_nodes[l]
+            if fld.space == "Pos":
+                w("  ci->dof_node[%d] = %d; ci->dof_kind[%d] = 0; ci->dof_index[%d] = %d;" % (k, node, k, k, fld.index))
+            else:
+                w("  ci->dof_node[%d] = %d; ci->dof_kind[%d] = 1; ci->dof_index[%d] = %d;" % (k, node, k, k, fld.index))
+        rn = code.residual_names()
+        w("  ci->n_residuals = %d;" % len(rn))
+        for i, n in enumerate(rn):
+            w('  strncpy(ci->residual_names[%d], "%s", 47);' % (i, n))
+        w("  ci->n_params = %d;" % len(code.global_params))
+        for i, n in enumerate(code.global_params):
+            w('  strncpy(ci->param_names[%d], "%s", 47);' % (i, n))
+        w("  ci->n_hist_val = %d; ci->n_hist_pos = %d; ci->max_dt_order = %d;" % (self.T_val, self.T_pos, code.max_dt_order()))
+        w("  ci->elems_per_block = %d; ci->threads_per_block = %d; ci->smem_bytes = %d;" % (
+            self.EPB, self.NT, max(self._kernel_smem.values())))
+        w("  ci->hessian_generated = 0;")
+        for what in (0, 1, 2):
+            w("  ci->alg_bytes_per_elem[%d] = %r;" % (what, self.algorithmic_bytes(what)))
+        w("  ci->alg_bytes_per_hist_level = %r;" % float(8 * sum(self._nnode_space(f.space) for f in code.nodal_fields())))
+        w("  table->launch_rjm = &pb2_launch_rjm;")
+        w("  table->launch_hessian = 0;")
+        w("}")
+        return "\n".join(o) + "\n"
+
+    def algorithmic_bytes(self, what: int) -> float:
+        """B_el of SURVEY 8(d): gather (positions, nodal values x history, local->global map) + scatter
+        (residual add, Jacobian values written once, element->CSR position map read)."""
+        code = self.code
+        c_pos = 2 if any(a.field.startswith("lagrangian") or a.deriv.startswith("dX") for rp in self.routines for a in rp.form.atoms) else 1
+        gather = 8 * self.NN * self.dim * c_pos
+        gather += 8 * self.T_val * sum(self._nnode_space(f.space) for f in code.nodal_fields())
+        gather += 4 * self.ndof
+        scatter = 8 * self.ndof
+        if what >= 1:
+            scatter += 12 * self.ndof * self.ndof
+        if what >= 2:
+            scatter += 12 * self.ndof * self.ndof
+        return float(gather + scatter)
+
+
+def emit_cuda_source(code: FiniteElementCode, name: str = "elem", **kw) -> str:
+    return CudaEmitter(code, name, **kw).emit()

@@ -1,0 +1,138 @@
+"""Shared problem definitions for the parity tests: the BASELINE configs at sizes the oracle finishes in seconds."""
+import numpy as np
+
+from pyoomph_b200.codegen import FiniteElementCode
+from pyoomph_b200.equations import (NavierStokesEquations, PoissonEquation, PseudoElasticMesh, TransientHeatEquation)
+from pyoomph_b200.expressions import exp, var, global_parameter
+from pyoomph_b200.meshes import CuboidBrickMesh, RectangularQuadMesh, assign_equation_numbers
+
+
+def smooth_field(pos, k, seed):
+    """uniform(-1,1) * smooth envelope, fixed seed (SURVEY 8d value distributions)."""
+    rng = np.random.default_rng(seed + 17 * k)
+    ph = rng.uniform(0, 2 * np.pi, size=pos.shape[1] + 1)
+    v = np.ones(pos.shape[0])
+    for d in range(pos.shape[1]):
+        v = v * np.sin((2 + k + d) * pos[:, d] + ph[d])
+    return v + 0.1 * rng.uniform(-1, 1, size=pos.shape[0])
+
+
+def poisson_source():
+    # docs/source/tutorial/spatial/poisson/poisson_2d.py:35-41
+    x, y = var("coordinate_x"), var("coordinate_y")
+    return 100 * exp(-100 * ((x - 0.5) ** 2 + (y - 0.5) ** 2))
+
+
+def make_problem(kind: str, N: int, seed: int = 0):
+    """Returns dict(code, mesh, dofmap, vals[T,n_node,nval], pos_hist or None, unsteady(bool), params)."""
+    params = {}
+    if kind == "poisson":          # config 1
+        mesh = RectangularQuadMesh(N)
+        code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")
+        pinned = {"u": np.concatenate([mesh.boundaries["left"], mesh.boundaries["right"]])}
+        unsteady = False
+    elif kind == "ns":             # config 2: lid-driven cavity, Taylor-Hood, Re=100
+        mesh = RectangularQuadMesh(N)
+        code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0), name="ns")
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "right", "bottom", "top")]))
+        pinned = {"velocity_x": wall, "velocity_y": wall, "pressure": np.array([0])}
+        unsteady = False
+    elif kind == "ns_unsteady":
+        mesh = RectangularQuadMesh(N)
+        code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0), name="ns")
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "right", "bottom", "top")]))
+        pinned = {"velocity_x": wall, "velocity_y": wall, "pressure": np.array([0])}
+        unsteady = True
+    elif kind == "ns_param":       # viscosity as global parameter -> dResidual/dParameter routines
+        mesh = RectangularQuadMesh(N)
+
+        class _NS(NavierStokesEquations):
+            def define_residuals(self):
+                self.dynamic_viscosity = global_parameter("mu")
+                super().define_residuals()
+        code = FiniteElementCode("Quad2dC2", _NS(mass_density=1.0), name="nsp")
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "right", "bottom", "top")]))
+        pinned = {"velocity_x": wall, "velocity_y": wall}
+        unsteady = False
+        params = {"mu": 0.013}
+    elif kind == "heat3d":         # config 3
+        mesh = CuboidBrickMesh(N)
+        code = FiniteElementCode("Brick3dC2", TransientHeatEquation(), name="heat3d")
+        pinned = {"u": mesh.boundaries["left"]}
+        unsteady = True
+    elif kind == "ale":            # config 4 bulk part: NS-TH on a pseudo-elastic moving mesh
+        mesh = RectangularQuadMesh(N)
+        code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + PseudoElasticMesh(), name="ale")
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
+        pinned = {"velocity_x": wall, "velocity_y": wall}
+        unsteady = True
+    else:
+        raise KeyError(kind)
+    pinned_pos = None
+    if code.coordinates_as_dofs:
+        pinned_pos = {"coordinate_x": mesh.boundaries["left"], "coordinate_y": mesh.boundaries["bottom"]}
+    dofmap = assign_equation_numbers(mesh, code, pinned, pinned_pos)
+    T = code.history_levels()
+    nval = code.n_nodal_values
+    vals = np.zeros((T, mesh.n_node, nval))
+    for t in range(T):
+        for f in range(nval):
+            vals[t, :, f] = smooth_field(mesh.node_pos, f + 3 * t, seed) * (1.0 - 0.05 * t)
+    pos_hist = None
+    if code.coordinates_as_dofs:
+        pos_hist = np.stack([mesh.node_pos + 1e-3 * (1 + 0.3 * t) * np.stack(
+            [smooth_field(mesh.node_pos, 10 + d + 2 * t, seed) for d in range(mesh.dim)], axis=1) for t in range(T)])
+    return dict(kind=kind, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=pos_hist, unsteady=unsteady, params=params)
+
+
+TIME = dict(t=0.3, dt=0.01, dtprev=0.012, unsteady_steps_done=2)
+
+
+def make_oracle(pb, **kw):
+    from oracle import OracleProblem
+    op = OracleProblem(pb["code"], pb["mesh"], pb["dofmap"], pb["vals"], node_pos_hist=pb["pos_hist"], name=pb["code"].name, **kw)
+    if pb["unsteady"]:
+        op.set_unsteady(TIME["t"], TIME["dt"], TIME["dtprev"], TIME["unsteady_steps_done"])
+    else:
+        op.set_steady()
+    if pb["params"]:
+        op.set_params([pb["params"][n] for n in pb["code"].global_params])
+    return op
+
+
+def make_gpu(pb, **kw):
+    from pyoomph_b200.assembly import B200Assembly
+    asm = B200Assembly(pb["code"], pb["mesh"], pb["dofmap"], name=pb["code"].name, **kw)
+    for t in range(pb["vals"].shape[0]):
+        asm.set_nodal_values(t, pb["vals"][t])
+    if pb["pos_hist"] is not None:
+        for t in range(pb["pos_hist"].shape[0]):
+            asm.set_nodal_positions(t, pb["pos_hist"][t])
+    if pb["unsteady"]:
+        asm.set_unsteady(TIME["t"], TIME["dt"], TIME["dtprev"], TIME["unsteady_steps_done"])
+    else:
+        asm.set_steady()
+    if pb["params"]:
+        asm.set_parameters(**pb["params"])
+    return asm
+
+
+def csr_to_sorted(n, rs, ci, va):
+    """canonical form: scipy CSR with sorted indices (the reference's vectors_of_pairs columns are unsorted)."""
+    from scipy.sparse import csr_matrix
+    A = csr_matrix((va, ci, rs), shape=(n, n))
+    A.sort_indices()
+    return A
+
+
+def compare_matrix(A_gpu, A_ref, tol=1e-12):
+    """A_ref's pattern (exact zeros dropped, problem.cc:5524) must be a subset of the fixed GPU pattern; values agree
+    to `tol` relative to the row scale; GPU-only entries must be numerically zero on that scale."""
+    D = (A_gpu - A_ref).tocsr()
+    rowmax = np.maximum(abs(A_ref).max(axis=1).toarray().ravel(), 1e-300)
+    err = abs(D).max(axis=1).toarray().ravel() / rowmax
+    # pattern subset: every reference entry position exists in the GPU pattern
+    P = A_gpu.copy(); P.data[:] = 1.0
+    Q = A_ref.copy(); Q.data[:] = 1.0
+    missing = (Q - Q.multiply(P)).count_nonzero()
+    return float(err.max()), int(missing)
