@@ -156,8 +156,11 @@ class CudaEmitter:
         self.T_val = code.history_levels()
         self.T_pos = self.T_val if code.coordinates_as_dofs else 1
         self._plan_groups()
-        self.EPB = elems_per_block or self._default_epb()
+        self.EPB_max = elems_per_block or self._default_epb()
+        self.smem_budget = int(os.environ.get("PB2_SMEM_BUDGET", str(100 * 1024 if self.dim == 2 else 110 * 1024)))
+        self.EPB = self.EPB_max
         self._layout_threads()
+        self._kernel_cfg: Dict[str, Tuple[int, int, int]] = {}
 
     # ------------------------------------------------------------------ planning
     def _col_index(self, field: str, lnode: int) -> int:
@@ -296,12 +299,17 @@ class CudaEmitter:
         ELS, EL0, PB = plan["ELS"], plan["EL0"], plan["PB"]
         kname = "pb2_%s_%s_f%d" % (self.name, rp.key, what)
         tab_n = self._tables_smem_size()
-        smem_doubles = tab_n + self.EPB * ELS
         ND, ND2 = self.ndof, self.ndof * self.ndof
+        # elements per block of THIS kernel: as many as the thread budget allows, capped by the shared-memory budget
+        per_el = ELS * 8 + 2 * ND * 4 + (2 * ND2 if what >= 1 else 0)
+        self.EPB = max(2, min(self.EPB_max, (self.smem_budget - tab_n * 8) // per_el))
+        self._layout_threads()
+        smem_doubles = tab_n + self.EPB * ELS
         # staged scatter maps: rowstart[EPB][ND] + res[EPB][ND] ints, then the (8|16 bit) offset bytes
         map_ints = 2 * self.EPB * ND
         map_bytes = 2 * self.EPB * ND2 if what >= 1 else 0
         self._kernel_smem[kname] = smem_doubles * 8 + map_ints * 4 + ((map_bytes + 15) // 16) * 16
+        self._kernel_cfg[kname] = (self.EPB, self.NT, self._kernel_smem[kname])
         w = o.append
         T2 = "s_psi2" if self.table_source == "smem" else "c_psi2"
         w("// %s  what=%d : %d slots, %d Jacobian coefficients, %d mass coefficients, element smem %d doubles" % (
@@ -806,22 +814,22 @@ class CudaEmitter:
         w("{")
         w("  if (flag > 2u) return 1;")
         w("  if (args->n_elem <= 0) return 0;")
-        w("  const int nbatch = (args->n_elem + %d - 1) / %d;" % (self.EPB, self.EPB))
-        w("  void (*kern)(const pb2_kernel_args) = 0; size_t smem = 0;")
+        w("  void (*kern)(const pb2_kernel_args) = 0; size_t smem = 0; int epb = 1, nt = 32;")
         for rp in self.routines:
             for what in (0, 1, 2):
                 kn = kernels[(rp.key, what)]
-                w("  if (residual_index == %d && param_index == %d && flag == %du) { kern = %s; smem = %d; }" % (
-                    rp.res_index, rp.param_index, what, kn, self._kernel_smem[kn]))
+                w("  if (residual_index == %d && param_index == %d && flag == %du) { kern = %s; smem = %d; epb = %d; nt = %d; }" % (
+                    rp.res_index, rp.param_index, what, kn, self._kernel_smem[kn], self._kernel_cfg[kn][0], self._kernel_cfg[kn][1]))
         w("  if (!kern) return 2;")
+        w("  const int nbatch = (args->n_elem + epb - 1) / epb;")
         w("  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
         w("  if (err != cudaSuccess) return 100 + (int)err;")
         w("  static int grid_cap = 0;")
         w("  if (!grid_cap) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); grid_cap = sms > 0 ? sms : 148; }")
-        w("  int per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, %d, smem);" % self.NT)
+        w("  int per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem);")
         w("  if (per_sm < 1) per_sm = 1;")
         w("  const int grid = nbatch < grid_cap * per_sm ? nbatch : grid_cap * per_sm;   // persistent blocks, one wave")
-        w("  kern<<<grid, %d, smem, (cudaStream_t)stream>>>(*args);" % self.NT)
+        w("  kern<<<grid, nt, smem, (cudaStream_t)stream>>>(*args);")
         w("  err = cudaGetLastError();")
         w("  return err == cudaSuccess ? 0 : 100 + (int)err;")
         w("}")
@@ -860,7 +868,7 @@ class CudaEmitter:
             w('  strncpy(ci->param_names[%d], "%s", 47);' % (i, n))
         w("  ci->n_hist_val = %d; ci->n_hist_pos = %d; ci->max_dt_order = %d;" % (self.T_val, self.T_pos, code.max_dt_order()))
         w("  ci->elems_per_block = %d; ci->threads_per_block = %d; ci->smem_bytes = %d;" % (
-            self.EPB, self.NT, max(self._kernel_smem.values())))
+            self._kernel_cfg[kernels[(self.routines[0].key, 1)]][0], self._kernel_cfg[kernels[(self.routines[0].key, 1)]][1], max(self._kernel_smem.values())))
         w("  ci->hessian_generated = 0;")
         for what in (0, 1, 2):
             w("  ci->alg_bytes_per_elem[%d] = %r;" % (what, self.algorithmic_bytes(what)))
