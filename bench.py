@@ -275,11 +275,11 @@ def main():
     achieved = b_el * n_elem_rank / (ms_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "alg_bytes_per_element": b_el, "kernel": "pb2_%s_r0_f1" % pb["code"].name,
-                "launches_per_step": asm.num_launches(), "avg_launch_ms": ms_step / max(1, asm.num_launches())}
+                "launches_per_step": launches // max(1, args.steps), "tiles_per_step": asm.num_launches(), "avg_launch_ms": ms_step / max(1, launches // max(1, args.steps))}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": pb["label"], "elements": int(total_elems), "dofs": int(asm.n_dof), "nnz": int(asm.nnz), "ndof_el": int(info.ndof_el),
-                       "colours": asm.num_colours(), "launches_per_step": asm.num_launches(), "cache": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2" % (b_el * n_elem_rank / 1e9),
+                       "colours": asm.num_colours(), "tiles": asm.num_launches(), "cache": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2" % (b_el * n_elem_rank / 1e9),
                        "setup_s": round(t_setup, 1), "parallelism": "element blocks x%d" % world},
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches)}
     if e2e is not None:

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 4
+#define PB2_ABI_VERSION 5
 #define PB2_MAX_PARAMS 16
 #define PB2_NTW 7           /* time-stepper storage, MultiTimeStepper (src/timestepper.hpp:37-45) */
 #define PB2_MAX_FIELDS 16
@@ -63,6 +63,12 @@ typedef struct pb2_kernel_args
   double *residual;           /* [n_dof] */
   double *jac_vals;           /* [nnz] */
   double *mass_vals;          /* [nnz] */
+  /* pipelined kernels: the whole assembly is one launch over batches ordered by tile = (chunk, colour) */
+  const int *batch_elem;      /* [n_batches] first element of the batch (colour-major element order) */
+  const int *batch_meta;      /* [n_batches] (tile << 6) | number of elements */
+  const int *tile_nbatch;     /* [n_tiles]   batches per tile */
+  int *tile_done;             /* [n_tiles]   completion counters, zeroed by the host before the launch */
+  int n_batches, n_tiles;
   const double *hvec;         /* [n_hvec][n_dof]   Hessian-vector inputs (or NULL) */
   int n_hvec, pad_;
   pb2_time_info ti;
@@ -99,14 +105,29 @@ typedef struct pb2_class_info
   double alg_bytes_per_hist_level; /* part of alg_bytes per history level beyond the current one (not read when steady) */
 } pb2_class_info;
 
-typedef int (*pb2_launch_fn)(int residual_index, int param_index, unsigned flag, const pb2_kernel_args *args,
-                             void *cuda_stream);
+/* launch configuration of one generated routine */
+typedef struct pb2_kernel_cfg
+{
+  int elems_per_batch;   /* elements one block processes per batch */
+  int threads;           /* block size */
+  int smem_bytes;        /* dynamic shared memory */
+  int pipelined;         /* 1: persistent warp-specialised kernel, one launch per assembly (batch tables in args);
+                            0: one launch per tile, args->elem_begin / n_elem select the tile */
+  int blocks_per_sm;     /* resident blocks per SM (occupancy), for sizing the persistent grid */
+  int pad_;
+  const void *func;      /* opaque kernel handle for pb2_launch_fn */
+} pb2_kernel_cfg;
+
+/* routine = ResidualAndJacobian<residual_index> (param_index < 0) or dResidual<i>dParameter_<param_index>;
+ * flag as in jitbridge.h:285.  kind 0: R/J/M routines, 1: Hessian-vector routines. */
+typedef int (*pb2_query_fn)(int kind, int residual_index, int param_index, unsigned flag, pb2_kernel_cfg *out);
+typedef int (*pb2_launch_fn)(const pb2_kernel_cfg *cfg, const pb2_kernel_args *args, int grid, void *cuda_stream);
 
 typedef struct pb2_cuda_table
 {
   pb2_class_info info;
-  pb2_launch_fn launch_rjm;        /* ResidualAndJacobian<i> / dResidual<i>dParameter_<p> (param_index>=0) */
-  pb2_launch_fn launch_hessian;    /* HessianVectorProduct<i>: args->hvec, flag semantics of SURVEY A.5 */
+  pb2_query_fn query;
+  pb2_launch_fn launch;
 } pb2_cuda_table_t;
 
 typedef void (*JIT_ELEMENT_init_cuda_SPEC)(pb2_cuda_table_t *table);

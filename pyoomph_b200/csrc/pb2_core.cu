@@ -58,6 +58,14 @@ struct pb2_problem
   pb2_time_info ti;
   double params[PB2_MAX_PARAMS];
   long long launches_last = 0, launches_total = 0;
+  int n_sms = 148;
+  // batch tables of the pipelined kernels, per elements-per-batch value
+  struct BatchTables
+  {
+    int epb = 0, n_batches = 0, n_tiles = 0;
+    int *d_batch_elem = nullptr, *d_batch_meta = nullptr, *d_tile_nbatch = nullptr, *d_tile_done = nullptr;
+  };
+  std::vector<BatchTables> batch_tables;
   cudaStream_t copy_stream = nullptr;
 };
 
@@ -115,6 +123,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   const pb2_class_info &ci = cls->table.info;
   CUDA_OK(cudaSetDevice(device));
   pb2_problem *p = new pb2_problem;
+  CUDA_OK(cudaDeviceGetAttribute(&p->n_sms, cudaDevAttrMultiProcessorCount, device));
   p->cls = cls;
   p->device = device;
   p->n_elem = m->n_elem;
@@ -165,7 +174,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   // resident in the 126 MB L2 (a global sweep per colour would write every 32 B sector up to `ncol` times to HBM).
   // Launches are stream-ordered and each holds one colour only, so chunk boundaries need no extra care.
   p->n_colours = ncol;
-  long long chunk = 1LL << 40;   // default: one global sweep per colour (measured faster on B200 than L2-sized chunks, profiles/)
+  long long chunk = 16384;
   if (const char *cs = getenv("PB2_CHUNK_ELEMS")) chunk = std::max(1LL, atoll(cs));
   const long long nchunk = (ne + chunk - 1) / chunk;
   p->colour_begin.assign((size_t)(nchunk * ncol) + 1, 0);
@@ -419,6 +428,13 @@ extern "C" void pb2_problem_free(pb2_problem *p)
   cudaFree(p->d_jac);
   cudaFree(p->d_mass);
   cudaFree(p->d_dofs);
+  for (auto &b : p->batch_tables)
+  {
+    cudaFree(b.d_batch_elem);
+    cudaFree(b.d_batch_meta);
+    cudaFree(b.d_tile_nbatch);
+    cudaFree(b.d_tile_done);
+  }
   delete p;
 }
 
@@ -533,13 +549,66 @@ extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int para
   a.ti = p->ti;
   memcpy(a.params, p->params, sizeof(a.params));
   p->launches_last = 0;
-  const int nlaunch = (int)p->colour_begin.size() - 1;
-  for (int c = 0; c < nlaunch; c++)
+  pb2_kernel_cfg cfg;
+  int rc = p->cls->table.query(0, residual_index, param_index, flag, &cfg);
+  if (rc != 0)
+    return fail("plugin has no kernel for this routine (rc " + std::to_string(rc) + (rc >= 100 ? std::string(": ") + cudaGetErrorString((cudaError_t)(rc - 100)) : "") + ")");
+  const int ntile = (int)p->colour_begin.size() - 1;
+  if (cfg.pipelined)
+  {
+    // one persistent launch: batches ordered by tile, tile order enforced on the device
+    pb2_problem::BatchTables *bt = nullptr;
+    for (auto &b : p->batch_tables)
+      if (b.epb == cfg.elems_per_batch) bt = &b;
+    if (!bt)
+    {
+      pb2_problem::BatchTables nb;
+      nb.epb = cfg.elems_per_batch;
+      std::vector<int> be, bm, tn;
+      int tile_out = 0;
+      for (int t = 0; t < ntile; t++)
+      {
+        const int b0 = p->colour_begin[t], b1 = p->colour_begin[t + 1];
+        if (b1 == b0) continue;
+        int cnt = 0;
+        for (int e = b0; e < b1; e += nb.epb, cnt++)
+        {
+          be.push_back(e);
+          bm.push_back((tile_out << 6) | std::min(nb.epb, b1 - e));
+        }
+        tn.push_back(cnt);
+        tile_out++;
+      }
+      nb.n_batches = (int)be.size();
+      nb.n_tiles = tile_out;
+      if (upload(&nb.d_batch_elem, be) || upload(&nb.d_batch_meta, bm) || upload(&nb.d_tile_nbatch, tn)) return 1;
+      CUDA_OK(cudaMalloc((void **)&nb.d_tile_done, std::max(1, nb.n_tiles) * sizeof(int)));
+      p->batch_tables.push_back(nb);
+      bt = &p->batch_tables.back();
+    }
+    CUDA_OK(cudaMemsetAsync(bt->d_tile_done, 0, std::max(1, bt->n_tiles) * sizeof(int), (cudaStream_t)cuda_stream));
+    a.batch_elem = bt->d_batch_elem;
+    a.batch_meta = bt->d_batch_meta;
+    a.tile_nbatch = bt->d_tile_nbatch;
+    a.tile_done = bt->d_tile_done;
+    a.n_batches = bt->n_batches;
+    a.n_tiles = bt->n_tiles;
+    a.n_elem = (int)p->n_elem;
+    // every block must be resident (the tile gate spins): grid <= SMs x occupancy
+    const int grid = std::min(bt->n_batches, p->n_sms * cfg.blocks_per_sm);
+    rc = p->cls->table.launch(&cfg, &a, grid, cuda_stream);
+    if (rc != 0) return fail("kernel launch failed (plugin rc " + std::to_string(rc) + (rc >= 100 ? std::string(": ") + cudaGetErrorString((cudaError_t)(rc - 100)) : "") + ")");
+    p->launches_last++;
+    p->launches_total++;
+    return 0;
+  }
+  for (int c = 0; c < ntile; c++)
   {
     a.elem_begin = p->colour_begin[c];
     a.n_elem = p->colour_begin[c + 1] - p->colour_begin[c];
     if (a.n_elem == 0) continue;
-    const int rc = p->cls->table.launch_rjm(residual_index, param_index, flag, &a, cuda_stream);
+    const int nbatch = (a.n_elem + cfg.elems_per_batch - 1) / cfg.elems_per_batch;
+    rc = p->cls->table.launch(&cfg, &a, std::min(nbatch, p->n_sms * cfg.blocks_per_sm), cuda_stream);
     if (rc != 0)
       return fail("kernel launch failed (plugin rc " + std::to_string(rc) + (rc >= 100 ? std::string(": ") + cudaGetErrorString((cudaError_t)(rc - 100)) : "") + ")");
     p->launches_last++;

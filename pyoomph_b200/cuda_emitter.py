@@ -161,6 +161,10 @@ class CudaEmitter:
         self.EPB = self.EPB_max
         self._layout_threads()
         self._kernel_cfg: Dict[str, Tuple[int, int, int]] = {}
+        self.pipeline = os.environ.get("PB2_PIPELINE", "1") != "0"
+        self.pipe_smem_budget = int(os.environ.get("PB2_PIPE_SMEM", str(200 * 1024)))
+        self.pipe_gather_threads = int(os.environ.get("PB2_PIPE_NG", "64"))
+        self.pipe_scatter_threads = int(os.environ.get("PB2_PIPE_NS", "128"))
 
     # ------------------------------------------------------------------ planning
     def _col_index(self, field: str, lnode: int) -> int:
@@ -401,6 +405,268 @@ class CudaEmitter:
         w("      const int el = i / %d, ipt = i - el * %d;" % (NIPT, NIPT))
         w("      double* E = s_el + el * %d;" % ELS)
         w("      double* P = E + %d + ipt * %d;" % (EL0, PB))
+        self._emit_phase1_body(o, rp, plan, what)
+        w("    }")
+        w("    __syncthreads();")
+        # ---------------- phase 2 + 3, once per output matrix ("J": residual + Jacobian, "M": mass matrix)
+        passes = [("J", form.J, plan["J_off"], "a.jac_vals", True)] if what >= 1 else [("R", {}, {}, None, True)]
+        if what >= 2:
+            passes.append(("M", form.M, plan["M_off"], "a.mass_vals", False))
+        nacc = max(self._group_nacc(form, g, coef) for g in self.groups for (_, coef, _, _, _) in passes)
+        w("    double acc[%d];" % max(1, nacc))
+        for pi_, (pname, coef, coff, target, with_res) in enumerate(passes):
+            w("    // ---- phase 2 (%s): register-tiled contraction over (l_test, l_shape)" % pname)
+            for g in self.groups:
+                self._emit_group_compute(o, rp, plan, g, pname, coef, coff, with_res)
+            if plan["stage_alias"]:
+                w("    __syncthreads();   // point data is dead from here on: the staging area aliases it")
+            w("    // ---- phase 3a (%s): element matrices -> shared memory, dense [row][col]" % pname)
+            for g in self.groups:
+                self._emit_group_stage(o, rp, plan, g, pname, coef, with_res, target is not None)
+            w("    __syncthreads();")
+            w("    // ---- phase 3b (%s): cooperative coloured scatter, consecutive threads = consecutive (row,col) entries" % pname)
+            self._emit_scatter(o, plan, target, with_res)
+            if pi_ + 1 < len(passes):
+                w("    __syncthreads();")
+        w("  }")
+        w("}")
+        w("")
+        return kname
+
+    # ------------------------------------------------------------------ pipelined, warp-specialised kernel
+    def _emit_kernel_pipe(self, o: List[str], rp: RoutinePlan, what: int):
+        """One persistent kernel per assembly.  Warps are specialised:
+             G (gather) warps   : element nodes -> IN[slot]   (positions, nodal values, time combinations)
+             C (compute) warps  : phase 1 (points) + phase 2 (register-tiled contraction) -> OUT[slot]
+             S (scatter) warps  : position maps -> MAPS, OUT[slot] -> CSR values / residual (stores + REDs)
+           connected by double-buffered shared-memory slots and named barriers (bar.sync / bar.arrive), so global-memory
+           latency of gather and scatter is hidden behind the fp64 work.  Batches are ordered (chunk, colour); the scatter
+           of the first batch of a tile waits on a global counter until the previous tile is complete, which keeps the
+           deterministic colour order and lets the CSR rows of a chunk be finished while they are resident in L2."""
+        code, dim, NN, NN1, NIPT = self.code, self.dim, self.NN, self.NN1, self.NIPT
+        form = rp.form
+        plan = self._plan_smem(form, what)
+        EL0, PB = plan["EL0"], plan["PB"]
+        ND, ND2 = self.ndof, self.ndof * self.ndof
+        kname = "pb2_%s_%s_f%d" % (self.name, rp.key, what)
+        tab_n = self._tables_smem_size()
+        IN_S = EL0 | 1
+        PT_S = (NIPT * PB) | 1
+        OUT_S = (ND2 + ND) if what >= 1 else ND
+        npass = 2 if what >= 2 else 1
+        per_el = 8 * (2 * IN_S + PT_S + 2 * OUT_S) + 2 * (2 * ND * 4 + (2 * ND2 if what >= 1 else 0))
+        budget = self.pipe_smem_budget - tab_n * 8 - 256
+        self.EPB = max(2, min(self.EPB_max, 63, budget // per_el))
+        self._layout_threads()
+        NC = sum(g.nthreads for g in self.groups)
+        NG, NS = self.pipe_gather_threads, self.pipe_scatter_threads
+        NT = NC + NG + NS
+        EPB = self.EPB
+        off_in = tab_n
+        off_pts = off_in + 2 * EPB * IN_S
+        off_out = off_pts + EPB * PT_S
+        off_maps = off_out + 2 * EPB * OUT_S          # doubles; ints/bytes follow
+        map_slot_bytes = 2 * EPB * ND * 4 + ((EPB * ND2 * 2 if what >= 1 else 0) + 15) // 16 * 16
+        smem_bytes = off_maps * 8 + 2 * map_slot_bytes
+        self._kernel_smem[kname] = smem_bytes
+        self._kernel_cfg[kname] = (EPB, NT, smem_bytes)
+        plan = dict(plan)
+        plan["PT_expr"] = "s_pts + el * %d" % PT_S
+        plan["SJ_expr"] = "s_out + el * %d" % OUT_S
+        w = o.append
+        w("// %s  what=%d : pipelined; %d compute + %d gather + %d scatter threads, %d elements per batch, %d B smem" % (
+            form.name or "<default residual>", what, NC, NG, NS, EPB, smem_bytes))
+        w("extern \"C\" __global__ void __launch_bounds__(%d, 1) %s(const pb2_kernel_args a)" % (NT, kname))
+        w("{")
+        w("  extern __shared__ double smem[];")
+        w("  double* const s_psi2 = smem;")
+        w("  double* const s_dpsi2 = s_psi2 + %d;" % (NIPT * NN))
+        w("  double* const s_psi1 = s_dpsi2 + %d;" % (NIPT * NN * dim))
+        w("  double* const s_dpsi1 = s_psi1 + %d;" % (NIPT * NN1))
+        w("  (void)s_psi1; (void)s_dpsi1;")
+        w("  const int tid = threadIdx.x;")
+        w("  for (int i = tid; i < %d; i += %d) smem[i] = g_tables[i];" % (tab_n, NT))
+        w("  __syncthreads();")
+        w("  const int G = gridDim.x;")
+        # ---------------------------------------------------------------- gather warps
+        w("  if (tid >= %d && tid < %d)" % (NC, NC + NG))
+        w("  {")
+        w("    const int gt = tid - %d;" % NC)
+        w("    int it = 0;")
+        w("    for (int batch = blockIdx.x; batch < a.n_batches; batch += G, ++it)")
+        w("    {")
+        w("      const int slot = it & 1;")
+        w("      const int e0 = a.batch_elem[batch], nel = a.batch_meta[batch] & 63;")
+        w("      if (it >= 2) pb2_bar_sync(%d + slot, %d);   // IN[slot] released by the compute warps" % (3, NC + NG))
+        w("      double* const s_in = smem + %d + slot * %d;" % (off_in, EPB * IN_S))
+        w("      for (int i = gt; i < nel * %d; i += %d)" % (NN, NG))
+        w("      {")
+        w("        const int el = i / %d, l = i - el * %d;" % (NN, NN))
+        w("        const long long node = __ldg(a.elem_nodes + (long long)(e0 + el) * %d + l);" % NN)
+        w("        double* E = s_in + el * %d;" % IN_S)
+        self._emit_gather_node(o, plan, c1=False)
+        w("      }")
+        if any(code.fields[f].space == "C1" for (f, kind) in plan["sources"]):
+            w("      for (int i = gt; i < nel * %d; i += %d)" % (NN1, NG))
+            w("      {")
+            w("        const int el = i / %d, l = i - el * %d;" % (NN1, NN1))
+            w("        const long long node = __ldg(a.elem_nodes + (long long)(e0 + el) * %d + c_c1node[l]);" % NN)
+            w("        double* E = s_in + el * %d;" % IN_S)
+            self._emit_gather_node(o, plan, c1=True)
+            w("      }")
+        w("      __threadfence_block();")
+        w("      pb2_bar_arrive(%d + slot, %d);            // IN[slot] full" % (1, NC + NG))
+        w("    }")
+        w("  }")
+        # ---------------------------------------------------------------- scatter warps
+        w("  else if (tid >= %d)" % (NC + NG))
+        w("  {")
+        w("    const int st = tid - %d;" % (NC + NG))
+        w("    int it = 0, item = 0, gated_tile = 0;")
+        w("    for (int batch = blockIdx.x; batch < a.n_batches; batch += G, ++it)")
+        w("    {")
+        w("      const int e0 = a.batch_elem[batch], meta = a.batch_meta[batch], nel = meta & 63, tile = meta >> 6;")
+        w("      unsigned char* const mbase = (unsigned char*)(smem + %d) + (it & 1) * %d;" % (off_maps, map_slot_bytes))
+        w("      int* const s_rowstart = (int*)mbase; int* const s_resmap = s_rowstart + %d; unsigned char* const s_map = (unsigned char*)(s_resmap + %d);" % (EPB * ND, EPB * ND))
+        w("      (void)s_map;")
+        w("      // position maps of this batch: loaded while the compute warps work on it")
+        w("      for (int i = st; i < nel * %d; i += %d) { s_rowstart[i] = __ldg(a.elem_rowstart + (long long)e0 * %d + i); s_resmap[i] = __ldg(a.elem_res + (long long)e0 * %d + i); }" % (ND, NS, ND, ND))
+        if what >= 1:
+            w("      {")
+            w("        const int mbytes = nel * %d * (a.map_bits >> 3);" % ND2)
+            w("        const unsigned char* __restrict__ gmap = (const unsigned char*)a.elem_off + (long long)e0 * %d * (a.map_bits >> 3);" % ND2)
+            if ND2 % 4 == 0:
+                w("        for (int i = st; i < (mbytes >> 2); i += %d) ((unsigned*)s_map)[i] = __ldg((const unsigned*)gmap + i);" % NS)
+            else:
+                w("        for (int i = st; i < mbytes; i += %d) s_map[i] = __ldg(gmap + i);" % NS)
+            w("      }")
+        w("      // stream order of the colours: everything of the previous tile must have been scattered")
+        w("      if (tile > gated_tile)")
+        w("      {")
+        w("        if (st == 0) { while (*(volatile int*)(a.tile_done + tile - 1) < a.tile_nbatch[tile - 1]) __nanosleep(64); }")
+        w("        gated_tile = tile;")
+        w("        __threadfence();")
+        w("      }")
+        w("      pb2_bar_sync(11, %d);                       // maps visible to all scatter warps, gate passed" % NS)
+        passes = [("J", "a.jac_vals", True)] if what >= 1 else [("R", None, True)]
+        if what >= 2:
+            passes.append(("M", "a.mass_vals", False))
+        w("      #pragma unroll 1")
+        w("      for (int pass = 0; pass < %d; ++pass, ++item)" % npass)
+        w("      {")
+        w("        const int oslot = item & 1;")
+        w("        pb2_bar_sync(%d + oslot, %d);             // OUT[oslot] full" % (5, NC + NS))
+        w("        const double* const s_out = smem + %d + oslot * %d;" % (off_out, EPB * OUT_S))
+        for pi_, (pname, target, with_res) in enumerate(passes):
+            w("        %sif (pass == %d)" % ("" if pi_ == 0 else "else ", pi_))
+            w("        {")
+            if target is not None:
+                w("          if (a.map_bits == 8)")
+                w("            pb2_scatter_matrix<unsigned char, 0x80u, 0xFFu, %d, %d, %d>((const unsigned char*)s_map, s_rowstart, s_out, %s, nel, st);" % (ND, OUT_S, NS, target))
+                w("          else")
+                w("            pb2_scatter_matrix<unsigned short, 0x8000u, 0xFFFFu, %d, %d, %d>((const unsigned short*)s_map, s_rowstart, s_out, %s, nel, st);" % (ND, OUT_S, NS, target))
+            if with_res:
+                w("          for (int idx = st; idx < nel * %d; idx += %d)" % (ND, NS))
+                w("          {")
+                w("            const int el = idx / %d, row = idx - el * %d;" % (ND, ND))
+                w("            pb2_put(a.residual, s_resmap[idx], s_out[el * %d + %d + row]);" % (OUT_S, ND2 if target is not None else 0))
+                w("          }")
+            w("        }")
+        w("        __threadfence_block();")
+        w("        pb2_bar_arrive(%d + oslot, %d);           // OUT[oslot] free again" % (7, NC + NS))
+        w("      }")
+        w("      // publish: this batch is completely in global memory")
+        w("      __threadfence();")
+        w("      pb2_bar_sync(11, %d);" % NS)
+        w("      if (st == 0) atomicAdd(a.tile_done + tile, 1);")
+        w("    }")
+        w("  }")
+        # ---------------------------------------------------------------- compute warps
+        w("  else")
+        w("  {")
+        cpasses = [("J", form.J, plan["J_off"], True, True)] if what >= 1 else [("R", {}, {}, True, False)]
+        if what >= 2:
+            cpasses.append(("M", form.M, plan["M_off"], False, True))
+        nacc = max(self._group_nacc(form, g, coef) for g in self.groups for (_, coef, _, _, _) in cpasses)
+        w("    double acc[%d];" % max(1, nacc))
+        w("    double* const s_pts = smem + %d;" % off_pts)
+        w("    int it = 0, item = 0;")
+        w("    for (int batch = blockIdx.x; batch < a.n_batches; batch += G, ++it)")
+        w("    {")
+        w("      const int slot = it & 1;")
+        w("      const int nel = a.batch_meta[batch] & 63;")
+        w("      pb2_bar_sync(%d + slot, %d);                // IN[slot] full" % (1, NC + NG))
+        w("      const double* const s_in = smem + %d + slot * %d;" % (off_in, EPB * IN_S))
+        w("      // ---- phase 1: one thread per (element, Gauss point)")
+        w("      for (int i = tid; i < nel * %d; i += %d)" % (NIPT, NC))
+        w("      {")
+        w("        const int el = i / %d, ipt = i - el * %d;" % (NIPT, NIPT))
+        w("        const double* E = s_in + el * %d;" % IN_S)
+        w("        double* P = s_pts + el * %d + ipt * %d;" % (PT_S, PB))
+        sub: List[str] = []
+        self._emit_phase1_body(sub, rp, plan, what)
+        for ln in sub:
+            w("  " + ln)
+        w("      }")
+        w("      __threadfence_block();")
+        w("      if (batch + 2 * G < a.n_batches) pb2_bar_arrive(%d + slot, %d);   // IN[slot] may be refilled" % (3, NC + NG))
+        w("      pb2_bar_sync(9, %d);                        // point data complete" % NC)
+        for pi_, (pname, coef, coff, with_res, with_matrix) in enumerate(cpasses):
+            w("      { // ---- phase 2 (%s): register-tiled contraction, then staging into OUT" % pname)
+            sub = []
+            for g in self.groups:
+                self._emit_group_compute(sub, rp, plan, g, pname, coef, coff, with_res)
+            for ln in sub:
+                w("  " + ln)
+            w("        const int oslot = item & 1;")
+            w("        if (item >= 2) pb2_bar_sync(%d + oslot, %d);  // OUT[oslot] drained by the scatter warps" % (7, NC + NS))
+            w("        double* const s_out = smem + %d + oslot * %d;" % (off_out, EPB * OUT_S))
+            sub = []
+            for g in self.groups:
+                self._emit_group_stage(sub, rp, plan, g, pname, coef, with_res, with_matrix)
+            for ln in sub:
+                w("  " + ln)
+            w("        __threadfence_block();")
+            w("        pb2_bar_arrive(%d + oslot, %d);           // OUT[oslot] full" % (5, NC + NS))
+            w("        ++item;")
+            w("      }")
+        w("      pb2_bar_sync(10, %d);                       // everybody done with the point data" % NC)
+        w("    }")
+        w("  }")
+        w("}")
+        w("")
+        return kname
+
+    def _emit_gather_node(self, o: List[str], plan, c1: bool):
+        code, dim = self.code, self.dim
+        w = o.append
+        if not c1:
+            for d in range(dim):
+                w("        E[%d + l * %d + %d] = a.node_pos[node * %d + %d];" % (plan["xpos"], dim, d, dim, d))
+            if plan["need_lagr"]:
+                for d in range(dim):
+                    w("        E[%d + l * %d + %d] = a.node_lagr[node * %d + %d];" % (plan["xlag"], dim, d, dim, d))
+        for (f, kind) in plan["sources"]:
+            fld = code.fields[f]
+            if (fld.space == "C1") != c1:
+                continue
+            soff = plan["src_off"][(f, kind)]
+            if fld.space == "Pos":
+                base, stride, comp = "a.node_pos", dim, ex.DIRS.index(f[-1])
+            else:
+                base, stride, comp = "a.node_val", self.nval, fld.index
+            if kind[0] == "cur":
+                w("        E[%d + l] = %s[((long long)%d * a.n_node + node) * %d + %d];" % (soff, base, kind[1], stride, comp))
+            else:
+                wn = self._w_name(kind[2], kind[1])
+                w("        { double s = 0.0; for (int t = 0; t < a.ti.ntstorage; ++t) s += %s[t] * %s[((long long)t * a.n_node + node) * %d + %d]; E[%d + l] = s; }" % (
+                    wn, base, stride, comp, soff))
+
+    def _emit_phase1_body(self, o: List[str], rp: RoutinePlan, plan, what: int):
+        """geometry + interpolation + CSE'd pointwise coefficients of one (element, Gauss point); expects E, P, ipt"""
+        code, dim, NN, NN1, NIPT = self.code, self.dim, self.NN, self.NN1, self.NIPT
+        form = rp.form
+        w = o.append
         w("      const double* ps2 = s_psi2 + ipt * %d; const double* dp2 = s_dpsi2 + ipt * %d;" % (NN, NN * dim))
         w("      const double* ps1 = s_psi1 + ipt * %d; const double* dp1 = s_dpsi1 + ipt * %d;" % (NN1, NN1 * dim))
         w("      (void)ps1; (void)dp1; (void)ps2;")
@@ -480,32 +746,6 @@ class CudaEmitter:
         for tgt, e in zip(targets, red):
             w("      P[%d] = %s;" % (tgt, pr.doprint(e)))
         self._flops_phase1 = sum(int(sp.count_ops(e)) for _, e in repl) + sum(int(sp.count_ops(e)) for e in red)
-        w("    }")
-        w("    __syncthreads();")
-        # ---------------- phase 2 + 3, once per output matrix ("J": residual + Jacobian, "M": mass matrix)
-        passes = [("J", form.J, plan["J_off"], "a.jac_vals", True)] if what >= 1 else [("R", {}, {}, None, True)]
-        if what >= 2:
-            passes.append(("M", form.M, plan["M_off"], "a.mass_vals", False))
-        nacc = max(self._group_nacc(form, g, coef) for g in self.groups for (_, coef, _, _, _) in passes)
-        w("    double acc[%d];" % max(1, nacc))
-        for pi_, (pname, coef, coff, target, with_res) in enumerate(passes):
-            w("    // ---- phase 2 (%s): register-tiled contraction over (l_test, l_shape)" % pname)
-            for g in self.groups:
-                self._emit_group_compute(o, rp, plan, g, pname, coef, coff, with_res)
-            if plan["stage_alias"]:
-                w("    __syncthreads();   // point data is dead from here on: the staging area aliases it")
-            w("    // ---- phase 3a (%s): element matrices -> shared memory, dense [row][col]" % pname)
-            for g in self.groups:
-                self._emit_group_stage(o, rp, plan, g, pname, coef, with_res, target is not None)
-            w("    __syncthreads();")
-            w("    // ---- phase 3b (%s): cooperative coloured scatter, consecutive threads = consecutive (row,col) entries" % pname)
-            self._emit_scatter(o, plan, target, with_res)
-            if pi_ + 1 < len(passes):
-                w("    __syncthreads();")
-        w("  }")
-        w("}")
-        w("")
-        return kname
 
     def _emit_geometry(self, o: List[str], plan, src: str, gname: str, detname: str):
         """Restates fill_shape_info_at_s for el_dim==nodal_dim (src/elements.cpp:3604-3626 tangents, :3677-3703 2D
@@ -598,7 +838,6 @@ class CudaEmitter:
         w("      const int el = tl / %d, q = tl - el * %d;" % (TPE, TPE))
         w("      if (el < nel)")
         w("      {")
-        w("        const double* E = s_el + el * %d;" % ELS)
         w("        #pragma unroll")
         w("        for (int i = 0; i < %d; ++i) acc[i] = 0.0;" % nacc)
         if self.ipt_unroll >= NIPT:
@@ -607,7 +846,7 @@ class CudaEmitter:
             w("        #pragma unroll %d" % self.ipt_unroll)
         w("        for (int ipt = 0; ipt < %d; ++ipt)" % NIPT)
         w("        {")
-        w("          const double* P = E + %d + ipt * %d;" % (EL0, PB))
+        w("          const double* P = %s + ipt * %d;" % (plan.get("PT_expr", "s_el + el * %d + %d" % (ELS, EL0)), PB))
         need_x = any(s.deriv.startswith("dx") for s in form.slots if s.field in fields) or any(a_.startswith("dx") for (F, G), l in pairs.items() for (_, a_) in l)
         need_X = any(s.deriv.startswith("dX") for s in form.slots if s.field in fields) or any(a_.startswith("dX") for (F, G), l in pairs.items() for (_, a_) in l)
         if need_x:
@@ -703,7 +942,7 @@ class CudaEmitter:
         w("      const int el = tl / %d, q = tl - el * %d;" % (TPE, TPE))
         w("      if (el < nel)")
         w("      {")
-        w("        double* SJ = s_el + el * %d + %d;" % (plan["ELS"], plan["SJ_off"]))
+        w("        double* SJ = %s;" % plan.get("SJ_expr", "s_el + el * %d + %d" % (plan["ELS"], plan["SJ_off"])))
         w("        #pragma unroll")
         w("        for (int k = 0; k < %d; ++k)" % RB)
         w("        {")
@@ -763,6 +1002,8 @@ class CudaEmitter:
         w("#include <string.h>")
         w('#include "pb2_jit_cuda.h"')
         w("")
+        w("static __device__ __forceinline__ void pb2_bar_sync(const int id, const int nthreads) { asm volatile(\"bar.sync %0, %1;\" :: \"r\"(id), \"r\"(nthreads) : \"memory\"); }")
+        w("static __device__ __forceinline__ void pb2_bar_arrive(const int id, const int nthreads) { asm volatile(\"bar.arrive %0, %1;\" :: \"r\"(id), \"r\"(nthreads) : \"memory\"); }")
         w("static __device__ __forceinline__ void pb2_put(double* __restrict__ dst, const int p, const double v)")
         w("{")
         w("  if (p >= 0) atomicAdd(dst + p, v);")
@@ -808,29 +1049,35 @@ class CudaEmitter:
         kernels: Dict[Tuple[str, int], str] = {}
         for rp in self.routines:
             for what in (0, 1, 2):
-                kernels[(rp.key, what)] = self._emit_kernel(o, rp, what)
+                kernels[(rp.key, what)] = self._emit_kernel_pipe(o, rp, what) if self.pipeline else self._emit_kernel(o, rp, what)
         # host side: launchers + table
-        w("static int pb2_launch_rjm(int residual_index, int param_index, unsigned flag, const pb2_kernel_args* args, void* stream)")
+        w("static int pb2_query(int kind, int residual_index, int param_index, unsigned flag, pb2_kernel_cfg* out)")
         w("{")
-        w("  if (flag > 2u) return 1;")
-        w("  if (args->n_elem <= 0) return 0;")
-        w("  void (*kern)(const pb2_kernel_args) = 0; size_t smem = 0; int epb = 1, nt = 32;")
+        w("  memset(out, 0, sizeof(*out));")
+        w("  if (kind != 0 || flag > 2u) return 1;")
         for rp in self.routines:
             for what in (0, 1, 2):
                 kn = kernels[(rp.key, what)]
-                w("  if (residual_index == %d && param_index == %d && flag == %du) { kern = %s; smem = %d; epb = %d; nt = %d; }" % (
+                w("  if (residual_index == %d && param_index == %d && flag == %du) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
                     rp.res_index, rp.param_index, what, kn, self._kernel_smem[kn], self._kernel_cfg[kn][0], self._kernel_cfg[kn][1]))
-        w("  if (!kern) return 2;")
-        w("  const int nbatch = (args->n_elem + epb - 1) / epb;")
-        w("  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);")
+        w("  if (!out->func) return 2;")
+        w("  out->pipelined = %d;" % (1 if self.pipeline else 0))
+        w("  cudaError_t err = cudaFuncSetAttribute(out->func, cudaFuncAttributeMaxDynamicSharedMemorySize, out->smem_bytes);")
         w("  if (err != cudaSuccess) return 100 + (int)err;")
-        w("  static int grid_cap = 0;")
-        w("  if (!grid_cap) { int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); grid_cap = sms > 0 ? sms : 148; }")
-        w("  int per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem);")
-        w("  if (per_sm < 1) per_sm = 1;")
-        w("  const int grid = nbatch < grid_cap * per_sm ? nbatch : grid_cap * per_sm;   // persistent blocks, one wave")
-        w("  kern<<<grid, nt, smem, (cudaStream_t)stream>>>(*args);")
-        w("  err = cudaGetLastError();")
+        w("  int per_sm = 0;")
+        w("  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, out->func, out->threads, (size_t)out->smem_bytes);")
+        w("  if (err != cudaSuccess) return 100 + (int)err;")
+        w("  if (per_sm < 1) return 3;")
+        w("  out->blocks_per_sm = per_sm;")
+        w("  return 0;")
+        w("}")
+        w("")
+        w("static int pb2_launch(const pb2_kernel_cfg* cfg, const pb2_kernel_args* args, int grid, void* stream)")
+        w("{")
+        w("  if (grid <= 0) return 0;")
+        w("  void* params[1] = {(void*)args};")
+        w("  cudaError_t err = cudaLaunchKernel(cfg->func, dim3((unsigned)grid), dim3((unsigned)cfg->threads), params, (size_t)cfg->smem_bytes, (cudaStream_t)stream);")
+        w("  if (err == cudaSuccess) err = cudaGetLastError();")
         w("  return err == cudaSuccess ? 0 : 100 + (int)err;")
         w("}")
         w("")
@@ -873,8 +1120,8 @@ class CudaEmitter:
         for what in (0, 1, 2):
             w("  ci->alg_bytes_per_elem[%d] = %r;" % (what, self.algorithmic_bytes(what)))
         w("  ci->alg_bytes_per_hist_level = %r;" % float(8 * sum(self._nnode_space(f.space) for f in code.nodal_fields())))
-        w("  table->launch_rjm = &pb2_launch_rjm;")
-        w("  table->launch_hessian = 0;")
+        w("  table->query = &pb2_query;")
+        w("  table->launch = &pb2_launch;")
         w("}")
         return "\n".join(o) + "\n"
 
