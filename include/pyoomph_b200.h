@@ -32,6 +32,8 @@ typedef struct pb2_mesh_desc
   const int *node_eqn;     /* [n_node][nval] global equation per nodal value, <0 pinned (Data::eqn_number) */
   const int *pos_eqn;      /* [n_node][dim] equations of nodal positions (SolidNode), NULL if mesh is fixed */
   long long n_dof;         /* global number of equations */
+  const int *elem_patch;   /* [n_elem] id of the compact patch (~64 neighbouring elements) an element belongs to, or NULL:
+                              then consecutive elements in mesh order form the patches.  Only a locality hint. */
   /* multi-GPU row blocks (oomph LinearAlgebraDistribution, problem.cc:6543): this rank assembles the given elements
    * and owns rows [row_begin,row_end); pass 0,n_dof for a single GPU */
   long long row_begin, row_end;

@@ -55,7 +55,7 @@ class ClassInfo(ctypes.Structure):
 
 class MeshDesc(ctypes.Structure):
     _fields_ = [("n_elem", ctypes.c_longlong), ("n_node", ctypes.c_longlong), ("elem_nodes", c_int_p),
-                ("node_eqn", c_int_p), ("pos_eqn", c_int_p), ("n_dof", ctypes.c_longlong),
+                ("node_eqn", c_int_p), ("pos_eqn", c_int_p), ("n_dof", ctypes.c_longlong), ("elem_patch", c_int_p),
                 ("row_begin", ctypes.c_longlong), ("row_end", ctypes.c_longlong)]
 
 
@@ -158,9 +158,17 @@ class B200Assembly(CustomAssemblyBase):
         self._elem_nodes = np.ascontiguousarray(en, dtype=np.int32)
         self._node_eqn = np.ascontiguousarray(dofmap.node_eqn, dtype=np.int32)
         self._pos_eqn = None if dofmap.pos_eqn is None else np.ascontiguousarray(dofmap.pos_eqn, dtype=np.int32)
+        patches = mesh.element_patches() if hasattr(mesh, "element_patches") else None
+        if patches is not None:
+            patches = patches if elements is None else patches[elements]
+            _, patches = np.unique(patches, return_inverse=True)       # dense ids, order preserved
+            self._elem_patch = np.ascontiguousarray(patches, dtype=np.int32)
+        else:
+            self._elem_patch = None
         md = MeshDesc(self._elem_nodes.shape[0], mesh.n_node, self._elem_nodes.ctypes.data_as(c_int_p),
                       self._node_eqn.ctypes.data_as(c_int_p),
-                      None if self._pos_eqn is None else self._pos_eqn.ctypes.data_as(c_int_p), dofmap.n_dof, 0, dofmap.n_dof)
+                      None if self._pos_eqn is None else self._pos_eqn.ctypes.data_as(c_int_p), dofmap.n_dof,
+                      None if self._elem_patch is None else self._elem_patch.ctypes.data_as(c_int_p), 0, dofmap.n_dof)
         self.prob = ctypes.c_void_p()
         _check(self.lib.pb2_problem_create(self.cls, device, ctypes.byref(md), ctypes.byref(self.prob)))
         rs, ci = c_int_p(), c_int_p()

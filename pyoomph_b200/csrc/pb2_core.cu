@@ -44,8 +44,9 @@ struct pb2_problem
   int device = 0;
   long long n_elem = 0, n_node = 0, n_dof = 0, nnz = 0;
   int ndof_el = 0, nnode = 0, dim = 0, nval = 0, T_val = 1, T_pos = 1;
-  std::vector<int> colour_begin; // [nlaunch+1] launch ranges in permuted element order: (chunk, colour) lexicographic
-  int n_colours = 0;
+  std::vector<int> colour_begin; // [(nunit*ncol)+1] ranges of the (unit, colour) groups in the permuted element order
+  std::vector<int> unit_tile;    // [nunit] tile (= patch colour) of each unit, units sorted by tile
+  int n_colours = 0, n_tiles = 0;
   std::vector<int> perm;         // permuted position -> original element
   std::vector<int> row_start, col_index;
   // device
@@ -62,8 +63,8 @@ struct pb2_problem
   // batch tables of the pipelined kernels, per elements-per-batch value
   struct BatchTables
   {
-    int epb = 0, n_batches = 0, n_tiles = 0;
-    int *d_batch_elem = nullptr, *d_batch_meta = nullptr, *d_tile_nbatch = nullptr, *d_tile_done = nullptr;
+    int epb = 0, grid = 0, n_batches = 0, n_tiles = 0;
+    int *d_batch_elem = nullptr, *d_batch_meta = nullptr, *d_tile_nbatch = nullptr, *d_tile_done = nullptr, *d_block_begin = nullptr;
   };
   std::vector<BatchTables> batch_tables;
   cudaStream_t copy_stream = nullptr;
@@ -169,22 +170,145 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
     for (int l = 0; l < nn; l++) node_mask[m->elem_nodes[e * nn + l]] |= (uint64_t)1 << c;
   }
   std::vector<uint64_t>().swap(node_mask);
-  // launch order = "chunked colour sweeps": elements are cut into chunks of consecutive mesh-order elements and
-  // every chunk runs its colours back to back, so the CSR rows a chunk touches are completed while they are still
-  // resident in the 126 MB L2 (a global sweep per colour would write every 32 B sector up to `ncol` times to HBM).
-  // Launches are stream-ordered and each holds one colour only, so chunk boundaries need no extra care.
+  // ---- schedule (DESIGN.md "Schedule"): elements are grouped into compact patches; patches are coloured (two patches
+  // sharing a node get different colours) and a patch colour is a TILE: all patches of a tile are independent and
+  // are processed concurrently by different thread blocks, each block running the element colours of its patches
+  // back to back (so the CSR rows interior to a patch are completed while they sit in L2), and the tiles follow
+  // each other behind a device-side gate (ncol_patch global synchronisations per assembly instead of one per colour
+  // and chunk).  Several patches of a tile form a UNIT, the piece of work a block takes at a time.
   p->n_colours = ncol;
-  long long chunk = 16384;
-  if (const char *cs = getenv("PB2_CHUNK_ELEMS")) chunk = std::max(1LL, atoll(cs));
-  const long long nchunk = (ne + chunk - 1) / chunk;
-  p->colour_begin.assign((size_t)(nchunk * ncol) + 1, 0);
-  for (long long e = 0; e < ne; e++) p->colour_begin[(size_t)((e / chunk) * ncol + colour[e]) + 1]++;
-  for (size_t c = 0; c + 1 < p->colour_begin.size(); c++) p->colour_begin[c + 1] += p->colour_begin[c];
-  p->perm.resize(ne);
+  std::vector<int> patch_of(ne);
+  int npatch = 0;
+  if (m->elem_patch)
   {
-    std::vector<int> fillpos(p->colour_begin.begin(), p->colour_begin.end() - 1);
-    for (long long e = 0; e < ne; e++) p->perm[fillpos[(size_t)((e / chunk) * ncol + colour[e])]++] = (int)e;
+    for (long long e = 0; e < ne; e++)
+    {
+      patch_of[e] = m->elem_patch[e];
+      if (patch_of[e] < 0)
+      {
+        delete p;
+        return fail("negative patch id");
+      }
+      npatch = std::max(npatch, patch_of[e] + 1);
+    }
   }
+  else
+  {
+    long long psize = 64;
+    if (const char *cs = getenv("PB2_PATCH_ELEMS")) psize = std::max(1LL, atoll(cs));
+    for (long long e = 0; e < ne; e++) patch_of[e] = (int)(e / psize);
+    npatch = (int)((ne + psize - 1) / psize);
+  }
+  // patch colouring through the nodes: greedy in patch order
+  std::vector<int> pcolour(npatch, -1);
+  int npcol = 0;
+  {
+    // node -> patches (each node is touched by few patches)
+    std::vector<int> np_start(m->n_node + 1, 0);
+    std::vector<std::pair<int, int>> node_patch; // (node, patch) unique pairs
+    node_patch.reserve((size_t)ne * nn / 4);
+    {
+      std::vector<int> last_patch_of_node(m->n_node, -1);
+      // elements sorted by patch so that duplicates of (node, patch) are adjacent in time
+      std::vector<int> order(ne);
+      for (long long e = 0; e < ne; e++) order[e] = (int)e;
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return patch_of[x] < patch_of[y]; });
+      for (long long i = 0; i < ne; i++)
+      {
+        const int e = order[i], pa = patch_of[e];
+        for (int l = 0; l < nn; l++)
+        {
+          const int node = m->elem_nodes[(long long)e * nn + l];
+          if (last_patch_of_node[node] != pa)
+          {
+            last_patch_of_node[node] = pa;
+            node_patch.push_back({node, pa});
+          }
+        }
+      }
+    }
+    for (auto &x : node_patch) np_start[x.first + 1]++;
+    for (long long n = 0; n < m->n_node; n++) np_start[n + 1] += np_start[n];
+    std::vector<int> np(node_patch.size());
+    {
+      std::vector<int> fp(np_start.begin(), np_start.end() - 1);
+      for (auto &x : node_patch) np[fp[x.first]++] = x.second;
+    }
+    // patch -> nodes
+    std::vector<int> pn_start(npatch + 1, 0);
+    for (auto &x : node_patch) pn_start[x.second + 1]++;
+    for (int q = 0; q < npatch; q++) pn_start[q + 1] += pn_start[q];
+    std::vector<int> pn(node_patch.size());
+    {
+      std::vector<int> fp(pn_start.begin(), pn_start.end() - 1);
+      for (auto &x : node_patch) pn[fp[x.second]++] = x.first;
+    }
+    for (int q = 0; q < npatch; q++)
+    {
+      uint64_t used = 0;
+      for (int i = pn_start[q]; i < pn_start[q + 1]; i++)
+      {
+        const int node = pn[i];
+        for (int j = np_start[node]; j < np_start[node + 1]; j++)
+        {
+          const int c = pcolour[np[j]];
+          if (c >= 0) used |= (uint64_t)1 << c;
+        }
+      }
+      int c = 0;
+      while (c < 64 && (used >> c & 1)) c++;
+      if (c == 64)
+      {
+        delete p;
+        return fail("more than 64 patch colours needed");
+      }
+      pcolour[q] = c;
+      npcol = std::max(npcol, c + 1);
+    }
+  }
+  // units: consecutive patches of one tile
+  int unit_patches = 7;
+  if (const char *cs = getenv("PB2_UNIT_PATCHES")) unit_patches = std::max(1, atoi(cs));
+  std::vector<int> unit_of_patch(npatch), unit_tile;
+  {
+    std::vector<int> cnt(npcol, 0), cur(npcol, -1);
+    for (int q = 0; q < npatch; q++)
+    {
+      const int t = pcolour[q];
+      if (cur[t] < 0 || cnt[t] == unit_patches)
+      {
+        cur[t] = (int)unit_tile.size();
+        unit_tile.push_back(t);
+        cnt[t] = 0;
+      }
+      unit_of_patch[q] = cur[t];
+      cnt[t]++;
+    }
+  }
+  // order units by tile, elements by (unit, colour, patch, mesh order)
+  const int nunit = (int)unit_tile.size();
+  std::vector<int> unit_rank(nunit);
+  {
+    std::vector<int> ord(nunit);
+    for (int u = 0; u < nunit; u++) ord[u] = u;
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return unit_tile[x] < unit_tile[y]; });
+    for (int r = 0; r < nunit; r++) unit_rank[ord[r]] = r;
+    p->unit_tile.assign(nunit, 0);
+    for (int u = 0; u < nunit; u++) p->unit_tile[unit_rank[u]] = unit_tile[u];
+  }
+  p->n_tiles = npcol;
+  p->perm.resize(ne);
+  for (long long e = 0; e < ne; e++) p->perm[e] = (int)e;
+  std::stable_sort(p->perm.begin(), p->perm.end(), [&](int x, int y) {
+    const int ux = unit_rank[unit_of_patch[patch_of[x]]], uy = unit_rank[unit_of_patch[patch_of[y]]];
+    if (ux != uy) return ux < uy;
+    if (colour[x] != colour[y]) return colour[x] < colour[y];
+    return patch_of[x] < patch_of[y];
+  });
+  // colour_begin: ranges of (unit, colour) groups in the permuted order
+  p->colour_begin.assign((size_t)nunit * ncol + 1, 0);
+  for (long long e = 0; e < ne; e++) p->colour_begin[(size_t)unit_rank[unit_of_patch[patch_of[e]]] * ncol + colour[e] + 1]++;
+  for (size_t c = 0; c + 1 < p->colour_begin.size(); c++) p->colour_begin[c + 1] += p->colour_begin[c];
 
   // ---- permuted element tables
   std::vector<int> elem_nodes((size_t)ne * nn), elem_eqn((size_t)ne * nd);
@@ -434,6 +558,7 @@ extern "C" void pb2_problem_free(pb2_problem *p)
     cudaFree(b.d_batch_meta);
     cudaFree(b.d_tile_nbatch);
     cudaFree(b.d_tile_done);
+    cudaFree(b.d_block_begin);
   }
   delete p;
 }
@@ -448,7 +573,7 @@ extern "C" int pb2_problem_pattern(pb2_problem *p, const int **row_start, const 
 }
 
 extern "C" int pb2_problem_num_colours(pb2_problem *p) { return p->n_colours; }
-extern "C" int pb2_problem_num_launches(pb2_problem *p) { return (int)p->colour_begin.size() - 1; }
+extern "C" int pb2_problem_num_launches(pb2_problem *p) { return p->n_tiles; }
 
 extern "C" int pb2_problem_set_nodal_values(pb2_problem *p, int t, const double *values)
 {
@@ -554,34 +679,65 @@ extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int para
   if (rc != 0)
     return fail("plugin has no kernel for this routine (rc " + std::to_string(rc) + (rc >= 100 ? std::string(": ") + cudaGetErrorString((cudaError_t)(rc - 100)) : "") + ")");
   const int ntile = (int)p->colour_begin.size() - 1;
+  if (!cfg.pipelined && ntile > 4096) return fail("the phase-synchronous kernels (PB2_PIPELINE=0) need PB2_UNIT_PATCHES large enough to keep the launch count reasonable");
   if (cfg.pipelined)
   {
-    // one persistent launch: batches ordered by tile, tile order enforced on the device
+    // one persistent launch; every block walks its own list of batches (units of one tile after the other)
+    const int ncol = p->n_colours, nunit = (int)p->unit_tile.size();
+    long long nb_total = 0;
+    for (int u = 0; u < nunit; u++)
+      for (int c = 0; c < ncol; c++)
+      {
+        const int n = p->colour_begin[(size_t)u * ncol + c + 1] - p->colour_begin[(size_t)u * ncol + c];
+        nb_total += (n + cfg.elems_per_batch - 1) / cfg.elems_per_batch;
+      }
+    // every block must be resident (the tile gate spins): grid <= SMs x occupancy
+    const int grid = (int)std::min<long long>(std::max<long long>(1, nb_total), (long long)p->n_sms * cfg.blocks_per_sm);
     pb2_problem::BatchTables *bt = nullptr;
     for (auto &b : p->batch_tables)
-      if (b.epb == cfg.elems_per_batch) bt = &b;
+      if (b.epb == cfg.elems_per_batch && b.grid == grid) bt = &b;
     if (!bt)
     {
       pb2_problem::BatchTables nb;
       nb.epb = cfg.elems_per_batch;
-      std::vector<int> be, bm, tn;
-      int tile_out = 0;
-      for (int t = 0; t < ntile; t++)
+      nb.grid = grid;
+      std::vector<std::vector<int>> be(grid), bm(grid);
+      std::vector<int> tn(std::max(1, p->n_tiles), 0);
+      int u = 0;
+      for (int t = 0; t < p->n_tiles; t++)
       {
-        const int b0 = p->colour_begin[t], b1 = p->colour_begin[t + 1];
-        if (b1 == b0) continue;
-        int cnt = 0;
-        for (int e = b0; e < b1; e += nb.epb, cnt++)
+        int k = 0;
+        for (; u < nunit && p->unit_tile[u] == t; u++, k++)
         {
-          be.push_back(e);
-          bm.push_back((tile_out << 6) | std::min(nb.epb, b1 - e));
+          const int blk = (k + t * 37) % grid; // round robin, rotated per tile so that remainders do not pile up
+          bool first_of_unit = true;
+          for (int c = 0; c < ncol; c++)
+          {
+            const int b0 = p->colour_begin[(size_t)u * ncol + c], b1 = p->colour_begin[(size_t)u * ncol + c + 1];
+            bool first_of_colour = true;
+            for (int e = b0; e < b1; e += nb.epb)
+            {
+              // bit 6: this batch must wait for the previous batch of the same unit (a new element colour starts)
+              const int fence = (!first_of_unit && first_of_colour) ? 64 : 0;
+              be[blk].push_back(e);
+              bm[blk].push_back((t << 7) | fence | std::min(nb.epb, b1 - e));
+              tn[t]++;
+              first_of_colour = false;
+              first_of_unit = false;
+            }
+          }
         }
-        tn.push_back(cnt);
-        tile_out++;
       }
-      nb.n_batches = (int)be.size();
-      nb.n_tiles = tile_out;
-      if (upload(&nb.d_batch_elem, be) || upload(&nb.d_batch_meta, bm) || upload(&nb.d_tile_nbatch, tn)) return 1;
+      std::vector<int> fe, fm, bb(grid + 1, 0);
+      for (int b = 0; b < grid; b++)
+      {
+        bb[b + 1] = bb[b] + (int)be[b].size();
+        fe.insert(fe.end(), be[b].begin(), be[b].end());
+        fm.insert(fm.end(), bm[b].begin(), bm[b].end());
+      }
+      nb.n_batches = (int)fe.size();
+      nb.n_tiles = p->n_tiles;
+      if (upload(&nb.d_batch_elem, fe) || upload(&nb.d_batch_meta, fm) || upload(&nb.d_tile_nbatch, tn) || upload(&nb.d_block_begin, bb)) return 1;
       CUDA_OK(cudaMalloc((void **)&nb.d_tile_done, std::max(1, nb.n_tiles) * sizeof(int)));
       p->batch_tables.push_back(nb);
       bt = &p->batch_tables.back();
@@ -591,11 +747,10 @@ extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int para
     a.batch_meta = bt->d_batch_meta;
     a.tile_nbatch = bt->d_tile_nbatch;
     a.tile_done = bt->d_tile_done;
+    a.block_begin = bt->d_block_begin;
     a.n_batches = bt->n_batches;
     a.n_tiles = bt->n_tiles;
     a.n_elem = (int)p->n_elem;
-    // every block must be resident (the tile gate spins): grid <= SMs x occupancy
-    const int grid = std::min(bt->n_batches, p->n_sms * cfg.blocks_per_sm);
     rc = p->cls->table.launch(&cfg, &a, grid, cuda_stream);
     if (rc != 0) return fail("kernel launch failed (plugin rc " + std::to_string(rc) + (rc >= 100 ? std::string(": ") + cudaGetErrorString((cudaError_t)(rc - 100)) : "") + ")");
     p->launches_last++;

@@ -487,13 +487,13 @@ class CudaEmitter:
         w("  const int tid = threadIdx.x;")
         w("  for (int i = tid; i < %d; i += %d) smem[i] = g_tables[i];" % (tab_n, NT))
         w("  __syncthreads();")
-        w("  const int G = gridDim.x;")
+        w("  const int ib0 = a.block_begin[blockIdx.x], ib1 = a.block_begin[blockIdx.x + 1];")
         # ---------------------------------------------------------------- gather warps
         w("  if (tid >= %d && tid < %d)" % (NC, NC + NG))
         w("  {")
         w("    const int gt = tid - %d;" % NC)
         w("    int it = 0;")
-        w("    for (int batch = blockIdx.x; batch < a.n_batches; batch += G, ++it)")
+        w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
         w("      const int slot = it & 1;")
         w("      const int e0 = a.batch_elem[batch], nel = a.batch_meta[batch] & 63;")
@@ -522,32 +522,50 @@ class CudaEmitter:
         w("  else if (tid >= %d)" % (NC + NG))
         w("  {")
         w("    const int st = tid - %d;" % (NC + NG))
-        w("    int it = 0, item = 0, gated_tile = 0;")
-        w("    for (int batch = blockIdx.x; batch < a.n_batches; batch += G, ++it)")
+        w("    int it = 0, item = 0, gated_tile = 0, prev_tile = -1, pending = 0;")
+        w("    unsigned char* const maps0 = (unsigned char*)(smem + %d);" % off_maps)
+        # prefetch helper (lambda-like macro through a local struct is overkill: emit the loop twice)
+        def emit_prefetch(indent, batch_expr, slot_expr):
+            w(indent + "{")
+            w(indent + "  const int pe0 = a.batch_elem[%s], pnel = a.batch_meta[%s] & 63;" % (batch_expr, batch_expr))
+            w(indent + "  unsigned char* const pm = maps0 + (%s) * %d;" % (slot_expr, map_slot_bytes))
+            w(indent + "  int* const prs = (int*)pm; int* const pres = prs + %d;" % (EPB * ND))
+            w(indent + "  for (int i = st; i < pnel * %d; i += %d) { pb2_cp_async4(prs + i, a.elem_rowstart + (long long)pe0 * %d + i); pb2_cp_async4(pres + i, a.elem_res + (long long)pe0 * %d + i); }" % (ND, NS, ND, ND))
+            if what >= 1:
+                w(indent + "  const int mbytes = pnel * %d * (a.map_bits >> 3);" % ND2)
+                w(indent + "  const unsigned char* __restrict__ gmap = (const unsigned char*)a.elem_off + (long long)pe0 * %d * (a.map_bits >> 3);" % ND2)
+                w(indent + "  unsigned char* const pmap = (unsigned char*)(pres + %d);" % (EPB * ND))
+                if ND2 % 4 == 0:
+                    w(indent + "  for (int i = st; i < (mbytes >> 2); i += %d) pb2_cp_async4(pmap + 4 * i, gmap + 4 * i);" % NS)
+                else:
+                    w(indent + "  for (int i = st; i < mbytes; i += %d) pmap[i] = __ldg(gmap + i);" % NS)
+            w(indent + "  asm volatile(\"cp.async.commit_group;\" ::: \"memory\");")
+            w(indent + "}")
+        w("    // position maps travel one batch ahead of the scatter (cp.async into the other MAPS slot)")
+        w("    if (ib0 < ib1)")
+        emit_prefetch("    ", "ib0", "0")
+        w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
-        w("      const int e0 = a.batch_elem[batch], meta = a.batch_meta[batch], nel = meta & 63, tile = meta >> 6;")
-        w("      unsigned char* const mbase = (unsigned char*)(smem + %d) + (it & 1) * %d;" % (off_maps, map_slot_bytes))
+        w("      const int meta = a.batch_meta[batch], nel = meta & 63, tile = meta >> 7;")
+        w("      unsigned char* const mbase = maps0 + (it & 1) * %d;" % map_slot_bytes)
         w("      int* const s_rowstart = (int*)mbase; int* const s_resmap = s_rowstart + %d; unsigned char* const s_map = (unsigned char*)(s_resmap + %d);" % (EPB * ND, EPB * ND))
         w("      (void)s_map;")
-        w("      // position maps of this batch: loaded while the compute warps work on it")
-        w("      for (int i = st; i < nel * %d; i += %d) { s_rowstart[i] = __ldg(a.elem_rowstart + (long long)e0 * %d + i); s_resmap[i] = __ldg(a.elem_res + (long long)e0 * %d + i); }" % (ND, NS, ND, ND))
-        if what >= 1:
-            w("      {")
-            w("        const int mbytes = nel * %d * (a.map_bits >> 3);" % ND2)
-            w("        const unsigned char* __restrict__ gmap = (const unsigned char*)a.elem_off + (long long)e0 * %d * (a.map_bits >> 3);" % ND2)
-            if ND2 % 4 == 0:
-                w("        for (int i = st; i < (mbytes >> 2); i += %d) ((unsigned*)s_map)[i] = __ldg((const unsigned*)gmap + i);" % NS)
-            else:
-                w("        for (int i = st; i < mbytes; i += %d) s_map[i] = __ldg(gmap + i);" % NS)
-            w("      }")
+        w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")
+        w("      const bool publish = prev_tile >= 0 && (tile != prev_tile || (meta & 64));")
+        w("      if (publish) __threadfence();               // everything scattered so far becomes globally visible")
+        w("      pb2_bar_sync(11, %d);                       // maps of this batch visible to all scatter warps; previous batch fully issued" % NS)
+        w("      if (batch + 1 < ib1)")
+        emit_prefetch("      ", "batch + 1", "(it + 1) & 1")
+        w("      if (publish && tile != prev_tile) { if (st == 0) atomicAdd(a.tile_done + prev_tile, pending); pending = 0; }")
+        w("      prev_tile = tile; ++pending;")
         w("      // stream order of the colours: everything of the previous tile must have been scattered")
         w("      if (tile > gated_tile)")
         w("      {")
         w("        if (st == 0) { while (*(volatile int*)(a.tile_done + tile - 1) < a.tile_nbatch[tile - 1]) __nanosleep(64); }")
         w("        gated_tile = tile;")
+        w("        pb2_bar_sync(12, %d);                     // gate passed (tile, gated_tile are uniform over the scatter warps)" % NS)
         w("        __threadfence();")
         w("      }")
-        w("      pb2_bar_sync(11, %d);                       // maps visible to all scatter warps, gate passed" % NS)
         passes = [("J", "a.jac_vals", True)] if what >= 1 else [("R", None, True)]
         if what >= 2:
             passes.append(("M", "a.mass_vals", False))
@@ -575,11 +593,8 @@ class CudaEmitter:
         w("        __threadfence_block();")
         w("        pb2_bar_arrive(%d + oslot, %d);           // OUT[oslot] free again" % (7, NC + NS))
         w("      }")
-        w("      // publish: this batch is completely in global memory")
-        w("      __threadfence();")
-        w("      pb2_bar_sync(11, %d);" % NS)
-        w("      if (st == 0) atomicAdd(a.tile_done + tile, 1);")
         w("    }")
+        w("    if (prev_tile >= 0) { __threadfence(); pb2_bar_sync(11, %d); if (st == 0) atomicAdd(a.tile_done + prev_tile, pending); }" % NS)
         w("  }")
         # ---------------------------------------------------------------- compute warps
         w("  else")
@@ -591,7 +606,7 @@ class CudaEmitter:
         w("    double acc[%d];" % max(1, nacc))
         w("    double* const s_pts = smem + %d;" % off_pts)
         w("    int it = 0, item = 0;")
-        w("    for (int batch = blockIdx.x; batch < a.n_batches; batch += G, ++it)")
+        w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
         w("      const int slot = it & 1;")
         w("      const int nel = a.batch_meta[batch] & 63;")
@@ -609,7 +624,7 @@ class CudaEmitter:
             w("  " + ln)
         w("      }")
         w("      __threadfence_block();")
-        w("      if (batch + 2 * G < a.n_batches) pb2_bar_arrive(%d + slot, %d);   // IN[slot] may be refilled" % (3, NC + NG))
+        w("      if (batch + 2 < ib1) pb2_bar_arrive(%d + slot, %d);   // IN[slot] may be refilled" % (3, NC + NG))
         w("      pb2_bar_sync(9, %d);                        // point data complete" % NC)
         for pi_, (pname, coef, coff, with_res, with_matrix) in enumerate(cpasses):
             w("      { // ---- phase 2 (%s): register-tiled contraction, then staging into OUT" % pname)
@@ -1002,12 +1017,21 @@ class CudaEmitter:
         w("#include <string.h>")
         w('#include "pb2_jit_cuda.h"')
         w("")
+        w("static __device__ __forceinline__ void pb2_cp_async4(void* smem_dst, const void* gsrc)")
+        w("{")
+        w("  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);")
+        w("  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 4;\" :: \"r\"(sa), \"l\"(gsrc) : \"memory\");")
+        w("}")
         w("static __device__ __forceinline__ void pb2_bar_sync(const int id, const int nthreads) { asm volatile(\"bar.sync %0, %1;\" :: \"r\"(id), \"r\"(nthreads) : \"memory\"); }")
         w("static __device__ __forceinline__ void pb2_bar_arrive(const int id, const int nthreads) { asm volatile(\"bar.arrive %0, %1;\" :: \"r\"(id), \"r\"(nthreads) : \"memory\"); }")
+        w("// branch-free: first touch of a CSR entry stores, later colours reduce (fire-and-forget red, no return value)")
+        w("static __device__ __forceinline__ void pb2_store_or_red(double* dst, const double v, const bool do_store, const bool do_red)")
+        w("{")
+        w("  asm volatile(\"{\\n\\t.reg .pred ps, pr;\\n\\tsetp.ne.u32 ps, %2, 0;\\n\\tsetp.ne.u32 pr, %3, 0;\\n\\t@ps st.global.f64 [%0], %1;\\n\\t@pr red.global.add.f64 [%0], %1;\\n\\t}\" :: \"l\"(dst), \"d\"(v), \"r\"((unsigned)do_store), \"r\"((unsigned)do_red) : \"memory\");")
+        w("}")
         w("static __device__ __forceinline__ void pb2_put(double* __restrict__ dst, const int p, const double v)")
         w("{")
-        w("  if (p >= 0) atomicAdd(dst + p, v);")
-        w("  else if (p != PB2_MAP_SKIP) dst[~p] = v;")
+        w("  pb2_store_or_red(dst + (p >= 0 ? p : ~p), v, p < 0 && p != PB2_MAP_SKIP, p >= 0);")
         w("}")
         w("// cooperative scatter of dense element matrices staged in shared memory (element stride ELS doubles) into the CSR")
         w("// value array: entry idx of the batch <-> byte idx of the position map, so map reads are perfectly coalesced and")
@@ -1035,11 +1059,8 @@ class CudaEmitter:
         w("        const unsigned code = (unsigned)m[kj[j]];")
         w("        const int r0 = rs[rj[j]];")
         w("        const double v = sv[kj[j]];")
-        w("        if (code != SKIP && r0 >= 0)")
-        w("        {")
-        w("          double* dst = vals + (r0 + (int)(code & (FIRST - 1u)));")
-        w("          if (code & FIRST) *dst = v; else atomicAdd(dst, v);")
-        w("        }")
+        w("        const bool ok = (code != SKIP) && (r0 >= 0);")
+        w("        pb2_store_or_red(vals + (r0 + (int)(code & (FIRST - 1u))), v, ok && (code & FIRST), ok && !(code & FIRST));")
         w("      }")
         w("    }")
         w("  }")
