@@ -70,6 +70,7 @@ typedef struct pb2_kernel_args
   const int *tile_nbatch;     /* [n_tiles]   batches per tile */
   int *tile_done;             /* [n_tiles]   completion counters, zeroed by the host before the launch */
   int n_batches, n_tiles;
+  unsigned long long *debug;  /* NULL, or [64] cycle counters filled by kernels built with PB2_TIMING=1 (development aid) */
   const double *hvec;         /* [n_hvec][n_dof]   Hessian-vector inputs (or NULL) */
   int n_hvec, pad_;
   pb2_time_info ti;

@@ -68,6 +68,7 @@ struct pb2_problem
   };
   std::vector<BatchTables> batch_tables;
   cudaStream_t copy_stream = nullptr;
+  unsigned long long *d_debug = nullptr;
 };
 
 extern "C" int pb2_version(void) { return PB2_ABI_VERSION; }
@@ -267,7 +268,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
     }
   }
   // units: consecutive patches of one tile
-  int unit_patches = 7;
+  int unit_patches = 4;
   if (const char *cs = getenv("PB2_UNIT_PATCHES")) unit_patches = std::max(1, atoi(cs));
   std::vector<int> unit_of_patch(npatch), unit_tile;
   {
@@ -751,10 +752,24 @@ extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int para
     a.n_batches = bt->n_batches;
     a.n_tiles = bt->n_tiles;
     a.n_elem = (int)p->n_elem;
+    if (getenv("PB2_TIMING"))
+    {
+      if (!p->d_debug) CUDA_OK(cudaMalloc((void **)&p->d_debug, 64 * sizeof(unsigned long long)));
+      CUDA_OK(cudaMemsetAsync(p->d_debug, 0, 64 * sizeof(unsigned long long), (cudaStream_t)cuda_stream));
+      a.debug = p->d_debug;
+    }
     rc = p->cls->table.launch(&cfg, &a, grid, cuda_stream);
     if (rc != 0) return fail("kernel launch failed (plugin rc " + std::to_string(rc) + (rc >= 100 ? std::string(": ") + cudaGetErrorString((cudaError_t)(rc - 100)) : "") + ")");
     p->launches_last++;
     p->launches_total++;
+    if (a.debug)
+    {
+      unsigned long long h[64];
+      CUDA_OK(cudaMemcpy(h, p->d_debug, sizeof(h), cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[pb2 timing] grid %d batches %d:", grid, bt->n_batches);
+      for (int i = 0; i < 24; i++) fprintf(stderr, " %.0f", (double)h[i] / grid);
+      fprintf(stderr, "\n");
+    }
     return 0;
   }
   for (int c = 0; c < ntile; c++)

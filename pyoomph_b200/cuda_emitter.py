@@ -147,6 +147,9 @@ class CudaEmitter:
             elems_per_block = int(os.environ["PB2_EPB"])
         self.min_blocks = int(os.environ.get("PB2_MINBLOCKS", "2" if self.dim == 2 else "1"))
         self.table_source = table_source or ("const" if self.dim == 2 else "smem")
+        import os as _os
+        if ipt_unroll is None and _os.environ.get("PB2_IPT_UNROLL"):
+            ipt_unroll = int(_os.environ["PB2_IPT_UNROLL"])
         self.ipt_unroll = ipt_unroll if ipt_unroll is not None else (self.NIPT if self.dim == 2 else 1)
         self.routines: List[RoutinePlan] = []
         for i, rn in enumerate(code.residual_names()):
@@ -162,6 +165,7 @@ class CudaEmitter:
         self._layout_threads()
         self._kernel_cfg: Dict[str, Tuple[int, int, int]] = {}
         self.pipeline = os.environ.get("PB2_PIPELINE", "1") != "0"
+        self.timing = os.environ.get("PB2_TIMING", "0") == "1"
         self.pipe_smem_budget = int(os.environ.get("PB2_PIPE_SMEM", str(200 * 1024)))
         self.pipe_gather_threads = int(os.environ.get("PB2_PIPE_NG", "64"))
         self.pipe_scatter_threads = int(os.environ.get("PB2_PIPE_NS", "128"))
@@ -492,12 +496,14 @@ class CudaEmitter:
         w("  if (tid >= %d && tid < %d)" % (NC, NC + NG))
         w("  {")
         w("    const int gt = tid - %d;" % NC)
-        w("    int it = 0;")
+        w("    int it = 0; long long dbg0 = 0, dbg1 = 0; (void)dbg0; (void)dbg1;")
         w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
         w("      const int slot = it & 1;")
         w("      const int e0 = a.batch_elem[batch], nel = a.batch_meta[batch] & 63;")
+        if self.timing: w("      long long tg0 = clock64();")
         w("      if (it >= 2) pb2_bar_sync(%d + slot, %d);   // IN[slot] released by the compute warps" % (3, NC + NG))
+        if self.timing: w("      long long tg1 = clock64(); dbg0 += tg1 - tg0;")
         w("      double* const s_in = smem + %d + slot * %d;" % (off_in, EPB * IN_S))
         w("      for (int i = gt; i < nel * %d; i += %d)" % (NN, NG))
         w("      {")
@@ -515,13 +521,16 @@ class CudaEmitter:
             self._emit_gather_node(o, plan, c1=True)
             w("      }")
         w("      __threadfence_block();")
+        if self.timing: w("      dbg1 += clock64() - tg1;")
         w("      pb2_bar_arrive(%d + slot, %d);            // IN[slot] full" % (1, NC + NG))
         w("    }")
+        if self.timing: w("    if (gt == 0 && a.debug) { atomicAdd(a.debug + 0, (unsigned long long)dbg0); atomicAdd(a.debug + 1, (unsigned long long)dbg1); atomicAdd(a.debug + 2, (unsigned long long)it); }")
         w("  }")
         # ---------------------------------------------------------------- scatter warps
         w("  else if (tid >= %d)" % (NC + NG))
         w("  {")
         w("    const int st = tid - %d;" % (NC + NG))
+        w("    long long dbs0 = 0, dbs1 = 0, dbs2 = 0, dbs3 = 0; (void)dbs0; (void)dbs1; (void)dbs2; (void)dbs3;")
         w("    int it = 0, item = 0, gated_tile = 0, prev_tile = -1, pending = 0;")
         w("    unsigned char* const maps0 = (unsigned char*)(smem + %d);" % off_maps)
         # prefetch helper (lambda-like macro through a local struct is overkill: emit the loop twice)
@@ -550,6 +559,7 @@ class CudaEmitter:
         w("      unsigned char* const mbase = maps0 + (it & 1) * %d;" % map_slot_bytes)
         w("      int* const s_rowstart = (int*)mbase; int* const s_resmap = s_rowstart + %d; unsigned char* const s_map = (unsigned char*)(s_resmap + %d);" % (EPB * ND, EPB * ND))
         w("      (void)s_map;")
+        if self.timing: w("      long long ts0 = clock64();")
         w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")
         w("      const bool publish = prev_tile >= 0 && (tile != prev_tile || (meta & 64));")
         w("      if (publish) __threadfence();               // everything scattered so far becomes globally visible")
@@ -558,6 +568,7 @@ class CudaEmitter:
         emit_prefetch("      ", "batch + 1", "(it + 1) & 1")
         w("      if (publish && tile != prev_tile) { if (st == 0) atomicAdd(a.tile_done + prev_tile, pending); pending = 0; }")
         w("      prev_tile = tile; ++pending;")
+        if self.timing: w("      long long ts1 = clock64(); dbs0 += ts1 - ts0;")
         w("      // stream order of the colours: everything of the previous tile must have been scattered")
         w("      if (tile > gated_tile)")
         w("      {")
@@ -573,7 +584,9 @@ class CudaEmitter:
         w("      for (int pass = 0; pass < %d; ++pass, ++item)" % npass)
         w("      {")
         w("        const int oslot = item & 1;")
+        if self.timing: w("        long long ts2 = clock64(); if (pass == 0) dbs1 += ts2 - ts1;")
         w("        pb2_bar_sync(%d + oslot, %d);             // OUT[oslot] full" % (5, NC + NS))
+        if self.timing: w("        long long ts3 = clock64(); dbs2 += ts3 - ts2;")
         w("        const double* const s_out = smem + %d + oslot * %d;" % (off_out, EPB * OUT_S))
         for pi_, (pname, target, with_res) in enumerate(passes):
             w("        %sif (pass == %d)" % ("" if pi_ == 0 else "else ", pi_))
@@ -591,10 +604,12 @@ class CudaEmitter:
                 w("          }")
             w("        }")
         w("        __threadfence_block();")
+        if self.timing: w("        dbs3 += clock64() - ts3;")
         w("        pb2_bar_arrive(%d + oslot, %d);           // OUT[oslot] free again" % (7, NC + NS))
         w("      }")
         w("    }")
         w("    if (prev_tile >= 0) { __threadfence(); pb2_bar_sync(11, %d); if (st == 0) atomicAdd(a.tile_done + prev_tile, pending); }" % NS)
+        if self.timing: w("    if (st == 0 && a.debug) { atomicAdd(a.debug + 4, (unsigned long long)dbs0); atomicAdd(a.debug + 5, (unsigned long long)dbs1); atomicAdd(a.debug + 6, (unsigned long long)dbs2); atomicAdd(a.debug + 7, (unsigned long long)dbs3); }")
         w("  }")
         # ---------------------------------------------------------------- compute warps
         w("  else")
@@ -606,11 +621,14 @@ class CudaEmitter:
         w("    double acc[%d];" % max(1, nacc))
         w("    double* const s_pts = smem + %d;" % off_pts)
         w("    int it = 0, item = 0;")
+        w("    long long dbc0 = 0, dbc1 = 0, dbc2 = 0, dbc3 = 0, dbc4 = 0; (void)dbc0; (void)dbc1; (void)dbc2; (void)dbc3; (void)dbc4;")
         w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
         w("      const int slot = it & 1;")
         w("      const int nel = a.batch_meta[batch] & 63;")
+        if self.timing: w("      long long tc0 = clock64();")
         w("      pb2_bar_sync(%d + slot, %d);                // IN[slot] full" % (1, NC + NG))
+        if self.timing: w("      long long tc1 = clock64(); dbc0 += tc1 - tc0;")
         w("      const double* const s_in = smem + %d + slot * %d;" % (off_in, EPB * IN_S))
         w("      // ---- phase 1: one thread per (element, Gauss point)")
         w("      for (int i = tid; i < nel * %d; i += %d)" % (NIPT, NC))
@@ -626,6 +644,7 @@ class CudaEmitter:
         w("      __threadfence_block();")
         w("      if (batch + 2 < ib1) pb2_bar_arrive(%d + slot, %d);   // IN[slot] may be refilled" % (3, NC + NG))
         w("      pb2_bar_sync(9, %d);                        // point data complete" % NC)
+        if self.timing: w("      long long tc2 = clock64(); dbc1 += tc2 - tc1;")
         for pi_, (pname, coef, coff, with_res, with_matrix) in enumerate(cpasses):
             w("      { // ---- phase 2 (%s): register-tiled contraction, then staging into OUT" % pname)
             sub = []
@@ -634,7 +653,9 @@ class CudaEmitter:
             for ln in sub:
                 w("  " + ln)
             w("        const int oslot = item & 1;")
+            if self.timing: w("        long long tc3 = clock64(); dbc2 += tc3 - tc2;")
             w("        if (item >= 2) pb2_bar_sync(%d + oslot, %d);  // OUT[oslot] drained by the scatter warps" % (7, NC + NS))
+            if self.timing: w("        long long tc4 = clock64(); dbc3 += tc4 - tc3;")
             w("        double* const s_out = smem + %d + oslot * %d;" % (off_out, EPB * OUT_S))
             sub = []
             for g in self.groups:
@@ -642,11 +663,13 @@ class CudaEmitter:
             for ln in sub:
                 w("  " + ln)
             w("        __threadfence_block();")
+            if self.timing: w("        tc2 = clock64(); dbc4 += tc2 - tc4;")
             w("        pb2_bar_arrive(%d + oslot, %d);           // OUT[oslot] full" % (5, NC + NS))
             w("        ++item;")
             w("      }")
         w("      pb2_bar_sync(10, %d);                       // everybody done with the point data" % NC)
         w("    }")
+        if self.timing: w("    if (tid == 0 && a.debug) { atomicAdd(a.debug + 8, (unsigned long long)dbc0); atomicAdd(a.debug + 9, (unsigned long long)dbc1); atomicAdd(a.debug + 10, (unsigned long long)dbc2); atomicAdd(a.debug + 11, (unsigned long long)dbc3); atomicAdd(a.debug + 12, (unsigned long long)dbc4); }")
         w("  }")
         w("}")
         w("")
