@@ -1,0 +1,129 @@
+"""CPU tests of the host side: mesh/equation ordering rules, symbolic coefficient form, CUDA emission (cross-compiled
+with nvcc for sm_100a, no GPU needed), compiler registry, and that the C-ABI library loads and exports every symbol
+include/*.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import sympy as sp
+
+from problems import make_problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_mesh_node_and_element_order_follow_reference_rules():
+    from pyoomph_b200.meshes import CuboidBrickMesh, RectangularQuadMesh
+    m = RectangularQuadMesh(2)
+    # simplemeshes.py:224-240 + meshtemplate.cpp:401-409: vertices first, first-touch order; local layout
+    # [n00,m_b,n10,m_l,c,m_r,n01,m_t,n11]
+    assert m.elem_nodes[0].tolist() == [0, 9, 1, 10, 11, 12, 2, 13, 3]
+    assert m.elem_nodes[1].tolist() == [2, 13, 3, 14, 15, 16, 4, 17, 5]      # iy inner: shares the top edge of element 0
+    assert m.elem_nodes[2].tolist() == [1, 18, 6, 12, 19, 20, 3, 21, 7]      # ix outer: shares the right edge of element 0
+    assert m.n_node == 25 and np.all(m.is_vertex()[:9]) and not np.any(m.is_vertex()[9:])
+    np.testing.assert_allclose(m.node_pos[11], [0.25, 0.25])
+    b = CuboidBrickMesh(2)
+    assert b.n_node == 125 and b.elem_nodes.shape == (8, 27)
+    # every element's nodes sit on its 3x3x3 lattice in oomph order (first coordinate fastest)
+    for e in range(8):
+        lat = b.node_lattice[b.elem_nodes[e]]
+        lat = lat - lat[0]
+        exp = np.array([[k % 3, (k // 3) % 3, k // 9] for k in range(27)])
+        assert np.array_equal(lat, exp)
+    # meshtemplate.cpp:583-617 creation order inside the first brick: edge mids 1,3 then face centre 4 ...
+    assert b.elem_nodes[0][[1, 3, 4, 5, 7, 9]].tolist() == [27, 28, 29, 30, 31, 32]
+
+
+def test_equation_numbering_order():
+    from pyoomph_b200.meshes import assign_equation_numbers
+    pb = make_problem("ale", 2)
+    dm, code, mesh = pb["dofmap"], pb["code"], pb["mesh"]
+    # node by node; positions first, then values by index; pinned skipped; C1 slots on non-vertex nodes are dummies
+    flat = np.concatenate([dm.pos_eqn, dm.node_eqn], axis=1).ravel()
+    nz = flat[flat >= 0]
+    assert np.array_equal(nz, np.arange(dm.n_dof))
+    p_idx = code.fields["pressure"].index
+    assert np.all(dm.node_eqn[~mesh.is_vertex(), p_idx] == -1)
+    assert np.all(dm.pos_eqn[mesh.boundaries["left"], 0] == -1)
+
+
+def test_coefficient_form_matches_direct_differentiation():
+    """J coefficients of the product path == derivative of the residual coefficient w.r.t. the interpolated atom."""
+    pb = make_problem("ns_unsteady", 2)
+    code = pb["code"]
+    form = code.derive("")
+    assert {s.field for s in form.slots} == {"velocity_x", "velocity_y", "pressure"}
+    for (si, G, a), c in form.J.items():
+        if a == "d0":
+            at = [s for s, info in code._atom_syms.items() if info.field == G and info.deriv == "d0" and info.dt_order == 0]
+            direct = sum(sp.diff(form.R[si], s) for s in at)
+            dt = [s for s, info in code._atom_syms.items() if info.field == G and info.deriv == "d0" and info.dt_order == 1]
+            w = sp.Symbol("W__BDF2_degr__1", real=True)
+            direct += sum(w * sp.diff(form.R[si], s) for s in dt)
+            assert sp.simplify(c - direct) == 0
+    # mass matrix: only d/d(partial_t u) terms, velocity test x velocity unknown
+    assert {(form.slots[si].field, G) for (si, G, a) in form.M} == {("velocity_x", "velocity_x"), ("velocity_y", "velocity_y")}
+    assert code.history_levels() == 3 and code.max_dt_order() == 1
+
+
+def test_moving_mesh_columns_present():
+    code = make_problem("ale", 2)["code"]
+    form = code.derive("")
+    cols = {G for (_, G, _) in form.J}
+    assert {"coordinate_x", "coordinate_y", "velocity_x", "velocity_y", "pressure"} <= cols
+    assert form.uses_dX and form.uses_dx
+    assert code.dof_layout()[:5] == [("coordinate_x", 0), ("coordinate_y", 0), ("velocity_x", 0), ("velocity_y", 0), ("pressure", 0)]
+
+
+def test_compiler_registry_and_cross_compile():
+    from pyoomph_b200.ccompiler import BaseCCompiler, CudaCCompiler, get_ccompiler
+    assert "cuda" in BaseCCompiler._registry
+    with pytest.raises(RuntimeError):
+        BaseCCompiler.factory_compiler("tcc")          # no CPU compiler is registered: no CPU fallback
+    cc = get_ccompiler("cuda")
+    assert isinstance(cc, CudaCCompiler)
+    from pyoomph_b200.cuda_emitter import CudaEmitter
+    code = make_problem("poisson", 2)["code"]
+    em = CudaEmitter(code, "poisson")
+    src = em.emit()
+    assert "JIT_ELEMENT_init_cuda" in src and "bar.sync" in src and "red.global.add.f64" in src
+    so = cc.compile_code(src, "poisson")
+    lib = ctypes.CDLL(so)
+    assert hasattr(lib, "JIT_ELEMENT_init_cuda")
+    # B_el of SURVEY 8(d): Poisson Q9 steady = 1296 B
+    assert em.algorithmic_bytes(1) == 1296.0
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from pyoomph_b200.ccompiler import build_core_library
+    lib = ctypes.CDLL(build_core_library())
+    hdr = open(os.path.join(ROOT, "include", "pyoomph_b200.h")).read()
+    names = re.findall(r"\b(pb2_[a-z0-9_]+)\s*\(", hdr)
+    assert len(set(names)) >= 25
+    for n in set(names):
+        assert hasattr(lib, n), n
+    assert lib.pb2_version() == int(re.search(r"#define PB2_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "pb2_jit_cuda.h")).read()).group(1))
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors of the C structs have the sizes the compiler gives them."""
+    import subprocess
+    import tempfile
+    from pyoomph_b200.assembly import ClassInfo, MeshDesc, TimeInfo
+    src = '#include <stdio.h>\n#include "pyoomph_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(pb2_class_info), sizeof(pb2_mesh_desc), sizeof(pb2_time_info));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "s.c"), "-o", os.path.join(d, "s")], check=True)
+        out = subprocess.run([os.path.join(d, "s")], capture_output=True, text=True).stdout.split()
+    assert [int(x) for x in out] == [ctypes.sizeof(ClassInfo), ctypes.sizeof(MeshDesc), ctypes.sizeof(TimeInfo)]
+
+
+def test_product_path_never_touches_the_oracle():
+    """the oracle is test infrastructure: nothing under pyoomph_b200/ may import or execute it"""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pyoomph_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, f
