@@ -185,14 +185,19 @@ def main():
     t_setup = time.time()
     pb = build_workload(args.workload, n)
     mesh = pb["mesh"]
-    if world > 1:
-        # element-block partition in mesh order (x-strips): contiguous element range per rank
-        lo, hi = mesh.n_elem * rank // world, mesh.n_elem * (rank + 1) // world
-        elements = np.arange(lo, hi)
-    else:
-        elements = None
     from pyoomph_b200.assembly import B200Assembly
-    asm = B200Assembly(pb["code"], mesh, pb["dofmap"], name=pb["code"].name, device=device, elements=elements)
+    dasm = None
+    if world > 1:
+        # element blocks in mesh order (x-strips), contiguous CSR row block per GPU, interface rows exchanged over NCCL
+        from pyoomph_b200.distributed import DistributedAssembly, GPULocalAssembler
+
+        def make_local(el, dm, extra):
+            a_ = B200Assembly(pb["code"], mesh, dm, name=pb["code"].name, device=device, elements=el, extra_pattern=extra)
+            return GPULocalAssembler(a_, device)
+        dasm = DistributedAssembly.create(pb["code"], mesh, pb["dofmap"], rank, world, make_local, dist=dist, device="cuda:%d" % device)
+        asm = dasm.local.asm
+    else:
+        asm = B200Assembly(pb["code"], mesh, pb["dofmap"], name=pb["code"].name, device=device)
     for t in range(pb["vals"].shape[0]):
         asm.set_nodal_values(t, pb["vals"][t])
     if pb["unsteady"]:
@@ -209,16 +214,22 @@ def main():
         lib.pb2_device_synchronize()
 
     # ---- device-resident timing (value)
+    def step():
+        if dasm is not None:
+            dasm.assemble(flag=1)
+        else:
+            asm.assemble(flag=1)
+
     for _ in range(max(3, args.warmup)):
-        asm.assemble(flag=1)
+        step()
     barrier()
     sampler = ClockSampler(device)
     sampler.start()
     launches = 0
     lib.pb2_event_record(0, None)
     for _ in range(args.steps):
-        asm.assemble(flag=1)
-        launches += asm.launch_count()
+        step()
+        launches += asm.launch_count() + (3 * (len(dasm.send) + len(dasm.recv)) if dasm is not None else 0)
     lib.pb2_event_record(1, None)
     ms = ctypes.c_float()
     lib.pb2_event_elapsed_ms(0, 1, ctypes.byref(ms))
@@ -235,7 +246,7 @@ def main():
 
     # ---- end-to-end through the reference-facing call (host buffers, copies inside the timed region)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and world == 1:
         eq = pb["dofmap"].node_eqn
         ndof, nnz = asm.n_dof, asm.nnz
 
@@ -280,7 +291,8 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": pb["label"], "elements": int(total_elems), "dofs": int(asm.n_dof), "nnz": int(asm.nnz), "ndof_el": int(info.ndof_el),
                        "colours": asm.num_colours(), "tiles": asm.num_launches(), "cache": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2" % (b_el * n_elem_rank / 1e9),
-                       "setup_s": round(t_setup, 1), "parallelism": "element blocks x%d" % world},
+                       "setup_s": round(t_setup, 1), "parallelism": "element blocks x%d" % world,
+                       "exchange_bytes_per_step_rank0": int(dasm.exchange_bytes) if dasm is not None else 0},
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches)}
     if e2e is not None:
         line["e2e"] = e2e

@@ -34,9 +34,11 @@ typedef struct pb2_mesh_desc
   long long n_dof;         /* global number of equations */
   const int *elem_patch;   /* [n_elem] id of the compact patch (~64 neighbouring elements) an element belongs to, or NULL:
                               then consecutive elements in mesh order form the patches.  Only a locality hint. */
-  /* multi-GPU row blocks (oomph LinearAlgebraDistribution, problem.cc:6543): this rank assembles the given elements
-   * and owns rows [row_begin,row_end); pass 0,n_dof for a single GPU */
-  long long row_begin, row_end;
+  /* multi-GPU: entries (extra_rows[i], extra_cols[i]) are added to the CSR pattern although no local element produces
+   * them -- the columns that neighbouring ranks contribute to interface rows owned by this rank (problem.cc:6970-7121).
+   * n_extra = 0 on a single GPU. */
+  long long n_extra;
+  const int *extra_rows, *extra_cols;
 } pb2_mesh_desc;
 
 int pb2_version(void);

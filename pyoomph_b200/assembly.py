@@ -56,7 +56,7 @@ class ClassInfo(ctypes.Structure):
 class MeshDesc(ctypes.Structure):
     _fields_ = [("n_elem", ctypes.c_longlong), ("n_node", ctypes.c_longlong), ("elem_nodes", c_int_p),
                 ("node_eqn", c_int_p), ("pos_eqn", c_int_p), ("n_dof", ctypes.c_longlong), ("elem_patch", c_int_p),
-                ("row_begin", ctypes.c_longlong), ("row_end", ctypes.c_longlong)]
+                ("n_extra", ctypes.c_longlong), ("extra_rows", c_int_p), ("extra_cols", c_int_p)]
 
 
 _LIB = None
@@ -143,7 +143,7 @@ class B200Assembly(CustomAssemblyBase):
 
     def __init__(self, code: FiniteElementCode, mesh, dofmap, *, name: str = "elem", device: int = 0,
                  compiler: Optional[CudaCCompiler] = None, emitter_options: Optional[dict] = None,
-                 elements: Optional[np.ndarray] = None):
+                 elements: Optional[np.ndarray] = None, extra_pattern: Optional[Tuple[np.ndarray, np.ndarray]] = None):
         super().__init__()
         self.code, self.mesh, self.dofmap = code, mesh, dofmap
         self.lib = load_library()
@@ -168,7 +168,13 @@ class B200Assembly(CustomAssemblyBase):
         md = MeshDesc(self._elem_nodes.shape[0], mesh.n_node, self._elem_nodes.ctypes.data_as(c_int_p),
                       self._node_eqn.ctypes.data_as(c_int_p),
                       None if self._pos_eqn is None else self._pos_eqn.ctypes.data_as(c_int_p), dofmap.n_dof,
-                      None if self._elem_patch is None else self._elem_patch.ctypes.data_as(c_int_p), 0, dofmap.n_dof)
+                      None if self._elem_patch is None else self._elem_patch.ctypes.data_as(c_int_p), 0, None, None)
+        if extra_pattern is not None and len(extra_pattern[0]):
+            self._ex_rows = np.ascontiguousarray(extra_pattern[0], dtype=np.int32)
+            self._ex_cols = np.ascontiguousarray(extra_pattern[1], dtype=np.int32)
+            md.n_extra = self._ex_rows.size
+            md.extra_rows = self._ex_rows.ctypes.data_as(c_int_p)
+            md.extra_cols = self._ex_cols.ctypes.data_as(c_int_p)
         self.prob = ctypes.c_void_p()
         _check(self.lib.pb2_problem_create(self.cls, device, ctypes.byref(md), ctypes.byref(self.prob)))
         rs, ci = c_int_p(), c_int_p()

@@ -112,15 +112,20 @@ class CudaCCompiler(BaseCCompiler):
         so = os.path.join(JIT_DIR, "%s_%s.so" % (name, tag))
         if os.path.exists(so) and not force:
             return so
-        with open(cu, "w") as f:
+        # several ranks may compile the same class at once: build under a private name, publish atomically
+        tmp_so = "%s.%d.tmp" % (so, os.getpid())
+        tmp_cu = os.path.join(JIT_DIR, "%s_%s.%d.cu" % (name, tag, os.getpid()))
+        with open(tmp_cu, "w") as f:
             f.write(source)
-        cmd = [self.nvcc] + self.flags() + [cu, "-o", so]
+        os.replace(tmp_cu, cu)
+        cmd = [self.nvcc] + self.flags() + [cu, "-o", tmp_so]
         r = subprocess.run(cmd, capture_output=True, text=True)
         self.last_log = r.stdout + r.stderr
         with open(os.path.join(JIT_DIR, "%s_%s.log" % (name, tag)), "w") as f:
             f.write(" ".join(cmd) + "\n" + self.last_log)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (cu, self.last_log[-6000:]))
+        os.replace(tmp_so, so)
         if not quiet:
             print(self.last_log)
         return so

@@ -69,6 +69,8 @@ struct pb2_problem
   std::vector<BatchTables> batch_tables;
   cudaStream_t copy_stream = nullptr;
   unsigned long long *d_debug = nullptr;
+  int *d_untouched = nullptr;      // CSR positions no local element writes (pattern entries owned for other ranks' contributions)
+  long long n_untouched = 0;
 };
 
 extern "C" int pb2_version(void) { return PB2_ABI_VERSION; }
@@ -343,6 +345,22 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
       }
   }
 
+  // extra pattern entries (interface columns contributed by other ranks), bucketed by row
+  std::vector<int> ex_start(nrow + 1, 0), ex_col(std::max<long long>(0, m->n_extra));
+  for (long long i = 0; i < m->n_extra; i++)
+  {
+    if (m->extra_rows[i] < 0 || m->extra_rows[i] >= nrow || m->extra_cols[i] < 0 || m->extra_cols[i] >= nrow)
+    {
+      delete p;
+      return fail("extra pattern entry out of range");
+    }
+    ex_start[m->extra_rows[i] + 1]++;
+  }
+  for (long long r = 0; r < nrow; r++) ex_start[r + 1] += ex_start[r];
+  {
+    std::vector<int> fp(ex_start.begin(), ex_start.end() - 1);
+    for (long long i = 0; i < m->n_extra; i++) ex_col[fp[m->extra_rows[i]]++] = m->extra_cols[i];
+  }
   // ---- CSR pattern, ascending columns: pass 1 counts, pass 2 fills
   p->row_start.assign(nrow + 1, 0);
   for (int pass = 0; pass < 2; pass++)
@@ -360,6 +378,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
           for (int k = 0; k < nd; k++)
             if (eq[k] >= 0) tmp.push_back(eq[k]);
         }
+        for (int a = ex_start[r]; a < ex_start[r + 1]; a++) tmp.push_back(ex_col[a]);
         std::sort(tmp.begin(), tmp.end());
         const int n = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
         if (pass == 0)
@@ -429,6 +448,18 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
       {
         b |= bit;
         elem_csr[i] = ~v;
+      }
+    }
+    if (m->n_extra > 0)
+    {
+      std::vector<int> unt;
+      for (long long i = 0; i < p->nnz; i++)
+        if (!(touched[(size_t)i >> 3] & (1u << (i & 7)))) unt.push_back((int)i);
+      p->n_untouched = (long long)unt.size();
+      if (upload(&p->d_untouched, unt))
+      {
+        delete p;
+        return 1;
       }
     }
     for (size_t i = 0; i < elem_res.size(); i++)
@@ -553,6 +584,7 @@ extern "C" void pb2_problem_free(pb2_problem *p)
   cudaFree(p->d_jac);
   cudaFree(p->d_mass);
   cudaFree(p->d_dofs);
+  cudaFree(p->d_untouched);
   for (auto &b : p->batch_tables)
   {
     cudaFree(b.d_batch_elem);
@@ -599,6 +631,14 @@ extern "C" int pb2_problem_set_lagrangian_positions(pb2_problem *p, const double
   CUDA_OK(cudaSetDevice(p->device));
   CUDA_OK(cudaMemcpy(p->d_node_lagr, pos, (size_t)p->n_node * p->dim * sizeof(double), cudaMemcpyHostToDevice));
   return 0;
+}
+
+static __global__ void pb2_zero_positions(double *__restrict__ a, double *__restrict__ b, const int *__restrict__ pos, long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  a[pos[i]] = 0.0;
+  if (b) b[pos[i]] = 0.0;
 }
 
 static __global__ void pb2_scatter_dofs(const double *__restrict__ dofs, const long long *__restrict__ target, long long n,
@@ -675,6 +715,15 @@ extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int para
   a.ti = p->ti;
   memcpy(a.params, p->params, sizeof(a.params));
   p->launches_last = 0;
+  if (p->n_untouched > 0 && flag >= 1u)
+  {
+    // entries that only other ranks contribute to start from zero in every assembly
+    const int bs = 256;
+    pb2_zero_positions<<<(unsigned)((p->n_untouched + bs - 1) / bs), bs, 0, (cudaStream_t)cuda_stream>>>(p->d_jac, flag >= 2u ? p->d_mass : nullptr, p->d_untouched, p->n_untouched);
+    CUDA_OK(cudaGetLastError());
+    p->launches_last++;
+    p->launches_total++;
+  }
   pb2_kernel_cfg cfg;
   int rc = p->cls->table.query(0, residual_index, param_index, flag, &cfg);
   if (rc != 0)
