@@ -220,11 +220,16 @@ def main():
         else:
             asm.assemble(flag=1)
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
     sampler = ClockSampler(device)
-    sampler.start()
+    sampler.start()                      # nvidia-smi needs a few 100 ms to deliver its first sample: start before the warm-up
+    t_w = time.time()
+    n_w = 0
+    while n_w < max(3, args.warmup) or time.time() - t_w < 0.6:
+        step()
+        n_w += 1
+        if n_w % 8 == 0:
+            lib.pb2_device_synchronize()
+    barrier()
     launches = 0
     lib.pb2_event_record(0, None)
     for _ in range(args.steps):

@@ -20,6 +20,7 @@ No tensor cores: per-element work is small irregular fp64 contraction (BASELINE 
 from __future__ import annotations
 
 import dataclasses
+import os
 from typing import Dict, List, Optional, Tuple
 
 import sympy as sp
@@ -142,15 +143,18 @@ class CudaEmitter:
         self.ndof = len(self.layout)
         self.nval = code.n_nodal_values
         import os
+        if self.dim == 3:
+            acc_max = min(acc_max, 60)        # 3 rows x 27 columns per thread spills at the 168-register cap of the pipelined kernel
         self.acc_max = int(os.environ.get("PB2_ACC_MAX", acc_max))
         if elems_per_block is None and os.environ.get("PB2_EPB"):
             elems_per_block = int(os.environ["PB2_EPB"])
         self.min_blocks = int(os.environ.get("PB2_MINBLOCKS", "2" if self.dim == 2 else "1"))
-        self.table_source = table_source or ("const" if self.dim == 2 else "smem")
+        import os as _os0
+        self.table_source = table_source or _os0.environ.get("PB2_TABLES") or ("const" if self.dim == 2 else "smem")
         import os as _os
         if ipt_unroll is None and _os.environ.get("PB2_IPT_UNROLL"):
             ipt_unroll = int(_os.environ["PB2_IPT_UNROLL"])
-        self.ipt_unroll = ipt_unroll if ipt_unroll is not None else (self.NIPT if self.dim == 2 else 1)
+        self.ipt_unroll = ipt_unroll if ipt_unroll is not None else (3 if self.dim == 2 else 1)
         self.routines: List[RoutinePlan] = []
         for i, rn in enumerate(code.residual_names()):
             self.routines.append(RoutinePlan("r%d" % i, code.derive(rn), i, -1))
@@ -458,12 +462,14 @@ class CudaEmitter:
         PT_S = (NIPT * PB) | 1
         OUT_S = (ND2 + ND) if what >= 1 else ND
         npass = 2 if what >= 2 else 1
-        per_el = 8 * (2 * IN_S + PT_S + 2 * OUT_S) + 2 * (2 * ND * 4 + (2 * ND2 if what >= 1 else 0))
+        per_el = 8 * (2 * IN_S + PT_S + 2 * OUT_S) + 2 * (2 * ND * 4 + (2 * ND2 if what >= 1 else 0)) + 2 * NN * 4
         budget = self.pipe_smem_budget - tab_n * 8 - 256
         self.EPB = max(2, min(self.EPB_max, 63, budget // per_el))
         self._layout_threads()
         NC = sum(g.nthreads for g in self.groups)
         NG, NS = self.pipe_gather_threads, self.pipe_scatter_threads
+        if NC + NG + NS > 384 and "PB2_PIPE_NS" not in os.environ:
+            NG, NS = 32, max(64, 384 - NC - 32)   # keep the register cap (65536 / block size) at 170 for the compute warps
         NT = NC + NG + NS
         EPB = self.EPB
         off_in = tab_n
@@ -471,7 +477,7 @@ class CudaEmitter:
         off_out = off_pts + EPB * PT_S
         off_maps = off_out + 2 * EPB * OUT_S          # doubles; ints/bytes follow
         map_slot_bytes = 2 * EPB * ND * 4 + ((EPB * ND2 * 2 if what >= 1 else 0) + 15) // 16 * 16
-        smem_bytes = off_maps * 8 + 2 * map_slot_bytes
+        smem_bytes = off_maps * 8 + 2 * map_slot_bytes + 2 * EPB * NN * 4
         self._kernel_smem[kname] = smem_bytes
         self._kernel_cfg[kname] = (EPB, NT, smem_bytes)
         plan = dict(plan)
@@ -497,10 +503,17 @@ class CudaEmitter:
         w("  {")
         w("    const int gt = tid - %d;" % NC)
         w("    int it = 0; long long dbg0 = 0, dbg1 = 0; (void)dbg0; (void)dbg1;")
+        w("    int* const s_idx0 = (int*)((unsigned char*)(smem + %d) + %d);" % (off_maps, 2 * map_slot_bytes))
+        w("    // element -> node indices travel one batch ahead (cp.async), so the nodal data of a batch needs one memory round trip")
+        w("    if (ib0 < ib1) { const int pe0 = a.batch_elem[ib0], pn = (a.batch_meta[ib0] & 63) * %d; for (int i = gt; i < pn; i += %d) pb2_cp_async4(s_idx0 + i, a.elem_nodes + (long long)pe0 * %d + i); }" % (NN, NG, NN))
+        w("    asm volatile(\"cp.async.commit_group;\" ::: \"memory\");")
         w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
         w("      const int slot = it & 1;")
-        w("      const int e0 = a.batch_elem[batch], nel = a.batch_meta[batch] & 63;")
+        w("      const int nel = a.batch_meta[batch] & 63;")
+        w("      const int* const s_idx = s_idx0 + slot * %d;" % (EPB * NN))
+        w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")
+        w("      pb2_bar_sync(13, %d);                        // indices of this batch visible to all gather warps" % NG)
         if self.timing: w("      long long tg0 = clock64();")
         w("      if (it >= 2) pb2_bar_sync(%d + slot, %d);   // IN[slot] released by the compute warps" % (3, NC + NG))
         if self.timing: w("      long long tg1 = clock64(); dbg0 += tg1 - tg0;")
@@ -508,18 +521,22 @@ class CudaEmitter:
         w("      for (int i = gt; i < nel * %d; i += %d)" % (NN, NG))
         w("      {")
         w("        const int el = i / %d, l = i - el * %d;" % (NN, NN))
-        w("        const long long node = __ldg(a.elem_nodes + (long long)(e0 + el) * %d + l);" % NN)
+        w("        const long long node = s_idx[i];")
         w("        double* E = s_in + el * %d;" % IN_S)
-        self._emit_gather_node(o, plan, c1=False)
+        self._emit_gather_node(o, plan, c1=False, use_async=True)
         w("      }")
         if any(code.fields[f].space == "C1" for (f, kind) in plan["sources"]):
             w("      for (int i = gt; i < nel * %d; i += %d)" % (NN1, NG))
             w("      {")
             w("        const int el = i / %d, l = i - el * %d;" % (NN1, NN1))
-            w("        const long long node = __ldg(a.elem_nodes + (long long)(e0 + el) * %d + c_c1node[l]);" % NN)
+            w("        const long long node = s_idx[el * %d + c_c1node[l]];" % NN)
             w("        double* E = s_in + el * %d;" % IN_S)
-            self._emit_gather_node(o, plan, c1=True)
+            self._emit_gather_node(o, plan, c1=True, use_async=True)
             w("      }")
+        w("      asm volatile(\"cp.async.commit_group;\" ::: \"memory\");")
+        w("      if (batch + 1 < ib1) { const int pe0 = a.batch_elem[batch + 1], pn = (a.batch_meta[batch + 1] & 63) * %d; int* const nx = s_idx0 + (slot ^ 1) * %d; for (int i = gt; i < pn; i += %d) pb2_cp_async4(nx + i, a.elem_nodes + (long long)pe0 * %d + i); }" % (NN, EPB * NN, NG, NN))
+        w("      asm volatile(\"cp.async.commit_group;\" ::: \"memory\");")
+        w("      asm volatile(\"cp.async.wait_group 1;\" ::: \"memory\");   // nodal data of this batch has landed; next indices may be in flight")
         w("      __threadfence_block();")
         if self.timing: w("      dbg1 += clock64() - tg1;")
         w("      pb2_bar_arrive(%d + slot, %d);            // IN[slot] full" % (1, NC + NG))
@@ -593,9 +610,9 @@ class CudaEmitter:
             w("        {")
             if target is not None:
                 w("          if (a.map_bits == 8)")
-                w("            pb2_scatter_matrix<unsigned char, 0x80u, 0xFFu, %d, %d, %d>((const unsigned char*)s_map, s_rowstart, s_out, %s, nel, st);" % (ND, OUT_S, NS, target))
+                w("            pb2_scatter_matrix<unsigned char, 0x80u, 0xFFu, %d, %d, %d, %d>((const unsigned char*)s_map, s_rowstart, s_out, %s, nel, st);" % (ND, OUT_S, NS, EPB, target))
                 w("          else")
-                w("            pb2_scatter_matrix<unsigned short, 0x8000u, 0xFFFFu, %d, %d, %d>((const unsigned short*)s_map, s_rowstart, s_out, %s, nel, st);" % (ND, OUT_S, NS, target))
+                w("            pb2_scatter_matrix<unsigned short, 0x8000u, 0xFFFFu, %d, %d, %d, %d>((const unsigned short*)s_map, s_rowstart, s_out, %s, nel, st);" % (ND, OUT_S, NS, EPB, target))
             if with_res:
                 w("          for (int idx = st; idx < nel * %d; idx += %d)" % (ND, NS))
                 w("          {")
@@ -675,15 +692,21 @@ class CudaEmitter:
         w("")
         return kname
 
-    def _emit_gather_node(self, o: List[str], plan, c1: bool):
+    def _emit_gather_node(self, o: List[str], plan, c1: bool, use_async: bool = False):
         code, dim = self.code, self.dim
         w = o.append
+
+        def copy(dst, src):
+            if use_async:
+                w("        pb2_cp_async8(&%s, &%s);" % (dst, src))
+            else:
+                w("        %s = %s;" % (dst, src))
         if not c1:
             for d in range(dim):
-                w("        E[%d + l * %d + %d] = a.node_pos[node * %d + %d];" % (plan["xpos"], dim, d, dim, d))
+                copy("E[%d + l * %d + %d]" % (plan["xpos"], dim, d), "a.node_pos[node * %d + %d]" % (dim, d))
             if plan["need_lagr"]:
                 for d in range(dim):
-                    w("        E[%d + l * %d + %d] = a.node_lagr[node * %d + %d];" % (plan["xlag"], dim, d, dim, d))
+                    copy("E[%d + l * %d + %d]" % (plan["xlag"], dim, d), "a.node_lagr[node * %d + %d]" % (dim, d))
         for (f, kind) in plan["sources"]:
             fld = code.fields[f]
             if (fld.space == "C1") != c1:
@@ -694,7 +717,7 @@ class CudaEmitter:
             else:
                 base, stride, comp = "a.node_val", self.nval, fld.index
             if kind[0] == "cur":
-                w("        E[%d + l] = %s[((long long)%d * a.n_node + node) * %d + %d];" % (soff, base, kind[1], stride, comp))
+                copy("E[%d + l]" % soff, "%s[((long long)%d * a.n_node + node) * %d + %d]" % (base, kind[1], stride, comp))
             else:
                 wn = self._w_name(kind[2], kind[1])
                 w("        { double s = 0.0; for (int t = 0; t < a.ti.ntstorage; ++t) s += %s[t] * %s[((long long)t * a.n_node + node) * %d + %d]; E[%d + l] = s; }" % (
@@ -1016,11 +1039,11 @@ class CudaEmitter:
         w("    {")
         if target is not None:
             w("      if (a.map_bits == 8)")
-            w("        pb2_scatter_matrix<unsigned char, 0x80u, 0xFFu, %d, %d, %d>((const unsigned char*)s_map, s_rowstart, s_el + %d, %s, nel, tid);" % (
-                ND, ELS, self.NT, SJ, target))
+            w("        pb2_scatter_matrix<unsigned char, 0x80u, 0xFFu, %d, %d, %d, %d>((const unsigned char*)s_map, s_rowstart, s_el + %d, %s, nel, tid);" % (
+                ND, ELS, self.NT, self.EPB, SJ, target))
             w("      else")
-            w("        pb2_scatter_matrix<unsigned short, 0x8000u, 0xFFFFu, %d, %d, %d>((const unsigned short*)s_map, s_rowstart, s_el + %d, %s, nel, tid);" % (
-                ND, ELS, self.NT, SJ, target))
+            w("        pb2_scatter_matrix<unsigned short, 0x8000u, 0xFFFFu, %d, %d, %d, %d>((const unsigned short*)s_map, s_rowstart, s_el + %d, %s, nel, tid);" % (
+                ND, ELS, self.NT, self.EPB, SJ, target))
         if with_res:
             w("      for (int idx = tid; idx < nel * %d; idx += %d)" % (ND, self.NT))
             w("      {")
@@ -1031,6 +1054,7 @@ class CudaEmitter:
 
     # ------------------------------------------------------------------ whole file
     def emit(self) -> str:
+        import os
         code = self.code
         self._kernel_smem: Dict[str, int] = {}
         o: List[str] = []
@@ -1044,6 +1068,11 @@ class CudaEmitter:
         w("{")
         w("  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);")
         w("  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 4;\" :: \"r\"(sa), \"l\"(gsrc) : \"memory\");")
+        w("}")
+        w("static __device__ __forceinline__ void pb2_cp_async8(void* smem_dst, const void* gsrc)")
+        w("{")
+        w("  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);")
+        w("  asm volatile(\"cp.async.ca.shared.global [%0], [%1], 8;\" :: \"r\"(sa), \"l\"(gsrc) : \"memory\");")
         w("}")
         w("static __device__ __forceinline__ void pb2_bar_sync(const int id, const int nthreads) { asm volatile(\"bar.sync %0, %1;\" :: \"r\"(id), \"r\"(nthreads) : \"memory\"); }")
         w("static __device__ __forceinline__ void pb2_bar_arrive(const int id, const int nthreads) { asm volatile(\"bar.arrive %0, %1;\" :: \"r\"(id), \"r\"(nthreads) : \"memory\"); }")
@@ -1059,31 +1088,51 @@ class CudaEmitter:
         w("// cooperative scatter of dense element matrices staged in shared memory (element stride ELS doubles) into the CSR")
         w("// value array: entry idx of the batch <-> byte idx of the position map, so map reads are perfectly coalesced and")
         w("// neighbouring lanes hit neighbouring columns of the same CSR row.")
-        w("template <typename MapT, unsigned FIRST, unsigned SKIP, int ND, int ELS, int NT>")
+        w("// one CSR entry: first touch stores, later colours reduce; pinned rows/columns are skipped.  Hand-written so that the")
+        w("// whole decision is predicates (no branches, no bool materialisation): 9 instructions next to the 3 shared loads.")
+        w("template <unsigned FIRST, unsigned SKIP>")
+        w("static __device__ __forceinline__ void pb2_scatter_entry(double* vals, const unsigned code, const int r0, const double v)")
+        w("{")
+        w("  asm volatile(\"{\\n\\t.reg .pred pok, ps, pr;\\n\\t.reg .b32 off, fb;\\n\\t.reg .s32 pos;\\n\\t.reg .b64 ad;\\n\\t\"")
+        w("               \"setp.ne.u32 pok, %2, %5;\\n\\tsetp.ge.and.s32 pok, %3, 0, pok;\\n\\t\"")
+        w("               \"and.b32 off, %2, %6;\\n\\tadd.s32 pos, %3, off;\\n\\tmad.wide.s32 ad, pos, 8, %0;\\n\\t\"")
+        w("               \"and.b32 fb, %2, %4;\\n\\tsetp.ne.and.u32 ps, fb, 0, pok;\\n\\tsetp.eq.and.u32 pr, fb, 0, pok;\\n\\t\"")
+        dbg = os.environ.get("PB2_DEBUG_SCATTER", "")
+        if dbg == "nostore":      # development experiment: no global writes at all (results are wrong)
+            w("               \"@ps add.f64 %1, %1, %1;\\n\\t}\"")
+        elif dbg == "nored":      # development experiment: reductions replaced by plain stores (results are wrong)
+            w("               \"@ps st.global.f64 [ad], %1;\\n\\t@pr st.global.f64 [ad], %1;\\n\\t}\"")
+        else:
+            w("               \"@ps st.global.f64 [ad], %1;\\n\\t@pr red.global.add.f64 [ad], %1;\\n\\t}\"")
+        w("               :: \"l\"(vals), \"d\"(v), \"r\"(code), \"r\"(r0), \"n\"(FIRST), \"n\"(SKIP), \"n\"(FIRST - 1u) : \"memory\");")
+        w("}")
+        w("template <typename MapT, unsigned FIRST, unsigned SKIP, int ND, int ELS, int NT, int EPB>")
         w("static __device__ __forceinline__ void pb2_scatter_matrix(const MapT* __restrict__ mp, const int* __restrict__ rowstart,")
         w("                                                          const double* __restrict__ sj, double* __restrict__ vals, const int nel, const int tid)")
         w("{")
         w("  // all operands are in shared memory; stores and reductions are fire-and-forget (colouring => one add per entry and launch,")
         w("  // stream order between launches => the summation order is fixed).  Lane <-> consecutive (row,col) entries of one element,")
-        w("  // so neighbouring lanes hit neighbouring columns of the same CSR row; the entry -> row split is loop invariant.")
+        w("  // so neighbouring lanes hit neighbouring columns of the same CSR row.  A thread keeps its (row,col) slots for all elements")
+        w("  // of the batch: the element loop is unrolled and every shared-memory address is base + immediate.")
         w("  constexpr int ND2 = ND * ND, NJ = (ND2 + NT - 1) / NT;")
-        w("  int kj[NJ], rj[NJ];")
+        w("  const MapT* m[NJ]; const int* rs[NJ]; const double* sv[NJ];")
         w("  #pragma unroll")
-        w("  for (int j = 0; j < NJ; ++j) { kj[j] = tid + j * NT; rj[j] = kj[j] / ND; }")
-        w("  #pragma unroll 2")
-        w("  for (int el = 0; el < nel; ++el)")
+        w("  for (int j = 0; j < NJ; ++j)")
         w("  {")
-        w("    const MapT* __restrict__ m = mp + el * ND2; const int* __restrict__ rs = rowstart + el * ND; const double* __restrict__ sv = sj + el * ELS;")
-        w("    #pragma unroll")
-        w("    for (int j = 0; j < NJ; ++j)")
+        w("    const int k = min(tid + j * NT, ND2 - 1);   // clamped slots are masked below")
+        w("    m[j] = mp + k; rs[j] = rowstart + k / ND; sv[j] = sj + k;")
+        w("  }")
+        w("  #pragma unroll")
+        w("  for (int el = 0; el < EPB; ++el)")
+        w("  {")
+        w("    if (el < nel)")
         w("    {")
-        w("      if (kj[j] < ND2)")
+        w("      #pragma unroll")
+        w("      for (int j = 0; j < NJ; ++j)")
         w("      {")
-        w("        const unsigned code = (unsigned)m[kj[j]];")
-        w("        const int r0 = rs[rj[j]];")
-        w("        const double v = sv[kj[j]];")
-        w("        const bool ok = (code != SKIP) && (r0 >= 0);")
-        w("        pb2_store_or_red(vals + (r0 + (int)(code & (FIRST - 1u))), v, ok && (code & FIRST), ok && !(code & FIRST));")
+        w("        const bool live = (j + 1 < NJ) || (tid + j * NT < ND2);")
+        w("        const unsigned code = live ? (unsigned)m[j][el * ND2] : SKIP;")
+        w("        pb2_scatter_entry<FIRST, SKIP>(vals, code, rs[j][el * ND], sv[j][el * ELS]);")
         w("      }")
         w("    }")
         w("  }")
