@@ -79,6 +79,15 @@ int pb2_problem_fetch(pb2_problem *p, double *residual, double *jac_vals, double
 /* the reference-facing call: host dofs in, host residual/CSR values out, copies included */
 int pb2_problem_assemble_host(pb2_problem *p, int residual_index, int param_index, unsigned flag, const double *dofs,
                               double *residual, double *jac_vals, double *mass_vals);
+/* Hessian-vector assembly = HessianVectorProduct<i> (jitbridge.h:286) without the ndof^3 buffers, as used by
+ * get_multi_assembly (src/elements.cpp:4983-4988) / the Hopf and azimuthal handlers (src/bifurcation.cpp):
+ *   flag 1: for each of the n_vec vectors Y_v (host, [n_vec][n_dof]) the matrix  N_v = d(J.Y_v)/dU  (row i, column k:
+ *           sum_j H_ijk Y_j) on the fixed CSR pattern;   flag 2: additionally  d(M.Y_v)/dU  for the mass matrix.
+ * Results stay on the device; pb2_problem_fetch_hessian copies matrix v to the host (mass_vals may be NULL). */
+int pb2_problem_assemble_hessian(pb2_problem *p, int residual_index, unsigned flag, int n_vec, const double *Y, void *cuda_stream);
+int pb2_problem_fetch_hessian(pb2_problem *p, int v, double *jac_hessian_vals, double *mass_hessian_vals);
+/* flag 0 of HessianVectorProduct: product_v[i] = sum_jk Y_j H_ijk C_vk  = (d(J.Y)/dU) C_v  for n_vec vectors C_v (host in, host out) */
+int pb2_problem_hessian_vector_products(pb2_problem *p, int residual_index, const double *Y, const double *C, int n_vec, double *products);
 /* number of kernel launches issued by the last assemble, and cumulative */
 long long pb2_problem_launch_count(pb2_problem *p);
 

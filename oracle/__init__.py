@@ -152,6 +152,40 @@ class OracleProblem:
             mats.append((rs, ci, va))
         return res, mats
 
+    def element_hessian(self, e: int, Y: np.ndarray, C: Optional[np.ndarray] = None, flag: int = 1, which: int = 0):
+        """HessianVectorProduct<which> on one element; Y (and C for flag 0) are GLOBAL vectors [nvec][n_dof]."""
+        Y = np.ascontiguousarray(np.atleast_2d(Y), dtype=np.float64)
+        n = self.maxdof
+        if flag == 0:
+            C = np.ascontiguousarray(np.atleast_2d(C), dtype=np.float64)
+            nvec = C.shape[0]
+            prod, Cs = np.zeros(nvec * n), None
+        else:
+            nvec = Y.shape[0]
+            prod, Cs = np.zeros(nvec * n * n), np.zeros(nvec * n * n)
+        eq = np.zeros(n, dtype=np.int32)
+        nd = self.lib.oracle_element_hessian(self.h, e, which, _dp(Y), _dp(C) if flag == 0 else None, nvec, flag, _dp(prod), _dp(Cs), _ip(eq))
+        if flag == 0:
+            return prod[:nvec * nd].reshape(nvec, nd).copy(), eq[:nd].copy()
+        return prod[:nvec * nd * nd].reshape(nvec, nd, nd).copy(), Cs[:nvec * nd * nd].reshape(nvec, nd, nd).copy(), eq[:nd].copy()
+
+    def assemble_hessian(self, Y: np.ndarray, flag: int = 2, which: int = 0):
+        """global d(J.Y_v)/dU (and d(M.Y_v)/dU) as scipy CSR matrices, element by element like get_multi_assembly"""
+        from scipy.sparse import coo_matrix
+        Y = np.ascontiguousarray(np.atleast_2d(Y), dtype=np.float64)
+        nvec, n = Y.shape[0], self.n_dof
+        rows, cols, vj, vm = [], [], [[] for _ in range(nvec)], [[] for _ in range(nvec)]
+        for e in range(self.mesh.elem_nodes.shape[0]):
+            P, Cs, eq = self.element_hessian(e, Y, flag=flag, which=which)
+            r, c = np.meshgrid(eq, eq, indexing="ij")
+            rows.append(r.ravel()); cols.append(c.ravel())
+            for v in range(nvec):
+                vj[v].append(P[v].ravel()); vm[v].append(Cs[v].ravel())
+        rows, cols = np.concatenate(rows), np.concatenate(cols)
+        J = [coo_matrix((np.concatenate(vj[v]), (rows, cols)), shape=(n, n)).tocsr() for v in range(nvec)]
+        M = [coo_matrix((np.concatenate(vm[v]), (rows, cols)), shape=(n, n)).tocsr() for v in range(nvec)]
+        return J, M
+
     def point_shapes(self, e: int, ipt: int, flag: int = 1):
         nn, d = self.mesh.elem_nodes.shape[1], self.dim
         w = np.zeros(3); sh = np.zeros(nn); dx = np.zeros((nn, d)); dX = np.zeros((nn, d))

@@ -803,6 +803,39 @@ double oracle_assemble(void *h, int which, int param, unsigned flag, double *res
   return (double)o->nnz[0];
 }
 
+/* fill_in_generic_hessian / get_multi_assembly Hessian part (src/elements.cpp:5512, :4983-4988): local slices of the global
+ * vectors are handed to HessianVectorProduct<i>; outputs are dense per element.  flag as in SURVEY A.5.
+ *   flag 0: Yg = one vector [n_dof], Cg = nvec vectors [nvec][n_dof]; product[nvec][ndof]
+ *   flag 1,2,4,5: Yg = nvec vectors; product (and Cs for 2,5) [nvec][ndof][ndof] */
+int oracle_element_hessian(void *h, int e, int which, const double *Yg, const double *Cg, int nvec, unsigned flag, double *product, double *Cs, int *eqns)
+{
+  Oracle *o = (Oracle *)h;
+  ThreadState *ts = ts_create(o);
+  TS = ts;
+  bind_element(ts, e);
+  prepare_shape_buffer(ts);
+  const int n = (int)ts->ei.ndof;
+  ts->si.jacobian_size = n;
+  ts->si.mass_matrix_size = n;
+  const int ny = flag == 0 ? 1 : nvec;
+  double *Yl = (double *)xcalloc((size_t)ny * n, sizeof(double));
+  for (int v = 0; v < ny; v++)
+    for (int j = 0; j < n; j++) Yl[v * n + j] = Yg[(size_t)v * o->n_dof + ts->eqn_of_local[j]];
+  double *Cl = Cs;
+  if (flag == 0)
+  {
+    Cl = (double *)xcalloc((size_t)nvec * n, sizeof(double));
+    for (int v = 0; v < nvec; v++)
+      for (int j = 0; j < n; j++) Cl[v * n + j] = Cg[(size_t)v * o->n_dof + ts->eqn_of_local[j]];
+  }
+  o->ft->HessianVectorProduct[which](&ts->ei, &ts->si, Yl, Cl, product, (unsigned)nvec, flag);
+  for (int i = 0; i < n; i++) eqns[i] = ts->eqn_of_local[i];
+  free(Yl);
+  if (flag == 0) free(Cl);
+  free(ts);
+  return n;
+}
+
 int64_t oracle_nnz(void *h, int m) { return ((Oracle *)h)->nnz[m]; }
 void oracle_get_csr(void *h, int m, int *row_start, int *col_index, double *value)
 {

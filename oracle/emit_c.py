@@ -271,8 +271,8 @@ class CEmitter:
         w("")
         return "\n".join(o)
 
-    def _gateaux(self, var_part: sp.Expr, F: str, G: str, names: Dict[sp.Symbol, str]) -> sp.Expr:
-        """d/d U_G^{l_shape} of the complete residual expression of test field F."""
+    def _gateaux(self, var_part: sp.Expr, F: str, G: str, names: Dict[sp.Symbol, str], lname: str = "l_shape", mass: bool = True) -> sp.Expr:
+        """d/d U_G^{lname} of the complete residual expression of test field F."""
         code = self.code
         var: Dict[sp.Symbol, sp.Expr] = {}
 
@@ -287,14 +287,14 @@ class CEmitter:
                 if a.past:
                     continue
                 if a.field == G:
-                    shp = csym(self._shape_str(G, a.deriv, "l_shape"))
+                    shp = csym(self._shape_str(G, a.deriv, lname))
                     if a.dt_order == 0:
                         var[s] = shp
                     else:
-                        var[s] = (csym(self._weights_name(a) + "[0]") + (MM if a.dt_order == 1 else 0)) * shp
+                        var[s] = (csym(self._weights_name(a) + "[0]") + (MM if (a.dt_order == 1 and mass) else 0)) * shp
                 elif G.startswith("coordinate_") and a.deriv.startswith("dx") and code.fields[a.field].space != "Pos":
                     j = ex.DIRS.index(G[-1])
-                    var[s] = csym(self._coorddiff_name(a, j) + "[l_shape]")
+                    var[s] = csym(self._coorddiff_name(a, j) + "[%s]" % lname)
         if G.startswith("coordinate_") and code.coordinates_as_dofs:
             j = ex.DIRS.index(G[-1])
             if var_part.has(ex.DX_EUL):
@@ -307,6 +307,157 @@ class CEmitter:
             return sp.Integer(0)
         perturbed = var_part.xreplace({s: s + EPS * v for s, v in var.items()})
         return sp.diff(perturbed, EPS).xreplace({EPS: 0})
+
+    # ---- HessianVectorProduct<i> (src/codegen.cpp:3646-3910, :1500-1881) ------------------------
+    def hessian_routine(self, funcname: str, resname: str, res_index: int) -> str:
+        """Full (non-symmetric) assembly of H[i][j][k] = d/dU_k dR_i/dU_j and of the mass Hessian into n_dof^3 buffers,
+        followed by the reference's tail contractions (src/codegen.cpp:3879-3905, macros src/jitbridge.h:624-691)."""
+        code = self.code
+        if code.coordinates_as_dofs:
+            raise RuntimeError("oracle Hessian: fixed meshes only")
+        E = code.atomize(code.residuals[resname])
+        atoms = sorted([code._atom_syms[s] for s in E.free_symbols if s in code._atom_syms], key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
+        tests = sorted([code._test_syms[s] for s in E.free_symbols if s in code._test_syms], key=lambda t: (t.field, t.deriv))
+        test_fields = []
+        for t in tests:
+            if t.field not in test_fields:
+                test_fields.append(t.field)
+        names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi"}
+        for a in atoms:
+            names[code.atom_symbol(a)] = "this_" + a.cname
+        for k, p in enumerate(code.global_params):
+            names[code._param_syms[p]] = "(*(my_func_table->global_parameters[%d]))" % k
+        for s in code._test_syms:
+            sl = code._test_syms[s]
+            names[s] = "testfunction[l_test]" if sl.deriv == "d0" else "d%s_testfunction[l_test][%s]" % (sl.deriv[1], sl.deriv[2:])
+        pr = _CPrinter(names)
+        o: List[str] = []
+        w = o.append
+        w("static void %s(const JITElementInfo_t * eleminfo, const JITShapeInfo_t * shapeinfo,const double * Y, double * Cs, double * product, unsigned numvectors, unsigned flag)" % funcname)
+        w("{")
+        w("  int local_eqn, local_unknown, local_deriv;")
+        w("  const double * t=shapeinfo->t;")
+        w("  const double * dt=shapeinfo->dt;")
+        w("  (void)t; (void)dt;")
+        w("  const unsigned n_dof=shapeinfo->jacobian_size;")
+        w("  double * hessian_buffer=(flag==3 ? product : (double*)calloc(n_dof*n_dof*n_dof,sizeof(double)));")
+        w("  double * hessian_M_buffer=(flag==3 ? Cs : ((flag==2 || flag==5) ? (double*)calloc(n_dof*n_dof*n_dof,sizeof(double)) : PYOOMPH_NULL_));")
+        for f in sorted({a.field for a in atoms} | set(test_fields)):
+            w("  const unsigned %s = %d;" % (_nodal_index_name(f), code.fields[f].index))
+        dt_atoms: Dict[str, AtomInfo] = {}
+        for a in atoms:
+            if a.dt_order:
+                dt_atoms.setdefault(self._dt_values_name(a), a)
+        for nm, a in dt_atoms.items():
+            w("  double %s[%d];" % (nm, code.etype.nnode))
+            w("  for (unsigned int l_shape=0;l_shape<%s;l_shape++)" % self._nnode_str(a.field))
+            w("  {")
+            w("    %s[l_shape]=0.0;" % nm)
+            w("    for (unsigned tindex=0;tindex<shapeinfo->timestepper_ntstorage;tindex++) %s[l_shape] += %s[tindex]*eleminfo->%s[l_shape][%s][tindex];" % (
+                nm, self._weights_name(a), self._data_array(a.field), _nodal_index_name(a.field)))
+            w("  }")
+        w("  for(unsigned ipt=0;ipt<shapeinfo->n_int_pt;ipt++)")
+        w("  {")
+        w("    my_func_table->fill_shape_buffer_for_point(ipt, &(my_func_table->shapes_required_Hessian[%d]), 3);" % res_index)
+        w("    const double dx = shapeinfo->int_pt_weight;")
+        w("    const double dX = shapeinfo->int_pt_weight_Lagrangian;")
+        w("    (void)dx; (void)dX;")
+        for space in ("Pos", "C2", "C1"):
+            sat = [a for a in atoms if code.fields[a.field].space == space]
+            if not sat:
+                continue
+            for a in sat:
+                w("    double this_%s=0.0;" % a.cname)
+            w("    for (unsigned int l_shape=0;l_shape<%s;l_shape++)" % self._nnode_str(sat[0].field))
+            w("    {")
+            for a in sat:
+                nd = ("%s[l_shape]" % self._dt_values_name(a)) if a.dt_order else "eleminfo->%s[l_shape][%s][%d]" % (self._data_array(a.field), _nodal_index_name(a.field), a.past)
+                w("      this_%s+= %s * %s;" % (a.cname, nd, self._shape_str(a.field, a.deriv, "l_shape")))
+            w("    }")
+        for space in ("C2", "C1"):
+            tf = [f for f in test_fields if code.fields[f].space == space]
+            if not tf:
+                continue
+            w("    {")
+            w("      double const * testfunction = shapeinfo->shape_%s;" % space)
+            w("      DX_SHAPE_FUNCTION_DECL(dx_testfunction) = shapeinfo->dx_shape_%s;" % space)
+            w("      DX_SHAPE_FUNCTION_DECL(dX_testfunction) = shapeinfo->dX_shape_%s;" % space)
+            w("      (void)testfunction; (void)dx_testfunction; (void)dX_testfunction;")
+            w("      for (unsigned int l_test=0;l_test<eleminfo->nnode_%s;l_test++)" % space)
+            w("      {")
+            for F in tf:
+                other = {s: 0 for s, sl in code._test_syms.items() if sl.field != F}
+                var_part = E.xreplace(other)
+                if var_part == 0:
+                    continue
+                w("        local_eqn=%s;" % self._eqn_str(F, "l_test"))
+                w("        if (local_eqn>=0)")
+                w("        {")
+                for G in code.unknown_field_names():
+                    d1 = self._gateaux(var_part, F, G, names, "l_shape")
+                    if d1 == 0:
+                        continue
+                    m1 = sp.diff(d1, MM)
+                    d1 = d1.xreplace({MM: 0})
+                    for H in code.unknown_field_names():
+                        d2 = self._gateaux(d1, F, H, names, "l_shape2", mass=False)
+                        m2 = self._gateaux(m1, F, H, names, "l_shape2", mass=False) if m1 != 0 else sp.Integer(0)
+                        if d2 == 0 and m2 == 0:
+                            continue
+                        w("          for (unsigned int l_shape=0;l_shape<%s;l_shape++)" % self._nnode_str(G))
+                        w("          {")
+                        w("            local_unknown=%s;" % self._eqn_str(G, "l_shape"))
+                        w("            if (local_unknown>=0)")
+                        w("            {")
+                        w("              for (unsigned int l_shape2=0;l_shape2<%s;l_shape2++)" % self._nnode_str(H))
+                        w("              {")
+                        w("                local_deriv=%s;" % self._eqn_str(H, "l_shape2"))
+                        w("                if (local_deriv>=0)")
+                        w("                {")
+                        if d2 != 0:
+                            w("                  hessian_buffer[local_eqn*n_dof*n_dof+local_unknown*n_dof+local_deriv] += %s;" % pr.doprint(d2))
+                        if m2 != 0:
+                            w("                  if (flag>=2 && flag!=4) hessian_M_buffer[local_eqn*n_dof*n_dof+local_unknown*n_dof+local_deriv] += %s;" % pr.doprint(m2))
+                        w("                }")
+                        w("              }")
+                        w("            }")
+                        w("          }")
+                w("        }")
+            w("      }")
+            w("    }")
+        w("  }")
+        # tail (jitbridge.h:637-691 restated: contraction of the middle index, or of the first one when transposed)
+        w("  if (!flag)")
+        w("  {")
+        w("    for (unsigned int i=0;i<n_dof;i++) for (unsigned int k=0;k<n_dof;k++)")
+        w("    {")
+        w("      double Yj_Hijk=0.0;")
+        w("      for (unsigned int j=0;j<n_dof;j++) Yj_Hijk+=Y[j]*hessian_buffer[i*n_dof*n_dof+j*n_dof+k];")
+        w("      for (unsigned int v=0;v<numvectors;v++) product[v*n_dof+i]+=Yj_Hijk*Cs[v*n_dof+k];")
+        w("    }")
+        w("    free(hessian_buffer);")
+        w("  }")
+        w("  else if (flag!=3)")
+        w("  {")
+        w("    for (unsigned int ivec=0;ivec<numvectors;ivec++) for (unsigned i=0;i<n_dof;i++) for (unsigned k=0;k<n_dof;k++) for (unsigned int j=0;j<n_dof;j++)")
+        w("    {")
+        w("      if (flag==5 || flag==4) product[n_dof*n_dof*ivec+i*n_dof+k] += hessian_buffer[j*n_dof*n_dof+i*n_dof+k]*Y[n_dof*ivec+j];")
+        w("      else product[n_dof*n_dof*ivec+i*n_dof+k] += hessian_buffer[i*n_dof*n_dof+j*n_dof+k]*Y[n_dof*ivec+j];")
+        w("    }")
+        w("    free(hessian_buffer);")
+        w("  }")
+        w("  if (flag==2 || flag==5)")
+        w("  {")
+        w("    for (unsigned int ivec=0;ivec<numvectors;ivec++) for (unsigned i=0;i<n_dof;i++) for (unsigned k=0;k<n_dof;k++) for (unsigned int j=0;j<n_dof;j++)")
+        w("    {")
+        w("      if (flag==5) Cs[n_dof*n_dof*ivec+i*n_dof+k] += hessian_M_buffer[j*n_dof*n_dof+i*n_dof+k]*Y[n_dof*ivec+j];")
+        w("      else Cs[n_dof*n_dof*ivec+i*n_dof+k] += hessian_M_buffer[i*n_dof*n_dof+j*n_dof+k]*Y[n_dof*ivec+j];")
+        w("    }")
+        w("    free(hessian_M_buffer);")
+        w("  }")
+        w("}")
+        w("")
+        return "\n".join(o)
 
     # ---- whole plugin file -------------------------------------------------------------------
     def emit(self) -> str:
@@ -324,11 +475,19 @@ class CEmitter:
             w(self.routine("ResidualAndJacobian%d" % i, rn, i, None))
             for p in code.global_params:
                 w(self.routine("dResidual%ddParameter_%s" % (i, p), rn, i, p))
+        hess = not code.coordinates_as_dofs
+        if hess:
+            w("#ifndef PYOOMPH_NULL_")
+            w("#define PYOOMPH_NULL_ ((double*)0)")
+            w("#endif")
+            for i, rn in enumerate(resnames):
+                w(self.hessian_routine("HessianVectorProduct%d" % i, rn, i))
         nC2 = len([f for f in code.nodal_fields() if f.space == "C2"])
         nC1 = len([f for f in code.nodal_fields() if f.space == "C1"])
         w("static void clean_up(JITFuncSpec_Table_FiniteElement_t *functable)")
         w("{")
         w(" free(functable->ResidualAndJacobian); free(functable->ResidualAndJacobianSteady); free(functable->shapes_required_ResJac);")
+        w(" if (functable->hessian_generated) { free(functable->HessianVectorProduct); free(functable->shapes_required_Hessian); }")
         w(" free(functable->global_parameters);")
         w(" for (unsigned i=0;i<functable->num_res_jacs;i++) { free(functable->ParameterDerivative[i]); free(functable->res_jac_names[i]); }")
         w(" free(functable->ParameterDerivative); free(functable->res_jac_names); free(functable->dominant_space);")
@@ -367,7 +526,12 @@ class CEmitter:
         w(" functable->moving_nodes=%s;" % ("true" if code.coordinates_as_dofs else "false"))
         w(" functable->integration_order=0;")
         w(' SET_INTERNAL_NAME(functable->dominant_space,"C2");')
-        w(" functable->hessian_generated=false;")
+        w(" functable->hessian_generated=%s;" % ("true" if hess else "false"))
+        if hess:
+            w(" functable->shapes_required_Hessian=(JITFuncSpec_RequiredShapes_FiniteElement_t *)calloc(%d,sizeof(JITFuncSpec_RequiredShapes_FiniteElement_t));" % max(1, len(resnames)))
+            w(" functable->HessianVectorProduct=(JITFuncSpec_HessianVectorProduct_FiniteElement *)calloc(%d,sizeof(JITFuncSpec_HessianVectorProduct_FiniteElement));" % max(1, len(resnames)))
+            for i, rn in enumerate(resnames):
+                w(" functable->HessianVectorProduct[%d]=&HessianVectorProduct%d;" % (i, i))
         w(" functable->clean_up=&clean_up;")
         w(" my_func_table=functable;")
         w("}")

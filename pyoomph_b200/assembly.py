@@ -76,7 +76,8 @@ def load_library() -> ctypes.CDLL:
     for fn in ("pb2_class_load", "pb2_class_get_info", "pb2_problem_create", "pb2_problem_pattern", "pb2_problem_set_nodal_values",
                "pb2_problem_set_nodal_positions", "pb2_problem_set_lagrangian_positions", "pb2_problem_set_dofs",
                "pb2_problem_set_time", "pb2_problem_set_parameters", "pb2_problem_assemble", "pb2_problem_device_outputs",
-               "pb2_problem_fetch", "pb2_problem_assemble_host", "pb2_problem_num_colours", "pb2_version"):
+               "pb2_problem_fetch", "pb2_problem_assemble_host", "pb2_problem_num_colours", "pb2_version",
+               "pb2_problem_assemble_hessian", "pb2_problem_fetch_hessian", "pb2_problem_hessian_vector_products"):
         getattr(L, fn).restype = ctypes.c_int
     _LIB = L
     return L
@@ -269,6 +270,30 @@ class B200Assembly(CustomAssemblyBase):
         d = None if dofs is None else self._dp(np.ascontiguousarray(dofs, dtype=np.float64))
         _check(self.lib.pb2_problem_assemble_host(self.prob, ri, pi, flag, d, self._dp(res),
                                                   None if jac is None else self._dp(jac), None if mass is None else self._dp(mass)))
+        return out
+
+    # ---- Hessian-vector products (MultiAssembleRequest.dJdU / dMdU, pyoomph/generic/bifurcation_tools.py:465-531) -----
+    def assemble_hessian(self, Y: np.ndarray, flag: int = 2, residual: str = ""):
+        """d(J.Y_v)/dU (flag 1) and d(M.Y_v)/dU (flag 2) for every row Y_v of Y; returns lists of CSR value arrays"""
+        Y = np.ascontiguousarray(np.atleast_2d(Y), dtype=np.float64)
+        assert Y.shape[1] == self.n_dof
+        ri = self.residual_names.index(residual)
+        _check(self.lib.pb2_problem_assemble_hessian(self.prob, ri, flag, Y.shape[0], self._dp(Y), None))
+        J, M = [], []
+        for v in range(Y.shape[0]):
+            jv = np.empty(self.nnz)
+            mv = np.empty(self.nnz) if flag >= 2 else None
+            _check(self.lib.pb2_problem_fetch_hessian(self.prob, v, self._dp(jv), None if mv is None else self._dp(mv)))
+            J.append(jv); M.append(mv)
+        return J, M
+
+    def hessian_vector_products(self, Y: np.ndarray, C: np.ndarray, residual: str = "") -> np.ndarray:
+        """flag 0 of HessianVectorProduct: out[v][i] = sum_jk Y_j H_ijk C_vk"""
+        Y = np.ascontiguousarray(Y, dtype=np.float64).ravel()
+        C = np.ascontiguousarray(np.atleast_2d(C), dtype=np.float64)
+        out = np.empty_like(C)
+        ri = self.residual_names.index(residual)
+        _check(self.lib.pb2_problem_hessian_vector_products(self.prob, ri, self._dp(Y), self._dp(C), C.shape[0], self._dp(out)))
         return out
 
     def device_outputs(self):

@@ -61,6 +61,7 @@ class Field:
     name: str
     space: str          # "C2", "C1" or "Pos"
     index: int = -1     # index into nodal_data / nodal_coords (src/codegen.cpp:2795-2835)
+    aux_of: str = ""    # "Y__<field>": values of a Hessian direction vector on the dofs of <field> (not a nodal value)
 
 
 @dataclasses.dataclass(frozen=True)
@@ -162,13 +163,13 @@ class FiniteElementCode:
         idx = 0
         for sp_name in SPACE_ORDER:
             for f in self.fields.values():
-                if f.space == sp_name:
+                if f.space == sp_name and not f.aux_of:
                     f.index = idx
                     idx += 1
         self.n_nodal_values = idx
 
     def nodal_fields(self) -> List[Field]:
-        return sorted([f for f in self.fields.values() if f.space != "Pos"], key=lambda f: f.index)
+        return sorted([f for f in self.fields.values() if f.space != "Pos" and not f.aux_of], key=lambda f: f.index)
 
     def _require_field(self, name: str):
         if name.startswith("coordinate_") or name.startswith("lagrangian_"):
@@ -381,6 +382,70 @@ class FiniteElementCode:
         atoms = sorted((self._atom_syms[s] for s in used), key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
         allsyms = set().union(*[e.free_symbols for e in list(R) + list(J.values()) + list(M.values())]) if R else set()
         return ResidualForm(name, slots, R, J, M, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=ex.DX_LAG in allsyms)
+
+    # -- Hessian (second derivatives), fixed meshes ------------------------------------------------
+    def derive_hessian(self, resname: str = ""):
+        """Coefficient form of HessianVectorProduct<i> (src/codegen.cpp:3646-3910) without the ndof^3 buffer.
+
+        The reference fills H[i][j][k] = d/dU_k (dR_i/dU_j) (and the mass Hessian d/dU_k (dR_i/d(partial_t U_j)),
+        src/codegen.cpp:1680-1843) and contracts the MIDDLE index with the vector (SET_DIRECTIONAL_SYMMETRIC_HESSIAN_FROM,
+        src/jitbridge.h:663): N_ik = sum_j H_ijk Y_j = d((A.Y)_i)/dU_k for A = J or M.  With A_ij = T_b C_{s,(G,a)} S_a[l_j] this is
+
+            N[(F,l_t),(H,l_k)] = T_b[l_t] * ( sum_{(G,a)} Yhat_{G,a} * dC_{s,(G,a)}/d atom(H,c) * fac ) * S_c[l_k]
+
+        where Yhat_{G,a} is Y interpolated like field G (value or gradient).  Returns (slots, DJ, DM) with
+        DJ[(slot, H, c)] = {(G, a): coefficient expression}."""
+        if self.coordinates_as_dofs:
+            raise RuntimeError("analytic Hessian with position dofs is outside the GPU path (second-order moving-mesh tensors)")
+        form = self.derive(resname)
+        unknowns = set(self.unknown_field_names())
+
+        def second(coefs):
+            out: Dict[Tuple[int, str, str], Dict[Tuple[str, str], sp.Expr]] = {}
+            for (si, G, a), c in coefs.items():
+                for sym in [x for x in c.free_symbols if x in self._atom_syms]:
+                    info = self._atom_syms[sym]
+                    if info.past or info.field not in unknowns:
+                        continue
+                    d = sp.diff(c, sym)
+                    if d == 0:
+                        continue
+                    if info.dt_order:
+                        d = d * sp.Symbol("W__%s__%d" % (info.scheme, info.dt_order), real=True)
+                    dst = out.setdefault((si, info.field, info.deriv), {})
+                    dst[(G, a)] = dst.get((G, a), sp.Integer(0)) + d
+            return out
+        return form, second(form.J), second(form.M)
+
+    def hessian_form(self, resname: str = "") -> ResidualForm:
+        """d((J.Y))/dU and d((M.Y))/dU as an ordinary coefficient form: the direction vector Y enters as auxiliary fields
+        ``Y__<field>`` interpolated like <field>, so the batched R/J/M kernel skeleton assembles it unchanged (no residual)."""
+        key = resname + "|hessian"
+        if key in self._forms:
+            return self._forms[key]
+        form, DJ, DM = self.derive_hessian(resname)
+
+        def fold(D):
+            out: Dict[Tuple[int, str, str], sp.Expr] = {}
+            for k, terms in D.items():
+                e = sp.Integer(0)
+                for (G, a), c in terms.items():
+                    yf = "Y__" + G
+                    if yf not in self.fields:
+                        self.fields[yf] = Field(yf, self.fields[G].space, -1, aux_of=G)
+                    e = e + self._atom(AtomInfo(yf, 0, "", a, 0)) * c
+                out[k] = e
+            return out
+        J, M = fold(DJ), fold(DM)
+        used = set()
+        for e in list(J.values()) + list(M.values()):
+            used |= {s_ for s_ in e.free_symbols if s_ in self._atom_syms}
+        atoms = sorted((self._atom_syms[s_] for s_ in used), key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
+        allsyms = set().union(*[e.free_symbols for e in list(J.values()) + list(M.values())]) if (J or M) else set()
+        hf = ResidualForm(key, list(form.slots), [sp.Integer(0)] * len(form.slots), J, M, atoms,
+                          uses_dx=ex.DX_EUL in allsyms, uses_dX=ex.DX_LAG in allsyms)
+        self._forms[key] = hf
+        return hf
 
     def atom_symbol(self, info: AtomInfo) -> sp.Symbol:
         return self._atom(info)

@@ -69,6 +69,9 @@ struct pb2_problem
   std::vector<BatchTables> batch_tables;
   cudaStream_t copy_stream = nullptr;
   unsigned long long *d_debug = nullptr;
+  double *d_hvec = nullptr, *d_hess = nullptr, *d_hessM = nullptr;
+  int hess_nvec = 0;
+  int *d_row_start = nullptr, *d_col_index = nullptr;
   int *d_untouched = nullptr;      // CSR positions no local element writes (pattern entries owned for other ranks' contributions)
   long long n_untouched = 0;
 };
@@ -585,6 +588,11 @@ extern "C" void pb2_problem_free(pb2_problem *p)
   cudaFree(p->d_mass);
   cudaFree(p->d_dofs);
   cudaFree(p->d_untouched);
+  cudaFree(p->d_hvec);
+  cudaFree(p->d_hess);
+  cudaFree(p->d_hessM);
+  cudaFree(p->d_row_start);
+  cudaFree(p->d_col_index);
   for (auto &b : p->batch_tables)
   {
     cudaFree(b.d_batch_elem);
@@ -687,14 +695,11 @@ extern "C" int pb2_problem_set_parameters(pb2_problem *p, const double *values, 
   return 0;
 }
 
-extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int param_index, unsigned flag, void *cuda_stream)
+static int run_routine(pb2_problem *p, int kind, int residual_index, int param_index, unsigned flag, double *out_jac, double *out_mass, const double *hvec, void *cuda_stream)
 {
-  CUDA_OK(cudaSetDevice(p->device));
   const pb2_class_info &ci = p->cls->table.info;
   if (residual_index < 0 || residual_index >= ci.n_residuals) return fail("residual index out of range");
   if (param_index >= ci.n_params) return fail("parameter index out of range");
-  if (flag > 2u) return fail("flag must be 0, 1 or 2");
-  if (flag == 2u && !p->d_mass) CUDA_OK(cudaMalloc((void **)&p->d_mass, std::max<size_t>(1, p->nnz) * sizeof(double)));
   pb2_kernel_args a;
   memset(&a, 0, sizeof(a));
   a.elem_nodes = p->d_elem_nodes;
@@ -710,8 +715,9 @@ extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int para
   a.n_hist_val = p->T_val;
   a.n_hist_pos = p->T_pos;
   a.residual = p->d_residual;
-  a.jac_vals = p->d_jac;
-  a.mass_vals = p->d_mass;
+  a.jac_vals = out_jac;
+  a.mass_vals = out_mass;
+  a.hvec = hvec;
   a.ti = p->ti;
   memcpy(a.params, p->params, sizeof(a.params));
   p->launches_last = 0;
@@ -719,13 +725,13 @@ extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int para
   {
     // entries that only other ranks contribute to start from zero in every assembly
     const int bs = 256;
-    pb2_zero_positions<<<(unsigned)((p->n_untouched + bs - 1) / bs), bs, 0, (cudaStream_t)cuda_stream>>>(p->d_jac, flag >= 2u ? p->d_mass : nullptr, p->d_untouched, p->n_untouched);
+    pb2_zero_positions<<<(unsigned)((p->n_untouched + bs - 1) / bs), bs, 0, (cudaStream_t)cuda_stream>>>(out_jac, flag >= 2u ? out_mass : nullptr, p->d_untouched, p->n_untouched);
     CUDA_OK(cudaGetLastError());
     p->launches_last++;
     p->launches_total++;
   }
   pb2_kernel_cfg cfg;
-  int rc = p->cls->table.query(0, residual_index, param_index, flag, &cfg);
+  int rc = p->cls->table.query(kind, residual_index, param_index, flag, &cfg);
   if (rc != 0)
     return fail("plugin has no kernel for this routine (rc " + std::to_string(rc) + (rc >= 100 ? std::string(": ") + cudaGetErrorString((cudaError_t)(rc - 100)) : "") + ")");
   const int ntile = (int)p->colour_begin.size() - 1;
@@ -833,6 +839,91 @@ extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int para
     p->launches_last++;
     p->launches_total++;
   }
+  return 0;
+}
+
+extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int param_index, unsigned flag, void *cuda_stream)
+{
+  CUDA_OK(cudaSetDevice(p->device));
+  if (flag > 2u) return fail("flag must be 0, 1 or 2");
+  if (flag == 2u && !p->d_mass) CUDA_OK(cudaMalloc((void **)&p->d_mass, std::max<size_t>(1, p->nnz) * sizeof(double)));
+  return run_routine(p, 0, residual_index, param_index, flag, p->d_jac, p->d_mass, nullptr, cuda_stream);
+}
+
+extern "C" int pb2_problem_assemble_hessian(pb2_problem *p, int residual_index, unsigned flag, int n_vec, const double *Y, void *cuda_stream)
+{
+  CUDA_OK(cudaSetDevice(p->device));
+  if (!p->cls->table.info.hessian_generated) return fail("this element class was generated without Hessian routines");
+  if (flag != 1u && flag != 2u) return fail("Hessian assembly: flag must be 1 (d(J.Y)/dU) or 2 (+ d(M.Y)/dU)");
+  if (n_vec < 1) return fail("n_vec must be positive");
+  if (n_vec > p->hess_nvec)
+  {
+    cudaFree(p->d_hvec); cudaFree(p->d_hess); cudaFree(p->d_hessM);
+    p->d_hvec = p->d_hess = p->d_hessM = nullptr;
+    CUDA_OK(cudaMalloc((void **)&p->d_hvec, (size_t)n_vec * std::max<long long>(1, p->n_dof) * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&p->d_hess, (size_t)n_vec * std::max<long long>(1, p->nnz) * sizeof(double)));
+    CUDA_OK(cudaMalloc((void **)&p->d_hessM, (size_t)n_vec * std::max<long long>(1, p->nnz) * sizeof(double)));
+    p->hess_nvec = n_vec;
+  }
+  CUDA_OK(cudaMemcpyAsync(p->d_hvec, Y, (size_t)n_vec * p->n_dof * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream));
+  long long launches = 0;
+  for (int v = 0; v < n_vec; v++)
+  {
+    const int rc = run_routine(p, 1, residual_index, -1, flag, p->d_hess + (size_t)v * p->nnz, p->d_hessM + (size_t)v * p->nnz, p->d_hvec + (size_t)v * p->n_dof, cuda_stream);
+    if (rc) return rc;
+    launches += p->launches_last;
+  }
+  p->launches_last = launches;
+  return 0;
+}
+
+extern "C" int pb2_problem_fetch_hessian(pb2_problem *p, int v, double *jac_hessian_vals, double *mass_hessian_vals)
+{
+  CUDA_OK(cudaSetDevice(p->device));
+  if (v < 0 || v >= p->hess_nvec) return fail("Hessian vector index out of range");
+  CUDA_OK(cudaDeviceSynchronize());
+  if (jac_hessian_vals) CUDA_OK(cudaMemcpy(jac_hessian_vals, p->d_hess + (size_t)v * p->nnz, (size_t)p->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+  if (mass_hessian_vals) CUDA_OK(cudaMemcpy(mass_hessian_vals, p->d_hessM + (size_t)v * p->nnz, (size_t)p->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// one warp per CSR row: y = A x
+static __global__ void pb2_spmv(const int *__restrict__ row_start, const int *__restrict__ col, const double *__restrict__ val,
+                                const double *__restrict__ x, double *__restrict__ y, long long n_rows)
+{
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  double s = 0.0;
+  for (int i = row_start[row] + lane; i < row_start[row + 1]; i += 32) s += val[i] * x[col[i]];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) y[row] = s;
+}
+
+extern "C" int pb2_problem_hessian_vector_products(pb2_problem *p, int residual_index, const double *Y, const double *C, int n_vec, double *products)
+{
+  int rc = pb2_problem_assemble_hessian(p, residual_index, 1u, 1, Y, nullptr);
+  if (rc) return rc;
+  if (!p->d_row_start)
+  {
+    if (upload(&p->d_row_start, p->row_start) || upload(&p->d_col_index, p->col_index)) return 1;
+  }
+  double *d_x = nullptr, *d_y = nullptr;
+  CUDA_OK(cudaMalloc((void **)&d_x, std::max<long long>(1, p->n_dof) * sizeof(double)));
+  CUDA_OK(cudaMalloc((void **)&d_y, std::max<long long>(1, p->n_dof) * sizeof(double)));
+  for (int v = 0; v < n_vec; v++)
+  {
+    CUDA_OK(cudaMemcpy(d_x, C + (size_t)v * p->n_dof, (size_t)p->n_dof * sizeof(double), cudaMemcpyHostToDevice));
+    const int bs = 256;
+    const long long nb = (p->n_dof * 32 + bs - 1) / bs;
+    pb2_spmv<<<(unsigned)nb, bs>>>(p->d_row_start, p->d_col_index, p->d_hess, d_x, d_y, p->n_dof);
+    CUDA_OK(cudaGetLastError());
+    p->launches_last++;
+    p->launches_total++;
+    CUDA_OK(cudaMemcpy(products + (size_t)v * p->n_dof, d_y, (size_t)p->n_dof * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_x);
+  cudaFree(d_y);
   return 0;
 }
 

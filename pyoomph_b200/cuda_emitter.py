@@ -160,6 +160,11 @@ class CudaEmitter:
             self.routines.append(RoutinePlan("r%d" % i, code.derive(rn), i, -1))
             for k, p in enumerate(code.global_params):
                 self.routines.append(RoutinePlan("r%d_dp%d" % (i, k), code.derive(rn, p), i, k))
+        self.hessian = (not code.coordinates_as_dofs) and os.environ.get("PB2_NO_HESSIAN", "0") != "1"
+        self.hroutines: List[RoutinePlan] = []
+        if self.hessian:
+            for i, rn in enumerate(code.residual_names()):
+                self.hroutines.append(RoutinePlan("h%d" % i, code.hessian_form(rn), i, -1))
         self.T_val = code.history_levels()
         self.T_pos = self.T_val if code.coordinates_as_dofs else 1
         self._plan_groups()
@@ -510,7 +515,7 @@ class CudaEmitter:
         w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
         w("      const int slot = it & 1;")
-        w("      const int nel = a.batch_meta[batch] & 63;")
+        w("      const int nel = a.batch_meta[batch] & 63, e0 = a.batch_elem[batch]; (void)e0;")
         w("      const int* const s_idx = s_idx0 + slot * %d;" % (EPB * NN))
         w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")
         w("      pb2_bar_sync(13, %d);                        // indices of this batch visible to all gather warps" % NG)
@@ -594,7 +599,8 @@ class CudaEmitter:
         w("        pb2_bar_sync(12, %d);                     // gate passed (tile, gated_tile are uniform over the scatter warps)" % NS)
         w("        __threadfence();")
         w("      }")
-        passes = [("J", "a.jac_vals", True)] if what >= 1 else [("R", None, True)]
+        is_h = rp.key.startswith("h")      # Hessian-vector routine: matrices only, no residual
+        passes = [("J", "a.jac_vals", not is_h)] if what >= 1 else [("R", None, True)]
         if what >= 2:
             passes.append(("M", "a.mass_vals", False))
         w("      #pragma unroll 1")
@@ -631,7 +637,7 @@ class CudaEmitter:
         # ---------------------------------------------------------------- compute warps
         w("  else")
         w("  {")
-        cpasses = [("J", form.J, plan["J_off"], True, True)] if what >= 1 else [("R", {}, {}, True, False)]
+        cpasses = [("J", form.J, plan["J_off"], not is_h, True)] if what >= 1 else [("R", {}, {}, True, False)]
         if what >= 2:
             cpasses.append(("M", form.M, plan["M_off"], False, True))
         nacc = max(self._group_nacc(form, g, coef) for g in self.groups for (_, coef, _, _, _) in cpasses)
@@ -712,6 +718,11 @@ class CudaEmitter:
             if (fld.space == "C1") != c1:
                 continue
             soff = plan["src_off"][(f, kind)]
+            if fld.aux_of:
+                # Hessian direction vector on the dofs of the underlying field (pinned dofs carry no direction)
+                w("        { const int yq = __ldg(a.elem_eqn + (long long)(e0 + el) * %d + c_row_%s[l]); E[%d + l] = yq >= 0 ? __ldg(a.hvec + yq) : 0.0; }" % (
+                    self.ndof, fld.aux_of, soff))
+                continue
             if fld.space == "Pos":
                 base, stride, comp = "a.node_pos", dim, ex.DIRS.index(f[-1])
             else:
@@ -1143,15 +1154,25 @@ class CudaEmitter:
         for rp in self.routines:
             for what in (0, 1, 2):
                 kernels[(rp.key, what)] = self._emit_kernel_pipe(o, rp, what) if self.pipeline else self._emit_kernel(o, rp, what)
+        if self.hessian and self.pipeline:
+            for rp in self.hroutines:
+                for what in (1, 2):
+                    kernels[(rp.key, what)] = self._emit_kernel_pipe(o, rp, what)
         # host side: launchers + table
         w("static int pb2_query(int kind, int residual_index, int param_index, unsigned flag, pb2_kernel_cfg* out)")
         w("{")
         w("  memset(out, 0, sizeof(*out));")
-        w("  if (kind != 0 || flag > 2u) return 1;")
+        w("  if (kind < 0 || kind > 1 || flag > 2u) return 1;")
+        if self.hessian and self.pipeline:
+            for rp in self.hroutines:
+                for what in (1, 2):
+                    kn = kernels[(rp.key, what)]
+                    w("  if (kind == 1 && residual_index == %d && flag == %du) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
+                        rp.res_index, what, kn, self._kernel_smem[kn], self._kernel_cfg[kn][0], self._kernel_cfg[kn][1]))
         for rp in self.routines:
             for what in (0, 1, 2):
                 kn = kernels[(rp.key, what)]
-                w("  if (residual_index == %d && param_index == %d && flag == %du) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
+                w("  if (kind == 0 && residual_index == %d && param_index == %d && flag == %du) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
                     rp.res_index, rp.param_index, what, kn, self._kernel_smem[kn], self._kernel_cfg[kn][0], self._kernel_cfg[kn][1]))
         w("  if (!out->func) return 2;")
         w("  out->pipelined = %d;" % (1 if self.pipeline else 0))
@@ -1209,7 +1230,7 @@ class CudaEmitter:
         w("  ci->n_hist_val = %d; ci->n_hist_pos = %d; ci->max_dt_order = %d;" % (self.T_val, self.T_pos, code.max_dt_order()))
         w("  ci->elems_per_block = %d; ci->threads_per_block = %d; ci->smem_bytes = %d;" % (
             self._kernel_cfg[kernels[(self.routines[0].key, 1)]][0], self._kernel_cfg[kernels[(self.routines[0].key, 1)]][1], max(self._kernel_smem.values())))
-        w("  ci->hessian_generated = 0;")
+        w("  ci->hessian_generated = %d;" % (1 if (self.hessian and self.pipeline) else 0))
         for what in (0, 1, 2):
             w("  ci->alg_bytes_per_elem[%d] = %r;" % (what, self.algorithmic_bytes(what)))
         w("  ci->alg_bytes_per_hist_level = %r;" % float(8 * sum(self._nnode_space(f.space) for f in code.nodal_fields())))

@@ -111,3 +111,19 @@ class PseudoElasticMesh(Equations):
         x, x_test = var_and_test("mesh")
         X = var("lagrangian")
         self.add_residual(Weak(sigma(x - X), eps(x_test)))
+
+
+class NonlinearHeatEquation(Equations):
+    """(1 + beta*u^2) partial_t(u) - div((1 + alpha*u) grad(u)) = 0: a solution-dependent mass matrix and conductivity, so that
+    both Hessians d(J.Y)/dU and d(M.Y)/dU are non-trivial (test problem for the HessianVectorProduct path)."""
+
+    def __init__(self, name: str = "u", alpha=0.5, beta=0.25):
+        super().__init__()
+        self.name, self.alpha, self.beta = name, alpha, beta
+
+    def define_fields(self):
+        self.define_scalar_field(self.name, "C2")
+
+    def define_residuals(self):
+        u, u_test = var_and_test(self.name)
+        self.add_residual(weak((1 + self.beta * u ** 2) * partial_t(u), u_test) + weak((1 + self.alpha * u) * grad(u), grad(u_test)))

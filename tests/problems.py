@@ -2,7 +2,8 @@
 import numpy as np
 
 from pyoomph_b200.codegen import FiniteElementCode
-from pyoomph_b200.equations import (NavierStokesEquations, PoissonEquation, PseudoElasticMesh, TransientHeatEquation)
+from pyoomph_b200.equations import (NavierStokesEquations, NonlinearHeatEquation, PoissonEquation, PseudoElasticMesh,
+                                    TransientHeatEquation)
 from pyoomph_b200.expressions import exp, var, global_parameter
 from pyoomph_b200.meshes import CuboidBrickMesh, RectangularQuadMesh, assign_equation_numbers
 
@@ -55,6 +56,11 @@ def make_problem(kind: str, N: int, seed: int = 0):
         pinned = {"velocity_x": wall, "velocity_y": wall}
         unsteady = False
         params = {"mu": 0.013}
+    elif kind == "nlheat":         # nonlinear mass matrix: exercises the mass Hessian
+        mesh = RectangularQuadMesh(N)
+        code = FiniteElementCode("Quad2dC2", NonlinearHeatEquation(), name="nlheat")
+        pinned = {"u": mesh.boundaries["left"]}
+        unsteady = True
     elif kind == "heat3d":         # config 3
         mesh = CuboidBrickMesh(N)
         code = FiniteElementCode("Brick3dC2", TransientHeatEquation(), name="heat3d")

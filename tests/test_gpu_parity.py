@@ -106,3 +106,28 @@ def test_size_independent_properties_large():
     assert np.abs(np.asarray(A.sum(axis=1)).ravel()[rows]).max() <= 1e-11 * scale
     assert np.abs(r[rows]).max() <= 1e-10 * scale * np.abs(pb["vals"][0]).max()
     asm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N", [("ns_unsteady", 8), ("nlheat", 7), ("ns", 6)])
+def test_hessian_vector_products_parity(kind, N):
+    """HessianVectorProduct<i>: d(J.Y)/dU, d(M.Y)/dU (flags 1,2) and sum_jk Y_j H_ijk C_k (flag 0) against the oracle's
+    ndof^3-buffer routine (which is itself checked against finite differences of the Jacobian in tests/test_oracle.py)."""
+    pb = make_problem(kind, N)
+    op = make_oracle(pb)
+    asm = make_gpu(pb)
+    n = pb["dofmap"].n_dof
+    rng = np.random.default_rng(1)
+    Y = rng.uniform(-1, 1, (2, n))
+    Jr, Mr = op.assemble_hessian(Y, flag=2)
+    Jg, Mg = asm.assemble_hessian(Y, flag=2)
+    from scipy.sparse import csr_matrix
+    for ref, got in list(zip(Jr, Jg)) + list(zip(Mr, Mg)):
+        A = csr_matrix((got, asm.indices, asm.indptr), shape=(n, n))
+        scale = max(abs(ref).max(), 1e-300)
+        assert abs(A - ref).max() <= 1e-12 * scale if ref.nnz else np.abs(got).max() == 0.0
+    C = rng.uniform(-1, 1, (3, n))
+    prod = asm.hessian_vector_products(Y[0], C)
+    ref = np.stack([Jr[0] @ c for c in C])
+    assert np.abs(prod - ref).max() <= 1e-12 * np.abs(ref).max()
+    op.close(); asm.close()

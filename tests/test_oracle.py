@@ -147,3 +147,42 @@ def test_golden_vectors(kind, N):
         v = np.cos(np.arange(n))
         assert abs(np.abs(A @ v).sum() - gold[key + "_matvec_l1"]) <= 1e-10 * max(gold[key + "_matvec_l1"], 1e-300)
     op.close()
+
+
+@pytest.mark.parametrize("kind,N", [("ns_unsteady", 3), ("nlheat", 3)])
+def test_hessian_routine_matches_finite_differences_and_flags(kind, N):
+    """the reference's debug_hessian idea (src/elements.cpp:5129): H.Y against finite differences of J and M; flag 0/1/3/4
+    are consistent contractions of the same ndof^3 tensor"""
+    pb = make_problem(kind, N)
+    op = make_oracle(pb)
+    n = pb["dofmap"].n_dof
+    rng = np.random.default_rng(2)
+    Y = rng.uniform(-1, 1, (2, n))
+    e = pb["mesh"].n_elem // 2
+    P, Cs, eq = op.element_hessian(e, Y, flag=2)
+    dm, vals, eps = pb["dofmap"], pb["vals"], 1e-6
+    NJ, NM = np.zeros_like(P[0]), np.zeros_like(P[0])
+    for k, g in enumerate(eq):
+        nn, f = np.argwhere(dm.node_eqn == g)[0]
+        out = []
+        for sgn in (-1, 1):
+            v = vals[0].copy(); v[nn, f] += sgn * eps
+            op.update_values(0, v)
+            out.append(op.element(e, flag=2))
+        op.update_values(0, vals[0])
+        NJ[:, k] = ((out[1][1] - out[0][1]) / (2 * eps)) @ Y[0][eq]
+        NM[:, k] = ((out[1][2] - out[0][2]) / (2 * eps)) @ Y[0][eq]
+    assert np.abs(P[0] - NJ).max() <= 1e-7 * max(np.abs(P[0]).max(), 1e-300)
+    assert np.abs(Cs[0] - NM).max() <= 1e-7 * max(np.abs(NM).max(), np.abs(P[0]).max())
+    if kind == "nlheat":
+        assert np.abs(Cs[0]).max() > 1e-6          # the mass Hessian is really exercised
+    # flag 3: raw tensors; flag 1 / 4 are its contractions over the middle / first index; flag 0 contracts both
+    nd = len(eq)
+    P1 = op.element_hessian(e, Y, flag=1)[0]
+    P4 = op.element_hessian(e, Y, flag=4)[0]
+    C = rng.uniform(-1, 1, (2, n))
+    p0, _ = op.element_hessian(e, Y[0], C=C, flag=0)
+    assert np.abs(p0 - np.stack([P1[0] @ C[v][eq] for v in range(2)])).max() <= 1e-12 * np.abs(p0).max()
+    if kind == "ns_unsteady":                   # convective Hessian is symmetric in (j,k) but not in (i,j)
+        assert np.abs(P1[0] - P4[0]).max() > 1e-8
+    op.close()
