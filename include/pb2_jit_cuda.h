@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 6
+#define PB2_ABI_VERSION 7
 #define PB2_MAX_PARAMS 16
 #define PB2_NTW 7           /* time-stepper storage, MultiTimeStepper (src/timestepper.hpp:37-45) */
 #define PB2_MAX_FIELDS 16
@@ -67,6 +67,8 @@ typedef struct pb2_kernel_args
   const int *block_begin;     /* [grid+1]    range of each thread block in the batch lists below */
   const int *batch_elem;      /* [n_batches] first element of the batch (scheduled element order) */
   const int *batch_meta;      /* [n_batches] (tile << 7) | (wait-for-previous-batch << 6) | number of elements */
+  const unsigned long long *batch_bar; /* [n_batches] bit i: the scatter warps synchronise before element i of the batch (it shares
+                                          CSR entries with an element of the same batch scattered since the last barrier) */
   const int *tile_nbatch;     /* [n_tiles]   batches per tile */
   int *tile_done;             /* [n_tiles]   completion counters, zeroed by the host before the launch */
   int n_batches, n_tiles;

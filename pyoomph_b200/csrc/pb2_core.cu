@@ -48,6 +48,9 @@ struct pb2_problem
   std::vector<int> unit_tile;    // [nunit] tile (= patch colour) of each unit, units sorted by tile
   int n_colours = 0, n_tiles = 0;
   std::vector<int> perm;         // permuted position -> original element
+  bool local_order = true;       // elements of a unit in patch order (chunks of a few elements, colour-sorted inside a chunk)
+  std::vector<int> unit_begin;   // [nunit+1] element range of each unit in the permuted order
+  std::vector<int> h_elem_nodes; // permuted element -> nodes (host copy, for the barrier masks of the batch tables)
   std::vector<int> row_start, col_index;
   // device
   int *d_elem_nodes = nullptr, *d_elem_eqn = nullptr, *d_elem_rowstart = nullptr, *d_elem_res = nullptr;
@@ -65,6 +68,7 @@ struct pb2_problem
   {
     int epb = 0, grid = 0, n_batches = 0, n_tiles = 0;
     int *d_batch_elem = nullptr, *d_batch_meta = nullptr, *d_tile_nbatch = nullptr, *d_tile_done = nullptr, *d_block_begin = nullptr;
+    unsigned long long *d_batch_bar = nullptr;
   };
   std::vector<BatchTables> batch_tables;
   cudaStream_t copy_stream = nullptr;
@@ -305,16 +309,40 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   p->n_tiles = npcol;
   p->perm.resize(ne);
   for (long long e = 0; e < ne; e++) p->perm[e] = (int)e;
-  std::stable_sort(p->perm.begin(), p->perm.end(), [&](int x, int y) {
-    const int ux = unit_rank[unit_of_patch[patch_of[x]]], uy = unit_rank[unit_of_patch[patch_of[y]]];
-    if (ux != uy) return ux < uy;
-    if (colour[x] != colour[y]) return colour[x] < colour[y];
-    return patch_of[x] < patch_of[y];
-  });
-  // colour_begin: ranges of (unit, colour) groups in the permuted order
+  if (const char *cs = getenv("PB2_ORDER")) p->local_order = strcmp(cs, "colour") != 0;
+  if (p->local_order)
+  {
+    // LOCAL order (default): inside a unit the elements follow patch after patch; a patch is cut into chunks of a few
+    // consecutive elements (mesh order) and only inside a chunk the elements are sorted by colour.  Elements that share
+    // CSR entries are then scattered within a few microseconds of each other by the SAME thread block (in program order,
+    // separated by block barriers where they conflict, see batch_bar), so the entry is still in L2 when it is completed.
+    int chunk = 16;
+    if (const char *cs = getenv("PB2_CHUNK")) chunk = std::max(1, atoi(cs));
+    std::vector<int> pos_in_patch(ne), cnt(npatch, 0);
+    for (long long e = 0; e < ne; e++) pos_in_patch[e] = cnt[patch_of[e]]++;
+    std::stable_sort(p->perm.begin(), p->perm.end(), [&](int x, int y) {
+      const int ux = unit_rank[unit_of_patch[patch_of[x]]], uy = unit_rank[unit_of_patch[patch_of[y]]];
+      if (ux != uy) return ux < uy;
+      if (patch_of[x] != patch_of[y]) return patch_of[x] < patch_of[y];
+      const int cx = pos_in_patch[x] / chunk, cy = pos_in_patch[y] / chunk;
+      if (cx != cy) return cx < cy;
+      return colour[x] < colour[y];
+    });
+  }
+  else
+    std::stable_sort(p->perm.begin(), p->perm.end(), [&](int x, int y) {
+      const int ux = unit_rank[unit_of_patch[patch_of[x]]], uy = unit_rank[unit_of_patch[patch_of[y]]];
+      if (ux != uy) return ux < uy;
+      if (colour[x] != colour[y]) return colour[x] < colour[y];
+      return patch_of[x] < patch_of[y];
+    });
+  // colour_begin: ranges of (unit, colour) groups in the permuted order (colour-major order only)
   p->colour_begin.assign((size_t)nunit * ncol + 1, 0);
   for (long long e = 0; e < ne; e++) p->colour_begin[(size_t)unit_rank[unit_of_patch[patch_of[e]]] * ncol + colour[e] + 1]++;
   for (size_t c = 0; c + 1 < p->colour_begin.size(); c++) p->colour_begin[c + 1] += p->colour_begin[c];
+  p->unit_begin.assign((size_t)nunit + 1, 0);
+  for (long long e = 0; e < ne; e++) p->unit_begin[(size_t)unit_rank[unit_of_patch[patch_of[e]]] + 1]++;
+  for (int u = 0; u < nunit; u++) p->unit_begin[u + 1] += p->unit_begin[u];
 
   // ---- permuted element tables
   std::vector<int> elem_nodes((size_t)ne * nn), elem_eqn((size_t)ne * nd);
@@ -330,6 +358,8 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
                                                  : m->node_eqn[node * ci.nval + ci.dof_index[k]];
     }
   }
+
+  p->h_elem_nodes = elem_nodes;
 
   // ---- dof -> elements adjacency (permuted element ids)
   const long long nrow = m->n_dof;
@@ -596,6 +626,7 @@ extern "C" void pb2_problem_free(pb2_problem *p)
   for (auto &b : p->batch_tables)
   {
     cudaFree(b.d_batch_elem);
+    cudaFree(b.d_batch_bar);
     cudaFree(b.d_batch_meta);
     cudaFree(b.d_tile_nbatch);
     cudaFree(b.d_tile_done);
@@ -741,12 +772,15 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
     // one persistent launch; every block walks its own list of batches (units of one tile after the other)
     const int ncol = p->n_colours, nunit = (int)p->unit_tile.size();
     long long nb_total = 0;
-    for (int u = 0; u < nunit; u++)
-      for (int c = 0; c < ncol; c++)
-      {
-        const int n = p->colour_begin[(size_t)u * ncol + c + 1] - p->colour_begin[(size_t)u * ncol + c];
-        nb_total += (n + cfg.elems_per_batch - 1) / cfg.elems_per_batch;
-      }
+    if (p->local_order)
+      for (int u = 0; u < nunit; u++) nb_total += (p->unit_begin[u + 1] - p->unit_begin[u] + cfg.elems_per_batch - 1) / cfg.elems_per_batch;
+    else
+      for (int u = 0; u < nunit; u++)
+        for (int c = 0; c < ncol; c++)
+        {
+          const int n = p->colour_begin[(size_t)u * ncol + c + 1] - p->colour_begin[(size_t)u * ncol + c];
+          nb_total += (n + cfg.elems_per_batch - 1) / cfg.elems_per_batch;
+        }
     // every block must be resident (the tile gate spins): grid <= SMs x occupancy
     const int grid = (int)std::min<long long>(std::max<long long>(1, nb_total), (long long)p->n_sms * cfg.blocks_per_sm);
     pb2_problem::BatchTables *bt = nullptr;
@@ -758,7 +792,11 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
       nb.epb = cfg.elems_per_batch;
       nb.grid = grid;
       std::vector<std::vector<int>> be(grid), bm(grid);
+      std::vector<std::vector<unsigned long long>> bbar(grid);
       std::vector<int> tn(std::max(1, p->n_tiles), 0);
+      std::vector<int> stamp;
+      int epoch = 0;
+      if (p->local_order) stamp.assign((size_t)p->n_node, -1);
       int u = 0;
       for (int t = 0; t < p->n_tiles; t++)
       {
@@ -766,6 +804,35 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
         for (; u < nunit && p->unit_tile[u] == t; u++, k++)
         {
           const int blk = (k + t * 37) % grid; // round robin, rotated per tile so that remainders do not pile up
+          if (p->local_order)
+          {
+            // batches = consecutive elements of the unit; bit i of the barrier mask: element i of the batch shares a node
+            // with an element scattered since the last barrier, so the scatter warps synchronise before it (the order
+            // of the contributions to every CSR entry is then the element order: deterministic, no lost first touch)
+            for (int e = p->unit_begin[u]; e < p->unit_begin[u + 1]; e += nb.epb)
+            {
+              const int nel = std::min(nb.epb, p->unit_begin[u + 1] - e);
+              unsigned long long mask = 0;
+              ++epoch;
+              for (int i = 0; i < nel; i++)
+              {
+                const int *en = &p->h_elem_nodes[(size_t)(e + i) * p->nnode];
+                bool conflict = false;
+                for (int l = 0; l < p->nnode; l++) conflict |= stamp[en[l]] == epoch;
+                if (conflict)
+                {
+                  mask |= 1ull << i;
+                  ++epoch;
+                }
+                for (int l = 0; l < p->nnode; l++) stamp[en[l]] = epoch;
+              }
+              be[blk].push_back(e);
+              bm[blk].push_back((t << 7) | nel);
+              bbar[blk].push_back(mask);
+              tn[t]++;
+            }
+            continue;
+          }
           bool first_of_unit = true;
           for (int c = 0; c < ncol; c++)
           {
@@ -777,6 +844,7 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
               const int fence = (!first_of_unit && first_of_colour) ? 64 : 0;
               be[blk].push_back(e);
               bm[blk].push_back((t << 7) | fence | std::min(nb.epb, b1 - e));
+              bbar[blk].push_back(0ull);
               tn[t]++;
               first_of_colour = false;
               first_of_unit = false;
@@ -785,15 +853,17 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
         }
       }
       std::vector<int> fe, fm, bb(grid + 1, 0);
+      std::vector<unsigned long long> fb;
       for (int b = 0; b < grid; b++)
       {
         bb[b + 1] = bb[b] + (int)be[b].size();
         fe.insert(fe.end(), be[b].begin(), be[b].end());
         fm.insert(fm.end(), bm[b].begin(), bm[b].end());
+        fb.insert(fb.end(), bbar[b].begin(), bbar[b].end());
       }
       nb.n_batches = (int)fe.size();
       nb.n_tiles = p->n_tiles;
-      if (upload(&nb.d_batch_elem, fe) || upload(&nb.d_batch_meta, fm) || upload(&nb.d_tile_nbatch, tn) || upload(&nb.d_block_begin, bb)) return 1;
+      if (upload(&nb.d_batch_elem, fe) || upload(&nb.d_batch_meta, fm) || upload(&nb.d_batch_bar, fb) || upload(&nb.d_tile_nbatch, tn) || upload(&nb.d_block_begin, bb)) return 1;
       CUDA_OK(cudaMalloc((void **)&nb.d_tile_done, std::max(1, nb.n_tiles) * sizeof(int)));
       p->batch_tables.push_back(nb);
       bt = &p->batch_tables.back();
@@ -801,6 +871,7 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
     CUDA_OK(cudaMemsetAsync(bt->d_tile_done, 0, std::max(1, bt->n_tiles) * sizeof(int), (cudaStream_t)cuda_stream));
     a.batch_elem = bt->d_batch_elem;
     a.batch_meta = bt->d_batch_meta;
+    a.batch_bar = bt->d_batch_bar;
     a.tile_nbatch = bt->d_tile_nbatch;
     a.tile_done = bt->d_tile_done;
     a.block_begin = bt->d_block_begin;
@@ -827,6 +898,7 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
     }
     return 0;
   }
+  if (p->local_order) return fail("the phase-synchronous kernels (PB2_PIPELINE=0) need the colour-major element order (PB2_ORDER=colour)");
   for (int c = 0; c < ntile; c++)
   {
     a.elem_begin = p->colour_begin[c];

@@ -578,6 +578,7 @@ class CudaEmitter:
         w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
         w("      const int meta = a.batch_meta[batch], nel = meta & 63, tile = meta >> 7;")
+        w("      const unsigned long long bmask = a.batch_bar[batch];")
         w("      unsigned char* const mbase = maps0 + (it & 1) * %d;" % map_slot_bytes)
         w("      int* const s_rowstart = (int*)mbase; int* const s_resmap = s_rowstart + %d; unsigned char* const s_map = (unsigned char*)(s_resmap + %d);" % (EPB * ND, EPB * ND))
         w("      (void)s_map;")
@@ -614,17 +615,16 @@ class CudaEmitter:
         for pi_, (pname, target, with_res) in enumerate(passes):
             w("        %sif (pass == %d)" % ("" if pi_ == 0 else "else ", pi_))
             w("        {")
+            targs = "%d, %d, %d, %d, %s, %s, %d" % (ND, OUT_S, NS, EPB, "true" if target is not None else "false", "true" if with_res else "false",
+                                                     ND2 if target is not None else 0)
+            tail = "s_rowstart, s_resmap, s_out, %s, a.residual, nel, st, bmask" % (target if target is not None else "(double*)0")
             if target is not None:
                 w("          if (a.map_bits == 8)")
-                w("            pb2_scatter_matrix<unsigned char, 0x80u, 0xFFu, %d, %d, %d, %d>((const unsigned char*)s_map, s_rowstart, s_out, %s, nel, st);" % (ND, OUT_S, NS, EPB, target))
+                w("            pb2_scatter_batch<unsigned char, 0x80u, 0xFFu, %s>((const unsigned char*)s_map, %s);" % (targs, tail))
                 w("          else")
-                w("            pb2_scatter_matrix<unsigned short, 0x8000u, 0xFFFFu, %d, %d, %d, %d>((const unsigned short*)s_map, s_rowstart, s_out, %s, nel, st);" % (ND, OUT_S, NS, EPB, target))
-            if with_res:
-                w("          for (int idx = st; idx < nel * %d; idx += %d)" % (ND, NS))
-                w("          {")
-                w("            const int el = idx / %d, row = idx - el * %d;" % (ND, ND))
-                w("            pb2_put(a.residual, s_resmap[idx], s_out[el * %d + %d + row]);" % (OUT_S, ND2 if target is not None else 0))
-                w("          }")
+                w("            pb2_scatter_batch<unsigned short, 0x8000u, 0xFFFFu, %s>((const unsigned short*)s_map, %s);" % (targs, tail))
+            else:
+                w("          pb2_scatter_batch<unsigned char, 0x80u, 0xFFu, %s>((const unsigned char*)s_map, %s);" % (targs, tail))
             w("        }")
         w("        __threadfence_block();")
         if self.timing: w("        dbs3 += clock64() - ts3;")
@@ -1144,6 +1144,48 @@ class CudaEmitter:
         w("        const bool live = (j + 1 < NJ) || (tid + j * NT < ND2);")
         w("        const unsigned code = live ? (unsigned)m[j][el * ND2] : SKIP;")
         w("        pb2_scatter_entry<FIRST, SKIP>(vals, code, rs[j][el * ND], sv[j][el * ELS]);")
+        w("      }")
+        w("    }")
+        w("  }")
+        w("}")
+        w("// scatter of one batch by the scatter warps of the pipelined kernels: matrix entries as above, the residual entry of row r by")
+        w("// thread NT-1-r.  Elements of a batch may share CSR entries: bit el of bmask = 'synchronise the scatter warps before element el'")
+        w("// (bar.sync orders the first-touch store of one thread before the reduction of another: same block, same address), so every")
+        w("// entry receives its contributions in element order and neighbouring elements complete it while the line is still in L2.")
+        w("template <typename MapT, unsigned FIRST, unsigned SKIP, int ND, int ELS, int NT, int EPB, bool MAT, bool RES, int ROFF>")
+        w("static __device__ __forceinline__ void pb2_scatter_batch(const MapT* __restrict__ mp, const int* __restrict__ rowstart, const int* __restrict__ resmap,")
+        w("                                                         const double* __restrict__ sj, double* __restrict__ vals, double* __restrict__ residual,")
+        w("                                                         const int nel, const int tid, const unsigned long long bmask)")
+        w("{")
+        w("  constexpr int ND2 = ND * ND, NJ = (ND2 + NT - 1) / NT;")
+        w("  const MapT* m[NJ]; const int* rs[NJ]; const double* sv[NJ];")
+        w("  #pragma unroll")
+        w("  for (int j = 0; j < NJ; ++j)")
+        w("  {")
+        w("    const int k = min(tid + j * NT, ND2 - 1);   // clamped slots are masked below")
+        w("    m[j] = mp + k; rs[j] = rowstart + k / ND; sv[j] = sj + k;")
+        w("  }")
+        w("  const int rrow = NT - 1 - tid;   // the residual rows go to the threads with the fewest matrix slots")
+        w("  #pragma unroll")
+        w("  for (int el = 0; el < EPB; ++el)")
+        w("  {")
+        w("    if (el < nel)")
+        w("    {")
+        w("      if ((bmask >> el) & 1ull) pb2_bar_sync(14, NT);")
+        w("      if (MAT)")
+        w("      {")
+        w("        #pragma unroll")
+        w("        for (int j = 0; j < NJ; ++j)")
+        w("        {")
+        w("          const bool live = (j + 1 < NJ) || (tid + j * NT < ND2);")
+        w("          const unsigned code = live ? (unsigned)m[j][el * ND2] : SKIP;")
+        w("          pb2_scatter_entry<FIRST, SKIP>(vals, code, rs[j][el * ND], sv[j][el * ELS]);")
+        w("        }")
+        w("      }")
+        w("      if (RES)")
+        w("      {")
+        w("        #pragma unroll")
+        w("        for (int r = rrow; r < ND; r += NT) pb2_put(residual, resmap[el * ND + r], sj[el * ELS + ROFF + r]);")
         w("      }")
         w("    }")
         w("  }")
