@@ -154,7 +154,7 @@ class CudaEmitter:
         import os as _os
         if ipt_unroll is None and _os.environ.get("PB2_IPT_UNROLL"):
             ipt_unroll = int(_os.environ["PB2_IPT_UNROLL"])
-        self.ipt_unroll = ipt_unroll if ipt_unroll is not None else (3 if self.dim == 2 else 1)
+        self.ipt_unroll = ipt_unroll if ipt_unroll is not None else 1
         self.routines: List[RoutinePlan] = []
         for i, rn in enumerate(code.residual_names()):
             self.routines.append(RoutinePlan("r%d" % i, code.derive(rn), i, -1))
@@ -464,8 +464,17 @@ class CudaEmitter:
         kname = "pb2_%s_%s_f%d" % (self.name, rp.key, what)
         tab_n = self._tables_smem_size()
         IN_S = EL0 | 1
-        PT_S = (NIPT * PB) | 1
-        OUT_S = (ND2 + ND) if what >= 1 else ND
+        vecP = os.environ.get("PB2_VEC_P", "1") != "0"
+        if vecP:
+            PB = (PB + 1) // 2 * 2                       # even point block: coefficients are read and written as double2
+            PT_S = NIPT * PB
+            if (PT_S // 2) % 2 == 0:
+                PT_S += 2                                # element stride = odd number of 16-byte units: elements of a warp hit different bank groups
+        else:
+            PT_S = (NIPT * PB) | 1
+        RS = (ND | 1) if os.environ.get("PB2_RS_PAD", "0") != "0" else ND   # optional odd row stride of the staged matrix: measured slower (scatter reads), off
+        OUT_S = ((ND * RS + ND) | 1) if what >= 1 else ND
+        ROFF = ND * RS if what >= 1 else 0             # residual behind the matrix
         npass = 2 if what >= 2 else 1
         per_el = 8 * (2 * IN_S + PT_S + 2 * OUT_S) + 2 * (2 * ND * 4 + (2 * ND2 if what >= 1 else 0)) + 2 * NN * 4
         budget = self.pipe_smem_budget - tab_n * 8 - 256
@@ -478,7 +487,7 @@ class CudaEmitter:
         NT = NC + NG + NS
         EPB = self.EPB
         off_in = tab_n
-        off_pts = off_in + 2 * EPB * IN_S
+        off_pts = (off_in + 2 * EPB * IN_S + 1) // 2 * 2   # 16-byte aligned
         off_out = off_pts + EPB * PT_S
         off_maps = off_out + 2 * EPB * OUT_S          # doubles; ints/bytes follow
         map_slot_bytes = 2 * EPB * ND * 4 + ((EPB * ND2 * 2 if what >= 1 else 0) + 15) // 16 * 16
@@ -486,6 +495,9 @@ class CudaEmitter:
         self._kernel_smem[kname] = smem_bytes
         self._kernel_cfg[kname] = (EPB, NT, smem_bytes)
         plan = dict(plan)
+        plan["RS"] = RS
+        plan["PB"] = PB
+        plan["vecP"] = vecP
         plan["PT_expr"] = "s_pts + el * %d" % PT_S
         plan["SJ_expr"] = "s_out + el * %d" % OUT_S
         w = o.append
@@ -615,8 +627,8 @@ class CudaEmitter:
         for pi_, (pname, target, with_res) in enumerate(passes):
             w("        %sif (pass == %d)" % ("" if pi_ == 0 else "else ", pi_))
             w("        {")
-            targs = "%d, %d, %d, %d, %s, %s, %d" % (ND, OUT_S, NS, EPB, "true" if target is not None else "false", "true" if with_res else "false",
-                                                     ND2 if target is not None else 0)
+            targs = "%d, %d, %d, %d, %d, %s, %s, %d" % (ND, RS, OUT_S, NS, EPB, "true" if target is not None else "false", "true" if with_res else "false",
+                                                         ROFF if target is not None else 0)
             tail = "s_rowstart, s_resmap, s_out, %s, a.residual, nel, st, bmask" % (target if target is not None else "(double*)0")
             if target is not None:
                 w("          if (a.map_bits == 8)")
@@ -661,6 +673,8 @@ class CudaEmitter:
         w("        double* P = s_pts + el * %d + ipt * %d;" % (PT_S, PB))
         sub: List[str] = []
         self._emit_phase1_body(sub, rp, plan, what)
+        if vecP:
+            sub = self._vectorise_point_writes(sub, PB)
         for ln in sub:
             w("  " + ln)
         w("      }")
@@ -672,7 +686,9 @@ class CudaEmitter:
             w("      { // ---- phase 2 (%s): register-tiled contraction, then staging into OUT" % pname)
             sub = []
             for g in self.groups:
-                self._emit_group_compute(sub, rp, plan, g, pname, coef, coff, with_res)
+                gsub: List[str] = []
+                self._emit_group_compute(gsub, rp, plan, g, pname, coef, coff, with_res)
+                sub += self._vectorise_point_reads(gsub) if vecP else gsub
             for ln in sub:
                 w("  " + ln)
             w("        const int oslot = item & 1;")
@@ -840,23 +856,26 @@ class CudaEmitter:
         am = lambda a, b: "am_%s%d%d" % (gname, a, b)
         if dim == 2:
             w("      const double det_%s = %s * %s - %s * %s;" % (gname, am(0, 0), am(1, 1), am(0, 1), am(1, 0)))
-            up = {(0, 0): "%s / det_%s" % (am(1, 1), gname), (0, 1): "-%s / det_%s" % (am(0, 1), gname),
-                  (1, 0): "-%s / det_%s" % (am(1, 0), gname), (1, 1): "%s / det_%s" % (am(0, 0), gname)}
+            # one IEEE reciprocal instead of the reference's four divisions by det (src/elements.cpp:3690-3703): <=1 ulp apart
+            w("      const double rdet_%s = 1.0 / det_%s;" % (gname, gname))
+            up = {(0, 0): "%s * rdet_%s" % (am(1, 1), gname), (0, 1): "-%s * rdet_%s" % (am(0, 1), gname),
+                  (1, 0): "-%s * rdet_%s" % (am(1, 0), gname), (1, 1): "%s * rdet_%s" % (am(0, 0), gname)}
         else:
             w("      const double det_%s = %s * %s * %s + %s * %s * %s + %s * %s * %s - %s * %s * %s - %s * %s * %s - %s * %s * %s;" % (
                 gname, am(0, 0), am(1, 1), am(2, 2), am(0, 1), am(1, 2), am(2, 0), am(0, 2), am(1, 0), am(2, 1),
                 am(0, 0), am(1, 2), am(2, 1), am(0, 1), am(1, 0), am(2, 2), am(0, 2), am(1, 1), am(2, 0)))
-            D = "det_" + gname
+            w("      const double rdet_%s = 1.0 / det_%s;" % (gname, gname))
+            D = "rdet_" + gname
             up = {
-                (0, 0): "(%s * %s - %s * %s) / %s" % (am(1, 1), am(2, 2), am(1, 2), am(2, 1), D),
-                (0, 1): "-(%s * %s - %s * %s) / %s" % (am(0, 1), am(2, 2), am(0, 2), am(2, 1), D),
-                (0, 2): "(%s * %s - %s * %s) / %s" % (am(0, 1), am(1, 2), am(0, 2), am(1, 1), D),
-                (1, 0): "-(%s * %s - %s * %s) / %s" % (am(1, 0), am(2, 2), am(1, 2), am(2, 0), D),
-                (1, 1): "(%s * %s - %s * %s) / %s" % (am(0, 0), am(2, 2), am(0, 2), am(2, 0), D),
-                (1, 2): "-(%s * %s - %s * %s) / %s" % (am(0, 0), am(1, 2), am(0, 2), am(1, 0), D),
-                (2, 0): "(%s * %s - %s * %s) / %s" % (am(1, 0), am(2, 1), am(1, 1), am(2, 0), D),
-                (2, 1): "-(%s * %s - %s * %s) / %s" % (am(0, 0), am(2, 1), am(0, 1), am(2, 0), D),
-                (2, 2): "(%s * %s - %s * %s) / %s" % (am(0, 0), am(1, 1), am(0, 1), am(1, 0), D),
+                (0, 0): "(%s * %s - %s * %s) * %s" % (am(1, 1), am(2, 2), am(1, 2), am(2, 1), D),
+                (0, 1): "-(%s * %s - %s * %s) * %s" % (am(0, 1), am(2, 2), am(0, 2), am(2, 1), D),
+                (0, 2): "(%s * %s - %s * %s) * %s" % (am(0, 1), am(1, 2), am(0, 2), am(1, 1), D),
+                (1, 0): "-(%s * %s - %s * %s) * %s" % (am(1, 0), am(2, 2), am(1, 2), am(2, 0), D),
+                (1, 1): "(%s * %s - %s * %s) * %s" % (am(0, 0), am(2, 2), am(0, 2), am(2, 0), D),
+                (1, 2): "-(%s * %s - %s * %s) * %s" % (am(0, 0), am(1, 2), am(0, 2), am(1, 0), D),
+                (2, 0): "(%s * %s - %s * %s) * %s" % (am(1, 0), am(2, 1), am(1, 1), am(2, 0), D),
+                (2, 1): "-(%s * %s - %s * %s) * %s" % (am(0, 0), am(2, 1), am(0, 1), am(2, 0), D),
+                (2, 2): "(%s * %s - %s * %s) * %s" % (am(0, 0), am(1, 1), am(0, 1), am(1, 0), D),
             }
         for (al, be), e in up.items():
             w("      const double up_%s%d%d = %s;" % (gname, al, be, e))
@@ -891,6 +910,53 @@ class CudaEmitter:
 
     def _group_nacc(self, form, g, coef) -> int:
         return self._group_acc_layout(form, g, coef)[1]
+
+    @staticmethod
+    def _vectorise_point_reads(lines: List[str]) -> List[str]:
+        """P[n] reads of the contraction become halves of 128-bit shared-memory loads (one wavefront serves two coefficients:
+        the shared-memory pipe, not the fp64 pipe, is the busiest unit of the kernel, profiles/r01_notes.md)"""
+        import re
+        out: List[str] = []
+        ptr_line = -1
+        used = set()
+        for ln in lines:
+            if "const double* P = " in ln:
+                ptr_line = len(out)
+                out.append(ln)
+                continue
+            if ptr_line >= 0:
+                def rep(m):
+                    n = int(m.group(1))
+                    used.add(n // 2)
+                    return "pq%d.%s" % (n // 2, "xy"[n % 2])
+                ln = re.sub(r"\bP\[(\d+)\]", rep, ln)
+            out.append(ln)
+        if ptr_line >= 0 and used:
+            ind = " " * (len(out[ptr_line]) - len(out[ptr_line].lstrip()))
+            loads = [ind + "const double2 pq%d = *reinterpret_cast<const double2*>(P + %d);" % (k, 2 * k) for k in sorted(used)]
+            out[ptr_line + 1:ptr_line + 1] = loads
+        return out
+
+    @staticmethod
+    def _vectorise_point_writes(lines: List[str], npoint: int) -> List[str]:
+        """P[n] = expr of phase 1 become registers that are stored pairwise (128-bit) at the end of the point"""
+        import re
+        out: List[str] = []
+        seen = set()
+        ind = "      "
+        for ln in lines:
+            m = re.match(r"^(\s*)P\[(\d+)\] = (.*);$", ln)
+            if m:
+                ind = m.group(1)
+                seen.add(int(m.group(2)))
+                out.append("%sconst double pw%s = %s;" % (m.group(1), m.group(2), m.group(3)))
+            else:
+                out.append(ln)
+        for k in range((npoint + 1) // 2):
+            a_, b_ = ("pw%d" % (2 * k) if 2 * k in seen else "0.0"), ("pw%d" % (2 * k + 1) if 2 * k + 1 in seen else "0.0")
+            if 2 * k in seen or 2 * k + 1 in seen:
+                out.append("%s*reinterpret_cast<double2*>(P + %d) = make_double2(%s, %s);" % (ind, 2 * k, a_, b_))
+        return out
 
     def _emit_group_compute(self, o: List[str], rp: RoutinePlan, plan, g: RowGroup, pname, coef, coff, with_res):
         code, dim, NIPT = self.code, self.dim, self.NIPT
@@ -1023,13 +1089,13 @@ class CudaEmitter:
             w("          {")
             w("            const int row = c_row_%s[lt];" % F)
             if with_res:
-                roff = ND * ND if with_matrix else 0
+                roff = ND * plan.get("RS", ND) if with_matrix else 0
                 if F in fields:
                     w("            SJ[%d + row] = acc[%d + k];" % (roff, base[(F, "__res")]))
                 else:
                     w("            SJ[%d + row] = 0.0;" % roff)
             if with_matrix:
-                w("            double* srow = SJ + row * %d;" % ND)
+                w("            double* srow = SJ + row * %d;" % plan.get("RS", ND))
                 for G in unknowns:
                     nnG = self._nnode_space(code.fields[G].space)
                     for c in range(nnG):
@@ -1152,7 +1218,7 @@ class CudaEmitter:
         w("// thread NT-1-r.  Elements of a batch may share CSR entries: bit el of bmask = 'synchronise the scatter warps before element el'")
         w("// (bar.sync orders the first-touch store of one thread before the reduction of another: same block, same address), so every")
         w("// entry receives its contributions in element order and neighbouring elements complete it while the line is still in L2.")
-        w("template <typename MapT, unsigned FIRST, unsigned SKIP, int ND, int ELS, int NT, int EPB, bool MAT, bool RES, int ROFF>")
+        w("template <typename MapT, unsigned FIRST, unsigned SKIP, int ND, int RS, int ELS, int NT, int EPB, bool MAT, bool RES, int ROFF>")
         w("static __device__ __forceinline__ void pb2_scatter_batch(const MapT* __restrict__ mp, const int* __restrict__ rowstart, const int* __restrict__ resmap,")
         w("                                                         const double* __restrict__ sj, double* __restrict__ vals, double* __restrict__ residual,")
         w("                                                         const int nel, const int tid, const unsigned long long bmask)")
@@ -1163,7 +1229,7 @@ class CudaEmitter:
         w("  for (int j = 0; j < NJ; ++j)")
         w("  {")
         w("    const int k = min(tid + j * NT, ND2 - 1);   // clamped slots are masked below")
-        w("    m[j] = mp + k; rs[j] = rowstart + k / ND; sv[j] = sj + k;")
+        w("    m[j] = mp + k; rs[j] = rowstart + k / ND; sv[j] = sj + (k / ND) * RS + k % ND;")
         w("  }")
         w("  const int rrow = NT - 1 - tid;   // the residual rows go to the threads with the fewest matrix slots")
         w("  #pragma unroll")
