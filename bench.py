@@ -289,7 +289,13 @@ def main():
         b_el -= float(info.alg_bytes_per_hist_level) * (info.n_hist_val - 1)   # steady: history levels are not read
     # dominant (only) kernel: the generated ResidualAndJacobian routine, one launch per colour
     achieved = b_el * n_elem_rank / (ms_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    try:   # DRAM bytes per launch from the committed ncu --set full capture of this very workload (profiles/r01_traffic.json)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = float(tj["%s:%d" % (args.workload, n)]["traffic_bytes"]) if world == 1 else None
+    except Exception:
+        traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "alg_bytes_per_element": b_el, "kernel": "pb2_%s_r0_f1" % pb["code"].name,
                 "launches_per_step": launches // max(1, args.steps), "tiles_per_step": asm.num_launches(), "avg_launch_ms": ms_step / max(1, launches // max(1, args.steps))}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
