@@ -183,7 +183,13 @@ def main():
     device = local_rank
 
     t_setup = time.time()
+    verbose = os.environ.get("PB2_BENCH_VERBOSE") and rank == 0
+
+    def note(msg):
+        if verbose:
+            print("[bench %.1fs] %s" % (time.time() - t_setup, msg), file=sys.stderr, flush=True)
     pb = build_workload(args.workload, n)
+    note("workload built")
     mesh = pb["mesh"]
     from pyoomph_b200.assembly import B200Assembly
     dasm = None
@@ -203,6 +209,7 @@ def main():
     if pb["unsteady"]:
         from problems import TIME
         asm.set_unsteady(TIME["t"], TIME["dt"], TIME["dtprev"], TIME["unsteady_steps_done"])
+    note("assembler ready")
     t_setup = time.time() - t_setup
     n_elem_rank = asm.n_elem
     info = asm.info
@@ -230,6 +237,7 @@ def main():
         if n_w % 8 == 0:
             lib.pb2_device_synchronize()
     barrier()
+    note("warm-up done (%d steps)" % n_w)
     launches = 0
     lib.pb2_event_record(0, None)
     for _ in range(args.steps):
