@@ -182,12 +182,12 @@ def main():
         dist = dist_mod
     device = local_rank
 
-    t_setup = time.time()
+    t_setup = t_start = time.time()
     verbose = os.environ.get("PB2_BENCH_VERBOSE") and rank == 0
 
     def note(msg):
         if verbose:
-            print("[bench %.1fs] %s" % (time.time() - t_setup, msg), file=sys.stderr, flush=True)
+            print("[bench %.1fs] %s" % (time.time() - t_start, msg), file=sys.stderr, flush=True)
     pb = build_workload(args.workload, n)
     note("workload built")
     mesh = pb["mesh"]
@@ -242,7 +242,7 @@ def main():
     lib.pb2_event_record(0, None)
     for _ in range(args.steps):
         step()
-        launches += asm.launch_count() + (3 * (len(dasm.send) + len(dasm.recv)) if dasm is not None else 0)
+        launches += asm.launch_count() + ((len(dasm.send) + len(dasm.recv)) if dasm is not None else 0)   # + one pack / add kernel per neighbour
     lib.pb2_event_record(1, None)
     ms = ctypes.c_float()
     lib.pb2_event_elapsed_ms(0, 1, ctypes.byref(ms))

@@ -74,6 +74,14 @@ int pb2_problem_set_parameters(pb2_problem *p, const double *values, int n);
 int pb2_problem_assemble(pb2_problem *p, int residual_index, int param_index, unsigned flag, void *cuda_stream);
 /* device pointers of the outputs (for GPU-side consumers) */
 int pb2_problem_device_outputs(pb2_problem *p, double **residual, double **jac_vals, double **mass_vals);
+/* multi-GPU interface exchange (oomph-lib ships off-rank row contributions to their owner, problem.cc:6970-7121): one kernel packs
+ * residual[rows[i]] and, for flag >= 1, jac_vals[pos[j]] (flag 2: then mass_vals[pos[j]]) into `buf` (device, n_rows + flag * n_pos
+ * doubles); the owner adds a received buffer with pb2_problem_unpack_add.  rows/pos are device arrays with unique entries, so the
+ * add needs no atomics and the sum order is the call order. */
+int pb2_problem_pack_rows(pb2_problem *p, const long long *rows, long long n_rows, const long long *pos, long long n_pos, unsigned flag,
+                          double *buf, void *cuda_stream);
+int pb2_problem_unpack_add(pb2_problem *p, const long long *rows, long long n_rows, const long long *pos, long long n_pos, unsigned flag,
+                           const double *buf, void *cuda_stream);
 /* copy results to host buffers (any may be NULL) */
 int pb2_problem_fetch(pb2_problem *p, double *residual, double *jac_vals, double *mass_vals);
 /* the reference-facing call: host dofs in, host residual/CSR values out, copies included */

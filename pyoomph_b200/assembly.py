@@ -77,7 +77,8 @@ def load_library() -> ctypes.CDLL:
                "pb2_problem_set_nodal_positions", "pb2_problem_set_lagrangian_positions", "pb2_problem_set_dofs",
                "pb2_problem_set_time", "pb2_problem_set_parameters", "pb2_problem_assemble", "pb2_problem_device_outputs",
                "pb2_problem_fetch", "pb2_problem_assemble_host", "pb2_problem_num_colours", "pb2_version",
-               "pb2_problem_assemble_hessian", "pb2_problem_fetch_hessian", "pb2_problem_hessian_vector_products"):
+               "pb2_problem_assemble_hessian", "pb2_problem_fetch_hessian", "pb2_problem_hessian_vector_products",
+               "pb2_problem_pack_rows", "pb2_problem_unpack_add"):
         getattr(L, fn).restype = ctypes.c_int
     _LIB = L
     return L
@@ -300,6 +301,16 @@ class B200Assembly(CustomAssemblyBase):
         r, j, m = c_double_p(), c_double_p(), c_double_p()
         _check(self.lib.pb2_problem_device_outputs(self.prob, ctypes.byref(r), ctypes.byref(j), ctypes.byref(m)))
         return (ctypes.cast(r, ctypes.c_void_p).value, ctypes.cast(j, ctypes.c_void_p).value, ctypes.cast(m, ctypes.c_void_p).value)
+
+    def pack_rows(self, rows_ptr: int, n_rows: int, pos_ptr: int, n_pos: int, flag: int, buf_ptr: int, stream=None):
+        """interface exchange, sender side: residual[rows] | jac[pos] (| mass[pos]) -> buf (all device pointers)"""
+        _check(self.lib.pb2_problem_pack_rows(self.prob, ctypes.c_void_p(rows_ptr), ctypes.c_longlong(n_rows), ctypes.c_void_p(pos_ptr),
+                                              ctypes.c_longlong(n_pos), ctypes.c_uint(flag), ctypes.c_void_p(buf_ptr), ctypes.c_void_p(stream or 0)))
+
+    def unpack_add(self, rows_ptr: int, n_rows: int, pos_ptr: int, n_pos: int, flag: int, buf_ptr: int, stream=None):
+        """interface exchange, owner side: residual[rows] += ..., jac[pos] += ... from a received buffer"""
+        _check(self.lib.pb2_problem_unpack_add(self.prob, ctypes.c_void_p(rows_ptr), ctypes.c_longlong(n_rows), ctypes.c_void_p(pos_ptr),
+                                               ctypes.c_longlong(n_pos), ctypes.c_uint(flag), ctypes.c_void_p(buf_ptr), ctypes.c_void_p(stream or 0)))
 
     def launch_count(self) -> int:
         return int(self.lib.pb2_problem_launch_count(self.prob))

@@ -1007,6 +1007,74 @@ extern "C" int pb2_problem_device_outputs(pb2_problem *p, double **residual, dou
   return 0;
 }
 
+// ---- interface exchange: pack / unpack-add of halo rows (one launch each; SM-count-multiple grids, 16-byte friendly index loads)
+static __global__ void pb2_pack_kernel(const double *__restrict__ res, const double *__restrict__ jac, const double *__restrict__ mass,
+                                       const long long *__restrict__ rows, long long n_rows, const long long *__restrict__ pos, long long n_pos,
+                                       int nmat, double *__restrict__ buf)
+{
+  const long long total = n_rows + (long long)nmat * n_pos;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+  {
+    if (i < n_rows)
+      buf[i] = res[rows[i]];
+    else
+    {
+      const long long j = i - n_rows;
+      buf[i] = j < n_pos ? jac[pos[j]] : mass[pos[j - n_pos]];
+    }
+  }
+}
+
+static __global__ void pb2_unpack_add_kernel(double *__restrict__ res, double *__restrict__ jac, double *__restrict__ mass,
+                                             const long long *__restrict__ rows, long long n_rows, const long long *__restrict__ pos, long long n_pos,
+                                             int nmat, const double *__restrict__ buf)
+{
+  const long long total = n_rows + (long long)nmat * n_pos;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+  {
+    if (i < n_rows)
+      res[rows[i]] += buf[i];
+    else
+    {
+      const long long j = i - n_rows;
+      if (j < n_pos)
+        jac[pos[j]] += buf[i];
+      else
+        mass[pos[j - n_pos]] += buf[i];
+    }
+  }
+}
+
+static int exchange_grid(pb2_problem *p, long long total) { return (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)p->n_sms * 8)); }
+
+extern "C" int pb2_problem_pack_rows(pb2_problem *p, const long long *rows, long long n_rows, const long long *pos, long long n_pos, unsigned flag,
+                                     double *buf, void *cuda_stream)
+{
+  CUDA_OK(cudaSetDevice(p->device));
+  if (flag > 2u) return fail("flag must be 0, 1 or 2");
+  if (flag == 2u && !p->d_mass) return fail("no mass matrix has been assembled");
+  const long long total = n_rows + (long long)flag * n_pos;
+  if (total <= 0) return 0;
+  pb2_pack_kernel<<<exchange_grid(p, total), 256, 0, (cudaStream_t)cuda_stream>>>(p->d_residual, p->d_jac, p->d_mass, rows, n_rows, pos, n_pos, (int)flag, buf);
+  CUDA_OK(cudaGetLastError());
+  p->launches_total++;
+  return 0;
+}
+
+extern "C" int pb2_problem_unpack_add(pb2_problem *p, const long long *rows, long long n_rows, const long long *pos, long long n_pos, unsigned flag,
+                                      const double *buf, void *cuda_stream)
+{
+  CUDA_OK(cudaSetDevice(p->device));
+  if (flag > 2u) return fail("flag must be 0, 1 or 2");
+  if (flag == 2u && !p->d_mass) return fail("no mass matrix has been assembled");
+  const long long total = n_rows + (long long)flag * n_pos;
+  if (total <= 0) return 0;
+  pb2_unpack_add_kernel<<<exchange_grid(p, total), 256, 0, (cudaStream_t)cuda_stream>>>(p->d_residual, p->d_jac, p->d_mass, rows, n_rows, pos, n_pos, (int)flag, buf);
+  CUDA_OK(cudaGetLastError());
+  p->launches_total++;
+  return 0;
+}
+
 extern "C" int pb2_problem_fetch(pb2_problem *p, double *residual, double *jac_vals, double *mass_vals)
 {
   CUDA_OK(cudaSetDevice(p->device));

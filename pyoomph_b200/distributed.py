@@ -257,13 +257,19 @@ class DistributedAssembly:
             tensors.append(self.local.jacobian_tensor())
         if flag >= 2:
             tensors.append(self.local.mass_tensor())
+        native = hasattr(self.local, "pack_rows")       # GPU: one pack kernel per neighbour, one grouped NCCL send/recv, one add kernel
         ops, recvbufs = [], {}
         for q, s in sorted(self.send.items()):
-            parts = [tensors[0][s["rows_t"]]] + [t[s["pos_t"]] for t in tensors[1:]]
-            ops.append(dist.P2POp(dist.isend, torch.cat(parts).contiguous(), q))
+            n = s["rows_local"].size + flag * s["pos"].size
+            if native:
+                buf = self._buffer(("s", q, flag), n)
+                self.local.pack_rows(s["rows_t"], s["pos_t"], flag, buf)
+            else:
+                buf = torch.cat([tensors[0][s["rows_t"]]] + [t[s["pos_t"]] for t in tensors[1:]]).contiguous()
+            ops.append(dist.P2POp(dist.isend, buf, q))
         for src, r in sorted(self.recv.items()):
             n = r["rows_local"].size + (len(tensors) - 1) * r["pos"].size
-            recvbufs[src] = torch.empty(n, dtype=torch.float64, device=self.device)
+            recvbufs[src] = self._buffer(("r", src, flag), n)
             ops.append(dist.P2POp(dist.irecv, recvbufs[src], src))
         if ops:
             for rq in dist.batch_isend_irecv(ops):      # one grouped send/recv (ncclGroupStart/End under NCCL)
@@ -272,9 +278,19 @@ class DistributedAssembly:
         for src in sorted(recvbufs):
             r, buf = self.recv[src], recvbufs[src]
             nr, npos = r["rows_local"].size, r["pos"].size
+            if native:
+                self.local.unpack_add(r["rows_t"], r["pos_t"], flag, buf)
+                continue
             tensors[0].index_add_(0, r["rows_t"], buf[:nr])
             for k, t in enumerate(tensors[1:]):
                 t.index_add_(0, r["pos_t"], buf[nr + k * npos: nr + (k + 1) * npos])
+
+    def _buffer(self, key, n: int):
+        """persistent exchange buffers (one per neighbour, direction and flag)"""
+        bufs = self.__dict__.setdefault("_bufs", {})
+        if key not in bufs or bufs[key].numel() != n:
+            bufs[key] = self.torch.empty(n, dtype=self.torch.float64, device=self.device)
+        return bufs[key]
 
     # ---- results ---------------------------------------------------------------------------------
     def owned_block(self, want_mass: bool = False):
@@ -314,6 +330,15 @@ class GPULocalAssembler:
             ptrs = self.asm.device_outputs()
             self._views[k] = self.torch.as_tensor(_DevicePointerArray(ptrs[k], n), device=self.dev)
         return self._views[k]
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def pack_rows(self, rows_t, pos_t, flag: int, buf):
+        self.asm.pack_rows(rows_t.data_ptr(), rows_t.numel(), pos_t.data_ptr(), pos_t.numel(), flag, buf.data_ptr(), self._stream())
+
+    def unpack_add(self, rows_t, pos_t, flag: int, buf):
+        self.asm.unpack_add(rows_t.data_ptr(), rows_t.numel(), pos_t.data_ptr(), pos_t.numel(), flag, buf.data_ptr(), self._stream())
 
     def residual_tensor(self):
         return self._view(0, self.asm.n_dof)
