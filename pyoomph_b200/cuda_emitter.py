@@ -259,9 +259,21 @@ class CudaEmitter:
         jkeys = sorted(form.J.keys()) if what >= 1 else []
         mkeys = sorted(form.M.keys()) if what >= 2 else []
         plan["R_off"] = poff
-        plan["J_off"] = {k: poff + ncoef + i for i, k in enumerate(jkeys)}
-        plan["M_off"] = {k: poff + ncoef + len(jkeys) + i for i, k in enumerate(mkeys)}
-        poff += ncoef + len(jkeys) + len(mkeys)
+        poff += ncoef
+        # Jacobian / mass coefficients: symbolically identical expressions share one slot of the point block (NS: 17 -> 9), every
+        # slot costs two shared-memory wavefronts per warp and Gauss point in the contraction (profiles/r01_notes.md)
+        dedup = os.environ.get("PB2_DEDUP", "1") != "0"
+        seen: Dict[object, int] = {}
+
+        def slot_of(expr):
+            nonlocal poff
+            key = sp.srepr(expr) if dedup else object()
+            if key not in seen:
+                seen[key] = poff
+                poff += 1
+            return seen[key]
+        plan["J_off"] = {k: slot_of(form.J[k]) for k in jkeys}
+        plan["M_off"] = {k: slot_of(form.M[k]) for k in mkeys}
         plan["PB"] = poff
         els = plan["EL0"] + self.NIPT * poff
         nstage = self.ndof * self.ndof + self.ndof if what >= 1 else self.ndof
@@ -476,11 +488,16 @@ class CudaEmitter:
         OUT_S = ((ND * RS + ND) | 1) if what >= 1 else ND
         ROFF = ND * RS if what >= 1 else 0             # residual behind the matrix
         npass = 2 if what >= 2 else 1
-        per_el = 8 * (2 * IN_S + PT_S + 2 * OUT_S) + 2 * (2 * ND * 4 + (2 * ND2 if what >= 1 else 0)) + 2 * NN * 4
-        budget = self.pipe_smem_budget - tab_n * 8 - 256
+        # helper mode: the row group with the least contraction work (the C1 rows of a Taylor-Hood class) also computes phase 1 of
+        # the NEXT batch, so the warps of the heavy row groups run the fp64-dense contraction back to back (point data double-buffered)
+        helper = self.groups[-1] if (len(self.groups) >= 2 and os.environ.get("PB2_HELPER", "0") != "0") else None
+        n_pts_slots = 2 if helper is not None else 1
+        per_el = 8 * (2 * IN_S + n_pts_slots * PT_S + 2 * OUT_S) + 2 * (2 * ND * 4 + (2 * ND2 if what >= 1 else 0)) + 2 * NN * 4
+        budget = (self.pipe_smem_budget if helper is None else max(self.pipe_smem_budget, 226 * 1024)) - tab_n * 8 - 256
         self.EPB = max(2, min(self.EPB_max, 63, budget // per_el))
         self._layout_threads()
         NC = sum(g.nthreads for g in self.groups)
+        NH = helper.nthreads if helper is not None else 0
         NG, NS = self.pipe_gather_threads, self.pipe_scatter_threads
         if NC + NG + NS > 384 and "PB2_PIPE_NS" not in os.environ:
             NG, NS = 32, max(64, 384 - NC - 32)   # keep the register cap (65536 / block size) at 170 for the compute warps
@@ -488,7 +505,7 @@ class CudaEmitter:
         EPB = self.EPB
         off_in = tab_n
         off_pts = (off_in + 2 * EPB * IN_S + 1) // 2 * 2   # 16-byte aligned
-        off_out = off_pts + EPB * PT_S
+        off_out = off_pts + n_pts_slots * EPB * PT_S
         off_maps = off_out + 2 * EPB * OUT_S          # doubles; ints/bytes follow
         map_slot_bytes = 2 * EPB * ND * 4 + ((EPB * ND2 * 2 if what >= 1 else 0) + 15) // 16 * 16
         smem_bytes = off_maps * 8 + 2 * map_slot_bytes + 2 * EPB * NN * 4
@@ -532,7 +549,7 @@ class CudaEmitter:
         w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")
         w("      pb2_bar_sync(13, %d);                        // indices of this batch visible to all gather warps" % NG)
         if self.timing: w("      long long tg0 = clock64();")
-        w("      if (it >= 2) pb2_bar_sync(%d + slot, %d);   // IN[slot] released by the compute warps" % (3, NC + NG))
+        w("      if (it >= 2) pb2_bar_sync(%d + slot, %d);   // IN[slot] released by the phase-1 threads" % (3, (NH or NC) + NG))
         if self.timing: w("      long long tg1 = clock64(); dbg0 += tg1 - tg0;")
         w("      double* const s_in = smem + %d + slot * %d;" % (off_in, EPB * IN_S))
         w("      for (int i = gt; i < nel * %d; i += %d)" % (NN, NG))
@@ -556,7 +573,7 @@ class CudaEmitter:
         w("      asm volatile(\"cp.async.wait_group 1;\" ::: \"memory\");   // nodal data of this batch has landed; next indices may be in flight")
         w("      __threadfence_block();")
         if self.timing: w("      dbg1 += clock64() - tg1;")
-        w("      pb2_bar_arrive(%d + slot, %d);            // IN[slot] full" % (1, NC + NG))
+        w("      pb2_bar_arrive(%d + slot, %d);            // IN[slot] full" % (1, (NH or NC) + NG))
         w("    }")
         if self.timing: w("    if (gt == 0 && a.debug) { atomicAdd(a.debug + 0, (unsigned long long)dbg0); atomicAdd(a.debug + 1, (unsigned long long)dbg1); atomicAdd(a.debug + 2, (unsigned long long)it); }")
         w("  }")
@@ -609,7 +626,7 @@ class CudaEmitter:
         w("      {")
         w("        if (st == 0) { while (*(volatile int*)(a.tile_done + tile - 1) < a.tile_nbatch[tile - 1]) __nanosleep(64); }")
         w("        gated_tile = tile;")
-        w("        pb2_bar_sync(12, %d);                     // gate passed (tile, gated_tile are uniform over the scatter warps)" % NS)
+        w("        pb2_bar_sync(11, %d);                     // gate passed (tile, gated_tile are uniform over the scatter warps)" % NS)
         w("        __threadfence();")
         w("      }")
         is_h = rp.key.startswith("h")      # Hessian-vector routine: matrices only, no residual
@@ -654,6 +671,13 @@ class CudaEmitter:
             cpasses.append(("M", form.M, plan["M_off"], False, True))
         nacc = max(self._group_nacc(form, g, coef) for g in self.groups for (_, coef, _, _, _) in cpasses)
         w("    double acc[%d];" % max(1, nacc))
+        if helper is not None:
+            self._emit_compute_helper_mode(o, rp, plan, what, cpasses, helper, dict(NC=NC, NH=NH, NG=NG, NS=NS, EPB=EPB, IN_S=IN_S, PT_S=PT_S, PB=PB, OUT_S=OUT_S,
+                                                                                   off_in=off_in, off_pts=off_pts, off_out=off_out, vecP=vecP))
+            w("  }")
+            w("}")
+            w("")
+            return kname
         w("    double* const s_pts = smem + %d;" % off_pts)
         w("    int it = 0, item = 0;")
         w("    long long dbc0 = 0, dbc1 = 0, dbc2 = 0, dbc3 = 0, dbc4 = 0; (void)dbc0; (void)dbc1; (void)dbc2; (void)dbc3; (void)dbc4;")
@@ -713,6 +737,115 @@ class CudaEmitter:
         w("}")
         w("")
         return kname
+
+    def _emit_compute_helper_mode(self, o: List[str], rp: RoutinePlan, plan, what: int, cpasses, helper: RowGroup, k):
+        """compute warps when one row group (`helper`) doubles as the phase-1 producer of the next batch; barrier ids:
+        1,2 IN full / 3,4 IN free (gather <-> helper), 10,15 PTS full / 12,14 PTS free (helper <-> heavy groups), 5,6 OUT full /
+        7,8 OUT free (all compute <-> scatter), 9 helper-internal"""
+        w = o.append
+        NC, NH, NG, NS, EPB = k["NC"], k["NH"], k["NG"], k["NS"], k["EPB"]
+        NIPT = self.NIPT
+        heavy = [g for g in self.groups if g is not helper]
+        PTS_FULL, PTS_FREE = (10, 15), (12, 14)
+
+        def stage_and_publish(groups, pname, coef, with_res, with_matrix, ind):
+            w(ind + "const int oslot = item & 1;")
+            w(ind + "if (item >= 2) pb2_bar_sync(%d + oslot, %d);  // OUT[oslot] drained by the scatter warps" % (7, NC + NS))
+            w(ind + "double* const s_out = smem + %d + oslot * %d;" % (k["off_out"], EPB * k["OUT_S"]))
+            sub: List[str] = []
+            for g in groups:
+                self._emit_group_stage(sub, rp, plan, g, pname, coef, with_res, with_matrix)
+            for ln in sub:
+                w(ind[:-6] + ln if len(ind) >= 6 else ln)
+            w(ind + "__threadfence_block();")
+            w(ind + "pb2_bar_arrive(%d + oslot, %d);           // OUT[oslot] full" % (5, NC + NS))
+            w(ind + "++item;")
+
+        def compute(groups, pname, coef, coff, with_res, ind):
+            sub: List[str] = []
+            for g in groups:
+                gsub: List[str] = []
+                self._emit_group_compute(gsub, rp, plan, g, pname, coef, coff, with_res)
+                sub += self._vectorise_point_reads(gsub) if k["vecP"] else gsub
+            for ln in sub:
+                w(ind[:-6] + ln if len(ind) >= 6 else ln)
+
+        def phase1(batch_expr, slot_expr, ind):
+            w(ind + "{ // ---- phase 1 of batch %s: one thread per (element, Gauss point), into PTS[%s]" % (batch_expr, slot_expr))
+            w(ind + "  const int nel1 = a.batch_meta[%s] & 63;" % batch_expr)
+            w(ind + "  const double* const s_in = smem + %d + (%s) * %d;" % (k["off_in"], slot_expr, EPB * k["IN_S"]))
+            w(ind + "  double* const s_ptw = smem + %d + (%s) * %d;" % (k["off_pts"], slot_expr, EPB * k["PT_S"]))
+            npar = int(os.environ.get("PB2_P1_ILP", "2"))
+            w(ind + "  // %d points per thread in one basic block: their dependent chains (9-term sums, reciprocal, sqrt) interleave" % npar)
+            w(ind + "  for (int i0 = tid - %d; i0 < nel1 * %d; i0 += %d)" % (helper.thread_off, NIPT, npar * NH))
+            w(ind + "  {")
+            for rep in range(npar):
+                w(ind + "    {")
+                w(ind + "      const int i = min(i0 + %d, nel1 * %d - 1);   // a clamped duplicate rewrites identical values" % (rep * NH, NIPT))
+                w(ind + "      const int el = i / %d, ipt = i - el * %d;" % (NIPT, NIPT))
+                w(ind + "      const double* E = s_in + el * %d;" % k["IN_S"])
+                w(ind + "      double* P = s_ptw + el * %d + ipt * %d;" % (k["PT_S"], k["PB"]))
+                sub: List[str] = []
+                self._emit_phase1_body(sub, rp, plan, what)
+                if k["vecP"]:
+                    sub = self._vectorise_point_writes(sub, k["PB"])
+                for ln in sub:
+                    w(ind + ln)
+                w(ind + "    }")
+            w(ind + "  }")
+            w(ind + "  __threadfence_block();")
+            w(ind + "}")
+        # ------------------------------------------------ heavy row groups: contraction only
+        w("    if (tid < %d)" % helper.thread_off)
+        w("    {")
+        w("      int it = 0, item = 0;")
+        w("      for (int batch = ib0; batch < ib1; ++batch, ++it)")
+        w("      {")
+        w("        const int slot = it & 1;")
+        w("        const int nel = a.batch_meta[batch] & 63;")
+        w("        pb2_bar_sync(slot ? %d : %d, %d);          // PTS[slot] full" % (PTS_FULL[1], PTS_FULL[0], NC))
+        w("        const double* const s_pts = smem + %d + slot * %d;" % (k["off_pts"], EPB * k["PT_S"]))
+        for pi_, (pname, coef, coff, with_res, with_matrix) in enumerate(cpasses):
+            w("        { // ---- phase 2 (%s)" % pname)
+            compute(heavy, pname, coef, coff, with_res, "          ")
+            if pi_ + 1 == len(cpasses):
+                w("          __threadfence_block();")
+                w("          if (batch + 2 < ib1) pb2_bar_arrive(slot ? %d : %d, %d);   // PTS[slot] may be refilled (results are in registers)" % (PTS_FREE[1], PTS_FREE[0], NC))
+            stage_and_publish(heavy, pname, coef, with_res, with_matrix, "          ")
+            w("        }")
+        w("      }")
+        w("    }")
+        # ------------------------------------------------ helper row group: its own rows + phase 1 of the next batch
+        w("    else")
+        w("    {")
+        w("      int it = 0, item = 0;")
+        w("      if (ib0 < ib1)")
+        w("      {")
+        w("        pb2_bar_sync(1, %d);                       // IN[0] full" % (NH + NG))
+        phase1("ib0", "0", "        ")
+        w("        if (ib0 + 2 < ib1) pb2_bar_arrive(3, %d);  // IN[0] may be refilled" % (NH + NG))
+        w("      }")
+        w("      for (int batch = ib0; batch < ib1; ++batch, ++it)")
+        w("      {")
+        w("        const int slot = it & 1;")
+        w("        const int nel = a.batch_meta[batch] & 63;")
+        w("        pb2_bar_sync(9, %d);                        // phase 1 of this batch complete (all helper threads)" % NH)
+        w("        pb2_bar_arrive(slot ? %d : %d, %d);        // PTS[slot] full: the heavy row groups may start" % (PTS_FULL[1], PTS_FULL[0], NC))
+        w("        const double* const s_pts = smem + %d + slot * %d;" % (k["off_pts"], EPB * k["PT_S"]))
+        w("        if (batch + 1 < ib1)   // first the point data the heavy groups wait for next, then this group's own rows")
+        w("        {")
+        w("          if (it >= 1) pb2_bar_sync(slot ? %d : %d, %d);   // PTS[slot ^ 1] released by the heavy row groups" % (PTS_FREE[0], PTS_FREE[1], NC))
+        w("          pb2_bar_sync(slot ? 1 : 2, %d);          // IN[slot ^ 1] full" % (NH + NG))
+        phase1("batch + 1", "slot ^ 1", "          ")
+        w("          if (batch + 3 < ib1) pb2_bar_arrive(slot ? 3 : 4, %d);   // IN[slot ^ 1] may be refilled" % (NH + NG))
+        w("        }")
+        for pi_, (pname, coef, coff, with_res, with_matrix) in enumerate(cpasses):
+            w("        { // ---- phase 2 (%s), helper rows" % pname)
+            compute([helper], pname, coef, coff, with_res, "          ")
+            stage_and_publish([helper], pname, coef, with_res, with_matrix, "          ")
+            w("        }")
+        w("      }")
+        w("    }")
 
     def _emit_gather_node(self, o: List[str], plan, c1: bool, use_async: bool = False):
         code, dim = self.code, self.dim
@@ -831,7 +964,11 @@ class CudaEmitter:
         pr = _CudaPrinter(names)
         for s, e in repl:
             w("      const double %s = %s;" % (s.name, pr.doprint(e)))
+        written = set()
         for tgt, e in zip(targets, red):
+            if tgt in written:
+                continue          # shared slot of identical coefficients
+            written.add(tgt)
             w("      P[%d] = %s;" % (tgt, pr.doprint(e)))
         self._flops_phase1 = sum(int(sp.count_ops(e)) for _, e in repl) + sum(int(sp.count_ops(e)) for e in red)
 
@@ -1055,9 +1192,22 @@ class CudaEmitter:
                 expr = accname
                 for (wn, tn) in parts:          # one DFMA per term, accumulated in place
                     expr = "fma(%s, %s, %s)" % (wn, tn, expr)
-                w("            #pragma unroll")
-                w("            for (int c = 0; c < %d; ++c)" % nnG)
-                w("              %s = %s;" % (accname, expr))
+                chunk = int(os.environ.get("PB2_COL_CHUNK", "9"))
+                if nnG > chunk and self.table_source == "smem":
+                    # shared-memory tables: without a fence ptxas hoists all table loads of the row (4 per column) above the
+                    # DFMAs and spills the accumulators (3D: 108 loads); columns go in chunks with a compiler barrier in between
+                    w("            #pragma unroll")
+                    w("            for (int c0 = 0; c0 < %d; c0 += %d)" % (nnG, chunk))
+                    w("            {")
+                    w("              #pragma unroll")
+                    w("              for (int c = c0; c < (c0 + %d < %d ? c0 + %d : %d); ++c)" % (chunk, nnG, chunk, nnG))
+                    w("                %s = %s;" % (accname, expr))
+                    w("              asm volatile(\"\" ::: \"memory\");")
+                    w("            }")
+                else:
+                    w("            #pragma unroll")
+                    w("            for (int c = 0; c < %d; ++c)" % nnG)
+                    w("              %s = %s;" % (accname, expr))
         w("          }")
         w("        }")
         w("      }")
@@ -1237,7 +1387,7 @@ class CudaEmitter:
         w("  {")
         w("    if (el < nel)")
         w("    {")
-        w("      if ((bmask >> el) & 1ull) pb2_bar_sync(14, NT);")
+        w("      if ((bmask >> el) & 1ull) pb2_bar_sync(11, NT);")
         w("      if (MAT)")
         w("      {")
         w("        #pragma unroll")
