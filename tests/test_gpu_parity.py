@@ -131,3 +131,43 @@ def test_hessian_vector_products_parity(kind, N):
     ref = np.stack([Jr[0] @ c for c in C])
     assert np.abs(prod - ref).max() <= 1e-12 * np.abs(ref).max()
     op.close(); asm.close()
+
+
+@pytest.mark.gpu
+def test_full_size_config2_windows_against_oracle():
+    """BASELINE config 2 at FULL size (NS Taylor-Hood 1024x1024, 1.05 M elements, all 148 blocks, all tile gates): rows of the
+    nodes interior to sampled 4x4-element windows -- domain corners and edges (pinned dofs), patch / unit / tile boundaries
+    (multiples of 8 and 32 elements), random interior places -- against the CPU oracle assembled on the window alone; and the
+    assembly is bit-reproducible at this size."""
+    from windows import check_windows
+    N = 1024
+    pb = make_problem("ns", N)
+    asm = make_gpu(pb)
+    asm.assemble(flag=1)
+    r, jac, _ = asm.fetch()
+    rng = np.random.default_rng(5)
+    windows = [(0, 0), (N - 4, N - 4), (0, N - 4), (N - 4, 0), (0, 510), (510, 0), (6, 6), (30, 30), (254, 510), (510, 766), (1018, 6)]
+    windows += [tuple(int(x) for x in rng.integers(0, N - 4, size=2)) for _ in range(8)]
+    worst = check_windows(pb, make_oracle, asm.indptr, asm.indices, jac, r, windows, w=4, tol=TOL)
+    print("full-size window parity: worst row-scaled error %.2e over %d windows" % (worst, len(windows)))
+    asm.assemble(flag=1)
+    r2, jac2, _ = asm.fetch()
+    assert np.array_equal(r, r2) and np.array_equal(jac, jac2)
+    asm.close()
+
+
+@pytest.mark.gpu
+def test_full_size_config3_windows_against_oracle():
+    """BASELINE config 3 at FULL size (transient heat, 126^3 = 2.0 M C2 bricks, BDF2): 2x2x2-element windows against the oracle."""
+    from windows import check_windows
+    N = 126
+    pb = make_problem("heat3d", N)
+    asm = make_gpu(pb)
+    asm.assemble(flag=1)
+    r, jac, _ = asm.fetch()
+    rng = np.random.default_rng(7)
+    windows = [(0, 0, 0), (N - 2, N - 2, N - 2), (0, 62, N - 2), (3, 3, 3), (62, 62, 62), (N - 2, 0, 63)]
+    windows += [tuple(int(x) for x in rng.integers(0, N - 2, size=3)) for _ in range(4)]
+    worst = check_windows(pb, make_oracle, asm.indptr, asm.indices, jac, r, windows, w=2, tol=TOL)
+    print("full-size window parity (config 3): worst row-scaled error %.2e over %d windows" % (worst, len(windows)))
+    asm.close()
