@@ -925,7 +925,7 @@ class CudaEmitter:
             if want_grad:
                 decl += ["s%d_%s = 0.0" % (b, tag) for b in range(dim)]
             w("      double %s;" % ", ".join(decl))
-            w("      #pragma unroll")
+            w("      #pragma unroll%s" % self._node_unroll(nn))
             w("      for (int l = 0; l < %d; ++l) { const double u = %s;" % (nn, srcexpr))
             if want_val:
                 w("        v_%s += u * %s[l];" % (tag, ps))
@@ -972,6 +972,12 @@ class CudaEmitter:
             w("      P[%d] = %s;" % (tgt, pr.doprint(e)))
         self._flops_phase1 = sum(int(sp.count_ops(e)) for _, e in repl) + sum(int(sp.count_ops(e)) for e in red)
 
+    @staticmethod
+    def _node_unroll(nn: int) -> str:
+        """node loops of phase 1: fully unrolled for 2D (9 nodes); for 27-node bricks ptxas hoists every load of a fully unrolled
+        loop (> 255 registers, accumulators of phase 2 end up in local memory), so the loop is unrolled by 3"""
+        return "" if nn <= 9 else " %d" % int(os.environ.get("PB2_NODE_UNROLL", "3"))
+
     def _emit_geometry(self, o: List[str], plan, src: str, gname: str, detname: str):
         """Restates fill_shape_info_at_s for el_dim==nodal_dim (src/elements.cpp:3604-3626 tangents, :3677-3703 2D
         metric/inverse, :3804-3836 3D) with the same operation order; stores gab_gai[b][i] to the point block."""
@@ -979,7 +985,7 @@ class CudaEmitter:
         w = o.append
         t = "t_" + gname
         w("      double %s;" % ", ".join("%s%d%d = 0.0" % (t, a, i) for a in range(dim) for i in range(dim)))
-        w("      #pragma unroll")
+        w("      #pragma unroll%s" % self._node_unroll(NN))
         w("      for (int l = 0; l < %d; ++l) {" % NN)
         for i in range(dim):
             for a in range(dim):
@@ -1192,22 +1198,9 @@ class CudaEmitter:
                 expr = accname
                 for (wn, tn) in parts:          # one DFMA per term, accumulated in place
                     expr = "fma(%s, %s, %s)" % (wn, tn, expr)
-                chunk = int(os.environ.get("PB2_COL_CHUNK", "9"))
-                if nnG > chunk and self.table_source == "smem":
-                    # shared-memory tables: without a fence ptxas hoists all table loads of the row (4 per column) above the
-                    # DFMAs and spills the accumulators (3D: 108 loads); columns go in chunks with a compiler barrier in between
-                    w("            #pragma unroll")
-                    w("            for (int c0 = 0; c0 < %d; c0 += %d)" % (nnG, chunk))
-                    w("            {")
-                    w("              #pragma unroll")
-                    w("              for (int c = c0; c < (c0 + %d < %d ? c0 + %d : %d); ++c)" % (chunk, nnG, chunk, nnG))
-                    w("                %s = %s;" % (accname, expr))
-                    w("              asm volatile(\"\" ::: \"memory\");")
-                    w("            }")
-                else:
-                    w("            #pragma unroll")
-                    w("            for (int c = 0; c < %d; ++c)" % nnG)
-                    w("              %s = %s;" % (accname, expr))
+                w("            #pragma unroll")
+                w("            for (int c = 0; c < %d; ++c)" % nnG)
+                w("              %s = %s;" % (accname, expr))
         w("          }")
         w("        }")
         w("      }")
