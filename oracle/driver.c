@@ -763,19 +763,31 @@ double oracle_assemble(void *h, int which, int param, unsigned flag, double *res
     }
     free(R); free(J); free(M); free(ts);
   }
-  /* merge per-range results in range order (single range: no-op) */
-  for (int th = 1; th < nthreads; th++)
+  /* merge per-range results in range order (single range: no-op).  Rows are independent, so the merge runs over row blocks in
+   * parallel: the order of the contributions to one row is still the range order (same result as a serial merge); this is what
+   * the reference gets from MPI ranks that each assemble their own rows (problem.cc:6543), without a serial bottleneck that
+   * would undersell the CPU baseline */
+  if (nthreads > 1)
   {
-    for (int i = 0; i < o->n_dof; i++) residuals[i] += res_t[th][i];
-    for (int m = 0; m < nmat; m++)
-      for (int i = 0; i < o->n_dof; i++)
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+#endif
+    for (int i = 0; i < o->n_dof; i++)
+      for (int th = 1; th < nthreads; th++)
       {
-        Row *r = &rows[th * 2 + m][i];
-        for (int k = 0; k < r->n; k++) row_add(&rows[m][i], r->p[k].col, r->p[k].val);
-        free(r->p);
+        residuals[i] += res_t[th][i];
+        for (int m = 0; m < nmat; m++)
+        {
+          Row *r = &rows[th * 2 + m][i];
+          for (int k = 0; k < r->n; k++) row_add(&rows[m][i], r->p[k].col, r->p[k].val);
+          free(r->p);
+        }
       }
-    free(res_t[th]);
-    for (int m = 0; m < nmat; m++) free(rows[th * 2 + m]);
+    for (int th = 1; th < nthreads; th++)
+    {
+      free(res_t[th]);
+      for (int m = 0; m < nmat; m++) free(rows[th * 2 + m]);
+    }
   }
   for (int m = 0; m < nmat; m++)
   {
