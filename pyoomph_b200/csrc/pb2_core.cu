@@ -19,6 +19,7 @@
 
 #include "pyoomph_b200.h"
 
+#define PB2_DOF_NO_TARGET ((long long)0x8000000000000000ULL)
 static thread_local std::string g_err;
 static int fail(const std::string &m)
 {
@@ -557,7 +558,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   std::vector<int>().swap(elem_csr);
 
   // ---- dof -> nodal storage target for set_dofs: >=0 index into node_val (t=0), <0: ~index into node_pos (t=0)
-  std::vector<long long> dof_target(nrow, 0);
+  std::vector<long long> dof_target(nrow, PB2_DOF_NO_TARGET);
   for (long long n = 0; n < m->n_node; n++)
   {
     for (int f = 0; f < ci.nval; f++)
@@ -686,6 +687,7 @@ static __global__ void pb2_scatter_dofs(const double *__restrict__ dofs, const l
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long t = target[i];
+  if (t == PB2_DOF_NO_TARGET) return; // a column-only (ghost) dof of a row-block partition: no nodal storage on this GPU
   if (t >= 0)
     node_val[t] = dofs[i];
   else

@@ -292,6 +292,29 @@ class DistributedAssembly:
             bufs[key] = self.torch.empty(n, dtype=self.torch.float64, device=self.device)
         return bufs[key]
 
+    def assemble_host(self, local_dofs: Optional[np.ndarray], flag: int = 1, out=None, **kw):
+        """The reference-facing call of one rank: host dof values of its LOCAL rows in (owned | halo | ghost order, `part.l2g`),
+        host residual / CSR values of its OWNED row block out.  Host<->device copies, the local kernels and the interface
+        exchange are all inside the call; `out` = (residual[n_owned], jac[nnz_owned] or None, mass[nnz_owned] or None) torch
+        CPU tensors (pinned for full PCIe speed), allocated when omitted.  Every rank moves only its own block, so N GPUs use
+        N host links."""
+        torch = self.torch
+        if local_dofs is not None:
+            self.local.set_dofs(local_dofs)
+        self.assemble(flag=flag, **kw)
+        nnz = int(self.indptr[self.n_owned])
+        if out is None:
+            out = (torch.empty(self.n_owned, dtype=torch.float64), torch.empty(nnz, dtype=torch.float64) if flag >= 1 else None,
+                   torch.empty(nnz, dtype=torch.float64) if flag >= 2 else None)
+        out[0].copy_(self.local.residual_tensor()[:self.n_owned], non_blocking=True)
+        if flag >= 1:
+            out[1].copy_(self.local.jacobian_tensor()[:nnz], non_blocking=True)
+        if flag >= 2:
+            out[2].copy_(self.local.mass_tensor()[:nnz], non_blocking=True)
+        if str(self.device).startswith("cuda"):
+            torch.cuda.synchronize(self.device)
+        return out
+
     # ---- results ---------------------------------------------------------------------------------
     def owned_block(self, want_mass: bool = False):
         """(row_begin, row_end, indptr, global column indices, values[, mass values], residual) of the owned row block"""
@@ -333,6 +356,10 @@ class GPULocalAssembler:
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def set_dofs(self, dofs):
+        """host values of the LOCAL dofs (owned | halo | ghost) -> nodal storage on the device (pb2_problem_set_dofs)"""
+        self.asm.set_dofs(dofs.numpy() if hasattr(dofs, "numpy") else dofs)
 
     def pack_rows(self, rows_t, pos_t, flag: int, buf):
         self.asm.pack_rows(rows_t.data_ptr(), rows_t.numel(), pos_t.data_ptr(), pos_t.numel(), flag, buf.data_ptr(), self._stream())

@@ -75,6 +75,8 @@ def _worker(rank, world, port, kind, N, outdir):
                                     lambda el, dm, extra: OracleLocalAssembler(pb, el, dm, extra), dist=dist)
     da.assemble(flag=2)
     rb, re, ip, gc, jv, mv, res = da.owned_block(want_mass=True)
+    h_res, h_jac, h_mass = da.assemble_host(None, 2)           # the host-facing call of one rank returns the same owned block
+    assert np.array_equal(h_res.numpy(), res) and np.array_equal(h_jac.numpy(), jv) and np.array_equal(h_mass.numpy(), mv)
     np.savez(os.path.join(outdir, "r%d.npz" % rank), rb=rb, re=re, ip=ip, gc=gc, jv=jv, mv=mv, res=res, new_of_old=da.part.new_of_old,
              xbytes=da.exchange_bytes)
     dist.barrier()
