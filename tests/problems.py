@@ -5,7 +5,7 @@ from pyoomph_b200.codegen import FiniteElementCode
 from pyoomph_b200.equations import (NavierStokesEquations, NonlinearHeatEquation, PoissonEquation, PseudoElasticMesh,
                                     TransientHeatEquation)
 from pyoomph_b200.expressions import exp, var, global_parameter
-from pyoomph_b200.meshes import CuboidBrickMesh, RectangularQuadMesh, assign_equation_numbers
+from pyoomph_b200.meshes import assign_equation_numbers
 
 
 def smooth_field(pos, k, seed):
@@ -24,9 +24,58 @@ def poisson_source():
     return 100 * exp(-100 * ((x - 0.5) ** 2 + (y - 0.5) ** 2))
 
 
-def make_problem(kind: str, N: int, seed: int = 0):
+class UnstructuredView:
+    """A structured mesh with its elements visited in random order and its nodes relabelled at random, WITHOUT the patch
+    hint: what a mesh from an external generator looks like to the assembler (no lattice order to lean on)."""
+
+    def __init__(self, mesh, seed):
+        rng = np.random.default_rng(seed)
+        eperm = rng.permutation(mesh.n_elem)
+        new_of_old = rng.permutation(mesh.n_node)
+        old_of_new = np.argsort(new_of_old)
+        self.dim, self.N, self.element_type = mesh.dim, mesh.N, mesh.element_type
+        self.elem_nodes = np.ascontiguousarray(new_of_old[mesh.elem_nodes[eperm]].astype(np.int32))
+        self.node_pos = np.ascontiguousarray(mesh.node_pos[old_of_new])
+        self.node_lattice = np.ascontiguousarray(mesh.node_lattice[old_of_new])
+        self.boundaries = {k: np.sort(new_of_old[v]) for k, v in mesh.boundaries.items()}
+        self.n_elem, self.n_node = mesh.n_elem, mesh.n_node
+
+    def is_vertex(self):
+        return np.all(self.node_lattice % 2 == 0, axis=1)
+
+
+def distort(mesh, amplitude, seed):
+    """smooth + random displacement of every node by up to `amplitude` element widths: non-affine elements, the mapping
+    Jacobian differs at every Gauss point (mid nodes leave the straight line between their vertices)"""
+    h = 1.0 / max(mesh.N)
+    rng = np.random.default_rng(seed + 991)
+    d = np.stack([smooth_field(mesh.node_pos, 20 + k, seed) for k in range(mesh.dim)], axis=1)
+    mesh.node_pos = mesh.node_pos + amplitude * h * (0.6 * d / max(1e-300, np.abs(d).max()) + 0.4 * rng.uniform(-1, 1, size=d.shape))
+    return mesh
+
+
+def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unstructured: bool = False):
     """Returns dict(code, mesh, dofmap, vals[T,n_node,nval], pos_hist or None, unsteady(bool), params)."""
     params = {}
+    variant = (distortion, unstructured)
+    if distortion or unstructured:
+        import pyoomph_b200.meshes as _m
+        _mk = {"quad": _m.RectangularQuadMesh, "brick": _m.CuboidBrickMesh}
+
+        def _variant(mesh):
+            if unstructured:
+                mesh = UnstructuredView(mesh, seed + 5)
+            if distortion:
+                mesh = distort(mesh, distortion, seed)
+            return mesh
+
+        def RectangularQuadMesh(n):
+            return _variant(_mk["quad"](n))
+
+        def CuboidBrickMesh(n):
+            return _variant(_mk["brick"](n))
+    else:
+        from pyoomph_b200.meshes import CuboidBrickMesh, RectangularQuadMesh
     if kind == "poisson":          # config 1
         mesh = RectangularQuadMesh(N)
         code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")

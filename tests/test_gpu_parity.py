@@ -15,10 +15,14 @@ TOL = 1e-12
 CASES = [("poisson", 64), ("poisson", 5), ("ns", 12), ("ns_unsteady", 9), ("heat3d", 3), ("ale", 7), ("ns_param", 6)]
 
 
+# (kind, N, distortion in element widths, unstructured = random element order + random node labels, no patch hint)
+VARIANTS = [("ns", 11, 0.12, False), ("ns_unsteady", 10, 0.1, True), ("heat3d", 3, 0.1, True), ("ale", 6, 0.08, True), ("poisson", 33, 0.15, True)]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,N", CASES)
-def test_residual_jacobian_mass_parity(kind, N):
-    pb = make_problem(kind, N)
+@pytest.mark.parametrize("kind,N,distortion,unstructured", [(k, n, 0.0, False) for k, n in CASES] + VARIANTS)
+def test_residual_jacobian_mass_parity(kind, N, distortion, unstructured):
+    pb = make_problem(kind, N, distortion=distortion, unstructured=unstructured)
     op = make_oracle(pb)
     asm = make_gpu(pb)
     n = pb["dofmap"].n_dof

@@ -47,6 +47,59 @@ def test_analytic_jacobian_matches_finite_differences(kind, N):
     op.close()
 
 
+@pytest.mark.parametrize("kind,N", [("ns", 4), ("heat3d", 2), ("ale", 3)])
+def test_analytic_jacobian_on_distorted_unstructured_meshes(kind, N):
+    """non-affine elements (curved edges, mapping Jacobian varying over the Gauss points), random element and node order"""
+    pb = make_problem(kind, N, distortion=0.12, unstructured=True)
+    op = make_oracle(pb)
+    for e in (0, pb["mesh"].n_elem - 1):
+        J, Jfd = _fd_jacobian(op, pb, e)
+        assert np.abs(J - Jfd).max() <= 5e-8 * np.abs(J).max()
+    op.close()
+
+
+def test_distorted_mesh_patch_test_and_relabelling_invariance():
+    """(i) a linear field on a distorted Q9 mesh has an exactly constant gradient: the interior Laplace residual stays at the
+    level the mistyped Gauss knots leave; the total area is the sum of the point weights.  (ii) relabelling nodes and
+    elements permutes the matrix symmetrically and nothing else."""
+    from pyoomph_b200.codegen import FiniteElementCode
+    from pyoomph_b200.equations import PoissonEquation
+    from scipy.sparse import csr_matrix
+    pb = make_problem("poisson", 5, distortion=0.12)
+    pb["code"] = FiniteElementCode("Quad2dC2", PoissonEquation(), name="laplace")
+    x = pb["mesh"].node_pos
+    pb["vals"][0][:, 0] = 0.5 - 1.5 * x[:, 0] + 2.5 * x[:, 1]
+    op = make_oracle(pb)
+    r, mats = op.assemble(flag=1)
+    lat = pb["mesh"].node_lattice
+    interior = np.all((lat > 2) & (lat < 2 * np.array(pb["mesh"].N) - 2), axis=1)
+    assert np.abs(r[pb["dofmap"].node_eqn[interior, 0]]).max() <= 1e-7
+    op.close()
+    a = make_problem("ns_param", 4, distortion=0.1)          # (no pin by node number in this problem: pins follow the boundaries)
+    b = make_problem("ns_param", 4, distortion=0.1, unstructured=True)
+    # same geometry and values, different labels: node i of `a` is node q[i] of `b`
+    key = lambda m: m.node_lattice[:, 0].astype(np.int64) * 1000 + m.node_lattice[:, 1]
+    q = np.argsort(key(b["mesh"]))[np.argsort(np.argsort(key(a["mesh"])))]
+    assert np.array_equal(b["mesh"].node_lattice[q], a["mesh"].node_lattice)
+    b["mesh"].node_pos[q] = a["mesh"].node_pos
+    for t in range(a["vals"].shape[0]):
+        b["vals"][t][q] = a["vals"][t]
+    oa, ob = make_oracle(a), make_oracle(b)
+    ra, ma = oa.assemble(flag=1)
+    rb, mb = ob.assemble(flag=1)
+    n = a["dofmap"].n_dof
+    ea, eb = a["dofmap"].node_eqn, b["dofmap"].node_eqn[q]
+    m = ea >= 0
+    assert np.array_equal(m, eb >= 0)
+    perm = np.empty(n, dtype=np.int64); perm[ea[m]] = eb[m]          # equation of a -> equation of b
+    A, B = csr_to_sorted(n, *ma[0]).tocoo(), csr_to_sorted(n, *mb[0])
+    Ap = csr_matrix((A.data, (perm[A.row], perm[A.col])), shape=(n, n))
+    assert abs(Ap - B).max() <= 1e-13 * abs(B).max()
+    rp = np.empty(n); rp[perm] = ra
+    assert np.abs(rp - rb).max() <= 1e-13 * np.abs(rb).max()
+    oa.close(); ob.close()
+
+
 def test_moving_mesh_tensors_match_finite_differences():
     """int_pt_weights_d_coords and d_dx_shape_dcoord (src/elements.cpp:3051-3155) against FD of the shape buffer."""
     pb = make_problem("ale", 3)
