@@ -111,9 +111,13 @@ class FiniteElementCode:
     pyoomph/generic/codegen.py:60)."""
 
     def __init__(self, element_type: str, equations: "Equations", *, default_timestepping_scheme: str = "BDF2",
-                 name: str = "domain"):
+                 name: str = "domain", coordinate_system=None):
         self.etype = ELEMENT_TYPES[element_type]
         self.nodal_dim = self.etype.nodal_dim
+        # Problem.set_coordinate_system (pyoomph/generic/problem.py) / Equations.get_coordinate_system: Cartesian unless told otherwise
+        if isinstance(coordinate_system, str):
+            coordinate_system = {"cartesian": ex.cartesian, "axisymmetric": ex.axisymmetric}[coordinate_system]
+        self.coordinate_system = coordinate_system or ex.cartesian
         self.name = name
         self.default_timestepping_scheme = default_timestepping_scheme
         self.fields: Dict[str, Field] = {}
@@ -154,7 +158,10 @@ class FiniteElementCode:
 
     def define_vector_field(self, name: str, space: str, dim: Optional[int] = None):
         dim = dim or self.nodal_dim
-        comps = [name + "_" + d for d in ex.DIRS[:dim]]
+        if dim > self.nodal_dim and self.coordinate_system.get_id_name() == "Axisymmetric":
+            comps = [name + "_x", name + "_y", name + "_phi"][:dim]       # azimuthal (swirl) component
+        else:
+            comps = [name + "_" + d for d in ex.DIRS[:dim]]
         for c in comps:
             self.define_scalar_field(c, space)
         self.vector_fields[name] = comps

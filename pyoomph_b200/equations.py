@@ -11,7 +11,7 @@ Scaling/non-dimensionalisation factors of the reference are all 1 here (no units
 from __future__ import annotations
 
 from .codegen import Equations
-from .expressions import (Weak, contract, div, dot, grad, identity_matrix, material_derivative, partial_t,
+from .expressions import (Weak, cartesian, contract, div, dot, grad, identity_matrix, material_derivative, partial_t,
                           rational_num, sym, testfunction, trace, var, var_and_test, weak)
 
 
@@ -50,15 +50,16 @@ class StokesEquations(Equations):
     """Stokes flow, Taylor-Hood: velocity in C2, pressure in C1 (navier_stokes.py:148-344)."""
 
     def __init__(self, *, dynamic_viscosity=1.0, bulkforce=None, velocity_name="velocity", pressure_name="pressure",
-                 pressure_sign_flip=False, pressure_factor=1):
+                 pressure_sign_flip=False, pressure_factor=1, with_azimuthal_velocity=False):
         super().__init__()
+        self.with_azimuthal_velocity = with_azimuthal_velocity      # axisymmetric flow with swirl: third velocity component
         self.dynamic_viscosity = dynamic_viscosity
         self.bulkforce = bulkforce
         self.velocity_name, self.pressure_name = velocity_name, pressure_name
         self.pressure_sign_flip, self.pressure_factor = pressure_sign_flip, pressure_factor
 
     def define_fields(self):
-        self.define_vector_field(self.velocity_name, "C2")
+        self.define_vector_field(self.velocity_name, "C2", dim=3 if self.with_azimuthal_velocity else None)
         self.define_scalar_field(self.pressure_name, "C1")
 
     def define_stress_tensor(self):
@@ -94,9 +95,9 @@ class NavierStokesEquations(StokesEquations):
 class PseudoElasticMesh(Equations):
     """Moving mesh as a linear-elastic pseudo solid in Lagrangian coordinates (ALE.py:97-146)."""
 
-    def __init__(self, E=1, nu=rational_num(3, 10)):
+    def __init__(self, E=1, nu=rational_num(3, 10), coordsys=cartesian):
         super().__init__()
-        self.E, self.nu = E, nu
+        self.E, self.nu, self.coordsys = E, nu, coordsys      # the mesh equations stay Cartesian by default (ALE.py:117)
 
     def define_fields(self):
         self.activate_coordinates_as_dofs()
@@ -106,11 +107,11 @@ class PseudoElasticMesh(Equations):
         mu = E / 2 / (1 + nu)
         lmbda = E * nu / (1 + nu) / (1 - 2 * nu)
         lmbda = 2 * mu * lmbda / (lmbda + 2 * mu)
-        eps = lambda v: sym(grad(v, lagrangian=True))
+        eps = lambda v: sym(grad(v, lagrangian=True, coordsys=self.coordsys))
         sigma = lambda v: lmbda * trace(eps(v)) * identity_matrix() + 2 * mu * eps(v)
         x, x_test = var_and_test("mesh")
         X = var("lagrangian")
-        self.add_residual(Weak(sigma(x - X), eps(x_test)))
+        self.add_residual(Weak(sigma(x - X), eps(x_test), coordinate_system=self.coordsys))
 
 
 class NonlinearHeatEquation(Equations):

@@ -84,6 +84,11 @@ def _vector_components(code, name: str) -> Optional[List[str]]:
 _ALIASES = {"mesh_x": "coordinate_x", "mesh_y": "coordinate_y", "mesh_z": "coordinate_z"}
 
 
+def _padding(code, comps) -> list:
+    """zero components up to the vector dimension of the coordinate system (an axisymmetric (r,z) vector is (r,z,0))"""
+    return [sp.Integer(0)] * max(0, code.coordinate_system.vector_dimension(code.nodal_dim) - len(comps))
+
+
 def var(arg: Union[str, Sequence[str]]):
     """Field value(s) by name; vector fields expand to a column of components (generic.py:137)."""
     if not isinstance(arg, str):
@@ -93,7 +98,7 @@ def var(arg: Union[str, Sequence[str]]):
         return TIME
     comps = _vector_components(code, arg)
     if comps is not None:
-        return sp.Matrix([_field(c) for c in comps])
+        return sp.Matrix([_field(c) for c in comps] + _padding(code, comps))
     return _field(_ALIASES.get(arg, arg))
 
 
@@ -104,7 +109,7 @@ def testfunction(arg: Union[str, Sequence[str]]):
     code = _Context.current()
     comps = _vector_components(code, arg)
     if comps is not None:
-        return sp.Matrix([_test(c) for c in comps])
+        return sp.Matrix([_test(c) for c in comps] + _padding(code, comps))
     return _test(_ALIASES.get(arg, arg))
 
 
@@ -127,27 +132,135 @@ def _coords(lagrangian: bool):
     return (LAG if lagrangian else EUL)[:code.nodal_dim]
 
 
-def grad(arg: ExpressionOrNum, lagrangian: bool = False):
-    """Gradient: scalar -> column vector, vector -> matrix G[i,j]=d u_i / d x_j (generic.py:355).
+class BaseCoordinateSystem:
+    """Differential operators and measure of a coordinate system (pyoomph/expressions/coordsys.py:37): the equation classes
+    call the generic grad/div/weak below, which dispatch to the coordinate system of the element code (or to an explicit
+    ``coordsys=`` argument, as pyoomph/equations/ALE.py:136-146 does for the mesh equations)."""
 
-    Only the Cartesian coordinate system is built here; axisymmetric terms are added by the
-    equation classes that need them (see equations.AxisymmetricNavierStokes)."""
-    cs = _coords(lagrangian)
+    def get_id_name(self) -> str:
+        raise NotImplementedError
+
+    def vector_dimension(self, nodal_dim: int) -> int:
+        """components of a vector expression (get_actual_dimension, coordsys.py:394)"""
+        return nodal_dim
+
+    def integral_dx(self, lagrangian: bool):
+        raise NotImplementedError
+
+    def scalar_gradient(self, arg, lagrangian: bool):
+        raise NotImplementedError
+
+    def vector_gradient(self, arg, lagrangian: bool):
+        raise NotImplementedError
+
+    def vector_divergence(self, arg, lagrangian: bool):
+        raise NotImplementedError
+
+    def tensor_divergence(self, arg, lagrangian: bool):
+        raise NotImplementedError
+
+
+class CartesianCoordinateSystem(BaseCoordinateSystem):
+    """coordsys.py:253.  Vectors that carry more components than the mesh has dimensions (the zero-padded vectors of an
+    axisymmetric element code handed to a Cartesian operator) keep their size: the missing derivatives are zero."""
+
+    def get_id_name(self) -> str:
+        return "Cartesian"
+
+    def integral_dx(self, lagrangian: bool):
+        return DX_LAG if lagrangian else DX_EUL
+
+    def scalar_gradient(self, arg, lagrangian: bool):
+        return sp.Matrix([sp.diff(arg, c) for c in _coords(lagrangian)])
+
+    def vector_gradient(self, arg, lagrangian: bool):
+        cs = _coords(lagrangian)
+        n = arg.shape[0]
+        return sp.Matrix(n, max(n, len(cs)), lambda i, j: sp.diff(arg[i, 0], cs[j]) if j < len(cs) else sp.Integer(0))
+
+    def vector_divergence(self, arg, lagrangian: bool):
+        cs = _coords(lagrangian)
+        return sum(sp.diff(arg[i, 0], cs[i]) for i in range(min(len(cs), arg.shape[0])))
+
+    def tensor_divergence(self, arg, lagrangian: bool):
+        cs = _coords(lagrangian)
+        return sp.Matrix([sum(sp.diff(arg[i, j], cs[j]) for j in range(min(len(cs), arg.shape[1]))) for i in range(arg.shape[0])])
+
+
+class AxisymmetricCoordinateSystem(BaseCoordinateSystem):
+    """(r, z) = (x, y), symmetry axis x = 0 (coordsys.py:386-560): vectors have three components (r, z, phi), the azimuthal one
+    zero unless the field was defined with it (swirl); dx = 2 pi r dr dz (:403-416); grad of a scalar = (d/dr, d/dz, 0) (:418);
+    grad of a vector = [[dr ur, dz ur, -uphi/r], [dr uz, dz uz, 0], [dr uphi, dz uphi, ur/r]] (:434-451 plus the swirl column);
+    div u = dr ur + ur/r + dz uz (:475-483).  The radius is the position field coordinate_x, so on a moving mesh all of these
+    terms get their position derivatives from the same symbolic differentiation as everything else."""
+
+    def get_id_name(self) -> str:
+        return "Axisymmetric"
+
+    def vector_dimension(self, nodal_dim: int) -> int:
+        if nodal_dim != 2:
+            raise RuntimeError("the axisymmetric coordinate system is built for 2d meshes")
+        return 3
+
+    @staticmethod
+    def _r(lagrangian: bool):
+        return _field("lagrangian_x" if lagrangian else "coordinate_x")
+
+    def integral_dx(self, lagrangian: bool):
+        return 2 * pi * self._r(lagrangian) * (DX_LAG if lagrangian else DX_EUL)
+
+    def scalar_gradient(self, arg, lagrangian: bool):
+        cs = _coords(lagrangian)
+        return sp.Matrix([sp.diff(arg, cs[0]), sp.diff(arg, cs[1]), sp.Integer(0)])
+
+    def vector_gradient(self, arg, lagrangian: bool):
+        if arg.shape[0] != 3:
+            raise RuntimeError("Cannot take a 2d axisymmetric vector gradient from a vector with dim!=3: " + str(arg))
+        x, y = _coords(lagrangian)
+        r = self._r(lagrangian)
+        return sp.Matrix([[sp.diff(arg[0, 0], x), sp.diff(arg[0, 0], y), -arg[2, 0] / r],
+                          [sp.diff(arg[1, 0], x), sp.diff(arg[1, 0], y), sp.Integer(0)],
+                          [sp.diff(arg[2, 0], x), sp.diff(arg[2, 0], y), arg[0, 0] / r]])
+
+    def vector_divergence(self, arg, lagrangian: bool):
+        x, y = _coords(lagrangian)
+        return sp.diff(arg[0, 0], x) + arg[0, 0] / self._r(lagrangian) + sp.diff(arg[1, 0], y)
+
+    def tensor_divergence(self, T, lagrangian: bool):
+        # coordsys.py:530-537 (first index contracted)
+        x, y = _coords(lagrangian)
+        r = self._r(lagrangian)
+        return sp.Matrix([sp.diff(T[0, 0], x) + (T[0, 0] - T[2, 2]) / r + sp.diff(T[1, 0], y),
+                          sp.diff(T[0, 1], x) + T[0, 1] / r + sp.diff(T[1, 1], y),
+                          sp.diff(T[0, 2], x) + (T[0, 2] - T[2, 0]) / r + sp.diff(T[1, 2], y)])
+
+
+cartesian = CartesianCoordinateSystem()
+axisymmetric = AxisymmetricCoordinateSystem()
+
+
+def _coordsys(coordsys=None) -> BaseCoordinateSystem:
+    return coordsys if coordsys is not None else _Context.current().coordinate_system
+
+
+def grad(arg: ExpressionOrNum, lagrangian: bool = False, coordsys: Optional[BaseCoordinateSystem] = None):
+    """Gradient: scalar -> column vector, vector -> matrix G[i,j]=d u_i / d x_j (generic.py:355), in the coordinate system
+    of the element code unless ``coordsys`` is given."""
+    cs = _coordsys(coordsys)
     if _is_matrix(arg):
         if arg.shape[1] != 1:
             raise RuntimeError("grad of a rank-2 tensor is not supported")
-        return sp.Matrix(arg.shape[0], len(cs), lambda i, j: sp.diff(arg[i, 0], cs[j]))
-    arg = sp.sympify(arg)
-    return sp.Matrix([sp.diff(arg, c) for c in cs])
+        return cs.vector_gradient(arg, lagrangian)
+    return cs.scalar_gradient(sp.sympify(arg), lagrangian)
 
 
-def div(arg, lagrangian: bool = False):
-    cs = _coords(lagrangian)
+def div(arg, lagrangian: bool = False, coordsys: Optional[BaseCoordinateSystem] = None):
+    cs = _coordsys(coordsys)
     if not _is_matrix(arg):
         raise RuntimeError("div needs a vector")
     if arg.shape[1] == 1:
-        return sum(sp.diff(arg[i, 0], cs[i]) for i in range(len(cs)))
-    return sp.Matrix([sum(sp.diff(arg[i, j], cs[j]) for j in range(len(cs))) for i in range(arg.shape[0])])
+        return cs.vector_divergence(arg, lagrangian)
+    return cs.tensor_divergence(arg, lagrangian)
 
 
 def dot(a, b):
@@ -175,14 +288,15 @@ def double_dot(a, b):
     return contract(a, b)
 
 
-def weak(a, b, *, lagrangian: bool = False):
-    """(a,b) = integral of contract(a,b) over the element, Eulerian dx unless lagrangian (generic.py:394)."""
-    return contract(a, b) * (DX_LAG if lagrangian else DX_EUL)
+def weak(a, b, *, lagrangian: bool = False, coordinate_system: Optional[BaseCoordinateSystem] = None):
+    """(a,b) = integral of contract(a,b) over the element, Eulerian dx unless lagrangian (generic.py:394); the measure is the
+    coordinate system's (2 pi r dx when axisymmetric)."""
+    return contract(a, b) * _coordsys(coordinate_system).integral_dx(lagrangian)
 
 
-def Weak(a, b):
+def Weak(a, b, *, coordinate_system: Optional[BaseCoordinateSystem] = None):
     """Lagrangian weak form (generic.py:429)."""
-    return weak(a, b, lagrangian=True)
+    return weak(a, b, lagrangian=True, coordinate_system=coordinate_system)
 
 
 def transpose(a):
@@ -199,7 +313,8 @@ def trace(a):
 
 def identity_matrix(dim: int = -1):
     if dim < 0:
-        dim = _Context.current().nodal_dim
+        code = _Context.current()
+        dim = code.coordinate_system.vector_dimension(code.nodal_dim)
     return sp.eye(dim)
 
 

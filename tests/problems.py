@@ -121,6 +121,25 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
         wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
         pinned = {"velocity_x": wall, "velocity_y": wall}
         unsteady = True
+    elif kind in ("ns_axi", "ns_axi_swirl"):
+        # configs 4/5, element class: axisymmetric Navier-Stokes (r = x, axis at the left boundary), Taylor-Hood; with swirl the
+        # azimuthal velocity is a third C2 component (ndof_el = 31, the class the Hopf/azimuthal tracking of config 5 assembles)
+        mesh = RectangularQuadMesh(N)
+        swirl = kind.endswith("swirl")
+        code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0, with_azimuthal_velocity=swirl),
+                                 name="nsswirl" if swirl else "nsaxi", coordinate_system="axisymmetric")
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("right", "bottom", "top")]))
+        pinned = {"velocity_x": np.unique(np.concatenate([wall, mesh.boundaries["left"]])), "velocity_y": wall}
+        if swirl:
+            pinned["velocity_phi"] = np.unique(np.concatenate([mesh.boundaries["right"], mesh.boundaries["left"]]))
+        unsteady = True
+    elif kind == "ale_axi":        # config 4 bulk part as BASELINE names it: axisymmetric NS-TH on a pseudo-elastic moving mesh
+        mesh = RectangularQuadMesh(N)
+        code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + PseudoElasticMesh(),
+                                 name="aleaxi", coordinate_system="axisymmetric")
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
+        pinned = {"velocity_x": wall, "velocity_y": wall}
+        unsteady = True
     else:
         raise KeyError(kind)
     pinned_pos = None

@@ -12,11 +12,13 @@ from problems import compare_matrix, csr_to_sorted, make_gpu, make_oracle, make_
 
 TOL = 1e-12
 
-CASES = [("poisson", 64), ("poisson", 5), ("ns", 12), ("ns_unsteady", 9), ("heat3d", 3), ("ale", 7), ("ns_param", 6)]
+CASES = [("poisson", 64), ("poisson", 5), ("ns", 12), ("ns_unsteady", 9), ("heat3d", 3), ("ale", 7), ("ns_param", 6),
+         ("ns_axi", 9), ("ns_axi_swirl", 7), ("ale_axi", 6)]      # axisymmetric classes of configs 4 and 5
 
 
 # (kind, N, distortion in element widths, unstructured = random element order + random node labels, no patch hint)
-VARIANTS = [("ns", 11, 0.12, False), ("ns_unsteady", 10, 0.1, True), ("heat3d", 3, 0.1, True), ("ale", 6, 0.08, True), ("poisson", 33, 0.15, True)]
+VARIANTS = [("ns", 11, 0.12, False), ("ns_unsteady", 10, 0.1, True), ("heat3d", 3, 0.1, True), ("ale", 6, 0.08, True), ("poisson", 33, 0.15, True),
+            ("ns_axi_swirl", 6, 0.1, True), ("ale_axi", 6, 0.08, True)]
 
 
 @pytest.mark.gpu
@@ -113,7 +115,7 @@ def test_size_independent_properties_large():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,N", [("ns_unsteady", 8), ("nlheat", 7), ("ns", 6)])
+@pytest.mark.parametrize("kind,N", [("ns_unsteady", 8), ("nlheat", 7), ("ns", 6), ("ns_axi_swirl", 5)])
 def test_hessian_vector_products_parity(kind, N):
     """HessianVectorProduct<i>: d(J.Y)/dU, d(M.Y)/dU (flags 1,2) and sum_jk Y_j H_ijk C_k (flag 0) against the oracle's
     ndof^3-buffer routine (which is itself checked against finite differences of the Jacobian in tests/test_oracle.py)."""

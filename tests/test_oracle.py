@@ -47,7 +47,7 @@ def test_analytic_jacobian_matches_finite_differences(kind, N):
     op.close()
 
 
-@pytest.mark.parametrize("kind,N", [("ns", 4), ("heat3d", 2), ("ale", 3)])
+@pytest.mark.parametrize("kind,N", [("ns", 4), ("heat3d", 2), ("ale", 3), ("ns_axi", 3), ("ns_axi_swirl", 3), ("ale_axi", 3)])
 def test_analytic_jacobian_on_distorted_unstructured_meshes(kind, N):
     """non-affine elements (curved edges, mapping Jacobian varying over the Gauss points), random element and node order"""
     pb = make_problem(kind, N, distortion=0.12, unstructured=True)
@@ -202,7 +202,7 @@ def test_golden_vectors(kind, N):
     op.close()
 
 
-@pytest.mark.parametrize("kind,N", [("ns_unsteady", 3), ("nlheat", 3)])
+@pytest.mark.parametrize("kind,N", [("ns_unsteady", 3), ("nlheat", 3), ("ns_axi_swirl", 3)])
 def test_hessian_routine_matches_finite_differences_and_flags(kind, N):
     """the reference's debug_hessian idea (src/elements.cpp:5129): H.Y against finite differences of J and M; flag 0/1/3/4
     are consistent contractions of the same ndof^3 tensor"""
