@@ -140,6 +140,35 @@ def test_hessian_vector_products_parity(kind, N):
 
 
 @pytest.mark.gpu
+def test_multi_assemble_request_matches_oracle():
+    """MultiAssembleRequest (bifurcation_tools.py:449): R, J, M, dR/dp, dJ/dp, d(J.Y)/dU, d(M.Y)/dU from one request, in request
+    order, against the oracle; the request needs 4 launches (one flag-2 launch, one parameter launch, one Hessian launch per vector)."""
+    from scipy.sparse import csr_matrix
+    from pyoomph_b200.multi_assembly import MultiAssembleRequest
+    pb = make_problem("ns_param", 6)
+    op = make_oracle(pb)
+    asm = make_gpu(pb)
+    n = pb["dofmap"].n_dof
+    rng = np.random.default_rng(3)
+    Y, Z = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    req = MultiAssembleRequest(asm).J().dJdU(Y).R().dRdp("mu").M().dMdU(Y).dJdp("mu").dJdU(Z)
+    J, JY, R, Rp, M, MY, Jp, JZ = req.assemble()
+    assert req.launches == 4
+    r_ref, mats = op.assemble(flag=2)
+    rp_ref, pmats = op.assemble(param=0, flag=1)
+    Jh, Mh = op.assemble_hessian(np.stack([Y, Z]), flag=2)
+    assert np.abs(R - r_ref).max() <= TOL * np.abs(r_ref).max() and np.abs(Rp - rp_ref).max() <= TOL * np.abs(rp_ref).max()
+    for got, ref in ((J, csr_to_sorted(n, *mats[0])), (M, csr_to_sorted(n, *mats[1])), (Jp, csr_to_sorted(n, *pmats[0]))):
+        err, missing = compare_matrix(got, ref)
+        assert missing == 0 and err <= TOL
+    for got, ref in ((JY, Jh[0]), (JZ, Jh[1]), (MY, Mh[0])):
+        assert abs(got - ref).max() <= TOL * max(abs(ref).max(), 1e-300) if ref.nnz else abs(got).max() == 0.0
+    with pytest.raises(NotImplementedError):
+        MultiAssembleRequest(asm).dJdU(Y, transposed=True)
+    op.close(); asm.close()
+
+
+@pytest.mark.gpu
 def test_full_size_config2_windows_against_oracle():
     """BASELINE config 2 at FULL size (NS Taylor-Hood 1024x1024, 1.05 M elements, all 148 blocks, all tile gates): rows of the
     nodes interior to sampled 4x4-element windows -- domain corners and edges (pinned dofs), patch / unit / tile boundaries

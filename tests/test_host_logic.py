@@ -127,3 +127,48 @@ def test_product_path_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, f
+
+
+def test_multi_assemble_request_groups_launches_and_keeps_request_order():
+    """host logic of MultiAssembleRequest (bifurcation_tools.py:449-531) against a recording stand-in for the assembler"""
+    import numpy as np
+    from pyoomph_b200.multi_assembly import MultiAssembleRequest
+
+    class Fake:
+        n_dof, nnz = 4, 4
+        indptr, indices = np.arange(5, dtype=np.int32), np.arange(4, dtype=np.int32)
+        residual_names, param_names = ["", "azi"], ["mu", "Re"]
+
+        def __init__(self):
+            self.calls = []
+
+        def assemble(self, flag=1, residual="", parameter=None):
+            self.calls.append(("rjm", residual, parameter, flag))
+            self._tag = 100 * self.residual_names.index(residual) + 10 * (0 if parameter is None else 1 + self.param_names.index(parameter))
+
+        def launch_count(self):
+            return 1
+
+        def fetch(self, want_jacobian=True, want_mass=False):
+            t = self._tag
+            return np.full(4, t + 0.0), np.full(4, t + 1.0) if want_jacobian else None, np.full(4, t + 2.0) if want_mass else None
+
+        def assemble_hessian(self, Y, flag=2, residual=""):
+            self.calls.append(("hvp", residual, Y.shape[0], flag))
+            return [np.full(4, 1000 + Y[v, 0]) for v in range(Y.shape[0])], [np.full(4, 2000 + Y[v, 0]) if flag >= 2 else None for v in range(Y.shape[0])]
+    f = Fake()
+    vs = [np.full(4, float(i)) for i in range(6)]
+    req = MultiAssembleRequest(f).M().R().dJdp("Re").J("azi").dRdp("Re").dMdU(vs[5])
+    for v in vs[:5]:
+        req.dJdU(v)
+    req.dJdU(vs[5])                    # same array object again: no new Hessian vector
+    out = req.assemble()
+    # one launch per (contribution, parameter) at the highest flag, Hessian vectors handed over in blocks of 4
+    assert f.calls[:3] == [("rjm", "", None, 2), ("rjm", "", "Re", 1), ("rjm", "azi", None, 1)]
+    assert sorted(c[2] for c in f.calls[3:]) == [2, 4] and req.launches == 5
+    assert out[0].data[0] == 2.0 and out[1][0] == 0.0 and out[2].data[0] == 21.0 and out[3].data[0] == 101.0 and out[4][0] == 20.0
+    assert out[5].data[0] == 2005.0 and [m.data[0] for m in out[6:]] == [1000.0, 1001.0, 1002.0, 1003.0, 1004.0, 1005.0]
+    with pytest.raises(RuntimeError):
+        MultiAssembleRequest(f).R("nope")
+    with pytest.raises(RuntimeError):
+        MultiAssembleRequest(f).dRdp("nu")
