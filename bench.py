@@ -347,6 +347,9 @@ def main():
                                 "sample": "%s at sample size %d (%d elements), oracle C plugin gcc -O3 -march=native, %d threads, 2 assemblies" % (args.workload, sample_n, ne, cores)}
         ne1, sec1 = cpu_run(args.workload, max(8, sample_n // 3), 1, 0, 1)
         line["cpu_baseline"]["value_1core"] = ne1 / sec1
+        # the port's element loop scales with threads, its vectors-of-pairs merge does not: perfect scaling of the 1-thread rate is the
+        # most any CPU run of this port could reach on this box
+        line["cpu_baseline"]["value_1core_times_cores"] = ne1 / sec1 * cores
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -18,12 +18,13 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 7
+#define PB2_ABI_VERSION 8
 #define PB2_MAX_PARAMS 16
 #define PB2_NTW 7           /* time-stepper storage, MultiTimeStepper (src/timestepper.hpp:37-45) */
 #define PB2_MAX_FIELDS 16
 #define PB2_MAX_ROUTINES 64
 #define PB2_MAX_HVEC 4      /* vectors per Hessian-vector launch */
+#define PB2_MAX_INTEGRALS 16 /* integral expressions per element class */
 
 /* what one launch writes (the `flag` of jitbridge.h:285 routines) */
 #define PB2_FLAG_RESIDUAL 0u
@@ -75,6 +76,7 @@ typedef struct pb2_kernel_args
   unsigned long long *debug;  /* NULL, or [64] cycle counters filled by kernels built with PB2_TIMING=1 (development aid) */
   const double *hvec;         /* [n_hvec][n_dof]   Hessian-vector inputs (or NULL) */
   int n_hvec, pad_;
+  double *integrals;          /* [n_elem_total][n_integrals]  per-element values of the integral expressions (kind 2 kernels) */
   pb2_time_info ti;
   double params[PB2_MAX_PARAMS]; /* global parameters (jitbridge.h:410) by value */
 } pb2_kernel_args;
@@ -107,6 +109,9 @@ typedef struct pb2_class_info
   double alg_bytes_per_elem[3];    /* algorithmic bytes per element for flag 0,1,2 */
   double flops_per_elem[3];        /* fp64 flops per element counted from the emitted code */
   double alg_bytes_per_hist_level; /* part of alg_bytes per history level beyond the current one (not read when steady) */
+  /* integral expressions = numintegral_expressions / integral_expressions_names of jitbridge.h:417-418 */
+  int n_integrals, pad_;
+  char integral_names[PB2_MAX_INTEGRALS][48];
 } pb2_class_info;
 
 /* launch configuration of one generated routine */
@@ -123,7 +128,9 @@ typedef struct pb2_kernel_cfg
 } pb2_kernel_cfg;
 
 /* routine = ResidualAndJacobian<residual_index> (param_index < 0) or dResidual<i>dParameter_<param_index>;
- * flag as in jitbridge.h:285.  kind 0: R/J/M routines, 1: Hessian-vector routines. */
+ * flag as in jitbridge.h:285.  kind 0: R/J/M routines, 1: Hessian-vector routines, 2: EvalIntegralExpression for ALL integral
+ * expressions at once (jitbridge.h:469; one launch per call, args->elem_begin / n_elem select the elements, args->integrals
+ * receives the per-element values; residual_index, param_index and flag are ignored). */
 typedef int (*pb2_query_fn)(int kind, int residual_index, int param_index, unsigned flag, pb2_kernel_cfg *out);
 typedef int (*pb2_launch_fn)(const pb2_kernel_cfg *cfg, const pb2_kernel_args *args, int grid, void *cuda_stream);
 

@@ -96,6 +96,12 @@ int pb2_problem_assemble_hessian(pb2_problem *p, int residual_index, unsigned fl
 int pb2_problem_fetch_hessian(pb2_problem *p, int v, double *jac_hessian_vals, double *mass_hessian_vals);
 /* flag 0 of HessianVectorProduct: product_v[i] = sum_jk Y_j H_ijk C_vk  = (d(J.Y)/dU) C_v  for n_vec vectors C_v (host in, host out) */
 int pb2_problem_hessian_vector_products(pb2_problem *p, int residual_index, const double *Y, const double *C, int n_vec, double *products);
+/* Integral expressions of the element class over ALL elements of the problem: replaces the element loop of
+ * Mesh::evaluate_integral_expression -> BulkElementBase::eval_integral_expression -> functable->EvalIntegralExpression
+ * (src/mesh.cpp:536-560, src/elements.cpp:4648-4657, jitbridge.h:469).  out[k] = value of expression k (order of
+ * pb2_class_info.integral_names), n_out = number of expressions.  One launch for the per-element values, one fixed-order
+ * reduction: the result is bit-reproducible. */
+int pb2_problem_eval_integrals(pb2_problem *p, double *out, int n_out);
 /* number of kernel launches issued by the last assemble, and cumulative */
 long long pb2_problem_launch_count(pb2_problem *p);
 

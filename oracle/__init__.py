@@ -90,6 +90,8 @@ class OracleProblem:
         L.oracle_create.restype = ctypes.c_void_p
         L.oracle_assemble.restype = ctypes.c_double
         L.oracle_nnz.restype = ctypes.c_int64
+        L.oracle_eval_integral.restype = ctypes.c_double
+        L.oracle_integral_name.restype = ctypes.c_char_p
         L.oracle_element.restype = ctypes.c_int
         self.dim = mesh.dim
         self.elem_nodes = np.ascontiguousarray(mesh.elem_nodes, dtype=np.int32)
@@ -107,6 +109,11 @@ class OracleProblem:
                                                  node_val.shape[2], self.T, pos.shape[0], _dp(pos), _dp(lagr),
                                                  _dp(node_val), _ip(self.node_eqn), _ip(self.pos_eqn), self.n_dof))
         self.maxdof = mesh.elem_nodes.shape[1] * (self.dim + node_val.shape[2])
+
+    def evaluate_integral_expressions(self):
+        """{name: sum over elements of EvalIntegralExpression(index)} (Mesh::evaluate_integral_expression, src/mesh.cpp:536)"""
+        n = self.lib.oracle_num_integrals(self.h)
+        return {self.lib.oracle_integral_name(self.h, i).decode(): float(self.lib.oracle_eval_integral(self.h, i)) for i in range(n)}
 
     def set_params(self, values):
         v = np.ascontiguousarray(values, dtype=np.float64)

@@ -848,6 +848,27 @@ int oracle_element_hessian(void *h, int e, int which, const double *Yg, const do
   return n;
 }
 
+/* Mesh::evaluate_integral_expression (src/mesh.cpp:536-548): sum over the elements, in mesh order, of
+ * BulkElementBase::eval_integral_expression (src/elements.cpp:4648-4657: prepare the shape buffer, call the generated routine) */
+int oracle_num_integrals(void *h) { return (int)((Oracle *)h)->ft->numintegral_expressions; }
+const char *oracle_integral_name(void *h, int i) { return ((Oracle *)h)->ft->integral_expressions_names[i]; }
+double oracle_eval_integral(void *h, int index)
+{
+  Oracle *o = (Oracle *)h;
+  if (!o->ft->EvalIntegralExpression || index < 0 || (unsigned)index >= o->ft->numintegral_expressions) return NAN;
+  ThreadState *ts = ts_create(o);
+  TS = ts;
+  double res = 0.0;
+  for (int e = 0; e < o->n_elem; e++)
+  {
+    bind_element(ts, e);
+    prepare_shape_buffer(ts);
+    res += o->ft->EvalIntegralExpression(&ts->ei, &ts->si, (unsigned)index);
+  }
+  free(ts);
+  return res;
+}
+
 int64_t oracle_nnz(void *h, int m) { return ((Oracle *)h)->nnz[m]; }
 void oracle_get_csr(void *h, int m, int *row_start, int *col_index, double *value)
 {

@@ -271,6 +271,94 @@ class CEmitter:
         w("")
         return "\n".join(o)
 
+    # ---- integral expressions ---------------------------------------------------------------------
+    def integral_routine(self) -> str:
+        """EvalIntegralExpression in the format of write_code_integral_or_local_expressions (src/codegen.cpp:4125-4364,
+        :4366-4368): time-derivative precalculation, Gauss loop with the shape callback, interpolation, then
+        ``switch(index)`` over the expressions; the integrands carry their own measure."""
+        code = self.code
+        exprs = [code.atomize(e) for e in code.integral_expressions.values()]
+        used = set()
+        for e in exprs:
+            used |= {s_ for s_ in e.free_symbols if s_ in code._atom_syms}
+        atoms = sorted([code._atom_syms[s_] for s_ in used], key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
+        names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi"}
+        for a in atoms:
+            names[code.atom_symbol(a)] = "this_" + a.cname
+        for k, p in enumerate(code.global_params):
+            names[code._param_syms[p]] = "(*(my_func_table->global_parameters[%d]))" % k
+        pr = _CPrinter(names)
+        o: List[str] = []
+        w = o.append
+        w("static double EvalIntegralExpression(const JITElementInfo_t * eleminfo, const JITShapeInfo_t * shapeinfo, unsigned index)")
+        w("{")
+        w("  const unsigned flag=0;")
+        w("  const double * t=shapeinfo->t;")
+        w("  const double * dt=shapeinfo->dt;")
+        w("  (void)t; (void)dt; (void)flag;")
+        for f in sorted({a.field for a in atoms}):
+            w("  const unsigned %s = %d;" % (_nodal_index_name(f), code.fields[f].index))
+        w("  //START: Precalculate time derivatives of the necessary data")
+        dt_atoms: Dict[str, AtomInfo] = {}
+        for a in atoms:
+            if a.dt_order:
+                dt_atoms.setdefault(self._dt_values_name(a), a)
+        by_space: Dict[str, List[Tuple[str, AtomInfo]]] = {}
+        for nm, a in dt_atoms.items():
+            by_space.setdefault(code.fields[a.field].space, []).append((nm, a))
+        for space, lst in by_space.items():
+            rng = self._nnode_str(lst[0][1].field)
+            for nm, a in lst:
+                w("  double %s[%d];" % (nm, code.etype.nnode))
+            w("  for (unsigned int l_shape=0;l_shape<%s;l_shape++)" % rng)
+            w("  {")
+            for nm, a in lst:
+                w("    %s[l_shape]=0.0;" % nm)
+            w("    for (unsigned tindex=0;tindex<shapeinfo->timestepper_ntstorage;tindex++)")
+            w("    {")
+            for nm, a in lst:
+                w("      %s[l_shape] += %s[tindex]*eleminfo->%s[l_shape][%s][tindex];" % (
+                    nm, self._weights_name(a), self._data_array(a.field), _nodal_index_name(a.field)))
+            w("    }")
+            w("  }")
+        w("  //END: Precalculate time derivatives of the necessary data")
+        w("")
+        w("  double res=0.0;")
+        w("  for(unsigned ipt=0;ipt<shapeinfo->n_int_pt;ipt++)")
+        w("  {")
+        w("    my_func_table->fill_shape_buffer_for_point(ipt, &(my_func_table->shapes_required_IntegralExprs), 0);")
+        w("    const double dx = shapeinfo->int_pt_weight;")
+        w("    const double dX = shapeinfo->int_pt_weight_Lagrangian;")
+        w("    (void)dx; (void)dX;")
+        w("    //START: Interpolate all required fields")
+        for space in ("Pos", "C2", "C1"):
+            sat = [a for a in atoms if code.fields[a.field].space == space]
+            if not sat:
+                continue
+            rng = self._nnode_str(sat[0].field)
+            for a in sat:
+                w("    double this_%s=0.0;" % a.cname)
+            w("    for (unsigned int l_shape=0;l_shape<%s;l_shape++)" % rng)
+            w("    {")
+            for a in sat:
+                if a.dt_order:
+                    nd = "%s[l_shape]" % self._dt_values_name(a)
+                else:
+                    nd = "eleminfo->%s[l_shape][%s][%d]" % (self._data_array(a.field), _nodal_index_name(a.field), a.past)
+                w("      this_%s+= %s * %s;" % (a.cname, nd, self._shape_str(a.field, a.deriv, "l_shape")))
+            w("    }")
+        w("    //END: Interpolate all required fields")
+        w("    switch (index)")
+        w("    {")
+        for i, (n, e) in enumerate(zip(code.integral_expressions.keys(), exprs)):
+            w("      case %d: res+= %s; break; // %s" % (i, pr.doprint(e), n))
+        w("    }")
+        w("  }")
+        w("  return res;")
+        w("}")
+        w("")
+        return "\n".join(o)
+
     def _gateaux(self, var_part: sp.Expr, F: str, G: str, names: Dict[sp.Symbol, str], lname: str = "l_shape", mass: bool = True) -> sp.Expr:
         """d/d U_G^{lname} of the complete residual expression of test field F."""
         code = self.code
@@ -482,10 +570,16 @@ class CEmitter:
             w("#endif")
             for i, rn in enumerate(resnames):
                 w(self.hessian_routine("HessianVectorProduct%d" % i, rn, i))
+        nint = len(code.integral_expressions)
+        if nint:
+            w(self.integral_routine())
         nC2 = len([f for f in code.nodal_fields() if f.space == "C2"])
         nC1 = len([f for f in code.nodal_fields() if f.space == "C1"])
         w("static void clean_up(JITFuncSpec_Table_FiniteElement_t *functable)")
         w("{")
+        if nint:
+            w(" for (unsigned i=0;i<functable->numintegral_expressions;i++) { pyoomph_tested_free(functable->integral_expressions_names[i]); }")
+            w(" pyoomph_tested_free(functable->integral_expressions_names);")
         w(" free(functable->ResidualAndJacobian); free(functable->ResidualAndJacobianSteady); free(functable->shapes_required_ResJac);")
         w(" if (functable->hessian_generated) { free(functable->HessianVectorProduct); free(functable->shapes_required_Hessian); }")
         w(" free(functable->global_parameters);")
@@ -532,6 +626,12 @@ class CEmitter:
             w(" functable->HessianVectorProduct=(JITFuncSpec_HessianVectorProduct_FiniteElement *)calloc(%d,sizeof(JITFuncSpec_HessianVectorProduct_FiniteElement));" % max(1, len(resnames)))
             for i, rn in enumerate(resnames):
                 w(" functable->HessianVectorProduct[%d]=&HessianVectorProduct%d;" % (i, i))
+        if nint:      # src/codegen.cpp:6991-7003
+            w(" functable->numintegral_expressions=%d;" % nint)
+            w(" functable->integral_expressions_names=(char **)malloc(sizeof(char*)*functable->numintegral_expressions);")
+            for i, n in enumerate(code.integral_expressions.keys()):
+                w(' SET_INTERNAL_FIELD_NAME(functable->integral_expressions_names,%d,"%s");' % (i, n))
+            w(" functable->EvalIntegralExpression=&EvalIntegralExpression;")
         w(" functable->clean_up=&clean_up;")
         w(" my_func_table=functable;")
         w("}")

@@ -74,6 +74,7 @@ typedef struct JITShapeInfo
 
 typedef void (*JITFuncSpec_ResidualAndJacobian_FiniteElement)(const JITElementInfo_t *, const JITShapeInfo_t *, double *, double *, double *, unsigned);
 typedef void (*JITFuncSpec_HessianVectorProduct_FiniteElement)(const JITElementInfo_t *, const JITShapeInfo_t *, const double *, double *, double *, unsigned, unsigned);
+typedef double (*JITFuncSpec_EvalIntegralExpr_FiniteElement)(const JITElementInfo_t *, const JITShapeInfo_t *, unsigned); /* jitbridge.h:291 */
 
 typedef struct JITFuncSpec_RequiredShapes_FiniteElement
 {
@@ -104,6 +105,10 @@ typedef struct JITFuncSpec_Table_FiniteElement
   JITFuncSpec_ResidualAndJacobian_FiniteElement *ResidualAndJacobianSteady;
   JITFuncSpec_HessianVectorProduct_FiniteElement *HessianVectorProduct;
   bool hessian_generated;
+  unsigned numintegral_expressions;                                /* jitbridge.h:417-418 */
+  char **integral_expressions_names;
+  JITFuncSpec_EvalIntegralExpr_FiniteElement EvalIntegralExpression; /* jitbridge.h:469-470 */
+  JITFuncSpec_RequiredShapes_FiniteElement_t shapes_required_IntegralExprs;
   char *domain_name;
   void (*check_compiler_size)(unsigned long long, unsigned long long, char *);
   void (*fill_shape_buffer_for_point)(unsigned, JITFuncSpec_RequiredShapes_FiniteElement_t *, int);

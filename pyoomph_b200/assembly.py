@@ -50,6 +50,7 @@ class ClassInfo(ctypes.Structure):
         ("hessian_generated", ctypes.c_int),
         ("alg_bytes_per_elem", ctypes.c_double * 3), ("flops_per_elem", ctypes.c_double * 3),
         ("alg_bytes_per_hist_level", ctypes.c_double),
+        ("n_integrals", ctypes.c_int), ("pad_", ctypes.c_int), ("integral_names", (ctypes.c_char * 48) * 16),
     ]
 
 
@@ -78,7 +79,7 @@ def load_library() -> ctypes.CDLL:
                "pb2_problem_set_time", "pb2_problem_set_parameters", "pb2_problem_assemble", "pb2_problem_device_outputs",
                "pb2_problem_fetch", "pb2_problem_assemble_host", "pb2_problem_num_colours", "pb2_version",
                "pb2_problem_assemble_hessian", "pb2_problem_fetch_hessian", "pb2_problem_hessian_vector_products",
-               "pb2_problem_pack_rows", "pb2_problem_unpack_add"):
+               "pb2_problem_pack_rows", "pb2_problem_unpack_add", "pb2_problem_eval_integrals"):
         getattr(L, fn).restype = ctypes.c_int
     _LIB = L
     return L
@@ -188,6 +189,7 @@ class B200Assembly(CustomAssemblyBase):
         self.n_elem = self._elem_nodes.shape[0]
         self.param_names = [self.info.param_names[i].value.decode() for i in range(self.info.n_params)]
         self.residual_names = [self.info.residual_names[i].value.decode() for i in range(self.info.n_residuals)]
+        self.integral_names = [self.info.integral_names[i].value.decode() for i in range(self.info.n_integrals)]
         self._params = np.zeros(max(1, self.info.n_params))
         self.set_nodal_positions(0, mesh.node_pos)
         for t in range(1, self.info.n_hist_pos):
@@ -296,6 +298,19 @@ class B200Assembly(CustomAssemblyBase):
         ri = self.residual_names.index(residual)
         _check(self.lib.pb2_problem_hessian_vector_products(self.prob, ri, self._dp(Y), self._dp(C), C.shape[0], self._dp(out)))
         return out
+
+    # ---- integral expressions (Mesh.evaluate_observable -> BulkElementBase::eval_integral_expression, src/mesh.cpp:545) ---------
+    def evaluate_integral_expressions(self) -> Dict[str, float]:
+        """all integral expressions of the element class over all elements: one launch for the per-element values and one
+        fixed-order reduction (bit-reproducible), {name: value}"""
+        if not self.integral_names:
+            raise RuntimeError("this element class defines no integral expressions")
+        out = np.empty(len(self.integral_names))
+        _check(self.lib.pb2_problem_eval_integrals(self.prob, self._dp(out), len(self.integral_names)))
+        return {n: float(v) for n, v in zip(self.integral_names, out)}
+
+    def evaluate_observable(self, name: str) -> float:
+        return self.evaluate_integral_expressions()[name]
 
     def device_outputs(self):
         r, j, m = c_double_p(), c_double_p(), c_double_p()

@@ -126,6 +126,7 @@ class FiniteElementCode:
         self.global_params: List[str] = []
         self._param_syms: Dict[str, sp.Symbol] = {}
         self.residuals: Dict[str, sp.Expr] = {}
+        self.integral_expressions: Dict[str, sp.Expr] = {}     # FiniteElementCode::integral_expressions (src/codegen.hpp:677)
         self._atom_syms: Dict[sp.Symbol, AtomInfo] = {}
         self._atom_by_info: Dict[AtomInfo, sp.Symbol] = {}
         self._test_syms: Dict[sp.Symbol, TestSlot] = {}
@@ -144,6 +145,7 @@ class FiniteElementCode:
             self._defining_fields = False
             self._index_fields()
             equations.define_residuals()
+            equations.define_additional_functions()
         finally:
             ex._Context.stack.pop()
         self._forms: Dict[str, ResidualForm] = {}
@@ -198,6 +200,45 @@ class FiniteElementCode:
 
     def residual_names(self) -> List[str]:
         return list(self.residuals.keys())
+
+    # -- integral expressions (FiniteElementCode::_register_integral_function, src/codegen.cpp:6186-6212) -------------
+    def add_integral_function(self, name: str, expr):
+        """integrand INCLUDING its measure (the caller multiplies by dx, pyoomph/equations/generic.py:699); a vector integrand
+        registers one expression per component, name_x, name_y, ... (src/codegen.cpp:6199-6208)"""
+        if isinstance(expr, sp.MatrixBase):
+            for i in range(expr.shape[0]):
+                if expr[i, 0] != 0 or i < self.nodal_dim:
+                    self.integral_expressions[name + "_" + (ex.DIRS[i] if i < self.nodal_dim else "phi")] = sp.sympify(expr[i, 0])
+            return
+        self.integral_expressions[name] = sp.sympify(expr)
+
+    def integral_expression_names(self) -> List[str]:
+        return list(self.integral_expressions.keys())
+
+    def integral_form(self) -> ResidualForm:
+        """The integral expressions as a coefficient form without test functions: slot i carries integrand i (its "R"), so the
+        emitters reuse their gather / geometry / interpolation code (write_code_integral_or_local_expressions,
+        src/codegen.cpp:4125-4364 does the same with the residual machinery)."""
+        if "|integrals" in self._forms:
+            return self._forms["|integrals"]
+        slots, R = [], []
+        for i, (n, e) in enumerate(self.integral_expressions.items()):
+            E = self.atomize(e)
+            if any(s in self._test_syms for s in E.free_symbols):
+                raise RuntimeError("Found test function in a custom integral/local expression")     # src/codegen.cpp:4145
+            slots.append(TestSlot("__integral_%d" % i, "d0"))
+            R.append(E)
+        used = set()
+        for e in R:
+            used |= {s for s in e.free_symbols if s in self._atom_syms}
+        atoms = sorted((self._atom_syms[s] for s in used), key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
+        allsyms = set().union(*[e.free_symbols for e in R]) if R else set()
+        form = ResidualForm("|integrals", slots, R, {}, {}, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=ex.DX_LAG in allsyms)
+        self._forms["|integrals"] = form
+        return form
+
+    def _all_forms(self) -> List[ResidualForm]:
+        return [self.derive(n) for n in self.residual_names()] + ([self.integral_form()] if self.integral_expressions else [])
 
     def space_nodes(self, space: str) -> Tuple[int, ...]:
         """Element-local node numbers of a space (src/elements.cpp:2870-2879)."""
@@ -459,16 +500,16 @@ class FiniteElementCode:
 
     def max_dt_order(self) -> int:
         m = 0
-        for n in self.residual_names():
-            for a in self.derive(n).atoms:
+        for form in self._all_forms():
+            for a in form.atoms:
                 m = max(m, a.dt_order)
         return m
 
     def history_levels(self) -> int:
         """Number of nodal history values the routines read (T in SURVEY 8d)."""
         t = 1
-        for n in self.residual_names():
-            for a in self.derive(n).atoms:
+        for form in self._all_forms():
+            for a in form.atoms:
                 if a.dt_order == 1:
                     t = max(t, 2 if a.scheme == "BDF1" else 3)
                 if a.dt_order == 2:
@@ -497,6 +538,18 @@ class Equations:
 
     def define_residuals(self):
         pass
+
+    def define_additional_functions(self):
+        """integral / local expressions (pyoomph/generic/codegen.py Equations.define_additional_functions)"""
+        pass
+
+    def add_integral_function(self, name: str, expr):
+        """pyoomph/generic/codegen.py:1251: the integrand carries its own measure (multiply by ``self.get_dx()``)"""
+        self._code.add_integral_function(name, expr)
+
+    def get_dx(self, lagrangian: bool = False, coordsys=None):
+        """measure of the element's (or the given) coordinate system: dx, or 2 pi r dx when axisymmetric"""
+        return (coordsys or self._code.coordinate_system).integral_dx(lagrangian)
 
     def define_scalar_field(self, name: str, space: str, **_scaling):
         self._code.define_scalar_field(name, space)
@@ -534,3 +587,7 @@ class CombinedEquations(Equations):
     def define_residuals(self):
         for p in self.parts:
             p.define_residuals()
+
+    def define_additional_functions(self):
+        for p in self.parts:
+            p.define_additional_functions()

@@ -77,6 +77,7 @@ struct pb2_problem
   double *d_hvec = nullptr, *d_hess = nullptr, *d_hessM = nullptr;
   int hess_nvec = 0;
   int *d_row_start = nullptr, *d_col_index = nullptr;
+  double *d_integrals = nullptr;   // [n_elem][n_integrals] per-element integral expressions, then [n_integrals] sums
   int *d_untouched = nullptr;      // CSR positions no local element writes (pattern entries owned for other ranks' contributions)
   long long n_untouched = 0;
 };
@@ -609,6 +610,7 @@ extern "C" void pb2_problem_free(pb2_problem *p)
   cudaFree(p->d_elem_eqn);
   cudaFree(p->d_elem_rowstart);
   cudaFree(p->d_elem_off);
+  cudaFree(p->d_integrals);
   cudaFree(p->d_elem_res);
   cudaFree(p->d_dof_target);
   cudaFree(p->d_node_pos);
@@ -728,12 +730,8 @@ extern "C" int pb2_problem_set_parameters(pb2_problem *p, const double *values, 
   return 0;
 }
 
-static int run_routine(pb2_problem *p, int kind, int residual_index, int param_index, unsigned flag, double *out_jac, double *out_mass, const double *hvec, void *cuda_stream)
+static void fill_common_args(pb2_problem *p, pb2_kernel_args &a)
 {
-  const pb2_class_info &ci = p->cls->table.info;
-  if (residual_index < 0 || residual_index >= ci.n_residuals) return fail("residual index out of range");
-  if (param_index >= ci.n_params) return fail("parameter index out of range");
-  pb2_kernel_args a;
   memset(&a, 0, sizeof(a));
   a.elem_nodes = p->d_elem_nodes;
   a.elem_eqn = p->d_elem_eqn;
@@ -748,11 +746,20 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
   a.n_hist_val = p->T_val;
   a.n_hist_pos = p->T_pos;
   a.residual = p->d_residual;
+  a.ti = p->ti;
+  memcpy(a.params, p->params, sizeof(a.params));
+}
+
+static int run_routine(pb2_problem *p, int kind, int residual_index, int param_index, unsigned flag, double *out_jac, double *out_mass, const double *hvec, void *cuda_stream)
+{
+  const pb2_class_info &ci = p->cls->table.info;
+  if (residual_index < 0 || residual_index >= ci.n_residuals) return fail("residual index out of range");
+  if (param_index >= ci.n_params) return fail("parameter index out of range");
+  pb2_kernel_args a;
+  fill_common_args(p, a);
   a.jac_vals = out_jac;
   a.mass_vals = out_mass;
   a.hvec = hvec;
-  a.ti = p->ti;
-  memcpy(a.params, p->params, sizeof(a.params));
   p->launches_last = 0;
   if (p->n_untouched > 0 && flag >= 1u)
   {
@@ -998,6 +1005,56 @@ extern "C" int pb2_problem_hessian_vector_products(pb2_problem *p, int residual_
   }
   cudaFree(d_x);
   cudaFree(d_y);
+  return 0;
+}
+
+// ---- integral expressions: per-element values by the generated kernel, then one fixed-order reduction per expression
+static __global__ void __launch_bounds__(1024) pb2_reduce_integrals(const double *__restrict__ per_elem, long long n_elem, int n_int, double *__restrict__ out)
+{
+  __shared__ double s[1024];
+  const int k = blockIdx.x;
+  double acc = 0.0;
+  for (long long e = threadIdx.x; e < n_elem; e += 1024) acc += per_elem[e * n_int + k]; // same elements, same order, every time
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int w = 512; w > 0; w >>= 1)
+  {
+    if ((int)threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[k] = s[0];
+}
+
+extern "C" int pb2_problem_eval_integrals(pb2_problem *p, double *out, int n_out)
+{
+  CUDA_OK(cudaSetDevice(p->device));
+  const pb2_class_info &ci = p->cls->table.info;
+  if (ci.n_integrals < 1) return fail("this element class defines no integral expressions");
+  if (n_out != ci.n_integrals) return fail("n_out must equal the number of integral expressions of the class");
+  pb2_kernel_cfg cfg;
+  int rc = p->cls->table.query(2, 0, -1, 0u, &cfg);
+  if (rc != 0) return fail("plugin has no integral-expression kernel (rc " + std::to_string(rc) + ")");
+  if (!p->d_integrals)
+    CUDA_OK(cudaMalloc((void **)&p->d_integrals, ((size_t)std::max<long long>(1, p->n_elem) + 1) * ci.n_integrals * sizeof(double)));
+  pb2_kernel_args a;
+  fill_common_args(p, a);
+  a.elem_begin = 0;
+  a.n_elem = (int)p->n_elem;
+  a.integrals = p->d_integrals;
+  p->launches_last = 0;
+  double *d_sum = p->d_integrals + (size_t)std::max<long long>(1, p->n_elem) * ci.n_integrals;
+  if (p->n_elem > 0)
+  {
+    const long long nbatch = (p->n_elem + cfg.elems_per_batch - 1) / cfg.elems_per_batch;
+    rc = p->cls->table.launch(&cfg, &a, (int)std::min<long long>(nbatch, (long long)p->n_sms * cfg.blocks_per_sm), nullptr);
+    if (rc != 0) return fail("integral kernel launch failed (plugin rc " + std::to_string(rc) + (rc >= 100 ? std::string(": ") + cudaGetErrorString((cudaError_t)(rc - 100)) : "") + ")");
+    p->launches_last++;
+  }
+  pb2_reduce_integrals<<<ci.n_integrals, 1024>>>(p->d_integrals, p->n_elem, ci.n_integrals, d_sum);
+  CUDA_OK(cudaGetLastError());
+  p->launches_last++;
+  p->launches_total += p->launches_last;
+  CUDA_OK(cudaMemcpy(out, d_sum, (size_t)ci.n_integrals * sizeof(double), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -363,6 +363,60 @@ class CudaEmitter:
         w("    const int nel = min(%d, a.n_elem - e0);" % self.EPB)
         w("    __syncthreads();")
         # ---------------- phase 0
+        self._emit_gather_sync(o, plan, ELS)
+        w("    // scatter maps of the batch: issued together with the gather, consumed in phase 3 (no dependent global load there)")
+        w("    {")
+        w("      const long long eg0 = (long long)(a.elem_begin + e0);")
+        w("      for (int i = tid; i < nel * %d; i += %d) { s_rowstart[i] = __ldg(a.elem_rowstart + eg0 * %d + i); s_resmap[i] = __ldg(a.elem_res + eg0 * %d + i); }" % (self.ndof, self.NT, self.ndof, self.ndof))
+        if what >= 1:
+            nd2 = self.ndof * self.ndof
+            w("      const int mbytes = nel * %d * (a.map_bits >> 3);" % nd2)
+            w("      const unsigned char* __restrict__ gmap = (const unsigned char*)a.elem_off + eg0 * %d * (a.map_bits >> 3);" % nd2)
+            if nd2 % 4 == 0:
+                w("      for (int i = tid; i < (mbytes >> 2); i += %d) ((unsigned*)s_map)[i] = __ldg((const unsigned*)gmap + i);" % self.NT)
+            else:
+                w("      for (int i = tid; i < mbytes; i += %d) s_map[i] = __ldg(gmap + i);" % self.NT)
+        w("    }")
+        w("    __syncthreads();")
+        # ---------------- phase 1
+        w("    // ---- phase 1: one thread per (element, Gauss point): geometry + interpolation + pointwise coefficients")
+        w("    for (int i = tid; i < nel * %d; i += %d)" % (NIPT, self.NT))
+        w("    {")
+        w("      const int el = i / %d, ipt = i - el * %d;" % (NIPT, NIPT))
+        w("      double* E = s_el + el * %d;" % ELS)
+        w("      double* P = E + %d + ipt * %d;" % (EL0, PB))
+        self._emit_phase1_body(o, rp, plan, what)
+        w("    }")
+        w("    __syncthreads();")
+        # ---------------- phase 2 + 3, once per output matrix ("J": residual + Jacobian, "M": mass matrix)
+        passes = [("J", form.J, plan["J_off"], "a.jac_vals", True)] if what >= 1 else [("R", {}, {}, None, True)]
+        if what >= 2:
+            passes.append(("M", form.M, plan["M_off"], "a.mass_vals", False))
+        nacc = max(self._group_nacc(form, g, coef) for g in self.groups for (_, coef, _, _, _) in passes)
+        w("    double acc[%d];" % max(1, nacc))
+        for pi_, (pname, coef, coff, target, with_res) in enumerate(passes):
+            w("    // ---- phase 2 (%s): register-tiled contraction over (l_test, l_shape)" % pname)
+            for g in self.groups:
+                self._emit_group_compute(o, rp, plan, g, pname, coef, coff, with_res)
+            if plan["stage_alias"]:
+                w("    __syncthreads();   // point data is dead from here on: the staging area aliases it")
+            w("    // ---- phase 3a (%s): element matrices -> shared memory, dense [row][col]" % pname)
+            for g in self.groups:
+                self._emit_group_stage(o, rp, plan, g, pname, coef, with_res, target is not None)
+            w("    __syncthreads();")
+            w("    // ---- phase 3b (%s): cooperative coloured scatter, consecutive threads = consecutive (row,col) entries" % pname)
+            self._emit_scatter(o, plan, target, with_res)
+            if pi_ + 1 < len(passes):
+                w("    __syncthreads();")
+        w("  }")
+        w("}")
+        w("")
+        return kname
+
+    def _emit_gather_sync(self, o: List[str], plan, ELS: int):
+        """phase 0 of the phase-synchronous kernels: element nodes -> s_el (expects e0, nel, tid, s_el)"""
+        code, dim, NN, NN1 = self.code, self.dim, self.NN, self.NN1
+        w = o.append
         w("    // ---- phase 0: gather element data (fill_element_info's pointer tables become one staged copy)")
         w("    for (int i = tid; i < nel * %d; i += %d)" % (NN, self.NT))
         w("    {")
@@ -409,50 +463,63 @@ class CudaEmitter:
                     w("      { double s = 0.0; for (int t = 0; t < a.ti.ntstorage; ++t) s += %s[t] * %s[((long long)t * a.n_node + node) * %d + %d]; E[%d + l] = s; }" % (
                         wn, base, stride, comp, soff))
             w("    }")
-        w("    // scatter maps of the batch: issued together with the gather, consumed in phase 3 (no dependent global load there)")
-        w("    {")
-        w("      const long long eg0 = (long long)(a.elem_begin + e0);")
-        w("      for (int i = tid; i < nel * %d; i += %d) { s_rowstart[i] = __ldg(a.elem_rowstart + eg0 * %d + i); s_resmap[i] = __ldg(a.elem_res + eg0 * %d + i); }" % (self.ndof, self.NT, self.ndof, self.ndof))
-        if what >= 1:
-            nd2 = self.ndof * self.ndof
-            w("      const int mbytes = nel * %d * (a.map_bits >> 3);" % nd2)
-            w("      const unsigned char* __restrict__ gmap = (const unsigned char*)a.elem_off + eg0 * %d * (a.map_bits >> 3);" % nd2)
-            if nd2 % 4 == 0:
-                w("      for (int i = tid; i < (mbytes >> 2); i += %d) ((unsigned*)s_map)[i] = __ldg((const unsigned*)gmap + i);" % self.NT)
-            else:
-                w("      for (int i = tid; i < mbytes; i += %d) s_map[i] = __ldg(gmap + i);" % self.NT)
-        w("    }")
+
+    def _emit_integral_kernel(self, o: List[str]) -> str:
+        """EvalIntegralExpression for all integral expressions at once (src/codegen.cpp:4125-4364): gather, one thread per
+        (element, Gauss point) for geometry + interpolation + integrands (they carry their measure), then one thread per
+        (element, expression) sums the Gauss points in order and writes the per-element value."""
+        form = self.code.integral_form()
+        rp = RoutinePlan("integrals", form, 0, -1)
+        plan = self._plan_smem(form, 0)
+        ELS, EL0, PB = plan["ELS"], plan["EL0"], plan["PB"]
+        NI, NIPT, NN, NN1, dim = len(form.slots), self.NIPT, self.NN, self.NN1, self.dim
+        tab_n = self._tables_smem_size()
+        NT = 256
+        EPB = max(2, min(NT // NIPT if NIPT <= NT else 2, (self.smem_budget - tab_n * 8) // (ELS * 8)))
+        kname = "pb2_%s_integrals" % self.name
+        self._kernel_smem[kname] = (tab_n + EPB * ELS) * 8
+        self._kernel_cfg[kname] = (EPB, NT, self._kernel_smem[kname])
+        w = o.append
+        w("// integral expressions: %s" % ", ".join(self.code.integral_expression_names()))
+        w("extern \"C\" __global__ void __launch_bounds__(%d) %s(const pb2_kernel_args a)" % (NT, kname))
+        w("{")
+        w("  extern __shared__ double smem[];")
+        w("  double* const s_psi2 = smem;")
+        w("  double* const s_dpsi2 = s_psi2 + %d;" % (NIPT * NN))
+        w("  double* const s_psi1 = s_dpsi2 + %d;" % (NIPT * NN * dim))
+        w("  double* const s_dpsi1 = s_psi1 + %d;" % (NIPT * NN1))
+        w("  double* const s_el = smem + %d;" % tab_n)
+        w("  const int tid = threadIdx.x;")
+        w("  for (int i = tid; i < %d; i += %d) smem[i] = g_tables[i];" % (tab_n, NT))
+        w("  const int nbatch = (a.n_elem + %d - 1) / %d;" % (EPB, EPB))
+        w("  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x)")
+        w("  {")
+        w("    const int e0 = batch * %d;" % EPB)
+        w("    const int nel = min(%d, a.n_elem - e0);" % EPB)
         w("    __syncthreads();")
-        # ---------------- phase 1
-        w("    // ---- phase 1: one thread per (element, Gauss point): geometry + interpolation + pointwise coefficients")
-        w("    for (int i = tid; i < nel * %d; i += %d)" % (NIPT, self.NT))
+        saved = self.NT
+        self.NT = NT
+        try:
+            self._emit_gather_sync(o, plan, ELS)
+        finally:
+            self.NT = saved
+        w("    __syncthreads();")
+        w("    for (int i = tid; i < nel * %d; i += %d)" % (NIPT, NT))
         w("    {")
         w("      const int el = i / %d, ipt = i - el * %d;" % (NIPT, NIPT))
         w("      double* E = s_el + el * %d;" % ELS)
         w("      double* P = E + %d + ipt * %d;" % (EL0, PB))
-        self._emit_phase1_body(o, rp, plan, what)
+        self._emit_phase1_body(o, rp, plan, 0)
         w("    }")
         w("    __syncthreads();")
-        # ---------------- phase 2 + 3, once per output matrix ("J": residual + Jacobian, "M": mass matrix)
-        passes = [("J", form.J, plan["J_off"], "a.jac_vals", True)] if what >= 1 else [("R", {}, {}, None, True)]
-        if what >= 2:
-            passes.append(("M", form.M, plan["M_off"], "a.mass_vals", False))
-        nacc = max(self._group_nacc(form, g, coef) for g in self.groups for (_, coef, _, _, _) in passes)
-        w("    double acc[%d];" % max(1, nacc))
-        for pi_, (pname, coef, coff, target, with_res) in enumerate(passes):
-            w("    // ---- phase 2 (%s): register-tiled contraction over (l_test, l_shape)" % pname)
-            for g in self.groups:
-                self._emit_group_compute(o, rp, plan, g, pname, coef, coff, with_res)
-            if plan["stage_alias"]:
-                w("    __syncthreads();   // point data is dead from here on: the staging area aliases it")
-            w("    // ---- phase 3a (%s): element matrices -> shared memory, dense [row][col]" % pname)
-            for g in self.groups:
-                self._emit_group_stage(o, rp, plan, g, pname, coef, with_res, target is not None)
-            w("    __syncthreads();")
-            w("    // ---- phase 3b (%s): cooperative coloured scatter, consecutive threads = consecutive (row,col) entries" % pname)
-            self._emit_scatter(o, plan, target, with_res)
-            if pi_ + 1 < len(passes):
-                w("    __syncthreads();")
+        w("    for (int i = tid; i < nel * %d; i += %d)" % (NI, NT))
+        w("    {")
+        w("      const int el = i / %d, k = i - el * %d;" % (NI, NI))
+        w("      const double* P = s_el + el * %d + %d + k;" % (ELS, EL0 + plan["R_off"]))
+        w("      double s = 0.0;")
+        w("      for (int ipt = 0; ipt < %d; ++ipt) s += P[ipt * %d];" % (NIPT, PB))
+        w("      a.integrals[(long long)(a.elem_begin + e0 + el) * %d + k] = s;" % NI)
+        w("    }")
         w("  }")
         w("}")
         w("")
@@ -1409,11 +1476,16 @@ class CudaEmitter:
             for rp in self.hroutines:
                 for what in (1, 2):
                     kernels[(rp.key, what)] = self._emit_kernel_pipe(o, rp, what)
+        integral_kernel = self._emit_integral_kernel(o) if self.code.integral_expressions else None
         # host side: launchers + table
         w("static int pb2_query(int kind, int residual_index, int param_index, unsigned flag, pb2_kernel_cfg* out)")
         w("{")
         w("  memset(out, 0, sizeof(*out));")
-        w("  if (kind < 0 || kind > 1 || flag > 2u) return 1;")
+        w("  if (kind < 0 || kind > 2 || flag > 2u) return 1;")
+        if integral_kernel:
+            w("  if (kind == 2) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
+                integral_kernel, self._kernel_smem[integral_kernel], self._kernel_cfg[integral_kernel][0], self._kernel_cfg[integral_kernel][1]))
+        w("  if (kind == 2 && !out->func) return 2;")
         if self.hessian and self.pipeline:
             for rp in self.hroutines:
                 for what in (1, 2):
@@ -1426,7 +1498,7 @@ class CudaEmitter:
                 w("  if (kind == 0 && residual_index == %d && param_index == %d && flag == %du) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
                     rp.res_index, rp.param_index, what, kn, self._kernel_smem[kn], self._kernel_cfg[kn][0], self._kernel_cfg[kn][1]))
         w("  if (!out->func) return 2;")
-        w("  out->pipelined = %d;" % (1 if self.pipeline else 0))
+        w("  out->pipelined = kind == 2 ? 0 : %d;" % (1 if self.pipeline else 0))
         w("  cudaError_t err = cudaFuncSetAttribute(out->func, cudaFuncAttributeMaxDynamicSharedMemorySize, out->smem_bytes);")
         w("  if (err != cudaSuccess) return 100 + (int)err;")
         w("  int per_sm = 0;")
@@ -1485,6 +1557,12 @@ class CudaEmitter:
         for what in (0, 1, 2):
             w("  ci->alg_bytes_per_elem[%d] = %r;" % (what, self.algorithmic_bytes(what)))
         w("  ci->alg_bytes_per_hist_level = %r;" % float(8 * sum(self._nnode_space(f.space) for f in code.nodal_fields())))
+        inames = code.integral_expression_names()
+        if len(inames) > 16:
+            raise RuntimeError("more than PB2_MAX_INTEGRALS integral expressions")
+        w("  ci->n_integrals = %d;" % len(inames))
+        for i, n in enumerate(inames):
+            w("  strncpy(ci->integral_names[%d], \"%s\", 47);" % (i, n))
         w("  table->query = &pb2_query;")
         w("  table->launch = &pb2_launch;")
         w("}")

@@ -128,3 +128,20 @@ class NonlinearHeatEquation(Equations):
     def define_residuals(self):
         u, u_test = var_and_test(self.name)
         self.add_residual(weak((1 + self.beta * u ** 2) * partial_t(u), u_test) + weak((1 + self.alpha * u) * grad(u), grad(u_test)))
+
+
+class IntegralObservables(Equations):
+    """Named integrals over the domain, ``IntegralObservables(volume=1, kinetic_energy=lambda: dot(u, u) / 2)``
+    (pyoomph/equations/generic.py:684-699): every integrand is multiplied by the measure of the coordinate system (or of
+    ``_coordinate_system``; Lagrangian if ``_lagrangian``) and registered with ``add_integral_function``."""
+
+    def __init__(self, _coordinate_system=None, _lagrangian: bool = False, **integral_observables):
+        super().__init__()
+        self._coordinate_system, self._lagrangian = _coordinate_system, _lagrangian
+        self.integral_observables = dict(integral_observables)
+
+    def define_additional_functions(self):
+        dx = self.get_dx(lagrangian=self._lagrangian, coordsys=self._coordinate_system)
+        for k, v in self.integral_observables.items():
+            v = v() if callable(v) else v
+            self.add_integral_function(k, v * dx)

@@ -133,6 +133,27 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
         if swirl:
             pinned["velocity_phi"] = np.unique(np.concatenate([mesh.boundaries["right"], mesh.boundaries["left"]]))
         unsteady = True
+    elif kind in ("ns_obs", "ns_axi_obs", "ale_axi_obs", "heat3d_obs"):
+        # integral expressions (IntegralObservables, pyoomph/equations/generic.py:684) next to the flow equations
+        from pyoomph_b200.equations import IntegralObservables
+        from pyoomph_b200.expressions import dot, grad, partial_t, var
+        if kind == "heat3d_obs":
+            mesh = CuboidBrickMesh(N)
+            obs = IntegralObservables(volume=1, heat=lambda: var("u"), heating_rate=lambda: partial_t(var("u")),
+                                      dirichlet_energy=lambda: dot(grad(var("u")), grad(var("u"))) / 2)
+            code = FiniteElementCode("Brick3dC2", TransientHeatEquation() + obs, name="heat3dobs")
+            pinned = {"u": mesh.boundaries["left"]}
+        else:
+            mesh = RectangularQuadMesh(N)
+            obs = IntegralObservables(volume=1, kinetic_energy=lambda: dot(var("velocity"), var("velocity")) / 2, momentum=lambda: var("velocity"),
+                                      pressure_integral=lambda: var("pressure"), dissipation=lambda: 0.01 * dot(grad(var("velocity_x")), grad(var("velocity_x"))))
+            eqs = NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + obs
+            if kind == "ale_axi_obs":
+                eqs = eqs + PseudoElasticMesh()
+            code = FiniteElementCode("Quad2dC2", eqs, name=kind.replace("_", ""), coordinate_system="axisymmetric" if "axi" in kind else "cartesian")
+            wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
+            pinned = {"velocity_x": wall, "velocity_y": wall}
+        unsteady = True
     elif kind == "ale_axi":        # config 4 bulk part as BASELINE names it: axisymmetric NS-TH on a pseudo-elastic moving mesh
         mesh = RectangularQuadMesh(N)
         code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + PseudoElasticMesh(),

@@ -140,6 +140,28 @@ def test_hessian_vector_products_parity(kind, N):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kind,N,distortion,unstructured", [("ns_obs", 9, 0.0, False), ("ns_axi_obs", 8, 0.1, True), ("ale_axi_obs", 6, 0.08, False),
+                                                          ("heat3d_obs", 3, 0.1, True), ("ns_obs", 100, 0.1, False)])
+def test_integral_expressions_parity(kind, N, distortion, unstructured):
+    """EvalIntegralExpression over the whole mesh (Mesh::evaluate_integral_expression): GPU kernel + fixed-order reduction against
+    the oracle's element loop, 1e-12 relative to the integral of |integrand| scale (here: to the largest observable), twice
+    (bit-reproducible), and next to a residual assembly on the same problem object."""
+    pb = make_problem(kind, N, distortion=distortion, unstructured=unstructured)
+    op = make_oracle(pb)
+    asm = make_gpu(pb)
+    ref = op.evaluate_integral_expressions()
+    got = asm.evaluate_integral_expressions()
+    assert asm.launch_count() == 2 and list(got) == list(ref) == asm.integral_names
+    scale = max(abs(v) for v in ref.values())
+    for k in ref:
+        assert abs(got[k] - ref[k]) <= TOL * scale, (k, got[k], ref[k])
+    asm.assemble(flag=1)
+    again = asm.evaluate_integral_expressions()
+    assert again == got and asm.evaluate_observable("volume") == got["volume"]
+    op.close(); asm.close()
+
+
+@pytest.mark.gpu
 def test_multi_assemble_request_matches_oracle():
     """MultiAssembleRequest (bifurcation_tools.py:449): R, J, M, dR/dp, dJ/dp, d(J.Y)/dU, d(M.Y)/dU from one request, in request
     order, against the oracle; the request needs 4 launches (one flag-2 launch, one parameter launch, one Hessian launch per vector)."""

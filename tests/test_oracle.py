@@ -239,3 +239,33 @@ def test_hessian_routine_matches_finite_differences_and_flags(kind, N):
     if kind == "ns_unsteady":                   # convective Hessian is symmetric in (j,k) but not in (i,j)
         assert np.abs(P1[0] - P4[0]).max() > 1e-8
     op.close()
+
+
+def test_integral_expressions_analytic_pins():
+    """EvalIntegralExpression (src/codegen.cpp:4125-4364) summed like Mesh::evaluate_integral_expression: volumes of the unit
+    square / cube / cylinder (2 pi r dx with the truncated Pi of jitbridge_hang.h:355), exact integrals of interpolated
+    polynomials, on uniform and on distorted meshes (the integral of 1 does not see interior distortion)."""
+    from pyoomph_b200.codegen import FiniteElementCode
+    from pyoomph_b200.equations import IntegralObservables, PoissonEquation
+    from pyoomph_b200.expressions import var
+    PI_T = 3.14159265359
+    for kind, N, vol in (("ns_obs", 4, 1.0), ("ns_axi_obs", 4, PI_T), ("heat3d_obs", 2, 1.0)):
+        pb = make_problem(kind, N)
+        op = make_oracle(pb)
+        obs = op.evaluate_integral_expressions()
+        assert abs(obs["volume"] - vol) <= 2e-9 * vol              # mistyped Gauss<2,3> knots: exact only to ~1e-9 for r dx
+        op.close()
+    # interior distortion moves no boundary node here: the area stays 1 to the quadrature's accuracy for the curved interior edges
+    pb = make_problem("ns_obs", 5)
+    x = pb["mesh"].node_pos
+    pb["vals"][0][:, pb["code"].fields["velocity_x"].index] = 1.0 + 2.0 * x[:, 0] - x[:, 1]           # Q9 reproduces it exactly
+    pb["vals"][0][:, pb["code"].fields["velocity_y"].index] = x[:, 0] * x[:, 1]
+    op = make_oracle(pb)
+    obs = op.evaluate_integral_expressions()
+    # the mistyped knots (+0.774596662941483 against -0.774596669241483) are not symmetric: even a linear integrand is off by ~1e-10
+    assert 1e-12 <= abs(obs["momentum_x"] - 1.5) <= 1e-9 and abs(obs["momentum_y"] - 0.25) <= 1e-9
+    assert list(obs) == ["volume", "kinetic_energy", "momentum_x", "momentum_y", "pressure_integral", "dissipation"]
+    op.close()
+    with pytest.raises(RuntimeError):
+        from pyoomph_b200.expressions import testfunction
+        FiniteElementCode("Quad2dC2", PoissonEquation() + IntegralObservables(bad=lambda: testfunction("u")), name="bad").integral_form()

@@ -72,7 +72,7 @@ def test_lagrange_polynomials_bit_exact(shim):
                     assert abs(dpsi[(i * order + j) * 2 + 1] - d[i] * p[j]) <= 8e-16
 
 
-@pytest.mark.parametrize("kind,N", [("ns_unsteady", 3), ("ale", 3), ("heat3d", 2)])
+@pytest.mark.parametrize("kind,N", [("ns_unsteady", 3), ("ale", 3), ("heat3d", 2), ("ale_axi_obs", 3)])
 def test_reference_headers_give_identical_results(kind, N):
     pb = make_problem(kind, N)
     out = []
@@ -80,7 +80,8 @@ def test_reference_headers_give_identical_results(kind, N):
         op = make_oracle(pb, reference_headers=ref)
         e = op.element(pb["mesh"].n_elem // 2, flag=2)
         r, m = op.assemble(flag=2)
-        out.append(e + (r,) + tuple(x for mat in m for x in mat))
+        obs = (np.array(list(op.evaluate_integral_expressions().values())),) if pb["code"].integral_expressions else ()
+        out.append(e + (r,) + tuple(x for mat in m for x in mat) + obs)     # EvalIntegralExpression through jitbridge.h:469 too
         op.close()
     for a, b in zip(*out):
         assert np.array_equal(a, b)
