@@ -185,7 +185,8 @@ class B200Assembly(CustomAssemblyBase):
         _check(self.lib.pb2_problem_pattern(self.prob, ctypes.byref(rs), ctypes.byref(ci), ctypes.byref(nnz), ctypes.byref(nrows)))
         self.n_dof, self.nnz = int(nrows.value), int(nnz.value)
         self.indptr = np.ctypeslib.as_array(rs, shape=(self.n_dof + 1,))
-        self.indices = np.ctypeslib.as_array(ci, shape=(max(self.nnz, 1),))[:self.nnz]
+        # an empty pattern (every dof pinned, or no element on this rank) has no column array at all
+        self.indices = np.ctypeslib.as_array(ci, shape=(self.nnz,)) if self.nnz > 0 else np.zeros(0, dtype=np.int32)
         self.n_elem = self._elem_nodes.shape[0]
         self.param_names = [self.info.param_names[i].value.decode() for i in range(self.info.n_params)]
         self.residual_names = [self.info.residual_names[i].value.decode() for i in range(self.info.n_residuals)]

@@ -162,6 +162,46 @@ def test_integral_expressions_parity(kind, N, distortion, unstructured):
 
 
 @pytest.mark.gpu
+def test_edge_cases_single_element_everything_pinned_no_elements():
+    """smallest and degenerate inputs: a one-element mesh; every dof of the class pinned (n_dof = 0, empty pattern: the launch must
+    still run and write nothing); an assembler that was given no elements at all (a rank whose block is empty): zero matrix on the
+    requested pattern, zero residual; bad arguments are reported, not computed around."""
+    for kind in ("ns", "heat3d", "ale"):
+        pb = make_problem(kind, 1)
+        op, asm = make_oracle(pb), make_gpu(pb)
+        n = pb["dofmap"].n_dof
+        r_ref, mats = op.assemble(flag=1)
+        asm.assemble(flag=1)
+        r, jac, _ = asm.fetch()
+        assert np.abs(r - r_ref).max() <= TOL * np.abs(r_ref).max()
+        err, missing = compare_matrix(csr_to_sorted(n, asm.indptr, asm.indices, jac), csr_to_sorted(n, *mats[0]))
+        assert missing == 0 and err <= TOL
+        op.close(); asm.close()
+    from pyoomph_b200.meshes import assign_equation_numbers
+    pb = make_problem("ns", 3)
+    everything = np.arange(pb["mesh"].n_node)
+    pb["dofmap"] = assign_equation_numbers(pb["mesh"], pb["code"], {"velocity_x": everything, "velocity_y": everything, "pressure": everything})
+    assert pb["dofmap"].n_dof == 0
+    asm = make_gpu(pb)
+    asm.assemble(flag=2)
+    r, jac, mass = asm.fetch(True, True)
+    assert asm.nnz == 0 and r.size == 0 and jac.size == 0 and mass.size == 0
+    asm.close()
+    pb = make_problem("ns", 3)
+    from pyoomph_b200.assembly import B200Assembly
+    asm = B200Assembly(pb["code"], pb["mesh"], pb["dofmap"], name=pb["code"].name, elements=np.zeros(0, dtype=np.int64),
+                       extra_pattern=(np.array([0, 1], dtype=np.int32), np.array([1, 0], dtype=np.int32)))
+    asm.assemble(flag=1)
+    r, jac, _ = asm.fetch()
+    assert asm.n_elem == 0 and asm.nnz == 2 and not jac.any()
+    with pytest.raises(RuntimeError):
+        asm.assemble(flag=3)
+    with pytest.raises(ValueError):
+        asm.assemble(flag=1, parameter="nope")
+    asm.close()
+
+
+@pytest.mark.gpu
 def test_multi_assemble_request_matches_oracle():
     """MultiAssembleRequest (bifurcation_tools.py:449): R, J, M, dR/dp, dJ/dp, d(J.Y)/dU, d(M.Y)/dU from one request, in request
     order, against the oracle; the request needs 4 launches (one flag-2 launch, one parameter launch, one Hessian launch per vector)."""
