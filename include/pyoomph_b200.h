@@ -66,6 +66,9 @@ int pb2_problem_set_nodal_positions(pb2_problem *p, int t, const double *pos /*[
 int pb2_problem_set_lagrangian_positions(pb2_problem *p, const double *pos /*[n_node][dim]*/);
 /* Problem::set_dofs equivalent: scatter a global dof vector (host) into current nodal values / positions on the device */
 int pb2_problem_set_dofs(pb2_problem *p, const double *dofs /*[n_dof]*/);
+/* Problem::shift_time_values on the packed data (device to device): history level t <- level t-1 for the nodal values and, on
+ * moving meshes, the nodal positions; level 0 keeps the current values.  Replaces a re-upload of every history level per time step. */
+int pb2_problem_shift_time_values(pb2_problem *p);
 int pb2_problem_set_time(pb2_problem *p, const pb2_time_info *ti);
 int pb2_problem_set_parameters(pb2_problem *p, const double *values, int n);
 

@@ -79,7 +79,7 @@ def load_library() -> ctypes.CDLL:
                "pb2_problem_set_time", "pb2_problem_set_parameters", "pb2_problem_assemble", "pb2_problem_device_outputs",
                "pb2_problem_fetch", "pb2_problem_assemble_host", "pb2_problem_num_colours", "pb2_version",
                "pb2_problem_assemble_hessian", "pb2_problem_fetch_hessian", "pb2_problem_hessian_vector_products",
-               "pb2_problem_pack_rows", "pb2_problem_unpack_add", "pb2_problem_eval_integrals"):
+               "pb2_problem_pack_rows", "pb2_problem_unpack_add", "pb2_problem_eval_integrals", "pb2_problem_shift_time_values"):
         getattr(L, fn).restype = ctypes.c_int
     _LIB = L
     return L
@@ -157,6 +157,14 @@ class B200Assembly(CustomAssemblyBase):
         _check(self.lib.pb2_class_load(self.plugin_path.encode(), ctypes.byref(self.cls)))
         self.info = ClassInfo()
         _check(self.lib.pb2_class_get_info(self.cls, ctypes.byref(self.info)))
+        self._device, self._elements, self._extra_pattern = device, elements, extra_pattern
+        self.prob = None
+        self._create_problem(mesh, dofmap)
+
+    def _create_problem(self, mesh, dofmap):
+        """pack mesh + numbering into the SoA buffers of a new pb2_problem (the element class and its kernels are kept)"""
+        device, elements, extra_pattern = self._device, self._elements, self._extra_pattern
+        self.mesh, self.dofmap = mesh, dofmap
         en = mesh.elem_nodes if elements is None else mesh.elem_nodes[elements]
         self._elem_nodes = np.ascontiguousarray(en, dtype=np.int32)
         self._node_eqn = np.ascontiguousarray(dofmap.node_eqn, dtype=np.int32)
@@ -191,13 +199,42 @@ class B200Assembly(CustomAssemblyBase):
         self.param_names = [self.info.param_names[i].value.decode() for i in range(self.info.n_params)]
         self.residual_names = [self.info.residual_names[i].value.decode() for i in range(self.info.n_residuals)]
         self.integral_names = [self.info.integral_names[i].value.decode() for i in range(self.info.n_integrals)]
-        self._params = np.zeros(max(1, self.info.n_params))
+        if not hasattr(self, "_params"):
+            self._params = np.zeros(max(1, self.info.n_params))
+        self._stale = False
         self.set_nodal_positions(0, mesh.node_pos)
         for t in range(1, self.info.n_hist_pos):
             self.set_nodal_positions(t, mesh.node_pos)
         self.set_lagrangian_positions(mesh.node_pos)
-        self.set_steady()
+        if hasattr(self, "ti"):
+            _check(self.lib.pb2_problem_set_time(self.prob, ctypes.byref(self.ti)))     # rebuild: keep time info and parameters
+            _check(self.lib.pb2_problem_set_parameters(self.prob, self._dp(self._params), self.info.n_params))
+        else:
+            self.set_steady()
         self._last_flag = -1
+
+    # ---- invalidation (CustomAssemblyBase hooks, pyoomph/generic/assembly.py:52-65) --------------------------------------------
+    def invalidate_cache(self) -> None:
+        """equation numbering, adaptation or remeshing changed what was packed: the next assembly must not use it"""
+        self._stale = True
+
+    def rebuild(self, mesh=None, dofmap=None, elements=None, extra_pattern=None) -> None:
+        """re-pack after renumbering / adaptation / remeshing: new pb2_problem (pattern, maps, schedule), same compiled class;
+        nodal values and positions of the new mesh must be set again (set_nodal_values / set_dofs)"""
+        if elements is not None or extra_pattern is not None:
+            self._elements, self._extra_pattern = elements, extra_pattern
+        if self.prob:
+            self.lib.pb2_problem_free(self.prob)
+            self.prob = None
+        self._create_problem(mesh if mesh is not None else self.mesh, dofmap if dofmap is not None else self.dofmap)
+
+    def _fresh(self):
+        if self._stale:
+            raise RuntimeError("the packed problem was invalidated (renumbering / adaptation / remeshing): call rebuild(mesh, dofmap) first")
+
+    def shift_time_values(self):
+        """Problem::shift_time_values on the device-resident history levels"""
+        _check(self.lib.pb2_problem_shift_time_values(self.prob))
 
     # ---- data ---------------------------------------------------------------------------------
     @staticmethod
@@ -250,6 +287,7 @@ class B200Assembly(CustomAssemblyBase):
     # ---- assembly -----------------------------------------------------------------------------
     def assemble(self, flag: int = 1, residual: str = "", parameter: Optional[str] = None, stream: int = 0):
         """Device-resident assembly (results stay in HBM); use fetch() or device_outputs()."""
+        self._fresh()
         ri = self.residual_names.index(residual)
         pi = -1 if parameter is None else self.param_names.index(parameter)
         _check(self.lib.pb2_problem_assemble(self.prob, ri, pi, flag, ctypes.c_void_p(stream)))
@@ -266,6 +304,7 @@ class B200Assembly(CustomAssemblyBase):
     def assemble_host(self, dofs: Optional[np.ndarray], flag: int = 1, residual: str = "", parameter: Optional[str] = None,
                       out: Optional[Tuple[np.ndarray, Optional[np.ndarray], Optional[np.ndarray]]] = None):
         """The reference-facing call: host dof vector in, host residual / CSR values out (copies included)."""
+        self._fresh()
         ri = self.residual_names.index(residual)
         pi = -1 if parameter is None else self.param_names.index(parameter)
         if out is None:

@@ -717,6 +717,20 @@ extern "C" int pb2_problem_set_dofs(pb2_problem *p, const double *dofs)
   return scatter_dofs_from_device(p, 0);
 }
 
+// oomph's Problem::shift_time_values (TimeStepper::shift_time_values of every Data, timesteppers.h): history level t takes the
+// values of level t-1, level 0 keeps the current values as the initial guess of the new step; device to device, no host copy
+extern "C" int pb2_problem_shift_time_values(pb2_problem *p)
+{
+  CUDA_OK(cudaSetDevice(p->device));
+  const pb2_class_info &ci = p->cls->table.info;
+  const size_t nv = (size_t)p->n_node * std::max(1, ci.nval) * sizeof(double), np_ = (size_t)p->n_node * ci.nodal_dim * sizeof(double);
+  for (int t = p->T_val - 1; t >= 1; t--)
+    CUDA_OK(cudaMemcpyAsync((char *)p->d_node_val + (size_t)t * nv, (char *)p->d_node_val + (size_t)(t - 1) * nv, nv, cudaMemcpyDeviceToDevice, 0));
+  for (int t = p->T_pos - 1; t >= 1; t--)
+    CUDA_OK(cudaMemcpyAsync((char *)p->d_node_pos + (size_t)t * np_, (char *)p->d_node_pos + (size_t)(t - 1) * np_, np_, cudaMemcpyDeviceToDevice, 0));
+  return 0;
+}
+
 extern "C" int pb2_problem_set_time(pb2_problem *p, const pb2_time_info *ti)
 {
   p->ti = *ti;

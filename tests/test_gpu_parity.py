@@ -202,6 +202,46 @@ def test_edge_cases_single_element_everything_pinned_no_elements():
 
 
 @pytest.mark.gpu
+def test_invalidate_rebuild_and_shift_time_values():
+    """the packer's life cycle (SURVEY N-a): invalidate_cache() after a renumbering makes the next assembly fail loudly until
+    rebuild(mesh, dofmap) re-packs (same compiled class, new pattern) -- results equal a fresh assembler's and the oracle's;
+    shift_time_values() moves the history levels on the device like Problem::shift_time_values."""
+    from pyoomph_b200.meshes import assign_equation_numbers
+    pb = make_problem("ns_unsteady", 7)
+    asm = make_gpu(pb)
+    asm.assemble(flag=1)
+    nnz0 = asm.nnz
+    asm.actions_after_equation_numbering()
+    with pytest.raises(RuntimeError):
+        asm.assemble(flag=1)
+    mesh = pb["mesh"]
+    pb["dofmap"] = assign_equation_numbers(mesh, pb["code"], {"velocity_x": mesh.boundaries["left"], "velocity_y": mesh.boundaries["left"]})
+    asm.rebuild(mesh, pb["dofmap"])
+    assert asm.nnz != nnz0 and asm.n_dof == pb["dofmap"].n_dof
+    for t in range(pb["vals"].shape[0]):
+        asm.set_nodal_values(t, pb["vals"][t])
+    op = make_oracle(pb)
+    n = pb["dofmap"].n_dof
+    r_ref, mats = op.assemble(flag=1)
+    asm.assemble(flag=1)                         # time info survived the rebuild (BDF2 weights of make_gpu)
+    r, jac, _ = asm.fetch()
+    err, missing = compare_matrix(csr_to_sorted(n, asm.indptr, asm.indices, jac), csr_to_sorted(n, *mats[0]))
+    assert missing == 0 and err <= TOL and np.abs(r - r_ref).max() <= TOL * np.abs(r_ref).max()
+    op.close()
+    # shift: level t <- level t-1, level 0 unchanged
+    asm.shift_time_values()
+    asm.assemble(flag=1)
+    r_shift, j_shift, _ = asm.fetch()
+    pb2 = dict(pb)
+    pb2["vals"] = np.stack([pb["vals"][0], pb["vals"][0], pb["vals"][1]])
+    ref = make_gpu(pb2)
+    ref.assemble(flag=1)
+    r2, j2, _ = ref.fetch()
+    assert np.array_equal(r_shift, r2) and np.array_equal(j_shift, j2)
+    asm.close(); ref.close()
+
+
+@pytest.mark.gpu
 def test_multi_assemble_request_matches_oracle():
     """MultiAssembleRequest (bifurcation_tools.py:449): R, J, M, dR/dp, dJ/dp, d(J.Y)/dU, d(M.Y)/dU from one request, in request
     order, against the oracle; the request needs 4 launches (one flag-2 launch, one parameter launch, one Hessian launch per vector)."""
