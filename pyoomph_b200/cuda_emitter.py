@@ -178,6 +178,9 @@ class CudaEmitter:
         self.pipe_smem_budget = int(os.environ.get("PB2_PIPE_SMEM", str(200 * 1024)))
         self.pipe_gather_threads = int(os.environ.get("PB2_PIPE_NG", "64"))
         self.pipe_scatter_threads = int(os.environ.get("PB2_PIPE_NS", "128"))
+        # 3D: the shape side of the contraction from the 1D factors of the tensor-product basis (18 uniform constants per Gauss point
+        # instead of 108 shared-memory table loads for the 27 columns of a Q27 field)
+        self.tensor_columns = self.dim == 3 and os.environ.get("PB2_TP3D", "1") != "0"
 
     # ------------------------------------------------------------------ planning
     def _col_index(self, field: str, lnode: int) -> int:
@@ -310,6 +313,15 @@ class CudaEmitter:
         o.append("__constant__ double c_dpsi1[%d] = {%s};" % (self.NIPT * self.NN1 * self.dim, arr(v for p in dpsi1 for l in p for v in l)))
         o.append("__device__ const double g_tables[%d] = {%s};" % (self._tables_smem_size(), arr(
             [v for p in psi2 for v in p] + [v for p in dpsi2 for l in p for v in l] + [v for p in psi1 for v in p] + [v for p in dpsi1 for l in p for v in l])))
+        if self.dim == 3:
+            # 1D factors per Gauss point: [ipt][dir][L_0..L_2, L'_0..L'_2] at the knot of that direction (psi_c = L_i(s0) L_j(s1) L_k(s2),
+            # c = i + 3j + 9k, Qelements.cc:621-660)
+            t1 = []
+            for sk in kn:
+                for d in range(3):
+                    P, D = _lag(3, sk[d])
+                    t1 += list(P) + list(D)
+            o.append("__constant__ double c_t1d[%d] = {%s};" % (len(t1), arr(t1)))
         o.append("__constant__ int c_c1node[%d] = {%s};" % (self.NN1, ", ".join(str(n) for n in self.et.c1_nodes)))
         # row dof index of (field, space-local node)
         for f in self.code.unknown_field_names():
@@ -1201,6 +1213,11 @@ class CudaEmitter:
             w("          " + " ".join("const double gg%d%d = P[%d];" % (b, i, plan["gg"] + b * dim + i) for b in range(dim) for i in range(dim)))
         if need_X:
             w("          " + " ".join("const double ggL%d%d = P[%d];" % (b, i, plan["ggL"] + b * dim + i) for b in range(dim) for i in range(dim)))
+        tp = self.tensor_columns and any(code.fields[G].space != "C1" for (F_, G) in pairs)
+        if tp:
+            for d in range(3):
+                w("          " + " ".join("const double tL%d%d = c_t1d[ipt * 18 + %d]; const double tD%d%d = c_t1d[ipt * 18 + %d];" % (
+                    d, n, d * 6 + n, d, n, d * 6 + 3 + n) for n in range(3)))
         w("          #pragma unroll")
         w("          for (int k = 0; k < %d; ++k)" % RB)
         w("          {")
@@ -1255,6 +1272,32 @@ class CudaEmitter:
                     tp, td = ("s_psi1", "s_dpsi1") if self.table_source == "smem" else ("c_psi1", "c_dpsi1")
                 else:
                     tp, td = ("s_psi2", "s_dpsi2") if self.table_source == "smem" else ("c_psi2", "c_dpsi2")
+                if self.tensor_columns and Gs != "C1":
+                    # psi_c = a_i b_j c_k: W0 psi + Ws.dpsi = (W0 a_i + Ws0 a'_i) b_j c_k + a_i (Ws1 b'_j c_k + Ws2 b_j c'_k)
+                    pf = "%s_%s" % (F, G)
+                    w0 = "W_%s_d0" % pf if "d0" in by_atom else None
+                    for i in range(3):
+                        terms = ([("%s * tL0%d" % (w0, i))] if w0 else []) + ([("Ws0_%s * tD0%d" % (pf, i))] if have_s else [])
+                        w("            const double tpA%d_%s = %s;" % (i, pf, " + ".join(terms)))
+                    for j in range(3):
+                        for i in range(3):
+                            w("            const double tpAB%d%d_%s = tpA%d_%s * tL1%d;" % (i, j, pf, i, pf, j))
+                    if have_s:
+                        for j in range(3):
+                            w("            const double tpX%d_%s = Ws1_%s * tD1%d; const double tpY%d_%s = Ws2_%s * tL1%d;" % (j, pf, pf, j, j, pf, pf, j))
+                        for k_ in range(3):
+                            for j in range(3):
+                                w("            const double tpC%d%d_%s = tL2%d * tpX%d_%s + tD2%d * tpY%d_%s;" % (j, k_, pf, k_, j, pf, k_, j, pf))
+                    for k_ in range(3):
+                        for j in range(3):
+                            for i in range(3):
+                                c = i + 3 * j + 9 * k_
+                                an = "acc[%d + k * %d + %d]" % (base[(F, G)], nnG, c)
+                                e = "fma(tpAB%d%d_%s, tL2%d, %s)" % (i, j, pf, k_, an)
+                                if have_s:
+                                    e = "fma(tL0%d, tpC%d%d_%s, %s)" % (i, j, k_, pf, e)
+                                w("            %s = %s;" % (an, e))
+                    continue
                 parts = []
                 if "d0" in by_atom:
                     parts.append(("W_%s_%s_d0" % (F, G), "%s[ipt * %d + c]" % (tp, nnG)))
