@@ -81,6 +81,42 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class gpu_local_cpus:
+    """Run the enclosed block on the CPUs of the GPU's NUMA node (pinned host buffers are placed on the node of the allocating
+    thread; a buffer on the far socket halves the host-link rate of the end-to-end leg).  No-op where the topology is not exposed."""
+
+    def __init__(self, device):
+        self.device, self.saved = device, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(self.device)).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+            if len(bus.split(":")[0]) == 8:
+                bus = bus[4:]
+            node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+            if node < 0:
+                return self
+            cpus = set()
+            for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus |= set(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                self.saved = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, cpus)
+        except Exception:
+            self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+        return False
+
+
 def build_workload(workload, n, seed=0):
     from problems import smooth_field
     from pyoomph_b200.codegen import FiniteElementCode
@@ -268,7 +304,10 @@ def main():
             if not ptr:
                 raise RuntimeError("pinned allocation failed")
             return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(nelem,))
-        h_dofs, h_res, h_jac = pinned(ndof), pinned(ndof), pinned(nnz)
+        with gpu_local_cpus(device):
+            h_dofs, h_res, h_jac = pinned(ndof), pinned(ndof), pinned(nnz)
+            h_res[:] = 0.0
+            h_jac[:] = 0.0          # touch the pages here, on the GPU's NUMA node
         h_dofs[:] = 0.0
         h_dofs[eq[eq >= 0]] = pb["vals"][0][eq >= 0]
         ksteps = max(1, min(args.steps, 5))
@@ -291,11 +330,12 @@ def main():
         try:
             part = dasm.part
             eq = part.local_dofmap.node_eqn
-            h_dofs = torch.zeros(asm.n_dof, dtype=torch.float64).pin_memory()
+            nnz_owned = int(dasm.indptr[dasm.n_owned])
+            with gpu_local_cpus(device):
+                h_dofs = torch.zeros(asm.n_dof, dtype=torch.float64).pin_memory()
+                outb = (torch.zeros(dasm.n_owned, dtype=torch.float64).pin_memory(), torch.zeros(nnz_owned, dtype=torch.float64).pin_memory(), None)
             m_ = eq >= 0
             h_dofs.numpy()[eq[m_]] = pb["vals"][0][m_]
-            nnz_owned = int(dasm.indptr[dasm.n_owned])
-            outb = (torch.empty(dasm.n_owned, dtype=torch.float64).pin_memory(), torch.empty(nnz_owned, dtype=torch.float64).pin_memory(), None)
             h2d, d2h = int(asm.n_dof * 8), int((dasm.n_owned + nnz_owned) * 8)
             dasm.assemble_host(h_dofs, 1, out=outb)          # warm-up (ends with a device synchronisation, like every call)
             t0 = time.perf_counter()
