@@ -315,6 +315,21 @@ class DistributedAssembly:
             torch.cuda.synchronize(self.device)
         return out
 
+    def evaluate_integral_expressions(self) -> Dict[str, float]:
+        """integral expressions over the whole mesh: every rank integrates over its own elements (they partition the mesh), the
+        per-rank values are gathered and added in rank order (deterministic, identical on all ranks)"""
+        local = self.local.evaluate_integral_expressions()
+        names = list(local)
+        mine = self.torch.tensor([local[n] for n in names], dtype=self.torch.float64, device=self.device)
+        if self.world == 1:
+            return dict(local)
+        parts = [self.torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(parts, mine)
+        total = parts[0].clone()
+        for q in range(1, self.world):
+            total += parts[q]
+        return {n: float(v) for n, v in zip(names, total.cpu().tolist())}
+
     # ---- results ---------------------------------------------------------------------------------
     def owned_block(self, want_mass: bool = False):
         """(row_begin, row_end, indptr, global column indices, values[, mass values], residual) of the owned row block"""
@@ -356,6 +371,9 @@ class GPULocalAssembler:
 
     def _stream(self):
         return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def evaluate_integral_expressions(self):
+        return self.asm.evaluate_integral_expressions()
 
     def set_dofs(self, dofs):
         """host values of the LOCAL dofs (owned | halo | ghost) -> nodal storage on the device (pb2_problem_set_dofs)"""

@@ -59,6 +59,9 @@ class OracleLocalAssembler:
         self._jac = self._embed(*mats[0]) if flag >= 1 else None
         self._mass = self._embed(*mats[1]) if flag >= 2 else None
 
+    def evaluate_integral_expressions(self):
+        return self.op.evaluate_integral_expressions()
+
     def residual_tensor(self): return self._res
     def jacobian_tensor(self): return self._jac
     def mass_tensor(self): return self._mass
@@ -77,13 +80,14 @@ def _worker(rank, world, port, kind, N, outdir):
     rb, re, ip, gc, jv, mv, res = da.owned_block(want_mass=True)
     h_res, h_jac, h_mass = da.assemble_host(None, 2)           # the host-facing call of one rank returns the same owned block
     assert np.array_equal(h_res.numpy(), res) and np.array_equal(h_jac.numpy(), jv) and np.array_equal(h_mass.numpy(), mv)
+    obs = da.evaluate_integral_expressions() if pb["code"].integral_expressions else {}
     np.savez(os.path.join(outdir, "r%d.npz" % rank), rb=rb, re=re, ip=ip, gc=gc, jv=jv, mv=mv, res=res, new_of_old=da.part.new_of_old,
-             xbytes=da.exchange_bytes)
+             xbytes=da.exchange_bytes, obs=np.array([obs[k] for k in obs]))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,N,world", [("ns_unsteady", 6, 2), ("ale", 5, 3), ("heat3d", 3, 2)])
+@pytest.mark.parametrize("kind,N,world", [("ns_unsteady", 6, 2), ("ale", 5, 3), ("heat3d", 3, 2), ("ale_axi_obs", 5, 3)])
 def test_row_block_assembly_matches_single_process(kind, N, world):
     import torch.multiprocessing as mp
     from scipy.sparse import csr_matrix
@@ -116,3 +120,7 @@ def test_row_block_assembly_matches_single_process(kind, N, world):
     res = np.concatenate([b["res"] for b in blocks])
     r_perm = np.empty(n); r_perm[p] = r_ref
     assert np.abs(res - r_perm).max() <= 1e-13 * np.abs(r_ref).max()
+    if pb["code"].integral_expressions:       # element blocks partition the mesh: rank-ordered sums equal the serial integrals
+        ref = np.array(list(op.evaluate_integral_expressions().values()))
+        for b in blocks:
+            assert np.array_equal(b["obs"], blocks[0]["obs"]) and np.abs(b["obs"] - ref).max() <= 1e-13 * np.abs(ref).max()
