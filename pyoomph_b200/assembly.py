@@ -339,6 +339,18 @@ class B200Assembly(CustomAssemblyBase):
         _check(self.lib.pb2_problem_hessian_vector_products(self.prob, ri, self._dp(Y), self._dp(C), C.shape[0], self._dp(out)))
         return out
 
+    # ---- eigenproblem matrices (Problem::assemble_eigenproblem_matrices, src/problem.cpp:715 -> oomph EigenProblemHandler) --------
+    def assemble_eigenproblem_matrices(self, sigma_r: float = 0.0, residual: str = ""):
+        """(M, J - sigma_r*M) from ONE flag-2 launch, as scipy CSR matrices over the fixed pattern; the shift is applied to the
+        assembled values (the reference shifts every element matrix, oomph-lib assembly_handler.cc:369-382: same sums)."""
+        from scipy.sparse import csr_matrix
+        self.assemble(flag=2, residual=residual)
+        _, jac, mass = self.fetch(True, True)
+        if sigma_r != 0.0:
+            jac = jac - sigma_r * mass
+        n = self.n_dof
+        return csr_matrix((mass, self.indices, self.indptr), shape=(n, n)), csr_matrix((jac, self.indices, self.indptr), shape=(n, n))
+
     # ---- integral expressions (Mesh.evaluate_observable -> BulkElementBase::eval_integral_expression, src/mesh.cpp:545) ---------
     def evaluate_integral_expressions(self) -> Dict[str, float]:
         """all integral expressions of the element class over all elements: one launch for the per-element values and one

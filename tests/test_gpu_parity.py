@@ -267,6 +267,9 @@ def test_multi_assemble_request_matches_oracle():
         assert abs(got - ref).max() <= TOL * max(abs(ref).max(), 1e-300) if ref.nnz else abs(got).max() == 0.0
     with pytest.raises(NotImplementedError):
         MultiAssembleRequest(asm).dJdU(Y, transposed=True)
+    # eigenproblem pair (Problem::assemble_eigenproblem_matrices): mass matrix and shifted Jacobian from one launch
+    Me, Je = asm.assemble_eigenproblem_matrices(sigma_r=0.75)
+    assert asm.launch_count() == 1 and abs(Me - M).max() == 0.0 and abs(Je - (J - 0.75 * M)).max() <= 1e-15 * abs(J).max()
     op.close(); asm.close()
 
 
