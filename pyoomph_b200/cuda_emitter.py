@@ -181,6 +181,9 @@ class CudaEmitter:
         # 3D: the shape side of the contraction from the 1D factors of the tensor-product basis (18 uniform constants per Gauss point
         # instead of 108 shared-memory table loads for the 27 columns of a Q27 field)
         self.tensor_columns = self.dim == 3 and os.environ.get("PB2_TP3D", "1") != "0"
+        # ... and phase 1 (geometry + interpolation of the Q27 / position fields) in ONE node loop with psi_l, dpsi_l built from the same
+        # 1D factors: 18 table loads per point instead of one per node, table and quantity
+        self.tensor_points = self.dim == 3 and os.environ.get("PB2_TP3D_POINTS", "1") != "0"
 
     # ------------------------------------------------------------------ planning
     def _col_index(self, field: str, lnode: int) -> int:
@@ -305,6 +308,15 @@ class CudaEmitter:
 
         def arr(vals):
             return ", ".join(repr(float(v)) for v in vals)
+        t1 = []
+        if self.dim == 3:
+            # 1D factors per Gauss point: [ipt][dir][L_0..L_2, L'_0..L'_2] at the knot of that direction (psi_c = L_i(s0) L_j(s1) L_k(s2),
+            # c = i + 3j + 9k, Qelements.cc:621-660)
+            for sk in kn:
+                for d in range(3):
+                    P, D = _lag(3, sk[d])
+                    t1 += list(P) + list(D)
+        t1_smem = t1
         o.append("// reference-element tables at the oomph Gauss points (integral.cc literals, shape.h polynomials)")
         o.append("__constant__ double c_w[%d] = {%s};" % (self.NIPT, arr(w)))
         o.append("__constant__ double c_psi2[%d] = {%s};" % (self.NIPT * self.NN, arr(v for p in psi2 for v in p)))
@@ -312,15 +324,8 @@ class CudaEmitter:
         o.append("__constant__ double c_psi1[%d] = {%s};" % (self.NIPT * self.NN1, arr(v for p in psi1 for v in p)))
         o.append("__constant__ double c_dpsi1[%d] = {%s};" % (self.NIPT * self.NN1 * self.dim, arr(v for p in dpsi1 for l in p for v in l)))
         o.append("__device__ const double g_tables[%d] = {%s};" % (self._tables_smem_size(), arr(
-            [v for p in psi2 for v in p] + [v for p in dpsi2 for l in p for v in l] + [v for p in psi1 for v in p] + [v for p in dpsi1 for l in p for v in l])))
+            [v for p in psi2 for v in p] + [v for p in dpsi2 for l in p for v in l] + [v for p in psi1 for v in p] + [v for p in dpsi1 for l in p for v in l] + t1_smem)))
         if self.dim == 3:
-            # 1D factors per Gauss point: [ipt][dir][L_0..L_2, L'_0..L'_2] at the knot of that direction (psi_c = L_i(s0) L_j(s1) L_k(s2),
-            # c = i + 3j + 9k, Qelements.cc:621-660)
-            t1 = []
-            for sk in kn:
-                for d in range(3):
-                    P, D = _lag(3, sk[d])
-                    t1 += list(P) + list(D)
             o.append("__constant__ double c_t1d[%d] = {%s};" % (len(t1), arr(t1)))
         o.append("__constant__ int c_c1node[%d] = {%s};" % (self.NN1, ", ".join(str(n) for n in self.et.c1_nodes)))
         # row dof index of (field, space-local node)
@@ -331,7 +336,7 @@ class CudaEmitter:
 
     def _tables_smem_size(self) -> int:
         """doubles of shape tables staged in shared memory (needed by phase 1 always, phase 2 in smem mode)."""
-        return self.NIPT * (self.NN * (1 + self.dim) + self.NN1 * (1 + self.dim))
+        return self.NIPT * (self.NN * (1 + self.dim) + self.NN1 * (1 + self.dim)) + (self.NIPT * 18 if self.dim == 3 else 0)
 
     def _emit_kernel(self, o: List[str], rp: RoutinePlan, what: int):
         code, dim, NN, NN1, NIPT = self.code, self.dim, self.NN, self.NN1, self.NIPT
@@ -362,6 +367,7 @@ class CudaEmitter:
         w("  double* const s_dpsi2 = s_psi2 + %d;" % (NIPT * NN))
         w("  double* const s_psi1 = s_dpsi2 + %d;" % (NIPT * NN * dim))
         w("  double* const s_dpsi1 = s_psi1 + %d;" % (NIPT * NN1))
+        w("  const double* const s_t1d = s_dpsi1 + %d; (void)s_t1d;" % (NIPT * NN1 * dim))
         w("  double* const s_el = smem + %d;" % tab_n)
         w("  int* const s_rowstart = (int*)(smem + %d);" % (tab_n + self.EPB * ELS))
         w("  int* const s_resmap = s_rowstart + %d;" % (self.EPB * self.ndof))
@@ -500,6 +506,7 @@ class CudaEmitter:
         w("  double* const s_dpsi2 = s_psi2 + %d;" % (NIPT * NN))
         w("  double* const s_psi1 = s_dpsi2 + %d;" % (NIPT * NN * dim))
         w("  double* const s_dpsi1 = s_psi1 + %d;" % (NIPT * NN1))
+        w("  const double* const s_t1d = s_dpsi1 + %d; (void)s_t1d;" % (NIPT * NN1 * dim))
         w("  double* const s_el = smem + %d;" % tab_n)
         w("  const int tid = threadIdx.x;")
         w("  for (int i = tid; i < %d; i += %d) smem[i] = g_tables[i];" % (tab_n, NT))
@@ -606,6 +613,7 @@ class CudaEmitter:
         w("  double* const s_dpsi2 = s_psi2 + %d;" % (NIPT * NN))
         w("  double* const s_psi1 = s_dpsi2 + %d;" % (NIPT * NN * dim))
         w("  double* const s_dpsi1 = s_psi1 + %d;" % (NIPT * NN1))
+        w("  const double* const s_t1d = s_dpsi1 + %d; (void)s_t1d;" % (NIPT * NN1 * dim))
         w("  (void)s_psi1; (void)s_dpsi1;")
         w("  const int tid = threadIdx.x;")
         w("  for (int i = tid; i < %d; i += %d) smem[i] = g_tables[i];" % (tab_n, NT))
@@ -970,9 +978,63 @@ class CudaEmitter:
         w("      const double* ps2 = s_psi2 + ipt * %d; const double* dp2 = s_dpsi2 + ipt * %d;" % (NN, NN * dim))
         w("      const double* ps1 = s_psi1 + ipt * %d; const double* dp1 = s_dpsi1 + ipt * %d;" % (NN1, NN1 * dim))
         w("      (void)ps1; (void)dp1; (void)ps2;")
-        self._emit_geometry(o, plan, "xpos", "gg", "detE")
+        # (field, kind) -> derivatives needed, for all atoms of the form
+        needed: Dict[Tuple[str, tuple], set] = {}
+        for at in form.atoms:
+            kind = ("dt", at.dt_order, at.scheme) if at.dt_order else ("cur", at.past)
+            needed.setdefault((at.field, kind), set()).add(at.deriv)
+
+        def src_of(f, kind):
+            if f.startswith("lagrangian_"):
+                return "E[%d + l * %d + %d]" % (plan["xlag"], dim, ex.DIRS.index(f[-1]))
+            if f.startswith("coordinate_") and kind == ("cur", 0):
+                return "E[%d + l * %d + %d]" % (plan["xpos"], dim, ex.DIRS.index(f[-1]))
+            return "E[%d + l]" % plan["src_off"][(f, kind)]
+
+        def tag_of(f, kind):
+            return "%s_%s" % (f, "_".join(str(k) for k in kind))
+        fused = set()
+        if self.tensor_points:
+            # ONE loop over the 27 nodes for the tangents and every Q27 / position quantity; psi_l and its local derivatives are built
+            # from the 1D factors of the Gauss point (psi_l = a_i b_j c_k, l = i + 3j + 9k)
+            geos = [("xpos", "gg")] + ([("xlag", "ggL")] if plan["need_lagr"] else [])
+            for (src, gname) in geos:
+                w("      double %s;" % ", ".join("t_%s%d%d = 0.0" % (gname, a, i) for a in range(dim) for i in range(dim)))
+            for (f, kind), derivs in needed.items():
+                if code.fields[f].space == "C1":
+                    continue
+                fused.add((f, kind))
+                tag = tag_of(f, kind)
+                decl = (["v_%s = 0.0" % tag] if "d0" in derivs else []) + (["s%d_%s = 0.0" % (b, tag) for b in range(dim)] if any(d != "d0" for d in derivs) else [])
+                w("      double %s;" % ", ".join(decl))
+            w("      {")
+            w("        const double* t1 = s_t1d + ipt * 18;")
+            w("        const double fa0 = t1[0], fa1 = t1[1], fa2 = t1[2], fda0 = t1[3], fda1 = t1[4], fda2 = t1[5];")
+            w("        const double fb0 = t1[6], fb1 = t1[7], fb2 = t1[8], fdb0 = t1[9], fdb1 = t1[10], fdb2 = t1[11];")
+            w("        #pragma unroll 1")
+            w("        for (int kk = 0; kk < 3; ++kk)")
+            w("        {")
+            w("          const double fc = t1[12 + kk], fdc = t1[15 + kk];")
+            for jj in range(3):
+                w("          { const double bc = fb%d * fc, dbc = fdb%d * fc, bdc = fb%d * fdc;" % (jj, jj, jj))
+                for ii in range(3):
+                    w("            { const int l = %d + 9 * kk; const double psi = fa%d * bc, d0 = fda%d * bc, d1 = fa%d * dbc, d2 = fa%d * bdc; (void)psi;" % (ii + 3 * jj, ii, ii, ii, ii))
+                    for (src, gname) in geos:
+                        for i in range(dim):
+                            w("              { const double x = E[%d + l * %d + %d]; %s }" % (plan[src], dim, i, " ".join("t_%s%d%d += x * d%d;" % (gname, a, i, a) for a in range(dim))))
+                    for (f, kind), derivs in needed.items():
+                        if (f, kind) not in fused:
+                            continue
+                        tag = tag_of(f, kind)
+                        upd = (["v_%s += u * psi;" % tag] if "d0" in derivs else []) + (["s%d_%s += u * d%d;" % (b, tag, b) for b in range(dim)] if any(d != "d0" for d in derivs) else [])
+                        w("              { const double u = %s; %s }" % (src_of(f, kind), " ".join(upd)))
+                    w("            }")
+                w("          }")
+            w("        }")
+            w("      }")
+        self._emit_geometry(o, plan, "xpos", "gg", "detE", sums_done=self.tensor_points)
         if plan["need_lagr"]:
-            self._emit_geometry(o, plan, "xlag", "ggL", "detL")
+            self._emit_geometry(o, plan, "xlag", "ggL", "detL", sums_done=self.tensor_points)
         w("      const double dx = c_w[ipt] * detE;")
         if plan["need_lagr"]:
             w("      const double dX = c_w[ipt] * detL;")
@@ -981,10 +1043,6 @@ class CudaEmitter:
         for k, p in enumerate(code.global_params):
             names[code._param_syms[p]] = "a.params[%d]" % k
         # local-derivative sums per (field, kind)
-        needed: Dict[Tuple[str, tuple], set] = {}
-        for at in form.atoms:
-            kind = ("dt", at.dt_order, at.scheme) if at.dt_order else ("cur", at.past)
-            needed.setdefault((at.field, kind), set()).add(at.deriv)
         for (f, kind), derivs in needed.items():
             fld = code.fields[f]
             nn = self._nnode_space(fld.space)
@@ -998,20 +1056,21 @@ class CudaEmitter:
             tag = "%s_%s" % (f, "_".join(str(k) for k in kind))
             want_val = "d0" in derivs
             want_grad = any(d != "d0" for d in derivs)
-            decl = []
-            if want_val:
-                decl.append("v_%s = 0.0" % tag)
-            if want_grad:
-                decl += ["s%d_%s = 0.0" % (b, tag) for b in range(dim)]
-            w("      double %s;" % ", ".join(decl))
-            w("      #pragma unroll%s" % self._node_unroll(nn))
-            w("      for (int l = 0; l < %d; ++l) { const double u = %s;" % (nn, srcexpr))
-            if want_val:
-                w("        v_%s += u * %s[l];" % (tag, ps))
-            if want_grad:
-                for b in range(dim):
-                    w("        s%d_%s += u * %s[l * %d + %d];" % (b, tag, dp, dim, b))
-            w("      }")
+            if (f, kind) not in fused:
+                decl = []
+                if want_val:
+                    decl.append("v_%s = 0.0" % tag)
+                if want_grad:
+                    decl += ["s%d_%s = 0.0" % (b, tag) for b in range(dim)]
+                w("      double %s;" % ", ".join(decl))
+                w("      #pragma unroll%s" % self._node_unroll(nn))
+                w("      for (int l = 0; l < %d; ++l) { const double u = %s;" % (nn, srcexpr))
+                if want_val:
+                    w("        v_%s += u * %s[l];" % (tag, ps))
+                if want_grad:
+                    for b in range(dim):
+                        w("        s%d_%s += u * %s[l * %d + %d];" % (b, tag, dp, dim, b))
+                w("      }")
             for d in sorted(derivs):
                 at = AtomInfo(f, kind[1] if kind[0] == "dt" else 0, kind[2] if kind[0] == "dt" else "", d, kind[1] if kind[0] == "cur" else 0)
                 sym = code.atom_symbol(at)
@@ -1057,19 +1116,20 @@ class CudaEmitter:
         loop (> 255 registers, accumulators of phase 2 end up in local memory), so the loop is unrolled by 3"""
         return "" if nn <= 9 else " %d" % int(os.environ.get("PB2_NODE_UNROLL", "3"))
 
-    def _emit_geometry(self, o: List[str], plan, src: str, gname: str, detname: str):
+    def _emit_geometry(self, o: List[str], plan, src: str, gname: str, detname: str, sums_done: bool = False):
         """Restates fill_shape_info_at_s for el_dim==nodal_dim (src/elements.cpp:3604-3626 tangents, :3677-3703 2D
         metric/inverse, :3804-3836 3D) with the same operation order; stores gab_gai[b][i] to the point block."""
         dim, NN = self.dim, self.NN
         w = o.append
         t = "t_" + gname
-        w("      double %s;" % ", ".join("%s%d%d = 0.0" % (t, a, i) for a in range(dim) for i in range(dim)))
-        w("      #pragma unroll%s" % self._node_unroll(NN))
-        w("      for (int l = 0; l < %d; ++l) {" % NN)
-        for i in range(dim):
-            for a in range(dim):
-                w("        %s%d%d += E[%d + l * %d + %d] * dp2[l * %d + %d];" % (t, a, i, plan[src], dim, i, dim, a))
-        w("      }")
+        if not sums_done:
+            w("      double %s;" % ", ".join("%s%d%d = 0.0" % (t, a, i) for a in range(dim) for i in range(dim)))
+            w("      #pragma unroll%s" % self._node_unroll(NN))
+            w("      for (int l = 0; l < %d; ++l) {" % NN)
+            for i in range(dim):
+                for a in range(dim):
+                    w("        %s%d%d += E[%d + l * %d + %d] * dp2[l * %d + %d];" % (t, a, i, plan[src], dim, i, dim, a))
+            w("      }")
         for al in range(dim):
             for be in range(dim):
                 terms = ["%s%d%d * %s%d%d" % (t, al, i, t, be, i) for i in range(dim)]
