@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from problems import csr_to_sorted, make_oracle, make_problem  # noqa: E402
 
-for kind, N in [("poisson", 5), ("ns_unsteady", 4), ("heat3d", 2), ("ale", 4)]:
+for kind, N in [("poisson", 5), ("ns_unsteady", 4), ("heat3d", 2), ("ale", 4), ("ns_axi_swirl", 3), ("ale_axi_obs", 3), ("heat3d_obs", 2)]:
     pb = make_problem(kind, N)
     op = make_oracle(pb)
     r, mats = op.assemble(flag=2)
@@ -23,5 +23,7 @@ for kind, N in [("poisson", 5), ("ns_unsteady", 4), ("heat3d", 2), ("ale", 4)]:
         g[key + "_nnz"] = int(A.nnz)
         g[key + "_l1"] = float(abs(A).sum())
         g[key + "_matvec_l1"] = float(np.abs(A @ v).sum())
+    if pb["code"].integral_expressions:
+        g["integrals"] = op.evaluate_integral_expressions()
     json.dump(g, open(os.path.join(HERE, "%s_%d.json" % (kind, N)), "w"), indent=1)
     print(g)

@@ -181,7 +181,7 @@ def test_bdf_weights_and_degraded_start():
     op.close()
 
 
-@pytest.mark.parametrize("kind,N", [("poisson", 5), ("ns_unsteady", 4), ("heat3d", 2), ("ale", 4)])
+@pytest.mark.parametrize("kind,N", [("poisson", 5), ("ns_unsteady", 4), ("heat3d", 2), ("ale", 4), ("ns_axi_swirl", 3), ("ale_axi_obs", 3), ("heat3d_obs", 2)])
 def test_golden_vectors(kind, N):
     """Committed fixtures (tests/golden/make_golden.py): checksums of residual/Jacobian/mass matrix of the oracle.
     They were generated by the oracle itself (the reference cannot run here), so they pin regressions, not parity."""
@@ -199,6 +199,8 @@ def test_golden_vectors(kind, N):
         assert abs(abs(A).sum() - gold[key + "_l1"]) <= 1e-11 * max(gold[key + "_l1"], 1e-300)
         v = np.cos(np.arange(n))
         assert abs(np.abs(A @ v).sum() - gold[key + "_matvec_l1"]) <= 1e-10 * max(gold[key + "_matvec_l1"], 1e-300)
+    for k, val in gold.get("integrals", {}).items():
+        assert abs(op.evaluate_integral_expressions()[k] - val) <= 1e-12 * max(abs(v_) for v_ in gold["integrals"].values())
     op.close()
 
 
