@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- element residual+Jacobian assemblies/s of the B200 assembly engine (BASELINE.json metric).
 
-One "step" = one full residual+Jacobian assembly (flag 1) of the workload mesh: gather -> generated batched kernels
-(one launch per colour) -> coloured scatter into the fixed CSR pattern.  Pattern/maps/colouring are setup and are
-not timed (DESIGN.md "Measurement"; the reference's Jacobian_setup_time includes its per-assembly pattern build).
+One "step" = one full residual+Jacobian assembly (flag 1) of the workload mesh: ONE persistent, warp-specialised launch of the
+generated routine (gather -> points -> contraction -> coloured scatter into the fixed CSR pattern; DESIGN.md sections 2-3), plus one
+pack and one add kernel per neighbour and a grouped NCCL send/recv when the mesh is split over several GPUs.  Pattern, position maps
+and schedule are setup and are not timed (the reference's Jacobian_setup_time includes its per-assembly pattern
+build).  `value` is device-resident (CUDA events, max over ranks); `e2e` is the reference-facing call with pinned host buffers, host
+dof vector in and host residual / CSR values out, every step; `cpu_baseline` / `--impl reference` time the CPU restatement of the
+reference path (oracle/, all host threads) on a bounded sample of the same element class.
 
   python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload ns_cavity|heat3d|poisson] [--n SIZE]
 
 Default workload: BASELINE configs[1], 2D Navier-Stokes lid-driven cavity, Taylor-Hood Q9/Q4, 1024x1024 elements.
---impl reference times the CPU restatement of the reference path (oracle/, all host threads) on a bounded sample.
 """
 import argparse
 import ctypes
