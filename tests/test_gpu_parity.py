@@ -202,6 +202,44 @@ def test_edge_cases_single_element_everything_pinned_no_elements():
 
 
 @pytest.mark.gpu
+def test_newton_solve_through_the_reference_facing_call():
+    """Problem.solve()'s loop with the GPU assembler behind it: every iteration hands the host dof vector to assemble_host and gets the
+    host residual and CSR values back (get_residuals_and_jacobian contract), SuperLU solves on the host.  Same iteration count and
+    residual history as the oracle-driven loop, same converged flow."""
+    from scipy.sparse import csr_matrix
+    from test_oracle import _cavity, newton_cavity
+    pb = _cavity(8)
+    n = pb["dofmap"].n_dof
+    eq = pb["dofmap"].node_eqn
+    m = eq >= 0
+    op = make_oracle(pb)
+
+    def set_dofs_cpu(U):
+        v = pb["vals"][0].copy()
+        v[m] = U[eq[m]]
+        op.update_values(0, v)
+
+    def assemble_cpu():
+        r, mats = op.assemble(flag=1)
+        return r, csr_to_sorted(n, *mats[0])
+    U_ref, hist_ref = newton_cavity(pb, assemble_cpu, set_dofs_cpu)
+    asm = make_gpu(pb)
+    state = {}
+
+    def assemble_gpu():
+        r, jac, _ = asm.assemble_host(state["U"], 1)
+        return r, csr_matrix((jac, asm.indices, asm.indptr), shape=(n, n))
+    U, hist = newton_cavity(pb, assemble_gpu, lambda U_: state.__setitem__("U", U_))
+    assert len(hist) == len(hist_ref) and hist[-1] < 1e-10
+    assert np.abs(U - U_ref).max() <= 1e-9 * np.abs(U_ref).max()
+    for a, b in zip(hist[:-1], hist_ref[:-1]):
+        assert abs(a - b) <= 1e-6 * max(b, 1e-12) + 1e-12
+    res, A = asm.get_residuals_and_jacobian(True)            # the CustomAssemblyBase entry point on the converged state
+    assert np.abs(res).max() < 1e-10 and A.shape == (n, n) and A.indptr.dtype == np.int32 and A.indices.dtype == np.int32
+    op.close(); asm.close()
+
+
+@pytest.mark.gpu
 def test_invalidate_rebuild_and_shift_time_values():
     """the packer's life cycle (SURVEY N-a): invalidate_cache() after a renumbering makes the next assembly fail loudly until
     rebuild(mesh, dofmap) re-packs (same compiled class, new pattern) -- results equal a fresh assembler's and the oracle's;

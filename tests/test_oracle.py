@@ -271,3 +271,63 @@ def test_integral_expressions_analytic_pins():
     with pytest.raises(RuntimeError):
         from pyoomph_b200.expressions import testfunction
         FiniteElementCode("Quad2dC2", PoissonEquation() + IntegralObservables(bad=lambda: testfunction("u")), name="bad").integral_form()
+
+
+def _cavity(N):
+    """lid-driven cavity of BASELINE config 2 at Re = 100: u = 1 on the lid, no slip elsewhere, pressure pinned at node 0"""
+    pb = make_problem("ns", N)
+    mesh, code = pb["mesh"], pb["code"]
+    vals = np.zeros_like(pb["vals"])
+    vals[0][mesh.boundaries["top"], code.fields["velocity_x"].index] = 1.0
+    pb["vals"] = vals
+    return pb
+
+
+def newton_cavity(pb, assemble, set_dofs, max_iter=12):
+    """Problem.solve()'s Newton loop (oomph Problem::newton_solve): U <- U - J^-1 R with SuperLU, until max|R| < 1e-10"""
+    from scipy.sparse.linalg import spsolve
+    eq = pb["dofmap"].node_eqn
+    m = eq >= 0
+    U = np.zeros(pb["dofmap"].n_dof)
+    U[eq[m]] = pb["vals"][0][m]
+    history = []
+    for _ in range(max_iter):
+        set_dofs(U)
+        r, A = assemble()
+        history.append(float(np.abs(r).max()))
+        if history[-1] < 1e-10:
+            break
+        U = U - spsolve(A.tocsc(), r)
+    return U, history
+
+
+def test_newton_solve_of_the_cavity_converges_quadratically():
+    """end-to-end pin of residual AND Jacobian (sign conventions, consistency): Newton's method on the lid-driven cavity converges
+    quadratically only with the exact Jacobian; the converged flow has the primary vortex (negative u on the lower half of the
+    vertical centre line) and is divergence free in the weak sense (continuity rows of the residual vanish)."""
+    N = 8
+    pb = _cavity(N)
+    op = make_oracle(pb)
+    n = pb["dofmap"].n_dof
+    eq = pb["dofmap"].node_eqn
+    m = eq >= 0
+
+    def set_dofs(U):
+        v = pb["vals"][0].copy()
+        v[m] = U[eq[m]]
+        op.update_values(0, v)
+
+    def assemble():
+        r, mats = op.assemble(flag=1)
+        return r, csr_to_sorted(n, *mats[0])
+    U, hist = newton_cavity(pb, assemble, set_dofs)
+    assert hist[-1] < 1e-10 and len(hist) <= 9
+    tail = [h for h in hist if h < 1e-2]
+    assert len(tail) >= 2 and tail[1] <= 50 * tail[0] ** 2 + 1e-12       # quadratic once close
+    ux = pb["vals"][0][:, pb["code"].fields["velocity_x"].index].copy()
+    mx = m[:, pb["code"].fields["velocity_x"].index]
+    ux[mx] = U[eq[mx, pb["code"].fields["velocity_x"].index]]
+    lat = pb["mesh"].node_lattice
+    centre_low = (lat[:, 0] == N) & (lat[:, 1] > 0) & (lat[:, 1] < N)
+    assert ux[centre_low].min() < -0.05
+    op.close()
