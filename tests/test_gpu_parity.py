@@ -240,6 +240,47 @@ def test_newton_solve_through_the_reference_facing_call():
 
 
 @pytest.mark.gpu
+def test_bdf2_time_stepping_of_config3_matches_the_oracle_driven_loop():
+    """BASELINE config 3 as a time loop (Problem.run's unsteady_newton_solve): per step shift the history (device-side on the GPU), set the
+    BDF weights (first step degraded to BDF1, src/elements.cpp:4611), one Newton solve of the linear problem; three steps with varying
+    dt, GPU-assembled against oracle-assembled, same SuperLU: same trajectory."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.linalg import spsolve
+    pb = make_problem("heat3d", 3)
+    n = pb["dofmap"].n_dof
+    eq = pb["dofmap"].node_eqn
+    m = eq >= 0
+    start = pb["vals"][0].copy()
+    pb["vals"] = np.stack([start, start, start])          # at rest before the first step
+    op, asm = make_oracle(pb), make_gpu(pb)
+    hist = [start.copy(), start.copy(), start.copy()]     # oracle side: nodal values per history level
+    U_gpu = np.zeros(n); U_gpu[eq[m]] = start[m]
+    t, dts = 0.0, [0.01, 0.012, 0.008]
+    for step, dt in enumerate(dts):
+        dtprev = dts[step - 1] if step else dt
+        t += dt
+        # --- oracle-driven step
+        hist = [hist[0].copy(), hist[0], hist[1]]
+        for lvl in range(3):
+            op.update_values(lvl, hist[lvl])
+        op.set_unsteady(t, dt, dtprev, step)
+        r, mats = op.assemble(flag=1)
+        U = np.zeros(n); U[eq[m]] = hist[0][m]
+        U -= spsolve(csr_to_sorted(n, *mats[0]).tocsc(), r)
+        hist[0][m] = U[eq[m]]
+        # --- GPU-driven step: nothing but the dof vector crosses the host link
+        asm.shift_time_values()
+        asm.set_unsteady(t, dt, dtprev, step)
+        rg, jac, _ = asm.assemble_host(U_gpu, 1)
+        U_gpu = U_gpu - spsolve(csr_matrix((jac, asm.indices, asm.indptr), shape=(n, n)).tocsc(), rg)
+        asm.set_dofs(U_gpu)
+        assert np.abs(U_gpu - U).max() <= 1e-10 * np.abs(U).max(), step
+    rg, _, _ = asm.assemble_host(None, 0)                 # linear problem: the step's residual is gone after one solve
+    assert np.abs(rg).max() <= 1e-9 * np.abs(r).max()
+    op.close(); asm.close()
+
+
+@pytest.mark.gpu
 def test_invalidate_rebuild_and_shift_time_values():
     """the packer's life cycle (SURVEY N-a): invalidate_cache() after a renumbering makes the next assembly fail loudly until
     rebuild(mesh, dofmap) re-packs (same compiled class, new pattern) -- results equal a fresh assembler's and the oracle's;
