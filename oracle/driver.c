@@ -784,8 +784,17 @@ double oracle_assemble(void *h, int which, int param, unsigned flag, double *res
         residuals[i] += res_t[th][i];
         for (int m = 0; m < nmat; m++)
         {
-          Row *r = &rows[th * 2 + m][i];
-          for (int k = 0; k < r->n; k++) row_add(&rows[m][i], r->p[k].col, r->p[k].val);
+          Row *r = &rows[th * 2 + m][i], *dst = &rows[m][i];
+          if (r->n == 0) { free(r->p); continue; }
+          if (dst->n == 0)
+          {
+            /* the row has been touched by no earlier range (true for all rows but those of the interface nodes between two element
+             * ranges): adopt it as it is -- same entries, same order as merging it entry by entry */
+            free(dst->p);
+            *dst = *r;
+            continue;
+          }
+          for (int k = 0; k < r->n; k++) row_add(dst, r->p[k].col, r->p[k].val);
           free(r->p);
         }
       }
