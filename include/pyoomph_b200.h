@@ -58,7 +58,7 @@ void pb2_problem_free(pb2_problem *p);
 /* pattern of the assembled matrix (host memory owned by the problem): CRDoubleMatrix row_start/column_index */
 int pb2_problem_pattern(pb2_problem *p, const int **row_start, const int **column_index, long long *nnz, long long *n_rows);
 int pb2_problem_num_colours(pb2_problem *p);
-int pb2_problem_num_launches(pb2_problem *p); /* kernel launches per assembly: chunks x colours */
+int pb2_problem_num_launches(pb2_problem *p); /* tiles (= patch colours, device-side gates) one persistent launch walks through */
 
 /* nodal data, host -> device.  t = history index (0 current). */
 int pb2_problem_set_nodal_values(pb2_problem *p, int t, const double *values /*[n_node][nval]*/);

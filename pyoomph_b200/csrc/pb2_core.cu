@@ -152,7 +152,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   memset(p->params, 0, sizeof(p->params));
   if (ci.moving_nodes && !m->pos_eqn)
   {
-    delete p;
+    pb2_problem_free(p); // releases whatever has been uploaded so far
     return fail("element class has position dofs but the mesh gives no pos_eqn");
   }
   if (m->n_elem * (long long)ci.ndof_el * ci.ndof_el > 0x7fffffffLL * 2)
@@ -174,7 +174,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
     while (c < 64 && (used >> c & 1)) c++;
     if (c == 64)
     {
-      delete p;
+      pb2_problem_free(p); // releases whatever has been uploaded so far
       return fail("more than 64 colours needed");
     }
     colour[e] = c;
@@ -198,7 +198,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
       patch_of[e] = m->elem_patch[e];
       if (patch_of[e] < 0)
       {
-        delete p;
+        pb2_problem_free(p); // releases whatever has been uploaded so far
         return fail("negative patch id");
       }
       npatch = std::max(npatch, patch_of[e] + 1);
@@ -271,7 +271,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
       while (c < 64 && (used >> c & 1)) c++;
       if (c == 64)
       {
-        delete p;
+        pb2_problem_free(p); // releases whatever has been uploaded so far
         return fail("more than 64 patch colours needed");
       }
       pcolour[q] = c;
@@ -386,7 +386,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   {
     if (m->extra_rows[i] < 0 || m->extra_rows[i] >= nrow || m->extra_cols[i] < 0 || m->extra_cols[i] >= nrow)
     {
-      delete p;
+      pb2_problem_free(p); // releases whatever has been uploaded so far
       return fail("extra pattern entry out of range");
     }
     ex_start[m->extra_rows[i] + 1]++;
@@ -428,7 +428,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
       for (long long r = 0; r < nrow; r++) tot += p->row_start[r + 1];
       if (tot >= 0x7fffffffLL)
       {
-        delete p;
+        pb2_problem_free(p); // releases whatever has been uploaded so far
         return fail("nnz exceeds int32 CSR indexing");
       }
       for (long long r = 0; r < nrow; r++) p->row_start[r + 1] += p->row_start[r];
@@ -493,7 +493,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
       p->n_untouched = (long long)unt.size();
       if (upload(&p->d_untouched, unt))
       {
-        delete p;
+        pb2_problem_free(p); // releases whatever has been uploaded so far
         return 1;
       }
     }
@@ -518,7 +518,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   p->map_bits = maxlen < 127 ? 8 : 16;
   if (maxlen >= 32767)
   {
-    delete p;
+    pb2_problem_free(p); // releases whatever has been uploaded so far
     return fail("CSR rows longer than 32766 entries are not supported by the position map");
   }
   std::vector<int> elem_rowstart((size_t)ne * nd);
@@ -626,6 +626,7 @@ extern "C" void pb2_problem_free(pb2_problem *p)
   cudaFree(p->d_hessM);
   cudaFree(p->d_row_start);
   cudaFree(p->d_col_index);
+  cudaFree(p->d_debug);
   for (auto &b : p->batch_tables)
   {
     cudaFree(b.d_batch_elem);
