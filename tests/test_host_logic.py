@@ -172,3 +172,49 @@ def test_multi_assemble_request_groups_launches_and_keeps_request_order():
         MultiAssembleRequest(f).R("nope")
     with pytest.raises(RuntimeError):
         MultiAssembleRequest(f).dRdp("nu")
+
+
+def test_axisymmetric_operators_match_the_reference_formulas():
+    """AxisymmetricCoordinateSystem against pyoomph/expressions/coordsys.py:386-537 written out by hand: measure 2 pi r dx, scalar
+    gradient (d/dr, d/dz, 0), vector gradient with the u_r/r (and swirl) entries, divergence d_r u_r + u_r/r + d_z u_z, tensor
+    divergence; Cartesian operators on the zero-padded vectors of an axisymmetric code (the ALE mesh equations); coordsys overrides."""
+    import sympy as sp
+    from pyoomph_b200 import expressions as ex
+    from pyoomph_b200.codegen import Equations, FiniteElementCode
+    seen = {}
+
+    class Probe(Equations):
+        def define_fields(self):
+            self.define_vector_field("velocity", "C2", dim=3)
+            self.define_scalar_field("pressure", "C1")
+
+        def define_residuals(self):
+            u, p = ex.var("velocity"), ex.var("pressure")
+            x, y = ex.EUL[:2]
+            r = ex.var("coordinate_x")
+            assert u.shape == (3, 1) and ex.var("mesh").shape == (3, 1) and ex.var("mesh")[2] == 0
+            assert ex.identity_matrix().shape == (3, 3)
+            G = ex.grad(u)
+            assert G[0, 2] == -u[2] / r and G[2, 2] == u[0] / r and G[1, 2] == 0 and G[2, 0] == sp.diff(u[2], x) and G[0, 1] == sp.diff(u[0], y)
+            assert ex.grad(p) == sp.Matrix([sp.diff(p, x), sp.diff(p, y), 0])
+            assert sp.simplify(ex.div(u) - (sp.diff(u[0], x) + u[0] / r + sp.diff(u[1], y))) == 0
+            T = ex.dyadic(u, u)
+            dT = ex.div(T)
+            assert sp.simplify(dT[0] - (sp.diff(T[0, 0], x) + (T[0, 0] - T[2, 2]) / r + sp.diff(T[1, 0], y))) == 0
+            assert sp.simplify(dT[2] - (sp.diff(T[0, 2], x) + (T[0, 2] - T[2, 0]) / r + sp.diff(T[1, 2], y))) == 0
+            assert ex.weak(p, p) == p * p * 2 * ex.pi * r * ex.DX_EUL
+            assert ex.weak(p, p, coordinate_system=ex.cartesian) == p * p * ex.DX_EUL
+            R = ex.var("lagrangian_x")
+            assert ex.Weak(p, p) == p * p * 2 * ex.pi * R * ex.DX_LAG
+            Gc = ex.grad(ex.var("mesh"), lagrangian=True, coordsys=ex.cartesian)        # 3-vector, 2 coordinates: zero padded 3x3
+            assert Gc.shape == (3, 3) and Gc[2, :] == sp.zeros(1, 3) and Gc[:, 2] == sp.zeros(3, 1)
+            ms = ex.var("mesh")
+            assert ex.div(ms, coordsys=ex.cartesian) == sp.diff(ms[0], x) + sp.diff(ms[1], y)      # (atomised to 1 + 1 later)
+            seen["ok"] = True
+            self.add_residual(ex.weak(ex.div(u), ex.testfunction("pressure")) + ex.weak(ex.grad(u), ex.grad(ex.testfunction("velocity"))))
+    code = FiniteElementCode("Quad2dC2", Probe(), name="probe", coordinate_system="axisymmetric")
+    assert seen["ok"] and code.coordinate_system.get_id_name() == "Axisymmetric"
+    assert [f for f, _ in code.dof_layout()].count("velocity_phi") == 9 and len(code.dof_layout()) == 31
+    # Cartesian codes are untouched: 2-vectors, 2x2 identity, plain dx
+    plain = make_problem("ns", 2)["code"]
+    assert plain.coordinate_system.get_id_name() == "Cartesian" and len(plain.dof_layout()) == 22
