@@ -218,3 +218,26 @@ def test_axisymmetric_operators_match_the_reference_formulas():
     # Cartesian codes are untouched: 2-vectors, 2x2 identity, plain dx
     plain = make_problem("ns", 2)["code"]
     assert plain.coordinate_system.get_id_name() == "Cartesian" and len(plain.dof_layout()) == 22
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on the host alone (the one place besides tests/ where the oracle may execute): ONE JSON line
+    with the keys the driver reads, the e2e object with zero copy bytes, a cpu_baseline describing the run; other ranks stay silent."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--workload", "poisson"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["dtype"] == "f64" and d["vs_baseline"] is None and "workload" in d["config"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    quiet = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
