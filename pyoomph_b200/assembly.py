@@ -146,8 +146,12 @@ class B200Assembly(CustomAssemblyBase):
 
     def __init__(self, code: FiniteElementCode, mesh, dofmap, *, name: str = "elem", device: int = 0,
                  compiler: Optional[CudaCCompiler] = None, emitter_options: Optional[dict] = None,
-                 elements: Optional[np.ndarray] = None, extra_pattern: Optional[Tuple[np.ndarray, np.ndarray]] = None):
+                 elements: Optional[np.ndarray] = None, extra_pattern: Optional[Tuple[np.ndarray, np.ndarray]] = None,
+                 patch_hint=None):
+        """patch_hint: None = the mesh's own `element_patches()` if it has one, else consecutive elements; "spatial" = Morton-ordered
+        patches from the element centroids (meshes.spatial_patches, for meshes without lattice order); or an int array [n_elem]."""
         super().__init__()
+        self._patch_hint = patch_hint
         self.code, self.mesh, self.dofmap = code, mesh, dofmap
         self.lib = load_library()
         self.compiler = compiler or get_ccompiler("cuda")
@@ -169,7 +173,17 @@ class B200Assembly(CustomAssemblyBase):
         self._elem_nodes = np.ascontiguousarray(en, dtype=np.int32)
         self._node_eqn = np.ascontiguousarray(dofmap.node_eqn, dtype=np.int32)
         self._pos_eqn = None if dofmap.pos_eqn is None else np.ascontiguousarray(dofmap.pos_eqn, dtype=np.int32)
-        patches = mesh.element_patches() if hasattr(mesh, "element_patches") else None
+        if isinstance(self._patch_hint, str):
+            if self._patch_hint != "spatial":
+                raise ValueError("unknown patch hint '%s'" % self._patch_hint)
+            from .meshes import spatial_patches
+            patches = spatial_patches(mesh.node_pos, mesh.elem_nodes)
+        elif self._patch_hint is not None:
+            patches = np.asarray(self._patch_hint)
+            if patches.shape != (mesh.elem_nodes.shape[0],):
+                raise ValueError("patch hint must have one entry per element of the mesh")
+        else:
+            patches = mesh.element_patches() if hasattr(mesh, "element_patches") else None
         if patches is not None:
             patches = patches if elements is None else patches[elements]
             _, patches = np.unique(patches, return_inverse=True)       # dense ids, order preserved

@@ -184,3 +184,24 @@ def assign_equation_numbers(mesh: StructuredMesh, code: FiniteElementCode,
     if pfree is not None:
         return DofMap(np.ascontiguousarray(eq[:, dim:]), np.ascontiguousarray(eq[:, :dim]), n_dof)
     return DofMap(np.ascontiguousarray(eq), None, n_dof)
+
+
+def spatial_patches(node_pos: np.ndarray, elem_nodes: np.ndarray, patch_elems: int = 64) -> np.ndarray:
+    """Locality hint (`pb2_mesh_desc.elem_patch`) for meshes that come without one -- external generators, refined or relabelled
+    meshes: elements are ranked along a Morton (Z-order) curve through their centroids and cut into patches of `patch_elems`
+    consecutive ranks.  Patches are then compact, touch few other patches (few patch colours = few tile gates per assembly) and
+    their interior CSR rows are completed while resident in L2.  Returns the patch id of every element (int32); the element order
+    itself is not changed (the engine keeps its own schedule order)."""
+    pos = np.asarray(node_pos, dtype=np.float64)
+    cen = pos[np.asarray(elem_nodes)].mean(axis=1)                       # [n_elem, dim]
+    lo, hi = cen.min(axis=0), cen.max(axis=0)
+    bits = 20 if pos.shape[1] == 3 else 30
+    q = np.clip(((cen - lo) / np.maximum(hi - lo, 1e-300) * ((1 << bits) - 1)).astype(np.uint64), 0, (1 << bits) - 1)
+    key = np.zeros(cen.shape[0], dtype=np.uint64)
+    dim = pos.shape[1]
+    for b in range(bits):
+        for d in range(dim):
+            key |= ((q[:, d] >> np.uint64(b)) & np.uint64(1)) << np.uint64(b * dim + d)
+    rank = np.empty(cen.shape[0], dtype=np.int64)
+    rank[np.argsort(key, kind="stable")] = np.arange(cen.shape[0])
+    return (rank // max(1, int(patch_elems))).astype(np.int32)

@@ -241,3 +241,35 @@ def test_bench_reference_arm_prints_the_contract_line():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     quiet = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+
+
+def test_spatial_patches_give_compact_patches_on_relabelled_meshes():
+    """the locality hint for meshes without lattice order: Morton-ordered patches touch few other patches, so the greedy patch colouring
+    of the schedule needs a handful of colours where consecutive-element patches of a shuffled mesh need one
+    colour per patch"""
+    from problems import UnstructuredView
+    from pyoomph_b200.meshes import RectangularQuadMesh, CuboidBrickMesh, spatial_patches
+
+    def patch_colours(elem_nodes, patch):
+        npatch = patch.max() + 1
+        node_patches = {}
+        for e, nodes in enumerate(elem_nodes):
+            for nd in nodes:
+                node_patches.setdefault(int(nd), set()).add(int(patch[e]))
+        adj = [set() for _ in range(npatch)]
+        for ps in node_patches.values():
+            for a in ps:
+                adj[a] |= ps
+        col = -np.ones(npatch, dtype=int)
+        for p_ in range(npatch):                     # greedy in patch order, like pb2_problem_create
+            used = {col[q] for q in adj[p_] if q != p_ and col[q] >= 0}
+            c = 0
+            while c in used:
+                c += 1
+            col[p_] = c
+        return col.max() + 1
+    for mesh, size in ((UnstructuredView(RectangularQuadMesh(32), 3), 64), (UnstructuredView(CuboidBrickMesh(12), 4), 64)):
+        hint = spatial_patches(mesh.node_pos, mesh.elem_nodes, size)
+        assert hint.dtype == np.int32 and hint.shape == (mesh.n_elem,) and np.bincount(hint).max() <= size
+        naive = (np.arange(mesh.n_elem) // size).astype(np.int32)
+        assert patch_colours(mesh.elem_nodes, hint) <= 14 and 2 * patch_colours(mesh.elem_nodes, hint) <= patch_colours(mesh.elem_nodes, naive)
