@@ -209,7 +209,6 @@ def main():
         return
 
     from pyoomph_b200.assembly import load_library
-    from problems import make_gpu
     lib = load_library()
     lib.pb2_host_alloc.restype = ctypes.c_void_p
     dist = None

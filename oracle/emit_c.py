@@ -26,7 +26,7 @@ import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
 from pyoomph_b200 import expressions as ex
-from pyoomph_b200.codegen import AtomInfo, FiniteElementCode, TestSlot
+from pyoomph_b200.codegen import AtomInfo, FiniteElementCode
 
 EPS = sp.Symbol("ORACLE__eps", real=True)
 MM = sp.Symbol("ORACLE__partial_t_mass_matrix", real=True)

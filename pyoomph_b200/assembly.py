@@ -12,11 +12,11 @@ from __future__ import annotations
 
 import ctypes
 import os
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 
-from .ccompiler import BaseCCompiler, CudaCCompiler, build_core_library, get_ccompiler
+from .ccompiler import CudaCCompiler, get_ccompiler
 from .codegen import FiniteElementCode
 from .cuda_emitter import CudaEmitter
 

@@ -27,7 +27,7 @@ import sympy as sp
 from sympy.printing.c import C99CodePrinter
 
 from . import expressions as ex
-from .codegen import AtomInfo, FiniteElementCode, ResidualForm, TestSlot
+from .codegen import AtomInfo, FiniteElementCode, ResidualForm
 
 K3 = 0.774596669241483
 K3T = 0.774596662941483   # sic: oomph-lib integral.cc:87-93 (mistyped literal, kept for parity)

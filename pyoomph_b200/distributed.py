@@ -94,7 +94,6 @@ def build_partition(mesh, dofmap: DofMap, rank: int, world: int) -> Partition:
         raise RuntimeError("ownership is inconsistent: a dof owned by rank %d is not touched by its elements" % rank)
     halo_new = np.sort(touched_new[~own_mask])
     l2g = np.concatenate([owned_new, halo_new]).astype(np.int64)
-    local_of_new = {}
     loc = np.full(dofmap.n_dof, -1, dtype=np.int64)
     loc[l2g] = np.arange(l2g.size)                             # indexed by NEW global number
     def localise(eq):

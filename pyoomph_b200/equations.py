@@ -11,8 +11,8 @@ Scaling/non-dimensionalisation factors of the reference are all 1 here (no units
 from __future__ import annotations
 
 from .codegen import Equations
-from .expressions import (Weak, cartesian, contract, div, dot, grad, identity_matrix, material_derivative, partial_t,
-                          rational_num, sym, testfunction, trace, var, var_and_test, weak)
+from .expressions import (Weak, cartesian, div, grad, identity_matrix, material_derivative, partial_t, rational_num, sym, trace, var,
+                          var_and_test, weak)
 
 
 class PoissonEquation(Equations):

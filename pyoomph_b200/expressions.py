@@ -15,7 +15,7 @@ turns into the coefficient form the CUDA kernels (and, independently, the CPU or
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Sequence, Tuple, Union
+from typing import List, Optional, Sequence, Union
 
 import sympy as sp
 from sympy.core.function import AppliedUndef

@@ -17,7 +17,7 @@ sizes, so the same *ordering rules* are applied here with vectorise
 from __future__ import annotations
 
 import dataclasses
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, Iterable, Optional, Sequence, Tuple
 
 import numpy as np
 
