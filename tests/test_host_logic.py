@@ -273,3 +273,24 @@ def test_spatial_patches_give_compact_patches_on_relabelled_meshes():
         assert hint.dtype == np.int32 and hint.shape == (mesh.n_elem,) and np.bincount(hint).max() <= size
         naive = (np.arange(mesh.n_elem) // size).astype(np.int32)
         assert patch_colours(mesh.elem_nodes, hint) <= 14 and 2 * patch_colours(mesh.elem_nodes, hint) <= patch_colours(mesh.elem_nodes, naive)
+
+
+def test_bench_kernels_fit_the_sm_without_spills():
+    """resource check of the cross-compiled sm_100a kernels the bench lines are measured on (ptxas -v log kept next to the plugin):
+    the flag-1 kernels of configs 2 and 3 use no local memory (a spill in the contraction costs 15 % of all instructions,
+    profiles/r01_notes.md), stay within the 65 536-register file at their block size and within 227 KB of shared memory."""
+    from pyoomph_b200.ccompiler import get_ccompiler
+    from pyoomph_b200.cuda_emitter import CudaEmitter
+    cc = get_ccompiler("cuda")
+    for kind, kernel in (("ns", "pb2_ns_r0_f1"), ("heat3d", "pb2_heat3d_r0_f1")):
+        code = make_problem(kind, 2)["code"]
+        em = CudaEmitter(code, code.name)
+        so = cc.compile_code(em.emit(), code.name)
+        log = open(so[:-3] + ".log").read()
+        m = re.search(r"Compiling entry function '%s'.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads.*?Used (\d+) registers" % kernel, log, re.S)
+        assert m, kernel
+        stack, st, ld, regs = (int(x) for x in m.groups())
+        epb, threads, smem = em._kernel_cfg[kernel]
+        assert (stack, st, ld) == (0, 0, 0), (kernel, stack, st, ld)
+        assert regs * threads <= 65536 and smem <= 227 * 1024 and threads % 32 == 0 and 2 <= epb <= 63
+        assert "sm_100a" in log
