@@ -184,6 +184,9 @@ class CudaEmitter:
         # ... and phase 1 (geometry + interpolation of the Q27 / position fields) in ONE node loop with psi_l, dpsi_l built from the same
         # 1D factors: 18 table loads per point instead of one per node, table and quantity
         self.tensor_points = self.dim == 3 and os.environ.get("PB2_TP3D_POINTS", "1") != "0"
+        # round-2 experiment (off: compiled and algebra-checked on the CPU only, not yet run on a GPU): sum factorisation of the column
+        # side over the Gauss points, DESIGN.md section 9 item 4
+        self.sum_factorise = self.tensor_columns and os.environ.get("PB2_SUMFAC", "0") == "1"
 
     # ------------------------------------------------------------------ planning
     def _col_index(self, field: str, lnode: int) -> int:
@@ -1260,12 +1263,30 @@ class CudaEmitter:
         w("      {")
         w("        #pragma unroll")
         w("        for (int i = 0; i < %d; ++i) acc[i] = 0.0;" % nacc)
-        if self.ipt_unroll >= NIPT:
-            w("        #pragma unroll")
+        sf = self.sum_factorise and RB == 1 and bool(pairs) and all(code.fields[G].space != "C1" for (F_, G) in pairs)
+        sf_pairs: List[Tuple[str, bool, bool, int]] = []
+        if sf:
+            # Gauss point (sp, sq, sr) = ipt sp*9 + sq*3 + sr; sr is contracted point by point into U, sq and sp after the inner loops
+            w("        #pragma unroll 1")
+            w("        for (int sp = 0; sp < 3; ++sp)")
+            w("        {")
+            for (F_, G_) in pairs:
+                w("          double sfU03_%s_%s[9], sfU1_%s_%s[9], sfU2_%s_%s[9];" % (F_, G_, F_, G_, F_, G_))
+                w("          #pragma unroll")
+                w("          for (int i = 0; i < 9; ++i) { sfU03_%s_%s[i] = 0.0; sfU1_%s_%s[i] = 0.0; sfU2_%s_%s[i] = 0.0; }" % (F_, G_, F_, G_, F_, G_))
+            w("          #pragma unroll")
+            w("          for (int sq = 0; sq < 3; ++sq)")
+            w("          #pragma unroll 1")
+            w("          for (int sr = 0; sr < 3; ++sr)")
+            w("        {")
+            w("          const int ipt = sp * 9 + sq * 3 + sr;")
         else:
-            w("        #pragma unroll %d" % self.ipt_unroll)
-        w("        for (int ipt = 0; ipt < %d; ++ipt)" % NIPT)
-        w("        {")
+            if self.ipt_unroll >= NIPT:
+                w("        #pragma unroll")
+            else:
+                w("        #pragma unroll %d" % self.ipt_unroll)
+            w("        for (int ipt = 0; ipt < %d; ++ipt)" % NIPT)
+            w("        {")
         w("          const double* P = %s + ipt * %d;" % (plan.get("PT_expr", "s_el + el * %d + %d" % (ELS, EL0)), PB))
         need_x = any(s.deriv.startswith("dx") for s in form.slots if s.field in fields) or any(a_.startswith("dx") for (F, G), l in pairs.items() for (_, a_) in l)
         need_X = any(s.deriv.startswith("dX") for s in form.slots if s.field in fields) or any(a_.startswith("dX") for (F, G), l in pairs.items() for (_, a_) in l)
@@ -1275,7 +1296,7 @@ class CudaEmitter:
             w("          " + " ".join("const double ggL%d%d = P[%d];" % (b, i, plan["ggL"] + b * dim + i) for b in range(dim) for i in range(dim)))
         tp = self.tensor_columns and any(code.fields[G].space != "C1" for (F_, G) in pairs)
         if tp:
-            for d in range(3):
+            for d in ((2,) if sf else range(3)):
                 w("          " + " ".join("const double tL%d%d = c_t1d[ipt * 18 + %d]; const double tD%d%d = c_t1d[ipt * 18 + %d];" % (
                     d, n, d * 6 + n, d, n, d * 6 + 3 + n) for n in range(3)))
         w("          #pragma unroll")
@@ -1332,6 +1353,19 @@ class CudaEmitter:
                     tp, td = ("s_psi1", "s_dpsi1") if self.table_source == "smem" else ("c_psi1", "c_dpsi1")
                 else:
                     tp, td = ("s_psi2", "s_dpsi2") if self.table_source == "smem" else ("c_psi2", "c_dpsi2")
+                if sf:
+                    # contraction of the third direction, point by point: U03 collects what is later multiplied by L_b(q) L_a(p),
+                    # U1 by L_b(q) L'_a(p), U2 by L'_b(q) L_a(p)
+                    pf = "%s_%s" % (F, G)
+                    w0 = "W_%s_d0" % pf if "d0" in by_atom else None
+                    for c in range(3):
+                        terms = ([("%s * tL2%d" % (w0, c))] if w0 else []) + ([("Ws2_%s * tD2%d" % (pf, c))] if have_s else [])
+                        w("            sfU03_%s[sq * 3 + %d] += %s;" % (pf, c, " + ".join(terms)))
+                        if have_s:
+                            w("            sfU1_%s[sq * 3 + %d] = fma(Ws0_%s, tL2%d, sfU1_%s[sq * 3 + %d]);" % (pf, c, pf, c, pf, c))
+                            w("            sfU2_%s[sq * 3 + %d] = fma(Ws1_%s, tL2%d, sfU2_%s[sq * 3 + %d]);" % (pf, c, pf, c, pf, c))
+                    sf_pairs.append((pf, have_s, base[(F, G)], nnG))
+                    continue
                 if self.tensor_columns and Gs != "C1":
                     # psi_c = a_i b_j c_k: W0 psi + Ws.dpsi = (W0 a_i + Ws0 a'_i) b_j c_k + a_i (Ws1 b'_j c_k + Ws2 b_j c'_k)
                     pf = "%s_%s" % (F, G)
@@ -1373,6 +1407,30 @@ class CudaEmitter:
                 w("              %s = %s;" % (accname, expr))
         w("          }")
         w("        }")
+        if sf:
+            # second direction (constant factors, q unrolled), then first direction (factors of plane sp)
+            w("          {")
+            w("            const int k = 0; (void)k;")
+            w("            " + " ".join("const double sfLa%d = c_t1d[sp * 162 + %d]; const double sfDa%d = c_t1d[sp * 162 + %d];" % (a_, a_, a_, 3 + a_) for a_ in range(3)))
+            for (pf, have_s, b0, nnG) in sf_pairs:
+                for c in range(3):
+                    for b in range(3):
+                        m_terms = ["sfU03_%s[%d] * c_t1d[%d]" % (pf, q_ * 3 + c, q_ * 54 + 6 + b) for q_ in range(3)]
+                        if have_s:
+                            m_terms += ["sfU2_%s[%d] * c_t1d[%d]" % (pf, q_ * 3 + c, q_ * 54 + 9 + b) for q_ in range(3)]
+                        w("            const double sfM%d%d_%s = %s;" % (b, c, pf, " + ".join(m_terms)))
+                        if have_s:
+                            w("            const double sfV%d%d_%s = %s;" % (b, c, pf, " + ".join("sfU1_%s[%d] * c_t1d[%d]" % (pf, q_ * 3 + c, q_ * 54 + 6 + b) for q_ in range(3))))
+                for c in range(3):
+                    for b in range(3):
+                        for a_ in range(3):
+                            an = "acc[%d + k * %d + %d]" % (b0, nnG, a_ + 3 * b + 9 * c)
+                            e = "fma(sfM%d%d_%s, sfLa%d, %s)" % (b, c, pf, a_, an)
+                            if have_s:
+                                e = "fma(sfV%d%d_%s, sfDa%d, %s)" % (b, c, pf, a_, e)
+                            w("            %s = %s;" % (an, e))
+            w("          }")
+            w("        }")
         w("      }")
         w("    }")
 

@@ -294,3 +294,39 @@ def test_bench_kernels_fit_the_sm_without_spills():
         assert (stack, st, ld) == (0, 0, 0), (kernel, stack, st, ld)
         assert regs * threads <= 65536 and smem <= 227 * 1024 and threads % 32 == 0 and 2 <= epb <= 63
         assert "sm_100a" in log
+
+
+def test_sum_factorised_columns_algebra():
+    """index algebra of the flagged 3D sum-factorised contraction (cuda_emitter, PB2_SUMFAC) with the
+    emitter's own tables and index expressions: contracting the third, second and first direction in turn reproduces the sum over
+    all 27 Gauss points of W0 psi_c + Ws . dpsi_c for every column c."""
+    from pyoomph_b200.cuda_emitter import _lag, gauss_rule, shape_tables
+    kn, _ = gauss_rule(3)
+    psi, dpsi = shape_tables(3, 3, kn)
+    t1 = []
+    for sk in kn:                                  # c_t1d[ipt*18 + d*6 + n] / [.. + 3 + n], as in CudaEmitter._emit_tables
+        for d in range(3):
+            P, D = _lag(3, sk[d])
+            t1 += list(P) + list(D)
+    t1 = np.array(t1)
+    rng = np.random.default_rng(5)
+    W0, Ws = rng.uniform(-1, 1, 27), rng.uniform(-1, 1, (27, 3))
+    ref = np.array([sum(W0[i] * psi[i][c] + sum(Ws[i, b] * dpsi[i][c][b] for b in range(3)) for i in range(27)) for c in range(27)])
+    acc = np.zeros(27)
+    for sp in range(3):
+        U03, U1, U2 = np.zeros(9), np.zeros(9), np.zeros(9)
+        for sq in range(3):
+            for sr in range(3):
+                ipt = sp * 9 + sq * 3 + sr
+                for c in range(3):
+                    tL2, tD2 = t1[ipt * 18 + 12 + c], t1[ipt * 18 + 15 + c]
+                    U03[sq * 3 + c] += W0[ipt] * tL2 + Ws[ipt, 2] * tD2
+                    U1[sq * 3 + c] += Ws[ipt, 0] * tL2
+                    U2[sq * 3 + c] += Ws[ipt, 1] * tL2
+        for c in range(3):
+            for b in range(3):
+                M = sum(U03[q * 3 + c] * t1[q * 54 + 6 + b] + U2[q * 3 + c] * t1[q * 54 + 9 + b] for q in range(3))
+                V = sum(U1[q * 3 + c] * t1[q * 54 + 6 + b] for q in range(3))
+                for a in range(3):
+                    acc[a + 3 * b + 9 * c] += M * t1[sp * 162 + a] + V * t1[sp * 162 + 3 + a]
+    assert np.abs(acc - ref).max() <= 1e-14 * np.abs(ref).max()

@@ -34,4 +34,8 @@ for hint in (None, "spatial"):
     err, missing = compare_matrix(csr_to_sorted(n, asm.indptr, asm.indices, jac), csr_to_sorted(n, *mats[0]))
     print("patch_hint", hint, "tiles", asm.num_launches(), "jac err", err, "missing", missing, "res err", np.abs(r - r_ref).max() / np.abs(r_ref).max())
 PY
+# flagged round-1 experiment: sum-factorised 3D columns (compiled + algebra-checked on the CPU only): parity, then the bench line
+( PB2_SUMFAC=1 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "heat3d or config3" 2>&1 | tail -3
+  PB2_SUMFAC=1 timeout 300 python bench.py --workload heat3d --steps 10 --warmup 3 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | cut -c1-220 ) > $out/sumfac.log 2>&1
+cat $out/sumfac.log
 tail -3 $out/verify.log; cat $out/patch_hint.log | tail -3; cat $out/bench_heat3d.json | cut -c1-200
