@@ -184,6 +184,8 @@ def main():
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle window check of the distributed matrix (N > 1)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads (BASELINE configs 1 and 3) of the default run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,16 +196,21 @@ def main():
     sample_n = {"ns_cavity": 160, "heat3d": 14, "poisson": 256}[args.workload]
 
     if args.impl == "reference":
+        # the reference's CPU path (oracle port: generated-format C plugin + restated element loop + vectors_of_pairs CSR build) on all host
+        # threads; EXACTLY --steps timed assemblies after --warmup untimed ones, each step one assembly of a bounded sample mesh of the
+        # same element class (the full mesh needs minutes per run on the host cores)
         if rank != 0:
             return
-        ne, sec = cpu_run(args.workload, sample_n, max(1, min(args.steps, 5)), 1, cores)
+        ref_n = int(os.environ.get("PB2_REF_SAMPLE_N", {"ns_cavity": 320, "heat3d": 20, "poisson": 512}[args.workload]))
+        ne, sec = cpu_run(args.workload, ref_n, max(1, args.steps), max(0, args.warmup), cores)
         val = ne / sec
         wl = build_label(args.workload, n)
-        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(0, args.warmup),
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl, "sample": "%d elements of the same element class per step" % ne},
+                "config": {"workload": wl},
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": "%s at %d^%d elements, oracle C plugin gcc -O3 -march=native, %d threads" % (args.workload, sample_n, 3 if args.workload == "heat3d" else 2, cores)},
+                                 "sample": "one assembly of %s at %d^%d = %d elements per step (same element class and data as the full workload), oracle C plugin gcc -O3 -march=native, %d threads" % (
+                                     args.workload, ref_n, 3 if args.workload == "heat3d" else 2, ne, cores)},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -215,8 +222,10 @@ def main():
     if world > 1:
         import torch
         import torch.distributed as dist_mod
+        import datetime
         torch.cuda.set_device(local_rank)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a desynchronised collective fails within two minutes instead of sitting in the NCCL watchdog's default ten
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=120))
         dist = dist_mod
     device = local_rank
 
@@ -267,13 +276,27 @@ def main():
 
     sampler = ClockSampler(device)
     sampler.start()                      # nvidia-smi needs a few 100 ms to deliver its first sample: start before the warm-up
+    # Warm-up.  Every step() of a multi-GPU run contains matched NCCL sends/receives, so ALL ranks must run the SAME number of steps:
+    # the count is fixed per group, and whether another group follows (>= 0.6 s of load, so that clocks and the nvidia-smi sampler have
+    # settled) is decided by an all-reduce, never by a rank-local clock.
+    barrier()
     t_w = time.time()
     n_w = 0
-    while n_w < max(3, args.warmup) or time.time() - t_w < 0.6:
-        step()
-        n_w += 1
-        if n_w % 8 == 0:
-            lib.pb2_device_synchronize()
+    group = max(3, args.warmup)
+    while True:
+        for _ in range(group):
+            step()
+        n_w += group
+        lib.pb2_device_synchronize()
+        more = 1.0 if (time.time() - t_w < 0.6 and n_w < 4096) else 0.0
+        if dist is not None:
+            import torch
+            flag_t = torch.tensor([more], device="cuda", dtype=torch.float64)
+            dist.all_reduce(flag_t, op=dist.ReduceOp.MAX)
+            more = float(flag_t.item())
+        if more == 0.0:
+            break
+        group = 16
     barrier()
     note("warm-up done (%d steps)" % n_w)
     launches = 0
@@ -294,6 +317,14 @@ def main():
         ms_step = float(tt.item())
     total_elems = mesh.n_elem
     value = total_elems / (ms_step * 1e-3)
+    exch_max = exch_sum = int(dasm.exchange_bytes) if dasm is not None else 0
+    if dist is not None:
+        import torch
+        et = torch.tensor([float(exch_max)], device="cuda", dtype=torch.float64)
+        es = et.clone()
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        dist.all_reduce(es, op=dist.ReduceOp.SUM)
+        exch_max, exch_sum = int(et.item()), int(es.item())
 
     # ---- end-to-end through the reference-facing call (host buffers, copies inside the timed region)
     e2e = None
@@ -326,34 +357,67 @@ def main():
         # N GPUs: every rank feeds the host dof values of its local rows and reads its owned CSR row block back (N host links);
         # local kernels + the NCCL interface exchange sit between the copies.  A failure on one rank must not desynchronise the
         # collectives: the timing all-reduce below is unconditional.
+        # The calls below contain collectives (the interface exchange), so nothing here is wrapped in try/except: a failure on one rank
+        # ends that process, torchrun ends the others, the run fails loudly instead of leaving peers in an unmatched send/recv.
         import torch
-        sec, h2d, d2h, ksteps = float("nan"), 0, 0, max(1, min(args.steps, 5))
+        ksteps = max(1, min(args.steps, 5))
+        part = dasm.part
+        eq = part.local_dofmap.node_eqn
+        nnz_owned = int(dasm.indptr[dasm.n_owned])
+        with gpu_local_cpus(device):
+            h_dofs = torch.zeros(asm.n_dof, dtype=torch.float64).pin_memory()
+            outb = (torch.zeros(dasm.n_owned, dtype=torch.float64).pin_memory(), torch.zeros(nnz_owned, dtype=torch.float64).pin_memory(), None)
+        m_ = eq >= 0
+        h_dofs.numpy()[eq[m_]] = pb["vals"][0][m_]
+        h2d, d2h = int(asm.n_dof * 8), int((dasm.n_owned + nnz_owned) * 8)
         barrier()
-        try:
-            part = dasm.part
-            eq = part.local_dofmap.node_eqn
-            nnz_owned = int(dasm.indptr[dasm.n_owned])
-            with gpu_local_cpus(device):
-                h_dofs = torch.zeros(asm.n_dof, dtype=torch.float64).pin_memory()
-                outb = (torch.zeros(dasm.n_owned, dtype=torch.float64).pin_memory(), torch.zeros(nnz_owned, dtype=torch.float64).pin_memory(), None)
-            m_ = eq >= 0
-            h_dofs.numpy()[eq[m_]] = pb["vals"][0][m_]
-            h2d, d2h = int(asm.n_dof * 8), int((dasm.n_owned + nnz_owned) * 8)
-            dasm.assemble_host(h_dofs, 1, out=outb)          # warm-up (ends with a device synchronisation, like every call)
-            t0 = time.perf_counter()
-            for _ in range(ksteps):
-                dasm.assemble_host(h_dofs, 1, out=outb)
-            sec = (time.perf_counter() - t0) / ksteps
-        except Exception as exc:      # reported, never silent
-            print("[bench] rank %d: e2e leg failed: %r" % (rank, exc), file=sys.stderr, flush=True)
-        tt = torch.tensor([sec if sec == sec else 1e30, float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+        dasm.assemble_host(h_dofs, 1, out=outb)          # warm-up (ends with a device synchronisation, like every call)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            dasm.assemble_host(h_dofs, 1, out=outb)
+        barrier()
+        sec = (time.perf_counter() - t0) / ksteps
+        tt = torch.tensor([sec, float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
         mx = tt.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(tt, op=dist.ReduceOp.SUM)
-        if float(mx[0].item()) < 1e29:
-            sec = float(mx[0].item())
-            e2e = {"value": total_elems / sec, "unit": UNIT, "h2d_bytes_per_step": int(tt[1].item()), "d2h_bytes_per_step": int(tt[2].item()),
-                   "ms_per_step": sec * 1e3, "steps": ksteps, "note": "bytes summed over ranks; every rank copies its own row block"}
+        sec = float(mx[0].item())
+        e2e = {"value": total_elems / sec, "unit": UNIT, "h2d_bytes_per_step": int(tt[1].item()), "d2h_bytes_per_step": int(tt[2].item()),
+               "ms_per_step": sec * 1e3, "steps": ksteps, "note": "bytes summed over ranks; every rank copies its own row block"}
+
+    # ---- N GPUs: correctness of THIS run's distributed matrix, on the hardware that was timed.  Every rank compares rows of its owned
+    # block inside 4x4-element windows that straddle its partition interfaces (the rows the NCCL exchange completes) and windows in its
+    # interior with the CPU oracle assembled on the window alone (tests/windows.py); worst error and row count are reduced over ranks.
+    mgp = None
+    if dasm is not None and args.workload == "ns_cavity" and not args.no_parity:
+        import torch
+        from problems import make_oracle
+        from windows import check_windows
+        dasm.assemble(flag=1)
+        rb, re_, ip_, gc_, jv_, res_ = dasm.owned_block()
+        wins = []
+        for q in range(1, world):                       # element blocks are x-strips in mesh order: interface q at element column n*q/world
+            ix0 = (n * n * q // world) // n
+            for jy in (0, n // 2 - 2, n - 4, (37 * q) % (n - 4)):
+                wins += [(max(0, min(n - 4, ix0 - 2)), jy), (max(0, min(n - 4, ix0 - 3)), jy), (max(0, min(n - 4, ix0 - 1)), jy)]
+        lo, hi = (n * n * rank // world) // n, (n * n * (rank + 1) // world) // n
+        wins += [(max(0, min(n - 4, (lo + hi) // 2)), n // 3), (max(0, min(n - 4, lo + 1)), 5)]
+        st_ = {}
+        try:          # no collective inside: a failed comparison on one rank is carried into the reduction below, not raised past it
+            worst = check_windows(pb, make_oracle, ip_, gc_, jv_, res_, sorted(set(wins)), w=4, tol=1e-12, new_of_old=dasm.part.new_of_old,
+                                  row_begin=rb, row_end=re_, stats=st_)
+        except AssertionError as exc:
+            print("[bench] rank %d: distributed window parity FAILED: %r" % (rank, exc), file=sys.stderr, flush=True)
+            worst = float("inf")
+        tw = torch.tensor([worst, -float(st_.get("rows", 0))], device="cuda", dtype=torch.float64)
+        tr = torch.tensor([float(st_.get("rows", 0))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tr, op=dist.ReduceOp.SUM)
+        mgp = {"checked": "rows of 4x4-element windows at every partition interface and inside every rank's block against the CPU oracle",
+               "rows_compared": int(tr.item()), "min_rows_on_a_rank": int(-tw[1].item()), "worst_row_scaled_error": float(tw[0].item()),
+               "tolerance": 1e-12, "ok": bool(tw[0].item() <= 1e-12 and -tw[1].item() > 0)}
+        del jv_
 
     if rank != 0:
         if dist is not None:
@@ -365,24 +429,30 @@ def main():
         b_el -= float(info.alg_bytes_per_hist_level) * (info.n_hist_val - 1)   # steady: history levels are not read
     # dominant (only) kernel: the generated ResidualAndJacobian routine, one launch per colour
     achieved = b_el * n_elem_rank / (ms_step * 1e-3) / 1e9
-    traffic = None
-    try:   # DRAM bytes per launch from the committed ncu --set full capture of this very workload (profiles/r01_traffic.json)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        traffic = float(tj["%s:%d" % (args.workload, n)]["traffic_bytes"]) if world == 1 else None
-    except Exception:
-        traffic = None
+    traffic, flops = profile_numbers(args.workload, n) if world == 1 else (None, None)
+    fp64_peak = ctypes.c_double(0.0)
+    if lib.pb2_measure_fp64_peak(device, ctypes.byref(fp64_peak)) != 0:
+        fp64_peak.value = 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "alg_bytes_per_element": b_el, "kernel": "pb2_%s_r0_f1" % pb["code"].name,
-                "launches_per_step": launches // max(1, args.steps), "tiles_per_step": asm.num_launches(), "avg_launch_ms": ms_step / max(1, launches // max(1, args.steps))}
+                "launches_per_step": launches // max(1, args.steps), "tiles_per_step": asm.num_launches(), "avg_launch_ms": ms_step / max(1, launches // max(1, args.steps)),
+                "fp64_peak_tflops": fp64_peak.value or None, "fp64_peak_source": "measured in this run (pb2_measure_fp64_peak: dependent-chain-free DFMA kernel)"}
+    if flops is not None and fp64_peak.value > 0:
+        tf = flops / (ms_step * 1e-3) / 1e12
+        roofline.update({"fp64_tflops": tf, "frac_fp64": tf / fp64_peak.value, "fp64_flops_per_element": flops / n_elem_rank})
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": pb["label"], "elements": int(total_elems), "dofs": int(asm.n_dof), "nnz": int(asm.nnz), "ndof_el": int(info.ndof_el),
                        "colours": asm.num_colours(), "tiles": asm.num_launches(), "cache": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2" % (b_el * n_elem_rank / 1e9),
-                       "setup_s": round(t_setup, 1), "parallelism": "element blocks x%d" % world,
-                       "exchange_bytes_per_step_rank0": int(dasm.exchange_bytes) if dasm is not None else 0},
+                       "setup_s": round(t_setup, 1), "pattern_setup_s": round(asm.setup_seconds, 2),
+                       "ms_per_step_incl_pattern_setup": ms_step + asm.setup_seconds * 1e3,
+                       "parallelism": "element blocks x%d" % world,
+                       "exchange_bytes_per_step_max_rank": exch_max, "exchange_bytes_per_step_all_ranks": exch_sum},
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches)}
     if e2e is not None:
         line["e2e"] = e2e
+    if mgp is not None:
+        line["multi_gpu_parity"] = mgp
     if not args.no_cpu_baseline and world == 1:
         ne, sec = cpu_run(args.workload, sample_n, 2, 1, cores)
         line["cpu_baseline"] = {"value": ne / sec, "unit": UNIT, "cores": cores, "kind": "port",
@@ -392,9 +462,74 @@ def main():
         # the port's element loop scales with threads, its vectors-of-pairs merge does not: perfect scaling of the 1-thread rate is the
         # most any CPU run of this port could reach on this box
         line["cpu_baseline"]["value_1core_times_cores"] = ne1 / sec1 * cores
+    if world == 1 and not args.no_extra and args.workload == "ns_cavity" and not args.n:
+        # BASELINE configs 1 and 3 on the same GPU, so that the driver's record carries them too (config 2 above is the headline)
+        asm.close()
+        line["extra_workloads"] = [run_extra_workload(lib, device, wl_, n_, max(3, min(args.steps, 10)), peak, fp64_peak.value)
+                                   for (wl_, n_) in (("heat3d", 126), ("poisson", 2048))]
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def profile_numbers(workload, n):
+    """DRAM bytes and executed fp64 flops per launch from the committed `ncu --set full` capture of this very workload (profiles/r0X_traffic.json,
+    newest round first); (None, None) when no capture of this workload/size is committed."""
+    for rnd in ("r02", "r01"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "%s_traffic.json" % rnd)))
+            e = tj["%s:%d" % (workload, n)]
+            return float(e["traffic_bytes"]), (float(e["fp64_flops"]) if "fp64_flops" in e else None)
+        except Exception:
+            continue
+    return None, None
+
+
+def run_extra_workload(lib, device, workload, n, steps, peak_hbm, peak_fp64):
+    """One more BASELINE config on the same GPU, device-resident timing only: ms per assembly, elements/s and both roofline fractions."""
+    from pyoomph_b200.assembly import B200Assembly
+    t0 = time.time()
+    pb = build_workload(workload, n)
+    asm = B200Assembly(pb["code"], pb["mesh"], pb["dofmap"], name=pb["code"].name, device=device)
+    for t in range(pb["vals"].shape[0]):
+        asm.set_nodal_values(t, pb["vals"][t])
+    if pb["unsteady"]:
+        from problems import TIME
+        asm.set_unsteady(TIME["t"], TIME["dt"], TIME["dtprev"], TIME["unsteady_steps_done"])
+    t_setup = time.time() - t0
+    t_w, n_w = time.time(), 0
+    while n_w < 3 or (time.time() - t_w < 0.4 and n_w < 2000):
+        asm.assemble(flag=1)
+        n_w += 1
+        if n_w % 4 == 0:
+            lib.pb2_device_synchronize()
+    lib.pb2_device_synchronize()
+    lib.pb2_event_record(2, None)
+    for _ in range(steps):
+        asm.assemble(flag=1)
+    lib.pb2_event_record(3, None)
+    ms = ctypes.c_float()
+    lib.pb2_event_elapsed_ms(2, 3, ctypes.byref(ms))
+    ms_step = ms.value / steps
+    info = asm.info
+    b_el = float(info.alg_bytes_per_elem[1])
+    if not pb["unsteady"]:
+        b_el -= float(info.alg_bytes_per_hist_level) * (info.n_hist_val - 1)
+    ne = pb["mesh"].n_elem
+    hbm = b_el * ne / (ms_step * 1e-3) / 1e9
+    traffic, flops = profile_numbers(workload, n)
+    out = {"workload": pb["label"], "elements": int(ne), "ndof_el": int(info.ndof_el), "nnz": int(asm.nnz), "steps": steps, "ms_per_step": ms_step,
+           "value": ne / (ms_step * 1e-3), "unit": UNIT, "setup_s": round(t_setup, 1), "pattern_setup_s": round(asm.setup_seconds, 2),
+           "roofline": {"bound": "hbm", "achieved": hbm, "peak": peak_hbm, "unit": "GB/s", "frac": hbm / peak_hbm, "alg_bytes_per_element": b_el,
+                        "traffic": traffic, "kernel": "pb2_%s_r0_f1" % pb["code"].name}}
+    if flops is not None and peak_fp64:
+        tf = flops / (ms_step * 1e-3) / 1e12
+        out["roofline"].update({"fp64_tflops": tf, "fp64_peak_tflops": peak_fp64, "frac_fp64": tf / peak_fp64, "fp64_flops_per_element": flops / ne})
+        # the kernel is bounded by whichever floor is higher: HBM time of the algorithmic bytes or fp64-pipe time of the executed flops
+        if tf / peak_fp64 > hbm / peak_hbm:
+            out["roofline"]["bound"] = "fp64"
+    asm.close()
+    return out
 
 
 def build_label(workload, n):

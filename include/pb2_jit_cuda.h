@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 8
+#define PB2_ABI_VERSION 9
 #define PB2_MAX_PARAMS 16
 #define PB2_NTW 7           /* time-stepper storage, MultiTimeStepper (src/timestepper.hpp:37-45) */
 #define PB2_MAX_FIELDS 16
@@ -33,6 +33,10 @@ extern "C" {
 
 /* residual position map encoding: >=0 accumulate at that position, <0 (but not SKIP) first touch: store at ~v */
 #define PB2_MAP_SKIP (-2147483647 - 1)
+
+/* error word written by the kernels (pb2_kernel_args.status) */
+#define PB2_STATUS_GATE_TIMEOUT 1
+#define PB2_GATE_TIMEOUT_NS 20000000000ull
 
 /* time information = what prepare_shape_buffer_for_integration copies per element (src/elements.cpp:4577-4646);
  * here it is one constant block per launch.  The *_degr aliases are resolved by the host. */
@@ -74,6 +78,9 @@ typedef struct pb2_kernel_args
   int *tile_done;             /* [n_tiles]   completion counters, zeroed by the host before the launch */
   int n_batches, n_tiles;
   unsigned long long *debug;  /* NULL, or [64] cycle counters filled by kernels built with PB2_TIMING=1 (development aid) */
+  int *status;                /* [1] device-visible error word, 0 = fine.  PB2_STATUS_GATE_TIMEOUT: a tile gate of the persistent kernel was
+                                 not opened within PB2_GATE_TIMEOUT_NS (blocks not co-resident / a lost block); the waiting warps give up,
+                                 the kernel ends, results are invalid and the host reports the error (never a silent hang) */
   const double *hvec;         /* [n_hvec][n_dof]   Hessian-vector inputs (or NULL) */
   int n_hvec, pad_;
   double *integrals;          /* [n_elem_total][n_integrals]  per-element values of the integral expressions (kind 2 kernels) */

@@ -66,6 +66,8 @@ int pb2_problem_set_nodal_positions(pb2_problem *p, int t, const double *pos /*[
 int pb2_problem_set_lagrangian_positions(pb2_problem *p, const double *pos /*[n_node][dim]*/);
 /* Problem::set_dofs equivalent: scatter a global dof vector (host) into current nodal values / positions on the device */
 int pb2_problem_set_dofs(pb2_problem *p, const double *dofs /*[n_dof]*/);
+/* Problem::set_history_dofs(t, dofs) equivalent (src/pybind/problem.cpp:540): the same scatter into history level t */
+int pb2_problem_set_history_dofs(pb2_problem *p, int t, const double *dofs /*[n_dof]*/);
 /* Problem::shift_time_values on the packed data (device to device): history level t <- level t-1 for the nodal values and, on
  * moving meshes, the nodal positions; level 0 keeps the current values.  Replaces a re-upload of every history level per time step. */
 int pb2_problem_shift_time_values(pb2_problem *p);
@@ -116,6 +118,11 @@ int pb2_event_elapsed_ms(int idx0, int idx1, float *ms);
 int pb2_device_synchronize(void);
 int pb2_device_count(int *n);
 int pb2_flush_l2(int device);
+/* wall time pb2_problem_create spent on colouring, pattern, position maps and upload (the reference's Jacobian_setup_time includes its
+ * per-assembly pattern build, oomph linear_solver.cc:986-1005: reported next to the assembly time) */
+double pb2_problem_setup_seconds(pb2_problem *p);
+/* fp64 roofline denominator measured on this device: DFMA throughput of a dependent-chain-free kernel, in TFLOP/s */
+int pb2_measure_fp64_peak(int device, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -79,8 +79,10 @@ def load_library() -> ctypes.CDLL:
                "pb2_problem_set_time", "pb2_problem_set_parameters", "pb2_problem_assemble", "pb2_problem_device_outputs",
                "pb2_problem_fetch", "pb2_problem_assemble_host", "pb2_problem_num_colours", "pb2_version",
                "pb2_problem_assemble_hessian", "pb2_problem_fetch_hessian", "pb2_problem_hessian_vector_products",
-               "pb2_problem_pack_rows", "pb2_problem_unpack_add", "pb2_problem_eval_integrals", "pb2_problem_shift_time_values"):
+               "pb2_problem_pack_rows", "pb2_problem_unpack_add", "pb2_problem_eval_integrals", "pb2_problem_shift_time_values",
+               "pb2_problem_set_history_dofs", "pb2_measure_fp64_peak"):
         getattr(L, fn).restype = ctypes.c_int
+    L.pb2_problem_setup_seconds.restype = ctypes.c_double
     _LIB = L
     return L
 
@@ -98,6 +100,25 @@ def bdf_weights(dt: float, dtprev: float):
     w2[2] = dt / ((dt + dtprev) * dtprev)
     w1[0] = 1.0 / dt
     w1[1] = -1.0 / dt
+    return w1, w2
+
+
+NSTEPS = 2          # MultiTimeStepper::NSTEPS (src/timestepper.hpp:49): history values 1..2, then the Newmark velocity / acceleration slots
+
+
+def newmark2_weights(dt: float, beta1: float = 0.5, beta2: float = 0.5):
+    """MultiTimeStepper::set_weights, Newmark2 part (/root/reference/src/timestepper.cpp:61-80; NewmarkBeta1 = NewmarkBeta2 = 0.5,
+    src/timestepper.hpp:63).  Returns (first-derivative weights, second-derivative weights); the slots NSTEPS+1 and NSTEPS+2
+    multiply the stored velocity and acceleration of the previous step."""
+    w1, w2 = np.zeros(PB2_NTW), np.zeros(PB2_NTW)
+    w2[0] = 2.0 / (beta2 * dt * dt)
+    w2[1] = -2.0 / (beta2 * dt * dt)
+    w2[NSTEPS + 1] = -2.0 / (dt * beta2)
+    w2[NSTEPS + 2] = (beta2 - 1.0) / beta2
+    w1[0] = beta1 * dt * w2[0]
+    w1[1] = beta1 * dt * w2[1]
+    w1[NSTEPS + 1] = 1.0 + beta1 * dt * w2[NSTEPS + 1]
+    w1[NSTEPS + 2] = dt * (1.0 - beta1) + beta1 * dt * w2[NSTEPS + 2]
     return w1, w2
 
 
@@ -206,9 +227,11 @@ class B200Assembly(CustomAssemblyBase):
         nnz, nrows = ctypes.c_longlong(), ctypes.c_longlong()
         _check(self.lib.pb2_problem_pattern(self.prob, ctypes.byref(rs), ctypes.byref(ci), ctypes.byref(nnz), ctypes.byref(nrows)))
         self.n_dof, self.nnz = int(nrows.value), int(nnz.value)
-        self.indptr = np.ctypeslib.as_array(rs, shape=(self.n_dof + 1,))
+        # numpy-owned copies: the arrays end up inside scipy matrices and exchange lists that outlive rebuild() / close()
+        self.indptr = np.ctypeslib.as_array(rs, shape=(self.n_dof + 1,)).copy()
         # an empty pattern (every dof pinned, or no element on this rank) has no column array at all
-        self.indices = np.ctypeslib.as_array(ci, shape=(self.nnz,)) if self.nnz > 0 else np.zeros(0, dtype=np.int32)
+        self.indices = np.ctypeslib.as_array(ci, shape=(self.nnz,)).copy() if self.nnz > 0 else np.zeros(0, dtype=np.int32)
+        self.setup_seconds = float(self.lib.pb2_problem_setup_seconds(self.prob))
         self.n_elem = self._elem_nodes.shape[0]
         self.param_names = [self.info.param_names[i].value.decode() for i in range(self.info.n_params)]
         self.residual_names = [self.info.residual_names[i].value.decode() for i in range(self.info.n_residuals)]
@@ -268,10 +291,14 @@ class B200Assembly(CustomAssemblyBase):
         v = np.ascontiguousarray(pos, dtype=np.float64)
         _check(self.lib.pb2_problem_set_lagrangian_positions(self.prob, self._dp(v)))
 
-    def set_dofs(self, dofs: np.ndarray):
+    def set_dofs(self, dofs: np.ndarray, t: int = 0):
+        """Problem.set_current_dofs (t = 0) / set_history_dofs(t) on the packed data: dof vector -> nodal values / positions of level t"""
         v = np.ascontiguousarray(dofs, dtype=np.float64)
         assert v.shape == (self.n_dof,)
-        _check(self.lib.pb2_problem_set_dofs(self.prob, self._dp(v)))
+        if t == 0:
+            _check(self.lib.pb2_problem_set_dofs(self.prob, self._dp(v)))
+        else:
+            _check(self.lib.pb2_problem_set_history_dofs(self.prob, t, self._dp(v)))
 
     def set_parameters(self, **values: float):
         for k, v in values.items():
@@ -283,17 +310,25 @@ class B200Assembly(CustomAssemblyBase):
         self.ti = TimeInfo()
         _check(self.lib.pb2_problem_set_time(self.prob, ctypes.byref(self.ti)))
 
-    def set_unsteady(self, t: float, dt: float, dtprev: float, unsteady_steps_done: int, ntstorage: int = 3):
-        """BDF weights + the _degr selection rule of prepare_shape_buffer_for_integration (src/elements.cpp:4611-4626)."""
+    def set_unsteady(self, t: float, dt: float, dtprev: float, unsteady_steps_done: int, ntstorage: Optional[int] = None):
+        """MultiTimeStepper weights (BDF1, BDF2, Newmark2; src/timestepper.cpp:31-80) + the _degr selection rule of
+        prepare_shape_buffer_for_integration (src/elements.cpp:4603-4626).  ntstorage: history levels the time sums run over; default =
+        the levels the element class reads (3 for BDF2, NSTEPS+3 = 5 when a second time derivative brings the Newmark slots in)."""
         ti = TimeInfo()
         w1, w2 = bdf_weights(dt, dtprev)
+        n1, n2 = newmark2_weights(dt)
         ti.t[0], ti.t[1], ti.t[2] = t, t - dt, t - dt - dtprev
         ti.dt[0], ti.dt[1] = dt, dtprev
         for i in range(PB2_NTW):
             ti.w_dt_BDF1[i], ti.w_dt_BDF2[i] = w1[i], w2[i]
+            ti.w_dt_Newmark2[i], ti.w_d2t_Newmark2[i] = n1[i], n2[i]
             degr = w1[i] if unsteady_steps_done == 0 else w2[i]
             ti.w_dt_BDF2_degr[i] = degr
-            ti.w_dt_Newmark2_degr[i] = degr if unsteady_steps_done <= 4 else ti.w_dt_Newmark2[i]
+            ti.w_dt_Newmark2_degr[i] = degr if unsteady_steps_done <= 4 else n1[i]
+        if ntstorage is None:
+            ntstorage = max(3, int(self.info.n_hist_val))
+        if ntstorage > max(int(self.info.n_hist_val), int(self.info.n_hist_pos)) and ntstorage > 3:
+            raise ValueError("ntstorage %d exceeds the history levels the element class stores" % ntstorage)
         ti.ntstorage = ntstorage
         self.ti = ti
         _check(self.lib.pb2_problem_set_time(self.prob, ctypes.byref(ti)))
@@ -332,6 +367,7 @@ class B200Assembly(CustomAssemblyBase):
     # ---- Hessian-vector products (MultiAssembleRequest.dJdU / dMdU, pyoomph/generic/bifurcation_tools.py:465-531) -----
     def assemble_hessian(self, Y: np.ndarray, flag: int = 2, residual: str = ""):
         """d(J.Y_v)/dU (flag 1) and d(M.Y_v)/dU (flag 2) for every row Y_v of Y; returns lists of CSR value arrays"""
+        self._fresh()
         Y = np.ascontiguousarray(np.atleast_2d(Y), dtype=np.float64)
         assert Y.shape[1] == self.n_dof
         ri = self.residual_names.index(residual)
@@ -346,6 +382,7 @@ class B200Assembly(CustomAssemblyBase):
 
     def hessian_vector_products(self, Y: np.ndarray, C: np.ndarray, residual: str = "") -> np.ndarray:
         """flag 0 of HessianVectorProduct: out[v][i] = sum_jk Y_j H_ijk C_vk"""
+        self._fresh()
         Y = np.ascontiguousarray(Y, dtype=np.float64).ravel()
         C = np.ascontiguousarray(np.atleast_2d(C), dtype=np.float64)
         out = np.empty_like(C)
@@ -371,6 +408,7 @@ class B200Assembly(CustomAssemblyBase):
         fixed-order reduction (bit-reproducible), {name: value}"""
         if not self.integral_names:
             raise RuntimeError("this element class defines no integral expressions")
+        self._fresh()
         out = np.empty(len(self.integral_names))
         _check(self.lib.pb2_problem_eval_integrals(self.prob, self._dp(out), len(self.integral_names)))
         return {n: float(v) for n, v in zip(self.integral_names, out)}
@@ -404,14 +442,42 @@ class B200Assembly(CustomAssemblyBase):
         return int(self.lib.pb2_problem_num_launches(self.prob))
 
     # ---- CustomAssemblyBase contract -----------------------------------------------------------
+    def sync_from_problem(self):
+        """Bring the packed data up to date with the host problem this assembler was attached to by Problem.set_custom_assembler
+        (pyoomph/generic/problem.py:1711-1721): current dofs and history dofs (Problem.get_current_dofs / get_history_dofs,
+        src/pybind/problem.cpp:518-527), time-stepper state (Time::time/dt, MultiTimeStepper weights by their inputs dt, dtprev and
+        get_num_unsteady_steps_done, src/timestepper.hpp:59) and global parameters (Problem.get_global_parameter(name).value).
+        Called by get_residuals_and_jacobian before every assembly: Newton updates, time shifts and continuation steps of the host
+        are what the kernels see.  Returns the current dof vector."""
+        pr = self.problem
+        dofs = np.asarray(pr.get_current_dofs()[0], dtype=np.float64)
+        if dofs.shape != (self.n_dof,):
+            raise RuntimeError("the problem has %d dofs, the packed assembler %d: renumbered without rebuild()?" % (dofs.size, self.n_dof))
+        ts = pr.timestepper
+        steady = bool(ts.is_steady())
+        if steady:
+            self.set_steady()
+        else:
+            tp = pr.time_pt()
+            self.set_unsteady(float(tp.time()), float(tp.dt(0)), float(tp.dt(1)), int(ts.get_num_unsteady_steps_done()))
+            for t in range(1, max(int(self.info.n_hist_val), int(self.info.n_hist_pos))):
+                self.set_dofs(np.asarray(pr.get_history_dofs(t), dtype=np.float64), t)
+        if self.param_names:
+            self.set_parameters(**{n: float(pr.get_global_parameter(n).value) for n in self.param_names})
+        return dofs
+
     def get_residuals_and_jacobian(self, require_jacobian: bool, dparameter: Optional[str] = None):
+        """CustomAssemblyBase contract (pyoomph/generic/assembly.py:83, called from Problem.get_custom_residuals_jacobian,
+        problem.py:1727-1745).  Attached to a problem, the current state of the problem is pulled first (sync_from_problem); detached
+        (self.problem is None: tests, benchmarks), the packed data is used as the set_* calls left it."""
+        dofs = self.sync_from_problem() if self.problem is not None else None
         if require_jacobian:
             if dparameter:
                 raise RuntimeError("Cannot derive custom Jacobian with respect to a parameter yet")  # problem.py:1733
-            res, jac, _ = self.assemble_host(None, 1)
+            res, jac, _ = self.assemble_host(dofs, 1)
             from scipy.sparse import csr_matrix
             return res, csr_matrix((jac, self.indices, self.indptr), shape=(self.n_dof, self.n_dof))
-        res, _, _ = self.assemble_host(None, 0, parameter=dparameter)
+        res, _, _ = self.assemble_host(dofs, 0, parameter=dparameter)
         return res
 
     def close(self):

@@ -80,7 +80,13 @@ struct pb2_problem
   double *d_integrals = nullptr;   // [n_elem][n_integrals] per-element integral expressions, then [n_integrals] sums
   int *d_untouched = nullptr;      // CSR positions no local element writes (pattern entries owned for other ranks' contributions)
   long long n_untouched = 0;
+  int *h_status = nullptr, *d_status = nullptr; // error word of the kernels: mapped pinned host memory, read without a copy
+  cudaEvent_t ev_inputs = nullptr; // recorded on the legacy stream after every input update; assemblies on other streams wait for it
+  double setup_seconds = 0.0;      // wall time of pb2_problem_create (colouring, pattern, maps, upload)
 };
+
+static int inputs_changed(pb2_problem *p);
+static int check_status(pb2_problem *p);
 
 extern "C" int pb2_version(void) { return PB2_ABI_VERSION; }
 extern "C" const char *pb2_last_error(void) { return g_err.c_str(); }
@@ -133,6 +139,7 @@ static int upload(T **dptr, const std::vector<T> &v)
 extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_desc *m, pb2_problem **out)
 {
   *out = nullptr;
+  const double t_create0 = omp_get_wtime();
   const pb2_class_info &ci = cls->table.info;
   CUDA_OK(cudaSetDevice(device));
   pb2_problem *p = new pb2_problem;
@@ -598,6 +605,16 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   CUDA_OK(cudaMalloc((void **)&p->d_residual, std::max<size_t>(1, nrow) * sizeof(double)));
   CUDA_OK(cudaMalloc((void **)&p->d_dofs, std::max<size_t>(1, nrow) * sizeof(double)));
   CUDA_OK(cudaMalloc((void **)&p->d_jac, std::max<size_t>(1, p->nnz) * sizeof(double)));
+  // rows / entries no local element touches (ghost rows, element subsets) read as zero, never as uninitialised memory
+  CUDA_OK(cudaMemset(p->d_residual, 0, std::max<size_t>(1, nrow) * sizeof(double)));
+  CUDA_OK(cudaMemset(p->d_dofs, 0, std::max<size_t>(1, nrow) * sizeof(double)));
+  CUDA_OK(cudaMemset(p->d_jac, 0, std::max<size_t>(1, p->nnz) * sizeof(double)));
+  CUDA_OK(cudaHostAlloc((void **)&p->h_status, sizeof(int), cudaHostAllocMapped));
+  *p->h_status = 0;
+  CUDA_OK(cudaHostGetDevicePointer((void **)&p->d_status, p->h_status, 0));
+  CUDA_OK(cudaEventCreateWithFlags(&p->ev_inputs, cudaEventDisableTiming));
+  CUDA_OK(cudaEventRecord(p->ev_inputs, 0));
+  p->setup_seconds = omp_get_wtime() - t_create0;
   *out = p;
   return 0;
 }
@@ -627,6 +644,8 @@ extern "C" void pb2_problem_free(pb2_problem *p)
   cudaFree(p->d_row_start);
   cudaFree(p->d_col_index);
   cudaFree(p->d_debug);
+  if (p->h_status) cudaFreeHost(p->h_status);
+  if (p->ev_inputs) cudaEventDestroy(p->ev_inputs);
   for (auto &b : p->batch_tables)
   {
     cudaFree(b.d_batch_elem);
@@ -657,7 +676,7 @@ extern "C" int pb2_problem_set_nodal_values(pb2_problem *p, int t, const double 
   CUDA_OK(cudaSetDevice(p->device));
   const size_t n = (size_t)p->n_node * p->nval;
   CUDA_OK(cudaMemcpy(p->d_node_val + (size_t)t * n, values, n * sizeof(double), cudaMemcpyHostToDevice));
-  return 0;
+  return inputs_changed(p);
 }
 
 extern "C" int pb2_problem_set_nodal_positions(pb2_problem *p, int t, const double *pos)
@@ -666,13 +685,21 @@ extern "C" int pb2_problem_set_nodal_positions(pb2_problem *p, int t, const doub
   CUDA_OK(cudaSetDevice(p->device));
   const size_t n = (size_t)p->n_node * p->dim;
   CUDA_OK(cudaMemcpy(p->d_node_pos + (size_t)t * n, pos, n * sizeof(double), cudaMemcpyHostToDevice));
-  return 0;
+  return inputs_changed(p);
 }
 
 extern "C" int pb2_problem_set_lagrangian_positions(pb2_problem *p, const double *pos)
 {
   CUDA_OK(cudaSetDevice(p->device));
   CUDA_OK(cudaMemcpy(p->d_node_lagr, pos, (size_t)p->n_node * p->dim * sizeof(double), cudaMemcpyHostToDevice));
+  return inputs_changed(p);
+}
+
+// every update of the packed inputs runs on the legacy default stream; an assembly on another (possibly non-blocking) stream is
+// ordered behind it through this event
+static int inputs_changed(pb2_problem *p)
+{
+  CUDA_OK(cudaEventRecord(p->ev_inputs, 0));
   return 0;
 }
 
@@ -697,18 +724,22 @@ static __global__ void pb2_scatter_dofs(const double *__restrict__ dofs, const l
     node_pos[~t] = dofs[i];
 }
 
-static int scatter_dofs_from_device(pb2_problem *p, cudaStream_t s)
+static int scatter_dofs_from_device(pb2_problem *p, cudaStream_t s, int t = 0)
 {
   const int bs = 256;
   const long long nb = (p->n_dof + bs - 1) / bs;
   if (nb > 0)
   {
-    pb2_scatter_dofs<<<(unsigned)nb, bs, 0, s>>>(p->d_dofs, p->d_dof_target, p->n_dof, p->d_node_val, p->d_node_pos);
+    // history level t of the nodal values / positions (levels beyond what a buffer stores are not written: the pointer stays at level 0
+    // only when that buffer has a single level and the class never reads its history)
+    double *val = p->d_node_val + (size_t)std::min(t, p->T_val - 1) * p->n_node * std::max(1, p->nval);
+    double *pos = p->d_node_pos + (size_t)std::min(t, p->T_pos - 1) * p->n_node * p->dim;
+    pb2_scatter_dofs<<<(unsigned)nb, bs, 0, s>>>(p->d_dofs, p->d_dof_target, p->n_dof, val, pos);
     p->launches_last++;
     p->launches_total++;
     CUDA_OK(cudaGetLastError());
   }
-  return 0;
+  return inputs_changed(p);
 }
 
 extern "C" int pb2_problem_set_dofs(pb2_problem *p, const double *dofs)
@@ -716,6 +747,16 @@ extern "C" int pb2_problem_set_dofs(pb2_problem *p, const double *dofs)
   CUDA_OK(cudaSetDevice(p->device));
   CUDA_OK(cudaMemcpy(p->d_dofs, dofs, (size_t)p->n_dof * sizeof(double), cudaMemcpyHostToDevice));
   return scatter_dofs_from_device(p, 0);
+}
+
+// Problem::set_history_dofs(t, ...) (src/pybind/problem.cpp:540): a dof vector of history level t -> nodal values / positions of that level
+extern "C" int pb2_problem_set_history_dofs(pb2_problem *p, int t, const double *dofs)
+{
+  if (t < 0 || t >= std::max(p->T_val, p->T_pos)) return fail("history index out of range");
+  CUDA_OK(cudaSetDevice(p->device));
+  if (t > 0 && p->T_pos <= t && p->cls->table.info.moving_nodes) return fail("position history level not stored");
+  CUDA_OK(cudaMemcpy(p->d_dofs, dofs, (size_t)p->n_dof * sizeof(double), cudaMemcpyHostToDevice));
+  return scatter_dofs_from_device(p, 0, t);
 }
 
 // oomph's Problem::shift_time_values (TimeStepper::shift_time_values of every Data, timesteppers.h): history level t takes the
@@ -729,7 +770,7 @@ extern "C" int pb2_problem_shift_time_values(pb2_problem *p)
     CUDA_OK(cudaMemcpyAsync((char *)p->d_node_val + (size_t)t * nv, (char *)p->d_node_val + (size_t)(t - 1) * nv, nv, cudaMemcpyDeviceToDevice, 0));
   for (int t = p->T_pos - 1; t >= 1; t--)
     CUDA_OK(cudaMemcpyAsync((char *)p->d_node_pos + (size_t)t * np_, (char *)p->d_node_pos + (size_t)(t - 1) * np_, np_, cudaMemcpyDeviceToDevice, 0));
-  return 0;
+  return inputs_changed(p);
 }
 
 extern "C" int pb2_problem_set_time(pb2_problem *p, const pb2_time_info *ti)
@@ -745,9 +786,23 @@ extern "C" int pb2_problem_set_parameters(pb2_problem *p, const double *values, 
   return 0;
 }
 
+// error word of the kernels (tile gate timed out): reported once, by the next call that could hand out results
+static int check_status(pb2_problem *p)
+{
+  if (p->h_status && *(volatile int *)p->h_status != 0)
+  {
+    const int st = *(volatile int *)p->h_status;
+    *(volatile int *)p->h_status = 0;
+    return fail(st == PB2_STATUS_GATE_TIMEOUT ? "a tile gate of the persistent assembly kernel timed out (blocks not co-resident); the results of that assembly are invalid"
+                                              : "the assembly kernel reported error " + std::to_string(st));
+  }
+  return 0;
+}
+
 static void fill_common_args(pb2_problem *p, pb2_kernel_args &a)
 {
   memset(&a, 0, sizeof(a));
+  a.status = p->d_status;
   a.elem_nodes = p->d_elem_nodes;
   a.elem_eqn = p->d_elem_eqn;
   a.elem_rowstart = p->d_elem_rowstart;
@@ -770,6 +825,8 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
   const pb2_class_info &ci = p->cls->table.info;
   if (residual_index < 0 || residual_index >= ci.n_residuals) return fail("residual index out of range");
   if (param_index >= ci.n_params) return fail("parameter index out of range");
+  if (check_status(p)) return 1;
+  if (cuda_stream) CUDA_OK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, p->ev_inputs, 0));
   pb2_kernel_args a;
   fill_common_args(p, a);
   a.jac_vals = out_jac;
@@ -978,6 +1035,7 @@ extern "C" int pb2_problem_fetch_hessian(pb2_problem *p, int v, double *jac_hess
   CUDA_OK(cudaSetDevice(p->device));
   if (v < 0 || v >= p->hess_nvec) return fail("Hessian vector index out of range");
   CUDA_OK(cudaDeviceSynchronize());
+  if (check_status(p)) return 1;
   if (jac_hessian_vals) CUDA_OK(cudaMemcpy(jac_hessian_vals, p->d_hess + (size_t)v * p->nnz, (size_t)p->nnz * sizeof(double), cudaMemcpyDeviceToHost));
   if (mass_hessian_vals) CUDA_OK(cudaMemcpy(mass_hessian_vals, p->d_hessM + (size_t)v * p->nnz, (size_t)p->nnz * sizeof(double), cudaMemcpyDeviceToHost));
   return 0;
@@ -1153,6 +1211,7 @@ extern "C" int pb2_problem_fetch(pb2_problem *p, double *residual, double *jac_v
 {
   CUDA_OK(cudaSetDevice(p->device));
   CUDA_OK(cudaDeviceSynchronize());
+  if (check_status(p)) return 1;
   if (residual) CUDA_OK(cudaMemcpy(residual, p->d_residual, (size_t)p->n_dof * sizeof(double), cudaMemcpyDeviceToHost));
   if (jac_vals) CUDA_OK(cudaMemcpy(jac_vals, p->d_jac, (size_t)p->nnz * sizeof(double), cudaMemcpyDeviceToHost));
   if (mass_vals)
@@ -1189,20 +1248,26 @@ extern "C" void *pb2_host_alloc(size_t nbytes)
 extern "C" void pb2_host_free(void *ptr) { cudaFreeHost(ptr); }
 
 static cudaEvent_t g_events[64];
-static bool g_event_made[64];
+static int g_event_device[64]; // device + 1 the slot's event belongs to, 0 = not created
 extern "C" int pb2_event_record(int idx, void *cuda_stream)
 {
   if (idx < 0 || idx >= 64) return fail("event index out of range");
-  if (!g_event_made[idx])
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  if (g_event_device[idx] != dev + 1)
   {
+    // an event belongs to the device that was current when it was created: a slot reused on another device gets a new event
+    if (g_event_device[idx] != 0) cudaEventDestroy(g_events[idx]);
     CUDA_OK(cudaEventCreate(&g_events[idx]));
-    g_event_made[idx] = true;
+    g_event_device[idx] = dev + 1;
   }
   CUDA_OK(cudaEventRecord(g_events[idx], (cudaStream_t)cuda_stream));
   return 0;
 }
 extern "C" int pb2_event_elapsed_ms(int i0, int i1, float *ms)
 {
+  if (i0 < 0 || i0 >= 64 || i1 < 0 || i1 >= 64 || !g_event_device[i0] || g_event_device[i0] != g_event_device[i1])
+    return fail("events were not recorded on the same device");
   CUDA_OK(cudaEventSynchronize(g_events[i1]));
   CUDA_OK(cudaEventElapsedTime(ms, g_events[i0], g_events[i1]));
   return 0;
@@ -1217,6 +1282,59 @@ extern "C" int pb2_device_count(int *n)
   CUDA_OK(cudaGetDeviceCount(n));
   return 0;
 }
+extern "C" double pb2_problem_setup_seconds(pb2_problem *p) { return p->setup_seconds; }
+
+// ---- fp64 roofline denominator: dependent-chain-free DFMA throughput of the device ("P64 measured on the box by an FMA
+// microbenchmark").  16 independent accumulators per thread, 4 blocks of 256 threads per SM: enough warps and ILP to keep the fp64
+// pipe of every sub-partition issuing back to back; 2 flops per DFMA.
+static __global__ void __launch_bounds__(256) pb2_fp64_fma_kernel(double *out, int iters, double x0)
+{
+  double a[16];
+  const double m = 1.0 + 1e-9 * x0, c = 1e-9 * (threadIdx.x + 1);
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = x0 + i;
+  for (int it = 0; it < iters; it++)
+  {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = fma(a[i], m, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += a[i];
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s; // never true: keeps the chain alive without a store
+}
+
+extern "C" int pb2_measure_fp64_peak(int device, double *tflops)
+{
+  CUDA_OK(cudaSetDevice(device));
+  int n_sms = 0;
+  CUDA_OK(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device));
+  double *d_out = nullptr;
+  const int grid = n_sms * 8, bs = 256, iters = 4096;
+  CUDA_OK(cudaMalloc((void **)&d_out, (size_t)grid * bs * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++)
+  {
+    CUDA_OK(cudaEventRecord(e0, 0));
+    pb2_fp64_fma_kernel<<<grid, bs>>>(d_out, iters, 1.0);
+    CUDA_OK(cudaEventRecord(e1, 0));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 16.0 * iters * (double)grid * bs / (ms * 1e-3) / 1e12;
+    if (rep >= 1) best = std::max(best, tf); // first repetition warms up
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  CUDA_OK(cudaGetLastError());
+  *tflops = best;
+  return 0;
+}
+
 extern "C" int pb2_flush_l2(int device)
 {
   // overwrite a buffer larger than the 126 MB L2

@@ -714,7 +714,7 @@ class CudaEmitter:
         w("      // stream order of the colours: everything of the previous tile must have been scattered")
         w("      if (tile > gated_tile)")
         w("      {")
-        w("        if (st == 0) { while (*(volatile int*)(a.tile_done + tile - 1) < a.tile_nbatch[tile - 1]) __nanosleep(64); }")
+        w("        if (st == 0) pb2_gate_wait(a.tile_done + tile - 1, a.tile_nbatch[tile - 1], a.status);")
         w("        gated_tile = tile;")
         w("        pb2_bar_sync(11, %d);                     // gate passed (tile, gated_tile are uniform over the scatter warps)" % NS)
         w("        __threadfence();")
@@ -1524,6 +1524,19 @@ class CudaEmitter:
         w("}")
         w("static __device__ __forceinline__ void pb2_bar_sync(const int id, const int nthreads) { asm volatile(\"bar.sync %0, %1;\" :: \"r\"(id), \"r\"(nthreads) : \"memory\"); }")
         w("static __device__ __forceinline__ void pb2_bar_arrive(const int id, const int nthreads) { asm volatile(\"bar.arrive %0, %1;\" :: \"r\"(id), \"r\"(nthreads) : \"memory\"); }")
+        w("// tile gate of the persistent kernels: wait until `done` reaches `need`.  The launch is cooperative (all blocks resident, or the")
+        w("// launch fails), so the gate opens; the deadline only turns an impossible wait (a lost block) into an error the host reports")
+        w("static __device__ __forceinline__ void pb2_gate_wait(const int* done, const int need, int* status)")
+        w("{")
+        w("  if (*(volatile const int*)done >= need) return;")
+        w("  unsigned long long t0; asm volatile(\"mov.u64 %0, %%globaltimer;\" : \"=l\"(t0));")
+        w("  while (*(volatile const int*)done < need)")
+        w("  {")
+        w("    __nanosleep(64);")
+        w("    unsigned long long t1; asm volatile(\"mov.u64 %0, %%globaltimer;\" : \"=l\"(t1));")
+        w("    if (t1 - t0 > PB2_GATE_TIMEOUT_NS || *(volatile int*)status != 0) { atomicExch(status, PB2_STATUS_GATE_TIMEOUT); break; }")
+        w("  }")
+        w("}")
         w("// branch-free: first touch of a CSR entry stores, later colours reduce (fire-and-forget red, no return value)")
         w("static __device__ __forceinline__ void pb2_store_or_red(double* dst, const double v, const bool do_store, const bool do_red)")
         w("{")
@@ -1674,7 +1687,10 @@ class CudaEmitter:
         w("{")
         w("  if (grid <= 0) return 0;")
         w("  void* params[1] = {(void*)args};")
-        w("  cudaError_t err = cudaLaunchKernel(cfg->func, dim3((unsigned)grid), dim3((unsigned)cfg->threads), params, (size_t)cfg->smem_bytes, (cudaStream_t)stream);")
+        w("  // persistent kernels wait on each other at the tile gates: cooperative launch = every block resident at once, or an error")
+        w("  cudaError_t err = cfg->pipelined")
+        w("    ? cudaLaunchCooperativeKernel(cfg->func, dim3((unsigned)grid), dim3((unsigned)cfg->threads), params, (size_t)cfg->smem_bytes, (cudaStream_t)stream)")
+        w("    : cudaLaunchKernel(cfg->func, dim3((unsigned)grid), dim3((unsigned)cfg->threads), params, (size_t)cfg->smem_bytes, (cudaStream_t)stream);")
         w("  if (err == cudaSuccess) err = cudaGetLastError();")
         w("  return err == cudaSuccess ? 0 : 100 + (int)err;")
         w("}")

@@ -231,3 +231,76 @@ def compare_matrix(A_gpu, A_ref, tol=1e-12):
     Q = A_ref.copy(); Q.data[:] = 1.0
     missing = (Q - Q.multiply(P)).count_nonzero()
     return float(err.max()), int(missing)
+
+
+def reference_pattern(indptr, indices, vals):
+    """What the reference keeps of a matrix assembled on a fixed structural pattern: oomph's sparse assembly stores an entry only if
+    fabs(value) > Numerical_zero_for_sparse_assembly = 0.0 (oomph-lib problem.cc:110, :5524; pyoomph's sorted variant
+    src/problem.cpp:2146-2277 likewise), columns ascending as in the "maps" assembly (src/problem.cpp:2200, :2268-2274).
+    Returns (row_ptr int32, col_idx int32, values) -- the CSR the reference would hand to its solver for these values."""
+    indptr, indices, vals = np.asarray(indptr), np.asarray(indices), np.asarray(vals)
+    n = indptr.size - 1
+    keep = np.abs(vals) > 0.0
+    rows = np.repeat(np.arange(n), np.diff(indptr))
+    row_ptr = np.concatenate([[0], np.cumsum(np.bincount(rows[keep], minlength=n))]).astype(np.int32)
+    return row_ptr, indices[keep].astype(np.int32), vals[keep]
+
+
+def compare_csr_exact(indptr, indices, vals, ref_csr, tol=1e-12):
+    """The north_star bar: after the reference's zero-drop rule the GPU matrix must have the reference's row_ptr / col_idx BIT-EXACT,
+    and every value within `tol` RELATIVE TO THE ENTRY.  ref_csr = (row_start, col_index, values) of the oracle in any column order.
+
+    Two counted allowances, both for entries that are sums with cancellation (their bits depend on summation order and FMA contraction
+    -- the reference's own bits change with its compiler flags):
+      * n_cancel_values: entries whose error exceeds tol*|entry| but not tol*(largest entry of the row);
+      * n_cancel_pattern: entries present in only one of the two patterns whose magnitude is below tol*(largest entry of the row),
+        i.e. an exact 0.0 on one side and rounding noise on the other.
+    Anything else is reported in n_bad_values / n_bad_pattern and must be zero.  Returns a dict of these counts."""
+    n = len(indptr) - 1
+    rp, ci, va = reference_pattern(indptr, indices, vals)
+    B = csr_to_sorted(n, *ref_csr)
+    B.eliminate_zeros()
+    out = dict(nnz_ref=int(B.nnz), nnz_gpu=int(va.size), n_cancel_values=0, n_cancel_pattern=0, n_bad_values=0, n_bad_pattern=0, worst_entry_rel=0.0)
+    rowmax = np.maximum(abs(B).max(axis=1).toarray().ravel(), 1e-300) if B.nnz else np.full(n, 1e-300)
+    out["pattern_equal"] = bool(np.array_equal(rp, B.indptr) and np.array_equal(ci, B.indices))
+    if out["pattern_equal"]:
+        a, b = va, B.data
+        rows = np.repeat(np.arange(n), np.diff(rp))
+    else:
+        # union of the two patterns through (row, col) keys
+        rows_a = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+        rows_b = np.repeat(np.arange(n, dtype=np.int64), np.diff(B.indptr))
+        ka, kb = rows_a * n + ci, rows_b * n + B.indices          # ascending: rows ascending, columns ascending inside a row
+        ku = np.union1d(ka, kb)
+        ua, ub = np.zeros(ku.size), np.zeros(ku.size)
+        in_a, in_b = np.zeros(ku.size, bool), np.zeros(ku.size, bool)
+        ia, ib = np.searchsorted(ku, ka), np.searchsorted(ku, kb)
+        ua[ia], ub[ib], in_a[ia], in_b[ib] = va, B.data, True, True
+        rows_u = ku // n
+        only = in_a != in_b
+        mag = np.maximum(np.abs(ua[only]), np.abs(ub[only]))
+        small = mag <= tol * rowmax[rows_u[only]]
+        out["n_cancel_pattern"] = int(small.sum())
+        out["n_bad_pattern"] = int((~small).sum())
+        both = ~only
+        a, b, rows = ua[both], ub[both], rows_u[both]
+    d = np.abs(a - b)
+    ok = d <= tol * np.abs(b)
+    cancel = ~ok & (d <= tol * rowmax[rows])
+    out["n_cancel_values"] = int(cancel.sum())
+    out["n_bad_values"] = int((~ok & ~cancel).sum())
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.where(ok, d / np.maximum(np.abs(b), 1e-300), 0.0)
+    out["worst_entry_rel"] = float(rel.max()) if rel.size else 0.0
+    return out
+
+
+def assert_csr_parity(indptr, indices, vals, ref_csr, tol=1e-12, label="", require_exact_pattern=False, max_cancel_fraction=0.02):
+    """assert the north_star bar of compare_csr_exact; returns its statistics (printed by the tests so the driver log carries them)"""
+    st = compare_csr_exact(indptr, indices, vals, ref_csr, tol)
+    msg = "%s: %r" % (label, st)
+    assert st["n_bad_pattern"] == 0 and st["n_bad_values"] == 0, msg
+    if require_exact_pattern:
+        assert st["pattern_equal"], msg
+    assert st["n_cancel_pattern"] + st["n_cancel_values"] <= max_cancel_fraction * max(1, st["nnz_ref"]), msg
+    return st

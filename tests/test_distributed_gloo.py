@@ -80,6 +80,15 @@ def _worker(rank, world, port, kind, N, outdir):
     rb, re, ip, gc, jv, mv, res = da.owned_block(want_mass=True)
     h_res, h_jac, h_mass = da.assemble_host(None, 2)           # the host-facing call of one rank returns the same owned block
     assert np.array_equal(h_res.numpy(), res) and np.array_equal(h_jac.numpy(), jv) and np.array_equal(h_mass.numpy(), mv)
+    if kind == "ns_unsteady":
+        # the row-block form of the window check bench.py runs on N GPUs (tests/windows.py): every owned row of the windows that
+        # straddle the partition interface against the oracle assembled on the window alone
+        from problems import make_oracle
+        from windows import check_windows
+        st = {}
+        check_windows(pb, make_oracle, ip, gc, jv, res, [(0, 0), (1, 2), (2, 1), (2, 2)], w=4, tol=1e-12, new_of_old=da.part.new_of_old,
+                      row_begin=rb, row_end=re, stats=st)
+        assert st["rows"] > 0
     obs = da.evaluate_integral_expressions() if pb["code"].integral_expressions else {}
     np.savez(os.path.join(outdir, "r%d.npz" % rank), rb=rb, re=re, ip=ip, gc=gc, jv=jv, mv=mv, res=res, new_of_old=da.part.new_of_old,
              xbytes=da.exchange_bytes, obs=np.array([obs[k] for k in obs]))

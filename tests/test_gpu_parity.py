@@ -8,9 +8,21 @@ row_ptr/col_idx of both agree wherever the reference keeps the entry.
 import numpy as np
 import pytest
 
-from problems import compare_matrix, csr_to_sorted, make_gpu, make_oracle, make_problem
+from problems import assert_csr_parity, compare_matrix, csr_to_sorted, make_gpu, make_oracle, make_problem
 
 TOL = 1e-12
+
+
+def _record(kind, N, distortion, unstructured, st):
+    """statistics of the bit-exact CSR comparison, printed (driver log) and appended to gpurun_out/ when that directory exists"""
+    import json
+    import os
+    line = json.dumps(dict(kind=kind, N=N, distortion=distortion, unstructured=unstructured, **st))
+    print("csr parity:", line)
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "csr_parity_stats.jsonl"), "a") as f:
+            f.write(line + "\n")
 
 CASES = [("poisson", 64), ("poisson", 5), ("ns", 12), ("ns_unsteady", 9), ("heat3d", 3), ("ale", 7), ("ns_param", 6),
          ("ns_axi", 9), ("ns_axi_swirl", 7), ("ale_axi", 6)]      # axisymmetric classes of configs 4 and 5
@@ -43,6 +55,10 @@ def test_residual_jacobian_mass_parity(kind, N, distortion, unstructured):
         err, missing = compare_matrix(A, B)
         assert missing == 0
         assert err <= TOL, (kind, err)
+        # the north_star bar: row_ptr / col_idx bit-exact after the reference's zero-drop rule, values 1e-12 relative to the ENTRY
+        st = assert_csr_parity(asm.indptr, asm.indices, vals, (rs, ci, va), TOL, label="%s N=%d" % (kind, N),
+                               require_exact_pattern=(distortion > 0.0))    # distorted meshes: no exact cancellation anywhere
+        _record(kind, N, distortion, unstructured, st)
     # flag 0 and flag 1 launches give the same numbers as the flag 2 launch (separate kernels)
     asm.assemble(flag=0)
     r0, _, _ = asm.fetch(False, False)
@@ -66,6 +82,7 @@ def test_parameter_derivative_parity():
     assert np.abs(r - r_ref).max() <= TOL * np.abs(r_ref).max()
     err, missing = compare_matrix(csr_to_sorted(n, asm.indptr, asm.indices, jac), csr_to_sorted(n, *mats[0]))
     assert missing == 0 and err <= TOL
+    _record("ns_param_dp", 6, 0.0, False, assert_csr_parity(asm.indptr, asm.indices, jac, mats[0], TOL, label="dJ/dmu"))
 
 
 @pytest.mark.gpu

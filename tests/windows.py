@@ -6,9 +6,14 @@ import numpy as np
 from pyoomph_b200.meshes import CuboidBrickMesh, RectangularQuadMesh, assign_equation_numbers
 
 
-def check_windows(pb, make_oracle, indptr, indices, jac, res, windows, w=4, tol=1e-12):
+def check_windows(pb, make_oracle, indptr, indices, jac, res, windows, w=4, tol=1e-12, new_of_old=None, row_begin=0, row_end=None,
+                  stats=None):
     """pb: the large problem (2D structured); (indptr, indices, jac, res): its assembled CSR Jacobian and residual;
-    windows: list of element offsets (one per dimension).  Returns the largest row-scaled error seen."""
+    windows: list of element offsets (one per dimension).  Returns the largest row-scaled error seen.
+
+    Row-block form (multi-GPU): (indptr, indices, jac, res) are ONE rank's owned rows [row_begin, row_end) of the matrix in the
+    partition-aligned numbering `new_of_old` (old equation -> new equation), `indices` holding new global columns; rows of a window
+    that another rank owns are skipped (that rank checks them).  `stats`, if given, receives the number of rows compared."""
     mesh, dm, code = pb["mesh"], pb["dofmap"], pb["code"]
     dim = mesh.dim
     L = [2 * n + 1 for n in mesh.N]
@@ -47,8 +52,17 @@ def check_windows(pb, make_oracle, indptr, indices, jac, res, windows, w=4, tol=
                 if be < 0:
                     continue                      # pinned in the large problem: the row does not exist there
                 cols_s, vals_s = ci[rs[se]:rs[se + 1]], va[rs[se]:rs[se + 1]]
+                cols_big = big_eq[cols_s]
+                if new_of_old is not None:
+                    be = int(new_of_old[be])
+                    if be < row_begin or (row_end is not None and be >= row_end):
+                        continue                  # owned by another rank
+                    be -= row_begin
+                    cols_big = np.where(cols_big >= 0, new_of_old[np.maximum(cols_big, 0)], -1)
+                if stats is not None:
+                    stats["rows"] = stats.get("rows", 0) + 1
                 ref = {}
-                for c, v in zip(big_eq[cols_s], vals_s):
+                for c, v in zip(cols_big, vals_s):
                     if c >= 0:
                         ref[int(c)] = ref.get(int(c), 0.0) + v
                 gc, gv = indices[indptr[be]:indptr[be + 1]], jac[indptr[be]:indptr[be + 1]]
