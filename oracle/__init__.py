@@ -123,12 +123,17 @@ class OracleProblem:
         z = np.zeros(7)
         self.lib.oracle_set_time(self.h, 1, 0, 0, _dp(z), _dp(z), _dp(z), _dp(z), _dp(z), _dp(z))
 
-    def set_unsteady(self, t: float, dt: float, dtprev: float, unsteady_steps_done: int, ntstorage: int = 3):
-        w1, w2, z = np.zeros(7), np.zeros(7), np.zeros(7)
+    def set_unsteady(self, t: float, dt: float, dtprev: float, unsteady_steps_done: int, ntstorage: Optional[int] = None):
+        """MultiTimeStepper weights (src/timestepper.cpp:31-80); ntstorage defaults to the history levels handed to the constructor
+        (3 for BDF2 problems, 5 = NSTEPS + 3 when the Newmark velocity / acceleration slots are stored)"""
+        w1, w2, n1, n2 = np.zeros(7), np.zeros(7), np.zeros(7), np.zeros(7)
         self.lib.oracle_bdf_weights(ctypes.c_double(dt), ctypes.c_double(dtprev), _dp(w1), _dp(w2))
+        self.lib.oracle_newmark2_weights(ctypes.c_double(dt), ctypes.c_double(0.5), ctypes.c_double(0.5), _dp(n1), _dp(n2))
         tt = np.zeros(7); tt[0] = t; tt[1] = t - dt; tt[2] = t - dt - dtprev
         dd = np.zeros(7); dd[0] = dt; dd[1] = dtprev
-        self.lib.oracle_set_time(self.h, 0, unsteady_steps_done, ntstorage, _dp(tt), _dp(dd), _dp(w1), _dp(w2), _dp(z), _dp(z))
+        if ntstorage is None:
+            ntstorage = max(3, self.T)
+        self.lib.oracle_set_time(self.h, 0, unsteady_steps_done, ntstorage, _dp(tt), _dp(dd), _dp(w1), _dp(w2), _dp(n1), _dp(n2))
         return w1, w2
 
     def update_values(self, t: int, node_val=None, node_pos=None):

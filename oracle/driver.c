@@ -630,6 +630,22 @@ void oracle_bdf_weights(double dt, double dtprev, double *wBDF1, double *wBDF2)
   wBDF1[1] = -1.0 / dt;
 }
 
+/* MultiTimeStepper::set_weights (src/timestepper.cpp:61-80), Newmark2 part: NSTEPS = 2 (src/timestepper.hpp:49), NewmarkBeta1 =
+ * NewmarkBeta2 = 0.5 unless setNewmark2Coeffs was called (src/timestepper.hpp:63, :109) */
+void oracle_newmark2_weights(double dt, double beta1, double beta2, double *w_dt, double *w_d2t)
+{
+  const int NSTEPS = 2;
+  for (int i = 0; i < NTW; i++) w_dt[i] = w_d2t[i] = 0.0;
+  w_d2t[0] = 2.0 / (beta2 * dt * dt);
+  w_d2t[1] = -2.0 / (beta2 * dt * dt);
+  w_d2t[NSTEPS + 1] = -2.0 / (dt * beta2);
+  w_d2t[NSTEPS + 2] = (beta2 - 1.0) / beta2;
+  w_dt[0] = beta1 * dt * w_d2t[0];
+  w_dt[1] = beta1 * dt * w_d2t[1];
+  w_dt[NSTEPS + 1] = 1.0 + beta1 * dt * w_d2t[NSTEPS + 1];
+  w_dt[NSTEPS + 2] = dt * (1.0 - beta1) + beta1 * dt * w_d2t[NSTEPS + 2];
+}
+
 /* update nodal values/positions at history level t from [node][k] arrays */
 void oracle_update_values(void *h, int t, const double *node_val, const double *node_pos)
 {
