@@ -186,7 +186,7 @@ class CudaEmitter:
         self.tensor_points = self.dim == 3 and os.environ.get("PB2_TP3D_POINTS", "1") != "0"
         # round-2 experiment (off: compiled and algebra-checked on the CPU only, not yet run on a GPU): sum factorisation of the column
         # side over the Gauss points, DESIGN.md section 9 item 4
-        self.sum_factorise = self.tensor_columns and os.environ.get("PB2_SUMFAC", "0") == "1"
+        self.sum_factorise = self.tensor_columns and os.environ.get("PB2_SUMFAC", "1") != "0"
 
     # ------------------------------------------------------------------ planning
     def _col_index(self, field: str, lnode: int) -> int:
@@ -1510,6 +1510,7 @@ class CudaEmitter:
         w("// generated by pyoomph_b200.cuda_emitter for element class '%s' (%s) -- sm_100a" % (self.name, self.et.name))
         w("#include <cuda_runtime.h>")
         w("#include <string.h>")
+        w("#include <stdlib.h>")
         w('#include "pb2_jit_cuda.h"')
         w("")
         w("static __device__ __forceinline__ void pb2_cp_async4(void* smem_dst, const void* gsrc)")
@@ -1530,9 +1531,11 @@ class CudaEmitter:
         w("{")
         w("  if (*(volatile const int*)done >= need) return;")
         w("  unsigned long long t0; asm volatile(\"mov.u64 %0, %%globaltimer;\" : \"=l\"(t0));")
+        w("  unsigned spins = 0;")
         w("  while (*(volatile const int*)done < need)")
         w("  {")
         w("    __nanosleep(64);")
+        w("    if ((++spins & 4095u) != 0u) continue;     // the deadline and the error word (host memory) are looked at every ~0.3 ms only")
         w("    unsigned long long t1; asm volatile(\"mov.u64 %0, %%globaltimer;\" : \"=l\"(t1));")
         w("    if (t1 - t0 > PB2_GATE_TIMEOUT_NS || *(volatile int*)status != 0) { atomicExch(status, PB2_STATUS_GATE_TIMEOUT); break; }")
         w("  }")
@@ -1688,7 +1691,8 @@ class CudaEmitter:
         w("  if (grid <= 0) return 0;")
         w("  void* params[1] = {(void*)args};")
         w("  // persistent kernels wait on each other at the tile gates: cooperative launch = every block resident at once, or an error")
-        w("  cudaError_t err = cfg->pipelined")
+        w("  static const int coop = getenv(\"PB2_COOP\") ? atoi(getenv(\"PB2_COOP\")) : 1;   // development switch: 0 = plain launch (no residency guarantee)")
+        w("  cudaError_t err = (cfg->pipelined && coop)")
         w("    ? cudaLaunchCooperativeKernel(cfg->func, dim3((unsigned)grid), dim3((unsigned)cfg->threads), params, (size_t)cfg->smem_bytes, (cudaStream_t)stream)")
         w("    : cudaLaunchKernel(cfg->func, dim3((unsigned)grid), dim3((unsigned)cfg->threads), params, (size_t)cfg->smem_bytes, (cudaStream_t)stream);")
         w("  if (err == cudaSuccess) err = cudaGetLastError();")
