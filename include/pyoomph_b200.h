@@ -53,6 +53,8 @@ void pb2_class_free(pb2_class *cls);
 /* build colouring, the fixed CSR pattern (columns ascending per row, like the "maps" assembly of
  * src/problem.cpp:2200-2274) and the element->CSR position maps; upload everything to `device`. */
 int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_desc *mesh, pb2_problem **out);
+/* device < 0 creates a PATTERN-ONLY problem: schedule, CSR pattern and position maps on the host, no CUDA call at all; only
+ * pb2_problem_pattern / num_colours / num_launches / setup_seconds / free accept it (everything that computes reports an error). */
 void pb2_problem_free(pb2_problem *p);
 
 /* pattern of the assembled matrix (host memory owned by the problem): CRDoubleMatrix row_start/column_index */

@@ -22,6 +22,24 @@ JIT_DIR = os.path.join(HERE, "_jit")
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
+def find_jitbridge_include() -> Optional[str]:
+    """directory holding the reference's jitbridge.h: $PB2_JITBRIDGE_INCLUDE, an installed pyoomph's JIT include directory, or the
+    reference tree next to this checkout; None if there is none (then the plugin exports only JIT_ELEMENT_init_cuda)"""
+    cands = [os.environ.get("PB2_JITBRIDGE_INCLUDE")]
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("pyoomph")
+        if spec and spec.submodule_search_locations:
+            cands += [os.path.join(p, "jitbridge") for p in spec.submodule_search_locations]
+    except Exception:
+        pass
+    cands.append("/root/reference/src")
+    for c in cands:
+        if c and os.path.exists(os.path.join(c, "jitbridge.h")):
+            return c
+    return None
+
+
 def find_nvcc() -> Optional[str]:
     for c in (os.environ.get("PB2_NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if c and os.path.exists(c):
@@ -62,6 +80,34 @@ class BaseCCompiler:
     def check_avail(self) -> bool:
         return False
 
+    # ---- pyoomph::CCompiler interface (src/ccompiler.hpp:35-76) and its Python helpers (pyoomph/generic/ccompiler.py:70-77) ------------
+    code_extension = ".c"
+
+    def set_code_from_file(self, ftrunk: str) -> None:
+        """the generated source lies at <ftrunk><code_extension> (the host wrote it, src/pybind/problem.cpp:694-696)"""
+        self._code_trunk = ftrunk
+
+    def get_code_trunk(self) -> str:
+        return getattr(self, "_code_trunk", "")
+
+    def get_code_filename(self) -> str:
+        return self.get_code_trunk() + self.code_extension
+
+    def get_shared_lib_extension(self) -> str:
+        return ".so"
+
+    def get_lib_filename(self) -> str:
+        return self.get_code_trunk() + self.get_shared_lib_extension()
+
+    def get_shared_library(self, code_trunk: str) -> str:
+        return code_trunk + self.get_shared_lib_extension()
+
+    def expand_full_library_name(self, relname: str) -> str:
+        return os.path.join(os.getcwd(), relname)
+
+    def get_jit_include_dir(self) -> str:
+        return INCLUDE_DIR
+
     def compile(self, suppress_compilation: bool, suppress_code_writing: bool, quiet: bool, extra_flags: List[str]) -> bool:
         raise NotImplementedError
 
@@ -77,6 +123,7 @@ class CudaCCompiler(BaseCCompiler):
     the path of the plugin .so (kept in-tree under pyoomph_b200/_jit so that it travels with the repository)."""
     compiler_id = "cuda"
     compiler_quality = 1.0
+    code_extension = ".cu"
 
     def __init__(self):
         self.nvcc = find_nvcc()
@@ -84,6 +131,9 @@ class CudaCCompiler(BaseCCompiler):
         self.fast_math = False
         self.keep_source = True
         self.last_log = ""
+        # directory of the reference's jitbridge.h (pyoomph ships it as its JIT include directory, src/ccompiler.hpp:31): when present the
+        # plugin also exports the reference's own JIT_ELEMENT_init (cuda_emitter._emit_jit_element_init)
+        self.jitbridge_include: Optional[str] = find_jitbridge_include()
 
     def check_avail(self) -> bool:
         return self.nvcc is not None
@@ -100,6 +150,8 @@ class CudaCCompiler(BaseCCompiler):
             fl.append("--use_fast_math")
         else:
             fl += ["--fmad=true"]
+        if self.jitbridge_include:
+            fl += ["-DPB2_WITH_JITBRIDGE", "-I", self.jitbridge_include]
         return fl + self.extra_flags
 
     def compile_code(self, source: str, name: str, *, force: bool = False, quiet: bool = True) -> str:
@@ -112,26 +164,46 @@ class CudaCCompiler(BaseCCompiler):
         so = os.path.join(JIT_DIR, "%s_%s.so" % (name, tag))
         if os.path.exists(so) and not force:
             return so
-        # several ranks may compile the same class at once: build under a private name, publish atomically
-        tmp_so = "%s.%d.tmp" % (so, os.getpid())
-        tmp_cu = os.path.join(JIT_DIR, "%s_%s.%d.cu" % (name, tag, os.getpid()))
-        with open(tmp_cu, "w") as f:
+        # several ranks may compile the same class at once: build under a private trunk, publish atomically
+        tmp_trunk = os.path.join(JIT_DIR, "%s_%s.%d" % (name, tag, os.getpid()))
+        with open(tmp_trunk + ".cu", "w") as f:
             f.write(source)
-        os.replace(tmp_cu, cu)
-        cmd = [self.nvcc] + self.flags() + [cu, "-o", tmp_so]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        self.last_log = r.stdout + r.stderr
-        with open(os.path.join(JIT_DIR, "%s_%s.log" % (name, tag)), "w") as f:
-            f.write(" ".join(cmd) + "\n" + self.last_log)
-        if r.returncode != 0:
-            raise RuntimeError("nvcc failed for %s:\n%s" % (cu, self.last_log[-6000:]))
-        os.replace(tmp_so, so)
-        if not quiet:
-            print(self.last_log)
+        self.set_code_from_file(tmp_trunk)
+        try:
+            self.compile(False, False, quiet, [])
+        finally:
+            os.replace(tmp_trunk + ".cu", cu)
+            if os.path.exists(tmp_trunk + ".log"):
+                os.replace(tmp_trunk + ".log", os.path.join(JIT_DIR, "%s_%s.log" % (name, tag)))
+        os.replace(tmp_trunk + ".so", so)
         return so
 
     def compile(self, suppress_compilation: bool, suppress_code_writing: bool, quiet: bool, extra_flags: List[str]) -> bool:
-        raise RuntimeError("CudaCCompiler is driven through compile_code(); see INTEGRATION.md for the pyoomph-side hook")
+        """The reference's compiler-plugin contract (src/ccompiler.hpp:69, pyoomph/generic/ccompiler.py:120-143): compile the generated
+        source <trunk>.cu (set_code_from_file) into <trunk>.so with nvcc for sm_100a.  suppress_compilation: nothing is done (the host
+        reuses an existing library); suppress_code_writing: the source was not rewritten, an existing <trunk>.so is kept as it is
+        (like TCCBoxCompiler.compile).  Returns True; a failing nvcc raises with its log."""
+        if suppress_compilation:
+            return True
+        if not self.check_avail():
+            raise RuntimeError("nvcc not found: the CUDA assembly path cannot be built (no CPU fallback exists)")
+        src, lib = self.get_code_filename(), self.get_lib_filename()
+        if suppress_code_writing and os.path.exists(lib):
+            return True
+        if not os.path.exists(src):
+            raise RuntimeError("generated CUDA source %s does not exist" % src)
+        cmd = [self.nvcc] + self.flags() + list(extra_flags) + [src, "-o", lib]
+        if not quiet:
+            print("Compiling " + src + " with jit-include dir " + self.get_jit_include_dir())
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        self.last_log = r.stdout + r.stderr
+        with open(self.get_code_trunk() + ".log", "w") as f:
+            f.write(" ".join(cmd) + "\n" + self.last_log)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (src, self.last_log[-6000:]))
+        if not quiet:
+            print(self.last_log)
+        return True
 
 
 def get_ccompiler(compiler_id: str = "cuda") -> BaseCCompiler:

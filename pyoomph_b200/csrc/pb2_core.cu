@@ -33,6 +33,13 @@ static int fail(const std::string &m)
     if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_));         \
   } while (0)
 
+#define NEED_DEVICE(p)                                                                                          \
+  do                                                                                                            \
+  {                                                                                                             \
+    if ((p)->device < 0) return fail("pattern-only problem (created with device < 0): it holds no device data"); \
+    CUDA_OK(cudaSetDevice((p)->device));                                                                        \
+  } while (0)
+
 struct pb2_class
 {
   void *handle = nullptr;
@@ -141,9 +148,23 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   *out = nullptr;
   const double t_create0 = omp_get_wtime();
   const pb2_class_info &ci = cls->table.info;
-  CUDA_OK(cudaSetDevice(device));
+  // device < 0: PATTERN-ONLY problem -- colouring, schedule, CSR pattern and position maps are built on the host and nothing touches
+  // CUDA (for hosts that need row_start / column_index before a device is chosen, and for testing the pattern without a GPU);
+  // every entry point that would compute refuses such a problem
+  const bool dev = device >= 0;
+  if (dev) CUDA_OK(cudaSetDevice(device));
   pb2_problem *p = new pb2_problem;
-  CUDA_OK(cudaDeviceGetAttribute(&p->n_sms, cudaDevAttrMultiProcessorCount, device));
+  if (dev) CUDA_OK(cudaDeviceGetAttribute(&p->n_sms, cudaDevAttrMultiProcessorCount, device));
+  const bool setup_timing = getenv("PB2_SETUP_TIMING") != nullptr;
+  double t_phase = omp_get_wtime();
+  auto phase = [&](const char *what) {
+    if (setup_timing)
+    {
+      const double now = omp_get_wtime();
+      fprintf(stderr, "[pb2 setup] %-28s %.3f s\n", what, now - t_phase);
+      t_phase = now;
+    }
+  };
   p->cls = cls;
   p->device = device;
   p->n_elem = m->n_elem;
@@ -189,6 +210,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
     for (int l = 0; l < nn; l++) node_mask[m->elem_nodes[e * nn + l]] |= (uint64_t)1 << c;
   }
   std::vector<uint64_t>().swap(node_mask);
+  phase("element colouring");
   // ---- schedule (DESIGN.md "Schedule"): elements are grouped into compact patches; patches are coloured (two patches
   // sharing a node get different colours) and a patch colour is a TILE: all patches of a tile are independent and
   // are processed concurrently by different thread blocks, each block running the element colours of its patches
@@ -285,6 +307,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
       npcol = std::max(npcol, c + 1);
     }
   }
+  phase("patch colouring");
   // units: consecutive patches of one tile
   int unit_patches = 4;
   if (const char *cs = getenv("PB2_UNIT_PATCHES")) unit_patches = std::max(1, atoi(cs));
@@ -353,6 +376,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   for (long long e = 0; e < ne; e++) p->unit_begin[(size_t)unit_rank[unit_of_patch[patch_of[e]]] + 1]++;
   for (int u = 0; u < nunit; u++) p->unit_begin[u + 1] += p->unit_begin[u];
 
+  phase("schedule order");
   // ---- permuted element tables
   std::vector<int> elem_nodes((size_t)ne * nn), elem_eqn((size_t)ne * nd);
 #pragma omp parallel for schedule(static)
@@ -370,6 +394,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
 
   p->h_elem_nodes = elem_nodes;
 
+  phase("element tables");
   // ---- dof -> elements adjacency (permuted element ids)
   const long long nrow = m->n_dof;
   std::vector<int> adj_start(nrow + 1, 0);
@@ -403,6 +428,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
     std::vector<int> fp(ex_start.begin(), ex_start.end() - 1);
     for (long long i = 0; i < m->n_extra; i++) ex_col[fp[m->extra_rows[i]]++] = m->extra_cols[i];
   }
+  phase("adjacency");
   // ---- CSR pattern, ascending columns: pass 1 counts, pass 2 fills
   p->row_start.assign(nrow + 1, 0);
   for (int pass = 0; pass < 2; pass++)
@@ -446,6 +472,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   std::vector<int>().swap(adj);
   std::vector<int>().swap(adj_start);
 
+  phase("CSR pattern");
   // ---- element -> CSR position maps
   std::vector<int> elem_csr((size_t)ne * nd * nd), elem_res((size_t)ne * nd);
 #pragma omp parallel
@@ -476,6 +503,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
       }
     }
   }
+  phase("position maps");
   // ---- first-touch flags in launch order (colour-major = permuted order): the first element to reach an
   // entry stores, later ones add; no zero-fill of the outputs is needed and the sum order is fixed.
   {
@@ -498,7 +526,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
       for (long long i = 0; i < p->nnz; i++)
         if (!(touched[(size_t)i >> 3] & (1u << (i & 7)))) unt.push_back((int)i);
       p->n_untouched = (long long)unt.size();
-      if (upload(&p->d_untouched, unt))
+      if (dev && upload(&p->d_untouched, unt))
       {
         pb2_problem_free(p); // releases whatever has been uploaded so far
         return 1;
@@ -518,6 +546,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
     }
   }
 
+  phase("first-touch flags");
   // ---- compress the position map: per local row its CSR row start (int32) and per (row,col) the offset inside the
   // row plus a first-touch bit, 8 bits if every row is shorter than 127 entries, else 16 (4*ndof^2 -> ndof^2 bytes)
   int maxlen = 0;
@@ -565,6 +594,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   }
   std::vector<int>().swap(elem_csr);
 
+  phase("map compression");
   // ---- dof -> nodal storage target for set_dofs: >=0 index into node_val (t=0), <0: ~index into node_pos (t=0)
   std::vector<long long> dof_target(nrow, PB2_DOF_NO_TARGET);
   for (long long n = 0; n < m->n_node; n++)
@@ -582,6 +612,13 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
       }
   }
 
+  phase("dof targets");
+  p->setup_seconds = omp_get_wtime() - t_create0;
+  if (!dev)
+  {
+    *out = p;
+    return 0;
+  }
   // ---- upload
   if (upload(&p->d_elem_nodes, elem_nodes) || upload(&p->d_elem_eqn, elem_eqn) || upload(&p->d_elem_rowstart, elem_rowstart) ||
       upload(&p->d_elem_res, elem_res) || upload(&p->d_dof_target, dof_target))
@@ -614,6 +651,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   CUDA_OK(cudaHostGetDevicePointer((void **)&p->d_status, p->h_status, 0));
   CUDA_OK(cudaEventCreateWithFlags(&p->ev_inputs, cudaEventDisableTiming));
   CUDA_OK(cudaEventRecord(p->ev_inputs, 0));
+  phase("upload + device buffers");
   p->setup_seconds = omp_get_wtime() - t_create0;
   *out = p;
   return 0;
@@ -622,6 +660,11 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
 extern "C" void pb2_problem_free(pb2_problem *p)
 {
   if (!p) return;
+  if (p->device < 0)
+  {
+    delete p;
+    return;
+  }
   cudaSetDevice(p->device);
   cudaFree(p->d_elem_nodes);
   cudaFree(p->d_elem_eqn);
@@ -673,7 +716,7 @@ extern "C" int pb2_problem_num_launches(pb2_problem *p) { return p->n_tiles; }
 extern "C" int pb2_problem_set_nodal_values(pb2_problem *p, int t, const double *values)
 {
   if (t < 0 || t >= p->T_val) return fail("history index out of range");
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   const size_t n = (size_t)p->n_node * p->nval;
   CUDA_OK(cudaMemcpy(p->d_node_val + (size_t)t * n, values, n * sizeof(double), cudaMemcpyHostToDevice));
   return inputs_changed(p);
@@ -682,7 +725,7 @@ extern "C" int pb2_problem_set_nodal_values(pb2_problem *p, int t, const double 
 extern "C" int pb2_problem_set_nodal_positions(pb2_problem *p, int t, const double *pos)
 {
   if (t < 0 || t >= p->T_pos) return fail("position history index out of range");
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   const size_t n = (size_t)p->n_node * p->dim;
   CUDA_OK(cudaMemcpy(p->d_node_pos + (size_t)t * n, pos, n * sizeof(double), cudaMemcpyHostToDevice));
   return inputs_changed(p);
@@ -690,7 +733,7 @@ extern "C" int pb2_problem_set_nodal_positions(pb2_problem *p, int t, const doub
 
 extern "C" int pb2_problem_set_lagrangian_positions(pb2_problem *p, const double *pos)
 {
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   CUDA_OK(cudaMemcpy(p->d_node_lagr, pos, (size_t)p->n_node * p->dim * sizeof(double), cudaMemcpyHostToDevice));
   return inputs_changed(p);
 }
@@ -744,7 +787,7 @@ static int scatter_dofs_from_device(pb2_problem *p, cudaStream_t s, int t = 0)
 
 extern "C" int pb2_problem_set_dofs(pb2_problem *p, const double *dofs)
 {
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   CUDA_OK(cudaMemcpy(p->d_dofs, dofs, (size_t)p->n_dof * sizeof(double), cudaMemcpyHostToDevice));
   return scatter_dofs_from_device(p, 0);
 }
@@ -753,7 +796,7 @@ extern "C" int pb2_problem_set_dofs(pb2_problem *p, const double *dofs)
 extern "C" int pb2_problem_set_history_dofs(pb2_problem *p, int t, const double *dofs)
 {
   if (t < 0 || t >= std::max(p->T_val, p->T_pos)) return fail("history index out of range");
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   if (t > 0 && p->T_pos <= t && p->cls->table.info.moving_nodes) return fail("position history level not stored");
   CUDA_OK(cudaMemcpy(p->d_dofs, dofs, (size_t)p->n_dof * sizeof(double), cudaMemcpyHostToDevice));
   return scatter_dofs_from_device(p, 0, t);
@@ -763,7 +806,7 @@ extern "C" int pb2_problem_set_history_dofs(pb2_problem *p, int t, const double 
 // values of level t-1, level 0 keeps the current values as the initial guess of the new step; device to device, no host copy
 extern "C" int pb2_problem_shift_time_values(pb2_problem *p)
 {
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   const pb2_class_info &ci = p->cls->table.info;
   const size_t nv = (size_t)p->n_node * std::max(1, ci.nval) * sizeof(double), np_ = (size_t)p->n_node * ci.nodal_dim * sizeof(double);
   for (int t = p->T_val - 1; t >= 1; t--)
@@ -997,7 +1040,7 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
 
 extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int param_index, unsigned flag, void *cuda_stream)
 {
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   if (flag > 2u) return fail("flag must be 0, 1 or 2");
   if (flag == 2u && !p->d_mass) CUDA_OK(cudaMalloc((void **)&p->d_mass, std::max<size_t>(1, p->nnz) * sizeof(double)));
   return run_routine(p, 0, residual_index, param_index, flag, p->d_jac, p->d_mass, nullptr, cuda_stream);
@@ -1005,7 +1048,7 @@ extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int para
 
 extern "C" int pb2_problem_assemble_hessian(pb2_problem *p, int residual_index, unsigned flag, int n_vec, const double *Y, void *cuda_stream)
 {
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   if (!p->cls->table.info.hessian_generated) return fail("this element class was generated without Hessian routines");
   if (flag != 1u && flag != 2u) return fail("Hessian assembly: flag must be 1 (d(J.Y)/dU) or 2 (+ d(M.Y)/dU)");
   if (n_vec < 1) return fail("n_vec must be positive");
@@ -1032,7 +1075,7 @@ extern "C" int pb2_problem_assemble_hessian(pb2_problem *p, int residual_index, 
 
 extern "C" int pb2_problem_fetch_hessian(pb2_problem *p, int v, double *jac_hessian_vals, double *mass_hessian_vals)
 {
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   if (v < 0 || v >= p->hess_nvec) return fail("Hessian vector index out of range");
   CUDA_OK(cudaDeviceSynchronize());
   if (check_status(p)) return 1;
@@ -1100,7 +1143,7 @@ static __global__ void __launch_bounds__(1024) pb2_reduce_integrals(const double
 
 extern "C" int pb2_problem_eval_integrals(pb2_problem *p, double *out, int n_out)
 {
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   const pb2_class_info &ci = p->cls->table.info;
   if (ci.n_integrals < 1) return fail("this element class defines no integral expressions");
   if (n_out != ci.n_integrals) return fail("n_out must equal the number of integral expressions of the class");
@@ -1182,7 +1225,7 @@ static int exchange_grid(pb2_problem *p, long long total) { return (int)std::max
 extern "C" int pb2_problem_pack_rows(pb2_problem *p, const long long *rows, long long n_rows, const long long *pos, long long n_pos, unsigned flag,
                                      double *buf, void *cuda_stream)
 {
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   if (flag > 2u) return fail("flag must be 0, 1 or 2");
   if (flag == 2u && !p->d_mass) return fail("no mass matrix has been assembled");
   const long long total = n_rows + (long long)flag * n_pos;
@@ -1196,7 +1239,7 @@ extern "C" int pb2_problem_pack_rows(pb2_problem *p, const long long *rows, long
 extern "C" int pb2_problem_unpack_add(pb2_problem *p, const long long *rows, long long n_rows, const long long *pos, long long n_pos, unsigned flag,
                                       const double *buf, void *cuda_stream)
 {
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   if (flag > 2u) return fail("flag must be 0, 1 or 2");
   if (flag == 2u && !p->d_mass) return fail("no mass matrix has been assembled");
   const long long total = n_rows + (long long)flag * n_pos;
@@ -1209,7 +1252,7 @@ extern "C" int pb2_problem_unpack_add(pb2_problem *p, const long long *rows, lon
 
 extern "C" int pb2_problem_fetch(pb2_problem *p, double *residual, double *jac_vals, double *mass_vals)
 {
-  CUDA_OK(cudaSetDevice(p->device));
+  NEED_DEVICE(p);
   CUDA_OK(cudaDeviceSynchronize());
   if (check_status(p)) return 1;
   if (residual) CUDA_OK(cudaMemcpy(residual, p->d_residual, (size_t)p->n_dof * sizeof(double), cudaMemcpyDeviceToHost));

@@ -1747,7 +1747,140 @@ class CudaEmitter:
         w("  table->query = &pb2_query;")
         w("  table->launch = &pb2_launch;")
         w("}")
+        self._emit_jit_element_init(o)
         return "\n".join(o) + "\n"
+
+    def _emit_jit_element_init(self, o: List[str]):
+        """The reference's own plugin entry point, ``JIT_ELEMENT_init(JITFuncSpec_Table_FiniteElement_t*)`` (src/jitbridge.h:499, emitted by
+        FiniteElementCode::write_code_info, src/codegen.cpp:6398-7090), next to JIT_ELEMENT_init_cuda in the SAME shared object, so that the
+        host's loader (DynamicBulkElementCode ctor, src/problem.cpp:101-142) accepts a CUDA plugin unchanged: the check_compiler_size
+        handshake, every metadata field the host reads (dimensions, per-space field counts / names / nodal and buffer offsets, residual
+        names, required shapes, global parameter indices, moving_nodes, max_dt_order, integration_order, dominant_space, integral
+        expression names, domain name) and clean_up.  The per-element CPU routines of the table do not exist in a CUDA plugin (no CPU
+        fallback): their slots hold a function that reports this and aborts; assembly goes through the batched launchers of the GPU block.
+        Compiled only when the reference's jitbridge.h is on the include path (-DPB2_WITH_JITBRIDGE, CudaCCompiler.jitbridge_include):
+        the table layout is the reference's own header, never a restatement."""
+        code = self.code
+        w = o.append
+        nf = code.nodal_fields()
+        c2 = [f for f in nf if f.space == "C2"]
+        c1 = [f for f in nf if f.space == "C1"]
+        rn = code.residual_names()
+        dim = self.dim
+        nres = max(1, len(rn))
+        w("")
+        w("#ifdef PB2_WITH_JITBRIDGE")
+        w("// ---- the reference's plugin contract (src/jitbridge.h:329-499), compiled against the reference's own header")
+        w("#define JIT_ELEMENT_SHARED_LIB")
+        w("#include <stdio.h>")
+        w('#include "jitbridge.h"')
+        w("static JITFuncSpec_Table_FiniteElement_t* my_func_table;")
+        w("static void pb2_no_cpu_rjm(const JITElementInfo_t*, const JITShapeInfo_t*, double*, double*, double*, unsigned)")
+        w('{ fprintf(stderr, "pyoomph_b200: element class \'%s\' is a CUDA plugin: per-element CPU routines do not exist, assemble through JIT_ELEMENT_init_cuda / libpyoomph_b200\\n"); abort(); }' % self.name)
+        w("static void pb2_no_cpu_hvp(const JITElementInfo_t*, const JITShapeInfo_t*, const double*, double*, double*, unsigned, unsigned)")
+        w('{ fprintf(stderr, "pyoomph_b200: element class \'%s\' is a CUDA plugin: per-element CPU routines do not exist, assemble through JIT_ELEMENT_init_cuda / libpyoomph_b200\\n"); abort(); }' % self.name)
+        w("static double pb2_no_cpu_integral(const JITElementInfo_t*, const JITShapeInfo_t*, unsigned) { pb2_no_cpu_rjm(0, 0, 0, 0, 0, 0u); return 0.0; }")
+        w("static void pb2_free_names(char** tab, unsigned n) { if (!tab) return; for (unsigned i = 0; i < n; ++i) pyoomph_tested_free(tab[i]); free(tab); }")
+        w("static void clean_up(JITFuncSpec_Table_FiniteElement_t* functable)")
+        w("{")
+        w("  pb2_free_names(functable->fieldnames_C2, functable->numfields_C2); functable->fieldnames_C2 = 0;")
+        w("  pb2_free_names(functable->fieldnames_C1, functable->numfields_C1); functable->fieldnames_C1 = 0;")
+        w("  pb2_free_names(functable->fieldnames_Pos, functable->numfields_Pos); functable->fieldnames_Pos = 0;")
+        w("  pb2_free_names(functable->res_jac_names, functable->num_res_jacs); functable->res_jac_names = 0;")
+        w("  pb2_free_names(functable->integral_expressions_names, functable->numintegral_expressions); functable->integral_expressions_names = 0;")
+        w("  if (functable->ParameterDerivative) { for (unsigned i = 0; i < functable->num_res_jacs; ++i) pyoomph_tested_free(functable->ParameterDerivative[i]); free(functable->ParameterDerivative); functable->ParameterDerivative = 0; }")
+        for nm in ("global_paramindices", "global_parameters", "ResidualAndJacobian", "ResidualAndJacobianSteady", "ResidualAndJacobian_NoHang",
+                   "shapes_required_ResJac", "shapes_required_Hessian", "HessianVectorProduct", "missing_residual_assembly",
+                   "has_constant_mass_matrix_for_sure", "temporal_error_scales", "discontinuous_refinement_exponents", "dominant_space", "domain_name"):
+            w("  pyoomph_tested_free(functable->%s); functable->%s = 0;" % (nm, nm))
+        w("}")
+        w("")
+        w('extern "C" JIT_API void JIT_ELEMENT_init(JITFuncSpec_Table_FiniteElement_t* functable)')
+        w("{")
+        w("  // the size handshake of src/codegen.cpp:6403-6421: the host compares with its own sizeof and refuses a mismatching compiler")
+        for t, nm in (("char", "char"), ("unsigned short", "unsigned short"), ("unsigned int", "unsigned int"), ("unsigned long int", "unsigned long int"),
+                      ("unsigned long long int", "unsigned long long int"), ("float", "float"), ("double", "double"), ("size_t", "size_t"),
+                      ("struct JITElementInfo", "struct JITElementInfo"), ("struct JITHangInfoEntry", "struct JITHangInfoEntry"),
+                      ("struct JITHangInfo", "struct JITHangInfo"), ("struct JITShapeInfo", "struct JITShapeInfo"),
+                      ("struct JITFuncSpec_RequiredShapes_FiniteElement", "struct JITFuncSpec_RequiredShapes_FiniteElement"),
+                      ("struct JITFuncSpec_Callback_Entry", "struct JITFuncSpec_Callback_Entry"),
+                      ("struct JITFuncSpec_MultiRet_Entry", "struct JITFuncSpec_MultiRet_Entry"),
+                      ("struct JITFuncSpec_Table_FiniteElement", "struct JITFuncSpec_Table_FiniteElement")):
+            w('  if (functable->check_compiler_size) functable->check_compiler_size(sizeof(%s), sizeof(%s), (char*)"%s");' % (t, t, nm))
+        w("  functable->nodal_dim = %d; functable->lagr_dim = %d;" % (dim, dim))
+        w("  functable->fd_jacobian = false; functable->fd_position_jacobian = false; functable->with_adaptivity = false;")
+        w("  functable->debug_jacobian_epsilon = 0.0; functable->stop_on_jacobian_difference = false;")
+        # position space: coordinate_*, lagrangian_* (src/codegen.cpp:2816-2835); continuous spaces in the order C2TB|C2|C1TB|C1
+        pos_names = ["coordinate_" + d for d in ex.DIRS[:dim]] + ["lagrangian_" + d for d in ex.DIRS[:dim]]
+        w("  functable->numfields_Pos = %d;" % len(pos_names))
+        w("  functable->fieldnames_Pos = (char**)malloc(sizeof(char*) * %d);" % len(pos_names))
+        for i, n in enumerate(pos_names):
+            w('  SET_INTERNAL_FIELD_NAME(functable->fieldnames_Pos, %d, "%s");' % (i, n))
+        off = 0
+        for sp_name, fl in (("C2", c2), ("C1", c1)):
+            w("  functable->numfields_%s = functable->numfields_%s_bulk = functable->numfields_%s_basebulk = functable->numfields_%s_new = %d;" % (
+                sp_name, sp_name, sp_name, sp_name, len(fl)))
+            w("  functable->nodal_offset_%s_basebulk = %d; functable->buffer_offset_%s_basebulk = %d;" % (sp_name, off, sp_name, off))
+            if fl:
+                w("  functable->fieldnames_%s = (char**)malloc(sizeof(char*) * %d);" % (sp_name, len(fl)))
+                for f in fl:
+                    w('  SET_INTERNAL_FIELD_NAME(functable->fieldnames_%s, %d, "%s");' % (sp_name, f.index - off, f.name))
+            off += len(fl)
+        w("  functable->hangindex_C1 = functable->hangindex_C2 = functable->hangindex_C1TB = functable->hangindex_C2TB = functable->hangindex_Pos = -1;")
+        w("  functable->num_res_jacs = %d; functable->current_res_jac = 0;" % len(rn))
+        w("  functable->res_jac_names = (char**)calloc(%d, sizeof(char*));" % nres)
+        for i, n in enumerate(rn):
+            w('  SET_INTERNAL_FIELD_NAME(functable->res_jac_names, %d, "%s");' % (i, n))
+        for nm, ty in (("ResidualAndJacobian", "JITFuncSpec_ResidualAndJacobian_FiniteElement"), ("ResidualAndJacobianSteady", "JITFuncSpec_ResidualAndJacobian_FiniteElement"),
+                       ("ResidualAndJacobian_NoHang", "JITFuncSpec_ResidualAndJacobian_FiniteElement"), ("HessianVectorProduct", "JITFuncSpec_HessianVectorProduct_FiniteElement"),
+                       ("shapes_required_ResJac", "JITFuncSpec_RequiredShapes_FiniteElement_t"), ("shapes_required_Hessian", "JITFuncSpec_RequiredShapes_FiniteElement_t")):
+            w("  functable->%s = (%s*)calloc(%d, sizeof(%s));" % (nm, ty, nres, ty))
+        w("  functable->missing_residual_assembly = (bool*)calloc(%d, sizeof(bool));" % nres)
+        w("  functable->has_constant_mass_matrix_for_sure = (bool*)calloc(%d, sizeof(bool));" % nres)
+        npar = len(code.global_params)
+        w("  functable->numglobal_params = %d;" % npar)
+        w("  functable->global_paramindices = (unsigned*)malloc(sizeof(unsigned) * %d);" % max(1, npar))
+        w("  functable->global_parameters = (double**)calloc(%d, sizeof(double*));" % max(1, npar))
+        for k in range(npar):
+            w("  functable->global_paramindices[%d] = %d;   // '%s': the host resolves names to its parameter table (src/codegen.cpp:6700-6706)" % (k, k, code.global_params[k]))
+        w("  functable->ParameterDerivative = (JITFuncSpec_ResidualAndJacobian_FiniteElement**)calloc(%d, sizeof(JITFuncSpec_ResidualAndJacobian_FiniteElement*));" % nres)
+        for i, n in enumerate(rn):
+            form = self.routines[[r.key for r in self.routines].index("r%d" % i)].form
+            need_lagr = any(a.deriv.startswith("dX") or a.field.startswith("lagrangian_") for a in form.atoms) or form.uses_dX
+            spaces_used = {code.fields[a.field].space for a in form.atoms} | {code.fields[s_.field].space for s_ in form.slots}
+            for S in ("C2", "C1"):
+                if S in spaces_used or (S == "C2" and "Pos" in spaces_used):
+                    w("  functable->shapes_required_ResJac[%d].psi_%s = true; functable->shapes_required_ResJac[%d].dx_psi_%s = true;%s" % (
+                        i, S, i, S, (" functable->shapes_required_ResJac[%d].dX_psi_%s = true;" % (i, S)) if need_lagr else ""))
+            w("  functable->shapes_required_ResJac[%d].psi_Pos = true; functable->shapes_required_ResJac[%d].dx_psi_Pos = true;%s" % (
+                i, i, (" functable->shapes_required_ResJac[%d].dX_psi_Pos = true;" % i) if need_lagr else ""))
+            w("  functable->shapes_required_Hessian[%d] = functable->shapes_required_ResJac[%d];" % (i, i))
+            w("  functable->ResidualAndJacobian[%d] = functable->ResidualAndJacobianSteady[%d] = functable->ResidualAndJacobian_NoHang[%d] = &pb2_no_cpu_rjm;" % (i, i, i))
+            w("  functable->HessianVectorProduct[%d] = &pb2_no_cpu_hvp;" % i)
+            w("  functable->ParameterDerivative[%d] = (JITFuncSpec_ResidualAndJacobian_FiniteElement*)calloc(%d, sizeof(JITFuncSpec_ResidualAndJacobian_FiniteElement));" % (i, max(1, npar)))
+            for k in range(npar):
+                w("  functable->ParameterDerivative[%d][%d] = &pb2_no_cpu_rjm;" % (i, k))
+        w("  functable->hessian_generated = %s;" % ("true" if (self.hessian and self.pipeline) else "false"))
+        w("  functable->use_shared_shape_buffer_during_multi_assemble = true;")
+        w("  functable->temporal_error_scales = (double*)calloc(%d, sizeof(double));" % max(1, len(nf)))
+        w("  functable->discontinuous_refinement_exponents = (double*)calloc(%d, sizeof(double));" % max(1, len(nf)))
+        inames = code.integral_expression_names()
+        w("  functable->numintegral_expressions = %d;" % len(inames))
+        if inames:
+            w("  functable->integral_expressions_names = (char**)malloc(sizeof(char*) * %d);" % len(inames))
+            for i, n in enumerate(inames):
+                w('  SET_INTERNAL_FIELD_NAME(functable->integral_expressions_names, %d, "%s");' % (i, n))
+            w("  functable->EvalIntegralExpression = &pb2_no_cpu_integral;")
+            w("  functable->shapes_required_IntegralExprs = functable->shapes_required_ResJac[0];")
+        w("  functable->max_dt_order = %d;" % code.max_dt_order())
+        w("  functable->moving_nodes = %s;" % ("true" if code.coordinates_as_dofs else "false"))
+        w("  functable->integration_order = 0;     // the element's default scheme: Gauss<DIM,3> (src/elements.cpp:184-249)")
+        w('  SET_INTERNAL_NAME(functable->dominant_space, "C2");')
+        w('  SET_INTERNAL_NAME(functable->domain_name, "%s");' % self.name)
+        w("  functable->clean_up = &clean_up;")
+        w("  my_func_table = functable;")
+        w("}")
+        w("#endif  // PB2_WITH_JITBRIDGE")
 
     def algorithmic_bytes(self, what: int) -> float:
         """B_el of SURVEY 8(d): gather (positions, nodal values x history, local->global map) + scatter
