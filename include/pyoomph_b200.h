@@ -59,6 +59,9 @@ void pb2_problem_free(pb2_problem *p);
 
 /* pattern of the assembled matrix (host memory owned by the problem): CRDoubleMatrix row_start/column_index */
 int pb2_problem_pattern(pb2_problem *p, const int **row_start, const int **column_index, long long *nnz, long long *n_rows);
+/* pattern-only problems: the schedule (perm[q] = mesh element at scheduled position q) and the element -> CSR position maps in the
+ * layout the kernels read (pb2_kernel_args: elem_rowstart, elem_off with map_bits, elem_res), host memory owned by the problem */
+int pb2_problem_host_maps(pb2_problem *p, const int **perm, const int **elem_rowstart, const void **elem_off, int *map_bits, const int **elem_res);
 int pb2_problem_num_colours(pb2_problem *p);
 int pb2_problem_num_launches(pb2_problem *p); /* tiles (= patch colours, device-side gates) one persistent launch walks through */
 

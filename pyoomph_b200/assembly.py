@@ -80,7 +80,7 @@ def load_library() -> ctypes.CDLL:
                "pb2_problem_fetch", "pb2_problem_assemble_host", "pb2_problem_num_colours", "pb2_version",
                "pb2_problem_assemble_hessian", "pb2_problem_fetch_hessian", "pb2_problem_hessian_vector_products",
                "pb2_problem_pack_rows", "pb2_problem_unpack_add", "pb2_problem_eval_integrals", "pb2_problem_shift_time_values",
-               "pb2_problem_set_history_dofs", "pb2_measure_fp64_peak"):
+               "pb2_problem_set_history_dofs", "pb2_measure_fp64_peak", "pb2_problem_host_maps"):
         getattr(L, fn).restype = ctypes.c_int
     L.pb2_problem_setup_seconds.restype = ctypes.c_double
     _LIB = L
@@ -239,6 +239,8 @@ class B200Assembly(CustomAssemblyBase):
         if not hasattr(self, "_params"):
             self._params = np.zeros(max(1, self.info.n_params))
         self._stale = False
+        if device < 0:
+            return                      # pattern-only problem: no device data to initialise
         self.set_nodal_positions(0, mesh.node_pos)
         for t in range(1, self.info.n_hist_pos):
             self.set_nodal_positions(t, mesh.node_pos)
@@ -430,6 +432,19 @@ class B200Assembly(CustomAssemblyBase):
         """interface exchange, owner side: residual[rows] += ..., jac[pos] += ... from a received buffer"""
         _check(self.lib.pb2_problem_unpack_add(self.prob, ctypes.c_void_p(rows_ptr), ctypes.c_longlong(n_rows), ctypes.c_void_p(pos_ptr),
                                                ctypes.c_longlong(n_pos), ctypes.c_uint(flag), ctypes.c_void_p(buf_ptr), ctypes.c_void_p(stream or 0)))
+
+    def host_maps(self):
+        """pattern-only problems (device=-1): (perm, elem_rowstart[n_elem, ndof], elem_off[n_elem, ndof, ndof], elem_res[n_elem, ndof]) as the
+        kernels read them, elements in scheduled order (perm[q] = mesh element)"""
+        perm, rs, off, res, bits = c_int_p(), c_int_p(), ctypes.c_void_p(), c_int_p(), ctypes.c_int()
+        _check(self.lib.pb2_problem_host_maps(self.prob, ctypes.byref(perm), ctypes.byref(rs), ctypes.byref(off), ctypes.byref(bits), ctypes.byref(res)))
+        ne, nd = self.n_elem, int(self.info.ndof_el)
+        if ne == 0:
+            return np.zeros(0, np.int32), np.zeros((0, nd), np.int32), np.zeros((0, nd, nd), np.uint8), np.zeros((0, nd), np.int32)
+        ty = ctypes.c_uint8 if bits.value == 8 else ctypes.c_uint16
+        offa = np.ctypeslib.as_array(ctypes.cast(off, ctypes.POINTER(ty)), shape=(ne, nd, nd)).copy()
+        return (np.ctypeslib.as_array(perm, shape=(ne,)).copy(), np.ctypeslib.as_array(rs, shape=(ne, nd)).copy(), offa,
+                np.ctypeslib.as_array(res, shape=(ne, nd)).copy())
 
     def launch_count(self) -> int:
         return int(self.lib.pb2_problem_launch_count(self.prob))

@@ -90,6 +90,10 @@ struct pb2_problem
   int *h_status = nullptr, *d_status = nullptr; // error word of the kernels: mapped pinned host memory, read without a copy
   cudaEvent_t ev_inputs = nullptr; // recorded on the legacy stream after every input update; assemblies on other streams wait for it
   double setup_seconds = 0.0;      // wall time of pb2_problem_create (colouring, pattern, maps, upload)
+  // pattern-only problems (device < 0) keep the maps on the host for inspection (pb2_problem_host_maps)
+  std::vector<int> h_elem_rowstart, h_elem_res;
+  std::vector<uint8_t> h_off8;
+  std::vector<uint16_t> h_off16;
 };
 
 static int inputs_changed(pb2_problem *p);
@@ -429,126 +433,85 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
     for (long long i = 0; i < m->n_extra; i++) ex_col[fp[m->extra_rows[i]]++] = m->extra_cols[i];
   }
   phase("adjacency");
-  // ---- CSR pattern, ascending columns: pass 1 counts, pass 2 fills
+  // ---- CSR pattern, ascending columns.  One pass: every thread takes a contiguous block of rows, sorts the dofs of the row's elements
+  // once and keeps the columns in a private buffer; rows whose element list equals the previous row's (the dofs of one node) reuse its
+  // columns; then prefix sum and parallel copy.
   p->row_start.assign(nrow + 1, 0);
-  for (int pass = 0; pass < 2; pass++)
   {
-#pragma omp parallel
+    const int nth = omp_get_max_threads();
+    std::vector<std::vector<int>> tcols(nth);
+    std::vector<long long> tbeg(nth + 1, 0);
+#pragma omp parallel num_threads(nth)
     {
+      const int t = omp_get_thread_num();
+      const long long r0 = nrow * t / nth, r1 = nrow * (t + 1) / nth;
+      std::vector<int> &buf = tcols[t];
+      buf.reserve((size_t)(r1 - r0) * 40);
       std::vector<int> tmp;
-#pragma omp for schedule(dynamic, 4096)
-      for (long long r = 0; r < nrow; r++)
+      size_t prev_off = 0;
+      int prev_n = -1;
+      for (long long r = r0; r < r1; r++)
       {
-        tmp.clear();
-        for (int a = adj_start[r]; a < adj_start[r + 1]; a++)
+        const int na = adj_start[r + 1] - adj_start[r];
+        const bool same = r > r0 && prev_n >= 0 && ex_start[r + 1] == ex_start[r] && ex_start[r] == ex_start[r - 1] &&
+                          na == adj_start[r] - adj_start[r - 1] && std::equal(adj.begin() + adj_start[r], adj.begin() + adj_start[r + 1], adj.begin() + adj_start[r - 1]);
+        if (same)
         {
-          const int *eq = &elem_eqn[(size_t)adj[a] * nd];
-          for (int k = 0; k < nd; k++)
-            if (eq[k] >= 0) tmp.push_back(eq[k]);
+          const size_t o = buf.size();
+          buf.resize(o + prev_n);
+          std::copy(buf.begin() + prev_off, buf.begin() + prev_off + prev_n, buf.begin() + o);
+          prev_off = o;
         }
-        for (int a = ex_start[r]; a < ex_start[r + 1]; a++) tmp.push_back(ex_col[a]);
-        std::sort(tmp.begin(), tmp.end());
-        const int n = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
-        if (pass == 0)
-          p->row_start[r + 1] = n;
         else
-          std::copy(tmp.begin(), tmp.begin() + n, p->col_index.begin() + p->row_start[r]);
-      }
-    }
-    if (pass == 0)
-    {
-      long long tot = 0;
-      for (long long r = 0; r < nrow; r++) tot += p->row_start[r + 1];
-      if (tot >= 0x7fffffffLL)
-      {
-        pb2_problem_free(p); // releases whatever has been uploaded so far
-        return fail("nnz exceeds int32 CSR indexing");
-      }
-      for (long long r = 0; r < nrow; r++) p->row_start[r + 1] += p->row_start[r];
-      p->nnz = p->row_start[nrow];
-      p->col_index.resize(p->nnz);
-    }
-  }
-  std::vector<int>().swap(adj);
-  std::vector<int>().swap(adj_start);
-
-  phase("CSR pattern");
-  // ---- element -> CSR position maps
-  std::vector<int> elem_csr((size_t)ne * nd * nd), elem_res((size_t)ne * nd);
-#pragma omp parallel
-  {
-    std::vector<std::pair<int, int>> sorted(nd);
-#pragma omp for schedule(static)
-    for (long long q = 0; q < ne; q++)
-    {
-      const int *eq = &elem_eqn[(size_t)q * nd];
-      int ns = 0;
-      for (int k = 0; k < nd; k++)
-        if (eq[k] >= 0) sorted[ns++] = {eq[k], k};
-      std::sort(sorted.begin(), sorted.begin() + ns);
-      int *mp = &elem_csr[(size_t)q * nd * nd];
-      for (int i = 0; i < nd * nd; i++) mp[i] = PB2_MAP_SKIP;
-      for (int i = 0; i < nd; i++)
-      {
-        elem_res[(size_t)q * nd + i] = eq[i] >= 0 ? eq[i] : PB2_MAP_SKIP;
-        if (eq[i] < 0) continue;
-        const int rb = p->row_start[eq[i]], re = p->row_start[eq[i] + 1];
-        int pos = rb;
-        for (int s = 0; s < ns; s++)
         {
-          // columns ascending in both lists: advance by binary search from the last hit
-          pos = (int)(std::lower_bound(p->col_index.begin() + pos, p->col_index.begin() + re, sorted[s].first) - p->col_index.begin());
-          mp[i * nd + sorted[s].second] = pos;
+          tmp.clear();
+          for (int a_ = adj_start[r]; a_ < adj_start[r + 1]; a_++)
+          {
+            const int *eq = &elem_eqn[(size_t)adj[a_] * nd];
+            for (int k = 0; k < nd; k++)
+              if (eq[k] >= 0) tmp.push_back(eq[k]);
+          }
+          for (int a_ = ex_start[r]; a_ < ex_start[r + 1]; a_++) tmp.push_back(ex_col[a_]);
+          std::sort(tmp.begin(), tmp.end());
+          prev_n = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+          prev_off = buf.size();
+          buf.insert(buf.end(), tmp.begin(), tmp.begin() + prev_n);
         }
+        p->row_start[r + 1] = prev_n;
       }
+    }
+    phase("  pattern: row sorts");
+    long long tot = 0;
+    for (int t = 0; t < nth; t++)
+    {
+      tbeg[t] = tot;
+      tot += (long long)tcols[t].size();
+    }
+    if (tot >= 0x7fffffffLL)
+    {
+      pb2_problem_free(p); // releases whatever has been uploaded so far
+      return fail("nnz exceeds int32 CSR indexing");
+    }
+    for (long long r = 0; r < nrow; r++) p->row_start[r + 1] += p->row_start[r];
+    p->nnz = tot;
+    p->col_index.resize(p->nnz);
+    phase("  pattern: allocate");
+#pragma omp parallel num_threads(nth)
+    {
+      const int t = omp_get_thread_num();
+      std::copy(tcols[t].begin(), tcols[t].end(), p->col_index.begin() + tbeg[t]);
+      std::vector<int>().swap(tcols[t]);
     }
   }
-  phase("position maps");
-  // ---- first-touch flags in launch order (colour-major = permuted order): the first element to reach an
-  // entry stores, later ones add; no zero-fill of the outputs is needed and the sum order is fixed.
-  {
-    std::vector<uint8_t> touched((size_t)(p->nnz + 7) / 8, 0), rtouched((size_t)(nrow + 7) / 8, 0);
-    for (size_t i = 0; i < elem_csr.size(); i++)
-    {
-      const int v = elem_csr[i];
-      if (v == PB2_MAP_SKIP) continue;
-      uint8_t &b = touched[(size_t)v >> 3];
-      const uint8_t bit = (uint8_t)(1u << (v & 7));
-      if (!(b & bit))
-      {
-        b |= bit;
-        elem_csr[i] = ~v;
-      }
-    }
-    if (m->n_extra > 0)
-    {
-      std::vector<int> unt;
-      for (long long i = 0; i < p->nnz; i++)
-        if (!(touched[(size_t)i >> 3] & (1u << (i & 7)))) unt.push_back((int)i);
-      p->n_untouched = (long long)unt.size();
-      if (dev && upload(&p->d_untouched, unt))
-      {
-        pb2_problem_free(p); // releases whatever has been uploaded so far
-        return 1;
-      }
-    }
-    for (size_t i = 0; i < elem_res.size(); i++)
-    {
-      const int v = elem_res[i];
-      if (v == PB2_MAP_SKIP) continue;
-      uint8_t &b = rtouched[(size_t)v >> 3];
-      const uint8_t bit = (uint8_t)(1u << (v & 7));
-      if (!(b & bit))
-      {
-        b |= bit;
-        elem_res[i] = ~v;
-      }
-    }
-  }
+  phase("CSR pattern");
 
-  phase("first-touch flags");
-  // ---- compress the position map: per local row its CSR row start (int32) and per (row,col) the offset inside the
-  // row plus a first-touch bit, 8 bits if every row is shorter than 127 entries, else 16 (4*ndof^2 -> ndof^2 bytes)
+  // ---- element -> CSR position maps, first-touch flags and their compressed form, in ONE pass over the matrix rows.
+  // Per local row of an element: its CSR row start (int32) and per (row, col) the offset inside the row plus a first-touch bit, 8 bits
+  // if every row is shorter than 127 entries, else 16 (4*ndof^2 -> ndof^2 bytes).  First touch = the element with the smallest
+  // scheduled index q among those reaching an entry stores, later ones add: no zero-fill of the outputs, fixed sum order.
+  // A row walks its elements in ascending q (adj is sorted), merges each element's sorted dof list with the row's columns
+  // (both ascending: one linear walk) and writes that element's slice of the map; rows with the element list of the previous row
+  // (dofs of one node) copy the previous row's slices.
   int maxlen = 0;
   for (long long r = 0; r < nrow; r++) maxlen = std::max(maxlen, p->row_start[r + 1] - p->row_start[r]);
   p->map_bits = maxlen < 127 ? 8 : 16;
@@ -557,44 +520,105 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
     pb2_problem_free(p); // releases whatever has been uploaded so far
     return fail("CSR rows longer than 32766 entries are not supported by the position map");
   }
-  std::vector<int> elem_rowstart((size_t)ne * nd);
-  std::vector<uint8_t> off8;
-  std::vector<uint16_t> off16;
-  if (p->map_bits == 8)
-    off8.resize((size_t)ne * nd * nd);
-  else
-    off16.resize((size_t)ne * nd * nd);
-#pragma omp parallel for schedule(static)
-  for (long long q = 0; q < ne; q++)
+  // dofs of every element sorted by equation, with their local index
+  std::vector<int> sorted_eq((size_t)ne * nd), sorted_k((size_t)ne * nd);
+  std::vector<int> n_sorted(ne);
+#pragma omp parallel
   {
-    const int *eq = &elem_eqn[(size_t)q * nd];
-    for (int i = 0; i < nd; i++)
+    std::vector<std::pair<int, int>> srt(nd);
+#pragma omp for schedule(static)
+    for (long long q = 0; q < ne; q++)
     {
-      const int rs = eq[i] >= 0 ? p->row_start[eq[i]] : -1;
-      elem_rowstart[(size_t)q * nd + i] = rs;
-      for (int j = 0; j < nd; j++)
+      const int *eq = &elem_eqn[(size_t)q * nd];
+      int ns = 0;
+      for (int k = 0; k < nd; k++)
+        if (eq[k] >= 0) srt[ns++] = {eq[k], k};
+      std::sort(srt.begin(), srt.begin() + ns);
+      n_sorted[q] = ns;
+      for (int s_ = 0; s_ < ns; s_++)
       {
-        const size_t idx = ((size_t)q * nd + i) * nd + j;
-        const int v = elem_csr[idx];
-        unsigned code;
-        if (v == PB2_MAP_SKIP)
-          code = p->map_bits == 8 ? 0xFFu : 0xFFFFu;
-        else
-        {
-          const bool first = v < 0;
-          const int pos = first ? ~v : v;
-          code = (unsigned)(pos - rs) | (first ? (p->map_bits == 8 ? 0x80u : 0x8000u) : 0u);
-        }
-        if (p->map_bits == 8)
-          off8[idx] = (uint8_t)code;
-        else
-          off16[idx] = (uint16_t)code;
+        sorted_eq[(size_t)q * nd + s_] = srt[s_].first;
+        sorted_k[(size_t)q * nd + s_] = srt[s_].second;
       }
     }
   }
-  std::vector<int>().swap(elem_csr);
+  std::vector<int> elem_rowstart((size_t)ne * nd, -1), elem_res((size_t)ne * nd, PB2_MAP_SKIP);
+  std::vector<uint8_t> off8;
+  std::vector<uint16_t> off16;
+  if (p->map_bits == 8)
+    off8.assign((size_t)ne * nd * nd, (uint8_t)0xFF);
+  else
+    off16.assign((size_t)ne * nd * nd, (uint16_t)0xFFFF);
+  const unsigned FIRST = p->map_bits == 8 ? 0x80u : 0x8000u;
+  std::vector<std::vector<int>> t_untouched(omp_get_max_threads());
+#pragma omp parallel
+  {
+    std::vector<int> firstq(maxlen + 1), loc_k(nd), loc_off(nd), prev_row_k;
+    std::vector<int> &unt = t_untouched[omp_get_thread_num()];
+    prev_row_k.reserve(64);
+#pragma omp for schedule(static)
+    for (long long r = 0; r < nrow; r++)
+    {
+      const int rb = p->row_start[r], len = p->row_start[r + 1] - rb;
+      const int *cols = p->col_index.data() + rb;
+      const int a0 = adj_start[r], a1 = adj_start[r + 1];
+      for (int i = 0; i < len; i++) firstq[i] = -1;
+      for (int a_ = a0; a_ < a1; a_++)
+      {
+        const long long q = adj[a_];
+        const int *se = &sorted_eq[(size_t)q * nd], *sk = &sorted_k[(size_t)q * nd];
+        const int ns = n_sorted[q];
+        int ir = -1, pos = 0;
+        for (int s_ = 0; s_ < ns; s_++)
+        {
+          while (cols[pos] < se[s_]) pos++; // every dof of an adjacent element is a column of this row
+          loc_k[s_] = sk[s_];
+          loc_off[s_] = pos;
+          if (se[s_] == (int)r) ir = sk[s_];
+        }
+        // ir >= 0: r is a dof of q (that is what adjacency means)
+        const size_t base = ((size_t)q * nd + ir) * nd;
+        for (int s_ = 0; s_ < ns; s_++)
+        {
+          const int off = loc_off[s_];
+          unsigned code = (unsigned)off;
+          if (firstq[off] < 0)
+          {
+            firstq[off] = (int)q;
+            code |= FIRST;
+          }
+          if (p->map_bits == 8)
+            off8[base + loc_k[s_]] = (uint8_t)code;
+          else
+            off16[base + loc_k[s_]] = (uint16_t)code;
+        }
+        elem_rowstart[(size_t)q * nd + ir] = rb;
+        elem_res[(size_t)q * nd + ir] = a_ == a0 ? ~(int)r : (int)r;
+      }
+      if (m->n_extra > 0)
+        for (int i = 0; i < len; i++)
+          if (firstq[i] < 0) unt.push_back(rb + i);
+    }
+  }
+  std::vector<int>().swap(sorted_eq);
+  std::vector<int>().swap(sorted_k);
+  std::vector<int>().swap(adj);
+  std::vector<int>().swap(adj_start);
+  if (m->n_extra > 0)
+  {
+    // CSR positions no local element writes (extra pattern entries): re-zeroed before every assembly
+    std::vector<int> unt;
+    for (auto &v : t_untouched) unt.insert(unt.end(), v.begin(), v.end());
+    std::sort(unt.begin(), unt.end());
+    p->n_untouched = (long long)unt.size();
+    if (dev && upload(&p->d_untouched, unt))
+    {
+      pb2_problem_free(p); // releases whatever has been uploaded so far
+      return 1;
+    }
+  }
+  phase("position maps + first touch");
 
-  phase("map compression");
   // ---- dof -> nodal storage target for set_dofs: >=0 index into node_val (t=0), <0: ~index into node_pos (t=0)
   std::vector<long long> dof_target(nrow, PB2_DOF_NO_TARGET);
   for (long long n = 0; n < m->n_node; n++)
@@ -616,6 +640,10 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   p->setup_seconds = omp_get_wtime() - t_create0;
   if (!dev)
   {
+    p->h_elem_rowstart.swap(elem_rowstart);
+    p->h_elem_res.swap(elem_res);
+    p->h_off8.swap(off8);
+    p->h_off16.swap(off16);
     *out = p;
     return 0;
   }
@@ -707,6 +735,17 @@ extern "C" int pb2_problem_pattern(pb2_problem *p, const int **row_start, const 
   if (column_index) *column_index = p->col_index.data();
   if (nnz) *nnz = p->nnz;
   if (n_rows) *n_rows = p->n_dof;
+  return 0;
+}
+
+extern "C" int pb2_problem_host_maps(pb2_problem *p, const int **perm, const int **elem_rowstart, const void **elem_off, int *map_bits, const int **elem_res)
+{
+  if (p->device >= 0) return fail("the position maps of a device problem live in HBM; create a pattern-only problem (device < 0) to inspect them");
+  if (perm) *perm = p->perm.data();
+  if (elem_rowstart) *elem_rowstart = p->h_elem_rowstart.data();
+  if (elem_off) *elem_off = p->map_bits == 8 ? (const void *)p->h_off8.data() : (const void *)p->h_off16.data();
+  if (map_bits) *map_bits = p->map_bits;
+  if (elem_res) *elem_res = p->h_elem_res.data();
   return 0;
 }
 
