@@ -40,6 +40,51 @@ static int fail(const std::string &m)
     CUDA_OK(cudaSetDevice((p)->device));                                                                        \
   } while (0)
 
+// Large host arrays of the setup (CSR columns, position maps: hundreds of MB at the BASELINE sizes): std::vector would value-initialise
+// and page-fault them on one thread; here the memory is first touched by the OpenMP threads that fill it.
+template <class T>
+struct RawVec
+{
+  T *d = nullptr;
+  size_t n = 0;
+  RawVec() {}
+  RawVec(const RawVec &) = delete;
+  RawVec &operator=(const RawVec &) = delete;
+  ~RawVec() { free(d); }
+  void resize_uninit(size_t m)
+  {
+    free(d);
+    d = (T *)malloc(std::max<size_t>(1, m) * sizeof(T));
+    n = d ? m : 0;
+  }
+  void assign(size_t m, T v)
+  {
+    resize_uninit(m);
+    T *q = d;
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)m; i++) q[i] = v;
+  }
+  void swap(RawVec &o)
+  {
+    std::swap(d, o.d);
+    std::swap(n, o.n);
+  }
+  void clear()
+  {
+    free(d);
+    d = nullptr;
+    n = 0;
+  }
+  T *data() { return d; }
+  const T *data() const { return d; }
+  T *begin() { return d; }
+  T *end() { return d + n; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T &operator[](size_t i) { return d[i]; }
+  const T &operator[](size_t i) const { return d[i]; }
+};
+
 struct pb2_class
 {
   void *handle = nullptr;
@@ -59,7 +104,8 @@ struct pb2_problem
   bool local_order = true;       // elements of a unit in patch order (chunks of a few elements, colour-sorted inside a chunk)
   std::vector<int> unit_begin;   // [nunit+1] element range of each unit in the permuted order
   std::vector<int> h_elem_nodes; // permuted element -> nodes (host copy, for the barrier masks of the batch tables)
-  std::vector<int> row_start, col_index;
+  std::vector<int> row_start;
+  RawVec<int> col_index;
   // device
   int *d_elem_nodes = nullptr, *d_elem_eqn = nullptr, *d_elem_rowstart = nullptr, *d_elem_res = nullptr;
   void *d_elem_off = nullptr;
@@ -91,9 +137,9 @@ struct pb2_problem
   cudaEvent_t ev_inputs = nullptr; // recorded on the legacy stream after every input update; assemblies on other streams wait for it
   double setup_seconds = 0.0;      // wall time of pb2_problem_create (colouring, pattern, maps, upload)
   // pattern-only problems (device < 0) keep the maps on the host for inspection (pb2_problem_host_maps)
-  std::vector<int> h_elem_rowstart, h_elem_res;
-  std::vector<uint8_t> h_off8;
-  std::vector<uint16_t> h_off16;
+  RawVec<int> h_elem_rowstart, h_elem_res;
+  RawVec<uint8_t> h_off8;
+  RawVec<uint16_t> h_off16;
 };
 
 static int inputs_changed(pb2_problem *p);
@@ -141,6 +187,33 @@ extern "C" void pb2_class_free(pb2_class *cls)
 
 template <class T>
 static int upload(T **dptr, const std::vector<T> &v)
+{
+  CUDA_OK(cudaMalloc((void **)dptr, std::max<size_t>(1, v.size()) * sizeof(T)));
+  if (!v.empty()) CUDA_OK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// out = sorted union without duplicates of two sorted lists (out must hold na + nb entries); returns its length
+static inline int merge_unique(const int *a, int na, const int *b, int nb, int *out)
+{
+  int i = 0, j = 0, n = 0;
+  while (i < na && j < nb)
+  {
+    const int x = a[i], y = b[j];
+    const int v = x < y ? x : y;
+    i += x <= y;
+    j += y <= x;
+    if (n == 0 || out[n - 1] != v) out[n++] = v;
+  }
+  for (; i < na; i++)
+    if (n == 0 || out[n - 1] != a[i]) out[n++] = a[i];
+  for (; j < nb; j++)
+    if (n == 0 || out[n - 1] != b[j]) out[n++] = b[j];
+  return n;
+}
+
+template <class T>
+static int upload(T **dptr, const RawVec<T> &v)
 {
   CUDA_OK(cudaMalloc((void **)dptr, std::max<size_t>(1, v.size()) * sizeof(T)));
   if (!v.empty()) CUDA_OK(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -433,95 +506,10 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
     for (long long i = 0; i < m->n_extra; i++) ex_col[fp[m->extra_rows[i]]++] = m->extra_cols[i];
   }
   phase("adjacency");
-  // ---- CSR pattern, ascending columns.  One pass: every thread takes a contiguous block of rows, sorts the dofs of the row's elements
-  // once and keeps the columns in a private buffer; rows whose element list equals the previous row's (the dofs of one node) reuse its
-  // columns; then prefix sum and parallel copy.
-  p->row_start.assign(nrow + 1, 0);
-  {
-    const int nth = omp_get_max_threads();
-    std::vector<std::vector<int>> tcols(nth);
-    std::vector<long long> tbeg(nth + 1, 0);
-#pragma omp parallel num_threads(nth)
-    {
-      const int t = omp_get_thread_num();
-      const long long r0 = nrow * t / nth, r1 = nrow * (t + 1) / nth;
-      std::vector<int> &buf = tcols[t];
-      buf.reserve((size_t)(r1 - r0) * 40);
-      std::vector<int> tmp;
-      size_t prev_off = 0;
-      int prev_n = -1;
-      for (long long r = r0; r < r1; r++)
-      {
-        const int na = adj_start[r + 1] - adj_start[r];
-        const bool same = r > r0 && prev_n >= 0 && ex_start[r + 1] == ex_start[r] && ex_start[r] == ex_start[r - 1] &&
-                          na == adj_start[r] - adj_start[r - 1] && std::equal(adj.begin() + adj_start[r], adj.begin() + adj_start[r + 1], adj.begin() + adj_start[r - 1]);
-        if (same)
-        {
-          const size_t o = buf.size();
-          buf.resize(o + prev_n);
-          std::copy(buf.begin() + prev_off, buf.begin() + prev_off + prev_n, buf.begin() + o);
-          prev_off = o;
-        }
-        else
-        {
-          tmp.clear();
-          for (int a_ = adj_start[r]; a_ < adj_start[r + 1]; a_++)
-          {
-            const int *eq = &elem_eqn[(size_t)adj[a_] * nd];
-            for (int k = 0; k < nd; k++)
-              if (eq[k] >= 0) tmp.push_back(eq[k]);
-          }
-          for (int a_ = ex_start[r]; a_ < ex_start[r + 1]; a_++) tmp.push_back(ex_col[a_]);
-          std::sort(tmp.begin(), tmp.end());
-          prev_n = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
-          prev_off = buf.size();
-          buf.insert(buf.end(), tmp.begin(), tmp.begin() + prev_n);
-        }
-        p->row_start[r + 1] = prev_n;
-      }
-    }
-    phase("  pattern: row sorts");
-    long long tot = 0;
-    for (int t = 0; t < nth; t++)
-    {
-      tbeg[t] = tot;
-      tot += (long long)tcols[t].size();
-    }
-    if (tot >= 0x7fffffffLL)
-    {
-      pb2_problem_free(p); // releases whatever has been uploaded so far
-      return fail("nnz exceeds int32 CSR indexing");
-    }
-    for (long long r = 0; r < nrow; r++) p->row_start[r + 1] += p->row_start[r];
-    p->nnz = tot;
-    p->col_index.resize(p->nnz);
-    phase("  pattern: allocate");
-#pragma omp parallel num_threads(nth)
-    {
-      const int t = omp_get_thread_num();
-      std::copy(tcols[t].begin(), tcols[t].end(), p->col_index.begin() + tbeg[t]);
-      std::vector<int>().swap(tcols[t]);
-    }
-  }
-  phase("CSR pattern");
-
-  // ---- element -> CSR position maps, first-touch flags and their compressed form, in ONE pass over the matrix rows.
-  // Per local row of an element: its CSR row start (int32) and per (row, col) the offset inside the row plus a first-touch bit, 8 bits
-  // if every row is shorter than 127 entries, else 16 (4*ndof^2 -> ndof^2 bytes).  First touch = the element with the smallest
-  // scheduled index q among those reaching an entry stores, later ones add: no zero-fill of the outputs, fixed sum order.
-  // A row walks its elements in ascending q (adj is sorted), merges each element's sorted dof list with the row's columns
-  // (both ascending: one linear walk) and writes that element's slice of the map; rows with the element list of the previous row
-  // (dofs of one node) copy the previous row's slices.
-  int maxlen = 0;
-  for (long long r = 0; r < nrow; r++) maxlen = std::max(maxlen, p->row_start[r + 1] - p->row_start[r]);
-  p->map_bits = maxlen < 127 ? 8 : 16;
-  if (maxlen >= 32767)
-  {
-    pb2_problem_free(p); // releases whatever has been uploaded so far
-    return fail("CSR rows longer than 32766 entries are not supported by the position map");
-  }
   // dofs of every element sorted by equation, with their local index
-  std::vector<int> sorted_eq((size_t)ne * nd), sorted_k((size_t)ne * nd);
+  RawVec<int> sorted_eq, sorted_k;
+  sorted_eq.resize_uninit((size_t)ne * nd);
+  sorted_k.resize_uninit((size_t)ne * nd);
   std::vector<int> n_sorted(ne);
 #pragma omp parallel
   {
@@ -542,9 +530,109 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
       }
     }
   }
-  std::vector<int> elem_rowstart((size_t)ne * nd, -1), elem_res((size_t)ne * nd, PB2_MAP_SKIP);
-  std::vector<uint8_t> off8;
-  std::vector<uint16_t> off16;
+  phase("sorted element dof lists");
+  // ---- CSR pattern, ascending columns.  One pass: every thread takes a contiguous block of rows, sorts the dofs of the row's elements
+  // once and keeps the columns in a private buffer; rows whose element list equals the previous row's (the dofs of one node) reuse its
+  // columns; then prefix sum and parallel copy.
+  p->row_start.assign(nrow + 1, 0);
+  {
+    const int nth = omp_get_max_threads();
+    std::vector<std::vector<int>> tcols(nth);
+    std::vector<long long> tbeg(nth + 1, 0);
+#pragma omp parallel num_threads(nth)
+    {
+      const int t = omp_get_thread_num();
+      const long long r0 = nrow * t / nth, r1 = nrow * (t + 1) / nth;
+      std::vector<int> &buf = tcols[t];
+      buf.reserve((size_t)((double)(r1 - r0) * ((double)ne * nd * nd / std::max<long long>(1, nrow)) * 0.3) + 1024);   // ~ nnz per row block, over-reserved
+      std::vector<int> tmp(256), tmp2(256);
+      size_t prev_off = 0;
+      int prev_n = -1;
+      for (long long r = r0; r < r1; r++)
+      {
+        const int na = adj_start[r + 1] - adj_start[r];
+        const bool same = r > r0 && prev_n >= 0 && ex_start[r + 1] == ex_start[r] && ex_start[r] == ex_start[r - 1] &&
+                          na == adj_start[r] - adj_start[r - 1] && std::equal(adj.begin() + adj_start[r], adj.begin() + adj_start[r + 1], adj.begin() + adj_start[r - 1]);
+        if (same)
+        {
+          const size_t o = buf.size();
+          buf.resize(o + prev_n);
+          std::copy(buf.begin() + prev_off, buf.begin() + prev_off + prev_n, buf.begin() + o);
+          prev_off = o;
+        }
+        else
+        {
+          // the dof lists of the row's elements are sorted already: merge them list by list (dropping duplicates) instead of sorting
+          // their union
+          int n_acc = 0;
+          for (int a_ = adj_start[r]; a_ < adj_start[r + 1]; a_++)
+          {
+            const long long q = adj[a_];
+            const int nb = n_sorted[q];
+            if ((int)tmp.size() < n_acc + nb) { tmp.resize(2 * (n_acc + nb) + 64); tmp2.resize(tmp.size()); }
+            n_acc = merge_unique(tmp.data(), n_acc, sorted_eq.data() + (size_t)q * nd, nb, tmp2.data());
+            tmp.swap(tmp2);
+          }
+          if (ex_start[r + 1] > ex_start[r])
+          {
+            std::vector<int> ex(ex_col.begin() + ex_start[r], ex_col.begin() + ex_start[r + 1]);
+            std::sort(ex.begin(), ex.end());
+            if ((int)tmp.size() < n_acc + (int)ex.size()) { tmp.resize(2 * (n_acc + ex.size()) + 64); tmp2.resize(tmp.size()); }
+            n_acc = merge_unique(tmp.data(), n_acc, ex.data(), (int)ex.size(), tmp2.data());
+            tmp.swap(tmp2);
+          }
+          prev_n = n_acc;
+          prev_off = buf.size();
+          buf.insert(buf.end(), tmp.begin(), tmp.begin() + prev_n);
+        }
+        p->row_start[r + 1] = prev_n;
+      }
+    }
+    phase("  pattern: row sorts");
+    long long tot = 0;
+    for (int t = 0; t < nth; t++)
+    {
+      tbeg[t] = tot;
+      tot += (long long)tcols[t].size();
+    }
+    if (tot >= 0x7fffffffLL)
+    {
+      pb2_problem_free(p); // releases whatever has been uploaded so far
+      return fail("nnz exceeds int32 CSR indexing");
+    }
+    for (long long r = 0; r < nrow; r++) p->row_start[r + 1] += p->row_start[r];
+    p->nnz = tot;
+    p->col_index.resize_uninit(p->nnz);
+    phase("  pattern: allocate");
+#pragma omp parallel num_threads(nth)
+    {
+      const int t = omp_get_thread_num();
+      std::copy(tcols[t].begin(), tcols[t].end(), p->col_index.data() + tbeg[t]);
+      std::vector<int>().swap(tcols[t]);
+    }
+  }
+  phase("CSR pattern");
+
+  // ---- element -> CSR position maps, first-touch flags and their compressed form, in ONE pass over the matrix rows.
+  // Per local row of an element: its CSR row start (int32) and per (row, col) the offset inside the row plus a first-touch bit, 8 bits
+  // if every row is shorter than 127 entries, else 16 (4*ndof^2 -> ndof^2 bytes).  First touch = the element with the smallest
+  // scheduled index q among those reaching an entry stores, later ones add: no zero-fill of the outputs, fixed sum order.
+  // A row walks its elements in ascending q (adj is sorted), merges each element's sorted dof list with the row's columns
+  // (both ascending: one linear walk) and writes that element's slice of the map; rows with the element list of the previous row
+  // (dofs of one node) copy the previous row's slices.
+  int maxlen = 0;
+  for (long long r = 0; r < nrow; r++) maxlen = std::max(maxlen, p->row_start[r + 1] - p->row_start[r]);
+  p->map_bits = maxlen < 127 ? 8 : 16;
+  if (maxlen >= 32767)
+  {
+    pb2_problem_free(p); // releases whatever has been uploaded so far
+    return fail("CSR rows longer than 32766 entries are not supported by the position map");
+  }
+  RawVec<int> elem_rowstart, elem_res;
+  elem_rowstart.assign((size_t)ne * nd, -1);
+  elem_res.assign((size_t)ne * nd, PB2_MAP_SKIP);
+  RawVec<uint8_t> off8;
+  RawVec<uint16_t> off16;
   if (p->map_bits == 8)
     off8.assign((size_t)ne * nd * nd, (uint8_t)0xFF);
   else
@@ -556,12 +644,35 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
     std::vector<int> firstq(maxlen + 1), loc_k(nd), loc_off(nd), prev_row_k;
     std::vector<int> &unt = t_untouched[omp_get_thread_num()];
     prev_row_k.reserve(64);
-#pragma omp for schedule(static)
+#pragma omp for schedule(static, 4096)
     for (long long r = 0; r < nrow; r++)
     {
       const int rb = p->row_start[r], len = p->row_start[r + 1] - rb;
       const int *cols = p->col_index.data() + rb;
       const int a0 = adj_start[r], a1 = adj_start[r + 1];
+      // dofs of one node: same elements and same columns as the previous row => the same offsets and first touches; only the row
+      // start differs.  (Not across the first row of a thread's block, and not when extra pattern entries are involved.)
+      const bool same = r > 0 && (r % 4096) != 0 && m->n_extra == 0 && len == p->row_start[r] - p->row_start[r - 1] && a1 - a0 == a0 - adj_start[r - 1] &&
+                        std::equal(adj.begin() + a0, adj.begin() + a1, adj.begin() + adj_start[r - 1]);
+      if (same)
+      {
+        for (int a_ = a0; a_ < a1; a_++)
+        {
+          const long long q = adj[a_];
+          const int *se = &sorted_eq[(size_t)q * nd], *sk = &sorted_k[(size_t)q * nd];
+          const int ns = n_sorted[q];
+          const int s_ = (int)(std::lower_bound(se, se + ns, (int)r) - se); // r is a dof of q
+          const int ir = sk[s_], ip = sk[s_ - 1];                            // ... and r - 1 the one before it in q's sorted list
+          const size_t base = ((size_t)q * nd + ir) * nd, basep = ((size_t)q * nd + ip) * nd;
+          if (p->map_bits == 8)
+            memcpy(&off8[base], &off8[basep], nd);
+          else
+            memcpy(&off16[base], &off16[basep], nd * sizeof(uint16_t));
+          elem_rowstart[(size_t)q * nd + ir] = rb;
+          elem_res[(size_t)q * nd + ir] = a_ == a0 ? ~(int)r : (int)r;
+        }
+        continue;
+      }
       for (int i = 0; i < len; i++) firstq[i] = -1;
       for (int a_ = a0; a_ < a1; a_++)
       {
@@ -600,8 +711,8 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
           if (firstq[i] < 0) unt.push_back(rb + i);
     }
   }
-  std::vector<int>().swap(sorted_eq);
-  std::vector<int>().swap(sorted_k);
+  sorted_eq.clear();
+  sorted_k.clear();
   std::vector<int>().swap(adj);
   std::vector<int>().swap(adj_start);
   if (m->n_extra > 0)
