@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 9
+#define PB2_ABI_VERSION 10
 #define PB2_MAX_PARAMS 16
 #define PB2_NTW 7           /* time-stepper storage, MultiTimeStepper (src/timestepper.hpp:37-45) */
 #define PB2_MAX_FIELDS 16
@@ -135,7 +135,9 @@ typedef struct pb2_kernel_cfg
 } pb2_kernel_cfg;
 
 /* routine = ResidualAndJacobian<residual_index> (param_index < 0) or dResidual<i>dParameter_<param_index>;
- * flag as in jitbridge.h:285.  kind 0: R/J/M routines, 1: Hessian-vector routines, 2: EvalIntegralExpression for ALL integral
+ * flag as in jitbridge.h:285.  kind 0: R/J/M routines, 1: Hessian-vector routines d(J.Y)/dU (flag 1) + d(M.Y)/dU (flag 2), 3: their
+ * TRANSPOSED contractions d(J^T.Y)/dU, d(M^T.Y)/dU (flags 4 / 5 of HessianVectorProduct, jitbridge.h:637-691; same flag values 1 / 2
+ * here), 2: EvalIntegralExpression for ALL integral
  * expressions at once (jitbridge.h:469; one launch per call, args->elem_begin / n_elem select the elements, args->integrals
  * receives the per-element values; residual_index, param_index and flag are ignored). */
 typedef int (*pb2_query_fn)(int kind, int residual_index, int param_index, unsigned flag, pb2_kernel_cfg *out);

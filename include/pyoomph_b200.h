@@ -100,7 +100,8 @@ int pb2_problem_assemble_host(pb2_problem *p, int residual_index, int param_inde
 /* Hessian-vector assembly = HessianVectorProduct<i> (jitbridge.h:286) without the ndof^3 buffers, as used by
  * get_multi_assembly (src/elements.cpp:4983-4988) / the Hopf and azimuthal handlers (src/bifurcation.cpp):
  *   flag 1: for each of the n_vec vectors Y_v (host, [n_vec][n_dof]) the matrix  N_v = d(J.Y_v)/dU  (row i, column k:
- *           sum_j H_ijk Y_j) on the fixed CSR pattern;   flag 2: additionally  d(M.Y_v)/dU  for the mass matrix.
+ *           sum_j H_ijk Y_j) on the fixed CSR pattern;   flag 2: additionally  d(M.Y_v)/dU  for the mass matrix;
+ *   flag 4 / 5: the transposed contractions  sum_j H_jik Y_j  = d(J^T.Y_v)/dU  (flag 5: and d(M^T.Y_v)/dU), jitbridge.h:637-691.
  * Results stay on the device; pb2_problem_fetch_hessian copies matrix v to the host (mass_vals may be NULL). */
 int pb2_problem_assemble_hessian(pb2_problem *p, int residual_index, unsigned flag, int n_vec, const double *Y, void *cuda_stream);
 int pb2_problem_fetch_hessian(pb2_problem *p, int v, double *jac_hessian_vals, double *mass_hessian_vals);

@@ -175,6 +175,9 @@ class OracleProblem:
             C = np.ascontiguousarray(np.atleast_2d(C), dtype=np.float64)
             nvec = C.shape[0]
             prod, Cs = np.zeros(nvec * n), None
+        elif flag == 3:
+            nvec = 1
+            prod, Cs = np.zeros(n * n * n), np.zeros(n * n * n)      # the raw H_ijk and mass Hessian, [i*n^2 + j*n + k]
         else:
             nvec = Y.shape[0]
             prod, Cs = np.zeros(nvec * n * n), np.zeros(nvec * n * n)
@@ -182,10 +185,30 @@ class OracleProblem:
         nd = self.lib.oracle_element_hessian(self.h, e, which, _dp(Y), _dp(C) if flag == 0 else None, nvec, flag, _dp(prod), _dp(Cs), _ip(eq))
         if flag == 0:
             return prod[:nvec * nd].reshape(nvec, nd).copy(), eq[:nd].copy()
+        if flag == 3:
+            return prod[:nd ** 3].reshape(nd, nd, nd).copy(), Cs[:nd ** 3].reshape(nd, nd, nd).copy(), eq[:nd].copy()
         return prod[:nvec * nd * nd].reshape(nvec, nd, nd).copy(), Cs[:nvec * nd * nd].reshape(nvec, nd, nd).copy(), eq[:nd].copy()
 
+    def assemble_hessian_tensor(self, which: int = 0):
+        """Problem::assemble_hessian_tensor restated (src/problem.cpp:1530-1560): per element the flag-3 buffer of
+        HessianVectorProduct, T(iG, jG, kG) += H_e[i][k][j] for |value| > 0; returns the list of (i, j, k, value) contributions in the
+        reference's accumulation order"""
+        ii, jj, kk, vv = [], [], [], []
+        Y0 = np.zeros((1, self.n_dof))
+        for e in range(self.mesh.elem_nodes.shape[0]):
+            H, _, eq = self.element_hessian(e, Y0, flag=3, which=which)
+            nd = eq.size
+            for i in range(nd):
+                for j in range(nd):
+                    for k in range(nd):
+                        hval = H[i, k, j]
+                        if abs(hval) > 0.0:
+                            ii.append(eq[i]); jj.append(eq[j]); kk.append(eq[k]); vv.append(hval)
+        return np.array(ii, dtype=np.int32), np.array(jj, dtype=np.int32), np.array(kk, dtype=np.int32), np.array(vv)
+
     def assemble_hessian(self, Y: np.ndarray, flag: int = 2, which: int = 0):
-        """global d(J.Y_v)/dU (and d(M.Y_v)/dU) as scipy CSR matrices, element by element like get_multi_assembly"""
+        """global d(J.Y_v)/dU (and d(M.Y_v)/dU; flags 4 / 5: the transposed contractions) as scipy CSR matrices, element by element
+        like get_multi_assembly"""
         from scipy.sparse import coo_matrix
         Y = np.ascontiguousarray(np.atleast_2d(Y), dtype=np.float64)
         nvec, n = Y.shape[0], self.n_dof

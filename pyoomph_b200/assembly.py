@@ -367,13 +367,14 @@ class B200Assembly(CustomAssemblyBase):
         return out
 
     # ---- Hessian-vector products (MultiAssembleRequest.dJdU / dMdU, pyoomph/generic/bifurcation_tools.py:465-531) -----
-    def assemble_hessian(self, Y: np.ndarray, flag: int = 2, residual: str = ""):
-        """d(J.Y_v)/dU (flag 1) and d(M.Y_v)/dU (flag 2) for every row Y_v of Y; returns lists of CSR value arrays"""
+    def assemble_hessian(self, Y: np.ndarray, flag: int = 2, residual: str = "", transposed: bool = False):
+        """d(J.Y_v)/dU (flag 1) and d(M.Y_v)/dU (flag 2) for every row Y_v of Y; transposed: d(J^T.Y_v)/dU and d(M^T.Y_v)/dU
+        (the reference's flags 4 and 5, src/jitbridge.h:637-691); returns lists of CSR value arrays"""
         self._fresh()
         Y = np.ascontiguousarray(np.atleast_2d(Y), dtype=np.float64)
         assert Y.shape[1] == self.n_dof
         ri = self.residual_names.index(residual)
-        _check(self.lib.pb2_problem_assemble_hessian(self.prob, ri, flag, Y.shape[0], self._dp(Y), None))
+        _check(self.lib.pb2_problem_assemble_hessian(self.prob, ri, flag + (3 if transposed else 0), Y.shape[0], self._dp(Y), None))
         J, M = [], []
         for v in range(Y.shape[0]):
             jv = np.empty(self.nnz)
@@ -391,6 +392,11 @@ class B200Assembly(CustomAssemblyBase):
         ri = self.residual_names.index(residual)
         _check(self.lib.pb2_problem_hessian_vector_products(self.prob, ri, self._dp(Y), self._dp(C), C.shape[0], self._dp(out)))
         return out
+
+    def assemble_hessian_tensor(self, symmetric: bool = False, residual: str = ""):
+        """Problem::assemble_hessian_tensor (src/problem.cpp:1530-1560): the global rank-3 tensor as a SparseRank3Tensor"""
+        from .hessian_tensor import assemble_hessian_tensor
+        return assemble_hessian_tensor(self, symmetric, residual)
 
     # ---- eigenproblem matrices (Problem::assemble_eigenproblem_matrices, src/problem.cpp:715 -> oomph EigenProblemHandler) --------
     def assemble_eigenproblem_matrices(self, sigma_r: float = 0.0, residual: str = ""):

@@ -465,13 +465,58 @@ class FiniteElementCode:
             return out
         return form, second(form.J), second(form.M)
 
-    def hessian_form(self, resname: str = "") -> ResidualForm:
-        """d((J.Y))/dU and d((M.Y))/dU as an ordinary coefficient form: the direction vector Y enters as auxiliary fields
-        ``Y__<field>`` interpolated like <field>, so the batched R/J/M kernel skeleton assembles it unchanged (no residual)."""
-        key = resname + "|hessian"
+    def derive_hessian_transposed(self, resname: str = ""):
+        """Coefficient form of the TRANSPOSED contraction of HessianVectorProduct<i> (flags 4 and 5, src/jitbridge.h:637-691,
+        src/codegen.cpp:3879-3905):  T_ik = sum_j H_jik Y_j = d((A^T.Y)_i)/dU_k  for A = J or M.  With A_ji = T_b[l_j] C_{s,(G,a)} S_a[l_i]
+        the vector is contracted with the TEST side (Y interpolated like the tested field F of slot s with the slot's derivative b),
+        the row is the former column (G, a), which becomes a test slot of the new form:
+
+            T[(G,l_i),(H,l_k)] = S_a[l_i] * ( sum_{s=(F,b)} Yhat_{F,b} * dC_{s,(G,a)}/d atom(H,c) * fac ) * S_c[l_k]
+
+        Returns (slots', TJ, TM) with TJ[(slot' index, H, c)] = {(F, b): coefficient expression}."""
+        if self.coordinates_as_dofs:
+            raise RuntimeError("analytic Hessian with position dofs is outside the GPU path (second-order moving-mesh tensors)")
+        form = self.derive(resname)
+        unknowns = set(self.unknown_field_names())
+        slots_t: List[TestSlot] = []
+
+        def slot_t(G, a):
+            sl = TestSlot(G, a)
+            if sl not in slots_t:
+                slots_t.append(sl)
+            return slots_t.index(sl)
+
+        def second(coefs):
+            out: Dict[Tuple[int, str, str], Dict[Tuple[str, str], sp.Expr]] = {}
+            for (si, G, a), c in sorted(coefs.items()):
+                F, b = form.slots[si].field, form.slots[si].deriv
+                for sym in sorted((x for x in c.free_symbols if x in self._atom_syms), key=lambda x: x.name):
+                    info = self._atom_syms[sym]
+                    if info.past or info.field not in unknowns:
+                        continue
+                    d = sp.diff(c, sym)
+                    if d == 0:
+                        continue
+                    if info.dt_order:
+                        d = d * sp.Symbol("W__%s__%d" % (info.scheme, info.dt_order), real=True)
+                    dst = out.setdefault((slot_t(G, a), info.field, info.deriv), {})
+                    dst[(F, b)] = dst.get((F, b), sp.Integer(0)) + d
+            return out
+        TJ, TM = second(form.J), second(form.M)
+        return slots_t, TJ, TM
+
+    def hessian_form(self, resname: str = "", transposed: bool = False) -> ResidualForm:
+        """d((J.Y))/dU and d((M.Y))/dU (transposed: d((J^T.Y))/dU, d((M^T.Y))/dU) as an ordinary coefficient form: the direction
+        vector Y enters as auxiliary fields ``Y__<field>`` interpolated like <field>, so the batched R/J/M kernel skeleton
+        assembles it unchanged (no residual)."""
+        key = resname + ("|hessianT" if transposed else "|hessian")
         if key in self._forms:
             return self._forms[key]
-        form, DJ, DM = self.derive_hessian(resname)
+        if transposed:
+            slots_t, DJ, DM = self.derive_hessian_transposed(resname)
+            form = ResidualForm(key, slots_t, [sp.Integer(0)] * len(slots_t), {}, {}, [])
+        else:
+            form, DJ, DM = self.derive_hessian(resname)
 
         def fold(D):
             out: Dict[Tuple[int, str, str], sp.Expr] = {}

@@ -1200,7 +1200,10 @@ extern "C" int pb2_problem_assemble_hessian(pb2_problem *p, int residual_index, 
 {
   NEED_DEVICE(p);
   if (!p->cls->table.info.hessian_generated) return fail("this element class was generated without Hessian routines");
-  if (flag != 1u && flag != 2u) return fail("Hessian assembly: flag must be 1 (d(J.Y)/dU) or 2 (+ d(M.Y)/dU)");
+  if (flag != 1u && flag != 2u && flag != 4u && flag != 5u)
+    return fail("Hessian assembly: flag must be 1 (d(J.Y)/dU), 2 (+ d(M.Y)/dU), 4 (d(J^T.Y)/dU) or 5 (+ d(M^T.Y)/dU)");
+  const int hkind = flag >= 4u ? 3 : 1;     // transposed contraction: plugin kind 3
+  if (flag >= 4u) flag -= 3u;
   if (n_vec < 1) return fail("n_vec must be positive");
   if (n_vec > p->hess_nvec)
   {
@@ -1215,7 +1218,7 @@ extern "C" int pb2_problem_assemble_hessian(pb2_problem *p, int residual_index, 
   long long launches = 0;
   for (int v = 0; v < n_vec; v++)
   {
-    const int rc = run_routine(p, 1, residual_index, -1, flag, p->d_hess + (size_t)v * p->nnz, p->d_hessM + (size_t)v * p->nnz, p->d_hvec + (size_t)v * p->n_dof, cuda_stream);
+    const int rc = run_routine(p, hkind, residual_index, -1, flag, p->d_hess + (size_t)v * p->nnz, p->d_hessM + (size_t)v * p->nnz, p->d_hvec + (size_t)v * p->n_dof, cuda_stream);
     if (rc) return rc;
     launches += p->launches_last;
   }

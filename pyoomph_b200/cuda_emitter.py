@@ -165,6 +165,8 @@ class CudaEmitter:
         if self.hessian:
             for i, rn in enumerate(code.residual_names()):
                 self.hroutines.append(RoutinePlan("h%d" % i, code.hessian_form(rn), i, -1))
+                # transposed contraction (flags 4 / 5 of HessianVectorProduct, src/jitbridge.h:637-691): plugin query kind 3
+                self.hroutines.append(RoutinePlan("ht%d" % i, code.hessian_form(rn, transposed=True), i, -1))
         self.T_val = code.history_levels()
         self.T_pos = self.T_val if code.coordinates_as_dofs else 1
         self._plan_groups()
@@ -1658,7 +1660,7 @@ class CudaEmitter:
         w("static int pb2_query(int kind, int residual_index, int param_index, unsigned flag, pb2_kernel_cfg* out)")
         w("{")
         w("  memset(out, 0, sizeof(*out));")
-        w("  if (kind < 0 || kind > 2 || flag > 2u) return 1;")
+        w("  if (kind < 0 || kind > 3 || flag > 2u) return 1;")
         if integral_kernel:
             w("  if (kind == 2) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
                 integral_kernel, self._kernel_smem[integral_kernel], self._kernel_cfg[integral_kernel][0], self._kernel_cfg[integral_kernel][1]))
@@ -1667,15 +1669,15 @@ class CudaEmitter:
             for rp in self.hroutines:
                 for what in (1, 2):
                     kn = kernels[(rp.key, what)]
-                    w("  if (kind == 1 && residual_index == %d && flag == %du) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
-                        rp.res_index, what, kn, self._kernel_smem[kn], self._kernel_cfg[kn][0], self._kernel_cfg[kn][1]))
+                    w("  if (kind == %d && residual_index == %d && flag == %du) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
+                        3 if rp.key.startswith("ht") else 1, rp.res_index, what, kn, self._kernel_smem[kn], self._kernel_cfg[kn][0], self._kernel_cfg[kn][1]))
         for rp in self.routines:
             for what in (0, 1, 2):
                 kn = kernels[(rp.key, what)]
                 w("  if (kind == 0 && residual_index == %d && param_index == %d && flag == %du) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
                     rp.res_index, rp.param_index, what, kn, self._kernel_smem[kn], self._kernel_cfg[kn][0], self._kernel_cfg[kn][1]))
         w("  if (!out->func) return 2;")
-        w("  out->pipelined = kind == 2 ? 0 : %d;" % (1 if self.pipeline else 0))
+        w("  out->pipelined = kind == 2 ? 0 : %d;   // kinds 0, 1, 3 are persistent pipelined kernels" % (1 if self.pipeline else 0))
         w("  cudaError_t err = cudaFuncSetAttribute(out->func, cudaFuncAttributeMaxDynamicSharedMemorySize, out->smem_bytes);")
         w("  if (err != cudaSuccess) return 100 + (int)err;")
         w("  int per_sm = 0;")

@@ -76,12 +76,13 @@ class MultiAssembleRequest:
         return self._add("dmass_matrix_dparameter", contribution)
 
     def _hvp(self, what: str, vector, contribution: str, transposed: bool):
-        if transposed:
-            raise NotImplementedError("transposed Hessian-vector products are not generated for the GPU path")
+        """transposed: the contraction sum_j H_jik Y_j (flags 4 / 5 of HessianVectorProduct; the reference's multi-assembly passes
+        hessian_vector_transposed along, bifurcation_tools.py:505-515 -> src/elements.cpp:4983-4988)"""
         v = np.asarray(vector, dtype=np.float64)
         if v.shape != (self.assembler.n_dof,):
             raise RuntimeError("Hessian vector must have one entry per dof")
         self._hessian_vector_indices.append(self._resolve_hessian_vector_index(vector))
+        self.__dict__.setdefault("_hessian_transposed", []).append(bool(transposed))
         return self._add(what, contribution)
 
     def dJdU(self, vector, contribution: str = "", transposed: bool = False):
@@ -111,10 +112,11 @@ class MultiAssembleRequest:
                 keys.append(k)
             else:
                 vi = self._hessian_vector_indices[hi]
+                tr = self.__dict__.get("_hessian_transposed", [])[hi]
                 hi += 1
-                d = hvp.setdefault(contrib, {})
+                d = hvp.setdefault((contrib, tr), {})
                 d[vi] = d.get(vi, False) or what.startswith("mass_matrix")
-                keys.append((contrib, vi))
+                keys.append((contrib, tr, vi))
         # 2. launches
         self.launches = 0
         got: Dict[Tuple[str, object], tuple] = {}
@@ -122,17 +124,17 @@ class MultiAssembleRequest:
             asm.assemble(flag=flag, residual=contrib, parameter=par)
             self.launches += asm.launch_count()
             got[(contrib, par)] = asm.fetch(want_jacobian=flag >= 1, want_mass=flag >= 2)
-        hgot: Dict[Tuple[str, int], tuple] = {}
-        for contrib, vecs in hvp.items():
+        hgot: Dict[Tuple[str, bool, int], tuple] = {}
+        for (contrib, tr), vecs in hvp.items():
             idx = sorted(vecs)
             for b in range(0, len(idx), PB2_MAX_HVEC):
                 blk = idx[b:b + PB2_MAX_HVEC]
                 flag = 2 if any(vecs[i] for i in blk) else 1
                 Y = np.stack([np.asarray(self._hessian_vectors[i], dtype=np.float64) for i in blk])
-                Jv, Mv = asm.assemble_hessian(Y, flag=flag, residual=contrib)
+                Jv, Mv = asm.assemble_hessian(Y, flag=flag, residual=contrib, transposed=tr)
                 self.launches += asm.launch_count()
                 for k, i in enumerate(blk):
-                    hgot[(contrib, i)] = (Jv[k], Mv[k])
+                    hgot[(contrib, tr, i)] = (Jv[k], Mv[k])
         # 3. results in request order
 
         def mat(values):

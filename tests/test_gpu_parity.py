@@ -361,8 +361,11 @@ def test_multi_assemble_request_matches_oracle():
         assert missing == 0 and err <= TOL
     for got, ref in ((JY, Jh[0]), (JZ, Jh[1]), (MY, Mh[0])):
         assert abs(got - ref).max() <= TOL * max(abs(ref).max(), 1e-300) if ref.nnz else abs(got).max() == 0.0
-    with pytest.raises(NotImplementedError):
-        MultiAssembleRequest(asm).dJdU(Y, transposed=True)
+    # transposed contractions through the same request (hessian_vector_transposed of the reference's multi-assembly)
+    JYt, MYt = MultiAssembleRequest(asm).dJdU(Y, transposed=True).dMdU(Y, transposed=True).assemble()
+    Jt, Mt = op.assemble_hessian(Y[None, :], flag=5)
+    for got, ref in ((JYt, Jt[0]), (MYt, Mt[0])):
+        assert abs(got - ref).max() <= TOL * max(abs(ref).max(), 1e-300) if ref.nnz else abs(got).max() == 0.0
     # eigenproblem pair (Problem::assemble_eigenproblem_matrices): mass matrix and shifted Jacobian from one launch
     Me, Je = asm.assemble_eigenproblem_matrices(sigma_r=0.75)
     assert asm.launch_count() == 1 and abs(Me - M).max() == 0.0 and abs(Je - (J - 0.75 * M)).max() <= 1e-15 * abs(J).max()
@@ -407,3 +410,58 @@ def test_full_size_config3_windows_against_oracle():
     worst = check_windows(pb, make_oracle, asm.indptr, asm.indices, jac, r, windows, w=2, tol=TOL)
     print("full-size window parity (config 3): worst row-scaled error %.2e over %d windows" % (worst, len(windows)))
     asm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N", [("ns_unsteady", 6), ("nlheat", 6), ("ns_axi_swirl", 4)])
+def test_transposed_hessian_vector_products_parity(kind, N):
+    """flags 4 and 5 of HessianVectorProduct<i> (src/jitbridge.h:637-691): T_ik = sum_j H_jik Y_j for the Jacobian and the mass
+    Hessian, against the oracle's ndof^3-buffer routine; and against the non-transposed products through the symmetry
+    T(Y) . C = (d(J.C)/dU)^T ... checked as a bilinear identity:  C^T T(Y) Z = Y^T N(C) Z  with N(C) = d(J.C)/dU."""
+    pb = make_problem(kind, N)
+    op = make_oracle(pb)
+    asm = make_gpu(pb)
+    n = pb["dofmap"].n_dof
+    rng = np.random.default_rng(4)
+    Y = rng.uniform(-1, 1, (2, n))
+    Jr, Mr = op.assemble_hessian(Y, flag=5)
+    Jg, Mg = asm.assemble_hessian(Y, flag=2, transposed=True)
+    from scipy.sparse import csr_matrix
+    for ref, got in list(zip(Jr, Jg)) + list(zip(Mr, Mg)):
+        A = csr_matrix((got, asm.indices, asm.indptr), shape=(n, n))
+        assert abs(A - ref).max() <= TOL * max(abs(ref).max(), 1e-300) if ref.nnz else np.abs(got).max() == 0.0
+    C, Z = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+    Tn, _ = asm.assemble_hessian(Y[:1], flag=1, transposed=True)
+    Nc, _ = asm.assemble_hessian(C[None, :], flag=1)
+    lhs = C @ (csr_matrix((Tn[0], asm.indices, asm.indptr), shape=(n, n)) @ Z)
+    rhs = Y[0] @ (csr_matrix((Nc[0], asm.indices, asm.indptr), shape=(n, n)) @ Z)
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs), 1e-300)
+    op.close(); asm.close()
+
+
+@pytest.mark.gpu
+def test_hessian_tensor_matches_the_reference_accumulation():
+    """Problem::assemble_hessian_tensor (src/problem.cpp:1530-1560) on the GPU (one Hessian-vector launch per tensor slice) against the
+    restated element loop over the oracle's flag-3 buffers, as SparseRank3Tensors: same (i, j, k) pattern up to exact cancellations,
+    values 1e-12; and the tensor-vector product equals d(J.v)/dU."""
+    from scipy.sparse import csr_matrix
+    from pyoomph_b200.hessian_tensor import SparseRank3Tensor
+    pb = make_problem("nlheat", 3)
+    op, asm = make_oracle(pb), make_gpu(pb)
+    n = pb["dofmap"].n_dof
+    T = asm.assemble_hessian_tensor()
+    ii, jj, kk, vv = op.assemble_hessian_tensor()
+    R = SparseRank3Tensor(n)
+    R.accumulate(ii, jj, kk, vv)
+    dg = {(a, b, c): v for a, b, c, v in T.get_entries()}
+    dr = {(a, b, c): v for a, b, c, v in R.get_entries()}
+    scale = max(abs(v) for v in dr.values())
+    for key in set(dg) | set(dr):
+        assert abs(dg.get(key, 0.0) - dr.get(key, 0.0)) <= TOL * scale, key
+    assert len(set(dg) ^ set(dr)) <= 0.02 * len(dr)
+    v = np.random.default_rng(9).uniform(-1, 1, n)
+    ci, rs = T.finalize_for_vector_product()
+    M = csr_matrix((T.right_vector_mult(v), ci, rs), shape=(n, n))
+    Nv, _ = asm.assemble_hessian(v[None, :], flag=1)
+    assert abs(M - csr_matrix((Nv[0], asm.indices, asm.indptr), shape=(n, n))).max() <= 1e-12 * abs(M).max()
+    op.close(); asm.close()

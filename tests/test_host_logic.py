@@ -153,7 +153,7 @@ def test_multi_assemble_request_groups_launches_and_keeps_request_order():
             t = self._tag
             return np.full(4, t + 0.0), np.full(4, t + 1.0) if want_jacobian else None, np.full(4, t + 2.0) if want_mass else None
 
-        def assemble_hessian(self, Y, flag=2, residual=""):
+        def assemble_hessian(self, Y, flag=2, residual="", transposed=False):
             self.calls.append(("hvp", residual, Y.shape[0], flag))
             return [np.full(4, 1000 + Y[v, 0]) for v in range(Y.shape[0])], [np.full(4, 2000 + Y[v, 0]) if flag >= 2 else None for v in range(Y.shape[0])]
     f = Fake()

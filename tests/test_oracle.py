@@ -331,3 +331,30 @@ def test_newton_solve_of_the_cavity_converges_quadratically():
     centre_low = (lat[:, 0] == N) & (lat[:, 1] > 0) & (lat[:, 1] < N)
     assert ux[centre_low].min() < -0.05
     op.close()
+
+
+@pytest.mark.parametrize("kind", ["ns_unsteady", "nlheat"])
+def test_hessian_flags_of_the_oracle_are_consistent(kind):
+    """SURVEY A.5 / src/jitbridge.h:624-691: flag 3 hands out the raw H_ijk (and the mass Hessian); flags 1/2 contract the MIDDLE index
+    (sum_j H_ijk Y_j), flags 4/5 the FIRST (sum_j H_jik Y_j); flag 0 = Y_j H_ijk C_k.  All from one element of the oracle."""
+    from problems import make_oracle, make_problem
+    pb = make_problem(kind, 3)
+    op = make_oracle(pb)
+    rng = np.random.default_rng(2)
+    n = pb["dofmap"].n_dof
+    Y = rng.uniform(-1, 1, (2, n))
+    e = pb["mesh"].n_elem // 2
+    H, MH, eq = op.element_hessian(e, Y[:1], flag=3)
+    Yl = Y[:, eq]
+    P2, C2, _ = op.element_hessian(e, Y, flag=2)
+    P5, C5, _ = op.element_hessian(e, Y, flag=5)
+    for v in range(2):
+        assert np.abs(P2[v] - np.einsum("ijk,j->ik", H, Yl[v])).max() <= 1e-13 * np.abs(P2).max()
+        assert np.abs(C2[v] - np.einsum("ijk,j->ik", MH, Yl[v])).max() <= 1e-13 * max(np.abs(C2).max(), 1e-300)
+        assert np.abs(P5[v] - np.einsum("jik,j->ik", H, Yl[v])).max() <= 1e-13 * np.abs(P5).max()
+        assert np.abs(C5[v] - np.einsum("jik,j->ik", MH, Yl[v])).max() <= 1e-13 * max(np.abs(C5).max(), 1e-300)
+    assert np.abs(H - H.transpose(0, 2, 1)).max() <= 1e-13 * np.abs(H).max()          # a Hessian: symmetric in (j, k)
+    C = rng.uniform(-1, 1, (3, n))
+    P0, _ = op.element_hessian(e, Y[:1], C, flag=0)
+    assert np.abs(P0 - np.einsum("j,ijk,vk->vi", Yl[0], H, C[:, eq])).max() <= 1e-13 * np.abs(P0).max()
+    op.close()

@@ -281,3 +281,27 @@ def test_timestepper_weights_bit_exact(oomph):
         drv.oracle_newmark2_weights(ctypes.c_double(dt), ctypes.c_double(0.5), ctypes.c_double(0.5), _dp(p1), _dp(p2))
         for a, b in ((o1, b1), (o2, b2), (p1, n1), (p2, n2)):
             assert np.abs(a - b).max() <= 4e-16 * max(1.0, np.abs(b).max())     # -O3 -march=native build of the driver: last-bit freedom
+
+
+def test_sparse_rank3_tensor_matches_compiled_reference(oomph):
+    """pyoomph_b200.hessian_tensor.SparseRank3Tensor against the compiled pyoomph::SparseRank3Tensor (src/hessian_tensor.cpp): same
+    CSR pattern of M_ij = T_ijk v_k from finalize_for_vector_product, same product values; repeated (i, j, k) accumulate."""
+    from pyoomph_b200.hessian_tensor import SparseRank3Tensor
+    rng = np.random.default_rng(5)
+    n, ne = 23, 900
+    ii, jj, kk = (rng.integers(0, n, ne).astype(np.int32) for _ in range(3))
+    ii[:50], jj[:50], kk[:50] = ii[50:100], jj[50:100], kk[50:100]          # repeated entries
+    vv = rng.uniform(-1, 1, ne)
+    vec = rng.uniform(-1, 1, n)
+    T = SparseRank3Tensor(n, False)
+    T.accumulate(ii, jj, kk, vv)
+    ci, rs = T.finalize_for_vector_product()
+    vals = T.right_vector_mult(vec)
+    ci_r, rs_r, va_r = np.zeros(ne, dtype=np.int32), np.zeros(n + 1, dtype=np.int32), np.zeros(ne)
+    nnz = oomph.ref_rank3_product(n, 0, ctypes.c_long(ne), _ip(ii), _ip(jj), _ip(kk), _dp(vv), _dp(vec), _ip(ci_r), _ip(rs_r), _dp(va_r))
+    assert nnz == vals.size and np.array_equal(rs, rs_r) and np.array_equal(ci, ci_r[:nnz])
+    assert np.abs(vals - va_r[:nnz]).max() <= 1e-14 * np.abs(va_r).max()
+    ent = T.get_entries()
+    assert len(ent) == len({(a, b, c) for a, b, c in zip(ii.tolist(), jj.tolist(), kk.tolist())}) and ent == sorted(ent, key=lambda t: t[:3])
+    with pytest.raises(RuntimeError):
+        SparseRank3Tensor(n).right_vector_mult(vec)

@@ -24,7 +24,8 @@ BIN = os.path.join(HERE, "c", "plugin_contract")
 def _build_program():
     """the checked-in program is compiled where the reference's header is available; the binary (git-ignored) travels to the GPU box"""
     src = os.path.join(HERE, "c", "plugin_contract.c")
-    if HAVE_REF and (not os.path.exists(BIN) or os.path.getmtime(BIN) < os.path.getmtime(src)):
+    deps = [src, os.path.join(ROOT, "include", "pb2_jit_cuda.h"), os.path.join(ROOT, "include", "pyoomph_b200.h")]
+    if HAVE_REF and (not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(d) for d in deps)):
         subprocess.run(["gcc", "-O1", "-std=gnu99", "-I", REF_SRC, "-I", os.path.join(ROOT, "include"), src, "-o", BIN, "-ldl"], check=True)
     return os.path.exists(BIN)
 
