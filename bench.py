@@ -327,7 +327,7 @@ def main():
         exch_max, exch_sum = int(et.item()), int(es.item())
 
     # ---- end-to-end through the reference-facing call (host buffers, copies inside the timed region)
-    e2e = None
+    e2e = e2e_dev = None
     if not args.no_e2e and world == 1:
         eq = pb["dofmap"].node_eqn
         ndof, nnz = asm.n_dof, asm.nnz
@@ -353,6 +353,18 @@ def main():
         sec = (time.perf_counter() - t0) / ksteps
         e2e = {"value": total_elems / sec, "unit": UNIT, "h2d_bytes_per_step": int(ndof * 8), "d2h_bytes_per_step": int((ndof + nnz) * 8),
                "ms_per_step": sec * 1e3, "steps": ksteps}
+        # the same step when the linear solver is device-resident (SURVEY N-d, pyoomph_b200/solvers.py): host dofs in, full R+J assembly,
+        # only the residual comes back -- the matrix stays in HBM for the solver.  Reported next to e2e, never instead of it.
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            asm.set_dofs(h_dofs)
+            asm.assemble(flag=1)
+            lib.pb2_problem_fetch(asm.prob, h_res.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), None, None)
+        barrier()
+        sec_d = (time.perf_counter() - t0) / ksteps
+        e2e_dev = {"value": total_elems / sec_d, "unit": UNIT, "h2d_bytes_per_step": int(ndof * 8), "d2h_bytes_per_step": int(ndof * 8),
+                   "ms_per_step": sec_d * 1e3, "steps": ksteps,
+                   "note": "Jacobian left on the device for a device-resident solver plugin (DeviceLinearSystemSolver); not the headline e2e"}
     elif not args.no_e2e:
         # N GPUs: every rank feeds the host dof values of its local rows and reads its owned CSR row block back (N host links);
         # local kernels + the NCCL interface exchange sit between the copies.  A failure on one rank must not desynchronise the
@@ -451,6 +463,8 @@ def main():
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches)}
     if e2e is not None:
         line["e2e"] = e2e
+    if e2e_dev is not None:
+        line["e2e_matrix_stays_on_device"] = e2e_dev
     if mgp is not None:
         line["multi_gpu_parity"] = mgp
     if not args.no_cpu_baseline and world == 1:

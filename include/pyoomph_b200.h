@@ -84,6 +84,14 @@ int pb2_problem_set_parameters(pb2_problem *p, const double *values, int n);
 int pb2_problem_assemble(pb2_problem *p, int residual_index, int param_index, unsigned flag, void *cuda_stream);
 /* device pointers of the outputs (for GPU-side consumers) */
 int pb2_problem_device_outputs(pb2_problem *p, double **residual, double **jac_vals, double **mass_vals);
+/* Device-resident hand-off to a GPU linear solver (SURVEY N-d; the reference's solver plugins receive host arrays,
+ * pyoomph/solvers/generic.py:64-118, src/pybind/solver.cpp:104-140): the fixed CSR pattern as device arrays (uploaded on first use)
+ * next to pb2_problem_device_outputs' values and residual, the device copy of the dof vector, and the Newton update applied on the
+ * device (dofs += alpha * delta, then the scatter of pb2_problem_set_dofs).  With these a Newton iteration moves no matrix over
+ * the host link. */
+int pb2_problem_device_pattern(pb2_problem *p, int **row_start, int **column_index);
+int pb2_problem_device_dofs(pb2_problem *p, double **dofs);
+int pb2_problem_update_dofs_device(pb2_problem *p, const double *d_delta, double alpha, void *cuda_stream);
 /* multi-GPU interface exchange (oomph-lib ships off-rank row contributions to their owner, problem.cc:6970-7121): one kernel packs
  * residual[rows[i]] and, for flag >= 1, jac_vals[pos[j]] (flag 2: then mass_vals[pos[j]]) into `buf` (device, n_rows + flag * n_pos
  * doubles); the owner adds a received buffer with pb2_problem_unpack_add.  rows/pos are device arrays with unique entries, so the

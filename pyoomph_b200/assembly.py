@@ -80,7 +80,8 @@ def load_library() -> ctypes.CDLL:
                "pb2_problem_fetch", "pb2_problem_assemble_host", "pb2_problem_num_colours", "pb2_version",
                "pb2_problem_assemble_hessian", "pb2_problem_fetch_hessian", "pb2_problem_hessian_vector_products",
                "pb2_problem_pack_rows", "pb2_problem_unpack_add", "pb2_problem_eval_integrals", "pb2_problem_shift_time_values",
-               "pb2_problem_set_history_dofs", "pb2_measure_fp64_peak", "pb2_problem_host_maps"):
+               "pb2_problem_set_history_dofs", "pb2_measure_fp64_peak", "pb2_problem_host_maps", "pb2_problem_device_pattern",
+               "pb2_problem_device_dofs", "pb2_problem_update_dofs_device"):
         getattr(L, fn).restype = ctypes.c_int
     L.pb2_problem_setup_seconds.restype = ctypes.c_double
     _LIB = L
@@ -423,6 +424,22 @@ class B200Assembly(CustomAssemblyBase):
 
     def evaluate_observable(self, name: str) -> float:
         return self.evaluate_integral_expressions()[name]
+
+    def newton_step_on_device(self, solver, residual: str = ""):
+        """one Newton iteration with a device-resident linear solver (pyoomph_b200.solvers.DeviceLinearSystemSolver): the matrix never
+        crosses the host link (SURVEY N-d).  Returns (max |residual| before the step, solver statistics)."""
+        from .solvers import newton_step_on_device
+        self._fresh()
+        return newton_step_on_device(self, solver, residual)
+
+    def fetch_dofs(self) -> np.ndarray:
+        """the engine's device dof vector (as set by set_dofs / updated by newton_step_on_device) back on the host"""
+        import torch
+        from .solvers import _DeviceArray
+        d = ctypes.c_void_p()
+        _check(self.lib.pb2_problem_device_dofs(self.prob, ctypes.byref(d)))
+        t = torch.as_tensor(_DeviceArray(d.value, self.n_dof, "<f8"), device=torch.device("cuda", self._device))
+        return t.cpu().numpy()
 
     def device_outputs(self):
         r, j, m = c_double_p(), c_double_p(), c_double_p()

@@ -1335,6 +1335,60 @@ extern "C" int pb2_problem_device_outputs(pb2_problem *p, double **residual, dou
   return 0;
 }
 
+// ---- device-resident hand-off to a GPU linear solver (SURVEY N-d): the CSR pattern on the device next to the values, and the Newton
+// update applied where the dofs live, so that per iteration only what the host really needs crosses the host link
+extern "C" int pb2_problem_device_pattern(pb2_problem *p, int **row_start, int **column_index)
+{
+  NEED_DEVICE(p);
+  if (!p->d_row_start)
+  {
+    if (upload(&p->d_row_start, p->row_start) || upload(&p->d_col_index, p->col_index)) return 1;
+  }
+  if (row_start) *row_start = p->d_row_start;
+  if (column_index) *column_index = p->d_col_index;
+  return 0;
+}
+
+extern "C" int pb2_problem_device_dofs(pb2_problem *p, double **dofs)
+{
+  NEED_DEVICE(p);
+  *dofs = p->d_dofs;
+  return 0;
+}
+
+static __global__ void pb2_axpy_kernel(double *__restrict__ y, const double *__restrict__ x, double alpha, long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] += alpha * x[i];
+}
+
+// dofs += alpha * delta (both on the device), then the same scatter into the nodal storage as pb2_problem_set_dofs: the Newton update
+// x -= dx of Problem::newton_solve (oomph-lib problem.cc) without a host round trip.  `cuda_stream`: the stream the solver produced
+// delta on (NULL: default stream).
+extern "C" int pb2_problem_update_dofs_device(pb2_problem *p, const double *d_delta, double alpha, void *cuda_stream)
+{
+  NEED_DEVICE(p);
+  const int bs = 256;
+  const long long nb = (p->n_dof + bs - 1) / bs;
+  if (nb > 0)
+  {
+    pb2_axpy_kernel<<<(unsigned)nb, bs, 0, (cudaStream_t)cuda_stream>>>(p->d_dofs, d_delta, alpha, p->n_dof);
+    CUDA_OK(cudaGetLastError());
+    if (cuda_stream)
+    {
+      // the scatter and every later assembly are ordered behind the update through the inputs event
+      pb2_scatter_dofs<<<(unsigned)nb, bs, 0, (cudaStream_t)cuda_stream>>>(p->d_dofs, p->d_dof_target, p->n_dof, p->d_node_val, p->d_node_pos);
+      CUDA_OK(cudaGetLastError());
+      CUDA_OK(cudaEventRecord(p->ev_inputs, (cudaStream_t)cuda_stream));
+      CUDA_OK(cudaStreamWaitEvent(0, p->ev_inputs, 0));
+      p->launches_total += 2;
+      return 0;
+    }
+    p->launches_total++;
+  }
+  return scatter_dofs_from_device(p, 0);
+}
+
 // ---- interface exchange: pack / unpack-add of halo rows (one launch each; SM-count-multiple grids, 16-byte friendly index loads)
 static __global__ void pb2_pack_kernel(const double *__restrict__ res, const double *__restrict__ jac, const double *__restrict__ mass,
                                        const long long *__restrict__ rows, long long n_rows, const long long *__restrict__ pos, long long n_pos,

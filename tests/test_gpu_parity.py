@@ -465,3 +465,35 @@ def test_hessian_tensor_matches_the_reference_accumulation():
     Nv, _ = asm.assemble_hessian(v[None, :], flag=1)
     assert abs(M - csr_matrix((Nv[0], asm.indices, asm.indptr), shape=(n, n))).max() <= 1e-12 * abs(M).max()
     op.close(); asm.close()
+
+
+@pytest.mark.gpu
+def test_newton_iteration_with_a_device_resident_solver():
+    """SURVEY N-d: assemble on the device, solve on the device (registered DeviceLinearSystemSolver plugin), update the dofs on the
+    device; the matrix never reaches the host.  One step of the (linear) transient heat problem ends where the host-side SuperLU step
+    ends, and the solver registry behaves like pyoomph's."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.linalg import spsolve
+    from pyoomph_b200.solvers import DeviceLinearSystemSolver, GenericLinearSystemSolver
+    pb = make_problem("heat3d", 3)
+    asm = make_gpu(pb)
+    n = pb["dofmap"].n_dof
+    eq = pb["dofmap"].node_eqn
+    m = eq >= 0
+    U0 = np.zeros(n); U0[eq[m]] = pb["vals"][0][m]
+    r, jac, _ = asm.assemble_host(U0, 1)
+    U_ref = U0 - spsolve(csr_matrix((jac, asm.indices, asm.indptr), shape=(n, n)).tocsc(), r)
+    solver = GenericLinearSystemSolver.factory_solver("torch_krylov")
+    assert isinstance(solver, DeviceLinearSystemSolver)
+    asm.set_dofs(U0)
+    rmax, stats = asm.newton_step_on_device(solver)
+    assert abs(rmax - np.abs(r).max()) <= 1e-12 * np.abs(r).max() and stats["relative_residual"] <= 1e-11
+    U = asm.fetch_dofs()
+    assert np.abs(U - U_ref).max() <= 1e-8 * np.abs(U_ref).max()
+    rmax2, _ = asm.newton_step_on_device(solver)                # the problem is linear: the residual is gone after one step
+    assert rmax2 <= 1e-8 * rmax
+    with pytest.raises(RuntimeError):
+        GenericLinearSystemSolver.factory_solver("no_such_solver")
+    with pytest.raises(RuntimeError):
+        GenericLinearSystemSolver.register_solver()(type("Dup", (GenericLinearSystemSolver,), {"idname": "torch_krylov"}))
+    asm.close()
