@@ -143,14 +143,14 @@ class CudaCCompiler(BaseCCompiler):
         self.fast_math = True
         return self
 
-    def flags(self) -> List[str]:
+    def flags(self, with_jitbridge: bool = True) -> List[str]:
         fl = NVCC_ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
                           "-I", INCLUDE_DIR, "-Xptxas", "-v"]
         if self.fast_math:
             fl.append("--use_fast_math")
         else:
             fl += ["--fmad=true"]
-        if self.jitbridge_include:
+        if self.jitbridge_include and with_jitbridge:
             fl += ["-DPB2_WITH_JITBRIDGE", "-I", self.jitbridge_include]
         return fl + self.extra_flags
 
@@ -159,7 +159,9 @@ class CudaCCompiler(BaseCCompiler):
             raise RuntimeError("nvcc not found: the CUDA assembly path cannot be built (no CPU fallback exists)")
         os.makedirs(JIT_DIR, exist_ok=True)
         hdr = open(os.path.join(INCLUDE_DIR, "pb2_jit_cuda.h")).read()
-        tag = hashlib.sha1((source + hdr + " ".join(self.flags())).encode()).hexdigest()[:12]
+        # the cache key leaves out where the reference's header was found: a plugin built where jitbridge.h is available (it then also
+        # exports JIT_ELEMENT_init) is the same plugin on a machine without it and must not be rebuilt there
+        tag = hashlib.sha1((source + hdr + " ".join(self.flags(with_jitbridge=False))).encode()).hexdigest()[:12]
         cu = os.path.join(JIT_DIR, "%s_%s.cu" % (name, tag))
         so = os.path.join(JIT_DIR, "%s_%s.so" % (name, tag))
         if os.path.exists(so) and not force:

@@ -106,3 +106,16 @@ def test_c_host_assembles_through_the_c_abi(tmp_path):
     assert np.array_equal(rs, asm.indptr) and np.array_equal(ci, asm.indices)
     assert np.array_equal(r_c, res) and np.array_equal(j_c, jac)
     asm.close()
+
+
+def test_prebuilt_plugins_are_reused_where_the_reference_header_is_absent():
+    """the GPU box has no /root/reference: the cache key of a plugin must not depend on where jitbridge.h was found at build time, or every
+    class would be recompiled there (and lose JIT_ELEMENT_init).  A compiler without the header and WITHOUT a working nvcc must hand back
+    the very same prebuilt shared object."""
+    from pyoomph_b200.ccompiler import CudaCCompiler
+    from pyoomph_b200.cuda_emitter import CudaEmitter
+    pb, so = _plugin("poisson")
+    cc = CudaCCompiler()
+    cc.jitbridge_include = None
+    cc.nvcc = "/nonexistent/nvcc"
+    assert cc.compile_code(CudaEmitter(pb["code"], pb["code"].name).emit(), pb["code"].name) == so
