@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 11
+#define PB2_ABI_VERSION 10
 #define PB2_MAX_PARAMS 16
 #define PB2_NTW 7           /* time-stepper storage, MultiTimeStepper (src/timestepper.hpp:37-45) */
 #define PB2_MAX_FIELDS 16
@@ -75,14 +75,7 @@ typedef struct pb2_kernel_args
   const unsigned long long *batch_bar; /* [n_batches] bit i: the scatter warps synchronise before element i of the batch (it shares
                                           CSR entries with an element of the same batch scattered since the last barrier) */
   const int *tile_nbatch;     /* [n_tiles]   batches per tile */
-  int *tile_done;             /* [n_tiles]   completion counters (kept for the per-tile schedule of ABI <= 10 plugins; unused since 11) */
-  /* dependency gates (ABI 11): a unit (a few patches of one tile, processed by ONE block) may scatter once the units of EARLIER tiles
-   * that share CSR rows with it are complete -- no device-wide synchronisation between tiles any more */
-  const int *batch_unit;      /* [n_batches] unit of the batch */
-  const int *unit_nbatch;     /* [n_units]   batches of the unit */
-  int *unit_done;             /* [n_units]   completed batches, zeroed by the host before the launch */
-  const int *unit_pred_begin; /* [n_units+1] range of the unit's predecessors in unit_pred */
-  const int *unit_pred;       /* units of earlier tiles sharing a node with the unit */
+  int *tile_done;             /* [n_tiles]   completion counters, zeroed by the host before the launch */
   int n_batches, n_tiles;
   unsigned long long *debug;  /* NULL, or [64] cycle counters filled by kernels built with PB2_TIMING=1 (development aid) */
   int *status;                /* [1] device-visible error word, 0 = fine.  PB2_STATUS_GATE_TIMEOUT: a tile gate of the persistent kernel was

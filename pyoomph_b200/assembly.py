@@ -205,11 +205,7 @@ class B200Assembly(CustomAssemblyBase):
             if patches.shape != (mesh.elem_nodes.shape[0],):
                 raise ValueError("patch hint must have one entry per element of the mesh")
         else:
-            if hasattr(mesh, "element_patches"):
-                from .meshes import balanced_patches
-                patches = balanced_patches(mesh, elements, elems_per_batch=max(1, int(self.info.elems_per_block)))
-            else:
-                patches = None
+            patches = mesh.element_patches() if hasattr(mesh, "element_patches") else None
         if patches is not None:
             patches = patches if elements is None else patches[elements]
             _, patches = np.unique(patches, return_inverse=True)       # dense ids, order preserved

@@ -103,8 +103,6 @@ struct pb2_problem
   std::vector<int> perm;         // permuted position -> original element
   bool local_order = true;       // elements of a unit in patch order (chunks of a few elements, colour-sorted inside a chunk)
   std::vector<int> unit_begin;   // [nunit+1] element range of each unit in the permuted order
-  std::vector<int> unit_pred_begin, unit_pred; // per unit: the units of earlier tiles that share a node with it (dependency gates)
-  int *d_unit_pred_begin = nullptr, *d_unit_pred = nullptr;
   std::vector<int> h_elem_nodes; // permuted element -> nodes (host copy, for the barrier masks of the batch tables)
   std::vector<int> row_start;
   RawVec<int> col_index;
@@ -124,8 +122,6 @@ struct pb2_problem
   {
     int epb = 0, grid = 0, n_batches = 0, n_tiles = 0;
     int *d_batch_elem = nullptr, *d_batch_meta = nullptr, *d_tile_nbatch = nullptr, *d_tile_done = nullptr, *d_block_begin = nullptr;
-    int *d_batch_unit = nullptr, *d_unit_nbatch = nullptr, *d_unit_done = nullptr;
-    int n_units = 0;
     unsigned long long *d_batch_bar = nullptr;
   };
   std::vector<BatchTables> batch_tables;
@@ -393,34 +389,8 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
     }
   }
   phase("patch colouring");
-  // units: consecutive patches of one tile.  A tile ends at a device-wide gate, so its units should split evenly over the persistent
-  // grid (one block per SM): among 4, 3, 2, 1 patches per unit take the one with the least idle time ceil(U / grid) * grid / U at the
-  // gates, larger units preferred on ties (measured, profiles/r02_notes.md: 262 k elements, 4 -> 1 patches per unit: 0.792 -> 0.700 ms).
+  // units: consecutive patches of one tile
   int unit_patches = 4;
-  {
-    std::vector<long long> per_tile(std::max(1, npcol), 0);
-    for (int q = 0; q < npatch; q++) per_tile[pcolour[q]]++;
-    const double grid_blocks = (double)std::max(1, p->n_sms), epb = (double)std::max(1, ci.elems_per_block);
-    const double patch_elems = (double)ne / std::max(1, npatch);
-    double best = 1e300;
-    for (int cand = 4; cand >= 1; cand--)
-    {
-      double idle = 0.0;
-      for (int t = 0; t < npcol; t++)
-      {
-        const double U = (double)((per_tile[t] + cand - 1) / cand);
-        if (U > 0) idle += std::ceil(U / grid_blocks) * grid_blocks / U;
-      }
-      // a unit is cut into batches of epb elements: small units leave their last batch half empty
-      const double fill = cand * patch_elems / (std::ceil(cand * patch_elems / epb) * epb);
-      const double cost = idle / std::max(1e-9, fill);
-      if (cost < best * 0.98)
-      {
-        best = cost;
-        unit_patches = cand;
-      }
-    }
-  }
   if (const char *cs = getenv("PB2_UNIT_PATCHES")) unit_patches = std::max(1, atoi(cs));
   std::vector<int> unit_of_patch(npatch), unit_tile;
   {
@@ -488,46 +458,6 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   for (int u = 0; u < nunit; u++) p->unit_begin[u + 1] += p->unit_begin[u];
 
   phase("schedule order");
-  // ---- dependency gates: unit u may scatter when every unit of an EARLIER tile sharing a node with it is complete
-  {
-    std::vector<std::pair<int, int>> node_unit; // unique (node, unit) pairs; elements of a unit are consecutive in the schedule
-    node_unit.reserve((size_t)ne * nn / 8 + 16);
-    std::vector<int> last_unit_of_node(m->n_node, -1);
-    for (long long q = 0; q < ne; q++)
-    {
-      const long long e = p->perm[q];
-      const int u = unit_rank[unit_of_patch[patch_of[e]]];
-      for (int l = 0; l < nn; l++)
-      {
-        const int node = m->elem_nodes[e * nn + l];
-        if (last_unit_of_node[node] != u)
-        {
-          last_unit_of_node[node] = u;
-          node_unit.push_back({node, u});
-        }
-      }
-    }
-    std::sort(node_unit.begin(), node_unit.end());
-    node_unit.erase(std::unique(node_unit.begin(), node_unit.end()), node_unit.end());
-    std::vector<std::pair<int, int>> dep; // (unit, predecessor)
-    for (size_t i = 0; i < node_unit.size();)
-    {
-      size_t j = i;
-      while (j < node_unit.size() && node_unit[j].first == node_unit[i].first) j++;
-      for (size_t x = i; x < j; x++)
-        for (size_t y = i; y < j; y++)
-          if (p->unit_tile[node_unit[y].second] < p->unit_tile[node_unit[x].second]) dep.push_back({node_unit[x].second, node_unit[y].second});
-      i = j;
-    }
-    std::sort(dep.begin(), dep.end());
-    dep.erase(std::unique(dep.begin(), dep.end()), dep.end());
-    p->unit_pred_begin.assign((size_t)nunit + 1, 0);
-    for (auto &d : dep) p->unit_pred_begin[d.first + 1]++;
-    for (int u = 0; u < nunit; u++) p->unit_pred_begin[u + 1] += p->unit_pred_begin[u];
-    p->unit_pred.resize(dep.size());
-    for (size_t i = 0; i < dep.size(); i++) p->unit_pred[i] = dep[i].second; // dep is sorted by unit: already in CSR order
-  }
-  phase("unit dependencies");
   // ---- permuted element tables
   std::vector<int> elem_nodes((size_t)ne * nn), elem_eqn((size_t)ne * nd);
 #pragma omp parallel for schedule(static)
@@ -900,8 +830,6 @@ extern "C" void pb2_problem_free(pb2_problem *p)
   cudaFree(p->d_row_start);
   cudaFree(p->d_col_index);
   cudaFree(p->d_debug);
-  cudaFree(p->d_unit_pred_begin);
-  cudaFree(p->d_unit_pred);
   if (p->h_status) cudaFreeHost(p->h_status);
   if (p->ev_inputs) cudaEventDestroy(p->ev_inputs);
   for (auto &b : p->batch_tables)
@@ -911,9 +839,6 @@ extern "C" void pb2_problem_free(pb2_problem *p)
     cudaFree(b.d_batch_meta);
     cudaFree(b.d_tile_nbatch);
     cudaFree(b.d_tile_done);
-    cudaFree(b.d_batch_unit);
-    cudaFree(b.d_unit_nbatch);
-    cudaFree(b.d_unit_done);
     cudaFree(b.d_block_begin);
   }
   delete p;
@@ -1144,9 +1069,9 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
       pb2_problem::BatchTables nb;
       nb.epb = cfg.elems_per_batch;
       nb.grid = grid;
-      std::vector<std::vector<int>> be(grid), bm(grid), bu(grid);
+      std::vector<std::vector<int>> be(grid), bm(grid);
       std::vector<std::vector<unsigned long long>> bbar(grid);
-      std::vector<int> tn(std::max(1, p->n_tiles), 0), un(std::max(1, nunit), 0);
+      std::vector<int> tn(std::max(1, p->n_tiles), 0);
       std::vector<int> stamp;
       int epoch = 0;
       if (p->local_order) stamp.assign((size_t)p->n_node, -1);
@@ -1181,10 +1106,8 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
               }
               be[blk].push_back(e);
               bm[blk].push_back((t << 7) | nel);
-              bu[blk].push_back(u);
               bbar[blk].push_back(mask);
               tn[t]++;
-              un[u]++;
             }
             continue;
           }
@@ -1199,43 +1122,31 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
               const int fence = (!first_of_unit && first_of_colour) ? 64 : 0;
               be[blk].push_back(e);
               bm[blk].push_back((t << 7) | fence | std::min(nb.epb, b1 - e));
-              bu[blk].push_back(u);
               bbar[blk].push_back(0ull);
               tn[t]++;
-              un[u]++;
               first_of_colour = false;
               first_of_unit = false;
             }
           }
         }
       }
-      std::vector<int> fe, fm, fu, bb(grid + 1, 0);
+      std::vector<int> fe, fm, bb(grid + 1, 0);
       std::vector<unsigned long long> fb;
       for (int b = 0; b < grid; b++)
       {
         bb[b + 1] = bb[b] + (int)be[b].size();
         fe.insert(fe.end(), be[b].begin(), be[b].end());
         fm.insert(fm.end(), bm[b].begin(), bm[b].end());
-        fu.insert(fu.end(), bu[b].begin(), bu[b].end());
         fb.insert(fb.end(), bbar[b].begin(), bbar[b].end());
       }
       nb.n_batches = (int)fe.size();
       nb.n_tiles = p->n_tiles;
       if (upload(&nb.d_batch_elem, fe) || upload(&nb.d_batch_meta, fm) || upload(&nb.d_batch_bar, fb) || upload(&nb.d_tile_nbatch, tn) || upload(&nb.d_block_begin, bb)) return 1;
       CUDA_OK(cudaMalloc((void **)&nb.d_tile_done, std::max(1, nb.n_tiles) * sizeof(int)));
-      nb.n_units = nunit;
-      if (upload(&nb.d_batch_unit, fu) || upload(&nb.d_unit_nbatch, un)) return 1;
-      CUDA_OK(cudaMalloc((void **)&nb.d_unit_done, std::max(1, nunit) * sizeof(int)));
-      if (!p->d_unit_pred_begin && (upload(&p->d_unit_pred_begin, p->unit_pred_begin) || upload(&p->d_unit_pred, p->unit_pred))) return 1;
       p->batch_tables.push_back(nb);
       bt = &p->batch_tables.back();
     }
-    CUDA_OK(cudaMemsetAsync(bt->d_unit_done, 0, std::max(1, bt->n_units) * sizeof(int), (cudaStream_t)cuda_stream));
-    a.batch_unit = bt->d_batch_unit;
-    a.unit_nbatch = bt->d_unit_nbatch;
-    a.unit_done = bt->d_unit_done;
-    a.unit_pred_begin = p->d_unit_pred_begin;
-    a.unit_pred = p->d_unit_pred;
+    CUDA_OK(cudaMemsetAsync(bt->d_tile_done, 0, std::max(1, bt->n_tiles) * sizeof(int), (cudaStream_t)cuda_stream));
     a.batch_elem = bt->d_batch_elem;
     a.batch_meta = bt->d_batch_meta;
     a.batch_bar = bt->d_batch_bar;

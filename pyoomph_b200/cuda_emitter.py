@@ -189,9 +189,6 @@ class CudaEmitter:
         # round-2 experiment (off: compiled and algebra-checked on the CPU only, not yet run on a GPU): sum factorisation of the column
         # side over the Gauss points, DESIGN.md section 9 item 4
         self.sum_factorise = self.tensor_columns and os.environ.get("PB2_SUMFAC", "1") != "0"
-        # 2D analogue: the Q9 column side of a row contracted direction by direction (135 instead of 243 DFMA per Q9 block and row);
-        # Q4 column blocks keep the table form
-        self.sum_factorise_2d = self.dim == 2 and os.environ.get("PB2_SUMFAC2D", "0") == "1"
 
     # ------------------------------------------------------------------ planning
     def _col_index(self, field: str, lnode: int) -> int:
@@ -325,14 +322,6 @@ class CudaEmitter:
                     P, D = _lag(3, sk[d])
                     t1 += list(P) + list(D)
         t1_smem = t1
-        if self.dim == 2 and self.sum_factorise_2d:
-            # the same for quads: [ipt][dir][L_0..L_2, L'_0..L'_2]; psi_c = L_a(s0) L_b(s1), c = a + 3b (Qelements.cc:348-377); constant bank only
-            t2 = []
-            for sk in kn:
-                for d in range(2):
-                    P, D = _lag(3, sk[d])
-                    t2 += list(P) + list(D)
-            o.append("__constant__ double c_t1d[%d] = {%s};" % (len(t2), ", ".join(repr(float(v)) for v in t2)))
         o.append("// reference-element tables at the oomph Gauss points (integral.cc literals, shape.h polynomials)")
         o.append("__constant__ double c_w[%d] = {%s};" % (self.NIPT, arr(w)))
         o.append("__constant__ double c_psi2[%d] = {%s};" % (self.NIPT * self.NN, arr(v for p in psi2 for v in p)))
@@ -685,7 +674,7 @@ class CudaEmitter:
         w("  {")
         w("    const int st = tid - %d;" % (NC + NG))
         w("    long long dbs0 = 0, dbs1 = 0, dbs2 = 0, dbs3 = 0; (void)dbs0; (void)dbs1; (void)dbs2; (void)dbs3;")
-        w("    int it = 0, item = 0, prev_unit = -1, pending = 0;")
+        w("    int it = 0, item = 0, gated_tile = 0, prev_tile = -1, pending = 0;")
         w("    unsigned char* const maps0 = (unsigned char*)(smem + %d);" % off_maps)
         # prefetch helper (lambda-like macro through a local struct is overkill: emit the loop twice)
         def emit_prefetch(indent, batch_expr, slot_expr):
@@ -709,33 +698,29 @@ class CudaEmitter:
         emit_prefetch("    ", "ib0", "0")
         w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
-        w("      const int meta = a.batch_meta[batch], nel = meta & 63, unit = a.batch_unit[batch];")
+        w("      const int meta = a.batch_meta[batch], nel = meta & 63, tile = meta >> 7;")
         w("      const unsigned long long bmask = a.batch_bar[batch];")
         w("      unsigned char* const mbase = maps0 + (it & 1) * %d;" % map_slot_bytes)
         w("      int* const s_rowstart = (int*)mbase; int* const s_resmap = s_rowstart + %d; unsigned char* const s_map = (unsigned char*)(s_resmap + %d);" % (EPB * ND, EPB * ND))
         w("      (void)s_map;")
         if self.timing: w("      long long ts0 = clock64();")
         w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")
-        w("      const bool publish = prev_unit >= 0 && (unit != prev_unit || (meta & 64));")
+        w("      const bool publish = prev_tile >= 0 && (tile != prev_tile || (meta & 64));")
         w("      if (publish) __threadfence();               // everything scattered so far becomes globally visible")
         w("      pb2_bar_sync(11, %d);                       // maps of this batch visible to all scatter warps; previous batch fully issued" % NS)
         w("      if (batch + 1 < ib1)")
         emit_prefetch("      ", "batch + 1", "(it + 1) & 1")
-        w("      if (publish && unit != prev_unit) { if (st == 0) atomicAdd(a.unit_done + prev_unit, pending); pending = 0; }")
+        w("      if (publish && tile != prev_tile) { if (st == 0) atomicAdd(a.tile_done + prev_tile, pending); pending = 0; }")
+        w("      prev_tile = tile; ++pending;")
         if self.timing: w("      long long ts1 = clock64(); dbs0 += ts1 - ts0;")
-        w("      // order of the colours without a device-wide barrier: a new unit starts scattering once the units of EARLIER tiles that share")
-        w("      // CSR rows with it are complete (their blocks never wait for a later tile: no cycle); one scatter thread per predecessor")
-        w("      if (unit != prev_unit)")
+        w("      // stream order of the colours: everything of the previous tile must have been scattered")
+        w("      if (tile > gated_tile)")
         w("      {")
-        w("        const int p0 = a.unit_pred_begin[unit], p1 = a.unit_pred_begin[unit + 1];")
-        w("        if (p1 > p0)")
-        w("        {")
-        w("          for (int pi = p0 + st; pi < p1; pi += %d) { const int pu = a.unit_pred[pi]; pb2_gate_wait(a.unit_done + pu, a.unit_nbatch[pu], a.status); }" % NS)
-        w("          pb2_bar_sync(11, %d);                   // all predecessors complete (unit is uniform over the scatter warps)" % NS)
-        w("          __threadfence();")
-        w("        }")
+        w("        if (st == 0) pb2_gate_wait(a.tile_done + tile - 1, a.tile_nbatch[tile - 1], a.status);")
+        w("        gated_tile = tile;")
+        w("        pb2_bar_sync(11, %d);                     // gate passed (tile, gated_tile are uniform over the scatter warps)" % NS)
+        w("        __threadfence();")
         w("      }")
-        w("      prev_unit = unit; ++pending;")
         is_h = rp.key.startswith("h")      # Hessian-vector routine: matrices only, no residual
         passes = [("J", "a.jac_vals", not is_h)] if what >= 1 else [("R", None, True)]
         if what >= 2:
@@ -767,7 +752,7 @@ class CudaEmitter:
         w("        pb2_bar_arrive(%d + oslot, %d);           // OUT[oslot] free again" % (7, NC + NS))
         w("      }")
         w("    }")
-        w("    if (prev_unit >= 0) { __threadfence(); pb2_bar_sync(11, %d); if (st == 0) atomicAdd(a.unit_done + prev_unit, pending); }" % NS)
+        w("    if (prev_tile >= 0) { __threadfence(); pb2_bar_sync(11, %d); if (st == 0) atomicAdd(a.tile_done + prev_tile, pending); }" % NS)
         if self.timing: w("    if (st == 0 && a.debug) { atomicAdd(a.debug + 4, (unsigned long long)dbs0); atomicAdd(a.debug + 5, (unsigned long long)dbs1); atomicAdd(a.debug + 6, (unsigned long long)dbs2); atomicAdd(a.debug + 7, (unsigned long long)dbs3); }")
         w("  }")
         # ---------------------------------------------------------------- compute warps
@@ -1282,22 +1267,7 @@ class CudaEmitter:
         w("        for (int i = 0; i < %d; ++i) acc[i] = 0.0;" % nacc)
         sf = self.sum_factorise and RB == 1 and bool(pairs) and all(code.fields[G].space != "C1" for (F_, G) in pairs)
         sf_pairs: List[Tuple[str, bool, bool, int]] = []
-        sf2 = self.sum_factorise_2d and RB == 1 and any(code.fields[G].space != "C1" for (F_, G) in pairs)
-        sf2_pairs: List[Tuple[str, bool, bool, int, int]] = []
-        if sf2:
-            # Gauss point (sp, sq) = ipt sp*3 + sq (s0 outer); the s1 direction is contracted point by point into X0 / X1, the s0 direction
-            # once per sp
-            w("        #pragma unroll 1")
-            w("        for (int sp = 0; sp < 3; ++sp)")
-            w("        {")
-            for (F_, G_) in pairs:
-                if code.fields[G_].space != "C1":
-                    w("          double sfX0_%s_%s[3] = {0.0, 0.0, 0.0}, sfX1_%s_%s[3] = {0.0, 0.0, 0.0};" % (F_, G_, F_, G_))
-            w("          #pragma unroll")
-            w("          for (int sq = 0; sq < 3; ++sq)")
-            w("        {")
-            w("          const int ipt = sp * 3 + sq;")
-        elif sf:
+        if sf:
             # Gauss point (sp, sq, sr) = ipt sp*9 + sq*3 + sr; sr is contracted point by point into U, sq and sp after the inner loops
             w("        #pragma unroll 1")
             w("        for (int sp = 0; sp < 3; ++sp)")
@@ -1326,8 +1296,6 @@ class CudaEmitter:
             w("          " + " ".join("const double gg%d%d = P[%d];" % (b, i, plan["gg"] + b * dim + i) for b in range(dim) for i in range(dim)))
         if need_X:
             w("          " + " ".join("const double ggL%d%d = P[%d];" % (b, i, plan["ggL"] + b * dim + i) for b in range(dim) for i in range(dim)))
-        if sf2:
-            w("          " + " ".join("const double tL1%d = c_t1d[ipt * 12 + %d]; const double tD1%d = c_t1d[ipt * 12 + %d];" % (n, 6 + n, n, 9 + n) for n in range(3)))
         tp = self.tensor_columns and any(code.fields[G].space != "C1" for (F_, G) in pairs)
         if tp:
             for d in ((2,) if sf else range(3)):
@@ -1387,17 +1355,6 @@ class CudaEmitter:
                     tp, td = ("s_psi1", "s_dpsi1") if self.table_source == "smem" else ("c_psi1", "c_dpsi1")
                 else:
                     tp, td = ("s_psi2", "s_dpsi2") if self.table_source == "smem" else ("c_psi2", "c_dpsi2")
-                if sf2 and Gs != "C1":
-                    # X0[b] += W0 L_b(q) + Ws1 L'_b(q);  X1[b] += Ws0 L_b(q)   (b: basis index of the s1 direction)
-                    pf = "%s_%s" % (F, G)
-                    w0 = "W_%s_d0" % pf if "d0" in by_atom else None
-                    for b in range(3):
-                        terms = ([("%s * tL1%d" % (w0, b))] if w0 else []) + ([("Ws1_%s * tD1%d" % (pf, b))] if have_s else [])
-                        w("            sfX0_%s[%d] += %s;" % (pf, b, " + ".join(terms)))
-                        if have_s:
-                            w("            sfX1_%s[%d] = fma(Ws0_%s, tL1%d, sfX1_%s[%d]);" % (pf, b, pf, b, pf, b))
-                    sf2_pairs.append((pf, have_s, base[(F, G)], nnG, 0))
-                    continue
                 if sf:
                     # contraction of the third direction, point by point: U03 collects what is later multiplied by L_b(q) L_a(p),
                     # U1 by L_b(q) L'_a(p), U2 by L'_b(q) L_a(p)
@@ -1452,21 +1409,6 @@ class CudaEmitter:
                 w("              %s = %s;" % (accname, expr))
         w("          }")
         w("        }")
-        if sf2:
-            # first direction: J[a + 3b] += L_a(p) X0[b] + L'_a(p) X1[b] with the factors of the s0 knot of this sp
-            w("          {")
-            w("            const int k = 0; (void)k;")
-            w("            " + " ".join("const double sfLa%d = c_t1d[sp * 36 + %d]; const double sfDa%d = c_t1d[sp * 36 + %d];" % (a_, a_, a_, 3 + a_) for a_ in range(3)))
-            for (pf, have_s, b0, nnG, _) in sf2_pairs:
-                for b in range(3):
-                    for a_ in range(3):
-                        an = "acc[%d + k * %d + %d]" % (b0, nnG, a_ + 3 * b)
-                        e = "fma(sfX0_%s[%d], sfLa%d, %s)" % (pf, b, a_, an)
-                        if have_s:
-                            e = "fma(sfX1_%s[%d], sfDa%d, %s)" % (pf, b, a_, e)
-                        w("            %s = %s;" % (an, e))
-            w("          }")
-            w("        }")
         if sf:
             # second direction (constant factors, q unrolled), then first direction (factors of plane sp)
             w("          {")

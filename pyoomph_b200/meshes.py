@@ -45,53 +45,16 @@ class StructuredMesh:
     def is_vertex(self) -> np.ndarray:
         return np.all(self.node_lattice % 2 == 0, axis=1)
 
-    def element_patches(self, width=None) -> np.ndarray:
-        """Locality hint for the GPU schedule: id of the compact patch (8x8 quads / 4x4x4 bricks) of every element.
-        width: one int or one per dimension (rectangular patches, e.g. (8, 4))."""
+    def element_patches(self, width: Optional[int] = None) -> np.ndarray:
+        """Locality hint for the GPU schedule: id of the compact patch (8x8 quads / 4x4x4 bricks) of every element."""
         import os
         w = width or int(os.environ.get("PB2_PATCH_WIDTH", "8" if self.dim == 2 else "4"))
-        ws = [int(w)] * self.dim if np.isscalar(w) else [int(x) for x in w]
-        grids = np.meshgrid(*[np.arange(n, dtype=np.int64) // ws[d] for d, n in enumerate(self.N)], indexing="ij")
-        npd = [(n + ws[d] - 1) // ws[d] for d, n in enumerate(self.N)]
+        grids = np.meshgrid(*[np.arange(n, dtype=np.int64) // w for n in self.N], indexing="ij")
+        npd = [(n + w - 1) // w for n in self.N]
         pid = grids[0].ravel()
         for d in range(1, self.dim):
             pid = pid * npd[d] + grids[d].ravel()
         return pid.astype(np.int32)
-
-
-def balanced_patches(mesh, elements=None, n_blocks: int = 148, elems_per_batch: int = 14):
-    """Patch hint for a structured mesh (or an element block of it) whose tiles split evenly over the persistent grid: the engine
-    synchronises device-wide after every tile (= patch colour; 2^dim of them on a lattice), so the number of work units per tile should
-    be close to a multiple of the block count, while a unit (1..4 patches, processed batch by batch) should fill its batches.
-    Cost of a patch shape = least (idle blocks at the gates) / (batch fill) over 4..1 patches per unit; among the shapes 8x8, 8x4,
-    4x8, 4x4 (bricks: 4x4x4, 4x4x2, 4x2x2) the first within 2 % of the best is taken, larger shapes first; the engine picks the
-    patches per unit by the same rule (pb2_problem_create).  Matters for the small per-GPU meshes of a multi-GPU run (128 x 1024
-    elements per GPU at 8 GPUs: 8x8 patches leave 13 % of the blocks idle at every gate, 8x4 patches 1 %)."""
-    import os
-    if os.environ.get("PB2_PATCH_WIDTH"):
-        return mesh.element_patches()
-    dim = mesh.dim
-    shapes = [(8, 8), (8, 4), (4, 8), (4, 4)] if dim == 2 else [(4, 4, 4), (4, 4, 2), (4, 2, 2)]
-    ntile = 2 ** dim
-    costs = []
-    for shp in shapes:
-        pid = mesh.element_patches(shp)
-        if elements is not None:
-            pid = pid[elements]
-        npatch = np.unique(pid).size
-        pel = float(np.prod(shp))
-        best = np.inf
-        for up in (4, 3, 2, 1):
-            U = max(1.0, np.ceil(npatch / ntile / up))
-            idle = np.ceil(U / n_blocks) * n_blocks / U
-            fill = (up * pel) / (np.ceil(up * pel / elems_per_batch) * elems_per_batch)
-            best = min(best, idle / fill)
-        costs.append(best)
-    target = min(costs) * 1.02
-    for shp, c in zip(shapes, costs):
-        if c <= target:
-            return mesh.element_patches(shp)
-    return mesh.element_patches(shapes[0])
 
 
 def _first_occurrence_ids(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
