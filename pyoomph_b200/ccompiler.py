@@ -161,7 +161,9 @@ class CudaCCompiler(BaseCCompiler):
         hdr = open(os.path.join(INCLUDE_DIR, "pb2_jit_cuda.h")).read()
         # the cache key leaves out where the reference's header was found: a plugin built where jitbridge.h is available (it then also
         # exports JIT_ELEMENT_init) is the same plugin on a machine without it and must not be rebuilt there
-        tag = hashlib.sha1((source + hdr + " ".join(self.flags(with_jitbridge=False))).encode()).hexdigest()[:12]
+        # ... nor on where the checkout lies (the GPU box mounts the repository under another path)
+        key_flags = ["<include>" if f == INCLUDE_DIR else f for f in self.flags(with_jitbridge=False)]
+        tag = hashlib.sha1((source + hdr + " ".join(key_flags)).encode()).hexdigest()[:12]
         cu = os.path.join(JIT_DIR, "%s_%s.cu" % (name, tag))
         so = os.path.join(JIT_DIR, "%s_%s.so" % (name, tag))
         if os.path.exists(so) and not force:

@@ -189,6 +189,9 @@ class CudaEmitter:
         # round-2 experiment (off: compiled and algebra-checked on the CPU only, not yet run on a GPU): sum factorisation of the column
         # side over the Gauss points, DESIGN.md section 9 item 4
         self.sum_factorise = self.tensor_columns and os.environ.get("PB2_SUMFAC", "1") != "0"
+        # 2D analogue: the Q9 column side of a row contracted direction by direction (135 instead of 243 DFMA per Q9 block and row);
+        # Q4 column blocks keep the table form
+        self.sum_factorise_2d = self.dim == 2 and os.environ.get("PB2_SUMFAC2D", "0") == "1"
 
     # ------------------------------------------------------------------ planning
     def _col_index(self, field: str, lnode: int) -> int:
@@ -322,6 +325,14 @@ class CudaEmitter:
                     P, D = _lag(3, sk[d])
                     t1 += list(P) + list(D)
         t1_smem = t1
+        if self.dim == 2 and self.sum_factorise_2d:
+            # the same for quads: [ipt][dir][L_0..L_2, L'_0..L'_2]; psi_c = L_a(s0) L_b(s1), c = a + 3b (Qelements.cc:348-377); constant bank only
+            t2 = []
+            for sk in kn:
+                for d in range(2):
+                    P, D = _lag(3, sk[d])
+                    t2 += list(P) + list(D)
+            o.append("__constant__ double c_t1d[%d] = {%s};" % (len(t2), ", ".join(repr(float(v)) for v in t2)))
         o.append("// reference-element tables at the oomph Gauss points (integral.cc literals, shape.h polynomials)")
         o.append("__constant__ double c_w[%d] = {%s};" % (self.NIPT, arr(w)))
         o.append("__constant__ double c_psi2[%d] = {%s};" % (self.NIPT * self.NN, arr(v for p in psi2 for v in p)))
@@ -1267,7 +1278,22 @@ class CudaEmitter:
         w("        for (int i = 0; i < %d; ++i) acc[i] = 0.0;" % nacc)
         sf = self.sum_factorise and RB == 1 and bool(pairs) and all(code.fields[G].space != "C1" for (F_, G) in pairs)
         sf_pairs: List[Tuple[str, bool, bool, int]] = []
-        if sf:
+        sf2 = self.sum_factorise_2d and RB == 1 and any(code.fields[G].space != "C1" for (F_, G) in pairs)
+        sf2_pairs: List[Tuple[str, bool, bool, int, int]] = []
+        if sf2:
+            # Gauss point (sp, sq) = ipt sp*3 + sq (s0 outer); the s1 direction is contracted point by point into X0 / X1, the s0 direction
+            # once per sp
+            w("        #pragma unroll 1")
+            w("        for (int sp = 0; sp < 3; ++sp)")
+            w("        {")
+            for (F_, G_) in pairs:
+                if code.fields[G_].space != "C1":
+                    w("          double sfX0_%s_%s[3] = {0.0, 0.0, 0.0}, sfX1_%s_%s[3] = {0.0, 0.0, 0.0};" % (F_, G_, F_, G_))
+            w("          #pragma unroll")
+            w("          for (int sq = 0; sq < 3; ++sq)")
+            w("        {")
+            w("          const int ipt = sp * 3 + sq;")
+        elif sf:
             # Gauss point (sp, sq, sr) = ipt sp*9 + sq*3 + sr; sr is contracted point by point into U, sq and sp after the inner loops
             w("        #pragma unroll 1")
             w("        for (int sp = 0; sp < 3; ++sp)")
@@ -1296,6 +1322,8 @@ class CudaEmitter:
             w("          " + " ".join("const double gg%d%d = P[%d];" % (b, i, plan["gg"] + b * dim + i) for b in range(dim) for i in range(dim)))
         if need_X:
             w("          " + " ".join("const double ggL%d%d = P[%d];" % (b, i, plan["ggL"] + b * dim + i) for b in range(dim) for i in range(dim)))
+        if sf2:
+            w("          " + " ".join("const double tL1%d = c_t1d[ipt * 12 + %d]; const double tD1%d = c_t1d[ipt * 12 + %d];" % (n, 6 + n, n, 9 + n) for n in range(3)))
         tp = self.tensor_columns and any(code.fields[G].space != "C1" for (F_, G) in pairs)
         if tp:
             for d in ((2,) if sf else range(3)):
@@ -1355,6 +1383,17 @@ class CudaEmitter:
                     tp, td = ("s_psi1", "s_dpsi1") if self.table_source == "smem" else ("c_psi1", "c_dpsi1")
                 else:
                     tp, td = ("s_psi2", "s_dpsi2") if self.table_source == "smem" else ("c_psi2", "c_dpsi2")
+                if sf2 and Gs != "C1":
+                    # X0[b] += W0 L_b(q) + Ws1 L'_b(q);  X1[b] += Ws0 L_b(q)   (b: basis index of the s1 direction)
+                    pf = "%s_%s" % (F, G)
+                    w0 = "W_%s_d0" % pf if "d0" in by_atom else None
+                    for b in range(3):
+                        terms = ([("%s * tL1%d" % (w0, b))] if w0 else []) + ([("Ws1_%s * tD1%d" % (pf, b))] if have_s else [])
+                        w("            sfX0_%s[%d] += %s;" % (pf, b, " + ".join(terms)))
+                        if have_s:
+                            w("            sfX1_%s[%d] = fma(Ws0_%s, tL1%d, sfX1_%s[%d]);" % (pf, b, pf, b, pf, b))
+                    sf2_pairs.append((pf, have_s, base[(F, G)], nnG, 0))
+                    continue
                 if sf:
                     # contraction of the third direction, point by point: U03 collects what is later multiplied by L_b(q) L_a(p),
                     # U1 by L_b(q) L'_a(p), U2 by L'_b(q) L_a(p)
@@ -1409,6 +1448,21 @@ class CudaEmitter:
                 w("              %s = %s;" % (accname, expr))
         w("          }")
         w("        }")
+        if sf2:
+            # first direction: J[a + 3b] += L_a(p) X0[b] + L'_a(p) X1[b] with the factors of the s0 knot of this sp
+            w("          {")
+            w("            const int k = 0; (void)k;")
+            w("            " + " ".join("const double sfLa%d = c_t1d[sp * 36 + %d]; const double sfDa%d = c_t1d[sp * 36 + %d];" % (a_, a_, a_, 3 + a_) for a_ in range(3)))
+            for (pf, have_s, b0, nnG, _) in sf2_pairs:
+                for b in range(3):
+                    for a_ in range(3):
+                        an = "acc[%d + k * %d + %d]" % (b0, nnG, a_ + 3 * b)
+                        e = "fma(sfX0_%s[%d], sfLa%d, %s)" % (pf, b, a_, an)
+                        if have_s:
+                            e = "fma(sfX1_%s[%d], sfDa%d, %s)" % (pf, b, a_, e)
+                        w("            %s = %s;" % (an, e))
+            w("          }")
+            w("        }")
         if sf:
             # second direction (constant factors, q unrolled), then first direction (factors of plane sp)
             w("          {")

@@ -45,12 +45,14 @@ class StructuredMesh:
     def is_vertex(self) -> np.ndarray:
         return np.all(self.node_lattice % 2 == 0, axis=1)
 
-    def element_patches(self, width: Optional[int] = None) -> np.ndarray:
-        """Locality hint for the GPU schedule: id of the compact patch (8x8 quads / 4x4x4 bricks) of every element."""
+    def element_patches(self, width=None) -> np.ndarray:
+        """Locality hint for the GPU schedule: id of the compact patch (8x8 quads / 4x4x4 bricks) of every element.
+        width: one int or one per dimension (rectangular patches, e.g. (8, 4))."""
         import os
         w = width or int(os.environ.get("PB2_PATCH_WIDTH", "8" if self.dim == 2 else "4"))
-        grids = np.meshgrid(*[np.arange(n, dtype=np.int64) // w for n in self.N], indexing="ij")
-        npd = [(n + w - 1) // w for n in self.N]
+        ws = [int(w)] * self.dim if np.isscalar(w) else [int(x) for x in w]
+        grids = np.meshgrid(*[np.arange(n, dtype=np.int64) // ws[d] for d, n in enumerate(self.N)], indexing="ij")
+        npd = [(n + ws[d] - 1) // ws[d] for d, n in enumerate(self.N)]
         pid = grids[0].ravel()
         for d in range(1, self.dim):
             pid = pid * npd[d] + grids[d].ravel()

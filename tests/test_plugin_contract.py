@@ -108,7 +108,7 @@ def test_c_host_assembles_through_the_c_abi(tmp_path):
     asm.close()
 
 
-def test_prebuilt_plugins_are_reused_where_the_reference_header_is_absent():
+def test_prebuilt_plugins_are_reused_where_the_reference_header_is_absent(tmp_path):
     """the GPU box has no /root/reference: the cache key of a plugin must not depend on where jitbridge.h was found at build time, or every
     class would be recompiled there (and lose JIT_ELEMENT_init).  A compiler without the header and WITHOUT a working nvcc must hand back
     the very same prebuilt shared object."""
@@ -119,3 +119,12 @@ def test_prebuilt_plugins_are_reused_where_the_reference_header_is_absent():
     cc.jitbridge_include = None
     cc.nvcc = "/nonexistent/nvcc"
     assert cc.compile_code(CudaEmitter(pb["code"], pb["code"].name).emit(), pb["code"].name) == so
+    # ... and the key must not contain the absolute path of the checkout either (the box mounts it elsewhere)
+    import pyoomph_b200.ccompiler as ccm
+    saved = ccm.INCLUDE_DIR
+    try:
+        ccm.INCLUDE_DIR = str(tmp_path / "include")
+        shutil.copytree(saved, ccm.INCLUDE_DIR)
+        assert os.path.basename(cc.compile_code(CudaEmitter(pb["code"], pb["code"].name).emit(), pb["code"].name)) == os.path.basename(so)
+    finally:
+        ccm.INCLUDE_DIR = saved
