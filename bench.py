@@ -127,7 +127,7 @@ def build_workload(workload, n, seed=0):
     from pyoomph_b200.meshes import CuboidBrickMesh, RectangularQuadMesh, assign_equation_numbers
     from problems import poisson_source
     if workload == "ns_cavity":
-        mesh = RectangularQuadMesh(n)
+        mesh = RectangularQuadMesh((n, int(os.environ["PB2_BENCH_NY"])) if os.environ.get("PB2_BENCH_NY") else n)   # strip meshes: schedule experiments
         code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0), name="ns")
         wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "right", "bottom", "top")]))
         pinned = {"velocity_x": wall, "velocity_y": wall, "pressure": np.array([0])}

@@ -49,7 +49,10 @@ class StructuredMesh:
         """Locality hint for the GPU schedule: id of the compact patch (8x8 quads / 4x4x4 bricks) of every element.
         width: one int or one per dimension (rectangular patches, e.g. (8, 4))."""
         import os
-        w = width or int(os.environ.get("PB2_PATCH_WIDTH", "8" if self.dim == 2 else "4"))
+        w = width or os.environ.get("PB2_PATCH_WIDTH", "8" if self.dim == 2 else "4")      # "8" or per dimension "8x4"
+        if isinstance(w, str):
+            w = [int(x) for x in w.split("x")]
+            w = w[0] if len(w) == 1 else w
         ws = [int(w)] * self.dim if np.isscalar(w) else [int(x) for x in w]
         grids = np.meshgrid(*[np.arange(n, dtype=np.int64) // ws[d] for d, n in enumerate(self.N)], indexing="ij")
         npd = [(n + ws[d] - 1) // ws[d] for d, n in enumerate(self.N)]
