@@ -18,13 +18,14 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 10
+#define PB2_ABI_VERSION 11
 #define PB2_MAX_PARAMS 16
 #define PB2_NTW 7           /* time-stepper storage, MultiTimeStepper (src/timestepper.hpp:37-45) */
 #define PB2_MAX_FIELDS 16
 #define PB2_MAX_ROUTINES 64
 #define PB2_MAX_HVEC 4      /* vectors per Hessian-vector launch */
 #define PB2_MAX_INTEGRALS 16 /* integral expressions per element class */
+#define PB2_MAX_POINT_EXPRS 32 /* local + extremum expressions + Z2 flux terms per element class */
 
 /* what one launch writes (the `flag` of jitbridge.h:285 routines) */
 #define PB2_FLAG_RESIDUAL 0u
@@ -119,6 +120,11 @@ typedef struct pb2_class_info
   /* integral expressions = numintegral_expressions / integral_expressions_names of jitbridge.h:417-418 */
   int n_integrals, pad_;
   char integral_names[PB2_MAX_INTEGRALS][48];
+  /* expressions evaluated at a local coordinate of every element (kind 4 kernels): numlocal_expressions / numextremum_expressions /
+   * num_Z2_flux_terms of jitbridge.h:420-424, :456 in one list; point_kind 0 local, 1 extremum, 2 Z2 flux */
+  int n_point_exprs, pad2_;
+  char point_names[PB2_MAX_POINT_EXPRS][48];
+  int point_kind[PB2_MAX_POINT_EXPRS];
 } pb2_class_info;
 
 /* launch configuration of one generated routine */
@@ -139,7 +145,9 @@ typedef struct pb2_kernel_cfg
  * TRANSPOSED contractions d(J^T.Y)/dU, d(M^T.Y)/dU (flags 4 / 5 of HessianVectorProduct, jitbridge.h:637-691; same flag values 1 / 2
  * here), 2: EvalIntegralExpression for ALL integral
  * expressions at once (jitbridge.h:469; one launch per call, args->elem_begin / n_elem select the elements, args->integrals
- * receives the per-element values; residual_index, param_index and flag are ignored). */
+ * receives the per-element values; residual_index, param_index and flag are ignored).  kind 4: EvalLocalExpression /
+ * EvalExtremumExpression / GetZ2Fluxes (jitbridge.h:470-471, :458) for ALL point expressions of the class at the points of one set --
+ * flag 0: the integration points, flag 1: the element's nodes -- args->integrals receives [element][point][expression]. */
 typedef int (*pb2_query_fn)(int kind, int residual_index, int param_index, unsigned flag, pb2_kernel_cfg *out);
 typedef int (*pb2_launch_fn)(const pb2_kernel_cfg *cfg, const pb2_kernel_args *args, int grid, void *cuda_stream);
 

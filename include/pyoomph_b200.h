@@ -121,6 +121,12 @@ int pb2_problem_hessian_vector_products(pb2_problem *p, int residual_index, cons
  * pb2_class_info.integral_names), n_out = number of expressions.  One launch for the per-element values, one fixed-order
  * reduction: the result is bit-reproducible. */
 int pb2_problem_eval_integrals(pb2_problem *p, double *out, int n_out);
+/* Expressions evaluated at a local coordinate of every element: replaces the per-point calls of functable->EvalLocalExpression,
+ * EvalExtremumExpression and GetZ2Fluxes (BulkElementBase::eval_local_expression_at_s / eval_extremum_expression_at_s / get_Z2_flux,
+ * src/elements.cpp:4666-4704, :7285-7305) behind Mesh output, Mesh::evaluate_extremum (src/mesh.cpp:444-500) and the Z2 error
+ * estimator.  point_set 0: the element's integration points, 1: its nodes.  out[element][point][expression] in the MESH's element
+ * order, expressions in the order of pb2_class_info.point_names; n_out = n_elem * points * expressions.  One launch. */
+int pb2_problem_eval_points(pb2_problem *p, int point_set, double *out, long long n_out);
 /* number of kernel launches issued by the last assemble, and cumulative */
 long long pb2_problem_launch_count(pb2_problem *p);
 

@@ -91,6 +91,7 @@ class OracleProblem:
         L.oracle_assemble.restype = ctypes.c_double
         L.oracle_nnz.restype = ctypes.c_int64
         L.oracle_eval_integral.restype = ctypes.c_double
+        L.oracle_eval_at_s.restype = ctypes.c_double
         L.oracle_integral_name.restype = ctypes.c_char_p
         L.oracle_element.restype = ctypes.c_int
         self.dim = mesh.dim
@@ -114,6 +115,35 @@ class OracleProblem:
         """{name: sum over elements of EvalIntegralExpression(index)} (Mesh::evaluate_integral_expression, src/mesh.cpp:536)"""
         n = self.lib.oracle_num_integrals(self.h)
         return {self.lib.oracle_integral_name(self.h, i).decode(): float(self.lib.oracle_eval_integral(self.h, i)) for i in range(n)}
+
+    def eval_point_expressions(self, points: str = "nodes") -> np.ndarray:
+        """every local expression, extremum expression and Z2 flux term (in that order, like the product's point_names) at the
+        integration points or the nodes of every element, one reference-style call per point: [n_elem, n_points, n_expressions]"""
+        dim = self.dim
+        nn = self.mesh.elem_nodes.shape[1]
+        if points == "nodes":
+            grid = (-1.0, 0.0, 1.0)
+            pts = [np.array([grid[(l // 3 ** d) % 3] for d in range(dim)]) for l in range(nn)]        # local_coordinate_of_node
+        else:
+            pts = []
+            for ipt in range(9 if dim == 2 else 27):
+                k, w = (ctypes.c_double * 3)(), ctypes.c_double()
+                self.lib.oracle_gauss(dim, ipt, k, ctypes.byref(w))
+                pts.append(np.array(list(k)[:dim]))
+        nl, nx, nz = (self.lib.oracle_num_point_exprs(self.h, k) for k in (0, 1, 2))
+        out = np.zeros((self.mesh.elem_nodes.shape[0], len(pts), nl + nx + nz))
+        zbuf = np.zeros(max(1, nz))
+        for e in range(out.shape[0]):
+            for ip, s in enumerate(pts):
+                s = np.ascontiguousarray(s, dtype=np.float64)
+                for i in range(nl):
+                    out[e, ip, i] = self.lib.oracle_eval_at_s(self.h, 0, i, e, _dp(s), None)
+                for i in range(nx):
+                    out[e, ip, nl + i] = self.lib.oracle_eval_at_s(self.h, 1, i, e, _dp(s), None)
+                if nz:
+                    self.lib.oracle_eval_at_s(self.h, 2, 0, e, _dp(s), _dp(zbuf))
+                    out[e, ip, nl + nx:] = zbuf[:nz]
+        return out
 
     def set_params(self, values):
         v = np.ascontiguousarray(values, dtype=np.float64)

@@ -911,6 +911,37 @@ double oracle_eval_integral(void *h, int index)
   return res;
 }
 
+/* expressions at a local coordinate of one element: BulkElementBase::eval_local_expression_at_s / eval_extremum_expression_at_s /
+ * get_Z2_flux (src/elements.cpp:4666-4704, :7285-7305): fill the shape buffer at s (weight 0: these carry no measure), prepare the
+ * time weights, call the generated routine.  kind 0 local (returns the value of expression `index`), 1 extremum, 2 Z2 fluxes (all
+ * flux terms into out[], returns their number). */
+int oracle_num_point_exprs(void *h, int kind)
+{
+  const JITFuncSpec_Table_FiniteElement_t *ft = ((Oracle *)h)->ft;
+  return kind == 0 ? (int)ft->numlocal_expressions : kind == 1 ? (int)ft->numextremum_expressions : (int)ft->num_Z2_flux_terms;
+}
+double oracle_eval_at_s(void *h, int kind, int index, int e, const double *s, double *out)
+{
+  Oracle *o = (Oracle *)h;
+  ThreadState *ts = ts_create(o);
+  TS = ts;
+  bind_element(ts, e);
+  fill_shape_info_at_s(ts, s, 0.0, 0u, NULL);
+  prepare_shape_buffer(ts);
+  double res = 0.0;
+  if (kind == 0 && o->ft->EvalLocalExpression) res = o->ft->EvalLocalExpression(&ts->ei, &ts->si, (unsigned)index);
+  else if (kind == 1 && o->ft->EvalExtremumExpression) res = o->ft->EvalExtremumExpression(&ts->ei, &ts->si, (unsigned)index);
+  else if (kind == 2 && o->ft->GetZ2Fluxes)
+  {
+    o->ft->GetZ2Fluxes(&ts->ei, &ts->si, out);
+    res = (double)o->ft->num_Z2_flux_terms;
+  }
+  else
+    res = NAN;
+  free(ts);
+  return res;
+}
+
 int64_t oracle_nnz(void *h, int m) { return ((Oracle *)h)->nnz[m]; }
 void oracle_get_csr(void *h, int m, int *row_start, int *col_index, double *value)
 {

@@ -274,10 +274,31 @@ class CEmitter:
     # ---- integral expressions ---------------------------------------------------------------------
     def integral_routine(self) -> str:
         """EvalIntegralExpression in the format of write_code_integral_or_local_expressions (src/codegen.cpp:4125-4364,
-        :4366-4368): time-derivative precalculation, Gauss loop with the shape callback, interpolation, then
-        ``switch(index)`` over the expressions; the integrands carry their own measure."""
+        integrate = true)"""
         code = self.code
-        exprs = [code.atomize(e) for e in code.integral_expressions.values()]
+        return self._expression_routine("EvalIntegralExpression", list(code.integral_expressions.keys()),
+                                        list(code.integral_expressions.values()), "IntegralExprs", integrate=True)
+
+    def point_routines(self) -> str:
+        """EvalLocalExpression / EvalExtremumExpression (the same writer with integrate = false: the host has filled the shape buffer
+        at the local coordinate it wants, src/codegen.cpp:4181-4186, src/elements.cpp:4666-4704) and GetZ2Fluxes
+        (write_code_get_z2_flux, src/codegen.cpp:4445-4530: all flux terms of the point into Z2Flux[])"""
+        code = self.code
+        out = []
+        if code.local_expressions:
+            out.append(self._expression_routine("EvalLocalExpression", list(code.local_expressions.keys()), list(code.local_expressions.values()),
+                                                "LocalExprs", integrate=False))
+        if code.extremum_expressions:
+            out.append(self._expression_routine("EvalExtremumExpression", list(code.extremum_expressions.keys()),
+                                                list(code.extremum_expressions.values()), "ExtremumExprs", integrate=False))
+        if code.Z2_fluxes:
+            out.append(self._expression_routine("GetZ2Fluxes", ["flux_%d" % i for i in range(len(code.Z2_fluxes))], list(code.Z2_fluxes),
+                                                "Z2Fluxes", integrate=False, z2=True))
+        return "\n".join(out)
+
+    def _expression_routine(self, funcname: str, enames: List[str], raw_exprs, reqname: str, integrate: bool, z2: bool = False) -> str:
+        code = self.code
+        exprs = [code.atomize(e) for e in raw_exprs]
         used = set()
         for e in exprs:
             used |= {s_ for s_ in e.free_symbols if s_ in code._atom_syms}
@@ -290,7 +311,10 @@ class CEmitter:
         pr = _CPrinter(names)
         o: List[str] = []
         w = o.append
-        w("static double EvalIntegralExpression(const JITElementInfo_t * eleminfo, const JITShapeInfo_t * shapeinfo, unsigned index)")
+        if z2:
+            w("static void %s(const JITElementInfo_t * eleminfo, const JITShapeInfo_t * shapeinfo, double * Z2Flux)" % funcname)
+        else:
+            w("static double %s(const JITElementInfo_t * eleminfo, const JITShapeInfo_t * shapeinfo, unsigned index)" % funcname)
         w("{")
         w("  const unsigned flag=0;")
         w("  const double * t=shapeinfo->t;")
@@ -323,10 +347,16 @@ class CEmitter:
             w("  }")
         w("  //END: Precalculate time derivatives of the necessary data")
         w("")
-        w("  double res=0.0;")
-        w("  for(unsigned ipt=0;ipt<shapeinfo->n_int_pt;ipt++)")
-        w("  {")
-        w("    my_func_table->fill_shape_buffer_for_point(ipt, &(my_func_table->shapes_required_IntegralExprs), 0);")
+        if integrate:
+            w("  double res=0.0;")
+            w("  for(unsigned ipt=0;ipt<shapeinfo->n_int_pt;ipt++)")
+            w("  {")
+            w("    my_func_table->fill_shape_buffer_for_point(ipt, &(my_func_table->shapes_required_%s), 0);" % reqname)
+        else:
+            if not z2:
+                w("  double res;")
+            w("  unsigned ipt=0; (void)ipt;")
+            w("  {")
         w("    const double dx = shapeinfo->int_pt_weight;")
         w("    const double dX = shapeinfo->int_pt_weight_Lagrangian;")
         w("    (void)dx; (void)dX;")
@@ -348,13 +378,20 @@ class CEmitter:
                 w("      this_%s+= %s * %s;" % (a.cname, nd, self._shape_str(a.field, a.deriv, "l_shape")))
             w("    }")
         w("    //END: Interpolate all required fields")
-        w("    switch (index)")
-        w("    {")
-        for i, (n, e) in enumerate(zip(code.integral_expressions.keys(), exprs)):
-            w("      case %d: res+= %s; break; // %s" % (i, pr.doprint(e), n))
-        w("    }")
+        if z2:
+            for i, (n, e) in enumerate(zip(enames, exprs)):
+                w("    Z2Flux[%d] = %s; // %s" % (i, pr.doprint(e), n))
+        else:
+            w("    switch (index)")
+            w("    {")
+            for i, (n, e) in enumerate(zip(enames, exprs)):
+                w("      case %d: res%s= %s; break; // %s" % (i, "+" if integrate else "", pr.doprint(e), n))
+            if not integrate:
+                w("      default: res=0.0;")
+            w("    }")
         w("  }")
-        w("  return res;")
+        if not z2:
+            w("  return res;")
         w("}")
         w("")
         return "\n".join(o)
@@ -571,6 +608,8 @@ class CEmitter:
             for i, rn in enumerate(resnames):
                 w(self.hessian_routine("HessianVectorProduct%d" % i, rn, i))
         nint = len(code.integral_expressions)
+        if code.point_expression_names():
+            w(self.point_routines())
         if nint:
             w(self.integral_routine())
         nC2 = len([f for f in code.nodal_fields() if f.space == "C2"])
@@ -632,6 +671,22 @@ class CEmitter:
             for i, n in enumerate(code.integral_expressions.keys()):
                 w(' SET_INTERNAL_FIELD_NAME(functable->integral_expressions_names,%d,"%s");' % (i, n))
             w(" functable->EvalIntegralExpression=&EvalIntegralExpression;")
+        # local / extremum expressions and Z2 fluxes (src/codegen.cpp:7008-7040, :6786-6796); names are not freed by this test plugin
+        if code.local_expressions:
+            w(" functable->numlocal_expressions=%d;" % len(code.local_expressions))
+            w(" functable->local_expressions_names=(char **)malloc(sizeof(char*)*functable->numlocal_expressions);")
+            for i, n in enumerate(code.local_expressions.keys()):
+                w(' SET_INTERNAL_FIELD_NAME(functable->local_expressions_names,%d,"%s");' % (i, n))
+            w(" functable->EvalLocalExpression=&EvalLocalExpression;")
+        if code.extremum_expressions:
+            w(" functable->numextremum_expressions=%d;" % len(code.extremum_expressions))
+            w(" functable->extremum_expressions_names=(char **)malloc(sizeof(char*)*functable->numextremum_expressions);")
+            for i, n in enumerate(code.extremum_expressions.keys()):
+                w(' SET_INTERNAL_FIELD_NAME(functable->extremum_expressions_names,%d,"%s");' % (i, n))
+            w(" functable->EvalExtremumExpression=&EvalExtremumExpression;")
+        if code.Z2_fluxes:
+            w(" functable->num_Z2_flux_terms = %d;" % len(code.Z2_fluxes))
+            w(" functable->GetZ2Fluxes=&GetZ2Fluxes;")
         w(" functable->clean_up=&clean_up;")
         w(" my_func_table=functable;")
         w("}")

@@ -82,6 +82,8 @@ typedef struct JITFuncSpec_RequiredShapes_FiniteElement
   bool psi_Pos, dx_psi_Pos, dX_psi_Pos;
 } JITFuncSpec_RequiredShapes_FiniteElement_t;
 
+typedef void (*JITFuncSpec_GetZ2Fluxes_FiniteElement)(const JITElementInfo_t *, const JITShapeInfo_t *, double *); /* jitbridge.h:287 */
+
 typedef struct JITFuncSpec_Table_FiniteElement
 {
   unsigned int nodal_dim, lagr_dim;
@@ -109,6 +111,14 @@ typedef struct JITFuncSpec_Table_FiniteElement
   char **integral_expressions_names;
   JITFuncSpec_EvalIntegralExpr_FiniteElement EvalIntegralExpression; /* jitbridge.h:469-470 */
   JITFuncSpec_RequiredShapes_FiniteElement_t shapes_required_IntegralExprs;
+  unsigned numlocal_expressions;                                   /* jitbridge.h:420-424 */
+  char **local_expressions_names;
+  unsigned numextremum_expressions;
+  char **extremum_expressions_names;
+  JITFuncSpec_EvalIntegralExpr_FiniteElement EvalLocalExpression;  /* jitbridge.h:471-473 */
+  JITFuncSpec_EvalIntegralExpr_FiniteElement EvalExtremumExpression;
+  unsigned num_Z2_flux_terms;                                      /* jitbridge.h:456-458 */
+  JITFuncSpec_GetZ2Fluxes_FiniteElement GetZ2Fluxes;
   char *domain_name;
   void (*check_compiler_size)(unsigned long long, unsigned long long, char *);
   void (*fill_shape_buffer_for_point)(unsigned, JITFuncSpec_RequiredShapes_FiniteElement_t *, int);

@@ -51,6 +51,7 @@ class ClassInfo(ctypes.Structure):
         ("alg_bytes_per_elem", ctypes.c_double * 3), ("flops_per_elem", ctypes.c_double * 3),
         ("alg_bytes_per_hist_level", ctypes.c_double),
         ("n_integrals", ctypes.c_int), ("pad_", ctypes.c_int), ("integral_names", (ctypes.c_char * 48) * 16),
+        ("n_point_exprs", ctypes.c_int), ("pad2_", ctypes.c_int), ("point_names", (ctypes.c_char * 48) * 32), ("point_kind", ctypes.c_int * 32),
     ]
 
 
@@ -81,7 +82,7 @@ def load_library() -> ctypes.CDLL:
                "pb2_problem_assemble_hessian", "pb2_problem_fetch_hessian", "pb2_problem_hessian_vector_products",
                "pb2_problem_pack_rows", "pb2_problem_unpack_add", "pb2_problem_eval_integrals", "pb2_problem_shift_time_values",
                "pb2_problem_set_history_dofs", "pb2_measure_fp64_peak", "pb2_problem_host_maps", "pb2_problem_device_pattern",
-               "pb2_problem_device_dofs", "pb2_problem_update_dofs_device"):
+               "pb2_problem_device_dofs", "pb2_problem_update_dofs_device", "pb2_problem_eval_points"):
         getattr(L, fn).restype = ctypes.c_int
     L.pb2_problem_setup_seconds.restype = ctypes.c_double
     _LIB = L
@@ -237,6 +238,8 @@ class B200Assembly(CustomAssemblyBase):
         self.param_names = [self.info.param_names[i].value.decode() for i in range(self.info.n_params)]
         self.residual_names = [self.info.residual_names[i].value.decode() for i in range(self.info.n_residuals)]
         self.integral_names = [self.info.integral_names[i].value.decode() for i in range(self.info.n_integrals)]
+        self.point_names = [(("local", "extremum", "z2")[self.info.point_kind[i]], self.info.point_names[i].value.decode())
+                            for i in range(self.info.n_point_exprs)]
         if not hasattr(self, "_params"):
             self._params = np.zeros(max(1, self.info.n_params))
         self._stale = False
@@ -421,6 +424,52 @@ class B200Assembly(CustomAssemblyBase):
         out = np.empty(len(self.integral_names))
         _check(self.lib.pb2_problem_eval_integrals(self.prob, self._dp(out), len(self.integral_names)))
         return {n: float(v) for n, v in zip(self.integral_names, out)}
+
+    # ---- expressions at local coordinates: local expressions, extremum expressions, Z2 fluxes (src/codegen.cpp:4366-4453) -------------
+    def evaluate_point_expressions(self, points: str = "nodes") -> np.ndarray:
+        """all point expressions of the class at the integration points ("gauss") or the nodes ("nodes") of every element:
+        array [n_elem, n_points, n_expressions] in the mesh's element order (expressions as in ``point_names``); one launch"""
+        if not self.point_names:
+            raise RuntimeError("this element class defines no local / extremum expressions or Z2 fluxes")
+        self._fresh()
+        ps = {"gauss": 0, "nodes": 1}[points]
+        npts = int(self.info.n_int_pt if ps == 0 else self.info.nnode)
+        out = np.empty((self.n_elem, npts, len(self.point_names)))
+        _check(self.lib.pb2_problem_eval_points(self.prob, ps, self._dp(out), ctypes.c_longlong(out.size)))
+        return out
+
+    def evaluate_local_expressions_at_nodes(self) -> Dict[str, np.ndarray]:
+        """BulkElementBase::eval_local_expression_at_node for every element and node (Mesh output): {name: [n_elem, nnode]}"""
+        vals = self.evaluate_point_expressions("nodes")
+        return {n: vals[:, :, i].copy() for i, (k, n) in enumerate(self.point_names) if k == "local"}
+
+    def get_Z2_fluxes(self, points: str = "gauss") -> np.ndarray:
+        """GetZ2Fluxes at the integration points (or nodes) of every element: [n_elem, n_points, num_Z2_flux_terms]"""
+        vals = self.evaluate_point_expressions(points)
+        idx = [i for i, (k, _) in enumerate(self.point_names) if k == "z2"]
+        return vals[:, :, idx].copy()
+
+    def evaluate_extremum(self, name: str, sign: int = 1):
+        """Mesh::evaluate_extremum (src/mesh.cpp:444-500) without its final Newton refinement: the largest value of sign * expression
+        over the integration points and the nodes of all elements, scanned in the reference's order (elements in mesh order, per element
+        first the integration points, then the nodes; a later sample wins only if strictly larger).  Returns (value, element,
+        ("gauss" | "nodes", point index))."""
+        names = [n for k, n in self.point_names]
+        kinds = [k for k, n in self.point_names]
+        if name not in names or kinds[names.index(name)] != "extremum":
+            raise RuntimeError("Extremum function " + name + " not defined on this mesh")
+        i = names.index(name)
+        g = sign * self.evaluate_point_expressions("gauss")[:, :, i]
+        nd = sign * self.evaluate_point_expressions("nodes")[:, :, i]
+        samples = np.concatenate([g, nd], axis=1)                       # per element: integration points, then nodes
+        start = nd[0, 0]                                                  # the reference starts from node 0 of element 0
+        flat = samples.ravel()
+        k = int(np.argmax(flat))                                          # first occurrence of the maximum = the reference's strict ">" scan
+        if flat[k] > start:
+            e, q = divmod(k, samples.shape[1])
+            where = ("gauss", q) if q < g.shape[1] else ("nodes", q - g.shape[1])
+            return float(sign * flat[k]), e, where
+        return float(sign * start), 0, ("nodes", 0)
 
     def evaluate_observable(self, name: str) -> float:
         return self.evaluate_integral_expressions()[name]

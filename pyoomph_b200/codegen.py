@@ -127,6 +127,11 @@ class FiniteElementCode:
         self._param_syms: Dict[str, sp.Symbol] = {}
         self.residuals: Dict[str, sp.Expr] = {}
         self.integral_expressions: Dict[str, sp.Expr] = {}     # FiniteElementCode::integral_expressions (src/codegen.hpp:677)
+        # expressions evaluated at a local coordinate of an element (no measure): local expressions (output at the nodes), extremum
+        # expressions (sampled at Gauss points and nodes), Z2 flux terms of the error estimator (src/codegen.cpp:4125-4453)
+        self.local_expressions: Dict[str, sp.Expr] = {}
+        self.extremum_expressions: Dict[str, sp.Expr] = {}
+        self.Z2_fluxes: List[sp.Expr] = []
         self._atom_syms: Dict[sp.Symbol, AtomInfo] = {}
         self._atom_by_info: Dict[AtomInfo, sp.Symbol] = {}
         self._test_syms: Dict[sp.Symbol, TestSlot] = {}
@@ -215,6 +220,64 @@ class FiniteElementCode:
     def integral_expression_names(self) -> List[str]:
         return list(self.integral_expressions.keys())
 
+    # -- local / extremum expressions and Z2 fluxes (src/codegen.cpp:4366-4453; pyoomph/generic/codegen.py:1213, :2126) -----------------
+    def _register_components(self, dest: Dict[str, sp.Expr], name: str, expr):
+        if isinstance(expr, sp.MatrixBase):
+            if expr.shape[1] == 1:
+                for i in range(expr.shape[0]):
+                    if expr[i, 0] != 0 or i < self.nodal_dim:
+                        dest[name + "_" + (ex.DIRS[i] if i < self.nodal_dim else "phi")] = sp.sympify(expr[i, 0])
+            else:
+                for i in range(self.nodal_dim):
+                    for j in range(self.nodal_dim):
+                        dest["%s_%s%s" % (name, ex.DIRS[i], ex.DIRS[j])] = sp.sympify(expr[i, j])
+            return
+        dest[name] = sp.sympify(expr)
+
+    def add_local_function(self, name: str, expr):
+        """node-wise output quantity (Equations.add_local_function, pyoomph/generic/codegen.py:1213): vectors / tensors register one
+        expression per component"""
+        self._register_components(self.local_expressions, name, expr() if callable(expr) else expr)
+
+    def add_extremum_function(self, name: str, expr):
+        self._register_components(self.extremum_expressions, name, expr() if callable(expr) else expr)
+
+    def add_Z2_flux(self, expr):
+        """flux terms of the Z2 error estimator (Equations.add_spatial_error_estimator -> _add_Z2_flux): every component of a
+        scalar / vector / tensor expression is one flux term"""
+        expr = expr() if callable(expr) else expr
+        if isinstance(expr, sp.MatrixBase):
+            self.Z2_fluxes += [sp.sympify(v) for v in expr]
+        else:
+            self.Z2_fluxes.append(sp.sympify(expr))
+
+    def point_expression_names(self) -> List[Tuple[str, str]]:
+        """(kind, name) of every expression of the point-evaluation routine, in its output order: local, extremum, Z2"""
+        return [("local", n) for n in self.local_expressions] + [("extremum", n) for n in self.extremum_expressions] + \
+               [("z2", "flux_%d" % i) for i in range(len(self.Z2_fluxes))]
+
+    def point_form(self) -> ResidualForm:
+        """EvalLocalExpression, EvalExtremumExpression and GetZ2Fluxes as ONE coefficient form without test functions and without
+        measure: slot i carries expression i of point_expression_names()"""
+        if "|points" in self._forms:
+            return self._forms["|points"]
+        exprs = list(self.local_expressions.values()) + list(self.extremum_expressions.values()) + list(self.Z2_fluxes)
+        slots, R = [], []
+        for i, e in enumerate(exprs):
+            E = self.atomize(e)
+            if any(s_ in self._test_syms for s_ in E.free_symbols):
+                raise RuntimeError("Found test function in a custom integral/local expression")     # src/codegen.cpp:4145
+            slots.append(TestSlot("__point_%d" % i, "d0"))
+            R.append(E)
+        used = set()
+        for e in R:
+            used |= {s_ for s_ in e.free_symbols if s_ in self._atom_syms}
+        atoms = sorted((self._atom_syms[s_] for s_ in used), key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
+        allsyms = set().union(*[e.free_symbols for e in R]) if R else set()
+        form = ResidualForm("|points", slots, R, {}, {}, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=ex.DX_LAG in allsyms)
+        self._forms["|points"] = form
+        return form
+
     def integral_form(self) -> ResidualForm:
         """The integral expressions as a coefficient form without test functions: slot i carries integrand i (its "R"), so the
         emitters reuse their gather / geometry / interpolation code (write_code_integral_or_local_expressions,
@@ -238,7 +301,8 @@ class FiniteElementCode:
         return form
 
     def _all_forms(self) -> List[ResidualForm]:
-        return [self.derive(n) for n in self.residual_names()] + ([self.integral_form()] if self.integral_expressions else [])
+        return [self.derive(n) for n in self.residual_names()] + ([self.integral_form()] if self.integral_expressions else []) + \
+               ([self.point_form()] if self.point_expression_names() else [])
 
     def space_nodes(self, space: str) -> Tuple[int, ...]:
         """Element-local node numbers of a space (src/elements.cpp:2870-2879)."""
@@ -591,6 +655,17 @@ class Equations:
     def add_integral_function(self, name: str, expr):
         """pyoomph/generic/codegen.py:1251: the integrand carries its own measure (multiply by ``self.get_dx()``)"""
         self._code.add_integral_function(name, expr)
+
+    def add_local_function(self, name: str, expr):
+        """pyoomph/generic/codegen.py:1213: quantity evaluated node-wise on output"""
+        self._code.add_local_function(name, expr)
+
+    def add_extremum_function(self, name: str, expr):
+        self._code.add_extremum_function(name, expr)
+
+    def add_spatial_error_estimator(self, expr):
+        """pyoomph/generic/codegen.py:2126: flux terms of the Z2 error estimator"""
+        self._code.add_Z2_flux(expr)
 
     def get_dx(self, lagrangian: bool = False, coordsys=None):
         """measure of the element's (or the given) coordinate system: dx, or 2 pi r dx when axisymmetric"""

@@ -1354,6 +1354,48 @@ extern "C" int pb2_problem_eval_integrals(pb2_problem *p, double *out, int n_out
   return 0;
 }
 
+// ---- point expressions: EvalLocalExpression / EvalExtremumExpression / GetZ2Fluxes of every element at one point set
+extern "C" int pb2_problem_eval_points(pb2_problem *p, int point_set, double *out, long long n_out)
+{
+  NEED_DEVICE(p);
+  const pb2_class_info &ci = p->cls->table.info;
+  if (ci.n_point_exprs < 1) return fail("this element class defines no local / extremum expressions or Z2 fluxes");
+  if (point_set != 0 && point_set != 1) return fail("point set must be 0 (integration points) or 1 (nodes)");
+  const int npts = point_set == 0 ? ci.n_int_pt : ci.nnode;
+  const long long per_elem = (long long)npts * ci.n_point_exprs, total = p->n_elem * per_elem;
+  if (n_out != total) return fail("n_out must be n_elem * points * expressions");
+  if (check_status(p)) return 1;
+  pb2_kernel_cfg cfg;
+  int rc = p->cls->table.query(4, 0, -1, (unsigned)point_set, &cfg);
+  if (rc != 0) return fail("plugin has no point-expression kernel (rc " + std::to_string(rc) + ")");
+  p->launches_last = 0;
+  if (p->n_elem == 0) return 0;
+  double *d_buf = nullptr;
+  CUDA_OK(cudaMalloc((void **)&d_buf, (size_t)total * sizeof(double)));
+  pb2_kernel_args a;
+  fill_common_args(p, a);
+  a.elem_begin = 0;
+  a.n_elem = (int)p->n_elem;
+  a.integrals = d_buf;
+  const long long nbatch = (p->n_elem + cfg.elems_per_batch - 1) / cfg.elems_per_batch;
+  rc = p->cls->table.launch(&cfg, &a, (int)std::min<long long>(nbatch, (long long)p->n_sms * std::max(1, cfg.blocks_per_sm)), nullptr);
+  if (rc != 0)
+  {
+    cudaFree(d_buf);
+    return fail("point-expression kernel launch failed (plugin rc " + std::to_string(rc) + (rc >= 100 ? std::string(": ") + cudaGetErrorString((cudaError_t)(rc - 100)) : "") + ")");
+  }
+  p->launches_last++;
+  p->launches_total++;
+  std::vector<double> tmp((size_t)total);
+  const cudaError_t e = cudaMemcpy(tmp.data(), d_buf, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_buf);
+  if (e != cudaSuccess) return fail(std::string("cudaMemcpy: ") + cudaGetErrorString(e));
+  // the kernel works in schedule order: hand the values back in the mesh's element order
+#pragma omp parallel for schedule(static)
+  for (long long q = 0; q < p->n_elem; q++) memcpy(out + (size_t)p->perm[q] * per_elem, tmp.data() + (size_t)q * per_elem, (size_t)per_elem * sizeof(double));
+  return 0;
+}
+
 extern "C" int pb2_problem_device_outputs(pb2_problem *p, double **residual, double **jac_vals, double **mass_vals)
 {
   if (residual) *residual = p->d_residual;

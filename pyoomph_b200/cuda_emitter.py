@@ -343,6 +343,21 @@ class CudaEmitter:
             [v for p in psi2 for v in p] + [v for p in dpsi2 for l in p for v in l] + [v for p in psi1 for v in p] + [v for p in dpsi1 for l in p for v in l] + t1_smem)))
         if self.dim == 3:
             o.append("__constant__ double c_t1d[%d] = {%s};" % (len(t1), arr(t1)))
+        if self.code.point_expression_names():
+            # the same tables at the element's NODES (local coordinates -1, 0, 1 per direction, oomph node order): point expressions are
+            # evaluated at the integration points or at the nodes (eval_local_expression_at_node, src/elements.cpp:4659)
+            grid = (-1.0, 0.0, 1.0)
+            nk = [tuple(grid[(l // 3 ** d) % 3] for d in range(self.dim)) for l in range(self.NN)]
+            npsi2, ndpsi2 = shape_tables(self.dim, 3, nk)
+            npsi1, ndpsi1 = shape_tables(self.dim, 2, nk)
+            nt1 = []
+            if self.dim == 3:
+                for sk in nk:
+                    for d in range(3):
+                        P, D = _lag(3, sk[d])
+                        nt1 += list(P) + list(D)
+            o.append("__device__ const double g_tables_nodes[%d] = {%s};" % (self.NN * (self.NN * (1 + self.dim) + self.NN1 * (1 + self.dim)) + len(nt1), arr(
+                [v for p in npsi2 for v in p] + [v for p in ndpsi2 for l in p for v in l] + [v for p in npsi1 for v in p] + [v for p in ndpsi1 for l in p for v in l] + nt1)))
         o.append("__constant__ int c_c1node[%d] = {%s};" % (self.NN1, ", ".join(str(n) for n in self.et.c1_nodes)))
         # row dof index of (field, space-local node)
         for f in self.code.unknown_field_names():
@@ -554,6 +569,64 @@ class CudaEmitter:
         w("      double s = 0.0;")
         w("      for (int ipt = 0; ipt < %d; ++ipt) s += P[ipt * %d];" % (NIPT, PB))
         w("      a.integrals[(long long)(a.elem_begin + e0 + el) * %d + k] = s;" % NI)
+        w("    }")
+        w("  }")
+        w("}")
+        w("")
+        return kname
+
+    def _emit_point_kernel(self, o: List[str], at_nodes: bool) -> str:
+        """EvalLocalExpression / EvalExtremumExpression / GetZ2Fluxes for all point expressions of the class (src/codegen.cpp:4366-4453)
+        at one point set: gather, then one thread per (element, point) for geometry + interpolation + the expressions, written to
+        integrals[element][point][expression].  The point set only changes the reference-element tables."""
+        form = self.code.point_form()
+        rp = RoutinePlan("points", form, 0, -1)
+        plan = self._plan_smem(form, 0)
+        ELS, EL0, PB = plan["ELS"], plan["EL0"], plan["PB"]
+        NE, NN, NN1, dim = len(form.slots), self.NN, self.NN1, self.dim
+        NPT = NN if at_nodes else self.NIPT
+        if at_nodes and NN != self.NIPT:
+            raise RuntimeError("node tables need as many nodes as integration points in this layout")
+        tab_n = self._tables_smem_size()
+        NT = 256
+        EPB = max(2, min(NT // NPT if NPT <= NT else 2, (self.smem_budget - tab_n * 8) // (ELS * 8)))
+        kname = "pb2_%s_points_%s" % (self.name, "n" if at_nodes else "g")
+        self._kernel_smem[kname] = (tab_n + EPB * ELS) * 8
+        self._kernel_cfg[kname] = (EPB, NT, self._kernel_smem[kname])
+        w = o.append
+        w("// point expressions at the %s: %s" % ("nodes" if at_nodes else "integration points", ", ".join(n for _, n in self.code.point_expression_names())))
+        w("extern \"C\" __global__ void __launch_bounds__(%d) %s(const pb2_kernel_args a)" % (NT, kname))
+        w("{")
+        w("  extern __shared__ double smem[];")
+        w("  double* const s_psi2 = smem;")
+        w("  double* const s_dpsi2 = s_psi2 + %d;" % (NPT * NN))
+        w("  double* const s_psi1 = s_dpsi2 + %d;" % (NPT * NN * dim))
+        w("  double* const s_dpsi1 = s_psi1 + %d;" % (NPT * NN1))
+        w("  const double* const s_t1d = s_dpsi1 + %d; (void)s_t1d;" % (NPT * NN1 * dim))
+        w("  double* const s_el = smem + %d;" % tab_n)
+        w("  const int tid = threadIdx.x;")
+        w("  for (int i = tid; i < %d; i += %d) smem[i] = %s[i];" % (tab_n, NT, "g_tables_nodes" if at_nodes else "g_tables"))
+        w("  const int nbatch = (a.n_elem + %d - 1) / %d;" % (EPB, EPB))
+        w("  for (int batch = blockIdx.x; batch < nbatch; batch += gridDim.x)")
+        w("  {")
+        w("    const int e0 = batch * %d;" % EPB)
+        w("    const int nel = min(%d, a.n_elem - e0);" % EPB)
+        w("    __syncthreads();")
+        saved = self.NT
+        self.NT = NT
+        try:
+            self._emit_gather_sync(o, plan, ELS)
+        finally:
+            self.NT = saved
+        w("    __syncthreads();")
+        w("    for (int i = tid; i < nel * %d; i += %d)" % (NPT, NT))
+        w("    {")
+        w("      const int el = i / %d, ipt = i - el * %d;" % (NPT, NPT))
+        w("      double* E = s_el + el * %d;" % ELS)
+        w("      double* P = E + %d + ipt * %d;" % (EL0, PB))
+        self._emit_phase1_body(o, rp, plan, 0)
+        w("      double* const out = a.integrals + ((long long)(a.elem_begin + e0 + el) * %d + ipt) * %d;" % (NPT, NE))
+        w("      for (int k = 0; k < %d; ++k) out[k] = P[%d + k];" % (NE, plan["R_off"]))
         w("    }")
         w("  }")
         w("}")
@@ -1710,15 +1783,20 @@ class CudaEmitter:
                 for what in (1, 2):
                     kernels[(rp.key, what)] = self._emit_kernel_pipe(o, rp, what)
         integral_kernel = self._emit_integral_kernel(o) if self.code.integral_expressions else None
+        point_kernels = [self._emit_point_kernel(o, False), self._emit_point_kernel(o, True)] if self.code.point_expression_names() else []
         # host side: launchers + table
         w("static int pb2_query(int kind, int residual_index, int param_index, unsigned flag, pb2_kernel_cfg* out)")
         w("{")
         w("  memset(out, 0, sizeof(*out));")
-        w("  if (kind < 0 || kind > 3 || flag > 2u) return 1;")
+        w("  if (kind < 0 || kind > 4 || flag > 2u) return 1;")
         if integral_kernel:
             w("  if (kind == 2) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
                 integral_kernel, self._kernel_smem[integral_kernel], self._kernel_cfg[integral_kernel][0], self._kernel_cfg[integral_kernel][1]))
         w("  if (kind == 2 && !out->func) return 2;")
+        for fl, kn in enumerate(point_kernels):
+            w("  if (kind == 4 && flag == %du) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
+                fl, kn, self._kernel_smem[kn], self._kernel_cfg[kn][0], self._kernel_cfg[kn][1]))
+        w("  if (kind == 4 && !out->func) return 2;")
         if self.hessian and self.pipeline:
             for rp in self.hroutines:
                 for what in (1, 2):
@@ -1731,7 +1809,7 @@ class CudaEmitter:
                 w("  if (kind == 0 && residual_index == %d && param_index == %d && flag == %du) { out->func = (const void*)%s; out->smem_bytes = %d; out->elems_per_batch = %d; out->threads = %d; }" % (
                     rp.res_index, rp.param_index, what, kn, self._kernel_smem[kn], self._kernel_cfg[kn][0], self._kernel_cfg[kn][1]))
         w("  if (!out->func) return 2;")
-        w("  out->pipelined = kind == 2 ? 0 : %d;   // kinds 0, 1, 3 are persistent pipelined kernels" % (1 if self.pipeline else 0))
+        w("  out->pipelined = (kind == 2 || kind == 4) ? 0 : %d;   // kinds 0, 1, 3 are persistent pipelined kernels" % (1 if self.pipeline else 0))
         w("  cudaError_t err = cudaFuncSetAttribute(out->func, cudaFuncAttributeMaxDynamicSharedMemorySize, out->smem_bytes);")
         w("  if (err != cudaSuccess) return 100 + (int)err;")
         w("  int per_sm = 0;")
@@ -1800,6 +1878,12 @@ class CudaEmitter:
         w("  ci->n_integrals = %d;" % len(inames))
         for i, n in enumerate(inames):
             w("  strncpy(ci->integral_names[%d], \"%s\", 47);" % (i, n))
+        pnames = code.point_expression_names()
+        if len(pnames) > 32:
+            raise RuntimeError("more than PB2_MAX_POINT_EXPRS point expressions")
+        w("  ci->n_point_exprs = %d;" % len(pnames))
+        for i, (kind_, n) in enumerate(pnames):
+            w("  strncpy(ci->point_names[%d], \"%s\", 47); ci->point_kind[%d] = %d;" % (i, n, i, {"local": 0, "extremum": 1, "z2": 2}[kind_]))
         w("  table->query = &pb2_query;")
         w("  table->launch = &pb2_launch;")
         w("}")

@@ -145,3 +145,40 @@ class IntegralObservables(Equations):
         for k, v in self.integral_observables.items():
             v = v() if callable(v) else v
             self.add_integral_function(k, v * dx)
+
+
+class LocalExpressions(Equations):
+    """``LocalExpressions(vorticity=lambda: ..., speed=...)`` (pyoomph/equations/generic.py): quantities evaluated node-wise on output,
+    registered with ``add_local_function``."""
+
+    def __init__(self, **local_expressions):
+        super().__init__()
+        self.local_expressions = dict(local_expressions)
+
+    def define_additional_functions(self):
+        for k, v in self.local_expressions.items():
+            self.add_local_function(k, v() if callable(v) else v)
+
+
+class ExtremumObservables(Equations):
+    """named expressions whose extremum over the mesh is sought (Mesh::evaluate_extremum, src/mesh.cpp:444)"""
+
+    def __init__(self, **extremum_observables):
+        super().__init__()
+        self.extremum_observables = dict(extremum_observables)
+
+    def define_additional_functions(self):
+        for k, v in self.extremum_observables.items():
+            self.add_extremum_function(k, v() if callable(v) else v)
+
+
+class SpatialErrorEstimator(Equations):
+    """``SpatialErrorEstimator(grad(var("u")))``: flux terms of the Z2 error estimator (pyoomph/generic/codegen.py:2126)"""
+
+    def __init__(self, *fluxes):
+        super().__init__()
+        self.fluxes = list(fluxes)
+
+    def define_additional_functions(self):
+        for f in self.fluxes:
+            self.add_spatial_error_estimator(f() if callable(f) else f)

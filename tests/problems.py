@@ -154,6 +154,29 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
             pinned = {"velocity_x": wall, "velocity_y": wall}
         unsteady = True
+    elif kind in ("ns_pts", "heat3d_pts", "ale_axi_pts"):
+        # local expressions (node-wise output), extremum expressions and Z2 error-estimator fluxes next to the equations
+        from pyoomph_b200.equations import ExtremumObservables, LocalExpressions, SpatialErrorEstimator
+        from pyoomph_b200.expressions import dot, grad, partial_t, var
+        if kind == "heat3d_pts":
+            mesh = CuboidBrickMesh(N)
+            extra = LocalExpressions(flux=lambda: -grad(var("u")), heating=lambda: partial_t(var("u"))) + \
+                ExtremumObservables(hottest=lambda: var("u")) + SpatialErrorEstimator(lambda: grad(var("u")))
+            code = FiniteElementCode("Brick3dC2", TransientHeatEquation() + extra, name="heat3dpts")
+            pinned = {"u": mesh.boundaries["left"]}
+        else:
+            mesh = RectangularQuadMesh(N)
+            extra = LocalExpressions(speed2=lambda: dot(var("velocity"), var("velocity")), p=lambda: var("pressure"),
+                                     vorticity=lambda: grad(var("velocity_y"))[0] - grad(var("velocity_x"))[1], strain=lambda: grad(var("velocity"))) + \
+                ExtremumObservables(pmax=lambda: var("pressure"), speed2=lambda: dot(var("velocity"), var("velocity"))) + \
+                SpatialErrorEstimator(lambda: grad(var("velocity")))
+            eqs = NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + extra
+            if kind == "ale_axi_pts":
+                eqs = eqs + PseudoElasticMesh()
+            code = FiniteElementCode("Quad2dC2", eqs, name=kind.replace("_", ""), coordinate_system="axisymmetric" if "axi" in kind else "cartesian")
+            wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
+            pinned = {"velocity_x": wall, "velocity_y": wall}
+        unsteady = True
     elif kind == "ale_axi":        # config 4 bulk part as BASELINE names it: axisymmetric NS-TH on a pseudo-elastic moving mesh
         mesh = RectangularQuadMesh(N)
         code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + PseudoElasticMesh(),

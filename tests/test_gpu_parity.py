@@ -497,3 +497,50 @@ def test_newton_iteration_with_a_device_resident_solver():
     with pytest.raises(RuntimeError):
         GenericLinearSystemSolver.register_solver()(type("Dup", (GenericLinearSystemSolver,), {"idname": "torch_krylov"}))
     asm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N,distortion,unstructured", [("ns_pts", 7, 0.1, False), ("heat3d_pts", 3, 0.1, True), ("ale_axi_pts", 5, 0.08, True), ("ns_pts", 60, 0.0, False)])
+def test_point_expressions_parity(kind, N, distortion, unstructured):
+    """EvalLocalExpression / EvalExtremumExpression / GetZ2Fluxes (src/codegen.cpp:4366-4453) for every element at its nodes and at its
+    integration points: one launch per point set against one reference-style call per (element, point, expression) of the oracle;
+    Mesh::evaluate_extremum's scan (src/mesh.cpp:444-500) on top of it."""
+    pb = make_problem(kind, N, distortion=distortion, unstructured=unstructured)
+    asm = make_gpu(pb)
+    op = make_oracle(pb)
+    names = asm.point_names
+    assert names == pb["code"].point_expression_names()
+    small = pb["mesh"].n_elem <= 200
+    for pts in ("nodes", "gauss"):
+        got = asm.evaluate_point_expressions(pts)
+        assert asm.launch_count() == 1
+        if small:
+            ref = op.eval_point_expressions(pts)
+            assert got.shape == ref.shape
+            for i in range(len(names)):
+                scale = max(np.abs(ref[:, :, i]).max(), 1e-300)
+                assert np.abs(got[:, :, i] - ref[:, :, i]).max() <= TOL * scale, (pts, names[i])
+        again = asm.evaluate_point_expressions(pts)
+        assert np.array_equal(got, again)
+    loc = asm.evaluate_local_expressions_at_nodes()
+    assert list(loc) == [n for k, n in names if k == "local"] and all(v.shape == (pb["mesh"].n_elem, pb["mesh"].elem_nodes.shape[1]) for v in loc.values())
+    z2 = asm.get_Z2_fluxes()
+    assert z2.shape[2] == sum(1 for k, _ in names if k == "z2")
+    # extremum: the reference's sampling (integration points, then nodes, element by element, strict ">") on the GPU values
+    xname = [n for k, n in names if k == "extremum"][0]
+    xi = [i for i, (k, n) in enumerate(names) if k == "extremum"][0]
+    for sign in (1, -1):
+        val, elem, where = asm.evaluate_extremum(xname, sign)
+        g, nd = asm.evaluate_point_expressions("gauss")[:, :, xi], asm.evaluate_point_expressions("nodes")[:, :, xi]
+        best, be, bw = sign * nd[0, 0], 0, ("nodes", 0)
+        for e in range(g.shape[0]):
+            for q in range(g.shape[1]):
+                if sign * g[e, q] > best:
+                    best, be, bw = sign * g[e, q], e, ("gauss", q)
+            for q in range(nd.shape[1]):
+                if sign * nd[e, q] > best:
+                    best, be, bw = sign * nd[e, q], e, ("nodes", q)
+        assert (val, elem, where) == (sign * best, be, bw)
+    with pytest.raises(RuntimeError):
+        asm.evaluate_extremum("no_such_expression")
+    op.close(); asm.close()

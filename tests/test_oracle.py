@@ -358,3 +358,28 @@ def test_hessian_flags_of_the_oracle_are_consistent(kind):
     P0, _ = op.element_hessian(e, Y[:1], C, flag=0)
     assert np.abs(P0 - np.einsum("j,ijk,vk->vi", Yl[0], H, C[:, eq])).max() <= 1e-13 * np.abs(P0).max()
     op.close()
+
+
+def test_point_expressions_of_the_oracle_linear_fields():
+    """EvalLocalExpression / GetZ2Fluxes of the oracle on a distorted mesh: for linear velocity fields the vorticity, the strain
+    components and the Z2 fluxes (the velocity gradient) are the analytic constants at every node and integration point; the
+    extremum expression of the pressure equals the interpolated pressure."""
+    from problems import make_oracle, make_problem
+    pb = make_problem("ns_pts", 3, distortion=0.12)
+    m = pb["mesh"]
+    pb["vals"][0][:, 0] = 2 + 3 * m.node_pos[:, 0] - m.node_pos[:, 1]
+    pb["vals"][0][:, 1] = -1 + 0.5 * m.node_pos[:, 0] + 4 * m.node_pos[:, 1]
+    op = make_oracle(pb)
+    names = [n for k, n in pb["code"].point_expression_names()]
+    for pts in ("nodes", "gauss"):
+        v = op.eval_point_expressions(pts)
+        for nm, expect in (("vorticity", 1.5), ("strain_xx", 3.0), ("strain_xy", -1.0), ("strain_yx", 0.5), ("strain_yy", 4.0)):
+            assert np.abs(v[:, :, names.index(nm)] - expect).max() <= 1e-11
+        z = v[:, :, [i for i, n in enumerate(names) if n.startswith("flux_")]]
+        assert np.abs(z - np.array([3.0, -1.0, 0.5, 4.0])).max() <= 1e-11
+    vn = op.eval_point_expressions("nodes")
+    ip = names.index("p")
+    en = m.elem_nodes
+    vert = [0, 2, 6, 8]
+    assert np.abs(vn[:, vert, ip] - pb["vals"][0][en[:, vert], 2]).max() <= 1e-13       # C1 field at the vertex nodes: the nodal values
+    op.close()
