@@ -88,6 +88,7 @@ class OracleProblem:
         self.lib = ctypes.CDLL(so)
         L = self.lib
         L.oracle_create.restype = ctypes.c_void_p
+        L.oracle_create_typed.restype = ctypes.c_void_p
         L.oracle_assemble.restype = ctypes.c_double
         L.oracle_nnz.restype = ctypes.c_int64
         L.oracle_eval_integral.restype = ctypes.c_double
@@ -106,7 +107,7 @@ class OracleProblem:
         self.node_eqn = np.ascontiguousarray(dofmap.node_eqn, dtype=np.int32)
         self.pos_eqn = None if dofmap.pos_eqn is None else np.ascontiguousarray(dofmap.pos_eqn, dtype=np.int32)
         self.n_dof = dofmap.n_dof
-        self.h = ctypes.c_void_p(L.oracle_create(self.dim, mesh.n_elem, _ip(self.elem_nodes), mesh.n_node,
+        self.h = ctypes.c_void_p(L.oracle_create_typed(self.dim, int(mesh.elem_nodes.shape[1]), mesh.n_elem, _ip(self.elem_nodes), mesh.n_node,
                                                  node_val.shape[2], self.T, pos.shape[0], _dp(pos), _dp(lagr),
                                                  _dp(node_val), _ip(self.node_eqn), _ip(self.pos_eqn), self.n_dof))
         self.maxdof = mesh.elem_nodes.shape[1] * (self.dim + node_val.shape[2])
@@ -121,14 +122,21 @@ class OracleProblem:
         integration points or the nodes of every element, one reference-style call per point: [n_elem, n_points, n_expressions]"""
         dim = self.dim
         nn = self.mesh.elem_nodes.shape[1]
+        tri = dim == 2 and nn == 6
         if points == "nodes":
             grid = (-1.0, 0.0, 1.0)
-            pts = [np.array([grid[(l // 3 ** d) % 3] for d in range(dim)]) for l in range(nn)]        # local_coordinate_of_node
+            if tri:
+                pts = [np.array(c) for c in ((1.0, 0.0), (0.0, 1.0), (0.0, 0.0), (0.5, 0.5), (0.0, 0.5), (0.5, 0.0))]   # Telements.h:575-621
+            else:
+                pts = [np.array([grid[(l // 3 ** d) % 3] for d in range(dim)]) for l in range(nn)]    # local_coordinate_of_node
         else:
             pts = []
-            for ipt in range(9 if dim == 2 else 27):
+            for ipt in range(7 if tri else (9 if dim == 2 else 27)):
                 k, w = (ctypes.c_double * 3)(), ctypes.c_double()
-                self.lib.oracle_gauss(dim, ipt, k, ctypes.byref(w))
+                if tri:
+                    self.lib.oracle_gauss_tri(ipt, k, ctypes.byref(w))
+                else:
+                    self.lib.oracle_gauss(dim, ipt, k, ctypes.byref(w))
                 pts.append(np.array(list(k)[:dim]))
         nl, nx, nz = (self.lib.oracle_num_point_exprs(self.h, k) for k in (0, 1, 2))
         out = np.zeros((self.mesh.elem_nodes.shape[0], len(pts), nl + nx + nz))

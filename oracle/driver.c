@@ -107,6 +107,54 @@ void oracle_dshape_local(int dim, int order, const double *s, double *psi, doubl
   }
 }
 
+/* ------------------------------------------------------------------ triangles: TElement<2,3> / TElement<2,2> and TGauss<2,3>
+ * (oomph-lib Telements.h:519-545, :627-664; integral.cc:355-369), literal tables and the same operation order */
+static const double TGauss23_knot[7][2] = {{0.1012865073235, 0.1012865073235}, {0.7974269853531, 0.1012865073235}, {0.1012865073235, 0.7974269853531},
+                                           {0.4701420641051, 0.0597158717898}, {0.4701420641051, 0.4701420641051}, {0.0597158717898, 0.4701420641051},
+                                           {0.3333333333333, 0.3333333333333}};
+static const double TGauss23_weight[7] = {0.5 * 0.1259391805448, 0.5 * 0.1259391805448, 0.5 * 0.1259391805448, 0.5 * 0.1323941527885,
+                                          0.5 * 0.1323941527885, 0.5 * 0.1323941527885, 0.5 * 0.225};
+void oracle_gauss_tri(int ipt, double *knot, double *weight)
+{
+  knot[0] = TGauss23_knot[ipt][0];
+  knot[1] = TGauss23_knot[ipt][1];
+  *weight = TGauss23_weight[ipt];
+}
+void oracle_dshape_local_tri(int order, const double *s, double *psi, double *dpsi)
+{
+  if (order == 3)
+  {
+    const double s_2 = 1.0 - s[0] - s[1];
+    psi[0] = 2.0 * s[0] * (s[0] - 0.5);
+    psi[1] = 2.0 * s[1] * (s[1] - 0.5);
+    psi[2] = 2.0 * s_2 * (s_2 - 0.5);
+    psi[3] = 4.0 * s[0] * s[1];
+    psi[4] = 4.0 * s[1] * s_2;
+    psi[5] = 4.0 * s_2 * s[0];
+    dpsi[0] = 4.0 * s[0] - 1.0;
+    dpsi[1] = 0.0;
+    dpsi[2] = 0.0;
+    dpsi[3] = 4.0 * s[1] - 1.0;
+    dpsi[4] = 2.0 * (2.0 * s[0] - 1.5 + 2.0 * s[1]);
+    dpsi[5] = 2.0 * (2.0 * s[0] - 1.5 + 2.0 * s[1]);
+    dpsi[6] = 4.0 * s[1];
+    dpsi[7] = 4.0 * s[0];
+    dpsi[8] = -4.0 * s[1];
+    dpsi[9] = 4.0 * (1.0 - s[0] - 2.0 * s[1]);
+    dpsi[10] = 4.0 * (1.0 - 2.0 * s[0] - s[1]);
+    dpsi[11] = -4.0 * s[0];
+  }
+  else
+  {
+    psi[0] = s[0];
+    psi[1] = s[1];
+    psi[2] = 1.0 - s[0] - s[1];
+    dpsi[0] = 1.0; dpsi[1] = 0.0;
+    dpsi[2] = 0.0; dpsi[3] = 1.0;
+    dpsi[4] = -1.0; dpsi[5] = -1.0;
+  }
+}
+
 /* ------------------------------------------------------------------ problem data */
 #define MAXN 27
 #define MAXD 3
@@ -116,6 +164,7 @@ typedef struct
 {
   int dim, nnode, nnode_C1, n_int;
   int c1_nodes[8];
+  int tri; /* TElement<2,3> instead of QElement<2,3> */
 } EType;
 
 typedef struct { int col; double val; } Pair;
@@ -201,7 +250,8 @@ static void fill_shape_info_at_s(ThreadState *ts, const double *s, double weight
   const int dim = o->et.dim, nn = o->et.nnode;
   JITShapeInfo_t *si = &ts->si;
   double psi[MAXN], dpsids[MAXN * MAXD];
-  oracle_dshape_local(dim, 3, s, psi, dpsids);
+  if (o->et.tri) oracle_dshape_local_tri(3, s, psi, dpsids);
+  else oracle_dshape_local(dim, 3, s, psi, dpsids);
   double t[MAXD][MAXD], TL[MAXD][MAXD]; /* tangents t(a,i) Eulerian and Lagrangian */
   memset(t, 0, sizeof(t));
   memset(TL, 0, sizeof(TL));
@@ -309,7 +359,8 @@ static void fill_shape_info_at_s(ThreadState *ts, const double *s, double weight
     const double *P = psi, *D = dpsids;
     if (space == 1)
     {
-      oracle_dshape_local(dim, 2, s, p1, d1);
+      if (o->et.tri) oracle_dshape_local_tri(2, s, p1, d1);
+      else oracle_dshape_local(dim, 2, s, p1, d1);
       P = p1;
       D = d1;
     }
@@ -352,7 +403,8 @@ static void cb_fill_shape_buffer_for_point(unsigned ipt, JITFuncSpec_RequiredSha
 {
   ThreadState *ts = TS;
   double s[MAXD], w;
-  oracle_gauss(ts->o->et.dim, (int)ipt, s, &w);
+  if (ts->o->et.tri) oracle_gauss_tri((int)ipt, s, &w);
+  else oracle_gauss(ts->o->et.dim, (int)ipt, s, &w);
   fill_shape_info_at_s(ts, s, w, (unsigned)flag, req);
 }
 
@@ -548,18 +600,31 @@ static void element_rjm(ThreadState *ts, int e, int which, int param, unsigned f
 }
 
 /* ------------------------------------------------------------------ public C entry points (ctypes) */
-void *oracle_create(int dim, int n_elem, const int *elem_nodes, int n_node, int nval, int T, int n_pos_hist,
-                    const double *node_pos, const double *node_lagr, const double *node_val, const int *node_eqn,
-                    const int *pos_eqn, int n_dof)
+void *oracle_create_typed(int dim, int nnode, int n_elem, const int *elem_nodes, int n_node, int nval, int T, int n_pos_hist,
+                          const double *node_pos, const double *node_lagr, const double *node_val, const int *node_eqn,
+                          const int *pos_eqn, int n_dof)
 {
   init_tables();
   Oracle *o = (Oracle *)xcalloc(1, sizeof(Oracle));
-  static const int c1q[4] = {0, 2, 6, 8}, c1b[8] = {0, 2, 6, 8, 18, 20, 24, 26};
+  static const int c1q[4] = {0, 2, 6, 8}, c1b[8] = {0, 2, 6, 8, 18, 20, 24, 26}, c1t[3] = {0, 1, 2};
   o->et.dim = dim;
-  o->et.nnode = dim == 2 ? 9 : 27;
-  o->et.nnode_C1 = dim == 2 ? 4 : 8;
-  o->et.n_int = dim == 2 ? 9 : 27;
-  memcpy(o->et.c1_nodes, dim == 2 ? c1q : c1b, sizeof(int) * o->et.nnode_C1);
+  o->et.tri = (dim == 2 && nnode == 6);
+  if (o->et.tri)
+  {
+    /* BulkElementTri2dC2 (src/elements.cpp:9844-9856): 6 nodes, C1 on the vertices, TGauss<2,3> */
+    o->et.nnode = 6;
+    o->et.nnode_C1 = 3;
+    o->et.n_int = 7;
+    memcpy(o->et.c1_nodes, c1t, sizeof(c1t));
+  }
+  else
+  {
+    o->et.nnode = dim == 2 ? 9 : 27;
+    o->et.nnode_C1 = dim == 2 ? 4 : 8;
+    o->et.n_int = dim == 2 ? 9 : 27;
+    memcpy(o->et.c1_nodes, dim == 2 ? c1q : c1b, sizeof(int) * o->et.nnode_C1);
+  }
+  if (nnode != o->et.nnode) { fprintf(stderr, "oracle: unsupported element (dim %d, %d nodes)\n", dim, nnode); abort(); }
   o->n_elem = n_elem;
   o->n_node = n_node;
   o->nval = nval;
@@ -589,6 +654,13 @@ void *oracle_create(int dim, int n_elem, const int *elem_nodes, int n_node, int 
   o->steady = 1;
   if ((int)o->ft->nodal_dim != dim) { fprintf(stderr, "oracle: plugin dimension mismatch\n"); abort(); }
   return o;
+}
+
+void *oracle_create(int dim, int n_elem, const int *elem_nodes, int n_node, int nval, int T, int n_pos_hist,
+                    const double *node_pos, const double *node_lagr, const double *node_val, const int *node_eqn,
+                    const int *pos_eqn, int n_dof)
+{
+  return oracle_create_typed(dim, dim == 2 ? 9 : 27, n_elem, elem_nodes, n_node, nval, T, n_pos_hist, node_pos, node_lagr, node_val, node_eqn, pos_eqn, n_dof);
 }
 
 int oracle_num_params(void *h) { return (int)((Oracle *)h)->ft->numglobal_params; }

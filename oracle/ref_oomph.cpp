@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "Qelements.h"
+#include "Telements.h"
 #include "integral.h"
 #include "mesh.h"
 #include "nodes.h"
@@ -117,6 +118,48 @@ extern "C"
     }
     delete el;
     return (int)n;
+  }
+
+  // TElement<2,nnode_1d>::dshape_local (Telements.h:519-545, :627-664) and local_coordinate_of_node; node_s may be NULL
+  int ref_tshape(int nnode_1d, const double *s, double *psi, double *dpsi, double *node_s)
+  {
+    Vector<double> sv(2);
+    sv[0] = s[0];
+    sv[1] = s[1];
+    FiniteElement *el = nnode_1d == 3 ? (FiniteElement *)new TElement<2, 3> : (FiniteElement *)new TElement<2, 2>;
+    const unsigned n = el->nnode();
+    Shape p(n);
+    DShape dp(n, 2);
+    el->dshape_local(sv, p, dp);
+    for (unsigned l = 0; l < n; l++)
+    {
+      psi[l] = p[l];
+      dpsi[l * 2] = dp(l, 0);
+      dpsi[l * 2 + 1] = dp(l, 1);
+      if (node_s)
+      {
+        Vector<double> ns;
+        el->local_coordinate_of_node(l, ns);
+        node_s[l * 2] = ns[0];
+        node_s[l * 2 + 1] = ns[1];
+      }
+    }
+    delete el;
+    return (int)n;
+  }
+
+  // default integration scheme of TElement<2,3> (TGauss<2,3>, integral.cc:355-369); returns the number of points
+  int ref_tgauss(int ipt, double *knot, double *w)
+  {
+    TElement<2, 3> el;
+    const int n = (int)el.integral_pt()->nweight();
+    if (ipt >= 0 && ipt < n)
+    {
+      knot[0] = el.integral_pt()->knot(ipt, 0);
+      knot[1] = el.integral_pt()->knot(ipt, 1);
+      *w = el.integral_pt()->weight(ipt);
+    }
+    return n;
   }
 
   // default integration scheme of QElement<dim,3>: knot[dim] and weight of point ipt; returns the number of points

@@ -51,6 +51,9 @@ class ElementType:
 ELEMENT_TYPES: Dict[str, ElementType] = {
     "Quad2dC2": ElementType("Quad2dC2", 2, 2, 9, 3, (0, 2, 6, 8), 9),
     "Brick3dC2": ElementType("Brick3dC2", 3, 3, 27, 3, (0, 2, 6, 8, 18, 20, 24, 26), 27),
+    # BulkElementTri2dC2 = oomph TElement<2,3> (src/elements.hpp:990, src/elements.cpp:9844-9856): 6 nodes (vertices 0,1,2 then the
+    # mid-side nodes 3: 0-1, 4: 1-2, 5: 2-0, Telements.h:575-621), C1 on the vertices, default scheme TGauss<2,3> with 7 points
+    "Tri2dC2": ElementType("Tri2dC2", 2, 2, 6, 3, (0, 1, 2), 7),
 }
 
 SPACE_ORDER = ("C2TB", "C2", "C1TB", "C1")  # nodal_data index order (src/codegen.cpp:2367-2380)

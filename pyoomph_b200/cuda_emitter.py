@@ -52,6 +52,51 @@ def gauss_rule(dim: int):
     return kn, w
 
 
+def tgauss_rule():
+    """Literal oomph table TGauss<2,3> (integral.cc:355-369): 7 points, degree 5 (Bathe)."""
+    a, b, c, d, e = 0.1012865073235, 0.7974269853531, 0.4701420641051, 0.0597158717898, 0.3333333333333
+    kn = [(a, a), (b, a), (a, b), (c, d), (c, c), (d, c), (e, e)]
+    w = [0.5 * 0.1259391805448] * 3 + [0.5 * 0.1323941527885] * 3 + [0.5 * 0.225]
+    return kn, w
+
+
+def triangle_shape_tables(order: int, knots):
+    """psi[ipt][l], dpsi[ipt][l][b] of TElementShape<2,3> (Telements.h:627-664) / TElementShape<2,2> (:519-545), same operation order"""
+    psi, dpsi = [], []
+    for (s0, s1) in knots:
+        if order == 3:
+            s2 = 1.0 - s0 - s1
+            ps = [2.0 * s0 * (s0 - 0.5), 2.0 * s1 * (s1 - 0.5), 2.0 * s2 * (s2 - 0.5), 4.0 * s0 * s1, 4.0 * s1 * s2, 4.0 * s2 * s0]
+            ds = [(4.0 * s0 - 1.0, 0.0), (0.0, 4.0 * s1 - 1.0), (2.0 * (2.0 * s0 - 1.5 + 2.0 * s1), 2.0 * (2.0 * s0 - 1.5 + 2.0 * s1)),
+                  (4.0 * s1, 4.0 * s0), (-4.0 * s1, 4.0 * (1.0 - s0 - 2.0 * s1)), (4.0 * (1.0 - 2.0 * s0 - s1), -4.0 * s0)]
+        else:
+            ps = [s0, s1, 1.0 - s0 - s1]
+            ds = [(1.0, 0.0), (0.0, 1.0), (-1.0, -1.0)]
+        psi.append(ps)
+        dpsi.append(ds)
+    return psi, dpsi
+
+
+TRIANGLE_NODE_COORDS = [(1.0, 0.0), (0.0, 1.0), (0.0, 0.0), (0.5, 0.5), (0.0, 0.5), (0.5, 0.0)]    # Telements.h:575-621
+
+
+def element_rule(et):
+    """(knots, weights) of the element type's default integration scheme"""
+    return tgauss_rule() if et.name.startswith("Tri") else gauss_rule(et.nodal_dim)
+
+
+def element_shape_tables(et, order: int, knots):
+    return triangle_shape_tables(order, knots) if et.name.startswith("Tri") else shape_tables(et.nodal_dim, order, knots)
+
+
+def element_node_coords(et):
+    """local coordinates of the element's nodes (local_coordinate_of_node)"""
+    if et.name.startswith("Tri"):
+        return list(TRIANGLE_NODE_COORDS)
+    grid = (-1.0, 0.0, 1.0)
+    return [tuple(grid[(l // 3 ** d) % 3] for d in range(et.nodal_dim)) for l in range(et.nnode)]
+
+
 def _lag(order: int, s: float):
     # oomph-lib shape.h:604-650, same operation order
     if order == 3:
@@ -310,9 +355,9 @@ class CudaEmitter:
         return "a.ti.w_%s_%s" % ("dt" if order == 1 else "d2t", scheme)
 
     def _emit_tables(self, o: List[str]):
-        kn, w = gauss_rule(self.dim)
-        psi2, dpsi2 = shape_tables(self.dim, 3, kn)
-        psi1, dpsi1 = shape_tables(self.dim, 2, kn)
+        kn, w = element_rule(self.et)
+        psi2, dpsi2 = element_shape_tables(self.et, 3, kn)
+        psi1, dpsi1 = element_shape_tables(self.et, 2, kn)
 
         def arr(vals):
             return ", ".join(repr(float(v)) for v in vals)
@@ -346,17 +391,16 @@ class CudaEmitter:
         if self.code.point_expression_names():
             # the same tables at the element's NODES (local coordinates -1, 0, 1 per direction, oomph node order): point expressions are
             # evaluated at the integration points or at the nodes (eval_local_expression_at_node, src/elements.cpp:4659)
-            grid = (-1.0, 0.0, 1.0)
-            nk = [tuple(grid[(l // 3 ** d) % 3] for d in range(self.dim)) for l in range(self.NN)]
-            npsi2, ndpsi2 = shape_tables(self.dim, 3, nk)
-            npsi1, ndpsi1 = shape_tables(self.dim, 2, nk)
+            nk = element_node_coords(self.et)
+            npsi2, ndpsi2 = element_shape_tables(self.et, 3, nk)
+            npsi1, ndpsi1 = element_shape_tables(self.et, 2, nk)
             nt1 = []
             if self.dim == 3:
                 for sk in nk:
                     for d in range(3):
                         P, D = _lag(3, sk[d])
                         nt1 += list(P) + list(D)
-            o.append("__device__ const double g_tables_nodes[%d] = {%s};" % (self.NN * (self.NN * (1 + self.dim) + self.NN1 * (1 + self.dim)) + len(nt1), arr(
+            o.append("__device__ const double g_tables_nodes[%d] = {%s};" % (self._tables_smem_size(self.NN), arr(
                 [v for p in npsi2 for v in p] + [v for p in ndpsi2 for l in p for v in l] + [v for p in npsi1 for v in p] + [v for p in ndpsi1 for l in p for v in l] + nt1)))
         o.append("__constant__ int c_c1node[%d] = {%s};" % (self.NN1, ", ".join(str(n) for n in self.et.c1_nodes)))
         # row dof index of (field, space-local node)
@@ -365,9 +409,11 @@ class CudaEmitter:
             o.append("__constant__ int c_row_%s[%d] = {%s};" % (f, nn, ", ".join(str(self._col_index(f, l)) for l in range(nn))))
         o.append("")
 
-    def _tables_smem_size(self) -> int:
-        """doubles of shape tables staged in shared memory (needed by phase 1 always, phase 2 in smem mode)."""
-        return self.NIPT * (self.NN * (1 + self.dim) + self.NN1 * (1 + self.dim)) + (self.NIPT * 18 if self.dim == 3 else 0)
+    def _tables_smem_size(self, npt: Optional[int] = None) -> int:
+        """doubles of shape tables staged in shared memory (needed by phase 1 always, phase 2 in smem mode) for npt points
+        (default: the integration points)"""
+        npt = self.NIPT if npt is None else npt
+        return npt * (self.NN * (1 + self.dim) + self.NN1 * (1 + self.dim)) + (npt * 18 if self.dim == 3 else 0)
 
     def _emit_kernel(self, o: List[str], rp: RoutinePlan, what: int):
         code, dim, NN, NN1, NIPT = self.code, self.dim, self.NN, self.NN1, self.NIPT
@@ -585,9 +631,7 @@ class CudaEmitter:
         ELS, EL0, PB = plan["ELS"], plan["EL0"], plan["PB"]
         NE, NN, NN1, dim = len(form.slots), self.NN, self.NN1, self.dim
         NPT = NN if at_nodes else self.NIPT
-        if at_nodes and NN != self.NIPT:
-            raise RuntimeError("node tables need as many nodes as integration points in this layout")
-        tab_n = self._tables_smem_size()
+        tab_n = self._tables_smem_size(NPT)
         NT = 256
         EPB = max(2, min(NT // NPT if NPT <= NT else 2, (self.smem_budget - tab_n * 8) // (ELS * 8)))
         kname = "pb2_%s_points_%s" % (self.name, "n" if at_nodes else "g")

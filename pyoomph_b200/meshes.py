@@ -59,6 +59,8 @@ class StructuredMesh:
         pid = grids[0].ravel()
         for d in range(1, self.dim):
             pid = pid * npd[d] + grids[d].ravel()
+        if self.element_type == "Tri2dC2":
+            pid = np.repeat(pid, 2)          # two triangles per lattice cell, stored one after the other
         return pid.astype(np.int32)
 
 
@@ -145,6 +147,23 @@ def RectangularQuadMesh(N=10, size=1.0, lower_left=(0.0, 0.0)) -> StructuredMesh
     N = (N, N) if np.isscalar(N) else tuple(N)
     size = (size, size) if np.isscalar(size) else tuple(size)
     return _structured(N, [float(s) for s in size], [float(v) for v in lower_left])
+
+
+def RectangularTriangleMesh(N=10, size=1.0, lower_left=(0.0, 0.0)) -> StructuredMesh:
+    """Six-node triangles (BulkElementTri2dC2 = oomph TElement<2,3>, src/elements.hpp:990) on the node set of the Q9 mesh of N[0] x N[1]
+    cells: every cell is cut along its lower-left -> upper-right diagonal into two counter-clockwise triangles; the cell's centre node
+    becomes the mid-side node of the diagonal.  Local node order of TElementShape<2,3> (Telements.h:575-621): vertices 0, 1, 2, then
+    the mid-side nodes 3 (between 0 and 1), 4 (1 and 2), 5 (2 and 0).  Node numbering, positions, boundaries and equation numbering are
+    those of the quad mesh (vertices before mid nodes); a stand-in for the gmsh triangle meshes of the reference's droplet
+    scripts, whose element order is the generator's."""
+    q = RectangularQuadMesh(N, size, lower_left)
+    en = q.elem_nodes
+    a = en[:, [0, 2, 8, 1, 5, 4]]          # lower-right triangle: ll, lr, ur | mids ll-lr, lr-ur, ur-ll (the cell centre)
+    b = en[:, [0, 8, 6, 4, 7, 3]]          # upper-left triangle:  ll, ur, ul | mids ll-ur (the cell centre), ur-ul, ul-ll
+    tri = np.empty((2 * en.shape[0], 6), dtype=np.int32)
+    tri[0::2], tri[1::2] = a, b
+    m = StructuredMesh(2, q.N, np.ascontiguousarray(tri), q.node_pos, q.node_lattice, q.boundaries, "Tri2dC2")
+    return m
 
 
 def CuboidBrickMesh(N=4, size=1.0, lower_left=(0.0, 0.0, 0.0)) -> StructuredMesh:

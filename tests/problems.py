@@ -76,7 +76,28 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             return _variant(_mk["brick"](n))
     else:
         from pyoomph_b200.meshes import CuboidBrickMesh, RectangularQuadMesh
-    if kind == "poisson":          # config 1
+    if kind in ("poisson_tri", "ns_tri", "ale_tri"):
+        # six-node triangles (the element class of the reference's gmsh droplet meshes): Poisson, Taylor-Hood P2/P1 Navier-Stokes,
+        # and NS on a pseudo-elastic moving mesh
+        import pyoomph_b200.meshes as _mm
+        mesh = _mm.RectangularTriangleMesh(N)
+        if unstructured:
+            raise NotImplementedError
+        if distortion:
+            mesh = distort(mesh, distortion, seed)
+        if kind == "poisson_tri":
+            code = FiniteElementCode("Tri2dC2", PoissonEquation(source=poisson_source), name="poissontri")
+            pinned = {"u": np.concatenate([mesh.boundaries["left"], mesh.boundaries["right"]])}
+            unsteady = False
+        else:
+            eqs = NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0)
+            if kind == "ale_tri":
+                eqs = eqs + PseudoElasticMesh()
+            code = FiniteElementCode("Tri2dC2", eqs, name=kind.replace("_", ""))
+            wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
+            pinned = {"velocity_x": wall, "velocity_y": wall}
+            unsteady = True
+    elif kind == "poisson":          # config 1
         mesh = RectangularQuadMesh(N)
         code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")
         pinned = {"u": np.concatenate([mesh.boundaries["left"], mesh.boundaries["right"]])}

@@ -29,12 +29,15 @@ CASES = [("poisson", 64), ("poisson", 5), ("ns", 12), ("ns_unsteady", 9), ("heat
 
 
 # (kind, N, distortion in element widths, unstructured = random element order + random node labels, no patch hint)
+# six-node triangles (BulkElementTri2dC2 = TElement<2,3>, TGauss<2,3>): Poisson, Taylor-Hood P2/P1 NS, NS on a pseudo-elastic moving mesh
+TRIANGLES = [("poisson_tri", 9, 0.0, False), ("poisson_tri", 8, 0.12, False), ("ns_tri", 7, 0.1, False), ("ale_tri", 5, 0.08, False)]
+
 VARIANTS = [("ns", 11, 0.12, False), ("ns_unsteady", 10, 0.1, True), ("heat3d", 3, 0.1, True), ("ale", 6, 0.08, True), ("poisson", 33, 0.15, True),
             ("ns_axi_swirl", 6, 0.1, True), ("ale_axi", 6, 0.08, True)]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,N,distortion,unstructured", [(k, n, 0.0, False) for k, n in CASES] + VARIANTS)
+@pytest.mark.parametrize("kind,N,distortion,unstructured", [(k, n, 0.0, False) for k, n in CASES] + VARIANTS + TRIANGLES)
 def test_residual_jacobian_mass_parity(kind, N, distortion, unstructured):
     pb = make_problem(kind, N, distortion=distortion, unstructured=unstructured)
     op = make_oracle(pb)

@@ -383,3 +383,50 @@ def test_point_expressions_of_the_oracle_linear_fields():
     vert = [0, 2, 6, 8]
     assert np.abs(vn[:, vert, ip] - pb["vals"][0][en[:, vert], 2]).max() <= 1e-13       # C1 field at the vertex nodes: the nodal values
     op.close()
+
+
+def test_triangle_elements_of_the_oracle():
+    """BulkElementTri2dC2 in the oracle: symmetric Laplace matrix with zero row sums, patch test on a distorted triangle mesh, the
+    element areas add up to the domain, analytic-vs-FD Jacobian of the Taylor-Hood P2/P1 Navier-Stokes class (src/elements.cpp:5880)."""
+    from problems import csr_to_sorted, make_oracle, make_problem
+    from pyoomph_b200.codegen import FiniteElementCode
+    from pyoomph_b200.equations import PoissonEquation
+    pb = make_problem("poisson_tri", 4, distortion=0.1)
+    m = pb["mesh"]
+    pb["code"] = FiniteElementCode("Tri2dC2", PoissonEquation(), name="laplacetri")
+    pb["vals"][0][:, 0] = 1 + 2 * m.node_pos[:, 0] - 3 * m.node_pos[:, 1]
+    op = make_oracle(pb)
+    r, mats = op.assemble(flag=1)
+    n = pb["dofmap"].n_dof
+    A = csr_to_sorted(n, *mats[0])
+    assert abs(A - A.T).max() <= 1e-13 * abs(A).max()
+    lat = m.node_lattice
+    interior = np.all((lat > 0) & (lat < 2 * np.array(m.N)), axis=1)
+    rows = pb["dofmap"].node_eqn[interior, 0]
+    rows = rows[rows >= 0]
+    assert np.abs(r[rows]).max() <= 1e-12 * abs(A).max()              # a linear field is reproduced exactly: zero interior residual
+    flat = make_problem("poisson_tri", 3)
+    op2 = make_oracle(flat)
+    area = sum(op2.point_shapes(e, ipt, flag=0)[0][0] for e in range(flat["mesh"].n_elem) for ipt in range(7))
+    assert abs(area - 1.0) <= 1e-12
+    op.close(); op2.close()
+    pb = make_problem("ns_tri", 2, distortion=0.1)
+    op = make_oracle(pb)
+    _, mats = op.assemble(flag=1)
+    n = pb["dofmap"].n_dof
+    A = csr_to_sorted(n, *mats[0]).toarray()
+    eq, eps = pb["dofmap"].node_eqn, 1e-6
+    for node, f in ((5, 0), (7, 1), (0, 2), (12, 0)):
+        g = eq[node, f]
+        if g < 0:
+            continue
+        v = pb["vals"][0].copy()
+        v[node, f] += eps
+        op.update_values(0, v)
+        rp, _ = op.assemble(flag=0)
+        v[node, f] -= 2 * eps
+        op.update_values(0, v)
+        rm, _ = op.assemble(flag=0)
+        op.update_values(0, pb["vals"][0])
+        assert np.abs((rp - rm) / (2 * eps) - A[:, g]).max() <= 1e-7 * np.abs(A[:, g]).max()
+    op.close()

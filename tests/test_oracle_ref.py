@@ -305,3 +305,35 @@ def test_sparse_rank3_tensor_matches_compiled_reference(oomph):
     assert len(ent) == len({(a, b, c) for a, b, c in zip(ii.tolist(), jj.tolist(), kk.tolist())}) and ent == sorted(ent, key=lambda t: t[:3])
     with pytest.raises(RuntimeError):
         SparseRank3Tensor(n).right_vector_mult(vec)
+
+
+def test_triangle_shape_functions_and_tgauss_bit_exact(oomph):
+    """TElement<2,3> / TElement<2,2>::dshape_local, local_coordinate_of_node and TGauss<2,3> of the compiled oomph-lib against the
+    emitter's triangle tables (bit-exact) and the oracle's restatement."""
+    from oracle import build_plugin
+    from pyoomph_b200.cuda_emitter import TRIANGLE_NODE_COORDS, tgauss_rule, triangle_shape_tables
+    pb = make_problem("poisson", 2)
+    drv = ctypes.CDLL(build_plugin(pb["code"], pb["code"].name))
+    kn, w = tgauss_rule()
+    k_ref, w_ref = (ctypes.c_double * 2)(), ctypes.c_double()
+    assert oomph.ref_tgauss(0, k_ref, ctypes.byref(w_ref)) == 7 == len(kn)
+    for ipt in range(7):
+        oomph.ref_tgauss(ipt, k_ref, ctypes.byref(w_ref))
+        assert list(k_ref) == list(kn[ipt]) and w_ref.value == w[ipt]
+        ko, wo = (ctypes.c_double * 3)(), ctypes.c_double()
+        drv.oracle_gauss_tri(ipt, ko, ctypes.byref(wo))
+        assert list(ko)[:2] == list(kn[ipt]) and wo.value == w[ipt]
+    rng = np.random.default_rng(8)
+    pts = [np.array(k) for k in kn] + [np.array(c) for c in TRIANGLE_NODE_COORDS] + [rng.dirichlet((1, 1, 1))[:2] for _ in range(10)]
+    for order, n in ((3, 6), (2, 3)):
+        for s in pts:
+            s = np.ascontiguousarray(s, dtype=np.float64)
+            psi, dpsi, ns = np.zeros(n), np.zeros((n, 2)), np.zeros((n, 2))
+            assert oomph.ref_tshape(order, _dp(s), _dp(psi), _dp(dpsi), _dp(ns)) == n
+            pt, dt = triangle_shape_tables(order, [tuple(s)])
+            assert np.array_equal(psi, np.array(pt[0])) and np.array_equal(dpsi, np.array(dt[0]))
+            po, do = np.zeros(n), np.zeros((n, 2))
+            drv.oracle_dshape_local_tri(order, _dp(s), _dp(po), _dp(do))
+            assert np.abs(po - psi).max() <= 4e-16 and np.abs(do - dpsi).max() <= 1e-15
+            if order == 3:
+                assert np.array_equal(ns, np.array(TRIANGLE_NODE_COORDS))
