@@ -65,6 +65,14 @@ void oracle_gauss(int dim, int ipt, double *knot, double *weight)
   else { for (int i = 0; i < 3; i++) knot[i] = Gauss33_knot[ipt][i]; *weight = Gauss33_weight[ipt]; }
 }
 
+/* Gauss<1,3> (oomph-lib integral.cc:50-53) */
+void oracle_gauss_1d(int ipt, double *knot, double *weight)
+{
+  static const double k[3] = {-0.774596669241483, 0.0, 0.774596669241483}, w[3] = {(5.0 / 9.0), (8.0 / 9.0), (5.0 / 9.0)};
+  knot[0] = k[ipt];
+  *weight = w[ipt];
+}
+
 /* ------------------------------------------------------------------ shape functions */
 static void lag3(double s, double *p) { p[0] = 0.5 * s * (s - 1.0); p[1] = 1.0 - s * s; p[2] = 0.5 * s * (s + 1.0); }
 static void dlag3(double s, double *p) { p[0] = s - 0.5; p[1] = -2.0 * s; p[2] = s + 0.5; }
@@ -164,7 +172,8 @@ typedef struct
 {
   int dim, nnode, nnode_C1, n_int;
   int c1_nodes[8];
-  int tri; /* TElement<2,3> instead of QElement<2,3> */
+  int tri;  /* TElement<2,3> instead of QElement<2,3> */
+  int edim; /* dimension of the element itself: dim for bulk elements, 1 for a line element in 2D (interface elements) */
 } EType;
 
 typedef struct { int col; double val; } Pair;
@@ -241,26 +250,38 @@ static void check_size(unsigned long long a, unsigned long long b, char *what)
 }
 
 /* ------------------------------------------------------------------ geometry at one Gauss point
- * restates BulkElementBase::fill_shape_info_at_s for el_dim == nodal_dim in {2,3} (src/elements.cpp:3593) */
+ * restates BulkElementBase::fill_shape_info_at_s (src/elements.cpp:3593-4268): tangents, metric, inverse metric, gab_gai and the
+ * determinant for el_dim 1 (:3651-3672), 2 (:3677-3703), 3 (:3804-3836) in nodal dimension >= el_dim; the unit normal of a line
+ * element in 2D (get_normal_at_s, :1730-1752) and its coordinate derivatives (get_dnormal_dcoords_at_s, :1461-1490) */
+static void element_dshape_local(const Oracle *o, int order, const double *s, double *psi, double *dpsi)
+{
+  if (o->et.tri) oracle_dshape_local_tri(order, s, psi, dpsi);
+  else if (o->et.edim == 1)
+  {
+    if (order == 3) { lag3(s[0], psi); dlag3(s[0], dpsi); }
+    else { lag2(s[0], psi); dlag2(s[0], dpsi); }
+  }
+  else oracle_dshape_local(o->et.dim, order, s, psi, dpsi);
+}
+
 static void fill_shape_info_at_s(ThreadState *ts, const double *s, double weight, unsigned flag,
                                  const JITFuncSpec_RequiredShapes_FiniteElement_t *req)
 {
   (void)req; /* everything is filled; the reference skips unrequired spaces, values are identical */
   Oracle *o = ts->o;
-  const int dim = o->et.dim, nn = o->et.nnode;
+  const int dim = o->et.dim, ed = o->et.edim, nn = o->et.nnode;
   JITShapeInfo_t *si = &ts->si;
   double psi[MAXN], dpsids[MAXN * MAXD];
-  if (o->et.tri) oracle_dshape_local_tri(3, s, psi, dpsids);
-  else oracle_dshape_local(dim, 3, s, psi, dpsids);
+  element_dshape_local(o, 3, s, psi, dpsids);
   double t[MAXD][MAXD], TL[MAXD][MAXD]; /* tangents t(a,i) Eulerian and Lagrangian */
   memset(t, 0, sizeof(t));
   memset(TL, 0, sizeof(TL));
   for (int l = 0; l < nn; l++)
   {
     for (int i = 0; i < dim; i++)
-      for (int j = 0; j < dim; j++) t[j][i] += ts->ei.nodal_coords[l][i][0] * dpsids[l * dim + j];
+      for (int j = 0; j < ed; j++) t[j][i] += ts->ei.nodal_coords[l][i][0] * dpsids[l * ed + j];
     for (int i = 0; i < dim; i++)
-      for (int j = 0; j < dim; j++) TL[j][i] += ts->ei.nodal_coords[l][dim + i][0] * dpsids[l * dim + j];
+      for (int j = 0; j < ed; j++) TL[j][i] += ts->ei.nodal_coords[l][dim + i][0] * dpsids[l * ed + j];
   }
   double gg[MAXD][MAXD], ggL[MAXD][MAXD], aup[MAXD][MAXD], detE = 0, detL = 0;
   const int require_dxdshape = (flag && o->ft->moving_nodes && !o->ft->fd_position_jacobian);
@@ -269,13 +290,20 @@ static void fill_shape_info_at_s(ThreadState *ts, const double *s, double weight
     double(*tt)[MAXD] = pass == 0 ? t : TL;
     double(*g)[MAXD] = pass == 0 ? gg : ggL;
     double amet[MAXD][MAXD], up[MAXD][MAXD], det_a;
-    for (int al = 0; al < dim; al++)
-      for (int be = 0; be < dim; be++)
+    memset(up, 0, sizeof(up));
+    for (int al = 0; al < ed; al++)
+      for (int be = 0; be < ed; be++)
       {
         amet[al][be] = 0.0;
         for (int i = 0; i < dim; i++) amet[al][be] += tt[al][i] * tt[be][i];
       }
-    if (dim == 2)
+    if (ed == 1)
+    {
+      det_a = amet[0][0];
+      up[0][0] = 1.0 / det_a;
+      for (int i = 0; i < dim; i++) g[0][i] = tt[0][i] / det_a;
+    }
+    else if (ed == 2)
     {
       det_a = amet[0][0] * amet[1][1] - amet[0][1] * amet[1][0];
       up[0][0] = amet[1][1] / det_a;
@@ -309,7 +337,7 @@ static void fill_shape_info_at_s(ThreadState *ts, const double *s, double weight
       detL = sqrt(det_a);
   }
 
-  /* moving-mesh helper (src/elements.cpp:3051-3155): int_pt_weights_d_coords and DXdshape_il_jb */
+  /* moving-mesh helper (src/elements.cpp:3051-3155): int_pt_weights_d_coords and DXdshape_il_jb, el_dim x nodal_dim general */
   static __thread double DX[MAXD][MAXN][MAXD][MAXD];
   if (require_dxdshape)
   {
@@ -318,33 +346,33 @@ static void fill_shape_info_at_s(ThreadState *ts, const double *s, double weight
       for (int i = 0; i < dim; i++)
       {
         double dshape_dx = 0.0;
-        for (int a = 0; a < dim; a++)
-          for (int b = 0; b < dim; b++) dshape_dx += aup[a][b] * dpsids[l * dim + b] * t[a][i];
+        for (int a = 0; a < ed; a++)
+          for (int b = 0; b < ed; b++) dshape_dx += aup[a][b] * dpsids[l * ed + b] * t[a][i];
         si->int_pt_weights_d_coords[i][l] = dshape_dx * detE * weight;
       }
     for (int l = 0; l < nn; l++)
-      for (int c = 0; c < dim; c++)
-        for (int d = 0; d < dim; d++)
-          for (int j = 0; j < dim; j++) Tt[l][c][d][j] = dpsids[l * dim + c] * t[d][j] + dpsids[l * dim + d] * t[c][j];
+      for (int c = 0; c < ed; c++)
+        for (int d = 0; d < ed; d++)
+          for (int j = 0; j < dim; j++) Tt[l][c][d][j] = dpsids[l * ed + c] * t[d][j] + dpsids[l * ed + d] * t[c][j];
     for (int l = 0; l < nn; l++)
-      for (int a = 0; a < dim; a++)
-        for (int b = 0; b < dim; b++)
+      for (int a = 0; a < ed; a++)
+        for (int b = 0; b < ed; b++)
           for (int j = 0; j < dim; j++)
           {
             double Gval = 0.0;
-            for (int c = 0; c < dim; c++)
-              for (int d = 0; d < dim; d++) Gval -= aup[a][c] * Tt[l][c][d][j] * aup[d][b];
+            for (int c = 0; c < ed; c++)
+              for (int d = 0; d < ed; d++) Gval -= aup[a][c] * Tt[l][c][d][j] * aup[d][b];
             G[l][a][b][j] = Gval;
           }
     for (int i = 0; i < dim; i++)
       for (int l = 0; l < nn; l++)
         for (int j = 0; j < dim; j++)
-          for (int b = 0; b < dim; b++)
+          for (int b = 0; b < ed; b++)
           {
             double v = 0.0;
-            for (int a = 0; a < dim; a++)
+            for (int a = 0; a < ed; a++)
             {
-              if (i == j) v += aup[a][b] * dpsids[l * dim + a];
+              if (i == j) v += aup[a][b] * dpsids[l * ed + a];
               v += t[a][j] * G[l][a][b][i];
             }
             DX[i][l][j][b] = v;
@@ -359,8 +387,7 @@ static void fill_shape_info_at_s(ThreadState *ts, const double *s, double weight
     const double *P = psi, *D = dpsids;
     if (space == 1)
     {
-      if (o->et.tri) oracle_dshape_local_tri(2, s, p1, d1);
-      else oracle_dshape_local(dim, 2, s, p1, d1);
+      element_dshape_local(o, 2, s, p1, d1);
       P = p1;
       D = d1;
     }
@@ -375,13 +402,13 @@ static void fill_shape_info_at_s(ThreadState *ts, const double *s, double weight
       for (int i = 0; i < dim; i++)
       {
         dx[l][i] = 0.0;
-        for (int b = 0; b < dim; b++) dx[l][i] += gg[b][i] * D[l * dim + b];
+        for (int b = 0; b < ed; b++) dx[l][i] += gg[b][i] * D[l * ed + b];
       }
-      for (int i = 0; i < dim; i++) dS[l][i] = D[l * dim + i];
+      for (int i = 0; i < ed; i++) dS[l][i] = D[l * ed + i];
       for (int i = 0; i < dim; i++)
       {
         dX[l][i] = 0.0;
-        for (int b = 0; b < dim; b++) dX[l][i] += ggL[b][i] * D[l * dim + b];
+        for (int b = 0; b < ed; b++) dX[l][i] += ggL[b][i] * D[l * ed + b];
       }
       if (require_dxdshape)
         for (int i = 0; i < dim; i++)
@@ -389,8 +416,27 @@ static void fill_shape_info_at_s(ThreadState *ts, const double *s, double weight
             for (int i2 = 0; i2 < dim; i2++)
             {
               dd[l][i][l2][i2] = 0.0;
-              for (int b = 0; b < dim; b++) dd[l][i][l2][i2] += DX[i2][l2][i][b] * D[l * dim + b];
+              for (int b = 0; b < ed; b++) dd[l][i][l2][i2] += DX[i2][l2][i][b] * D[l * ed + b];
             }
+    }
+  }
+  if (ed == 1 && dim == 2)
+  {
+    /* get_normal_at_s for a line element (src/elements.cpp:1730-1752): n = (-dxds_y, dxds_x) / |dxds| */
+    double len = t[0][0] * t[0][0] + t[0][1] * t[0][1];
+    if (len < 1e-20) len = 1;
+    const double len_sqr = len;
+    len = sqrt(len);
+    si->normal[0] = -t[0][1] / len;
+    si->normal[1] = t[0][0] / len;
+    if (require_dxdshape)
+    {
+      /* get_dnormal_dcoords_at_s (src/elements.cpp:1461-1490) */
+      (void)len_sqr;
+      const double denom = 1 / (len * len * len);
+      for (int i = 0; i < dim; i++)
+        for (int l = 0; l < nn; l++)
+          for (int k = 0; k < dim; k++) si->d_normal_dcoord[i][l][k] = dpsids[l] * denom * (k == 1 ? -1 : 1) * t[0][i] * t[0][1 - k];
     }
   }
   si->int_pt_weight_unity = weight;
@@ -404,6 +450,7 @@ static void cb_fill_shape_buffer_for_point(unsigned ipt, JITFuncSpec_RequiredSha
   ThreadState *ts = TS;
   double s[MAXD], w;
   if (ts->o->et.tri) oracle_gauss_tri((int)ipt, s, &w);
+  else if (ts->o->et.edim == 1) oracle_gauss_1d((int)ipt, s, &w);
   else oracle_gauss(ts->o->et.dim, (int)ipt, s, &w);
   fill_shape_info_at_s(ts, s, w, (unsigned)flag, req);
 }
@@ -426,6 +473,9 @@ static ThreadState *ts_create(Oracle *o)
   si->dX_shape_C1 = alloc2(8, dim);
   si->dS_shape_C1 = alloc2(8, dim);
   si->d_dx_shape_dcoord_C1 = alloc4(8, dim, nn, dim);
+  si->normal = (double *)xcalloc(MAXD, sizeof(double));
+  si->d_normal_dcoord = (double ***)xcalloc(MAXD, sizeof(double **));
+  for (int i = 0; i < MAXD; i++) si->d_normal_dcoord[i] = alloc2(nn, MAXD);
   /* set_remaining_shapes_appropriately: Pos aliases C2 (src/elements.cpp:4534-4542) */
   si->shape_Pos = si->shape_C2;
   si->dx_shape_Pos = si->dx_shape_C2;
@@ -607,9 +657,20 @@ void *oracle_create_typed(int dim, int nnode, int n_elem, const int *elem_nodes,
   init_tables();
   Oracle *o = (Oracle *)xcalloc(1, sizeof(Oracle));
   static const int c1q[4] = {0, 2, 6, 8}, c1b[8] = {0, 2, 6, 8, 18, 20, 24, 26}, c1t[3] = {0, 1, 2};
+  static const int c1l[2] = {0, 2};
   o->et.dim = dim;
+  o->et.edim = dim;
   o->et.tri = (dim == 2 && nnode == 6);
-  if (o->et.tri)
+  if (dim == 2 && nnode == 3)
+  {
+    /* InterfaceElementLine1dC2: QElement<1,3> in a 2D space, C1 on the end nodes, Gauss<1,3> */
+    o->et.edim = 1;
+    o->et.nnode = 3;
+    o->et.nnode_C1 = 2;
+    o->et.n_int = 3;
+    memcpy(o->et.c1_nodes, c1l, sizeof(c1l));
+  }
+  else if (o->et.tri)
   {
     /* BulkElementTri2dC2 (src/elements.cpp:9844-9856): 6 nodes, C1 on the vertices, TGauss<2,3> */
     o->et.nnode = 6;

@@ -120,7 +120,8 @@ class CEmitter:
         for t in tests:
             if t.field not in test_fields:
                 test_fields.append(t.field)
-        names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi"}
+        names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi",
+                                       ex.NORMAL[0]: "shapeinfo->normal[0]", ex.NORMAL[1]: "shapeinfo->normal[1]", ex.NORMAL[2]: "shapeinfo->normal[2]"}
         for a in atoms:
             names[code.atom_symbol(a)] = "this_" + a.cname
         for k, p in enumerate(code.global_params):
@@ -303,7 +304,8 @@ class CEmitter:
         for e in exprs:
             used |= {s_ for s_ in e.free_symbols if s_ in code._atom_syms}
         atoms = sorted([code._atom_syms[s_] for s_ in used], key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
-        names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi"}
+        names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi",
+                                       ex.NORMAL[0]: "shapeinfo->normal[0]", ex.NORMAL[1]: "shapeinfo->normal[1]", ex.NORMAL[2]: "shapeinfo->normal[2]"}
         for a in atoms:
             names[code.atom_symbol(a)] = "this_" + a.cname
         for k, p in enumerate(code.global_params):
@@ -447,7 +449,8 @@ class CEmitter:
         for t in tests:
             if t.field not in test_fields:
                 test_fields.append(t.field)
-        names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi"}
+        names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi",
+                                       ex.NORMAL[0]: "shapeinfo->normal[0]", ex.NORMAL[1]: "shapeinfo->normal[1]", ex.NORMAL[2]: "shapeinfo->normal[2]"}
         for a in atoms:
             names[code.atom_symbol(a)] = "this_" + a.cname
         for k, p in enumerate(code.global_params):

@@ -70,6 +70,8 @@ typedef struct JITShapeInfo
   double *timestepper_weights_dt_BDF2_degr, *timestepper_weights_dt_Newmark2_degr;
   JITHangInfo_t *hanginfo_C1, *hanginfo_C2, *hanginfo_Pos;
   struct JITShapeInfo *bulk_shapeinfo, *opposite_shapeinfo;
+  double *normal;            /* [dim] unit normal of an interface element at the point (jitbridge.h:251) */
+  double ***d_normal_dcoord; /* [dir][coord node][coord dir] (jitbridge.h:252) */
 } JITShapeInfo_t;
 
 typedef void (*JITFuncSpec_ResidualAndJacobian_FiniteElement)(const JITElementInfo_t *, const JITShapeInfo_t *, double *, double *, double *, unsigned);

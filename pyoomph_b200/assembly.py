@@ -82,7 +82,7 @@ def load_library() -> ctypes.CDLL:
                "pb2_problem_assemble_hessian", "pb2_problem_fetch_hessian", "pb2_problem_hessian_vector_products",
                "pb2_problem_pack_rows", "pb2_problem_unpack_add", "pb2_problem_eval_integrals", "pb2_problem_shift_time_values",
                "pb2_problem_set_history_dofs", "pb2_measure_fp64_peak", "pb2_problem_host_maps", "pb2_problem_device_pattern",
-               "pb2_problem_device_dofs", "pb2_problem_update_dofs_device", "pb2_problem_eval_points"):
+               "pb2_problem_device_dofs", "pb2_problem_update_dofs_device", "pb2_problem_eval_points", "pb2_problem_create_child"):
         getattr(L, fn).restype = ctypes.c_int
     L.pb2_problem_setup_seconds.restype = ctypes.c_double
     _LIB = L
@@ -170,8 +170,11 @@ class B200Assembly(CustomAssemblyBase):
     def __init__(self, code: FiniteElementCode, mesh, dofmap, *, name: str = "elem", device: int = 0,
                  compiler: Optional[CudaCCompiler] = None, emitter_options: Optional[dict] = None,
                  elements: Optional[np.ndarray] = None, extra_pattern: Optional[Tuple[np.ndarray, np.ndarray]] = None,
-                 patch_hint=None):
-        """patch_hint: None = the mesh's own `element_patches()` if it has one, else consecutive elements; "spatial" = Morton-ordered
+                 patch_hint=None, parent: Optional["B200Assembly"] = None):
+        """parent: another assembly whose CSR matrix, residual and nodal data this element class scatters into (interface / boundary
+        element classes on the parent's nodes and equations: pb2_problem_create_child); `mesh` then carries the child's elements
+        (meshes.boundary_line_mesh) and `dofmap` is the parent's.  `parent.assemble()` assembles the parent and then its children.
+        patch_hint: None = the mesh's own `element_patches()` if it has one, else consecutive elements; "spatial" = Morton-ordered
         patches from the element centroids (meshes.spatial_patches, for meshes without lattice order); or an int array [n_elem]."""
         super().__init__()
         self._patch_hint = patch_hint
@@ -186,7 +189,14 @@ class B200Assembly(CustomAssemblyBase):
         _check(self.lib.pb2_class_get_info(self.cls, ctypes.byref(self.info)))
         self._device, self._elements, self._extra_pattern = device, elements, extra_pattern
         self.prob = None
+        self.parent, self.children = parent, []
+        if parent is not None:
+            if elements is not None or extra_pattern is not None:
+                raise ValueError("a child assembly has no element subset / pattern of its own")
+            self._device = parent._device
         self._create_problem(mesh, dofmap)
+        if parent is not None:
+            parent.children.append(self)
 
     def _create_problem(self, mesh, dofmap):
         """pack mesh + numbering into the SoA buffers of a new pb2_problem (the element class and its kernels are kept)"""
@@ -224,7 +234,11 @@ class B200Assembly(CustomAssemblyBase):
             md.extra_rows = self._ex_rows.ctypes.data_as(c_int_p)
             md.extra_cols = self._ex_cols.ctypes.data_as(c_int_p)
         self.prob = ctypes.c_void_p()
-        _check(self.lib.pb2_problem_create(self.cls, device, ctypes.byref(md), ctypes.byref(self.prob)))
+        if self.parent is not None:
+            self.parent._fresh()
+            _check(self.lib.pb2_problem_create_child(self.cls, self.parent.prob, ctypes.byref(md), ctypes.byref(self.prob)))
+        else:
+            _check(self.lib.pb2_problem_create(self.cls, device, ctypes.byref(md), ctypes.byref(self.prob)))
         rs, ci = c_int_p(), c_int_p()
         nnz, nrows = ctypes.c_longlong(), ctypes.c_longlong()
         _check(self.lib.pb2_problem_pattern(self.prob, ctypes.byref(rs), ctypes.byref(ci), ctypes.byref(nnz), ctypes.byref(nrows)))
@@ -245,6 +259,13 @@ class B200Assembly(CustomAssemblyBase):
         self._stale = False
         if device < 0:
             return                      # pattern-only problem: no device data to initialise
+        if self.parent is not None:
+            # nodal data are the parent's; only the class's own time info and parameters are set
+            self.ti = self.parent.ti
+            _check(self.lib.pb2_problem_set_time(self.prob, ctypes.byref(self.ti)))
+            _check(self.lib.pb2_problem_set_parameters(self.prob, self._dp(self._params), self.info.n_params))
+            self._last_flag = -1
+            return
         self.set_nodal_positions(0, mesh.node_pos)
         for t in range(1, self.info.n_hist_pos):
             self.set_nodal_positions(t, mesh.node_pos)
@@ -266,10 +287,18 @@ class B200Assembly(CustomAssemblyBase):
         nodal values and positions of the new mesh must be set again (set_nodal_values / set_dofs)"""
         if elements is not None or extra_pattern is not None:
             self._elements, self._extra_pattern = elements, extra_pattern
+        for c in self.children:         # children alias this problem's buffers: released first, to be rebuilt by the caller afterwards
+            c._release()
+            c._stale = True
         if self.prob:
             self.lib.pb2_problem_free(self.prob)
             self.prob = None
         self._create_problem(mesh if mesh is not None else self.mesh, dofmap if dofmap is not None else self.dofmap)
+
+    def _release(self):
+        if self.prob:
+            self.lib.pb2_problem_free(self.prob)
+            self.prob = None
 
     def _fresh(self):
         if self._stale:
@@ -315,6 +344,8 @@ class B200Assembly(CustomAssemblyBase):
         """oomph steady solve: all time weights zero, ntstorage 0 (src/elements.cpp:4583-4596)."""
         self.ti = TimeInfo()
         _check(self.lib.pb2_problem_set_time(self.prob, ctypes.byref(self.ti)))
+        for c in self.children:
+            c.set_steady()
 
     def set_unsteady(self, t: float, dt: float, dtprev: float, unsteady_steps_done: int, ntstorage: Optional[int] = None):
         """MultiTimeStepper weights (BDF1, BDF2, Newmark2; src/timestepper.cpp:31-80) + the _degr selection rule of
@@ -338,6 +369,8 @@ class B200Assembly(CustomAssemblyBase):
         ti.ntstorage = ntstorage
         self.ti = ti
         _check(self.lib.pb2_problem_set_time(self.prob, ctypes.byref(ti)))
+        for c in self.children:
+            c.set_unsteady(t, dt, dtprev, unsteady_steps_done, ntstorage)
 
     # ---- assembly -----------------------------------------------------------------------------
     def assemble(self, flag: int = 1, residual: str = "", parameter: Optional[str] = None, stream: int = 0):
@@ -347,6 +380,11 @@ class B200Assembly(CustomAssemblyBase):
         pi = -1 if parameter is None else self.param_names.index(parameter)
         _check(self.lib.pb2_problem_assemble(self.prob, ri, pi, flag, ctypes.c_void_p(stream)))
         self._last_flag = flag
+        # the element classes attached to this one add to the matrix just written (same stream: ordered after it); a class that
+        # does not know the residual / parameter contributes nothing
+        for c in self.children:
+            if residual in c.residual_names and (parameter is None or parameter in c.param_names):
+                c.assemble(flag=flag, residual=residual, parameter=parameter, stream=stream)
 
     def fetch(self, want_jacobian: bool = True, want_mass: bool = False):
         res = np.empty(self.n_dof)
@@ -519,7 +557,7 @@ class B200Assembly(CustomAssemblyBase):
                 np.ctypeslib.as_array(res, shape=(ne, nd)).copy())
 
     def launch_count(self) -> int:
-        return int(self.lib.pb2_problem_launch_count(self.prob))
+        return int(self.lib.pb2_problem_launch_count(self.prob)) + sum(c.launch_count() for c in self.children)
 
     def num_colours(self) -> int:
         return int(self.lib.pb2_problem_num_colours(self.prob))
@@ -568,6 +606,8 @@ class B200Assembly(CustomAssemblyBase):
         return res
 
     def close(self):
+        for c in getattr(self, "children", []):       # they alias this problem's device buffers
+            c._release()
         if getattr(self, "prob", None):
             self.lib.pb2_problem_free(self.prob)
             self.prob = None

@@ -54,6 +54,9 @@ ELEMENT_TYPES: Dict[str, ElementType] = {
     # BulkElementTri2dC2 = oomph TElement<2,3> (src/elements.hpp:990, src/elements.cpp:9844-9856): 6 nodes (vertices 0,1,2 then the
     # mid-side nodes 3: 0-1, 4: 1-2, 5: 2-0, Telements.h:575-621), C1 on the vertices, default scheme TGauss<2,3> with 7 points
     "Tri2dC2": ElementType("Tri2dC2", 2, 2, 6, 3, (0, 1, 2), 7),
+    # InterfaceElementLine1dC2 (src/elements.hpp:1435-2298): the three nodes of a Q9 / T6 edge in a 2D space; QElement<1,3> shapes,
+    # C1 on the end nodes, Gauss<1,3>
+    "Line1dC2": ElementType("Line1dC2", 2, 1, 3, 3, (0, 2), 3),
 }
 
 SPACE_ORDER = ("C2TB", "C2", "C1TB", "C1")  # nodal_data index order (src/codegen.cpp:2367-2380)

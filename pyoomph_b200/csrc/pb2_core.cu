@@ -137,6 +137,10 @@ struct pb2_problem
   cudaEvent_t ev_inputs = nullptr; // recorded on the legacy stream after every input update; assemblies on other streams wait for it
   double setup_seconds = 0.0;      // wall time of pb2_problem_create (colouring, pattern, maps, upload)
   // pattern-only problems (device < 0) keep the maps on the host for inspection (pb2_problem_host_maps)
+  int n_children = 0;              // child problems alive (they alias this problem's device buffers)
+  pb2_problem *parent = nullptr;   // child problem: another element class scattering into the parent's matrix, residual and nodal data
+  int *d_untouched_rows = nullptr; // residual rows no element of this problem writes (rows only a child class contributes to)
+  long long n_untouched_rows = 0;
   RawVec<int> h_elem_rowstart, h_elem_res;
   RawVec<uint8_t> h_off8;
   RawVec<uint16_t> h_off16;
@@ -220,7 +224,31 @@ static int upload(T **dptr, const RawVec<T> &v)
   return 0;
 }
 
+static int create_impl(pb2_class *cls, int device, const pb2_mesh_desc *m, pb2_problem *parent, pb2_problem **out);
+
 extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_desc *m, pb2_problem **out)
+{
+  return create_impl(cls, device, m, nullptr, out);
+}
+
+// A CHILD problem: elements of another class (interface elements on the bulk's boundary, src/elements.hpp:1435-2298) that live on the
+// parent's nodes and equations and scatter into the parent's CSR matrix and residual (the reference assembles all element classes of a
+// problem into one matrix, oomph-lib problem.cc:5332-5666).  The parent's pattern must contain every entry the child produces: create
+// the parent with them as extra pattern entries (pb2_mesh_desc.extra_*).  The child owns its schedule and position maps only; it
+// always ADDS (no first-touch stores): assemble the parent first, then its children, on the same stream.
+extern "C" int pb2_problem_create_child(pb2_class *cls, pb2_problem *parent, const pb2_mesh_desc *m, pb2_problem **out)
+{
+  *out = nullptr;
+  if (!parent) return fail("child problem needs a parent");
+  if (parent->parent) return fail("the parent of a child problem must be a root problem");
+  if (m->n_node != parent->n_node || m->n_dof != parent->n_dof) return fail("a child problem lives on the parent's nodes and equations: n_node / n_dof differ");
+  if (cls->table.info.nval != parent->nval || cls->table.info.nodal_dim != parent->dim) return fail("child and parent element classes must share the nodal record (fields, dimension)");
+  if (cls->table.info.n_hist_val > parent->T_val || cls->table.info.n_hist_pos > parent->T_pos) return fail("the child class reads more history levels than the parent stores");
+  if (m->n_extra != 0) return fail("a child problem has no pattern of its own");
+  return create_impl(cls, parent->device, m, parent, out);
+}
+
+static int create_impl(pb2_class *cls, int device, const pb2_mesh_desc *m, pb2_problem *parent, pb2_problem **out)
 {
   *out = nullptr;
   const pb2_class_info &ci = cls->table.info;
@@ -248,6 +276,8 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   };
   p->cls = cls;
   p->device = device;
+  p->parent = parent;
+  if (parent) parent->n_children++;
   p->n_elem = m->n_elem;
   p->n_node = m->n_node;
   p->n_dof = m->n_dof;
@@ -562,6 +592,12 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   // once and keeps the columns in a private buffer; rows whose element list equals the previous row's (the dofs of one node) reuse its
   // columns; then prefix sum and parallel copy.
   p->row_start.assign(nrow + 1, 0);
+  if (parent)
+  {
+    p->row_start = parent->row_start; // the child scatters into the parent's matrix
+    p->nnz = parent->nnz;
+  }
+  else
   {
     const int nth = omp_get_max_threads();
     std::vector<std::vector<int>> tcols(nth);
@@ -665,21 +701,32 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   else
     off16.assign((size_t)ne * nd * nd, (uint16_t)0xFFFF);
   const unsigned FIRST = p->map_bits == 8 ? 0x80u : 0x8000u;
-  std::vector<std::vector<int>> t_untouched(omp_get_max_threads());
+  std::vector<std::vector<int>> t_untouched(omp_get_max_threads()), t_untouched_rows(omp_get_max_threads());
+  const int *const col_base = parent ? parent->col_index.data() : p->col_index.data();
+  const bool child = parent != nullptr;
+  int missing_entries = 0;
 #pragma omp parallel
   {
     std::vector<int> firstq(maxlen + 1), loc_k(nd), loc_off(nd), prev_row_k;
     std::vector<int> &unt = t_untouched[omp_get_thread_num()];
+    std::vector<int> &untr = t_untouched_rows[omp_get_thread_num()];
     prev_row_k.reserve(64);
 #pragma omp for schedule(static, 4096)
     for (long long r = 0; r < nrow; r++)
     {
       const int rb = p->row_start[r], len = p->row_start[r + 1] - rb;
-      const int *cols = p->col_index.data() + rb;
+      const int *cols = col_base + rb;
       const int a0 = adj_start[r], a1 = adj_start[r + 1];
+      if (a0 == a1)
+      {
+        if (m->n_extra > 0) untr.push_back((int)r); // a row only other classes / ranks contribute to: its residual restarts from zero
+        if (m->n_extra > 0)
+          for (int i = 0; i < len; i++) unt.push_back(rb + i);
+        continue;
+      }
       // dofs of one node: same elements and same columns as the previous row => the same offsets and first touches; only the row
       // start differs.  (Not across the first row of a thread's block, and not when extra pattern entries are involved.)
-      const bool same = r > 0 && (r % 4096) != 0 && m->n_extra == 0 && len == p->row_start[r] - p->row_start[r - 1] && a1 - a0 == a0 - adj_start[r - 1] &&
+      const bool same = !child && r > 0 && (r % 4096) != 0 && m->n_extra == 0 && len == p->row_start[r] - p->row_start[r - 1] && a1 - a0 == a0 - adj_start[r - 1] &&
                         std::equal(adj.begin() + a0, adj.begin() + a1, adj.begin() + adj_start[r - 1]);
       if (same)
       {
@@ -709,21 +756,31 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
         int ir = -1, pos = 0;
         for (int s_ = 0; s_ < ns; s_++)
         {
-          while (cols[pos] < se[s_]) pos++; // every dof of an adjacent element is a column of this row
+          if (se[s_] == (int)r) ir = sk[s_];
+          while (pos < len && cols[pos] < se[s_]) pos++; // every dof of an adjacent element is a column of this row
+          if (pos >= len || cols[pos] != se[s_])
+          {
+            // only possible for a child: the parent's pattern lacks an entry this class produces
+#pragma omp atomic
+            missing_entries++;
+            pos = 0;
+            loc_k[s_] = -1;
+            continue;
+          }
           loc_k[s_] = sk[s_];
           loc_off[s_] = pos;
-          if (se[s_] == (int)r) ir = sk[s_];
         }
         // ir >= 0: r is a dof of q (that is what adjacency means)
         const size_t base = ((size_t)q * nd + ir) * nd;
         for (int s_ = 0; s_ < ns; s_++)
         {
+          if (loc_k[s_] < 0) continue;
           const int off = loc_off[s_];
           unsigned code = (unsigned)off;
           if (firstq[off] < 0)
           {
             firstq[off] = (int)q;
-            code |= FIRST;
+            if (!child) code |= FIRST; // a child adds to what the parent (and earlier children) wrote
           }
           if (p->map_bits == 8)
             off8[base + loc_k[s_]] = (uint8_t)code;
@@ -731,7 +788,7 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
             off16[base + loc_k[s_]] = (uint16_t)code;
         }
         elem_rowstart[(size_t)q * nd + ir] = rb;
-        elem_res[(size_t)q * nd + ir] = a_ == a0 ? ~(int)r : (int)r;
+        elem_res[(size_t)q * nd + ir] = (a_ == a0 && !child) ? ~(int)r : (int)r;
       }
       if (m->n_extra > 0)
         for (int i = 0; i < len; i++)
@@ -742,6 +799,23 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
   sorted_k.clear();
   std::vector<int>().swap(adj);
   std::vector<int>().swap(adj_start);
+  if (missing_entries > 0)
+  {
+    pb2_problem_free(p);
+    return fail("the parent's CSR pattern lacks " + std::to_string(missing_entries) + " entries this element class produces: create the parent with them as extra pattern entries");
+  }
+  if (m->n_extra > 0)
+  {
+    std::vector<int> untr;
+    for (auto &v : t_untouched_rows) untr.insert(untr.end(), v.begin(), v.end());
+    std::sort(untr.begin(), untr.end());
+    p->n_untouched_rows = (long long)untr.size();
+    if (dev && upload(&p->d_untouched_rows, untr))
+    {
+      pb2_problem_free(p); // releases whatever has been uploaded so far
+      return 1;
+    }
+  }
   if (m->n_extra > 0)
   {
     // CSR positions no local element writes (extra pattern entries): re-zeroed before every assembly
@@ -797,6 +871,26 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
     pb2_problem_free(p);
     return 1;
   }
+  if (parent)
+  {
+    // nodal data, dof vector and outputs are the parent's (history strides included: the child reads the parent's levels)
+    p->T_val = parent->T_val;
+    p->T_pos = parent->T_pos;
+    p->d_node_pos = parent->d_node_pos;
+    p->d_node_lagr = parent->d_node_lagr;
+    p->d_node_val = parent->d_node_val;
+    p->d_residual = parent->d_residual;
+    p->d_dofs = parent->d_dofs;
+    p->d_jac = parent->d_jac;
+    CUDA_OK(cudaHostAlloc((void **)&p->h_status, sizeof(int), cudaHostAllocMapped));
+    *p->h_status = 0;
+    CUDA_OK(cudaHostGetDevicePointer((void **)&p->d_status, p->h_status, 0));
+    CUDA_OK(cudaEventCreateWithFlags(&p->ev_inputs, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(p->ev_inputs, 0));
+    p->setup_seconds = omp_get_wtime() - t_create0;
+    *out = p;
+    return 0;
+  }
   const size_t npos = (size_t)p->T_pos * m->n_node * ci.nodal_dim, nlag = (size_t)m->n_node * ci.nodal_dim,
                nvals = (size_t)p->T_val * m->n_node * std::max(1, ci.nval);
   CUDA_OK(cudaMalloc((void **)&p->d_node_pos, npos * sizeof(double)));
@@ -826,12 +920,19 @@ extern "C" int pb2_problem_create(pb2_class *cls, int device, const pb2_mesh_des
 extern "C" void pb2_problem_free(pb2_problem *p)
 {
   if (!p) return;
+  if (p->parent) p->parent->n_children--; // children are released before their parent
   if (p->device < 0)
   {
     delete p;
     return;
   }
   cudaSetDevice(p->device);
+  if (p->parent)
+  {
+    // aliases of the parent's buffers are not this problem's to release
+    p->d_node_pos = p->d_node_lagr = p->d_node_val = p->d_residual = p->d_jac = p->d_dofs = nullptr;
+  }
+  cudaFree(p->d_untouched_rows);
   cudaFree(p->d_elem_nodes);
   cudaFree(p->d_elem_eqn);
   cudaFree(p->d_elem_rowstart);
@@ -870,7 +971,7 @@ extern "C" void pb2_problem_free(pb2_problem *p)
 extern "C" int pb2_problem_pattern(pb2_problem *p, const int **row_start, const int **column_index, long long *nnz, long long *n_rows)
 {
   if (row_start) *row_start = p->row_start.data();
-  if (column_index) *column_index = p->col_index.data();
+  if (column_index) *column_index = p->parent ? p->parent->col_index.data() : p->col_index.data();
   if (nnz) *nnz = p->nnz;
   if (n_rows) *n_rows = p->n_dof;
   return 0;
@@ -1062,6 +1163,15 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
     p->launches_last++;
     p->launches_total++;
   }
+  if (p->n_untouched_rows > 0 && p->n_children > 0 && kind == 0)
+  {
+    // residual rows only a child class contributes to restart from zero with the parent's assembly
+    const int bs = 256;
+    pb2_zero_positions<<<(unsigned)((p->n_untouched_rows + bs - 1) / bs), bs, 0, (cudaStream_t)cuda_stream>>>(a.residual, nullptr, p->d_untouched_rows, p->n_untouched_rows);
+    CUDA_OK(cudaGetLastError());
+    p->launches_last++;
+    p->launches_total++;
+  }
   pb2_kernel_cfg cfg;
   int rc = p->cls->table.query(kind, residual_index, param_index, flag, &cfg);
   if (rc != 0)
@@ -1219,6 +1329,12 @@ extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int para
 {
   NEED_DEVICE(p);
   if (flag > 2u) return fail("flag must be 0, 1 or 2");
+  if (p->parent)
+  {
+    // a child adds to the matrices its parent assembled (flag 2: the parent's mass matrix must exist)
+    if (flag == 2u && !p->parent->d_mass) return fail("assemble the parent with flag 2 before its children: no mass matrix yet");
+    return run_routine(p, 0, residual_index, param_index, flag, p->parent->d_jac, p->parent->d_mass, nullptr, cuda_stream);
+  }
   if (flag == 2u && !p->d_mass) CUDA_OK(cudaMalloc((void **)&p->d_mass, std::max<size_t>(1, p->nnz) * sizeof(double)));
   return run_routine(p, 0, residual_index, param_index, flag, p->d_jac, p->d_mass, nullptr, cuda_stream);
 }
@@ -1243,6 +1359,12 @@ extern "C" int pb2_problem_assemble_hessian(pb2_problem *p, int residual_index, 
   }
   CUDA_OK(cudaMemcpyAsync(p->d_hvec, Y, (size_t)n_vec * p->n_dof * sizeof(double), cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream));
   long long launches = 0;
+  if (p->parent)
+  {
+    // a child has no first-touch stores: its Hessian contribution (kept in its own buffers, to be added to the parent's) starts from zero
+    CUDA_OK(cudaMemsetAsync(p->d_hess, 0, (size_t)n_vec * std::max<long long>(1, p->nnz) * sizeof(double), (cudaStream_t)cuda_stream));
+    if (flag == 2u) CUDA_OK(cudaMemsetAsync(p->d_hessM, 0, (size_t)n_vec * std::max<long long>(1, p->nnz) * sizeof(double), (cudaStream_t)cuda_stream));
+  }
   for (int v = 0; v < n_vec; v++)
   {
     const int rc = run_routine(p, hkind, residual_index, -1, flag, p->d_hess + (size_t)v * p->nnz, p->d_hessM + (size_t)v * p->nnz, p->d_hvec + (size_t)v * p->n_dof, cuda_stream);
@@ -1283,7 +1405,7 @@ extern "C" int pb2_problem_hessian_vector_products(pb2_problem *p, int residual_
   if (rc) return rc;
   if (!p->d_row_start)
   {
-    if (upload(&p->d_row_start, p->row_start) || upload(&p->d_col_index, p->col_index)) return 1;
+    if (upload(&p->d_row_start, p->row_start) || upload(&p->d_col_index, p->parent ? p->parent->col_index : p->col_index)) return 1;
   }
   double *d_x = nullptr, *d_y = nullptr;
   CUDA_OK(cudaMalloc((void **)&d_x, std::max<long long>(1, p->n_dof) * sizeof(double)));
@@ -1411,7 +1533,7 @@ extern "C" int pb2_problem_device_pattern(pb2_problem *p, int **row_start, int *
   NEED_DEVICE(p);
   if (!p->d_row_start)
   {
-    if (upload(&p->d_row_start, p->row_start) || upload(&p->d_col_index, p->col_index)) return 1;
+    if (upload(&p->d_row_start, p->row_start) || upload(&p->d_col_index, p->parent ? p->parent->col_index : p->col_index)) return 1;
   }
   if (row_start) *row_start = p->d_row_start;
   if (column_index) *column_index = p->d_col_index;

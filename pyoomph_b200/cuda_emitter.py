@@ -80,13 +80,36 @@ def triangle_shape_tables(order: int, knots):
 TRIANGLE_NODE_COORDS = [(1.0, 0.0), (0.0, 1.0), (0.0, 0.0), (0.5, 0.5), (0.0, 0.5), (0.5, 0.0)]    # Telements.h:575-621
 
 
+def gauss_rule_1d():
+    """Literal oomph table Gauss<1,3> (integral.cc:50-53; these knots are the correct ones)."""
+    return [(-0.774596669241483,), (0.0,), (0.774596669241483,)], [5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0]
+
+
+def line_shape_tables(order: int, knots):
+    """QElement<1,3> / QElement<1,2>: the 1D Lagrange polynomials themselves (shape.h:604-650)"""
+    psi, dpsi = [], []
+    for (s0,) in knots:
+        P, D = _lag(order, s0)
+        psi.append(list(P))
+        dpsi.append([(d,) for d in D])
+    return psi, dpsi
+
+
 def element_rule(et):
     """(knots, weights) of the element type's default integration scheme"""
-    return tgauss_rule() if et.name.startswith("Tri") else gauss_rule(et.nodal_dim)
+    if et.name.startswith("Tri"):
+        return tgauss_rule()
+    if et.elem_dim == 1:
+        return gauss_rule_1d()
+    return gauss_rule(et.nodal_dim)
 
 
 def element_shape_tables(et, order: int, knots):
-    return triangle_shape_tables(order, knots) if et.name.startswith("Tri") else shape_tables(et.nodal_dim, order, knots)
+    if et.name.startswith("Tri"):
+        return triangle_shape_tables(order, knots)
+    if et.elem_dim == 1:
+        return line_shape_tables(order, knots)
+    return shape_tables(et.nodal_dim, order, knots)
 
 
 def element_node_coords(et):
@@ -94,7 +117,7 @@ def element_node_coords(et):
     if et.name.startswith("Tri"):
         return list(TRIANGLE_NODE_COORDS)
     grid = (-1.0, 0.0, 1.0)
-    return [tuple(grid[(l // 3 ** d) % 3] for d in range(et.nodal_dim)) for l in range(et.nnode)]
+    return [tuple(grid[(l // 3 ** d) % 3] for d in range(et.elem_dim)) for l in range(et.nnode)]
 
 
 def _lag(order: int, s: float):
@@ -181,6 +204,7 @@ class CudaEmitter:
         self.name = name
         self.et = code.etype
         self.dim = code.nodal_dim
+        self.edim = self.et.elem_dim          # local coordinates of the element: < dim for interface elements (lines in 2D)
         self.NN = self.et.nnode
         self.NN1 = self.et.nnode_C1
         self.NIPT = self.et.n_int_pt
@@ -310,10 +334,10 @@ class CudaEmitter:
         # per-point block
         poff = 0
         plan["gg"] = poff
-        poff += dim * dim
+        poff += self.edim * dim
         if need_lagr:
             plan["ggL"] = poff
-            poff += dim * dim
+            poff += self.edim * dim
         ncoef = len(form.slots)
         jkeys = sorted(form.J.keys()) if what >= 1 else []
         mkeys = sorted(form.M.keys()) if what >= 2 else []
@@ -381,9 +405,9 @@ class CudaEmitter:
         o.append("// reference-element tables at the oomph Gauss points (integral.cc literals, shape.h polynomials)")
         o.append("__constant__ double c_w[%d] = {%s};" % (self.NIPT, arr(w)))
         o.append("__constant__ double c_psi2[%d] = {%s};" % (self.NIPT * self.NN, arr(v for p in psi2 for v in p)))
-        o.append("__constant__ double c_dpsi2[%d] = {%s};" % (self.NIPT * self.NN * self.dim, arr(v for p in dpsi2 for l in p for v in l)))
+        o.append("__constant__ double c_dpsi2[%d] = {%s};" % (self.NIPT * self.NN * self.edim, arr(v for p in dpsi2 for l in p for v in l)))
         o.append("__constant__ double c_psi1[%d] = {%s};" % (self.NIPT * self.NN1, arr(v for p in psi1 for v in p)))
-        o.append("__constant__ double c_dpsi1[%d] = {%s};" % (self.NIPT * self.NN1 * self.dim, arr(v for p in dpsi1 for l in p for v in l)))
+        o.append("__constant__ double c_dpsi1[%d] = {%s};" % (self.NIPT * self.NN1 * self.edim, arr(v for p in dpsi1 for l in p for v in l)))
         o.append("__device__ const double g_tables[%d] = {%s};" % (self._tables_smem_size(), arr(
             [v for p in psi2 for v in p] + [v for p in dpsi2 for l in p for v in l] + [v for p in psi1 for v in p] + [v for p in dpsi1 for l in p for v in l] + t1_smem)))
         if self.dim == 3:
@@ -413,7 +437,7 @@ class CudaEmitter:
         """doubles of shape tables staged in shared memory (needed by phase 1 always, phase 2 in smem mode) for npt points
         (default: the integration points)"""
         npt = self.NIPT if npt is None else npt
-        return npt * (self.NN * (1 + self.dim) + self.NN1 * (1 + self.dim)) + (npt * 18 if self.dim == 3 else 0)
+        return npt * (self.NN * (1 + self.edim) + self.NN1 * (1 + self.edim)) + (npt * 18 if self.dim == 3 else 0)
 
     def _emit_kernel(self, o: List[str], rp: RoutinePlan, what: int):
         code, dim, NN, NN1, NIPT = self.code, self.dim, self.NN, self.NN1, self.NIPT
@@ -442,9 +466,9 @@ class CudaEmitter:
         w("  extern __shared__ double smem[];")
         w("  double* const s_psi2 = smem;")
         w("  double* const s_dpsi2 = s_psi2 + %d;" % (NIPT * NN))
-        w("  double* const s_psi1 = s_dpsi2 + %d;" % (NIPT * NN * dim))
+        w("  double* const s_psi1 = s_dpsi2 + %d;" % (NIPT * NN * self.edim))
         w("  double* const s_dpsi1 = s_psi1 + %d;" % (NIPT * NN1))
-        w("  const double* const s_t1d = s_dpsi1 + %d; (void)s_t1d;" % (NIPT * NN1 * dim))
+        w("  const double* const s_t1d = s_dpsi1 + %d; (void)s_t1d;" % (NIPT * NN1 * self.edim))
         w("  double* const s_el = smem + %d;" % tab_n)
         w("  int* const s_rowstart = (int*)(smem + %d);" % (tab_n + self.EPB * ELS))
         w("  int* const s_resmap = s_rowstart + %d;" % (self.EPB * self.ndof))
@@ -581,9 +605,9 @@ class CudaEmitter:
         w("  extern __shared__ double smem[];")
         w("  double* const s_psi2 = smem;")
         w("  double* const s_dpsi2 = s_psi2 + %d;" % (NIPT * NN))
-        w("  double* const s_psi1 = s_dpsi2 + %d;" % (NIPT * NN * dim))
+        w("  double* const s_psi1 = s_dpsi2 + %d;" % (NIPT * NN * self.edim))
         w("  double* const s_dpsi1 = s_psi1 + %d;" % (NIPT * NN1))
-        w("  const double* const s_t1d = s_dpsi1 + %d; (void)s_t1d;" % (NIPT * NN1 * dim))
+        w("  const double* const s_t1d = s_dpsi1 + %d; (void)s_t1d;" % (NIPT * NN1 * self.edim))
         w("  double* const s_el = smem + %d;" % tab_n)
         w("  const int tid = threadIdx.x;")
         w("  for (int i = tid; i < %d; i += %d) smem[i] = g_tables[i];" % (tab_n, NT))
@@ -644,9 +668,9 @@ class CudaEmitter:
         w("  extern __shared__ double smem[];")
         w("  double* const s_psi2 = smem;")
         w("  double* const s_dpsi2 = s_psi2 + %d;" % (NPT * NN))
-        w("  double* const s_psi1 = s_dpsi2 + %d;" % (NPT * NN * dim))
+        w("  double* const s_psi1 = s_dpsi2 + %d;" % (NPT * NN * self.edim))
         w("  double* const s_dpsi1 = s_psi1 + %d;" % (NPT * NN1))
-        w("  const double* const s_t1d = s_dpsi1 + %d; (void)s_t1d;" % (NPT * NN1 * dim))
+        w("  const double* const s_t1d = s_dpsi1 + %d; (void)s_t1d;" % (NPT * NN1 * self.edim))
         w("  double* const s_el = smem + %d;" % tab_n)
         w("  const int tid = threadIdx.x;")
         w("  for (int i = tid; i < %d; i += %d) smem[i] = %s[i];" % (tab_n, NT, "g_tables_nodes" if at_nodes else "g_tables"))
@@ -744,9 +768,9 @@ class CudaEmitter:
         w("  extern __shared__ double smem[];")
         w("  double* const s_psi2 = smem;")
         w("  double* const s_dpsi2 = s_psi2 + %d;" % (NIPT * NN))
-        w("  double* const s_psi1 = s_dpsi2 + %d;" % (NIPT * NN * dim))
+        w("  double* const s_psi1 = s_dpsi2 + %d;" % (NIPT * NN * self.edim))
         w("  double* const s_dpsi1 = s_psi1 + %d;" % (NIPT * NN1))
-        w("  const double* const s_t1d = s_dpsi1 + %d; (void)s_t1d;" % (NIPT * NN1 * dim))
+        w("  const double* const s_t1d = s_dpsi1 + %d; (void)s_t1d;" % (NIPT * NN1 * self.edim))
         w("  (void)s_psi1; (void)s_dpsi1;")
         w("  const int tid = threadIdx.x;")
         w("  for (int i = tid; i < %d; i += %d) smem[i] = g_tables[i];" % (tab_n, NT))
@@ -1108,8 +1132,9 @@ class CudaEmitter:
         code, dim, NN, NN1, NIPT = self.code, self.dim, self.NN, self.NN1, self.NIPT
         form = rp.form
         w = o.append
-        w("      const double* ps2 = s_psi2 + ipt * %d; const double* dp2 = s_dpsi2 + ipt * %d;" % (NN, NN * dim))
-        w("      const double* ps1 = s_psi1 + ipt * %d; const double* dp1 = s_dpsi1 + ipt * %d;" % (NN1, NN1 * dim))
+        edim = self.edim
+        w("      const double* ps2 = s_psi2 + ipt * %d; const double* dp2 = s_dpsi2 + ipt * %d;" % (NN, NN * edim))
+        w("      const double* ps1 = s_psi1 + ipt * %d; const double* dp1 = s_dpsi1 + ipt * %d;" % (NN1, NN1 * edim))
         w("      (void)ps1; (void)dp1; (void)ps2;")
         # (field, kind) -> derivatives needed, for all atoms of the form
         needed: Dict[Tuple[str, tuple], set] = {}
@@ -1173,6 +1198,8 @@ class CudaEmitter:
             w("      const double dX = c_w[ipt] * detL;")
         # interpolation
         names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "a.ti.t[0]", ex.pi: "3.14159265359"}
+        for i_, ns_ in enumerate(ex.NORMAL):
+            names[ns_] = "nrm%d" % i_          # computed by _emit_geometry on interface elements
         for k, p in enumerate(code.global_params):
             names[code._param_syms[p]] = "a.params[%d]" % k
         # local-derivative sums per (field, kind)
@@ -1194,15 +1221,15 @@ class CudaEmitter:
                 if want_val:
                     decl.append("v_%s = 0.0" % tag)
                 if want_grad:
-                    decl += ["s%d_%s = 0.0" % (b, tag) for b in range(dim)]
+                    decl += ["s%d_%s = 0.0" % (b, tag) for b in range(edim)]
                 w("      double %s;" % ", ".join(decl))
                 w("      #pragma unroll%s" % self._node_unroll(nn))
                 w("      for (int l = 0; l < %d; ++l) { const double u = %s;" % (nn, srcexpr))
                 if want_val:
                     w("        v_%s += u * %s[l];" % (tag, ps))
                 if want_grad:
-                    for b in range(dim):
-                        w("        s%d_%s += u * %s[l * %d + %d];" % (b, tag, dp, dim, b))
+                    for b in range(edim):
+                        w("        s%d_%s += u * %s[l * %d + %d];" % (b, tag, dp, edim, b))
                 w("      }")
             for d in sorted(derivs):
                 at = AtomInfo(f, kind[1] if kind[0] == "dt" else 0, kind[2] if kind[0] == "dt" else "", d, kind[1] if kind[0] == "cur" else 0)
@@ -1214,7 +1241,7 @@ class CudaEmitter:
                 else:
                     g = "gg" if d[1] == "x" else "ggL"
                     i = int(d[2:])
-                    w("      const double %s = %s;" % (cn, " + ".join("%s%d%d * s%d_%s" % (g, b, i, b, tag) for b in range(dim))))
+                    w("      const double %s = %s;" % (cn, " + ".join("%s%d%d * s%d_%s" % (g, b, i, b, tag) for b in range(edim))))
         for sch in ("BDF1", "BDF2", "Newmark2", "BDF2_degr", "Newmark2_degr"):
             names[sp.Symbol("W__%s__1" % sch, real=True)] = "a.ti.w_dt_%s[0]" % sch
         names[sp.Symbol("W__Newmark2__2", real=True)] = "a.ti.w_d2t_Newmark2[0]"
@@ -1250,26 +1277,31 @@ class CudaEmitter:
         return "" if nn <= 9 else " %d" % int(os.environ.get("PB2_NODE_UNROLL", "3"))
 
     def _emit_geometry(self, o: List[str], plan, src: str, gname: str, detname: str, sums_done: bool = False):
-        """Restates fill_shape_info_at_s for el_dim==nodal_dim (src/elements.cpp:3604-3626 tangents, :3677-3703 2D
-        metric/inverse, :3804-3836 3D) with the same operation order; stores gab_gai[b][i] to the point block."""
-        dim, NN = self.dim, self.NN
+        """Restates fill_shape_info_at_s (src/elements.cpp:3604-3626 tangents; metric, inverse and gab_gai for el_dim 1 :3651-3672,
+        2 :3677-3703, 3 :3804-3836) with the same operation order; stores gab_gai[b][i] to the point block.  el_dim < nodal_dim
+        (interface elements): the same metric form gives the surface gradient, sqrt(det) the surface measure."""
+        dim, NN, edim = self.dim, self.NN, self.edim
         w = o.append
         t = "t_" + gname
         if not sums_done:
-            w("      double %s;" % ", ".join("%s%d%d = 0.0" % (t, a, i) for a in range(dim) for i in range(dim)))
+            w("      double %s;" % ", ".join("%s%d%d = 0.0" % (t, a, i) for a in range(edim) for i in range(dim)))
             w("      #pragma unroll%s" % self._node_unroll(NN))
             w("      for (int l = 0; l < %d; ++l) {" % NN)
             for i in range(dim):
-                for a in range(dim):
-                    w("        %s%d%d += E[%d + l * %d + %d] * dp2[l * %d + %d];" % (t, a, i, plan[src], dim, i, dim, a))
+                for a in range(edim):
+                    w("        %s%d%d += E[%d + l * %d + %d] * dp2[l * %d + %d];" % (t, a, i, plan[src], dim, i, edim, a))
             w("      }")
-        for al in range(dim):
-            for be in range(dim):
+        for al in range(edim):
+            for be in range(edim):
                 terms = ["%s%d%d * %s%d%d" % (t, al, i, t, be, i) for i in range(dim)]
                 # amet += in order i=0.. starting from 0.0
                 w("      const double am_%s%d%d = %s;" % (gname, al, be, " + ".join(terms)))
         am = lambda a, b: "am_%s%d%d" % (gname, a, b)
-        if dim == 2:
+        if edim == 1:
+            w("      const double det_%s = %s;" % (gname, am(0, 0)))
+            w("      const double rdet_%s = 1.0 / det_%s;" % (gname, gname))
+            up = {(0, 0): "rdet_%s" % gname}
+        elif edim == 2:
             w("      const double det_%s = %s * %s - %s * %s;" % (gname, am(0, 0), am(1, 1), am(0, 1), am(1, 0)))
             # one IEEE reciprocal instead of the reference's four divisions by det (src/elements.cpp:3690-3703): <=1 ulp apart
             w("      const double rdet_%s = 1.0 / det_%s;" % (gname, gname))
@@ -1294,11 +1326,15 @@ class CudaEmitter:
             }
         for (al, be), e in up.items():
             w("      const double up_%s%d%d = %s;" % (gname, al, be, e))
-        for b in range(dim):
+        for b in range(edim):
             for i in range(dim):
-                w("      const double %s%d%d = %s;" % (gname, b, i, " + ".join("up_%s%d%d * %s%d%d" % (gname, a_, b, t, a_, i) for a_ in range(dim))))
+                w("      const double %s%d%d = %s;" % (gname, b, i, " + ".join("up_%s%d%d * %s%d%d" % (gname, a_, b, t, a_, i) for a_ in range(edim))))
                 w("      P[%d] = %s%d%d;" % (plan[gname] + b * dim + i, gname, b, i))
         w("      const double %s = sqrt(det_%s);" % (detname, gname))
+        if edim == 1 and dim == 2 and gname == "gg":
+            # unit normal of a line element (BulkElementBase::get_normal_at_s, src/elements.cpp:1730-1752): (-t_y, t_x) / |t|
+            w("      const double nrm_len = (det_gg < 1e-20) ? 1.0 : sqrt(det_gg);")
+            w("      const double nrm0 = -%s01 / nrm_len, nrm1 = %s00 / nrm_len; (void)nrm0; (void)nrm1;" % (t, t))
 
     def _group_pairs(self, form: ResidualForm, g: RowGroup, coef):
         fields = [f for f in g.fields if any(s.field == f for s in form.slots)]
@@ -1436,9 +1472,9 @@ class CudaEmitter:
         need_x = any(s.deriv.startswith("dx") for s in form.slots if s.field in fields) or any(a_.startswith("dx") for (F, G), l in pairs.items() for (_, a_) in l)
         need_X = any(s.deriv.startswith("dX") for s in form.slots if s.field in fields) or any(a_.startswith("dX") for (F, G), l in pairs.items() for (_, a_) in l)
         if need_x:
-            w("          " + " ".join("const double gg%d%d = P[%d];" % (b, i, plan["gg"] + b * dim + i) for b in range(dim) for i in range(dim)))
+            w("          " + " ".join("const double gg%d%d = P[%d];" % (b, i, plan["gg"] + b * dim + i) for b in range(self.edim) for i in range(dim)))
         if need_X:
-            w("          " + " ".join("const double ggL%d%d = P[%d];" % (b, i, plan["ggL"] + b * dim + i) for b in range(dim) for i in range(dim)))
+            w("          " + " ".join("const double ggL%d%d = P[%d];" % (b, i, plan["ggL"] + b * dim + i) for b in range(self.edim) for i in range(dim)))
         if sf2:
             w("          " + " ".join("const double tL1%d = c_t1d[ipt * 12 + %d]; const double tD1%d = c_t1d[ipt * 12 + %d];" % (n, 6 + n, n, 9 + n) for n in range(3)))
         tp = self.tensor_columns and any(code.fields[G].space != "C1" for (F_, G) in pairs)
@@ -1454,14 +1490,14 @@ class CudaEmitter:
         w("            const double T_d0 = %s[ipt * %d + lt]; (void)T_d0;" % (sps, nn_g))
         test_derivs = {s.deriv for s in form.slots if s.field in fields}
         if any(d != "d0" for d in test_derivs):
-            for b in range(dim):
-                w("            const double Ts%d = %s[(ipt * %d + lt) * %d + %d];" % (b, sdp, nn_g, dim, b))
+            for b in range(self.edim):
+                w("            const double Ts%d = %s[(ipt * %d + lt) * %d + %d];" % (b, sdp, nn_g, self.edim, b))
         for d in sorted(test_derivs):
             if d == "d0":
                 continue
             gn = "gg" if d[1] == "x" else "ggL"
             i = int(d[2:])
-            w("            const double T_%s = %s;" % (d, " + ".join("%s%d%d * Ts%d" % (gn, b, i, b) for b in range(dim))))
+            w("            const double T_%s = %s;" % (d, " + ".join("%s%d%d * Ts%d" % (gn, b, i, b) for b in range(self.edim))))
         for F in fields:
             fslots = [(si, s) for si, s in enumerate(form.slots) if s.field == F]
             if with_res:
@@ -1484,17 +1520,17 @@ class CudaEmitter:
                     w("            const double W_%s_%s_%s = %s;" % (F, G, a_, " + ".join(
                         "T_%s * P[%d]" % (form.slots[si].deriv, coff[(si, G, a_)]) for si in sis)))
                 have_s = False
-                sterms = {b: [] for b in range(dim)}
+                sterms = {b: [] for b in range(self.edim)}
                 for a_ in sorted(by_atom):
                     if a_ == "d0":
                         continue
                     gn = "gg" if a_[1] == "x" else "ggL"
                     i = int(a_[2:])
-                    for b in range(dim):
+                    for b in range(self.edim):
                         sterms[b].append("W_%s_%s_%s * %s%d%d" % (F, G, a_, gn, b, i))
                     have_s = True
                 if have_s:
-                    for b in range(dim):
+                    for b in range(self.edim):
                         w("            const double Ws%d_%s_%s = %s;" % (b, F, G, " + ".join(sterms[b])))
                 if Gs == "C1":
                     tp, td = ("s_psi1", "s_dpsi1") if self.table_source == "smem" else ("c_psi1", "c_dpsi1")
@@ -1554,8 +1590,8 @@ class CudaEmitter:
                 if "d0" in by_atom:
                     parts.append(("W_%s_%s_d0" % (F, G), "%s[ipt * %d + c]" % (tp, nnG)))
                 if have_s:
-                    for b in range(dim):
-                        parts.append(("Ws%d_%s_%s" % (b, F, G), "%s[(ipt * %d + c) * %d + %d]" % (td, nnG, dim, b)))
+                    for b in range(self.edim):
+                        parts.append(("Ws%d_%s_%s" % (b, F, G), "%s[(ipt * %d + c) * %d + %d]" % (td, nnG, self.edim, b)))
                 accname = "acc[%d + k * %d + c]" % (base[(F, G)], nnG)
                 expr = accname
                 for (wn, tn) in parts:          # one DFMA per term, accumulated in place

@@ -11,7 +11,7 @@ Scaling/non-dimensionalisation factors of the reference are all 1 here (no units
 from __future__ import annotations
 
 from .codegen import Equations
-from .expressions import (Weak, cartesian, div, grad, identity_matrix, material_derivative, partial_t, rational_num, sym, trace, var,
+from .expressions import (Weak, cartesian, div, dot, grad, identity_matrix, material_derivative, partial_t, rational_num, sym, trace, var,
                           var_and_test, weak)
 
 
@@ -182,3 +182,66 @@ class SpatialErrorEstimator(Equations):
     def define_additional_functions(self):
         for f in self.fluxes:
             self.add_spatial_error_estimator(f() if callable(f) else f)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Interface equations: element classes on the boundary edges of a bulk mesh (InterfaceEquations, pyoomph/generic/codegen.py;
+# interface element classes src/elements.hpp:1435-2298).  They see the bulk fields at their nodes under the same names and nodal
+# indices, add their own interface fields behind them, integrate with the surface measure, and grad / div are the surface operators.
+# ---------------------------------------------------------------------------------------------------------------------------------
+class DeclareFields(Equations):
+    """fields that exist in the nodal record without a residual of their own on this element class: the bulk fields an interface class
+    reads or merely skips over, or -- on the bulk side -- the slots of the interface fields (the reference resizes the nodal Data of
+    the interface nodes instead, index_of_first_value_assigned_by_face_element, src/elements.cpp:12107-12193)"""
+
+    def __init__(self, **fields):
+        super().__init__()
+        self.fields = dict(fields)          # name -> space; a name ending in "*" is a vector field
+
+    def define_fields(self):
+        for n, sp_ in self.fields.items():
+            if n.endswith("*"):
+                self.define_vector_field(n[:-1], sp_)
+            else:
+                self.define_scalar_field(n, sp_)
+
+
+class RobinBC(Equations):
+    """alpha*(u - u_ext) flux through the boundary (Neumann for alpha*u_ext alone): pyoomph/equations/poisson.py PoissonFarFieldMonopoleCondition
+    / NeumannBC family; the interface elements of BASELINE config 1's tutorial script"""
+
+    def __init__(self, name: str = "u", alpha=1, external=0, flux=0):
+        super().__init__()
+        self.name, self.alpha, self.external, self.flux = name, alpha, external, flux
+
+    def define_fields(self):
+        self.define_scalar_field(self.name, "C2")
+
+    def define_residuals(self):
+        u, u_test = var_and_test(self.name)
+        ext = self.external() if callable(self.external) else self.external
+        self.add_residual(weak(self.alpha * (u - ext) - self.flux, u_test))
+
+
+class FreeSurfaceOnFixedMesh(Equations):
+    """The interface terms of NavierStokesFreeSurface (pyoomph/equations/navier_stokes.py:520-676) on a mesh that does not move:
+    surface tension  sigma * div_S(v)  on the velocity test functions, and the no-penetration condition  u.n = 0  imposed by a
+    Lagrange multiplier field that lives on the interface nodes (the kinematic condition with the mesh velocity set to zero).
+    Uses the surface divergence, the unit normal and an interface field: everything an interface element adds except the
+    coordinate derivatives of the normal (moving meshes)."""
+
+    def __init__(self, surface_tension=1.0, velocity_name: str = "velocity", pressure_name: str = "pressure", lagrange_name: str = "_kin_bc"):
+        super().__init__()
+        self.sigma, self.velocity_name, self.pressure_name, self.lagrange_name = surface_tension, velocity_name, pressure_name, lagrange_name
+
+    def define_fields(self):
+        self.define_vector_field(self.velocity_name, "C2")
+        self.define_scalar_field(self.pressure_name, "C1")      # bulk field: only its slot in the nodal record matters here
+        self.define_scalar_field(self.lagrange_name, "C2")
+
+    def define_residuals(self):
+        u, v = var_and_test(self.velocity_name)
+        l, ltest = var_and_test(self.lagrange_name)
+        n = var("normal")
+        self.add_residual(weak(self.sigma, div(v)))
+        self.add_residual(weak(dot(u, n), ltest) + weak(l, dot(n, v)))

@@ -27,6 +27,9 @@ TIME = sp.Symbol("t", real=True)
 # measures: Eulerian dx / Lagrangian dX  (GiNaCSpatialIntegralSymbol, src/codegen.cpp:7562)
 DX_EUL = sp.Symbol("M__dx", real=True)
 DX_LAG = sp.Symbol("M__dX", real=True)
+# unit normal of an interface element at the integration point (var("normal"); GiNaCNormalSymbol, src/codegen.cpp:7780-7823; printed as
+# shapeinfo->normal[i] by the reference)
+NORMAL = sp.symbols("NRM__0 NRM__1 NRM__2", real=True)
 
 DIRS = ("x", "y", "z")
 
@@ -96,6 +99,10 @@ def var(arg: Union[str, Sequence[str]]):
     code = _Context.current()
     if arg == "time":
         return TIME
+    if arg == "normal":
+        if code.etype.elem_dim >= code.nodal_dim:
+            raise RuntimeError("var(\"normal\") is defined on interface elements only")
+        return sp.Matrix(list(NORMAL[:code.nodal_dim]) + _padding(code, NORMAL[:code.nodal_dim]))
     comps = _vector_components(code, arg)
     if comps is not None:
         return sp.Matrix([_field(c) for c in comps] + _padding(code, comps))

@@ -166,6 +166,64 @@ def RectangularTriangleMesh(N=10, size=1.0, lower_left=(0.0, 0.0)) -> Structured
     return m
 
 
+@dataclasses.dataclass
+class InterfaceMesh:
+    """Line elements (InterfaceElementLine1dC2, src/elements.hpp:1435-2298) on boundary edges of a 2D bulk mesh: they live on the bulk
+    mesh's nodes (same node numbers, positions and nodal values) and remember the bulk element and face they were built from."""
+    dim: int
+    N: Tuple[int, ...]
+    elem_nodes: np.ndarray           # [n_elem, 3] bulk node numbers, ordered so that (-t_y, t_x) is the OUTER normal
+    node_pos: np.ndarray
+    node_lattice: np.ndarray
+    boundaries: Dict[str, np.ndarray]
+    element_type: str
+    bulk_element: np.ndarray         # [n_elem] bulk element the edge belongs to
+    face_index: np.ndarray           # [n_elem] oomph face index of that edge (-1: s0=-1, 1: s0=+1, -2: s1=-1, 2: s1=+1)
+    is_vertex_mask: np.ndarray
+
+    @property
+    def n_elem(self) -> int:
+        return self.elem_nodes.shape[0]
+
+    @property
+    def n_node(self) -> int:
+        return self.node_pos.shape[0]
+
+    def is_vertex(self) -> np.ndarray:
+        return self.is_vertex_mask
+
+
+def boundary_line_mesh(mesh: StructuredMesh, names: Sequence[str]) -> InterfaceMesh:
+    """The Q9 edges on the named boundaries ("left", "right", "bottom", "top") of a RectangularQuadMesh as three-node line elements.
+    BulkElementBase::get_normal_at_s gives a line element the normal (-t_y, t_x)/|t| (src/elements.cpp:1730-1752); the reference's
+    interface elements orient it with FaceElement::normal_sign so that it leaves the bulk (outer_unit_normal, src/elements.hpp:1630).
+    Here the node order of every edge is chosen so that (-t_y, t_x) IS the outer normal: bottom edges run right -> left, right edges
+    top -> bottom, top edges left -> right, left edges bottom -> top (pinned against the compiled oomph-lib FaceElement in
+    tests/test_oracle_ref.py)."""
+    if mesh.dim != 2 or mesh.element_type != "Quad2dC2":
+        raise ValueError("boundary_line_mesh needs a 2D Q9 mesh")
+    nx, ny = mesh.N
+    e_of = lambda ix, iy: ix * ny + iy
+    local = {"bottom": ((2, 1, 0), -2), "right": ((8, 5, 2), 1), "top": ((6, 7, 8), 2), "left": ((0, 3, 6), -1)}
+    en, be, fi = [], [], []
+    for nm in names:
+        loc, face = local[nm]
+        if nm == "bottom":
+            els = [e_of(ix, 0) for ix in range(nx)]
+        elif nm == "top":
+            els = [e_of(ix, ny - 1) for ix in range(nx)]
+        elif nm == "left":
+            els = [e_of(0, iy) for iy in range(ny)]
+        else:
+            els = [e_of(nx - 1, iy) for iy in range(ny)]
+        for e in els:
+            en.append([int(mesh.elem_nodes[e, l]) for l in loc])
+            be.append(e)
+            fi.append(face)
+    return InterfaceMesh(2, mesh.N, np.ascontiguousarray(np.array(en, dtype=np.int32).reshape(-1, 3)), mesh.node_pos, mesh.node_lattice,
+                         mesh.boundaries, "Line1dC2", np.array(be, dtype=np.int32), np.array(fi, dtype=np.int32), mesh.is_vertex())
+
+
 def CuboidBrickMesh(N=4, size=1.0, lower_left=(0.0, 0.0, 0.0)) -> StructuredMesh:
     """Q27 mesh of N[0] x N[1] x N[2] elements (simplemeshes.py:456)."""
     N = (N, N, N) if np.isscalar(N) else tuple(N)

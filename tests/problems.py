@@ -76,6 +76,36 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             return _variant(_mk["brick"](n))
     else:
         from pyoomph_b200.meshes import CuboidBrickMesh, RectangularQuadMesh
+    if kind in ("robin_if", "freesurf_if"):
+        # interface element classes (InterfaceElementLine1dC2) on boundary edges of a (distorted) Q9 mesh, on the bulk's nodes, nodal
+        # values and equation numbers: a Robin condition for the Poisson field of config 1, and the free-surface terms of config 4
+        # (surface tension, no-penetration through a Lagrange multiplier field on the interface) on a mesh that does not move
+        import pyoomph_b200.meshes as _mm
+        from pyoomph_b200.equations import DeclareFields, FreeSurfaceOnFixedMesh, RobinBC
+        from pyoomph_b200.expressions import var as _var
+        bulk = _mm.RectangularQuadMesh(N)
+        if distortion:
+            bulk = distort(bulk, distortion, seed)
+        mesh = _mm.boundary_line_mesh(bulk, ["right", "top"] if kind == "robin_if" else ["top", "left"])
+        if kind == "robin_if":
+            code = FiniteElementCode("Line1dC2", RobinBC("u", alpha=2.5, external=lambda: _var("coordinate_x") * _var("coordinate_y"), flux=0.3), name="robinif")
+            bulk_code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")
+            pinned = {"u": bulk.boundaries["left"]}
+        else:
+            code = FiniteElementCode("Line1dC2", FreeSurfaceOnFixedMesh(surface_tension=0.7), name="freesurfif")
+            bulk_code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + DeclareFields(_kin_bc="C2"), name="nsif")
+            wall = np.unique(np.concatenate([bulk.boundaries[b] for b in ("bottom", "right")]))
+            off_interface = np.setdiff1d(np.arange(bulk.n_node), np.unique(mesh.elem_nodes))
+            pinned = {"velocity_x": wall, "velocity_y": wall, "_kin_bc": off_interface}     # the multiplier exists on the interface nodes only
+        unsteady = False
+        dofmap = assign_equation_numbers(bulk, bulk_code, pinned, None)
+        assert [f.name for f in code.nodal_fields()] == [f.name for f in bulk_code.nodal_fields()]
+        T, nval = code.history_levels(), code.n_nodal_values
+        vals = np.zeros((T, bulk.n_node, nval))
+        for t in range(T):
+            for f in range(nval):
+                vals[t, :, f] = smooth_field(bulk.node_pos, f + 3 * t, seed) * (1.0 - 0.05 * t)
+        return dict(kind=kind, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=None, unsteady=unsteady, params={}, bulk_mesh=bulk, bulk_code=bulk_code)
     if kind in ("poisson_tri", "ns_tri", "ale_tri"):
         # six-node triangles (the element class of the reference's gmsh droplet meshes): Poisson, Taylor-Hood P2/P1 Navier-Stokes,
         # and NS on a pseudo-elastic moving mesh

@@ -550,3 +550,71 @@ def test_point_expressions_parity(kind, N, distortion, unstructured):
     with pytest.raises(RuntimeError):
         asm.evaluate_extremum("no_such_expression")
     op.close(); asm.close()
+
+
+INTERFACES = [("robin_if", 6, 0.12), ("robin_if", 9, 0.0), ("freesurf_if", 5, 0.1), ("freesurf_if", 24, 0.05)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N,distortion", INTERFACES)
+def test_interface_element_classes_parity(kind, N, distortion):
+    """Line elements in a 2D nodal space (InterfaceElementLine1dC2: tangent, outer normal and surface gradients from a 1x2 mapping)
+    assembled on their own: residual and Jacobian against the oracle, CSR bit-exact after the zero-drop rule."""
+    pb = make_problem(kind, N, distortion=distortion)
+    op = make_oracle(pb)
+    asm = make_gpu(pb)
+    n = pb["dofmap"].n_dof
+    r_ref, mats = op.assemble(flag=1)
+    asm.assemble(flag=1)
+    r, jac, _ = asm.fetch(True, False)
+    scale = np.abs(r_ref).max()
+    assert np.abs(r - r_ref).max() <= TOL * scale
+    A = csr_to_sorted(n, asm.indptr, asm.indices, jac)
+    B = csr_to_sorted(n, *mats[0])
+    err, missing = compare_matrix(A, B)
+    assert missing == 0 and err <= TOL, (kind, err, missing)
+    st = assert_csr_parity(asm.indptr, asm.indices, jac, mats[0], TOL, label="%s N=%d" % (kind, N), max_cancel_fraction=0.02 if distortion > 0 else 0.30)
+    _record(kind, N, distortion, False, st)
+    asm.assemble(flag=0)
+    r0, _, _ = asm.fetch(False, False)
+    assert np.abs(r0 - r).max() <= 1e-13 * scale
+    op.close()
+    asm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N,distortion", [("robin_if", 7, 0.1), ("freesurf_if", 6, 0.1), ("freesurf_if", 40, 0.0)])
+def test_interface_class_assembled_into_the_matrix_of_its_bulk_class(kind, N, distortion):
+    """A child problem (pb2_problem_create_child): the interface class scatters into the CSR matrix and residual its bulk class just
+    wrote, on the device; the sum equals the oracle's two classes assembled into one matrix (oomph assembles all element classes of a
+    Problem into one matrix, problem.cc:5332-5666)."""
+    from pyoomph_b200.assembly import B200Assembly
+    pb = make_problem(kind, N, distortion=distortion)
+    bulk_pb = dict(pb, code=pb["bulk_code"], mesh=pb["bulk_mesh"])
+    bulk = make_gpu(bulk_pb)
+    child = B200Assembly(pb["code"], pb["mesh"], pb["dofmap"], name=pb["code"].name, parent=bulk)
+    ob, oi = make_oracle(bulk_pb), make_oracle(pb)
+    n = pb["dofmap"].n_dof
+    rb, mb = ob.assemble(flag=1)
+    ri, mi = oi.assemble(flag=1)
+    J_ref = (csr_to_sorted(n, *mb[0]) + csr_to_sorted(n, *mi[0])).tocsr()
+    J_ref.sort_indices()
+    r_ref = rb + ri
+    for rep in range(2):                       # the second pass starts from the first one's values: first-touch stores, then adds
+        bulk.assemble(flag=1)
+        r, jac, _ = bulk.fetch(True, False)
+        assert np.abs(r - r_ref).max() <= TOL * np.abs(r_ref).max()
+        err, missing = compare_matrix(csr_to_sorted(n, bulk.indptr, bulk.indices, jac), J_ref)
+        assert missing == 0 and err <= TOL, (kind, rep, err, missing)
+    assert bulk.launch_count() == 2            # one persistent launch per element class
+    # the interface class really contributed
+    assert np.abs(ri).max() > 1e-3 * np.abs(r_ref).max()
+    # the bulk class alone, afterwards, gives the bulk matrix again (the child only ever adds to what the parent stored)
+    child.close()
+    bulk.children.clear()
+    bulk.assemble(flag=1)
+    r2, jac2, _ = bulk.fetch(True, False)
+    assert np.abs(r2 - rb).max() <= TOL * np.abs(rb).max()
+    for o in (ob, oi):
+        o.close()
+    bulk.close()

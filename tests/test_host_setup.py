@@ -83,3 +83,44 @@ def test_pattern_with_extra_entries_and_element_subset():
     ip, ix = structural_pattern(ed, n, (ex_r, ex_c))
     assert np.array_equal(asm.indptr, ip) and np.array_equal(asm.indices, ix)
     asm.close()
+
+
+@pytest.mark.parametrize("kind,N", [("robin_if", 6), ("freesurf_if", 5)])
+def test_child_problem_maps_point_into_the_parents_pattern(kind, N):
+    """pb2_problem_create_child: an interface element class on the bulk class's nodes and equations scatters into the PARENT's CSR
+    pattern -- every position map entry of the child names the parent's entry (row of dof i, column of dof j), nothing is a
+    first-touch store (the child adds to what the parent wrote), and a parent whose pattern lacks the child's entries is refused."""
+    pb = make_problem(kind, N, distortion=0.1)
+    bulk = B200Assembly(pb["bulk_code"], pb["bulk_mesh"], pb["dofmap"], name=pb["bulk_code"].name, device=-1)
+    child = B200Assembly(pb["code"], pb["mesh"], pb["dofmap"], name=pb["code"].name, parent=bulk)
+    assert child in bulk.children
+    assert np.array_equal(child.indptr, bulk.indptr) and np.array_equal(child.indices, bulk.indices)
+    perm, rowstart, off, res = child.host_maps()
+    ne = pb["mesh"].n_elem
+    assert sorted(perm.tolist()) == list(range(ne))
+    ed = element_dof_table(pb["code"], pb["mesh"], pb["dofmap"], np.arange(ne))[perm]
+    bits = 8 * off.dtype.itemsize
+    skip, firstbit = (1 << bits) - 1, 1 << (bits - 1)
+    live = ed >= 0
+    assert live.any() and (~live).any()
+    assert np.array_equal(rowstart[live], bulk.indptr[ed[live]]) and np.all(rowstart[~live] == -1)
+    assert np.array_equal(res[live], ed[live])                      # plain row numbers: always added, never the ~row store form
+    assert np.all(res[~live] == np.iinfo(np.int32).min)
+    for q in range(ne):
+        for i in np.nonzero(live[q])[0]:
+            for j in range(ed.shape[1]):
+                if ed[q, j] < 0:
+                    assert off[q, i, j] == skip
+                else:
+                    assert (int(off[q, i, j]) & firstbit) == 0
+                    assert bulk.indices[rowstart[q, i] + int(off[q, i, j])] == ed[q, j]
+    # a parent that does not hold the child's entries (bulk elements far from the interface only)
+    far = B200Assembly(pb["bulk_code"], pb["bulk_mesh"], pb["dofmap"], name=pb["bulk_code"].name, device=-1, elements=np.arange(3))
+    with pytest.raises(RuntimeError, match="lacks"):
+        B200Assembly(pb["code"], pb["mesh"], pb["dofmap"], name=pb["code"].name, parent=far)
+    # a child of a child, or a class with another nodal record, is refused
+    with pytest.raises(RuntimeError, match="root problem"):
+        B200Assembly(pb["code"], pb["mesh"], pb["dofmap"], name=pb["code"].name, parent=child)
+    child.close()
+    bulk.close()
+    far.close()

@@ -430,3 +430,56 @@ def test_triangle_elements_of_the_oracle():
         op.update_values(0, pb["vals"][0])
         assert np.abs((rp - rm) / (2 * eps) - A[:, g]).max() <= 1e-7 * np.abs(A[:, g]).max()
     op.close()
+
+
+def test_interface_elements_of_the_oracle():
+    """InterfaceElementLine1dC2 in the oracle (el_dim 1 in nodal dimension 2: src/elements.cpp:3651-3672, normal :1730-1752): on a
+    distorted Q9 mesh the edges' surface measure adds up to the length of the boundary polyline of parabolas, the unit normal is
+    orthogonal to the tangent and LEAVES the bulk element the edge belongs to (what FaceElement::normal_sign achieves in the reference),
+    the surface gradient of a linear field is its tangential projection, and the analytic Jacobians of the Robin and free-surface
+    classes agree with finite differences of the residual."""
+    from problems import csr_to_sorted, make_oracle, make_problem
+    from pyoomph_b200.cuda_emitter import gauss_rule_1d
+    pb = make_problem("freesurf_if", 4, distortion=0.15)
+    im, bulk = pb["mesh"], pb["bulk_mesh"]
+    a, b = np.array([0.7, -1.3]), 0.4
+    pb["vals"][0][:, 0] = b + bulk.node_pos @ a                                        # velocity_x linear in (x, y)
+    op = make_oracle(pb)
+    kn, _ = gauss_rule_1d()
+    for e in range(im.n_elem):
+        xe = im.node_pos[im.elem_nodes[e]]
+        centroid = bulk.node_pos[bulk.elem_nodes[im.bulk_element[e]]].mean(axis=0)
+        for ipt in range(3):
+            wts, sh, dx, dX, _, _ = op.point_shapes(e, ipt, flag=0)
+            s = kn[ipt][0]
+            t = np.array([s - 0.5, -2.0 * s, s + 0.5]) @ xe
+            n = np.array([-t[1], t[0]]) / np.hypot(*t)
+            assert abs(n @ t) <= 1e-14 and abs(np.hypot(*n) - 1.0) <= 1e-14
+            assert n @ (sh @ xe - centroid) > 0.0                                      # outward
+            assert abs(wts[0] - np.hypot(*t) * (5.0 / 9.0 if ipt != 1 else 8.0 / 9.0)) <= 1e-14
+            grad_s = pb["vals"][0][im.elem_nodes[e], 0] @ dx                           # surface gradient of the linear field
+            tau = t / np.hypot(*t)
+            assert np.abs(grad_s - (a @ tau) * tau).max() <= 1e-12
+    op.close()
+    for kind in ("robin_if", "freesurf_if"):
+        pb = make_problem(kind, 3, distortion=0.12)
+        op = make_oracle(pb)
+        _, mats = op.assemble(flag=1)
+        n = pb["dofmap"].n_dof
+        A = csr_to_sorted(n, *mats[0]).toarray()
+        eq, eps = pb["dofmap"].node_eqn, 1e-6
+        for node in np.unique(pb["mesh"].elem_nodes)[:6]:
+            for f in range(eq.shape[1]):
+                g = eq[node, f]
+                if g < 0:
+                    continue
+                v = pb["vals"][0].copy()
+                v[node, f] += eps
+                op.update_values(0, v)
+                rp, _ = op.assemble(flag=0)
+                v[node, f] -= 2 * eps
+                op.update_values(0, v)
+                rm, _ = op.assemble(flag=0)
+                op.update_values(0, pb["vals"][0])
+                assert np.abs((rp - rm) / (2 * eps) - A[:, g]).max() <= 1e-8 * max(np.abs(A).max(), 1e-300)
+        op.close()
