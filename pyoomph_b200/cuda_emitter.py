@@ -763,7 +763,12 @@ class CudaEmitter:
         w = o.append
         w("// %s  what=%d : pipelined; %d compute + %d gather + %d scatter threads, %d elements per batch, %d B smem" % (
             form.name or "<default residual>", what, NC, NG, NS, EPB, smem_bytes))
-        w("extern \"C\" __global__ void __launch_bounds__(%d, 1) %s(const pb2_kernel_args a)" % (NT, kname))
+        # blocks per SM: light element classes (one scalar field on Q9: 63 KB of shared memory, 10 accumulators per thread) are bound by the
+        # hand-offs between the roles, not by a pipe -- a second resident block fills the gaps if the registers allow it
+        minb = int(os.environ.get("PB2_PIPE_MINBLOCKS", "1"))
+        if minb > 1 and (smem_bytes + 1024) * minb > 227 * 1024:
+            minb = 1
+        w("extern \"C\" __global__ void __launch_bounds__(%d, %d) %s(const pb2_kernel_args a)" % (NT, minb, kname))
         w("{")
         w("  extern __shared__ double smem[];")
         w("  double* const s_psi2 = smem;")
