@@ -110,7 +110,20 @@ class OracleProblem:
         self.h = ctypes.c_void_p(L.oracle_create_typed(self.dim, int(mesh.elem_nodes.shape[1]), mesh.n_elem, _ip(self.elem_nodes), mesh.n_node,
                                                  node_val.shape[2], self.T, pos.shape[0], _dp(pos), _dp(lagr),
                                                  _dp(node_val), _ip(self.node_eqn), _ip(self.pos_eqn), self.n_dof))
-        self.maxdof = mesh.elem_nodes.shape[1] * (self.dim + node_val.shape[2])
+        self.maxdof = 2 * mesh.elem_nodes.shape[1] * (self.dim + node_val.shape[2])     # x2: master values outside the element
+        hanging = getattr(mesh, "hanging", None)
+        if hanging is not None:
+            for space, table in ((0, hanging.C2), (1, hanging.C1)):
+                start = np.zeros(mesh.n_node + 1, dtype=np.int32)
+                for n, (m, w) in table.items():
+                    start[n + 1] = len(m)
+                start = np.cumsum(start).astype(np.int32)
+                masters = np.zeros(max(1, int(start[-1])), dtype=np.int32)
+                weights = np.zeros(max(1, int(start[-1])))
+                for n, (m, w) in table.items():
+                    masters[start[n]:start[n + 1]] = m
+                    weights[start[n]:start[n + 1]] = w
+                L.oracle_set_hanging(self.h, space, _ip(start), _ip(masters), _dp(weights))
 
     def evaluate_integral_expressions(self):
         """{name: sum over elements of EvalIntegralExpression(index)} (Mesh::evaluate_integral_expression, src/mesh.cpp:536)"""

@@ -198,6 +198,9 @@ typedef struct
   int *row_start[2], *col_index[2];
   double *value[2];
   int64_t nnz[2];
+  /* hanging nodes per space (0: C2 / positions, 1: C1), CSR over the nodes: masters and weights (oomph-lib HangInfo) */
+  int *hang_start[2], *hang_master[2];
+  double *hang_weight[2];
 } Oracle;
 
 /* per-thread assembly state = the reference's global shape buffer + _currently_assembled_element
@@ -211,6 +214,10 @@ typedef struct
   int node_of[MAXN];
   int eqn_of_local[MAXN * (MAXD + 16)];
   JITHangInfo_t nohang[MAXN];
+#define MAXM 9
+  JITHangInfo_t hang_C2[MAXN], hang_C1[8];
+  JITHangInfoEntry_t hang_entries_C2[MAXN][MAXM], hang_entries_C1[8][MAXM];
+  int hang_eqn_C2[MAXN][MAXM][32], hang_eqn_C1[8][MAXM][32];
   /* backing storage */
   double **coord_ptr[MAXN], **data_ptr[MAXN];
   double *coord_slots[MAXN][2 * MAXD], *data_slots[MAXN][32];
@@ -570,7 +577,82 @@ static void bind_element(ThreadState *ts, int e)
         ts->eqn_of_local[nloc++] = g;
       }
     }
+  /* hanging nodes: fill_hang_info_with_equations (src/elements.cpp:812-1160) on top of RefineableElement::assign_hanging_local_eqn_numbers
+   * (oomph-lib refineable_elements.cc:312-470): nodes n, values j, masters m; a master value that is already a local dof keeps its
+   * number, a new one is appended behind the element's own dofs; pinned master values give -1. */
+  JITShapeInfo_t *si = &ts->si;
+  si->hanginfo_C1 = ts->nohang;
+  si->hanginfo_C2 = ts->nohang;
+  si->hanginfo_Pos = ts->nohang;
+  if (o->hang_start[0] || o->hang_start[1])
+  {
+    if (o->pos_eqn)
+    {
+      fprintf(stderr, "oracle: hanging nodes on a moving mesh are not restated\n");
+      abort();
+    }
+    si->hanginfo_C2 = ts->hang_C2;
+    si->hanginfo_C1 = ts->hang_C1;
+    for (int sp = 0; sp < 2; sp++)
+    {
+      const int nl = sp == 0 ? nn : o->et.nnode_C1, f0 = sp == 0 ? 0 : nC2, f1 = sp == 0 ? nC2 : nC2 + nC1;
+      for (int l = 0; l < nl; l++)
+      {
+        const int node = sp == 0 ? en[l] : en[o->et.c1_nodes[l]];
+        JITHangInfo_t *hi = sp == 0 ? &ts->hang_C2[l] : &ts->hang_C1[l];
+        JITHangInfoEntry_t *ent = sp == 0 ? ts->hang_entries_C2[l] : ts->hang_entries_C1[l];
+        hi->nummaster = 0;
+        hi->masters = ent;
+        if (!o->hang_start[sp]) continue;
+        const int h0 = o->hang_start[sp][node], h1 = o->hang_start[sp][node + 1];
+        if (h1 == h0) continue;
+        if (h1 - h0 > MAXM)
+        {
+          fprintf(stderr, "oracle: more than %d masters\n", MAXM);
+          abort();
+        }
+        hi->nummaster = h1 - h0;
+        for (int m = 0; m < h1 - h0; m++)
+        {
+          ent[m].weight = o->hang_weight[sp][h0 + m];
+          ent[m].local_eqn = sp == 0 ? ts->hang_eqn_C2[l][m] : ts->hang_eqn_C1[l][m];
+          for (int f = 0; f < nC2 + nC1; f++) ent[m].local_eqn[f] = -1;
+        }
+        for (int f = f0; f < f1; f++)
+          for (int m = 0; m < h1 - h0; m++)
+          {
+            const int g = o->node_eqn[(size_t)o->hang_master[sp][h0 + m] * o->nval + f];
+            if (g < 0) continue;
+            int loc = -1;
+            for (int k = 0; k < nloc; k++)
+              if (ts->eqn_of_local[k] == g) loc = k;
+            if (loc < 0)
+            {
+              loc = nloc;
+              ts->eqn_of_local[nloc++] = g;
+            }
+            ent[m].local_eqn[f] = loc;
+          }
+      }
+    }
+  }
   ts->ei.ndof = nloc;
+}
+
+/* hanging nodes of one space (0: C2 and positions, 1: C1): CSR over the nodes */
+void oracle_set_hanging(void *h, int space, const int *start, const int *masters, const double *weights)
+{
+  Oracle *o = (Oracle *)h;
+  const int n = start[o->n_node];
+  free(o->hang_start[space]);
+  free(o->hang_master[space]);
+  free(o->hang_weight[space]);
+  o->hang_start[space] = (int *)xcalloc((size_t)o->n_node + 1, sizeof(int));
+  o->hang_master[space] = (int *)xcalloc((size_t)n + 1, sizeof(int));
+  o->hang_weight[space] = (double *)xcalloc((size_t)n + 1, sizeof(double));
+  memcpy(o->hang_start[space], start, ((size_t)o->n_node + 1) * sizeof(int));
+  memcpy(o->hang_master[space], masters, (size_t)n * sizeof(int));
+  memcpy(o->hang_weight[space], weights, (size_t)n * sizeof(double));
 }
 
 /* prepare_shape_buffer_for_integration (src/elements.cpp:4577-4646) */
@@ -885,7 +967,7 @@ double oracle_assemble(void *h, int which, int param, unsigned flag, double *res
     const int th = 0;
 #endif
     ThreadState *ts = ts_create(o);
-    const int maxdof = o->et.nnode * (o->et.dim + o->nval);
+    const int maxdof = 2 * o->et.nnode * (o->et.dim + o->nval); /* x2: master values outside the element (hanging nodes) */
     double *R = (double *)xcalloc(maxdof, sizeof(double));
     double *J = (double *)xcalloc((size_t)maxdof * maxdof, sizeof(double));
     double *M = (double *)xcalloc((size_t)maxdof * maxdof, sizeof(double));
@@ -1090,5 +1172,6 @@ void oracle_free(void *h)
   for (int m = 0; m < 2; m++) { free(o->row_start[m]); free(o->col_index[m]); free(o->value[m]); }
   if (o->ft->clean_up) o->ft->clean_up(o->ft);
   free(o->ft); free(o->pos); free(o->lagr); free(o->val); free(o->params);
+  for (int sp = 0; sp < 2; sp++) { free(o->hang_start[sp]); free(o->hang_master[sp]); free(o->hang_weight[sp]); }
   free(o);
 }

@@ -82,7 +82,7 @@ def load_library() -> ctypes.CDLL:
                "pb2_problem_assemble_hessian", "pb2_problem_fetch_hessian", "pb2_problem_hessian_vector_products",
                "pb2_problem_pack_rows", "pb2_problem_unpack_add", "pb2_problem_eval_integrals", "pb2_problem_shift_time_values",
                "pb2_problem_set_history_dofs", "pb2_measure_fp64_peak", "pb2_problem_host_maps", "pb2_problem_device_pattern",
-               "pb2_problem_device_dofs", "pb2_problem_update_dofs_device", "pb2_problem_eval_points", "pb2_problem_create_child"):
+               "pb2_problem_device_dofs", "pb2_problem_update_dofs_device", "pb2_problem_eval_points", "pb2_problem_create_child", "pb2_problem_set_constraints"):
         getattr(L, fn).restype = ctypes.c_int
     L.pb2_problem_setup_seconds.restype = ctypes.c_double
     _LIB = L

@@ -137,6 +137,11 @@ struct pb2_problem
   cudaEvent_t ev_inputs = nullptr; // recorded on the legacy stream after every input update; assemblies on other streams wait for it
   double setup_seconds = 0.0;      // wall time of pb2_problem_create (colouring, pattern, maps, upload)
   // pattern-only problems (device < 0) keep the maps on the host for inspection (pb2_problem_host_maps)
+  // hanging-node constraints (pb2_problem_set_constraints): reduction lists of P^T J P on the extended system
+  long long c_ntarget = 0, c_nres = 0, c_nclear = 0, c_nvirt = 0;
+  int *d_c_target = nullptr, *d_c_src_start = nullptr, *d_c_src_pos = nullptr, *d_c_res_row = nullptr, *d_c_res_start = nullptr,
+      *d_c_res_src = nullptr, *d_c_clear = nullptr, *d_c_virt_rows = nullptr, *d_c_diag = nullptr;
+  double *d_c_src_w = nullptr, *d_c_res_w = nullptr;
   int n_children = 0;              // child problems alive (they alias this problem's device buffers)
   pb2_problem *parent = nullptr;   // child problem: another element class scattering into the parent's matrix, residual and nodal data
   int *d_untouched_rows = nullptr; // residual rows no element of this problem writes (rows only a child class contributes to)
@@ -933,6 +938,9 @@ extern "C" void pb2_problem_free(pb2_problem *p)
     p->d_node_pos = p->d_node_lagr = p->d_node_val = p->d_residual = p->d_jac = p->d_dofs = nullptr;
   }
   cudaFree(p->d_untouched_rows);
+  cudaFree(p->d_c_target); cudaFree(p->d_c_src_start); cudaFree(p->d_c_src_pos); cudaFree(p->d_c_src_w);
+  cudaFree(p->d_c_res_row); cudaFree(p->d_c_res_start); cudaFree(p->d_c_res_src); cudaFree(p->d_c_res_w);
+  cudaFree(p->d_c_clear); cudaFree(p->d_c_virt_rows); cudaFree(p->d_c_diag);
   cudaFree(p->d_elem_nodes);
   cudaFree(p->d_elem_eqn);
   cudaFree(p->d_elem_rowstart);
@@ -1325,6 +1333,109 @@ static int run_routine(pb2_problem *p, int kind, int residual_index, int param_i
   return 0;
 }
 
+// ---- hanging-node constraints: J = P^T J_ext P, R = P^T R_ext on the assembled extended system (pyoomph_b200/hanging.py).
+// One thread per target: a fixed-order weighted sum of its sources (entries of virtual rows / columns, which no target is) -- no atomics.
+static __global__ void pb2_constraint_gather(double *__restrict__ a, double *__restrict__ b, const int *__restrict__ target, const int *__restrict__ start,
+                                             const int *__restrict__ src, const double *__restrict__ w, long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = target[i];
+  double sa = 0.0, sb = 0.0;
+  for (int k = start[i]; k < start[i + 1]; k++)
+  {
+    sa += w[k] * a[src[k]];
+    if (b) sb += w[k] * b[src[k]];
+  }
+  a[t] += sa;
+  if (b) b[t] += sb;
+}
+
+// virtual rows and columns: cleared, unit diagonal in the Jacobian (zero in a mass matrix or a parameter derivative), residual zero
+// (the diagonal entries are among the cleared ones: they are written by the launch after this one)
+static __global__ void pb2_constraint_clear(double *__restrict__ jac, double *__restrict__ mass, double *__restrict__ res, const int *__restrict__ clear, long long nclear,
+                                            const int *__restrict__ rows, long long nvirt)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nclear)
+  {
+    if (jac) jac[clear[i]] = 0.0;
+    if (mass) mass[clear[i]] = 0.0;
+  }
+  if (i < nvirt && res) res[rows[i]] = 0.0;
+}
+
+static __global__ void pb2_constraint_diag(double *__restrict__ jac, const int *__restrict__ diag, long long nvirt, double diag_value)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nvirt) jac[diag[i]] = diag_value;
+}
+
+extern "C" int pb2_problem_set_constraints(pb2_problem *p, long long n_target, const int *target_pos, const int *src_start, const int *src_pos, const double *src_w,
+                                           long long n_res, const int *res_row, const int *res_start, const int *res_src, const double *res_w,
+                                           long long n_clear, const int *clear_pos, long long n_virtual, const int *virtual_rows, const int *virtual_diag_pos)
+{
+  NEED_DEVICE(p);
+  if (p->parent || p->n_children) return fail("constraints on parent / child problems are not supported");
+  for (long long i = 0; i < n_target; i++)
+    if (target_pos[i] < 0 || target_pos[i] >= p->nnz) return fail("constraint target outside the matrix");
+  const long long ns = n_target ? src_start[n_target] : 0, nrs = n_res ? res_start[n_res] : 0;
+  for (long long i = 0; i < ns; i++)
+    if (src_pos[i] < 0 || src_pos[i] >= p->nnz) return fail("constraint source outside the matrix");
+  for (long long i = 0; i < n_virtual; i++)
+    if (virtual_rows[i] < 0 || virtual_rows[i] >= p->n_dof || virtual_diag_pos[i] < 0 || virtual_diag_pos[i] >= p->nnz) return fail("virtual equation outside the system");
+  for (int **d : {&p->d_c_target, &p->d_c_src_start, &p->d_c_src_pos, &p->d_c_res_row, &p->d_c_res_start, &p->d_c_res_src, &p->d_c_clear, &p->d_c_virt_rows, &p->d_c_diag})
+  {
+    cudaFree(*d); // replacing earlier lists
+    *d = nullptr;
+  }
+  cudaFree(p->d_c_src_w); cudaFree(p->d_c_res_w);
+  p->d_c_src_w = p->d_c_res_w = nullptr;
+  p->c_nvirt = 0;
+  std::vector<int> v;
+  auto up_i = [&](int **d, const int *h, long long n) { v.assign(h, h + n); return upload(d, v); };
+  std::vector<double> vd;
+  auto up_d = [&](double **d, const double *h, long long n) { vd.assign(h, h + n); return upload(d, vd); };
+  if (up_i(&p->d_c_target, target_pos, n_target) || up_i(&p->d_c_src_start, src_start, n_target + 1) || up_i(&p->d_c_src_pos, src_pos, ns) || up_d(&p->d_c_src_w, src_w, ns) ||
+      up_i(&p->d_c_res_row, res_row, n_res) || up_i(&p->d_c_res_start, res_start, n_res + 1) || up_i(&p->d_c_res_src, res_src, nrs) || up_d(&p->d_c_res_w, res_w, nrs) ||
+      up_i(&p->d_c_clear, clear_pos, n_clear) || up_i(&p->d_c_virt_rows, virtual_rows, n_virtual) || up_i(&p->d_c_diag, virtual_diag_pos, n_virtual))
+    return 1;
+  p->c_ntarget = n_target;
+  p->c_nres = n_res;
+  p->c_nclear = n_clear;
+  p->c_nvirt = n_virtual;
+  return 0;
+}
+
+// after an R / J / M assembly (or a parameter derivative: zero instead of unit diagonal) of a problem with constraints
+static int apply_constraints(pb2_problem *p, unsigned flag, bool parameter_derivative, double *jac, double *mass, void *cuda_stream)
+{
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int bs = 256;
+  auto grid = [&](long long n) { return (unsigned)std::max<long long>(1, (n + bs - 1) / bs); };
+  if (flag >= 1u && p->c_ntarget > 0)
+  {
+    pb2_constraint_gather<<<grid(p->c_ntarget), bs, 0, st>>>(jac, flag >= 2u ? mass : nullptr, p->d_c_target, p->d_c_src_start, p->d_c_src_pos, p->d_c_src_w, p->c_ntarget);
+    p->launches_last++;
+  }
+  if (p->c_nres > 0)
+  {
+    pb2_constraint_gather<<<grid(p->c_nres), bs, 0, st>>>(p->d_residual, nullptr, p->d_c_res_row, p->d_c_res_start, p->d_c_res_src, p->d_c_res_w, p->c_nres);
+    p->launches_last++;
+  }
+  pb2_constraint_clear<<<grid(std::max(p->c_nclear, p->c_nvirt)), bs, 0, st>>>(flag >= 1u ? jac : nullptr, flag >= 2u ? mass : nullptr, p->d_residual, p->d_c_clear, p->c_nclear,
+                                                                             p->d_c_virt_rows, p->c_nvirt);
+  p->launches_last++;
+  if (flag >= 1u && !parameter_derivative && p->c_nvirt > 0)
+  {
+    pb2_constraint_diag<<<grid(p->c_nvirt), bs, 0, st>>>(jac, p->d_c_diag, p->c_nvirt, 1.0);
+    p->launches_last++;
+  }
+  CUDA_OK(cudaGetLastError());
+  p->launches_total += 4;
+  return 0;
+}
+
 extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int param_index, unsigned flag, void *cuda_stream)
 {
   NEED_DEVICE(p);
@@ -1336,13 +1447,16 @@ extern "C" int pb2_problem_assemble(pb2_problem *p, int residual_index, int para
     return run_routine(p, 0, residual_index, param_index, flag, p->parent->d_jac, p->parent->d_mass, nullptr, cuda_stream);
   }
   if (flag == 2u && !p->d_mass) CUDA_OK(cudaMalloc((void **)&p->d_mass, std::max<size_t>(1, p->nnz) * sizeof(double)));
-  return run_routine(p, 0, residual_index, param_index, flag, p->d_jac, p->d_mass, nullptr, cuda_stream);
+  const int rc = run_routine(p, 0, residual_index, param_index, flag, p->d_jac, p->d_mass, nullptr, cuda_stream);
+  if (rc == 0 && p->c_nvirt > 0) return apply_constraints(p, flag, param_index >= 0, p->d_jac, p->d_mass, cuda_stream);
+  return rc;
 }
 
 extern "C" int pb2_problem_assemble_hessian(pb2_problem *p, int residual_index, unsigned flag, int n_vec, const double *Y, void *cuda_stream)
 {
   NEED_DEVICE(p);
   if (!p->cls->table.info.hessian_generated) return fail("this element class was generated without Hessian routines");
+  if (p->c_nvirt > 0) return fail("Hessian routines of a problem with hanging-node constraints are not supported");
   if (flag != 1u && flag != 2u && flag != 4u && flag != 5u)
     return fail("Hessian assembly: flag must be 1 (d(J.Y)/dU), 2 (+ d(M.Y)/dU), 4 (d(J^T.Y)/dU) or 5 (+ d(M^T.Y)/dU)");
   const int hkind = flag >= 4u ? 3 : 1;     // transposed contraction: plugin kind 3

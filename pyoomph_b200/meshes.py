@@ -232,6 +232,120 @@ def CuboidBrickMesh(N=4, size=1.0, lower_left=(0.0, 0.0, 0.0)) -> StructuredMesh
 
 
 @dataclasses.dataclass
+class HangingNodes:
+    """Hanging-node constraints per interpolation space (oomph-lib HangInfo per value index; pyoomph keeps one set for the C2 / position
+    values and one for the C1 values of a node, src/elements.cpp:812-1160): node -> (master nodes, weights); the value at the node is
+    sum_k weight_k * value(master_k) and it has no equation of its own."""
+    C2: Dict[int, Tuple[np.ndarray, np.ndarray]]
+    C1: Dict[int, Tuple[np.ndarray, np.ndarray]]
+
+    def of_space(self, space: str) -> Dict[int, Tuple[np.ndarray, np.ndarray]]:
+        return self.C1 if space == "C1" else self.C2
+
+
+@dataclasses.dataclass
+class RefinedQuadMesh:
+    """A Q9 mesh after one level of quadtree refinement of some elements (RefineableQElement<2> sons SW, SE, NW, NE): conforming
+    through hanging nodes on the edges between refined and unrefined elements."""
+    dim: int
+    elem_nodes: np.ndarray
+    node_pos: np.ndarray
+    node_lattice: np.ndarray          # position on the (4N+1)^2 lattice of the refined level
+    boundaries: Dict[str, np.ndarray]
+    element_type: str
+    vertex_mask: np.ndarray
+    hanging: HangingNodes
+    parent_element: np.ndarray        # [n_elem] element of the unrefined mesh
+
+    @property
+    def n_elem(self) -> int:
+        return self.elem_nodes.shape[0]
+
+    @property
+    def n_node(self) -> int:
+        return self.node_pos.shape[0]
+
+    def is_vertex(self) -> np.ndarray:
+        return self.vertex_mask
+
+
+def _lag3(s: float) -> np.ndarray:
+    return np.array([0.5 * s * (s - 1.0), 1.0 - s * s, 0.5 * s * (s + 1.0)])
+
+
+def refine_quad_mesh(mesh: StructuredMesh, refine: np.ndarray) -> RefinedQuadMesh:
+    """Split the elements flagged in `refine` ([n_elem] bool, element order of `mesh`) into their four sons.  New nodes are placed by the
+    father's Q9 mapping (so a distorted mesh is refined on its own geometry); on an edge between a refined and an unrefined element the
+    two quarter-point nodes hang on the three nodes of the coarse edge with the quadratic weights psi(-1/2), psi(+1/2) (C2 / position
+    values) and the coarse mid-edge node -- a vertex of the sons -- hangs on the two end vertices with weights 1/2 for the C1 values
+    (oomph-lib refineable_quad_element.cc, quad_hang_helper)."""
+    if mesh.dim != 2 or mesh.element_type != "Quad2dC2":
+        raise NotImplementedError("refinement with hanging nodes: Q9 meshes only")
+    refine = np.asarray(refine, dtype=bool)
+    Nx, Ny = mesh.N
+    assert refine.shape == (mesh.n_elem,)
+    key_of = {}
+    lat = mesh.node_lattice.astype(np.int64) * 2
+    for n in range(mesh.n_node):
+        key_of[(int(lat[n, 0]), int(lat[n, 1]))] = n
+    pos = [mesh.node_pos[n].copy() for n in range(mesh.n_node)]
+    flat = [tuple(int(v) for v in lat[n]) for n in range(mesh.n_node)]
+    elems, parent = [], []
+    psi1 = {k: _lag3(0.5 * k - 1.0) for k in range(5)}
+    for e in range(mesh.n_elem):
+        en = mesh.elem_nodes[e]
+        if not refine[e]:
+            elems.append(en.copy())
+            parent.append(e)
+            continue
+        ex, ey = e // Ny, e % Ny
+        X = mesh.node_pos[en]                      # [9, 2], local index i + 3 j
+        grid = np.empty((5, 5), dtype=np.int64)
+        for fj in range(5):
+            for fi in range(5):
+                key = (4 * ex + fi, 4 * ey + fj)
+                if key not in key_of:
+                    w = np.outer(psi1[fj], psi1[fi]).ravel()        # psi_{i + 3 j}(s) = L_i(s0) L_j(s1)
+                    key_of[key] = len(pos)
+                    pos.append(w @ X)
+                    flat.append(key)
+                grid[fi, fj] = key_of[key]
+        for b in range(2):              # sons SW, SE, NW, NE
+            for a in range(2):
+                elems.append(np.array([grid[2 * a + i, 2 * b + j] for j in range(3) for i in range(3)], dtype=np.int32))
+                parent.append(e)
+    hang_C2, hang_C1 = {}, {}
+    rgrid = refine.reshape(Nx, Ny)
+    for ex in range(Nx):
+        for ey in range(Ny):
+            if not rgrid[ex, ey]:
+                continue
+            # (neighbour offset, fine keys of the five nodes along the shared edge)
+            edges = [((-1, 0), [(4 * ex, 4 * ey + k) for k in range(5)]), ((1, 0), [(4 * ex + 4, 4 * ey + k) for k in range(5)]),
+                     ((0, -1), [(4 * ex + k, 4 * ey) for k in range(5)]), ((0, 1), [(4 * ex + k, 4 * ey + 4) for k in range(5)])]
+            for (dx, dy), keys in edges:
+                nx, ny = ex + dx, ey + dy
+                if not (0 <= nx < Nx and 0 <= ny < Ny) or rgrid[nx, ny]:
+                    continue
+                nodes = [key_of[k] for k in keys]
+                masters = np.array([nodes[0], nodes[2], nodes[4]], dtype=np.int64)
+                hang_C2[nodes[1]] = (masters, _lag3(-0.5))
+                hang_C2[nodes[3]] = (masters, _lag3(0.5))
+                hang_C1[nodes[2]] = (np.array([nodes[0], nodes[4]], dtype=np.int64), np.array([0.5, 0.5]))
+    elem_nodes = np.ascontiguousarray(np.stack(elems), dtype=np.int32)
+    node_pos = np.ascontiguousarray(np.stack(pos), dtype=np.float64)
+    # positions of hanging nodes are the interpolation of their masters (BulkElementBase::interpolate_hang_values, src/elements.cpp:448)
+    for n, (m, w) in hang_C2.items():
+        node_pos[n] = w @ node_pos[m]
+    node_lat = np.array(flat, dtype=np.int32)
+    vertex = np.zeros(node_pos.shape[0], dtype=bool)
+    vertex[elem_nodes[:, [0, 2, 6, 8]].ravel()] = True
+    boundaries = {"left": np.nonzero(node_lat[:, 0] == 0)[0], "right": np.nonzero(node_lat[:, 0] == 4 * Nx)[0],
+                  "bottom": np.nonzero(node_lat[:, 1] == 0)[0], "top": np.nonzero(node_lat[:, 1] == 4 * Ny)[0]}
+    return RefinedQuadMesh(2, elem_nodes, node_pos, node_lat, boundaries, "Quad2dC2", vertex, HangingNodes(hang_C2, hang_C1), np.array(parent, dtype=np.int64))
+
+
+@dataclasses.dataclass
 class DofMap:
     node_eqn: np.ndarray             # [n_node, nval] int32, -1 pinned
     pos_eqn: Optional[np.ndarray]    # [n_node, dim] int32 or None
@@ -241,7 +355,8 @@ class DofMap:
 def assign_equation_numbers(mesh: StructuredMesh, code: FiniteElementCode,
                             pinned: Optional[Dict[str, Iterable[int]]] = None,
                             pinned_positions: Optional[Dict[str, Iterable[int]]] = None) -> DofMap:
-    """Global equation numbers in oomph's order (mesh.cc:686-708): node by node; positions first."""
+    """Global equation numbers in oomph's order (mesh.cc:686-708): node by node; positions first.  Hanging values (mesh.hanging) are
+    constrained: no equation (oomph-lib Data::Is_constrained)."""
     nval = code.n_nodal_values
     n_node, dim = mesh.n_node, mesh.dim
     free = np.ones((n_node, nval), dtype=bool)
@@ -249,6 +364,14 @@ def assign_equation_numbers(mesh: StructuredMesh, code: FiniteElementCode,
     for f in code.nodal_fields():
         if f.space == "C1":
             free[~vertex, f.index] = False     # dummy values on non-vertex nodes (src/elements.cpp:2235-2271)
+    hanging = getattr(mesh, "hanging", None)
+    if hanging is not None:
+        if code.coordinates_as_dofs:
+            raise NotImplementedError("hanging nodes on a moving mesh (hanging position dofs)")
+        for f in code.nodal_fields():
+            hn = np.fromiter(hanging.of_space(f.space).keys(), dtype=np.int64)
+            if hn.size:
+                free[hn, f.index] = False
     for name, nodes in (pinned or {}).items():
         free[np.asarray(list(nodes) if not isinstance(nodes, np.ndarray) else nodes, dtype=np.int64), code.fields[name].index] = False
     if code.coordinates_as_dofs:

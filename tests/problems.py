@@ -127,6 +127,28 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
             pinned = {"velocity_x": wall, "velocity_y": wall}
             unsteady = True
+    elif kind in ("poisson_hang", "ns_hang", "ns_unsteady_hang"):
+        # one level of quadtree refinement of some elements of a (distorted) Q9 mesh: hanging nodes on the edges between refined and
+        # unrefined elements (a14; the same element classes -- hanging is a property of the mesh, the generated code is the same)
+        import pyoomph_b200.meshes as _mm
+        base = _mm.RectangularQuadMesh(N)
+        if distortion:
+            base = distort(base, distortion, seed)
+        rng = np.random.default_rng(seed + 11)
+        flags = np.zeros((N, N), dtype=bool)
+        flags[N // 3: N // 3 + max(2, N // 3), N // 4: N // 4 + max(2, N // 2)] = True          # a block inside the mesh
+        flags[0, 0] = flags[-1, -2] = True                                                       # corner / boundary elements
+        flags |= rng.random((N, N)) < 0.08                                                       # isolated refined elements
+        mesh = _mm.refine_quad_mesh(base, flags.ravel())
+        if kind == "poisson_hang":
+            code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")
+            pinned = {"u": np.concatenate([mesh.boundaries["left"], mesh.boundaries["right"]])}
+            unsteady = False
+        else:
+            code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0), name="ns")
+            wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "right", "bottom", "top")]))
+            pinned = {"velocity_x": wall, "velocity_y": wall, "pressure": np.array([0])}
+            unsteady = kind == "ns_unsteady_hang"
     elif kind == "poisson":          # config 1
         mesh = RectangularQuadMesh(N)
         code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")
@@ -247,6 +269,12 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
     for t in range(T):
         for f in range(nval):
             vals[t, :, f] = smooth_field(mesh.node_pos, f + 3 * t, seed) * (1.0 - 0.05 * t)
+    hanging = getattr(mesh, "hanging", None)
+    if hanging is not None:
+        # hanging values are the interpolation of their masters (Node::value on a hanging node), for every history level
+        for f in code.nodal_fields():
+            for n, (m, w) in hanging.of_space(f.space).items():
+                vals[:, n, f.index] = vals[:, m, f.index] @ w
     pos_hist = None
     if code.coordinates_as_dofs:
         pos_hist = np.stack([mesh.node_pos + 1e-3 * (1 + 0.3 * t) * np.stack(

@@ -618,3 +618,56 @@ def test_interface_class_assembled_into_the_matrix_of_its_bulk_class(kind, N, di
     for o in (ob, oi):
         o.close()
     bulk.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N,distortion", [("poisson_hang", 8, 0.12), ("ns_hang", 6, 0.1), ("ns_unsteady_hang", 6, 0.08), ("ns_hang", 24, 0.05)])
+def test_hanging_nodes_parity(kind, N, distortion):
+    """a14: a mesh with hanging nodes (one quadtree level).  Oracle: the reference's hang macros inside the element routine with its
+    local numbering of the master values.  Product: the unchanged element kernel over virtual equations for the hanging values, then
+    P^T J_ext P on the device (fixed-order gathers).  Compared: residual, Jacobian, mass matrix of the real equations; CSR bit-exact after
+    the zero-drop rule."""
+    from problems import TIME
+    from pyoomph_b200.hanging import HangingNodeAssembly
+    pb = make_problem(kind, N, distortion=distortion)
+    op = make_oracle(pb)
+    n = pb["dofmap"].n_dof
+    flag = 2 if pb["unsteady"] else 1
+    r_ref, mats = op.assemble(flag=flag)
+    asm = HangingNodeAssembly(pb["code"], pb["mesh"], pb["dofmap"], name=pb["code"].name)
+    assert asm.n_dof == n and asm.n_ext > n
+    for t in range(pb["vals"].shape[0]):
+        asm.set_nodal_values(t, pb["vals"][t])
+    if pb["unsteady"]:
+        asm.set_unsteady(TIME["t"], TIME["dt"], TIME["dtprev"], TIME["unsteady_steps_done"])
+    else:
+        asm.set_steady()
+    for rep in range(2):                   # the second assembly starts from the reduced matrix of the first
+        asm.assemble(flag=flag)
+        r, jac, mass = asm.fetch(True, flag == 2)
+        assert np.abs(r - r_ref).max() <= TOL * np.abs(r_ref).max()
+        for vals, ref in zip((jac, mass), mats):
+            err, missing = compare_matrix(csr_to_sorted(n, asm.indptr, asm.indices, vals), csr_to_sorted(n, *ref))
+            assert missing == 0 and err <= TOL, (kind, rep, err, missing)
+    st = assert_csr_parity(asm.indptr, asm.indices, jac, mats[0], TOL, label="%s N=%d" % (kind, N), max_cancel_fraction=0.02)
+    _record(kind, N, distortion, False, st)
+    # the device holds J (+) I over the extended equations: virtual rows / columns cleared, unit diagonal, zero residual
+    r_ext, j_ext, _ = asm.fetch_extended(True, False)
+    A = csr_to_sorted(asm.n_ext, asm.asm.indptr, asm.asm.indices, j_ext)
+    nv = asm.n_ext - n
+    assert np.array_equal(A[n:, n:].toarray(), np.eye(nv)) and abs(A[n:, :n]).max() == 0.0 and abs(A[:n, n:]).max() == 0.0
+    assert np.all(r_ext[n:] == 0.0)
+    # a dof vector scattered on the device: hanging values follow their masters (pinned masters included)
+    ne = pb["dofmap"].node_eqn
+    u = np.zeros(n)
+    u[ne[ne >= 0]] = pb["vals"][0][ne >= 0]
+    asm.set_dofs(u)
+    asm.assemble(flag=1)
+    r2, jac2, _ = asm.fetch(True, False)
+    assert np.abs(r2 - r_ref).max() <= TOL * np.abs(r_ref).max()
+    # bit-reproducible (fixed-order gathers, no atomics in the reduction)
+    asm.assemble(flag=1)
+    r3, jac3, _ = asm.fetch(True, False)
+    assert np.array_equal(r2, r3) and np.array_equal(jac2, jac3)
+    op.close()
+    asm.close()
