@@ -426,6 +426,9 @@ class CEmitter:
             j = ex.DIRS.index(G[-1])
             if var_part.has(ex.DX_EUL):
                 var[ex.DX_EUL] = csym("shapeinfo->int_pt_weights_d_coords[%d][l_shape]" % j)
+            for i in range(self.dim):     # interface elements: the normal moves with the nodes (GiNaCNormalSymbol derivative -> d_normal_dcoord)
+                if var_part.has(ex.NORMAL[i]):
+                    var[ex.NORMAL[i]] = csym("shapeinfo->d_normal_dcoord[%d][l_shape][%d]" % (i, j))
             for s, sl in code._test_syms.items():
                 if sl.field == F and sl.deriv.startswith("dx") and var_part.has(s):
                     S = _space_shape_name(code, F)

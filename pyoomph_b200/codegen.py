@@ -494,6 +494,35 @@ class FiniteElementCode:
                     if slot.deriv.startswith("dx"):
                         sj = slot_index(TestSlot(slot.field, "dx%d" % j))
                         add(J, (sj, Xj, slot.deriv), -Rs)
+                    if self.etype.elem_dim < self.nodal_dim:
+                        # Interface elements (a line in 2D): dpsi_m/dx_d = t_d psi'_m / g is the SURFACE gradient (g = t.t), so
+                        #   d(dpsi_m/dx_d)/dX_j^l = -dpsi_m/dx_d dpsi_l/dx_j  +  n_d n_j (grad_S psi_m . grad_S psi_l)
+                        # (the first part is the bulk identity: tau_d tau_j is symmetric), d(dx)/dX_j^l = dx dpsi_l/dx_j as in the bulk,
+                        # and the unit normal n = (-t_y, t_x)/|t| moves with the nodes:
+                        #   d n_i / dX_j^l = -tau_i n_j psi'_l/|t| = -tau_i n_j (tau . grad_S psi_l),   tau = (n_y, -n_x)
+                        # (get_dnormal_dcoords_at_s, src/elements.cpp:1461-1490; the reference gets the gradient part from its general
+                        # el_dim x nodal_dim tensors, src/elements.cpp:3051-3155).
+                        if self.nodal_dim != 2:
+                            raise NotImplementedError("moving interface elements: lines in 2D only")
+                        nrm = ex.NORMAL[:2]
+                        tau = (nrm[1], -nrm[0])
+                        for a in atoms:
+                            info = self._atom_syms[a]
+                            if info.deriv.startswith("dx") and not info.past:
+                                d = int(info.deriv[2:])
+                                for b in range(2):
+                                    ab = self._atom(dataclasses.replace(info, deriv="dx%d" % b))
+                                    add(J, (si, Xj, "dx%d" % b), sp.diff(Rs, a) * nrm[d] * nrm[j] * ab)
+                        if slot.deriv.startswith("dx"):
+                            d = int(slot.deriv[2:])
+                            for b in range(2):
+                                sb = slot_index(TestSlot(slot.field, "dx%d" % b))
+                                add(J, (sb, Xj, "dx%d" % b), Rs * nrm[d] * nrm[j])
+                        for i in range(2):
+                            dRn = sp.diff(Rs, nrm[i])
+                            if dRn != 0:
+                                for b in range(2):
+                                    add(J, (si, Xj, "dx%d" % b), -dRn * tau[i] * nrm[j] * tau[b])
         used = set()
         for e in list(R) + list(J.values()) + list(M.values()):
             used |= {s for s in e.free_symbols if s in self._atom_syms}

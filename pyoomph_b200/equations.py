@@ -11,7 +11,7 @@ Scaling/non-dimensionalisation factors of the reference are all 1 here (no units
 from __future__ import annotations
 
 from .codegen import Equations
-from .expressions import (Weak, cartesian, div, dot, grad, identity_matrix, material_derivative, partial_t, rational_num, sym, trace, var,
+from .expressions import (Weak, cartesian, div, dot, grad, identity_matrix, material_derivative, mesh_velocity, partial_t, rational_num, sym, trace, var,
                           var_and_test, weak)
 
 
@@ -245,3 +245,50 @@ class FreeSurfaceOnFixedMesh(Equations):
         n = var("normal")
         self.add_residual(weak(self.sigma, div(v)))
         self.add_residual(weak(dot(u, n), ltest) + weak(l, dot(n, v)))
+
+
+class NavierStokesFreeSurface(Equations):
+    """Kinematic and dynamic boundary condition of a free surface (pyoomph/equations/navier_stokes.py:520-676), the interface class of
+    BASELINE config 4.  On a MOVING mesh (the bulk class solves for the nodal positions: ``static_interface=False`` / "auto" with
+    coordinates as dofs) the Lagrange multiplier field ``_kin_bc`` enforces  (mesh_velocity - u).n = 0  and acts on the position
+    equations:
+
+        weak((mesh_velocity() - u).n, l_test)  -  weak(l, n.x_test)  +  weak(sigma, div_S(u_test))  [+ weak(traction, n.u_test)]
+
+    (navier_stokes.py:641-655); on a static mesh it reduces to  -weak(u.n, l_test) + weak(l, n.u_test)  (:628-635).  The normal, the
+    surface divergence and the line measure all depend on the nodal positions: their derivatives enter the Jacobian columns of the
+    position dofs (codegen._coefficient_form, interface branch)."""
+
+    def __init__(self, *, surface_tension=1, kinbc_name: str = "_kin_bc", static_interface="auto", additional_normal_traction=0,
+                 velocity_name: str = "velocity", pressure_name: str = "pressure"):
+        super().__init__()
+        self.surface_tension, self.kinbc_name, self.static_interface = surface_tension, kinbc_name, static_interface
+        self.additional_normal_traction, self.velocity_name, self.pressure_name = additional_normal_traction, velocity_name, pressure_name
+        if static_interface not in ("auto", True, False):
+            raise RuntimeError("property static_interface must be either 'auto', True or False")
+
+    def define_fields(self):
+        # the nodal record of the bulk class: velocity, pressure (only its slot matters here), the multiplier
+        self.define_vector_field(self.velocity_name, "C2")
+        self.define_scalar_field(self.pressure_name, "C1")
+        self.define_scalar_field(self.kinbc_name, "C2")
+        if self.static_interface is False:
+            self.activate_coordinates_as_dofs()
+
+    def define_residuals(self):
+        n = var("normal")
+        u, u_test = var_and_test(self.velocity_name)
+        l, l_test = var_and_test(self.kinbc_name)
+        static = self.static_interface
+        if static == "auto":
+            static = not self.get_current_code_generator().coordinates_as_dofs
+        if static:
+            self.add_residual(weak(-dot(u, n), l_test))
+            self.add_residual(weak(l, dot(n, u_test)))
+        else:
+            _, R_test = var_and_test("mesh")
+            self.add_residual(weak(dot(mesh_velocity() - u, n), l_test))
+            self.add_residual(-weak(l, dot(n, R_test)))
+        self.add_residual(weak(self.surface_tension, div(u_test)))
+        if self.additional_normal_traction != 0:
+            self.add_residual(weak(self.additional_normal_traction, dot(n, u_test)))

@@ -76,12 +76,12 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             return _variant(_mk["brick"](n))
     else:
         from pyoomph_b200.meshes import CuboidBrickMesh, RectangularQuadMesh
-    if kind in ("robin_if", "freesurf_if"):
+    if kind in ("robin_if", "freesurf_if", "freesurf_mov_if"):
         # interface element classes (InterfaceElementLine1dC2) on boundary edges of a (distorted) Q9 mesh, on the bulk's nodes, nodal
         # values and equation numbers: a Robin condition for the Poisson field of config 1, and the free-surface terms of config 4
         # (surface tension, no-penetration through a Lagrange multiplier field on the interface) on a mesh that does not move
         import pyoomph_b200.meshes as _mm
-        from pyoomph_b200.equations import DeclareFields, FreeSurfaceOnFixedMesh, RobinBC
+        from pyoomph_b200.equations import DeclareFields, FreeSurfaceOnFixedMesh, NavierStokesFreeSurface, RobinBC
         from pyoomph_b200.expressions import var as _var
         bulk = _mm.RectangularQuadMesh(N)
         if distortion:
@@ -91,21 +91,38 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             code = FiniteElementCode("Line1dC2", RobinBC("u", alpha=2.5, external=lambda: _var("coordinate_x") * _var("coordinate_y"), flux=0.3), name="robinif")
             bulk_code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")
             pinned = {"u": bulk.boundaries["left"]}
+        elif kind == "freesurf_mov_if":
+            # config 4 as BASELINE names it: the free surface of a MOVING mesh (kinematic condition with the mesh velocity, the multiplier
+            # acting on the position equations; normal, surface divergence and line measure depend on the position dofs)
+            code = FiniteElementCode("Line1dC2", NavierStokesFreeSurface(surface_tension=0.7, static_interface=False), name="freesurfmov")
+            bulk_code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + PseudoElasticMesh() +
+                                          DeclareFields(_kin_bc="C2"), name="aleif")
+            wall = np.unique(np.concatenate([bulk.boundaries[b] for b in ("bottom", "right")]))
+            off_interface = np.setdiff1d(np.arange(bulk.n_node), np.unique(mesh.elem_nodes))
+            pinned = {"velocity_x": wall, "velocity_y": wall, "_kin_bc": off_interface}
         else:
             code = FiniteElementCode("Line1dC2", FreeSurfaceOnFixedMesh(surface_tension=0.7), name="freesurfif")
             bulk_code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + DeclareFields(_kin_bc="C2"), name="nsif")
             wall = np.unique(np.concatenate([bulk.boundaries[b] for b in ("bottom", "right")]))
             off_interface = np.setdiff1d(np.arange(bulk.n_node), np.unique(mesh.elem_nodes))
             pinned = {"velocity_x": wall, "velocity_y": wall, "_kin_bc": off_interface}     # the multiplier exists on the interface nodes only
-        unsteady = False
-        dofmap = assign_equation_numbers(bulk, bulk_code, pinned, None)
+        unsteady = kind == "freesurf_mov_if"
+        pinned_pos = None
+        if bulk_code.coordinates_as_dofs:
+            pinned_pos = {"coordinate_x": bulk.boundaries["right"], "coordinate_y": bulk.boundaries["bottom"]}
+        dofmap = assign_equation_numbers(bulk, bulk_code, pinned, pinned_pos)
         assert [f.name for f in code.nodal_fields()] == [f.name for f in bulk_code.nodal_fields()]
-        T, nval = code.history_levels(), code.n_nodal_values
+        assert code.coordinates_as_dofs == bulk_code.coordinates_as_dofs
+        T, nval = max(code.history_levels(), bulk_code.history_levels()) if unsteady else code.history_levels(), code.n_nodal_values
         vals = np.zeros((T, bulk.n_node, nval))
         for t in range(T):
             for f in range(nval):
                 vals[t, :, f] = smooth_field(bulk.node_pos, f + 3 * t, seed) * (1.0 - 0.05 * t)
-        return dict(kind=kind, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=None, unsteady=unsteady, params={}, bulk_mesh=bulk, bulk_code=bulk_code)
+        pos_hist = None
+        if code.coordinates_as_dofs:
+            pos_hist = np.stack([bulk.node_pos + 1e-3 * (1 + 0.3 * t) * np.stack(
+                [smooth_field(bulk.node_pos, 10 + d + 2 * t, seed) for d in range(bulk.dim)], axis=1) for t in range(T)])
+        return dict(kind=kind, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=pos_hist, unsteady=unsteady, params={}, bulk_mesh=bulk, bulk_code=bulk_code)
     if kind in ("poisson_tri", "ns_tri", "ale_tri"):
         # six-node triangles (the element class of the reference's gmsh droplet meshes): Poisson, Taylor-Hood P2/P1 Navier-Stokes,
         # and NS on a pseudo-elastic moving mesh

@@ -552,7 +552,9 @@ def test_point_expressions_parity(kind, N, distortion, unstructured):
     op.close(); asm.close()
 
 
-INTERFACES = [("robin_if", 6, 0.12), ("robin_if", 9, 0.0), ("freesurf_if", 5, 0.1), ("freesurf_if", 24, 0.05)]
+INTERFACES = [("robin_if", 6, 0.12), ("robin_if", 9, 0.0), ("freesurf_if", 5, 0.1), ("freesurf_if", 24, 0.05),
+              # config 4's interface class on a MOVING mesh: kinematic condition with the mesh velocity, position dofs in the Jacobian
+              ("freesurf_mov_if", 5, 0.1), ("freesurf_mov_if", 20, 0.06)]
 
 
 @pytest.mark.gpu
@@ -583,7 +585,7 @@ def test_interface_element_classes_parity(kind, N, distortion):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,N,distortion", [("robin_if", 7, 0.1), ("freesurf_if", 6, 0.1), ("freesurf_if", 40, 0.0)])
+@pytest.mark.parametrize("kind,N,distortion", [("robin_if", 7, 0.1), ("freesurf_if", 6, 0.1), ("freesurf_if", 40, 0.0), ("freesurf_mov_if", 6, 0.08)])
 def test_interface_class_assembled_into_the_matrix_of_its_bulk_class(kind, N, distortion):
     """A child problem (pb2_problem_create_child): the interface class scatters into the CSR matrix and residual its bulk class just
     wrote, on the device; the sum equals the oracle's two classes assembled into one matrix (oomph assembles all element classes of a

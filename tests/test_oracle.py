@@ -483,3 +483,51 @@ def test_interface_elements_of_the_oracle():
                 op.update_values(0, pb["vals"][0])
                 assert np.abs((rp - rm) / (2 * eps) - A[:, g]).max() <= 1e-8 * max(np.abs(A).max(), 1e-300)
         op.close()
+
+
+def test_moving_free_surface_of_the_oracle_matches_finite_differences():
+    """NavierStokesFreeSurface on a moving mesh (config 4's interface class): Jacobian columns of velocities, the multiplier AND the
+    nodal positions -- derivative of the unit normal (d_normal_dcoord, src/elements.cpp:1461-1490), of the line measure and of the surface
+    gradients of the test functions (the el_dim x nodal_dim tensors of src/elements.cpp:3051-3155) -- against central differences of the
+    residual, BDF2 step with mesh velocity"""
+    from problems import csr_to_sorted, make_oracle, make_problem
+    pb = make_problem("freesurf_mov_if", 4, distortion=0.12)
+    assert pb["code"].coordinates_as_dofs and pb["unsteady"]
+    op = make_oracle(pb)
+    _, mats = op.assemble(flag=1)
+    n = pb["dofmap"].n_dof
+    A = csr_to_sorted(n, *mats[0]).toarray()
+    scale = np.abs(A).max()
+    eq, peq, eps = pb["dofmap"].node_eqn, pb["dofmap"].pos_eqn, 1e-6
+    nodes = np.unique(pb["mesh"].elem_nodes)
+    checked_pos = 0
+    for node in nodes[:7]:
+        for f in range(eq.shape[1]):
+            g = eq[node, f]
+            if g < 0:
+                continue
+            v = pb["vals"][0].copy()
+            v[node, f] += eps
+            op.update_values(0, v)
+            rp, _ = op.assemble(flag=0)
+            v[node, f] -= 2 * eps
+            op.update_values(0, v)
+            rm, _ = op.assemble(flag=0)
+            op.update_values(0, pb["vals"][0])
+            assert np.abs((rp - rm) / (2 * eps) - A[:, g]).max() <= 1e-8 * scale, ("value", node, f)
+        for d in range(2):
+            g = peq[node, d]
+            if g < 0:
+                continue
+            x = pb["pos_hist"][0].copy()
+            x[node, d] += eps
+            op.update_values(0, None, x)
+            rp, _ = op.assemble(flag=0)
+            x[node, d] -= 2 * eps
+            op.update_values(0, None, x)
+            rm, _ = op.assemble(flag=0)
+            op.update_values(0, None, pb["pos_hist"][0])
+            assert np.abs((rp - rm) / (2 * eps) - A[:, g]).max() <= 2e-8 * scale, ("position", node, d)
+            checked_pos += 1
+    assert checked_pos >= 8
+    op.close()
