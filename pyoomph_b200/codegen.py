@@ -207,7 +207,19 @@ class FiniteElementCode:
 
     def add_residual(self, expr, destination: str = ""):
         expr = sp.sympify(expr)
-        self.residuals[destination] = self.residuals.get(destination, sp.Integer(0)) + expr
+        cs = self.coordinate_system
+        if getattr(cs, "has_normal_mode_expansion", False):
+            # Problem._residual_mapping_functions of define_problem_for_axial_symmetry_breaking_investigation
+            # (pyoomph/generic/problem.py:4543-4558): one residual -> base mode + real / imaginary part of the angular eigenproblem
+            parts = {destination: cs.map_residual_on_base_mode(expr),
+                     cs.real_contribution_name + destination: cs.map_residual_on_angular_eigenproblem_real(expr),
+                     cs.imag_contribution_name + destination: cs.map_residual_on_angular_eigenproblem_imag(expr)}
+        else:
+            parts = {destination: expr}
+        for dest, e in parts.items():
+            if e == 0 and dest != destination:
+                continue                     # e.g. the imaginary part of a scalar diffusion operator: no empty routines
+            self.residuals[dest] = self.residuals.get(dest, sp.Integer(0)) + e
 
     def residual_names(self) -> List[str]:
         return list(self.residuals.keys())
@@ -411,8 +423,17 @@ class FiniteElementCode:
             if dt > 2:
                 raise RuntimeError("Too high dt order")
             scheme = self._time_scheme(dt) if dt else ""
+            if field.endswith(ex.MODE_SUFFIX) and field not in self.fields and field[:-len(ex.MODE_SUFFIX)] not in self.fields:
+                raise RuntimeError("mode copy of an unknown field: " + field)
             repl[d] = self._atom(AtomInfo(field, dt, scheme, deriv, past))
         return expr.xreplace(repl)
+
+    def _mode_base(self, field: str) -> Optional[str]:
+        """base field of a perturbation-mode copy that is NOT a field of its own (the azimuthal eigenvector lives on the dofs of the
+        base fields); None for ordinary fields"""
+        if field.endswith(ex.MODE_SUFFIX) and field not in self.fields:
+            return field[:-len(ex.MODE_SUFFIX)]
+        return None
 
     # -- derivation ----------------------------------------------------------------------------
     def unknown_field_names(self) -> List[str]:
@@ -461,22 +482,31 @@ class FiniteElementCode:
                 R.append(sp.Integer(0))
             return slots.index(slot)
 
+        # Angular eigenproblem contributions (azimuthal stability): the residual is linear in the mode copies U__M1 of the fields; its
+        # Jacobian and mass matrix are taken with respect to THEM (expansion_mode tags, src/codegen.cpp:7567, :8196) and land in the
+        # columns of the base fields' dofs; afterwards the copies are evaluated at the base state.
+        mode_atoms = {s: self._atom_syms[s] for s in E.free_symbols if s in self._atom_syms and self._mode_base(self._atom_syms[s].field)}
         nslot0 = len(slots)
         for si in range(nslot0):
             Rs = R[si]
             atoms = [s for s in Rs.free_symbols if s in self._atom_syms]
             for a in atoms:
                 info = self._atom_syms[a]
-                if info.past or info.field not in unknowns:
+                col_field = info.field
+                if mode_atoms:
+                    if a not in mode_atoms:
+                        continue
+                    col_field = self._mode_base(info.field)
+                if info.past or col_field not in unknowns:
                     continue  # history values and non-dof data carry no Jacobian (src/codegen.cpp:8256)
                 c = sp.diff(Rs, a)
                 if info.dt_order == 0:
-                    add(J, (si, info.field, info.deriv), c)
+                    add(J, (si, col_field, info.deriv), c)
                 else:
                     w = sp.Symbol("W__%s__%d" % (info.scheme, info.dt_order), real=True)
-                    add(J, (si, info.field, info.deriv), w * c)
+                    add(J, (si, col_field, info.deriv), w * c)
                     if info.dt_order == 1:
-                        add(M, (si, info.field, info.deriv), c)  # __partial_t_mass_matrix (src/codegen.cpp:8260)
+                        add(M, (si, col_field, info.deriv), c)  # __partial_t_mass_matrix (src/codegen.cpp:8260)
             if self.coordinates_as_dofs:
                 RE = ex.DX_EUL * sp.diff(Rs, ex.DX_EUL)  # Eulerian-measure part
                 slot = slots[si]
@@ -523,6 +553,13 @@ class FiniteElementCode:
                             if dRn != 0:
                                 for b in range(2):
                                     add(J, (si, Xj, "dx%d" % b), -dRn * tau[i] * nrm[j] * tau[b])
+        if mode_atoms:
+            if self.coordinates_as_dofs:
+                raise NotImplementedError("mode expansion on a moving mesh")
+            to_base = {s: self._atom(dataclasses.replace(i, field=self._mode_base(i.field))) for s, i in mode_atoms.items()}
+            R = [e.xreplace(to_base) for e in R]
+            J = {k: v.xreplace(to_base) for k, v in J.items()}
+            M = {k: v.xreplace(to_base) for k, v in M.items()}
         used = set()
         for e in list(R) + list(J.values()) + list(M.values()):
             used |= {s for s in e.free_symbols if s in self._atom_syms}

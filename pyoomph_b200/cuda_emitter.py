@@ -722,6 +722,10 @@ class CudaEmitter:
         vecP = os.environ.get("PB2_VEC_P", "1") != "0"
         if vecP:
             PB = (PB + 1) // 2 * 2                       # even point block: coefficients are read and written as double2
+            if (PB // 2) % 2 == 0 and os.environ.get("PB2_PB_PAD", "1") != "0":
+                PB += 2                                  # odd number of 16-byte units per point: the (element, point) threads of phase 1 write their
+                #                                          blocks with STS.128 at a stride of PB doubles -- an even count puts all 8 lanes of a quarter
+                #                                          warp on one bank group (measured on Q27 heat: 174 of 201 wavefronts per element were conflicts)
             PT_S = NIPT * PB
             if (PT_S // 2) % 2 == 0:
                 PT_S += 2                                # element stride = odd number of 16-byte units: elements of a warp hit different bank groups

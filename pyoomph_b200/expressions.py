@@ -62,16 +62,29 @@ class TestFunctionSymbol(sp.Function):
     is_real = True
 
 
+MODE_SUFFIX = "__M1"      # name suffix of the perturbation-mode copy of a field (GiNaC_eval_at_expansion_mode(expr, 1))
+
+
 def _field(name: str) -> sp.Expr:
     code = _Context.current()
     code._require_field(name)
-    return sp.Function("F__" + name, real=True)(*_args(code.nodal_dim))
+    f = sp.Function("F__" + name, real=True)(*_args(code.nodal_dim))
+    cs = code.coordinate_system
+    if getattr(cs, "has_normal_mode_expansion", False) and cs.expands(code, name):
+        # U = U_base + eps * U_mode * exp(i m phi)   (AxisymmetryBreakingCoordinateSystem.get_mode_expansion_of_var_or_test, coordsys.py:989-1016)
+        f1 = sp.Function("F__" + name + MODE_SUFFIX, real=True)(*_args(code.nodal_dim))
+        return f + cs.expansion_eps * f1 * cs.field_mode
+    return f
 
 
 def _test(name: str) -> sp.Expr:
     code = _Context.current()
     code._require_field(name)
-    return sp.Function("T__" + name, real=True)(*_args(code.nodal_dim))
+    t = sp.Function("T__" + name, real=True)(*_args(code.nodal_dim))
+    cs = code.coordinate_system
+    if getattr(cs, "has_normal_mode_expansion", False) and cs.expands(code, name):
+        return t * cs.test_mode              # test functions carry exp(-i m phi)
+    return t
 
 
 def _vector_components(code, name: str) -> Optional[List[str]]:
@@ -240,6 +253,89 @@ class AxisymmetricCoordinateSystem(BaseCoordinateSystem):
         return sp.Matrix([sp.diff(T[0, 0], x) + (T[0, 0] - T[2, 2]) / r + sp.diff(T[1, 0], y),
                           sp.diff(T[0, 1], x) + T[0, 1] / r + sp.diff(T[1, 1], y),
                           sp.diff(T[0, 2], x) + (T[0, 2] - T[2, 0]) / r + sp.diff(T[1, 2], y)])
+
+
+class AxisymmetryBreakingCoordinateSystem(AxisymmetricCoordinateSystem):
+    """Azimuthal normal-mode expansion about an axisymmetric base state (pyoomph/expressions/coordsys.py:967-1200; BASELINE config 5):
+    every field is  U_base(r,z) + eps * U_mode(r,z) * exp(i m phi),  every test function carries  exp(-i m phi),  and the operators keep
+    their phi-derivatives: grad s = (d_r s, d_z s, d_phi s / r), the third column of grad v gets (d_phi v_r - v_phi)/r, d_phi v_z / r,
+    (d_phi v_phi + v_r)/r, div v gets d_phi v_phi / r.  A residual R then yields three contributions (`map_residual_*`):
+
+      base           R at eps = 0, m = 0                                          -> the axisymmetric problem
+      real_contrib_azimuthal_stability, imag_contrib_azimuthal_stability
+                     Re / Im of dR/d(eps) at eps = 0 with m the azimuthal mode    -> their Jacobians / mass matrices with respect to the
+                                                                                   MODE fields are Re/Im of the m-dependent linear operator
+
+    The mode fields are not new nodal values: they stand on the dofs of their base fields (the eigenvector lives on the same equations),
+    which is how codegen._coefficient_form differentiates them.  Fixed meshes only."""
+    has_normal_mode_expansion = True
+    real_contribution_name = "real_contrib_azimuthal_stability"      # pyoomph/generic/problem.py:101-102
+    imag_contribution_name = "imag_contrib_azimuthal_stability"
+
+    def __init__(self, angular_mode="azimuthal_m"):
+        self.angular_mode = angular_mode if isinstance(angular_mode, str) else sp.sympify(angular_mode)
+        self.expansion_eps = sp.Symbol("EPS__mode_expansion", real=True)
+        self.m_angular_symbol = sp.Symbol("M__angular", real=True)
+        self.phi = sp.Symbol("PHI__angular", real=True)
+        self.field_mode = sp.exp(sp.I * self.m_angular_symbol * self.phi)
+        self.test_mode = sp.exp(-sp.I * self.m_angular_symbol * self.phi)
+
+    def expands(self, code, fieldname: str) -> bool:
+        if fieldname.endswith(MODE_SUFFIX):
+            return False
+        if fieldname.startswith("lagrangian_") or fieldname.startswith("coordinate_"):
+            if code.coordinates_as_dofs and fieldname.startswith("coordinate_"):
+                raise NotImplementedError("azimuthal mode expansion on a moving mesh")
+            return False
+        return True
+
+    def scalar_gradient(self, arg, lagrangian: bool):
+        cs = _coords(lagrangian)
+        third = sp.Integer(0) if lagrangian else sp.diff(arg, self.phi) / self._r(lagrangian)
+        return sp.Matrix([sp.diff(arg, cs[0]), sp.diff(arg, cs[1]), third])
+
+    def vector_gradient(self, arg, lagrangian: bool):
+        G = super().vector_gradient(arg, lagrangian)
+        if not lagrangian:
+            r = self._r(lagrangian)
+            for i in range(3):
+                G[i, 2] += sp.diff(arg[i, 0], self.phi) / r
+        return G
+
+    def vector_divergence(self, arg, lagrangian: bool):
+        d = super().vector_divergence(arg, lagrangian)
+        if not lagrangian:
+            d += sp.diff(arg[2, 0], self.phi) / self._r(lagrangian)
+        return d
+
+    def tensor_divergence(self, T, lagrangian: bool):
+        d = super().tensor_divergence(T, lagrangian)
+        if not lagrangian:
+            r = self._r(lagrangian)
+            for j in range(3):
+                d[j, 0] += sp.diff(T[2, j], self.phi) / r
+        return d
+
+    # ---- the three contributions of a residual (coordsys.py:1018-1041)
+    def map_residual_on_base_mode(self, residual):
+        return sp.sympify(residual).subs(self.expansion_eps, 0).subs(self.m_angular_symbol, 0).doit()
+
+    def _first_order(self, residual):
+        e = sp.diff(sp.expand(sp.sympify(residual)), self.expansion_eps).subs(self.expansion_eps, 0).doit()
+        e = sp.expand(sp.powsimp(sp.expand(e)))               # exp(i m phi) exp(-i m phi) -> 1
+        if e.has(self.phi):
+            raise RuntimeError("the first-order mode expansion still depends on the azimuthal angle: " + str(e))
+        m = self.angular_mode
+        if isinstance(m, str):               # a global parameter by name (pyoomph: "azimuthal_m", problem.py:103)
+            m = _Context.current()._global_param_symbol(m)
+        return e.subs(self.m_angular_symbol, m)
+
+    def map_residual_on_angular_eigenproblem_real(self, residual):
+        e = self._first_order(residual)
+        return sp.expand(e - sp.I * e.coeff(sp.I))
+
+    def map_residual_on_angular_eigenproblem_imag(self, residual):
+        return sp.expand(self._first_order(residual).coeff(sp.I))
 
 
 cartesian = CartesianCoordinateSystem()

@@ -267,6 +267,26 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
             pinned = {"velocity_x": wall, "velocity_y": wall}
         unsteady = True
+    elif kind in ("ns_azi", "ns_azi_ext"):
+        # config 5 as BASELINE names it: azimuthal normal-mode expansion exp(i m phi) about the axisymmetric NS base flow with swirl.
+        # "ns_azi": the product's class -- base residual + real / imaginary contribution of the angular eigenproblem, the mode fields
+        # standing on the dofs of the base fields.  "ns_azi_ext": the checker's class -- the SAME expanded residuals, but the mode fields
+        # declared as nodal fields of their own, so that the ordinary Jacobian machinery of the oracle differentiates with respect to them.
+        from pyoomph_b200.equations import DeclareFields
+        from pyoomph_b200.expressions import MODE_SUFFIX, AxisymmetryBreakingCoordinateSystem
+        mesh = RectangularQuadMesh(N)
+        eqs = NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0, with_azimuthal_velocity=True)
+        base_names = ["velocity_x", "velocity_y", "velocity_phi", "pressure"]
+        if kind == "ns_azi_ext":
+            eqs = eqs + DeclareFields(**{n + MODE_SUFFIX: ("C1" if n == "pressure" else "C2") for n in base_names})
+        code = FiniteElementCode("Quad2dC2", eqs, name="nsazi" if kind == "ns_azi" else "nsaziext", coordinate_system=AxisymmetryBreakingCoordinateSystem("azimuthal_m"))
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("right", "bottom", "top")]))
+        pinned = {"velocity_x": np.unique(np.concatenate([wall, mesh.boundaries["left"]])), "velocity_y": wall,
+                  "velocity_phi": np.unique(np.concatenate([mesh.boundaries["right"], mesh.boundaries["left"]]))}
+        if kind == "ns_azi_ext":
+            pinned.update({n + MODE_SUFFIX: v for n, v in list(pinned.items())})
+        unsteady = True
+        params = {"azimuthal_m": 1.0}
     elif kind == "ale_axi":        # config 4 bulk part as BASELINE names it: axisymmetric NS-TH on a pseudo-elastic moving mesh
         mesh = RectangularQuadMesh(N)
         code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + PseudoElasticMesh(),
@@ -286,6 +306,13 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
     for t in range(T):
         for f in range(nval):
             vals[t, :, f] = smooth_field(mesh.node_pos, f + 3 * t, seed) * (1.0 - 0.05 * t)
+    if kind == "ns_azi_ext":
+        # base and mode fields carry the values the product's class has in its base fields (the contributions are evaluated at the base state)
+        from pyoomph_b200.expressions import MODE_SUFFIX
+        base = make_problem("ns_azi", N, seed, distortion, unstructured)
+        for f in base["code"].nodal_fields():
+            vals[:, :, code.fields[f.name].index] = base["vals"][:, :, f.index]
+            vals[:, :, code.fields[f.name + MODE_SUFFIX].index] = base["vals"][:, :, f.index]
     hanging = getattr(mesh, "hanging", None)
     if hanging is not None:
         # hanging values are the interpolation of their masters (Node::value on a hanging node), for every history level

@@ -575,7 +575,10 @@ def test_interface_element_classes_parity(kind, N, distortion):
     B = csr_to_sorted(n, *mats[0])
     err, missing = compare_matrix(A, B)
     assert missing == 0 and err <= TOL, (kind, err, missing)
-    st = assert_csr_parity(asm.indptr, asm.indices, jac, mats[0], TOL, label="%s N=%d" % (kind, N), max_cancel_fraction=0.02 if distortion > 0 else 0.30)
+    # moving interface: sliding a node ALONG the line changes no integral, so the tangential position columns are analytic zeros that
+    # come out as cancellation noise on both sides (measured 15 % of the entries); no value is outside the bar on the row scale
+    st = assert_csr_parity(asm.indptr, asm.indices, jac, mats[0], TOL, label="%s N=%d" % (kind, N),
+                           max_cancel_fraction=0.30 if (distortion == 0 or kind == "freesurf_mov_if") else 0.02)
     _record(kind, N, distortion, False, st)
     asm.assemble(flag=0)
     r0, _, _ = asm.fetch(False, False)
