@@ -676,3 +676,76 @@ def test_hanging_nodes_parity(kind, N, distortion):
     assert np.array_equal(r2, r3) and np.array_equal(jac2, jac3)
     op.close()
     asm.close()
+
+
+def _azimuthal_maps(pb, pbx):
+    """selection matrices between the product's numbering and the checker's extended class: rows = base-field equations, columns =
+    equations of the mode copies (scipy CSR, n_ext x n)"""
+    from scipy.sparse import csr_matrix
+    from pyoomph_b200.expressions import MODE_SUFFIX
+    n, nx = pb["dofmap"].n_dof, pbx["dofmap"].n_dof
+    rr, rc, cr, cc = [], [], [], []
+    for f in pb["code"].nodal_fields():
+        g = pb["dofmap"].node_eqn[:, f.index]
+        gb = pbx["dofmap"].node_eqn[:, pbx["code"].fields[f.name].index]
+        gm = pbx["dofmap"].node_eqn[:, pbx["code"].fields[f.name + MODE_SUFFIX].index]
+        live = g >= 0
+        assert np.array_equal(live, gb >= 0) and np.array_equal(live, gm >= 0)
+        rr += list(gb[live]); rc += list(g[live]); cr += list(gm[live]); cc += list(g[live])
+    Sr = csr_matrix((np.ones(len(rr)), (rr, rc)), shape=(nx, n))
+    Sc = csr_matrix((np.ones(len(cr)), (cr, cc)), shape=(nx, n))
+    return Sr, Sc
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,distortion", [(4, 0.1), (7, 0.0)])
+def test_azimuthal_mode_contributions_parity(N, distortion):
+    """BASELINE config 5: real and imaginary contribution of the azimuthal (m = 1, then m = 2) eigenproblem of axisymmetric NS with swirl:
+    Jacobian and mass matrix with respect to the mode fields, and the Hessian-vector products d(J.Y)/dU with respect to the BASE state
+    that the azimuthal Hopf / fold trackers assemble.  The checker assembles an extended element class in which the mode fields are
+    ordinary nodal fields and takes the (base rows, mode columns) block."""
+    from problems import TIME
+    pb = make_problem("ns_azi", N, distortion=distortion)
+    pbx = make_problem("ns_azi_ext", N, distortion=distortion)
+    Sr, Sc = _azimuthal_maps(pb, pbx)
+    n, nx = pb["dofmap"].n_dof, pbx["dofmap"].n_dof
+    asm = make_gpu(pb)
+    op = make_oracle(pbx)
+    names = pb["code"].residual_names()
+    assert names == pbx["code"].residual_names() and len(names) == 3
+    rng = np.random.default_rng(5)
+    for m in (1.0, 2.0):
+        asm.set_parameters(azimuthal_m=m)
+        op.set_params([m])
+        for which, rn in enumerate(names):
+            r_x, mats = op.assemble(which=which, flag=2)
+            asm.assemble(flag=2, residual=rn)
+            r, jac, mass = asm.fetch(True, True)
+            r_ref = Sr.T @ r_x
+            assert np.abs(r - r_ref).max() <= TOL * max(np.abs(r_ref).max(), 1e-300), (rn, m)
+            for vals, (rs, ci, va) in zip((jac, mass), mats):
+                Jx = csr_to_sorted(nx, rs, ci, va)
+                # base residual: its own Jacobian (base columns); contributions: the columns of the mode copies
+                B = (Sr.T @ Jx @ (Sr if which == 0 else Sc)).tocsr()
+                B.sort_indices()
+                A = csr_to_sorted(n, asm.indptr, asm.indices, vals)
+                if B.nnz == 0 or abs(B).max() == 0.0:
+                    assert np.abs(vals).max() == 0.0
+                    continue
+                err, missing = compare_matrix(A, B)
+                assert missing == 0 and err <= TOL, (rn, m, err, missing)
+        # Hessian-vector products of the contributions: derivative with respect to the base state, contracted with a mode vector
+        Y = rng.standard_normal(n)
+        for which, rn in enumerate(names[1:], start=1):
+            HJ, HM = asm.assemble_hessian(Y[None, :], flag=2, residual=rn)
+            Jr, Mr = op.assemble_hessian((Sc @ Y)[None, :], flag=2, which=which)
+            for vals, ref in ((HJ[0], Jr[0]), (HM[0], Mr[0])):
+                B = (Sr.T @ ref @ Sr).tocsr()
+                A = csr_to_sorted(n, asm.indptr, asm.indices, vals)
+                if abs(B).max() == 0.0:
+                    assert np.abs(vals).max() <= 1e-300
+                    continue
+                D = abs(A - B)
+                assert D.max() <= 1e-11 * abs(B).max(), (rn, m, D.max(), abs(B).max())
+    op.close()
+    asm.close()
