@@ -163,6 +163,60 @@ void oracle_dshape_local_tri(int order, const double *s, double *psi, double *dp
   }
 }
 
+/* ------------------------------------------------------------------ tetrahedra: TElement<3,3> / TElement<3,2> and TGauss<3,3>
+ * (oomph-lib Telements.h:1978-2012, :2133-2197; integral.cc:752-776), literal tables and the same operation order */
+static const double TGauss33_knot[11][3] = {{0.25, 0.25, 0.25},
+                                            {0.785714285714286, 0.071428571428571, 0.071428571428571},
+                                            {0.071428571428571, 0.071428571428571, 0.071428571428571},
+                                            {0.071428571428571, 0.785714285714286, 0.071428571428571},
+                                            {0.071428571428571, 0.071428571428571, 0.785714285714286},
+                                            {0.399403576166799, 0.399403576166799, 0.100596423833201},
+                                            {0.399403576166799, 0.100596423833201, 0.399403576166799},
+                                            {0.100596423833201, 0.399403576166799, 0.399403576166799},
+                                            {0.399403576166799, 0.100596423833201, 0.100596423833201},
+                                            {0.100596423833201, 0.399403576166799, 0.100596423833201},
+                                            {0.100596423833201, 0.100596423833201, 0.399403576166799}};
+static const double TGauss33_weight[11] = {-0.01315555555556, 0.00762222222222, 0.00762222222222, 0.00762222222222, 0.00762222222222, 0.02488888888889,
+                                           0.02488888888889,  0.02488888888889, 0.02488888888889, 0.02488888888889, 0.02488888888889};
+void oracle_gauss_tet(int ipt, double *knot, double *weight)
+{
+  for (int d = 0; d < 3; d++) knot[d] = TGauss33_knot[ipt][d];
+  *weight = TGauss33_weight[ipt];
+}
+void oracle_dshape_local_tet(int order, const double *s, double *psi, double *dpsi)
+{
+  const double s3 = 1.0 - s[0] - s[1] - s[2];
+  if (order == 3)
+  {
+    psi[0] = (2.0 * s[0] - 1.0) * s[0];
+    psi[1] = (2.0 * s[1] - 1.0) * s[1];
+    psi[2] = (2.0 * s[2] - 1.0) * s[2];
+    psi[3] = (2.0 * s3 - 1.0) * s3;
+    psi[4] = 4.0 * s[0] * s[1];
+    psi[5] = 4.0 * s[0] * s[2];
+    psi[6] = 4.0 * s[0] * s3;
+    psi[7] = 4.0 * s[1] * s[2];
+    psi[8] = 4.0 * s[2] * s3;
+    psi[9] = 4.0 * s[1] * s3;
+    const double d[10][3] = {{4.0 * s[0] - 1.0, 0.0, 0.0}, {0.0, 4.0 * s[1] - 1.0, 0.0}, {0.0, 0.0, 4.0 * s[2] - 1.0},
+                             {-4.0 * s3 + 1.0, -4.0 * s3 + 1.0, -4.0 * s3 + 1.0}, {4.0 * s[1], 4.0 * s[0], 0.0}, {4.0 * s[2], 0.0, 4.0 * s[0]},
+                             {4.0 * (s3 - s[0]), -4.0 * s[0], -4.0 * s[0]}, {0.0, 4.0 * s[2], 4.0 * s[1]}, {-4.0 * s[2], -4.0 * s[2], 4.0 * (s3 - s[2])},
+                             {-4.0 * s[1], 4.0 * (s3 - s[1]), -4.0 * s[1]}};
+    for (int l = 0; l < 10; l++)
+      for (int b = 0; b < 3; b++) dpsi[l * 3 + b] = d[l][b];
+  }
+  else
+  {
+    psi[0] = s[0];
+    psi[1] = s[1];
+    psi[2] = s[2];
+    psi[3] = 1.0 - s[0] - s[1] - s[2];
+    const double d[4][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}, {-1.0, -1.0, -1.0}};
+    for (int l = 0; l < 4; l++)
+      for (int b = 0; b < 3; b++) dpsi[l * 3 + b] = d[l][b];
+  }
+}
+
 /* ------------------------------------------------------------------ problem data */
 #define MAXN 27
 #define MAXD 3
@@ -262,7 +316,8 @@ static void check_size(unsigned long long a, unsigned long long b, char *what)
  * element in 2D (get_normal_at_s, :1730-1752) and its coordinate derivatives (get_dnormal_dcoords_at_s, :1461-1490) */
 static void element_dshape_local(const Oracle *o, int order, const double *s, double *psi, double *dpsi)
 {
-  if (o->et.tri) oracle_dshape_local_tri(order, s, psi, dpsi);
+  if (o->et.tri && o->et.dim == 3) oracle_dshape_local_tet(order, s, psi, dpsi);
+  else if (o->et.tri) oracle_dshape_local_tri(order, s, psi, dpsi);
   else if (o->et.edim == 1)
   {
     if (order == 3) { lag3(s[0], psi); dlag3(s[0], dpsi); }
@@ -456,7 +511,8 @@ static void cb_fill_shape_buffer_for_point(unsigned ipt, JITFuncSpec_RequiredSha
 {
   ThreadState *ts = TS;
   double s[MAXD], w;
-  if (ts->o->et.tri) oracle_gauss_tri((int)ipt, s, &w);
+  if (ts->o->et.tri && ts->o->et.dim == 3) oracle_gauss_tet((int)ipt, s, &w);
+  else if (ts->o->et.tri) oracle_gauss_tri((int)ipt, s, &w);
   else if (ts->o->et.edim == 1) oracle_gauss_1d((int)ipt, s, &w);
   else oracle_gauss(ts->o->et.dim, (int)ipt, s, &w);
   fill_shape_info_at_s(ts, s, w, (unsigned)flag, req);
@@ -742,7 +798,7 @@ void *oracle_create_typed(int dim, int nnode, int n_elem, const int *elem_nodes,
   static const int c1l[2] = {0, 2};
   o->et.dim = dim;
   o->et.edim = dim;
-  o->et.tri = (dim == 2 && nnode == 6);
+  o->et.tri = (dim == 2 && nnode == 6) || (dim == 3 && nnode == 10); /* simplex elements: TElement<2,3>, TElement<3,3> */
   if (dim == 2 && nnode == 3)
   {
     /* InterfaceElementLine1dC2: QElement<1,3> in a 2D space, C1 on the end nodes, Gauss<1,3> */
@@ -751,6 +807,15 @@ void *oracle_create_typed(int dim, int nnode, int n_elem, const int *elem_nodes,
     o->et.nnode_C1 = 2;
     o->et.n_int = 3;
     memcpy(o->et.c1_nodes, c1l, sizeof(c1l));
+  }
+  else if (o->et.tri && dim == 3)
+  {
+    /* BulkElementTetra3dC2 (src/elements.cpp:11397-11409): 10 nodes, C1 on the vertices, TGauss<3,3> */
+    static const int c1tet[4] = {0, 1, 2, 3};
+    o->et.nnode = 10;
+    o->et.nnode_C1 = 4;
+    o->et.n_int = 11;
+    memcpy(o->et.c1_nodes, c1tet, sizeof(c1tet));
   }
   else if (o->et.tri)
   {

@@ -149,6 +149,44 @@ extern "C"
   }
 
   // default integration scheme of TElement<2,3> (TGauss<2,3>, integral.cc:355-369); returns the number of points
+  // TElement<3,3> / TElement<3,2>: shape functions, local derivatives and local node coordinates of the compiled oomph-lib
+  int ref_tshape3(int nnode_1d, const double *s, double *psi, double *dpsi, double *node_s)
+  {
+    Vector<double> sv(3);
+    for (int d = 0; d < 3; d++) sv[d] = s[d];
+    FiniteElement *el = nnode_1d == 3 ? (FiniteElement *)new TElement<3, 3> : (FiniteElement *)new TElement<3, 2>;
+    const unsigned n = el->nnode();
+    Shape p(n);
+    DShape dp(n, 3);
+    el->dshape_local(sv, p, dp);
+    for (unsigned l = 0; l < n; l++)
+    {
+      psi[l] = p[l];
+      for (int d = 0; d < 3; d++) dpsi[l * 3 + d] = dp(l, d);
+      if (node_s)
+      {
+        Vector<double> ns;
+        el->local_coordinate_of_node(l, ns);
+        for (int d = 0; d < 3; d++) node_s[l * 3 + d] = ns[d];
+      }
+    }
+    delete el;
+    return (int)n;
+  }
+
+  // default integration scheme of TElement<3,3> (TGauss<3,3>)
+  int ref_tgauss3(int ipt, double *knot, double *w)
+  {
+    TElement<3, 3> el;
+    const int n = (int)el.integral_pt()->nweight();
+    if (ipt >= 0 && ipt < n)
+    {
+      for (int d = 0; d < 3; d++) knot[d] = el.integral_pt()->knot(ipt, d);
+      *w = el.integral_pt()->weight(ipt);
+    }
+    return n;
+  }
+
   int ref_tgauss(int ipt, double *knot, double *w)
   {
     TElement<2, 3> el;

@@ -57,6 +57,9 @@ ELEMENT_TYPES: Dict[str, ElementType] = {
     # InterfaceElementLine1dC2 (src/elements.hpp:1435-2298): the three nodes of a Q9 / T6 edge in a 2D space; QElement<1,3> shapes,
     # C1 on the end nodes, Gauss<1,3>
     "Line1dC2": ElementType("Line1dC2", 2, 1, 3, 3, (0, 2), 3),
+    # BulkElementTetra3dC2 = TElement<3,3>: ten-node tetrahedra (vertices 0-3, then the mid-edge nodes in oomph order, Telements.h:2051),
+    # C1 on the four vertices, TGauss<3,3> (11 points)
+    "Tetra3dC2": ElementType("Tetra3dC2", 3, 3, 10, 3, (0, 1, 2, 3), 11),
 }
 
 SPACE_ORDER = ("C2TB", "C2", "C1TB", "C1")  # nodal_data index order (src/codegen.cpp:2367-2380)

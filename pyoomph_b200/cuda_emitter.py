@@ -80,6 +80,38 @@ def triangle_shape_tables(order: int, knots):
 TRIANGLE_NODE_COORDS = [(1.0, 0.0), (0.0, 1.0), (0.0, 0.0), (0.5, 0.5), (0.0, 0.5), (0.5, 0.0)]    # Telements.h:575-621
 
 
+def tgauss3_rule():
+    """Literal oomph table TGauss<3,3> (integral.cc:752-776): 11 points (one weight negative), degree 4 (Keast)."""
+    a, b, c, d = 0.785714285714286, 0.071428571428571, 0.399403576166799, 0.100596423833201
+    kn = [(0.25, 0.25, 0.25), (a, b, b), (b, b, b), (b, a, b), (b, b, a), (c, c, d), (c, d, c), (d, c, c), (c, d, d), (d, c, d), (d, d, c)]
+    w = [-0.01315555555556] + [0.00762222222222] * 4 + [0.02488888888889] * 6
+    return kn, w
+
+
+def tetra_shape_tables(order: int, knots):
+    """psi[ipt][l], dpsi[ipt][l][b] of TElementShape<3,3> (Telements.h:2133-2197) / TElementShape<3,2> (:1978-2012), same operation order"""
+    psi, dpsi = [], []
+    for (s0, s1, s2) in knots:
+        s3 = 1.0 - s0 - s1 - s2
+        if order == 3:
+            ps = [(2.0 * s0 - 1.0) * s0, (2.0 * s1 - 1.0) * s1, (2.0 * s2 - 1.0) * s2, (2.0 * s3 - 1.0) * s3,
+                  4.0 * s0 * s1, 4.0 * s0 * s2, 4.0 * s0 * s3, 4.0 * s1 * s2, 4.0 * s2 * s3, 4.0 * s1 * s3]
+            q = -4.0 * s3 + 1.0
+            ds = [(4.0 * s0 - 1.0, 0.0, 0.0), (0.0, 4.0 * s1 - 1.0, 0.0), (0.0, 0.0, 4.0 * s2 - 1.0), (q, q, q),
+                  (4.0 * s1, 4.0 * s0, 0.0), (4.0 * s2, 0.0, 4.0 * s0), (4.0 * (s3 - s0), -4.0 * s0, -4.0 * s0),
+                  (0.0, 4.0 * s2, 4.0 * s1), (-4.0 * s2, -4.0 * s2, 4.0 * (s3 - s2)), (-4.0 * s1, 4.0 * (s3 - s1), -4.0 * s1)]
+        else:
+            ps = [s0, s1, s2, 1.0 - s0 - s1 - s2]
+            ds = [(1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0), (-1.0, -1.0, -1.0)]
+        psi.append(ps)
+        dpsi.append(ds)
+    return psi, dpsi
+
+
+TETRA_NODE_COORDS = [(1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0), (0.0, 0.0, 0.0), (0.5, 0.5, 0.0), (0.5, 0.0, 0.5), (0.5, 0.0, 0.0),
+                     (0.0, 0.5, 0.5), (0.0, 0.0, 0.5), (0.0, 0.5, 0.0)]                       # Telements.h:2051-2127
+
+
 def gauss_rule_1d():
     """Literal oomph table Gauss<1,3> (integral.cc:50-53; these knots are the correct ones)."""
     return [(-0.774596669241483,), (0.0,), (0.774596669241483,)], [5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0]
@@ -99,6 +131,8 @@ def element_rule(et):
     """(knots, weights) of the element type's default integration scheme"""
     if et.name.startswith("Tri"):
         return tgauss_rule()
+    if et.name.startswith("Tetra"):
+        return tgauss3_rule()
     if et.elem_dim == 1:
         return gauss_rule_1d()
     return gauss_rule(et.nodal_dim)
@@ -107,6 +141,8 @@ def element_rule(et):
 def element_shape_tables(et, order: int, knots):
     if et.name.startswith("Tri"):
         return triangle_shape_tables(order, knots)
+    if et.name.startswith("Tetra"):
+        return tetra_shape_tables(order, knots)
     if et.elem_dim == 1:
         return line_shape_tables(order, knots)
     return shape_tables(et.nodal_dim, order, knots)
@@ -116,6 +152,8 @@ def element_node_coords(et):
     """local coordinates of the element's nodes (local_coordinate_of_node)"""
     if et.name.startswith("Tri"):
         return list(TRIANGLE_NODE_COORDS)
+    if et.name.startswith("Tetra"):
+        return list(TETRA_NODE_COORDS)
     grid = (-1.0, 0.0, 1.0)
     return [tuple(grid[(l // 3 ** d) % 3] for d in range(et.elem_dim)) for l in range(et.nnode)]
 
@@ -251,10 +289,11 @@ class CudaEmitter:
         self.pipe_scatter_threads = int(os.environ.get("PB2_PIPE_NS", "128"))
         # 3D: the shape side of the contraction from the 1D factors of the tensor-product basis (18 uniform constants per Gauss point
         # instead of 108 shared-memory table loads for the 27 columns of a Q27 field)
-        self.tensor_columns = self.dim == 3 and os.environ.get("PB2_TP3D", "1") != "0"
+        self.brick = self.dim == 3 and self.NN == 27            # tensor-product 3D elements: the 1D-factor forms below; tetrahedra use the tables
+        self.tensor_columns = self.brick and os.environ.get("PB2_TP3D", "1") != "0"
         # ... and phase 1 (geometry + interpolation of the Q27 / position fields) in ONE node loop with psi_l, dpsi_l built from the same
         # 1D factors: 18 table loads per point instead of one per node, table and quantity
-        self.tensor_points = self.dim == 3 and os.environ.get("PB2_TP3D_POINTS", "1") != "0"
+        self.tensor_points = self.brick and os.environ.get("PB2_TP3D_POINTS", "1") != "0"
         # round-2 experiment (off: compiled and algebra-checked on the CPU only, not yet run on a GPU): sum factorisation of the column
         # side over the Gauss points, DESIGN.md section 9 item 4
         self.sum_factorise = self.tensor_columns and os.environ.get("PB2_SUMFAC", "1") != "0"
@@ -386,7 +425,7 @@ class CudaEmitter:
         def arr(vals):
             return ", ".join(repr(float(v)) for v in vals)
         t1 = []
-        if self.dim == 3:
+        if self.brick:
             # 1D factors per Gauss point: [ipt][dir][L_0..L_2, L'_0..L'_2] at the knot of that direction (psi_c = L_i(s0) L_j(s1) L_k(s2),
             # c = i + 3j + 9k, Qelements.cc:621-660)
             for sk in kn:
@@ -410,7 +449,7 @@ class CudaEmitter:
         o.append("__constant__ double c_dpsi1[%d] = {%s};" % (self.NIPT * self.NN1 * self.edim, arr(v for p in dpsi1 for l in p for v in l)))
         o.append("__device__ const double g_tables[%d] = {%s};" % (self._tables_smem_size(), arr(
             [v for p in psi2 for v in p] + [v for p in dpsi2 for l in p for v in l] + [v for p in psi1 for v in p] + [v for p in dpsi1 for l in p for v in l] + t1_smem)))
-        if self.dim == 3:
+        if self.brick:
             o.append("__constant__ double c_t1d[%d] = {%s};" % (len(t1), arr(t1)))
         if self.code.point_expression_names():
             # the same tables at the element's NODES (local coordinates -1, 0, 1 per direction, oomph node order): point expressions are
@@ -419,7 +458,7 @@ class CudaEmitter:
             npsi2, ndpsi2 = element_shape_tables(self.et, 3, nk)
             npsi1, ndpsi1 = element_shape_tables(self.et, 2, nk)
             nt1 = []
-            if self.dim == 3:
+            if self.brick:
                 for sk in nk:
                     for d in range(3):
                         P, D = _lag(3, sk[d])
@@ -437,7 +476,7 @@ class CudaEmitter:
         """doubles of shape tables staged in shared memory (needed by phase 1 always, phase 2 in smem mode) for npt points
         (default: the integration points)"""
         npt = self.NIPT if npt is None else npt
-        return npt * (self.NN * (1 + self.edim) + self.NN1 * (1 + self.edim)) + (npt * 18 if self.dim == 3 else 0)
+        return npt * (self.NN * (1 + self.edim) + self.NN1 * (1 + self.edim)) + (npt * 18 if self.brick else 0)
 
     def _emit_kernel(self, o: List[str], rp: RoutinePlan, what: int):
         code, dim, NN, NN1, NIPT = self.code, self.dim, self.NN, self.NN1, self.NIPT

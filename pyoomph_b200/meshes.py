@@ -61,6 +61,8 @@ class StructuredMesh:
             pid = pid * npd[d] + grids[d].ravel()
         if self.element_type == "Tri2dC2":
             pid = np.repeat(pid, 2)          # two triangles per lattice cell, stored one after the other
+        if self.element_type == "Tetra3dC2":
+            pid = np.repeat(pid, 6)          # six tetrahedra per lattice cell
         return pid.astype(np.int32)
 
 
@@ -164,6 +166,34 @@ def RectangularTriangleMesh(N=10, size=1.0, lower_left=(0.0, 0.0)) -> Structured
     tri[0::2], tri[1::2] = a, b
     m = StructuredMesh(2, q.N, np.ascontiguousarray(tri), q.node_pos, q.node_lattice, q.boundaries, "Tri2dC2")
     return m
+
+
+def CuboidTetraMesh(N=4, size=1.0, lower_left=(0.0, 0.0, 0.0)) -> StructuredMesh:
+    """Ten-node tetrahedra (BulkElementTetra3dC2 = oomph TElement<3,3>, src/elements.cpp:11397) on the node set of the Q27 mesh: every
+    cell is cut into the six Kuhn tetrahedra around its main diagonal (one per order in which the three axes are walked from the
+    lower corner to the upper one); the edge, face-diagonal and body-diagonal midpoints are exactly the cell's remaining lattice nodes.
+    Local node order of TElementShape<3,3> (Telements.h:2051-2127): vertices 0-3 = (1,0,0), (0,1,0), (0,0,1), (0,0,0) in local
+    coordinates, mid-edge nodes 4: 0-1, 5: 0-2, 6: 0-3, 7: 1-2, 8: 2-3, 9: 1-3.  All tetrahedra positively oriented."""
+    import itertools
+    b = CuboidBrickMesh(N, size, lower_left)
+    loc = lambda o: o[0] + 3 * o[1] + 9 * o[2]
+    tets = []
+    for perm in itertools.permutations(range(3)):
+        v = [np.zeros(3, dtype=int)]
+        for ax in perm:
+            nxt = v[-1].copy()
+            nxt[ax] += 2
+            v.append(nxt)
+        # oomph local vertices 0, 1, 2 span the tetrahedron from vertex 3: take v[3] (the upper corner) as local 3
+        quad = [v[0], v[1], v[2], v[3]]
+        e1, e2, e3 = quad[0] - quad[3], quad[1] - quad[3], quad[2] - quad[3]
+        if np.linalg.det(np.array([e1, e2, e3], dtype=float)) < 0:
+            quad[0], quad[1] = quad[1], quad[0]
+        mids = [(0, 1), (0, 2), (0, 3), (1, 2), (2, 3), (1, 3)]
+        tets.append([loc(q) for q in quad] + [loc((quad[i] + quad[j]) // 2) for i, j in mids])
+    tets = np.array(tets, dtype=np.int64)                       # [6, 10] local brick-node indices
+    en = b.elem_nodes[:, tets].reshape(-1, 10)
+    return StructuredMesh(3, b.N, np.ascontiguousarray(en, dtype=np.int32), b.node_pos, b.node_lattice, b.boundaries, "Tetra3dC2")
 
 
 @dataclasses.dataclass

@@ -123,6 +123,35 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             pos_hist = np.stack([bulk.node_pos + 1e-3 * (1 + 0.3 * t) * np.stack(
                 [smooth_field(bulk.node_pos, 10 + d + 2 * t, seed) for d in range(bulk.dim)], axis=1) for t in range(T)])
         return dict(kind=kind, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=pos_hist, unsteady=unsteady, params={}, bulk_mesh=bulk, bulk_code=bulk_code)
+    if kind in ("poisson_tet", "heat3d_tet", "ns_tet"):
+        # ten-node tetrahedra (BulkElementTetra3dC2 = TElement<3,3>, TGauss<3,3>): Poisson, transient heat, 3D Taylor-Hood P2/P1 NS
+        import pyoomph_b200.meshes as _mm
+        mesh = _mm.CuboidTetraMesh(N)
+        if unstructured:
+            raise NotImplementedError
+        if distortion:
+            mesh = distort(mesh, distortion, seed)
+        params = {}
+        if kind == "poisson_tet":
+            code = FiniteElementCode("Tetra3dC2", PoissonEquation(source=poisson_source), name="poissontet")
+            pinned = {"u": np.concatenate([mesh.boundaries["left"], mesh.boundaries["right"]])}
+            unsteady = False
+        elif kind == "heat3d_tet":
+            code = FiniteElementCode("Tetra3dC2", TransientHeatEquation(), name="heat3dtet")
+            pinned = {"u": mesh.boundaries["left"]}
+            unsteady = True
+        else:
+            code = FiniteElementCode("Tetra3dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0), name="nstet")
+            wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom", "back")]))
+            pinned = {"velocity_x": wall, "velocity_y": wall, "velocity_z": wall}
+            unsteady = True
+        dofmap = assign_equation_numbers(mesh, code, pinned, None)
+        T, nval = code.history_levels(), code.n_nodal_values
+        vals = np.zeros((T, mesh.n_node, nval))
+        for t in range(T):
+            for f in range(nval):
+                vals[t, :, f] = smooth_field(mesh.node_pos, f + 3 * t, seed) * (1.0 - 0.05 * t)
+        return dict(kind=kind, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=None, unsteady=unsteady, params=params)
     if kind in ("poisson_tri", "ns_tri", "ale_tri"):
         # six-node triangles (the element class of the reference's gmsh droplet meshes): Poisson, Taylor-Hood P2/P1 Navier-Stokes,
         # and NS on a pseudo-elastic moving mesh

@@ -32,12 +32,15 @@ CASES = [("poisson", 64), ("poisson", 5), ("ns", 12), ("ns_unsteady", 9), ("heat
 # six-node triangles (BulkElementTri2dC2 = TElement<2,3>, TGauss<2,3>): Poisson, Taylor-Hood P2/P1 NS, NS on a pseudo-elastic moving mesh
 TRIANGLES = [("poisson_tri", 9, 0.0, False), ("poisson_tri", 8, 0.12, False), ("ns_tri", 7, 0.1, False), ("ale_tri", 5, 0.08, False)]
 
+# ten-node tetrahedra (BulkElementTetra3dC2 = TElement<3,3>, TGauss<3,3> with its negative weight): Poisson, transient heat, 3D P2/P1 NS
+TETRAHEDRA = [("poisson_tet", 3, 0.0, False), ("poisson_tet", 3, 0.1, False), ("heat3d_tet", 3, 0.1, False), ("ns_tet", 2, 0.1, False)]
+
 VARIANTS = [("ns", 11, 0.12, False), ("ns_unsteady", 10, 0.1, True), ("heat3d", 3, 0.1, True), ("ale", 6, 0.08, True), ("poisson", 33, 0.15, True),
             ("ns_axi_swirl", 6, 0.1, True), ("ale_axi", 6, 0.08, True)]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,N,distortion,unstructured", [(k, n, 0.0, False) for k, n in CASES] + VARIANTS + TRIANGLES)
+@pytest.mark.parametrize("kind,N,distortion,unstructured", [(k, n, 0.0, False) for k, n in CASES] + VARIANTS + TRIANGLES + TETRAHEDRA)
 def test_residual_jacobian_mass_parity(kind, N, distortion, unstructured):
     pb = make_problem(kind, N, distortion=distortion, unstructured=unstructured)
     op = make_oracle(pb)
@@ -63,7 +66,7 @@ def test_residual_jacobian_mass_parity(kind, N, distortion, unstructured):
                                # distorted meshes: no symmetric cancellations (measured <= 0.2 % on quads / bricks, 1.2 % on the
                                # P2/P1 triangles); uniform meshes: analytic zeros of the reference element come out as noise on both
                                # sides (6-15 % on squares, 45 % of the P2 stiffness entries on right triangles)
-                               max_cancel_fraction=(0.02 if distortion > 0.0 else (0.60 if kind.endswith("_tri") else 0.30)))
+                               max_cancel_fraction=(0.02 if distortion > 0.0 else (0.60 if kind.endswith(("_tri", "_tet")) else 0.30)))
         _record(kind, N, distortion, unstructured, st)
     # flag 0 and flag 1 launches give the same numbers as the flag 2 launch (separate kernels)
     asm.assemble(flag=0)

@@ -337,3 +337,35 @@ def test_triangle_shape_functions_and_tgauss_bit_exact(oomph):
             assert np.abs(po - psi).max() <= 4e-16 and np.abs(do - dpsi).max() <= 1e-15
             if order == 3:
                 assert np.array_equal(ns, np.array(TRIANGLE_NODE_COORDS))
+
+
+def test_tetrahedron_shape_functions_and_tgauss_bit_exact(oomph):
+    """TElement<3,3> / TElement<3,2>::dshape_local, local_coordinate_of_node and TGauss<3,3> (11 points, one negative weight) of the
+    compiled oomph-lib against the emitter's tetrahedron tables (bit-exact) and the oracle's restatement."""
+    from oracle import build_plugin
+    from pyoomph_b200.cuda_emitter import TETRA_NODE_COORDS, tetra_shape_tables, tgauss3_rule
+    pb = make_problem("poisson", 2)
+    drv = ctypes.CDLL(build_plugin(pb["code"], pb["code"].name))
+    kn, w = tgauss3_rule()
+    k_ref, w_ref = (ctypes.c_double * 3)(), ctypes.c_double()
+    assert oomph.ref_tgauss3(0, k_ref, ctypes.byref(w_ref)) == 11 == len(kn)
+    for ipt in range(11):
+        oomph.ref_tgauss3(ipt, k_ref, ctypes.byref(w_ref))
+        assert list(k_ref) == list(kn[ipt]) and w_ref.value == w[ipt]
+        ko, wo = (ctypes.c_double * 3)(), ctypes.c_double()
+        drv.oracle_gauss_tet(ipt, ko, ctypes.byref(wo))
+        assert list(ko) == list(kn[ipt]) and wo.value == w[ipt]
+    rng = np.random.default_rng(9)
+    pts = [np.array(k) for k in kn] + [np.array(c) for c in TETRA_NODE_COORDS] + [rng.dirichlet((1, 1, 1, 1))[:3] for _ in range(10)]
+    for order, n in ((3, 10), (2, 4)):
+        for s in pts:
+            s = np.ascontiguousarray(s, dtype=np.float64)
+            psi, dpsi, ns = np.zeros(n), np.zeros((n, 3)), np.zeros((n, 3))
+            assert oomph.ref_tshape3(order, _dp(s), _dp(psi), _dp(dpsi), _dp(ns)) == n
+            pt, dt = tetra_shape_tables(order, [tuple(s)])
+            assert np.array_equal(psi, np.array(pt[0])) and np.array_equal(dpsi, np.array(dt[0]))
+            po, do = np.zeros(n), np.zeros((n, 3))
+            drv.oracle_dshape_local_tet(order, _dp(s), _dp(po), _dp(do))
+            assert np.array_equal(po, psi) and np.array_equal(do, dpsi)
+            if order == 3:
+                assert np.array_equal(ns, np.array(TETRA_NODE_COORDS))
