@@ -452,6 +452,33 @@ class B200Assembly(CustomAssemblyBase):
         n = self.n_dof
         return csr_matrix((mass, self.indices, self.indptr), shape=(n, n)), csr_matrix((jac, self.indices, self.indptr), shape=(n, n))
 
+    def assemble_azimuthal_eigenproblem_matrices(self, m: float, sigma_r: float = 0.0, residual: str = ""):
+        """Complex (M, J - sigma_r M) of the azimuthal mode m about the current axisymmetric base state: two flag-2 launches (real and
+        imaginary contribution, pyoomph/generic/problem.py:4543-4558 and the normal-mode eigensolve of problem.py) combined as
+        J = J_re + i J_im, M = M_re + i M_im on the fixed pattern.  The element class must have been generated with an
+        ``AxisymmetryBreakingCoordinateSystem`` whose mode is the global parameter ``azimuthal_m``."""
+        from scipy.sparse import csr_matrix
+        cs = self.code.coordinate_system
+        if not getattr(cs, "has_normal_mode_expansion", False):
+            raise RuntimeError("the element class has no azimuthal mode expansion")
+        if "azimuthal_m" in self.param_names:
+            self.set_parameters(azimuthal_m=float(m))
+        parts = []
+        for prefix in (cs.real_contribution_name, cs.imag_contribution_name):
+            name = prefix + residual
+            if name in self.residual_names:
+                self.assemble(flag=2, residual=name)
+                _, jac, mass = self.fetch(True, True)
+            else:                       # a purely real operator has no imaginary contribution
+                jac, mass = np.zeros(self.nnz), np.zeros(self.nnz)
+            parts.append((jac, mass))
+        jac = parts[0][0] + 1j * parts[1][0]
+        mass = parts[0][1] + 1j * parts[1][1]
+        if sigma_r != 0.0:
+            jac = jac - sigma_r * mass
+        n = self.n_dof
+        return csr_matrix((mass, self.indices, self.indptr), shape=(n, n)), csr_matrix((jac, self.indices, self.indptr), shape=(n, n))
+
     # ---- integral expressions (Mesh.evaluate_observable -> BulkElementBase::eval_integral_expression, src/mesh.cpp:545) ---------
     def evaluate_integral_expressions(self) -> Dict[str, float]:
         """all integral expressions of the element class over all elements: one launch for the per-element values and one

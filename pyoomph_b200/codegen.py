@@ -651,6 +651,10 @@ class FiniteElementCode:
         key = resname + ("|hessianT" if transposed else "|hessian")
         if key in self._forms:
             return self._forms[key]
+        if self.coordinates_as_dofs and not transposed:
+            hf = self._hessian_form_moving_mesh(resname, key)
+            self._forms[key] = hf
+            return hf
         if transposed:
             slots_t, DJ, DM = self.derive_hessian_transposed(resname)
             form = ResidualForm(key, slots_t, [sp.Integer(0)] * len(slots_t), {}, {}, [])
@@ -678,6 +682,41 @@ class FiniteElementCode:
                           uses_dx=ex.DX_EUL in allsyms, uses_dX=ex.DX_LAG in allsyms)
         self._forms[key] = hf
         return hf
+
+    def _hessian_form_moving_mesh(self, resname: str, key: str) -> ResidualForm:
+        """d((J.Y))/dU and d((M.Y))/dU when the nodal positions are unknowns (the reference's second-order tensors d2_dx2_shape_dcoord,
+        int_pt_weights_d2_coords, src/elements.cpp:3163-3217, src/codegen.cpp:1500-1881).  (A.Y)_i = sum_s T_s[l_i] sum_(G,a) C_{s,(G,a)} Yhat_{G,a}
+        is itself a weak form that is linear in the test functions, with Y interpolated like the unknowns (values, gradients, and the
+        POSITION columns of A contracted with the position part of Y).  Its derivative with respect to every unknown -- fields and
+        positions, through the measure, the Eulerian gradients of fields, of Y and of the test functions, and the radius of an
+        axisymmetric system -- is what `_coefficient_form` computes for any such form: the first-order identities applied once more."""
+        form = self.derive(resname)
+
+        def contracted(coefs) -> sp.Expr:
+            E = sp.Integer(0)
+            for (si, G, a), c in coefs.items():
+                yf = "Y__" + G
+                if yf not in self.fields:
+                    self.fields[yf] = Field(yf, self.fields[G].space, -1, aux_of=G)
+                E = E + self._test_atom(form.slots[si]) * c * self._atom(AtomInfo(yf, 0, "", a, 0))
+            return E
+        fJ = self._coefficient_form(contracted(form.J), key + "|J")
+        slots = list(fJ.slots)
+        J = dict(fJ.J)
+        M: Dict[Tuple[int, str, str], sp.Expr] = {}
+        if form.M:
+            fM = self._coefficient_form(contracted(form.M), key + "|M")
+            for (si, H, c), v in fM.J.items():
+                sl = fM.slots[si]
+                if sl not in slots:
+                    slots.append(sl)
+                M[(slots.index(sl), H, c)] = v
+        used = set()
+        for e in list(J.values()) + list(M.values()):
+            used |= {s_ for s_ in e.free_symbols if s_ in self._atom_syms}
+        atoms = sorted((self._atom_syms[s_] for s_ in used), key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
+        allsyms = set().union(*[e.free_symbols for e in list(J.values()) + list(M.values())]) if (J or M) else set()
+        return ResidualForm(key, slots, [sp.Integer(0)] * len(slots), J, M, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=ex.DX_LAG in allsyms)
 
     def atom_symbol(self, info: AtomInfo) -> sp.Symbol:
         return self._atom(info)

@@ -267,13 +267,14 @@ class CudaEmitter:
             self.routines.append(RoutinePlan("r%d" % i, code.derive(rn), i, -1))
             for k, p in enumerate(code.global_params):
                 self.routines.append(RoutinePlan("r%d_dp%d" % (i, k), code.derive(rn, p), i, k))
-        self.hessian = (not code.coordinates_as_dofs) and os.environ.get("PB2_NO_HESSIAN", "0") != "1"
+        self.hessian = os.environ.get("PB2_NO_HESSIAN", "0") != "1" and (not code.coordinates_as_dofs or code.etype.elem_dim == code.nodal_dim)
         self.hroutines: List[RoutinePlan] = []
         if self.hessian:
             for i, rn in enumerate(code.residual_names()):
                 self.hroutines.append(RoutinePlan("h%d" % i, code.hessian_form(rn), i, -1))
-                # transposed contraction (flags 4 / 5 of HessianVectorProduct, src/jitbridge.h:637-691): plugin query kind 3
-                self.hroutines.append(RoutinePlan("ht%d" % i, code.hessian_form(rn, transposed=True), i, -1))
+                if not code.coordinates_as_dofs:
+                    # transposed contraction (flags 4 / 5 of HessianVectorProduct, src/jitbridge.h:637-691): plugin query kind 3
+                    self.hroutines.append(RoutinePlan("ht%d" % i, code.hessian_form(rn, transposed=True), i, -1))
         self.T_val = code.history_levels()
         self.T_pos = self.T_val if code.coordinates_as_dofs else 1
         self._plan_groups()

@@ -750,5 +750,72 @@ def test_azimuthal_mode_contributions_parity(N, distortion):
                     continue
                 D = abs(A - B)
                 assert D.max() <= 1e-11 * abs(B).max(), (rn, m, D.max(), abs(B).max())
+    # the complex eigenproblem pair of mode m = 2 from the two contributions
+    Mc, Jc = asm.assemble_azimuthal_eigenproblem_matrices(2.0)
+    asm.assemble(flag=2, residual=names[1])
+    _, jr, mr = asm.fetch(True, True)
+    asm.assemble(flag=2, residual=names[2])
+    _, ji, mi = asm.fetch(True, True)
+    assert np.array_equal(Jc.data, jr + 1j * ji) and np.array_equal(Mc.data, mr + 1j * mi) and np.abs(ji).max() > 0
+    op.close()
+    asm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N,distortion", [("ale", 3, 0.08), ("ale_axi", 3, 0.08), ("ale_tri", 2, 0.08)])
+def test_moving_mesh_hessian_vector_products(kind, N, distortion):
+    """d(J.Y)/dU and d(M.Y)/dU with POSITION dofs among the unknowns (the reference's second-order moving-mesh tensors,
+    src/elements.cpp:3163-3217): every column -- nodal values and nodal positions -- against central differences of the ORACLE's Jacobian
+    and mass matrix (the reference checks its analytic derivatives the same way, src/elements.cpp:5880).  Tolerance 2e-6 of the largest
+    entry: finite-difference accuracy, not round-off."""
+    from scipy.sparse import csr_matrix
+    pb = make_problem(kind, N, distortion=distortion)
+    assert pb["code"].coordinates_as_dofs
+    n = pb["dofmap"].n_dof
+    asm = make_gpu(pb)
+    op = make_oracle(pb)
+    rng = np.random.default_rng(11)
+    Y = rng.standard_normal(n)
+    HJ, HM = asm.assemble_hessian(Y[None, :], flag=2)
+    A = csr_matrix((HJ[0], asm.indices, asm.indptr), shape=(n, n)).toarray()
+    AM = csr_matrix((HM[0], asm.indices, asm.indptr), shape=(n, n)).toarray()
+
+    def JY_MY():
+        _, mats = op.assemble(flag=2)
+        return csr_to_sorted(n, *mats[0]) @ Y, csr_to_sorted(n, *mats[1]) @ Y
+    eps = 1e-6
+    ref, refM = np.zeros((n, n)), np.zeros((n, n))
+    vals0, pos0 = pb["vals"][0], pb["pos_hist"][0]
+    for node in range(pb["mesh"].n_node):
+        for f in range(vals0.shape[1]):
+            g = pb["dofmap"].node_eqn[node, f]
+            if g < 0:
+                continue
+            v = vals0.copy()
+            v[node, f] += eps
+            op.update_values(0, v)
+            jp, mp = JY_MY()
+            v[node, f] -= 2 * eps
+            op.update_values(0, v)
+            jm, mm = JY_MY()
+            ref[:, g], refM[:, g] = (jp - jm) / (2 * eps), (mp - mm) / (2 * eps)
+        op.update_values(0, vals0)
+        for d in range(pos0.shape[1]):
+            g = pb["dofmap"].pos_eqn[node, d]
+            if g < 0:
+                continue
+            x = pos0.copy()
+            x[node, d] += eps
+            op.update_values(0, None, x)
+            jp, mp = JY_MY()
+            x[node, d] -= 2 * eps
+            op.update_values(0, None, x)
+            jm, mm = JY_MY()
+            ref[:, g], refM[:, g] = (jp - jm) / (2 * eps), (mp - mm) / (2 * eps)
+        op.update_values(0, None, pos0)
+    pos_cols = pb["dofmap"].pos_eqn[pb["dofmap"].pos_eqn >= 0]
+    assert np.abs(ref[:, pos_cols]).max() > 1e-3 * np.abs(ref).max()          # the position columns are not a side show
+    assert np.abs(A - ref).max() <= 2e-6 * np.abs(ref).max(), (np.abs(A - ref).max(), np.abs(ref).max())
+    assert np.abs(AM - refM).max() <= 2e-6 * max(np.abs(refM).max(), 1e-300), (np.abs(AM - refM).max(), np.abs(refM).max())
     op.close()
     asm.close()
