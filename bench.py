@@ -145,15 +145,52 @@ def build_workload(workload, n, seed=0):
         pinned = {"u": np.concatenate([mesh.boundaries["left"], mesh.boundaries["right"]])}
         unsteady = False
         label = "2D Poisson QUAD2 %dx%d" % (n, n)
+    elif workload == "ale_freesurface":
+        # BASELINE config 4's element classes: NS Taylor-Hood on a pseudo-elastic moving mesh (40 dofs per element) + the free-surface
+        # interface class on the top boundary, assembled into the same matrix (child problem)
+        from pyoomph_b200.equations import DeclareFields, NavierStokesFreeSurface, PseudoElasticMesh
+        from pyoomph_b200.meshes import boundary_line_mesh
+        mesh = RectangularQuadMesh(n)
+        code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + PseudoElasticMesh() + DeclareFields(_kin_bc="C2"), name="aleif")
+        imesh = boundary_line_mesh(mesh, ["top"])
+        icode = FiniteElementCode("Line1dC2", NavierStokesFreeSurface(surface_tension=0.7, static_interface=False), name="freesurfmov")
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("bottom", "left", "right")]))
+        pinned = {"velocity_x": wall, "velocity_y": wall, "_kin_bc": np.setdiff1d(np.arange(mesh.n_node), np.unique(imesh.elem_nodes))}
+        pinned_pos = {"coordinate_x": np.unique(np.concatenate([mesh.boundaries["left"], mesh.boundaries["right"]])), "coordinate_y": mesh.boundaries["bottom"]}
+        unsteady = True
+        label = "2D NS Taylor-Hood on a pseudo-elastic moving mesh %dx%d + free-surface interface class (%d line elements) in one matrix, BDF2" % (n, n, imesh.n_elem)
+        extra = dict(interface_mesh=imesh, interface_code=icode)
+    elif workload in ("ns_swirl_hvp", "ns_azimuthal"):
+        # BASELINE config 5's element class: axisymmetric NS Taylor-Hood with swirl (31 dofs per element); timed: one Hessian-vector
+        # product d(J.Y)/dU, resp. the real contribution of the azimuthal m = 1 eigenproblem (Jacobian + mass matrix)
+        from pyoomph_b200.expressions import AxisymmetryBreakingCoordinateSystem
+        mesh = RectangularQuadMesh(n)
+        eqs = NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0, with_azimuthal_velocity=True)
+        if workload == "ns_swirl_hvp":
+            code = FiniteElementCode("Quad2dC2", eqs, name="nsswirl", coordinate_system="axisymmetric")
+            label = "axisymmetric NS Taylor-Hood with swirl %dx%d: one Hessian-vector product d(J.Y)/dU, BDF2" % (n, n)
+        else:
+            code = FiniteElementCode("Quad2dC2", eqs, name="nsazi", coordinate_system=AxisymmetryBreakingCoordinateSystem("azimuthal_m"))
+            label = "axisymmetric NS Taylor-Hood with swirl %dx%d: real contribution of the azimuthal m=1 eigenproblem (J and M), BDF2" % (n, n)
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("right", "bottom", "top")]))
+        pinned = {"velocity_x": np.unique(np.concatenate([wall, mesh.boundaries["left"]])), "velocity_y": wall,
+                  "velocity_phi": np.unique(np.concatenate([mesh.boundaries["right"], mesh.boundaries["left"]]))}
+        unsteady = True
     else:
         raise SystemExit("unknown workload " + workload)
-    dofmap = assign_equation_numbers(mesh, code, pinned)
+    dofmap = assign_equation_numbers(mesh, code, pinned, locals().get("pinned_pos"))
     T, nval = code.history_levels(), code.n_nodal_values
     vals = np.zeros((T, mesh.n_node, nval))
     for t in range(T):
         for f in range(nval):
             vals[t, :, f] = smooth_field(mesh.node_pos, f + 3 * t, seed) * (1.0 - 0.05 * t)
-    return dict(kind=workload, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=None, unsteady=unsteady, params={}, label=label)
+    pos_hist = None
+    if code.coordinates_as_dofs:
+        pos_hist = np.stack([mesh.node_pos + 1e-3 / n * (1 + 0.3 * t) * np.stack(
+            [smooth_field(mesh.node_pos, 10 + d + 2 * t, seed) for d in range(mesh.dim)], axis=1) for t in range(T)])
+    out = dict(kind=workload, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=pos_hist, unsteady=unsteady, params={}, label=label)
+    out.update(locals().get("extra") or {})
+    return out
 
 
 def cpu_run(workload, n_sample, steps, warmup, threads):
@@ -436,7 +473,7 @@ def main():
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peaks()
-    b_el = float(info.alg_bytes_per_elem[1])
+    b_el = float(info.alg_bytes_per_elem[2 if workload == "ns_azimuthal" else 1])
     if not pb["unsteady"]:
         b_el -= float(info.alg_bytes_per_hist_level) * (info.n_hist_val - 1)   # steady: history levels are not read
     # dominant (only) kernel: the generated ResidualAndJacobian routine, one launch per colour
@@ -477,10 +514,10 @@ def main():
         # most any CPU run of this port could reach on this box
         line["cpu_baseline"]["value_1core_times_cores"] = ne1 / sec1 * cores
     if world == 1 and not args.no_extra and args.workload == "ns_cavity" and not args.n:
-        # BASELINE configs 1 and 3 on the same GPU, so that the driver's record carries them too (config 2 above is the headline)
+        # BASELINE configs 1, 3 and the element classes of 4 and 5 on the same GPU, so that the driver's record carries them too (config 2 above is the headline)
         asm.close()
         line["extra_workloads"] = [run_extra_workload(lib, device, wl_, n_, max(3, min(args.steps, 10)), peak, fp64_peak.value)
-                                   for (wl_, n_) in (("heat3d", 126), ("poisson", 2048))]
+                                   for (wl_, n_) in (("heat3d", 126), ("poisson", 2048), ("ale_freesurface", 512), ("ns_swirl_hvp", 512), ("ns_azimuthal", 512))]
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -507,20 +544,43 @@ def run_extra_workload(lib, device, workload, n, steps, peak_hbm, peak_fp64):
     asm = B200Assembly(pb["code"], pb["mesh"], pb["dofmap"], name=pb["code"].name, device=device)
     for t in range(pb["vals"].shape[0]):
         asm.set_nodal_values(t, pb["vals"][t])
+    if pb["pos_hist"] is not None:
+        for t in range(pb["pos_hist"].shape[0]):
+            asm.set_nodal_positions(t, pb["pos_hist"][t])
+    child = None
+    if "interface_code" in pb:
+        child = B200Assembly(pb["interface_code"], pb["interface_mesh"], pb["dofmap"], name=pb["interface_code"].name, parent=asm)
     if pb["unsteady"]:
         from problems import TIME
         asm.set_unsteady(TIME["t"], TIME["dt"], TIME["dtprev"], TIME["unsteady_steps_done"])
+    if workload == "ns_azimuthal":
+        asm.set_parameters(azimuthal_m=1.0)
     t_setup = time.time() - t0
+    if workload == "ns_swirl_hvp":
+        Y = np.random.default_rng(3).standard_normal(asm.n_dof)[None, :]
+        Yp = Y.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+        def step():          # the vector is copied to the device inside the call (asm.n_dof doubles): part of what a tracker pays per product
+            if lib.pb2_problem_assemble_hessian(asm.prob, 0, 1, 1, Yp, None) != 0:
+                raise RuntimeError(lib.pb2_last_error().decode())
+    elif workload == "ns_azimuthal":
+        rn = pb["code"].coordinate_system.real_contribution_name
+
+        def step():
+            asm.assemble(flag=2, residual=rn)
+    else:
+        def step():
+            asm.assemble(flag=1)     # a parent assembles its child element classes behind its own launch
     t_w, n_w = time.time(), 0
     while n_w < 3 or (time.time() - t_w < 0.4 and n_w < 2000):
-        asm.assemble(flag=1)
+        step()
         n_w += 1
         if n_w % 4 == 0:
             lib.pb2_device_synchronize()
     lib.pb2_device_synchronize()
     lib.pb2_event_record(2, None)
     for _ in range(steps):
-        asm.assemble(flag=1)
+        step()
     lib.pb2_event_record(3, None)
     ms = ctypes.c_float()
     lib.pb2_event_elapsed_ms(2, 3, ctypes.byref(ms))
@@ -535,7 +595,10 @@ def run_extra_workload(lib, device, workload, n, steps, peak_hbm, peak_fp64):
     out = {"workload": pb["label"], "elements": int(ne), "ndof_el": int(info.ndof_el), "nnz": int(asm.nnz), "steps": steps, "ms_per_step": ms_step,
            "value": ne / (ms_step * 1e-3), "unit": UNIT, "setup_s": round(t_setup, 1), "pattern_setup_s": round(asm.setup_seconds, 2),
            "roofline": {"bound": "hbm", "achieved": hbm, "peak": peak_hbm, "unit": "GB/s", "frac": hbm / peak_hbm, "alg_bytes_per_element": b_el,
-                        "traffic": traffic, "kernel": "pb2_%s_r0_f1" % pb["code"].name}}
+                        "traffic": traffic, "kernel": {"ns_swirl_hvp": "pb2_%s_h0_f1", "ns_azimuthal": "pb2_%s_r1_f2"}.get(workload, "pb2_%s_r0_f1") % pb["code"].name}}
+    if child is not None:
+        out["launches_per_step"] = 2
+        out["interface_elements"] = int(pb["interface_mesh"].n_elem)
     if flops is not None and peak_fp64:
         tf = flops / (ms_step * 1e-3) / 1e12
         out["roofline"].update({"fp64_tflops": tf, "fp64_peak_tflops": peak_fp64, "frac_fp64": tf / peak_fp64, "fp64_flops_per_element": flops / ne})

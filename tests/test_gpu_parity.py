@@ -819,3 +819,71 @@ def test_moving_mesh_hessian_vector_products(kind, N, distortion):
     assert np.abs(AM - refM).max() <= 2e-6 * max(np.abs(refM).max(), 1e-300), (np.abs(AM - refM).max(), np.abs(refM).max())
     op.close()
     asm.close()
+
+
+@pytest.mark.gpu
+def test_newton_iterations_of_the_coupled_free_surface_problem():
+    """BASELINE config 4 as a user runs it, in small: NS Taylor-Hood on a pseudo-elastic moving mesh (bulk class) + the free-surface class
+    on two boundaries (kinematic condition with the mesh velocity, multiplier on the position equations), one BDF2 step solved by Newton's
+    method.  GPU: parent + child problem assemble ONE matrix on the device per iteration; oracle: both classes assembled and summed.  Same
+    SuperLU on both sides: same iterates (positions, velocities, pressure, multipliers), same residual history."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.linalg import splu
+    from pyoomph_b200.assembly import B200Assembly
+    pb = make_problem("freesurf_mov_if", 6, distortion=0.05)
+    bulk_pb = dict(pb, code=pb["bulk_code"], mesh=pb["bulk_mesh"])
+    n = pb["dofmap"].n_dof
+    eq, peq = pb["dofmap"].node_eqn, pb["dofmap"].pos_eqn
+    m, mp = eq >= 0, peq >= 0
+    U0 = np.zeros(n)
+    U0[eq[m]] = 0.05 * pb["vals"][0][m]                      # a gentle start: small velocities, slightly displaced mesh
+    U0[peq[mp]] = pb["pos_hist"][0][mp]
+    for p_ in (pb, bulk_pb):
+        p_["vals"] = 0.05 * pb["vals"]
+
+    def newton(assemble, set_dofs):
+        U, hist = U0.copy(), []
+        for it in range(8):
+            set_dofs(U)
+            r, J = assemble()
+            hist.append(float(np.abs(r).max()))
+            if hist[-1] < 1e-11:
+                break
+            U = U - splu(J.tocsc()).solve(r)
+        return U, hist
+
+    ob, oi = make_oracle(bulk_pb), make_oracle(pb)
+
+    def set_cpu(U):
+        v, x = bulk_pb["vals"][0].copy(), pb["pos_hist"][0].copy()
+        v[m] = U[eq[m]]
+        x[mp] = U[peq[mp]]
+        for o in (ob, oi):
+            o.update_values(0, v, x)
+
+    def assemble_cpu():
+        rb, mb = ob.assemble(flag=1)
+        ri, mi = oi.assemble(flag=1)
+        return rb + ri, (csr_to_sorted(n, *mb[0]) + csr_to_sorted(n, *mi[0])).tocsr()
+    U_ref, hist_ref = newton(assemble_cpu, set_cpu)
+
+    bulk = make_gpu(bulk_pb)
+    child = B200Assembly(pb["code"], pb["mesh"], pb["dofmap"], name=pb["code"].name, parent=bulk)
+
+    def assemble_gpu():
+        bulk.assemble(flag=1)
+        r, jac, _ = bulk.fetch(True, False)
+        return r, csr_matrix((jac, bulk.indices, bulk.indptr), shape=(n, n))
+    U, hist = newton(assemble_gpu, bulk.set_dofs)
+    assert hist_ref[-1] < 1e-11 and len(hist_ref) <= 7, hist_ref          # quadratic convergence of the coupled problem
+    assert len(hist) == len(hist_ref)
+    for a, b in zip(hist[:-1], hist_ref[:-1]):
+        assert abs(a - b) <= 1e-6 * max(b, 1e-12) + 1e-12, (hist, hist_ref)
+    assert np.abs(U - U_ref).max() <= 1e-9 * np.abs(U_ref).max()
+    # the free surface moved and carries a multiplier: the interface class was part of the solve
+    lam = pb["code"].fields["_kin_bc"].index
+    assert np.abs(U[eq[:, lam][eq[:, lam] >= 0]]).max() > 1e-6 and np.abs(U[peq[mp]] - U0[peq[mp]]).max() > 1e-6
+    assert child in bulk.children
+    for o in (ob, oi):
+        o.close()
+    bulk.close()
