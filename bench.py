@@ -473,7 +473,7 @@ def main():
             dist.destroy_process_group()
         return
     peak, peak_src = measured_peaks()
-    b_el = float(info.alg_bytes_per_elem[2 if workload == "ns_azimuthal" else 1])
+    b_el = float(info.alg_bytes_per_elem[1])
     if not pb["unsteady"]:
         b_el -= float(info.alg_bytes_per_hist_level) * (info.n_hist_val - 1)   # steady: history levels are not read
     # dominant (only) kernel: the generated ResidualAndJacobian routine, one launch per colour
@@ -586,7 +586,7 @@ def run_extra_workload(lib, device, workload, n, steps, peak_hbm, peak_fp64):
     lib.pb2_event_elapsed_ms(2, 3, ctypes.byref(ms))
     ms_step = ms.value / steps
     info = asm.info
-    b_el = float(info.alg_bytes_per_elem[1])
+    b_el = float(info.alg_bytes_per_elem[2 if workload == "ns_azimuthal" else 1])
     if not pb["unsteady"]:
         b_el -= float(info.alg_bytes_per_hist_level) * (info.n_hist_val - 1)
     ne = pb["mesh"].n_elem
