@@ -702,9 +702,9 @@ static int create_impl(pb2_class *cls, int device, const pb2_mesh_desc *m, pb2_p
   RawVec<uint8_t> off8;
   RawVec<uint16_t> off16;
   if (p->map_bits == 8)
-    off8.assign((size_t)ne * nd * nd, (uint8_t)0xFF);
+    off8.assign((size_t)ne * nd * nd + 16, (uint8_t)0xFF);   // + slack: the kernels prefetch the 4-byte words that COVER a batch's slice
   else
-    off16.assign((size_t)ne * nd * nd, (uint16_t)0xFFFF);
+    off16.assign((size_t)ne * nd * nd + 8, (uint16_t)0xFFFF);
   const unsigned FIRST = p->map_bits == 8 ? 0x80u : 0x8000u;
   std::vector<std::vector<int>> t_untouched(omp_get_max_threads()), t_untouched_rows(omp_get_max_threads());
   const int *const col_base = parent ? parent->col_index.data() : p->col_index.data();

@@ -794,7 +794,7 @@ class CudaEmitter:
         off_pts = (off_in + 2 * EPB * IN_S + 1) // 2 * 2   # 16-byte aligned
         off_out = off_pts + n_pts_slots * EPB * PT_S
         off_maps = off_out + 2 * EPB * OUT_S          # doubles; ints/bytes follow
-        map_slot_bytes = 2 * EPB * ND * 4 + ((EPB * ND2 * 2 if what >= 1 else 0) + 15) // 16 * 16
+        map_slot_bytes = 2 * EPB * ND * 4 + ((EPB * ND2 * 2 if what >= 1 else 0) + 15) // 16 * 16 + 16   # + the leading bytes of an unaligned map slice
         smem_bytes = off_maps * 8 + 2 * map_slot_bytes + 2 * EPB * NN * 4
         self._kernel_smem[kname] = smem_bytes
         self._kernel_cfg[kname] = (EPB, NT, smem_bytes)
@@ -886,12 +886,18 @@ class CudaEmitter:
             w(indent + "  for (int i = st; i < pnel * %d; i += %d) { pb2_cp_async4(prs + i, a.elem_rowstart + (long long)pe0 * %d + i); pb2_cp_async4(pres + i, a.elem_res + (long long)pe0 * %d + i); }" % (ND, NS, ND, ND))
             if what >= 1:
                 w(indent + "  const int mbytes = pnel * %d * (a.map_bits >> 3);" % ND2)
-                w(indent + "  const unsigned char* __restrict__ gmap = (const unsigned char*)a.elem_off + (long long)pe0 * %d * (a.map_bits >> 3);" % ND2)
                 w(indent + "  unsigned char* const pmap = (unsigned char*)(pres + %d);" % (EPB * ND))
                 if ND2 % 4 == 0:
+                    w(indent + "  const unsigned char* __restrict__ gmap = (const unsigned char*)a.elem_off + (long long)pe0 * %d * (a.map_bits >> 3);" % ND2)
                     w(indent + "  for (int i = st; i < (mbytes >> 2); i += %d) pb2_cp_async4(pmap + 4 * i, gmap + 4 * i);" % NS)
                 else:
-                    w(indent + "  for (int i = st; i < mbytes; i += %d) pmap[i] = __ldg(gmap + i);" % NS)
+                    # ndof^2 odd (9, 27, 31, 49 dofs): the batch's bytes start at any alignment.  Copy the 4-byte words that cover them
+                    # asynchronously (the consumer skips the leading `shift` bytes); byte loads through registers would put a global
+                    # round trip per batch on the scatter warps' critical path (measured: 14 % of all samples of the Q27 kernel).
+                    w(indent + "  const long long goff = (long long)pe0 * %d * (a.map_bits >> 3);" % ND2)
+                    w(indent + "  const int shift = (int)(goff & 3);")
+                    w(indent + "  const unsigned char* __restrict__ gal = (const unsigned char*)a.elem_off + (goff - shift);")
+                    w(indent + "  for (int i = st; i < ((shift + mbytes + 3) >> 2); i += %d) pb2_cp_async4(pmap + 4 * i, gal + 4 * i);" % NS)
             w(indent + "  asm volatile(\"cp.async.commit_group;\" ::: \"memory\");")
             w(indent + "}")
         w("    // position maps travel one batch ahead of the scatter (cp.async into the other MAPS slot)")
@@ -902,7 +908,11 @@ class CudaEmitter:
         w("      const int meta = a.batch_meta[batch], nel = meta & 63, tile = meta >> 7;")
         w("      const unsigned long long bmask = a.batch_bar[batch];")
         w("      unsigned char* const mbase = maps0 + (it & 1) * %d;" % map_slot_bytes)
-        w("      int* const s_rowstart = (int*)mbase; int* const s_resmap = s_rowstart + %d; unsigned char* const s_map = (unsigned char*)(s_resmap + %d);" % (EPB * ND, EPB * ND))
+        w("      int* const s_rowstart = (int*)mbase; int* const s_resmap = s_rowstart + %d;" % (EPB * ND))
+        if ND2 % 4 == 0:
+            w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d);" % (EPB * ND))
+        else:
+            w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d) + (int)(((long long)a.batch_elem[batch] * %d * (a.map_bits >> 3)) & 3);" % (EPB * ND, ND2))
         w("      (void)s_map;")
         if self.timing: w("      long long ts0 = clock64();")
         w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")
