@@ -878,6 +878,8 @@ class CudaEmitter:
         w("    int it = 0, item = 0, gated_tile = 0, prev_tile = -1, pending = 0;")
         w("    unsigned char* const maps0 = (unsigned char*)(smem + %d);" % off_maps)
         # prefetch helper (lambda-like macro through a local struct is overkill: emit the loop twice)
+        map_async = os.environ.get("PB2_MAP_ASYNC", "1") != "0"     # A/B switch: byte loads through registers for odd ndof^2 (the round-1 form)
+
         def emit_prefetch(indent, batch_expr, slot_expr):
             w(indent + "{")
             w(indent + "  const int pe0 = a.batch_elem[%s], pnel = a.batch_meta[%s] & 63;" % (batch_expr, batch_expr))
@@ -887,17 +889,21 @@ class CudaEmitter:
             if what >= 1:
                 w(indent + "  const int mbytes = pnel * %d * (a.map_bits >> 3);" % ND2)
                 w(indent + "  unsigned char* const pmap = (unsigned char*)(pres + %d);" % (EPB * ND))
-                if ND2 % 4 == 0:
+                if not map_async:
                     w(indent + "  const unsigned char* __restrict__ gmap = (const unsigned char*)a.elem_off + (long long)pe0 * %d * (a.map_bits >> 3);" % ND2)
-                    w(indent + "  for (int i = st; i < (mbytes >> 2); i += %d) pb2_cp_async4(pmap + 4 * i, gmap + 4 * i);" % NS)
+                    if ND2 % 4 == 0:
+                        w(indent + "  for (int i = st; i < (mbytes >> 2); i += %d) pb2_cp_async4(pmap + 4 * i, gmap + 4 * i);" % NS)
+                    else:
+                        w(indent + "  for (int i = st; i < mbytes; i += %d) pmap[i] = __ldg(gmap + i);" % NS)
                 else:
-                    # ndof^2 odd (9, 27, 31, 49 dofs): the batch's bytes start at any alignment.  Copy the 4-byte words that cover them
-                    # asynchronously (the consumer skips the leading `shift` bytes); byte loads through registers would put a global
-                    # round trip per batch on the scatter warps' critical path (measured: 14 % of all samples of the Q27 kernel).
+                    # The batch's bytes start at any alignment when ndof^2 is odd (9, 27, 31, 49 dofs).  Copy the 8-byte words that cover
+                    # them asynchronously (the consumer skips the leading `shift` bytes); byte loads through registers put a global
+                    # round trip per batch on the scatter warps' critical path (14 % of all samples of the Q27 kernel, 22 % of the
+                    # Poisson kernel's time).
                     w(indent + "  const long long goff = (long long)pe0 * %d * (a.map_bits >> 3);" % ND2)
-                    w(indent + "  const int shift = (int)(goff & 3);")
+                    w(indent + "  const int shift = (int)(goff & 7);")
                     w(indent + "  const unsigned char* __restrict__ gal = (const unsigned char*)a.elem_off + (goff - shift);")
-                    w(indent + "  for (int i = st; i < ((shift + mbytes + 3) >> 2); i += %d) pb2_cp_async4(pmap + 4 * i, gal + 4 * i);" % NS)
+                    w(indent + "  for (int i = st; i < ((shift + mbytes + 7) >> 3); i += %d) pb2_cp_async8(pmap + 8 * i, gal + 8 * i);" % NS)
             w(indent + "  asm volatile(\"cp.async.commit_group;\" ::: \"memory\");")
             w(indent + "}")
         w("    // position maps travel one batch ahead of the scatter (cp.async into the other MAPS slot)")
@@ -909,10 +915,10 @@ class CudaEmitter:
         w("      const unsigned long long bmask = a.batch_bar[batch];")
         w("      unsigned char* const mbase = maps0 + (it & 1) * %d;" % map_slot_bytes)
         w("      int* const s_rowstart = (int*)mbase; int* const s_resmap = s_rowstart + %d;" % (EPB * ND))
-        if ND2 % 4 == 0:
+        if not map_async:
             w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d);" % (EPB * ND))
         else:
-            w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d) + (int)(((long long)a.batch_elem[batch] * %d * (a.map_bits >> 3)) & 3);" % (EPB * ND, ND2))
+            w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d) + (int)(((long long)a.batch_elem[batch] * %d * (a.map_bits >> 3)) & 7);" % (EPB * ND, ND2))
         w("      (void)s_map;")
         if self.timing: w("      long long ts0 = clock64();")
         w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")
