@@ -899,11 +899,18 @@ class CudaEmitter:
                     # The batch's bytes start at any alignment when ndof^2 is odd (9, 27, 31, 49 dofs).  Copy the 8-byte words that cover
                     # them asynchronously (the consumer skips the leading `shift` bytes); byte loads through registers put a global
                     # round trip per batch on the scatter warps' critical path (14 % of all samples of the Q27 kernel, 22 % of the
-                    # Poisson kernel's time).
-                    w(indent + "  const long long goff = (long long)pe0 * %d * (a.map_bits >> 3);" % ND2)
-                    w(indent + "  const int shift = (int)(goff & 7);")
-                    w(indent + "  const unsigned char* __restrict__ gal = (const unsigned char*)a.elem_off + (goff - shift);")
-                    w(indent + "  for (int i = st; i < ((shift + mbytes + 7) >> 3); i += %d) pb2_cp_async8(pmap + 8 * i, gal + 8 * i);" % NS)
+                    # Poisson kernel's time).  16-bit maps (rows of 127 entries and more: the 49-dof moving-mesh class) keep the
+                    # register path: measured 4 % faster there.
+                    w(indent + "  const unsigned char* __restrict__ gmap = (const unsigned char*)a.elem_off + (long long)pe0 * %d * (a.map_bits >> 3);" % ND2)
+                    w(indent + "  if (a.map_bits == 8)")
+                    w(indent + "  {")
+                    w(indent + "    const int shift = (int)((unsigned long long)gmap & 7);")
+                    w(indent + "    for (int i = st; i < ((shift + mbytes + 7) >> 3); i += %d) pb2_cp_async8(pmap + 8 * i, gmap - shift + 8 * i);" % NS)
+                    w(indent + "  }")
+                    if ND2 % 2 == 0:
+                        w(indent + "  else for (int i = st; i < (mbytes >> 2); i += %d) pb2_cp_async4(pmap + 4 * i, gmap + 4 * i);" % NS)
+                    else:
+                        w(indent + "  else for (int i = st; i < (mbytes >> 1); i += %d) ((unsigned short*)pmap)[i] = __ldg((const unsigned short*)gmap + i);" % NS)
             w(indent + "  asm volatile(\"cp.async.commit_group;\" ::: \"memory\");")
             w(indent + "}")
         w("    // position maps travel one batch ahead of the scatter (cp.async into the other MAPS slot)")
@@ -918,7 +925,7 @@ class CudaEmitter:
         if not map_async:
             w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d);" % (EPB * ND))
         else:
-            w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d) + (int)(((long long)a.batch_elem[batch] * %d * (a.map_bits >> 3)) & 7);" % (EPB * ND, ND2))
+            w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d) + (a.map_bits == 8 ? (int)(((long long)a.batch_elem[batch] * %d) & 7) : 0);" % (EPB * ND, ND2))
         w("      (void)s_map;")
         if self.timing: w("      long long ts0 = clock64();")
         w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")

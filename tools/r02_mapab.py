@@ -5,7 +5,7 @@ import bench
 from pyoomph_b200.assembly import load_library
 lib = load_library()
 lib.pb2_set_device(0) if hasattr(lib, "pb2_set_device") else None
-for wl, n in (("ale_freesurface", 512), ("heat3d", 126), ("ns_swirl_hvp", 512), ("poisson", 2048), ("ns_cavity", 1024)):
+for wl, n in (("ale_freesurface", 512),):
     for v in ("0", "1", "0", "1"):
         os.environ["PB2_MAP_ASYNC"] = v
         out = bench.run_extra_workload(lib, 0, wl, n, 10, 6556.2, 36.9)
