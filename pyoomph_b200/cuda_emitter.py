@@ -878,7 +878,11 @@ class CudaEmitter:
         w("    int it = 0, item = 0, gated_tile = 0, prev_tile = -1, pending = 0;")
         w("    unsigned char* const maps0 = (unsigned char*)(smem + %d);" % off_maps)
         # prefetch helper (lambda-like macro through a local struct is overkill: emit the loop twice)
-        map_async = os.environ.get("PB2_MAP_ASYNC", "1") != "0"     # A/B switch: byte loads through registers for odd ndof^2 (the round-1 form)
+        # position maps into shared memory: 8-byte asynchronous copies over the words that cover a batch's slice.  A/B switch
+        # PB2_MAP_ASYNC=0: the round-1 form (cp.async of 4 bytes when ndof^2 is a multiple of 4, else byte loads through registers).
+        # Classes with large maps (ndof^2 > 1024 bytes per element: the 49-dof moving-mesh class) keep the round-1 form: measured
+        # 4 % faster there, while Poisson gains 23 %, the Q27 and Taylor-Hood classes 1-5 % (profiles/r02_notes.md).
+        map_async = os.environ.get("PB2_MAP_ASYNC", "1") != "0" and ND2 <= 1024
 
         def emit_prefetch(indent, batch_expr, slot_expr):
             w(indent + "{")
@@ -899,18 +903,11 @@ class CudaEmitter:
                     # The batch's bytes start at any alignment when ndof^2 is odd (9, 27, 31, 49 dofs).  Copy the 8-byte words that cover
                     # them asynchronously (the consumer skips the leading `shift` bytes); byte loads through registers put a global
                     # round trip per batch on the scatter warps' critical path (14 % of all samples of the Q27 kernel, 22 % of the
-                    # Poisson kernel's time).  16-bit maps (rows of 127 entries and more: the 49-dof moving-mesh class) keep the
-                    # register path: measured 4 % faster there.
-                    w(indent + "  const unsigned char* __restrict__ gmap = (const unsigned char*)a.elem_off + (long long)pe0 * %d * (a.map_bits >> 3);" % ND2)
-                    w(indent + "  if (a.map_bits == 8)")
-                    w(indent + "  {")
-                    w(indent + "    const int shift = (int)((unsigned long long)gmap & 7);")
-                    w(indent + "    for (int i = st; i < ((shift + mbytes + 7) >> 3); i += %d) pb2_cp_async8(pmap + 8 * i, gmap - shift + 8 * i);" % NS)
-                    w(indent + "  }")
-                    if ND2 % 2 == 0:
-                        w(indent + "  else for (int i = st; i < (mbytes >> 2); i += %d) pb2_cp_async4(pmap + 4 * i, gmap + 4 * i);" % NS)
-                    else:
-                        w(indent + "  else for (int i = st; i < (mbytes >> 1); i += %d) ((unsigned short*)pmap)[i] = __ldg((const unsigned short*)gmap + i);" % NS)
+                    # Poisson kernel's time).
+                    w(indent + "  const long long goff = (long long)pe0 * %d * (a.map_bits >> 3);" % ND2)
+                    w(indent + "  const int shift = (int)(goff & 7);")
+                    w(indent + "  const unsigned char* __restrict__ gal = (const unsigned char*)a.elem_off + (goff - shift);")
+                    w(indent + "  for (int i = st; i < ((shift + mbytes + 7) >> 3); i += %d) pb2_cp_async8(pmap + 8 * i, gal + 8 * i);" % NS)
             w(indent + "  asm volatile(\"cp.async.commit_group;\" ::: \"memory\");")
             w(indent + "}")
         w("    // position maps travel one batch ahead of the scatter (cp.async into the other MAPS slot)")
@@ -925,7 +922,7 @@ class CudaEmitter:
         if not map_async:
             w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d);" % (EPB * ND))
         else:
-            w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d) + (a.map_bits == 8 ? (int)(((long long)a.batch_elem[batch] * %d) & 7) : 0);" % (EPB * ND, ND2))
+            w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d) + (int)(((long long)a.batch_elem[batch] * %d * (a.map_bits >> 3)) & 7);" % (EPB * ND, ND2))
         w("      (void)s_map;")
         if self.timing: w("      long long ts0 = clock64();")
         w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")
