@@ -832,12 +832,16 @@ class CudaEmitter:
         w("    int it = 0; long long dbg0 = 0, dbg1 = 0; (void)dbg0; (void)dbg1;")
         w("    int* const s_idx0 = (int*)((unsigned char*)(smem + %d) + %d);" % (off_maps, 2 * map_slot_bytes))
         w("    // element -> node indices travel one batch ahead (cp.async), so the nodal data of a batch needs one memory round trip")
-        w("    if (ib0 < ib1) { const int pe0 = a.batch_elem[ib0], pn = (a.batch_meta[ib0] & 63) * %d; for (int i = gt; i < pn; i += %d) pb2_cp_async4(s_idx0 + i, a.elem_nodes + (long long)pe0 * %d + i); }" % (NN, NG, NN))
+        w("    int gt_m0 = 0, gt_m1 = 0, gt_m2 = 0, gt_e0 = 0, gt_e1 = 0, gt_e2 = 0;     // batch table two batches ahead in registers")
+        w("    if (ib0 < ib1) { gt_m0 = __ldg(a.batch_meta + ib0); gt_e0 = __ldg(a.batch_elem + ib0); }")
+        w("    if (ib0 + 1 < ib1) { gt_m1 = __ldg(a.batch_meta + ib0 + 1); gt_e1 = __ldg(a.batch_elem + ib0 + 1); }")
+        w("    if (ib0 < ib1) { const int pe0 = gt_e0, pn = (gt_m0 & 63) * %d; for (int i = gt; i < pn; i += %d) pb2_cp_async4(s_idx0 + i, a.elem_nodes + (long long)pe0 * %d + i); }" % (NN, NG, NN))
         w("    asm volatile(\"cp.async.commit_group;\" ::: \"memory\");")
         w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
         w("      const int slot = it & 1;")
-        w("      const int nel = a.batch_meta[batch] & 63, e0 = a.batch_elem[batch]; (void)e0;")
+        w("      const int nel = gt_m0 & 63, e0 = gt_e0; (void)e0;")
+        w("      if (batch + 2 < ib1) { gt_m2 = __ldg(a.batch_meta + batch + 2); gt_e2 = __ldg(a.batch_elem + batch + 2); }")
         w("      const int* const s_idx = s_idx0 + slot * %d;" % (EPB * NN))
         w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")
         w("      pb2_bar_sync(13, %d);                        // indices of this batch visible to all gather warps" % NG)
@@ -861,12 +865,13 @@ class CudaEmitter:
             self._emit_gather_node(o, plan, c1=True, use_async=True)
             w("      }")
         w("      asm volatile(\"cp.async.commit_group;\" ::: \"memory\");")
-        w("      if (batch + 1 < ib1) { const int pe0 = a.batch_elem[batch + 1], pn = (a.batch_meta[batch + 1] & 63) * %d; int* const nx = s_idx0 + (slot ^ 1) * %d; for (int i = gt; i < pn; i += %d) pb2_cp_async4(nx + i, a.elem_nodes + (long long)pe0 * %d + i); }" % (NN, EPB * NN, NG, NN))
+        w("      if (batch + 1 < ib1) { const int pe0 = gt_e1, pn = (gt_m1 & 63) * %d; int* const nx = s_idx0 + (slot ^ 1) * %d; for (int i = gt; i < pn; i += %d) pb2_cp_async4(nx + i, a.elem_nodes + (long long)pe0 * %d + i); }" % (NN, EPB * NN, NG, NN))
         w("      asm volatile(\"cp.async.commit_group;\" ::: \"memory\");")
         w("      asm volatile(\"cp.async.wait_group 1;\" ::: \"memory\");   // nodal data of this batch has landed; next indices may be in flight")
         w("      __threadfence_block();")
         if self.timing: w("      dbg1 += clock64() - tg1;")
         w("      pb2_bar_arrive(%d + slot, %d);            // IN[slot] full" % (1, (NH or NC) + NG))
+        w("      gt_m0 = gt_m1; gt_e0 = gt_e1; gt_m1 = gt_m2; gt_e1 = gt_e2;")
         w("    }")
         if self.timing: w("    if (gt == 0 && a.debug) { atomicAdd(a.debug + 0, (unsigned long long)dbg0); atomicAdd(a.debug + 1, (unsigned long long)dbg1); atomicAdd(a.debug + 2, (unsigned long long)it); }")
         w("  }")
@@ -884,9 +889,9 @@ class CudaEmitter:
         # 4 % faster there, while Poisson gains 23 %, the Q27 and Taylor-Hood classes 1-5 % (profiles/r02_notes.md).
         map_async = os.environ.get("PB2_MAP_ASYNC", "1") != "0" and ND2 <= 1024
 
-        def emit_prefetch(indent, batch_expr, slot_expr):
+        def emit_prefetch(indent, pe0_expr, meta_expr, slot_expr):
             w(indent + "{")
-            w(indent + "  const int pe0 = a.batch_elem[%s], pnel = a.batch_meta[%s] & 63;" % (batch_expr, batch_expr))
+            w(indent + "  const int pe0 = %s, pnel = (%s) & 63;" % (pe0_expr, meta_expr))
             w(indent + "  unsigned char* const pm = maps0 + (%s) * %d;" % (slot_expr, map_slot_bytes))
             w(indent + "  int* const prs = (int*)pm; int* const pres = prs + %d;" % (EPB * ND))
             w(indent + "  for (int i = st; i < pnel * %d; i += %d) { pb2_cp_async4(prs + i, a.elem_rowstart + (long long)pe0 * %d + i); pb2_cp_async4(pres + i, a.elem_res + (long long)pe0 * %d + i); }" % (ND, NS, ND, ND))
@@ -911,18 +916,24 @@ class CudaEmitter:
             w(indent + "  asm volatile(\"cp.async.commit_group;\" ::: \"memory\");")
             w(indent + "}")
         w("    // position maps travel one batch ahead of the scatter (cp.async into the other MAPS slot)")
+        w("    // the batch table (first element, size | tile, conflict mask) travels TWO batches ahead in registers: the scatter warps are the")
+        w("    // critical role and would otherwise wait for an L2 round trip at the top of every batch")
+        w("    int bt_m0 = 0, bt_m1 = 0, bt_m2 = 0, bt_e0 = 0, bt_e1 = 0, bt_e2 = 0; unsigned long long bt_b0 = 0, bt_b1 = 0, bt_b2 = 0;")
+        w("    if (ib0 < ib1) { bt_m0 = __ldg(a.batch_meta + ib0); bt_e0 = __ldg(a.batch_elem + ib0); bt_b0 = __ldg(a.batch_bar + ib0); }")
+        w("    if (ib0 + 1 < ib1) { bt_m1 = __ldg(a.batch_meta + ib0 + 1); bt_e1 = __ldg(a.batch_elem + ib0 + 1); bt_b1 = __ldg(a.batch_bar + ib0 + 1); }")
         w("    if (ib0 < ib1)")
-        emit_prefetch("    ", "ib0", "0")
+        emit_prefetch("    ", "bt_e0", "bt_m0", "0")
         w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
-        w("      const int meta = a.batch_meta[batch], nel = meta & 63, tile = meta >> 7;")
-        w("      const unsigned long long bmask = a.batch_bar[batch];")
+        w("      const int meta = bt_m0, nel = meta & 63, tile = meta >> 7, e0_this = bt_e0; (void)e0_this;")
+        w("      const unsigned long long bmask = bt_b0;")
+        w("      if (batch + 2 < ib1) { bt_m2 = __ldg(a.batch_meta + batch + 2); bt_e2 = __ldg(a.batch_elem + batch + 2); bt_b2 = __ldg(a.batch_bar + batch + 2); }")
         w("      unsigned char* const mbase = maps0 + (it & 1) * %d;" % map_slot_bytes)
         w("      int* const s_rowstart = (int*)mbase; int* const s_resmap = s_rowstart + %d;" % (EPB * ND))
         if not map_async:
             w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d);" % (EPB * ND))
         else:
-            w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d) + (int)(((long long)a.batch_elem[batch] * %d * (a.map_bits >> 3)) & 7);" % (EPB * ND, ND2))
+            w("      unsigned char* const s_map = (unsigned char*)(s_resmap + %d) + (int)(((long long)e0_this * %d * (a.map_bits >> 3)) & 7);" % (EPB * ND, ND2))
         w("      (void)s_map;")
         if self.timing: w("      long long ts0 = clock64();")
         w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")
@@ -930,7 +941,7 @@ class CudaEmitter:
         w("      if (publish) __threadfence();               // everything scattered so far becomes globally visible")
         w("      pb2_bar_sync(11, %d);                       // maps of this batch visible to all scatter warps; previous batch fully issued" % NS)
         w("      if (batch + 1 < ib1)")
-        emit_prefetch("      ", "batch + 1", "(it + 1) & 1")
+        emit_prefetch("      ", "bt_e1", "bt_m1", "(it + 1) & 1")
         w("      if (publish && tile != prev_tile) { if (st == 0) atomicAdd(a.tile_done + prev_tile, pending); pending = 0; }")
         w("      prev_tile = tile; ++pending;")
         if self.timing: w("      long long ts1 = clock64(); dbs0 += ts1 - ts0;")
@@ -972,6 +983,7 @@ class CudaEmitter:
         if self.timing: w("        dbs3 += clock64() - ts3;")
         w("        pb2_bar_arrive(%d + oslot, %d);           // OUT[oslot] free again" % (7, NC + NS))
         w("      }")
+        w("      bt_m0 = bt_m1; bt_e0 = bt_e1; bt_b0 = bt_b1; bt_m1 = bt_m2; bt_e1 = bt_e2; bt_b1 = bt_b2;")
         w("    }")
         w("    if (prev_tile >= 0) { __threadfence(); pb2_bar_sync(11, %d); if (st == 0) atomicAdd(a.tile_done + prev_tile, pending); }" % NS)
         if self.timing: w("    if (st == 0 && a.debug) { atomicAdd(a.debug + 4, (unsigned long long)dbs0); atomicAdd(a.debug + 5, (unsigned long long)dbs1); atomicAdd(a.debug + 6, (unsigned long long)dbs2); atomicAdd(a.debug + 7, (unsigned long long)dbs3); }")
