@@ -832,6 +832,8 @@ class CudaEmitter:
         w("    int it = 0; long long dbg0 = 0, dbg1 = 0; (void)dbg0; (void)dbg1;")
         w("    int* const s_idx0 = (int*)((unsigned char*)(smem + %d) + %d);" % (off_maps, 2 * map_slot_bytes))
         w("    // element -> node indices travel one batch ahead (cp.async), so the nodal data of a batch needs one memory round trip")
+        bt_pipe_g = os.environ.get("PB2_BT_PIPE_G", "1") != "0"
+        bt_pipe_s = os.environ.get("PB2_BT_PIPE_S", "1") != "0"
         w("    int gt_m0 = 0, gt_m1 = 0, gt_m2 = 0, gt_e0 = 0, gt_e1 = 0, gt_e2 = 0;     // batch table two batches ahead in registers")
         w("    if (ib0 < ib1) { gt_m0 = __ldg(a.batch_meta + ib0); gt_e0 = __ldg(a.batch_elem + ib0); }")
         w("    if (ib0 + 1 < ib1) { gt_m1 = __ldg(a.batch_meta + ib0 + 1); gt_e1 = __ldg(a.batch_elem + ib0 + 1); }")
@@ -840,8 +842,12 @@ class CudaEmitter:
         w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
         w("      const int slot = it & 1;")
-        w("      const int nel = gt_m0 & 63, e0 = gt_e0; (void)e0;")
-        w("      if (batch + 2 < ib1) { gt_m2 = __ldg(a.batch_meta + batch + 2); gt_e2 = __ldg(a.batch_elem + batch + 2); }")
+        if bt_pipe_g:
+            w("      const int nel = gt_m0 & 63, e0 = gt_e0; (void)e0;")
+            w("      if (batch + 2 < ib1) { gt_m2 = __ldg(a.batch_meta + batch + 2); gt_e2 = __ldg(a.batch_elem + batch + 2); }")
+        else:
+            w("      const int nel = a.batch_meta[batch] & 63, e0 = a.batch_elem[batch]; (void)e0;")
+            w("      if (batch + 1 < ib1) { gt_m1 = a.batch_meta[batch + 1]; gt_e1 = a.batch_elem[batch + 1]; }")
         w("      const int* const s_idx = s_idx0 + slot * %d;" % (EPB * NN))
         w("      asm volatile(\"cp.async.wait_all;\" ::: \"memory\");")
         w("      pb2_bar_sync(13, %d);                        // indices of this batch visible to all gather warps" % NG)
@@ -925,9 +931,14 @@ class CudaEmitter:
         emit_prefetch("    ", "bt_e0", "bt_m0", "0")
         w("    for (int batch = ib0; batch < ib1; ++batch, ++it)")
         w("    {")
-        w("      const int meta = bt_m0, nel = meta & 63, tile = meta >> 7, e0_this = bt_e0; (void)e0_this;")
-        w("      const unsigned long long bmask = bt_b0;")
-        w("      if (batch + 2 < ib1) { bt_m2 = __ldg(a.batch_meta + batch + 2); bt_e2 = __ldg(a.batch_elem + batch + 2); bt_b2 = __ldg(a.batch_bar + batch + 2); }")
+        if bt_pipe_s:
+            w("      const int meta = bt_m0, nel = meta & 63, tile = meta >> 7, e0_this = bt_e0; (void)e0_this;")
+            w("      const unsigned long long bmask = bt_b0;")
+            w("      if (batch + 2 < ib1) { bt_m2 = __ldg(a.batch_meta + batch + 2); bt_e2 = __ldg(a.batch_elem + batch + 2); bt_b2 = __ldg(a.batch_bar + batch + 2); }")
+        else:
+            w("      const int meta = a.batch_meta[batch], nel = meta & 63, tile = meta >> 7, e0_this = a.batch_elem[batch]; (void)e0_this;")
+            w("      const unsigned long long bmask = a.batch_bar[batch];")
+            w("      if (batch + 1 < ib1) { bt_m1 = a.batch_meta[batch + 1]; bt_e1 = a.batch_elem[batch + 1]; }")
         w("      unsigned char* const mbase = maps0 + (it & 1) * %d;" % map_slot_bytes)
         w("      int* const s_rowstart = (int*)mbase; int* const s_resmap = s_rowstart + %d;" % (EPB * ND))
         if not map_async:
