@@ -832,8 +832,12 @@ class CudaEmitter:
         w("    int it = 0; long long dbg0 = 0, dbg1 = 0; (void)dbg0; (void)dbg1;")
         w("    int* const s_idx0 = (int*)((unsigned char*)(smem + %d) + %d);" % (off_maps, 2 * map_slot_bytes))
         w("    // element -> node indices travel one batch ahead (cp.async), so the nodal data of a batch needs one memory round trip")
-        bt_pipe_g = os.environ.get("PB2_BT_PIPE_G", "1") != "0"
-        bt_pipe_s = os.environ.get("PB2_BT_PIPE_S", "1") != "0"
+        # Batch table (first element, size | tile, conflict mask) two batches ahead in registers instead of global loads at the top of
+        # every batch.  A/B on one box (tools/r02_btab.py): in the SCATTER role it shortens config 2 by 1.9 % (2.703 -> 2.653 ms: the
+        # critical role no longer waits for an L2 round trip per batch) but costs the classes with little scatter work per batch
+        # 0.3-1.3 % (Poisson, Q27 heat); in the GATHER role it changes nothing.  Default: scatter role for batches of >= 6000 matrix entries.
+        bt_pipe_g = os.environ.get("PB2_BT_PIPE_G", "0") != "0"
+        bt_pipe_s = os.environ.get("PB2_BT_PIPE_S", "1" if ND2 * EPB >= 6000 else "0") != "0"
         w("    int gt_m0 = 0, gt_m1 = 0, gt_m2 = 0, gt_e0 = 0, gt_e1 = 0, gt_e2 = 0;     // batch table two batches ahead in registers")
         w("    if (ib0 < ib1) { gt_m0 = __ldg(a.batch_meta + ib0); gt_e0 = __ldg(a.batch_elem + ib0); }")
         w("    if (ib0 + 1 < ib1) { gt_m1 = __ldg(a.batch_meta + ib0 + 1); gt_e1 = __ldg(a.batch_elem + ib0 + 1); }")
