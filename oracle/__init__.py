@@ -111,6 +111,8 @@ class OracleProblem:
                                                  node_val.shape[2], self.T, pos.shape[0], _dp(pos), _dp(lagr),
                                                  _dp(node_val), _ip(self.node_eqn), _ip(self.pos_eqn), self.n_dof))
         self.maxdof = 2 * mesh.elem_nodes.shape[1] * (self.dim + node_val.shape[2])     # x2: master values outside the element
+        if code.etype.name.startswith("QuadFace"):
+            L.oracle_set_face_mode(self.h)
         hanging = getattr(mesh, "hanging", None)
         if hanging is not None:
             for space, table in ((0, hanging.C2), (1, hanging.C1)):

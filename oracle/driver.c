@@ -228,6 +228,8 @@ typedef struct
   int c1_nodes[8];
   int tri;  /* TElement<2,3> instead of QElement<2,3> */
   int edim; /* dimension of the element itself: dim for bulk elements, 1 for a line element in 2D (interface elements) */
+  int face; /* a face (s1 = -1) of a Q9 bulk element seen through the bulk element: bulk shape functions and gradients on the face,
+               Gauss<1,3> along it, measure |dx/ds0|, outer normal (the reference's bulk_eleminfo / opposite_eleminfo, jitbridge.h:88-120) */
 } EType;
 
 typedef struct { int col; double val; } Pair;
@@ -392,11 +394,11 @@ static void fill_shape_info_at_s(ThreadState *ts, const double *s, double weight
     }
     if (pass == 0)
     {
-      detE = sqrt(det_a);
+      detE = sqrt(o->et.face ? amet[0][0] : det_a);
       memcpy(aup, up, sizeof(up));
     }
     else
-      detL = sqrt(det_a);
+      detL = sqrt(o->et.face ? amet[0][0] : det_a);
   }
 
   /* moving-mesh helper (src/elements.cpp:3051-3155): int_pt_weights_d_coords and DXdshape_il_jb, el_dim x nodal_dim general */
@@ -501,6 +503,13 @@ static void fill_shape_info_at_s(ThreadState *ts, const double *s, double weight
           for (int k = 0; k < dim; k++) si->d_normal_dcoord[i][l][k] = dpsids[l] * denom * (k == 1 ? -1 : 1) * t[0][i] * t[0][1 - k];
     }
   }
+  if (o->et.face)
+  {
+    /* outer unit normal of the face s1 = -1 of a counter-clockwise element: (t_y, -t_x) / |t|, t = dx/ds0 */
+    const double len = sqrt(t[0][0] * t[0][0] + t[0][1] * t[0][1]);
+    si->normal[0] = t[0][1] / len;
+    si->normal[1] = -t[0][0] / len;
+  }
   si->int_pt_weight_unity = weight;
   si->int_pt_weight = weight * detE;
   si->int_pt_weight_Lagrangian = weight * detL;
@@ -511,7 +520,12 @@ static void cb_fill_shape_buffer_for_point(unsigned ipt, JITFuncSpec_RequiredSha
 {
   ThreadState *ts = TS;
   double s[MAXD], w;
-  if (ts->o->et.tri && ts->o->et.dim == 3) oracle_gauss_tet((int)ipt, s, &w);
+  if (ts->o->et.face)
+  {
+    oracle_gauss_1d((int)ipt, s, &w);
+    s[1] = -1.0;
+  }
+  else if (ts->o->et.tri && ts->o->et.dim == 3) oracle_gauss_tet((int)ipt, s, &w);
   else if (ts->o->et.tri) oracle_gauss_tri((int)ipt, s, &w);
   else if (ts->o->et.edim == 1) oracle_gauss_1d((int)ipt, s, &w);
   else oracle_gauss(ts->o->et.dim, (int)ipt, s, &w);
@@ -693,6 +707,15 @@ static void bind_element(ThreadState *ts, int e)
     }
   }
   ts->ei.ndof = nloc;
+}
+
+/* the elements are FACES (s1 = -1) of Q9 bulk elements given by their nine (rotated) bulk nodes */
+void oracle_set_face_mode(void *h)
+{
+  Oracle *o = (Oracle *)h;
+  if (o->et.dim != 2 || o->et.nnode != 9 || o->pos_eqn) { fprintf(stderr, "oracle: face mode needs Q9 elements on a fixed mesh\n"); abort(); }
+  o->et.face = 1;
+  o->et.n_int = 3;
 }
 
 /* hanging nodes of one space (0: C2 and positions, 1: C1): CSR over the nodes */

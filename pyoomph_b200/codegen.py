@@ -60,6 +60,11 @@ ELEMENT_TYPES: Dict[str, ElementType] = {
     # BulkElementTetra3dC2 = TElement<3,3>: ten-node tetrahedra (vertices 0-3, then the mid-edge nodes in oomph order, Telements.h:2051),
     # C1 on the four vertices, TGauss<3,3> (11 points)
     "Tetra3dC2": ElementType("Tetra3dC2", 3, 3, 10, 3, (0, 1, 2, 3), 11),
+    # A FACE of a Q9 bulk element seen through the bulk element (the reference's bulk_eleminfo / opposite_eleminfo of an interface element,
+    # src/jitbridge.h:88-120: `blk_` / `oppblk_` quantities of the generated code): the nine nodes of the bulk element, rotated so that the
+    # face is s1 = -1; the integral runs over the face (Gauss<1,3> in s0, measure |dx/ds0|, outer normal (t_y, -t_x)/|t|) while shape
+    # functions and their Eulerian gradients are the BULK ones evaluated on the face -- normal derivatives of bulk fields are available.
+    "QuadFace2dC2": ElementType("QuadFace2dC2", 2, 2, 9, 3, (0, 2, 6, 8), 3),
 }
 
 SPACE_ORDER = ("C2TB", "C2", "C1TB", "C1")  # nodal_data index order (src/codegen.cpp:2367-2380)
@@ -510,6 +515,8 @@ class FiniteElementCode:
                     add(J, (si, col_field, info.deriv), w * c)
                     if info.dt_order == 1:
                         add(M, (si, col_field, info.deriv), c)  # __partial_t_mass_matrix (src/codegen.cpp:8260)
+            if self.coordinates_as_dofs and self.etype.name.startswith("QuadFace"):
+                raise NotImplementedError("bulk-face interface elements on a moving mesh (position derivatives of the face measure and normal)")
             if self.coordinates_as_dofs:
                 RE = ex.DX_EUL * sp.diff(Rs, ex.DX_EUL)  # Eulerian-measure part
                 slot = slots[si]

@@ -129,6 +129,9 @@ def line_shape_tables(order: int, knots):
 
 def element_rule(et):
     """(knots, weights) of the element type's default integration scheme"""
+    if et.name.startswith("QuadFace"):
+        k1, w1 = gauss_rule_1d()          # the face s1 = -1 of the bulk element, Gauss<1,3> along it
+        return [(k[0], -1.0) for k in k1], list(w1)
     if et.name.startswith("Tri"):
         return tgauss_rule()
     if et.name.startswith("Tetra"):
@@ -1426,7 +1429,15 @@ class CudaEmitter:
             for i in range(dim):
                 w("      const double %s%d%d = %s;" % (gname, b, i, " + ".join("up_%s%d%d * %s%d%d" % (gname, a_, b, t, a_, i) for a_ in range(edim))))
                 w("      P[%d] = %s%d%d;" % (plan[gname] + b * dim + i, gname, b, i))
-        w("      const double %s = sqrt(det_%s);" % (detname, gname))
+        if self.et.name.startswith("QuadFace") and gname == "gg":
+            # face of a bulk element: the integral runs over s0 on the face s1 = -1, measure |dx/ds0|; outer normal of a counter-clockwise
+            # element (t_y, -t_x)/|t| (the reference: FaceElement::outer_unit_normal with the bulk element's normal_sign)
+            w("      const double %s = sqrt(am_%s00);" % (detname, gname))
+            w("      const double nrm0 = %s01 / %s, nrm1 = -%s00 / %s; (void)nrm0; (void)nrm1;" % (t, detname, t, detname))
+        elif self.et.name.startswith("QuadFace"):
+            w("      const double %s = sqrt(am_%s00);" % (detname, gname))
+        else:
+            w("      const double %s = sqrt(det_%s);" % (detname, gname))
         if edim == 1 and dim == 2 and gname == "gg":
             # unit normal of a line element (BulkElementBase::get_normal_at_s, src/elements.cpp:1730-1752): (-t_y, t_x) / |t|
             w("      const double nrm_len = (det_gg < 1e-20) ? 1.0 : sqrt(det_gg);")

@@ -292,3 +292,27 @@ class NavierStokesFreeSurface(Equations):
         self.add_residual(weak(self.surface_tension, div(u_test)))
         if self.additional_normal_traction != 0:
             self.add_residual(weak(self.additional_normal_traction, dot(n, u_test)))
+
+
+class NitscheDirichletBC(Equations):
+    """Weakly imposed Dirichlet condition  u = u_D  of  -div(k(u) grad u) = f  on a boundary (Nitsche's method):
+
+        - weak(k grad(u).n, v)  - weak(u - u_D, k grad(v).n)  + weak(gamma (u - u_D), v)
+
+    The normal derivatives of the field AND of the test function are BULK quantities: the class lives on faces seen through their bulk
+    elements (element type QuadFace2dC2; in the reference an interface element reaching into `bulk_eleminfo`, src/jitbridge.h:88-120 --
+    the same access the evaporation flux of config 4 makes to the gas-side gradient through `opposite_eleminfo`)."""
+
+    def __init__(self, name: str = "u", value=0, conductivity=None, penalty=100.0):
+        super().__init__()
+        self.name, self.value, self.conductivity, self.penalty = name, value, conductivity, penalty
+
+    def define_fields(self):
+        self.define_scalar_field(self.name, "C2")
+
+    def define_residuals(self):
+        u, v = var_and_test(self.name)
+        n = var("normal")
+        k = self.conductivity(u) if callable(self.conductivity) else (1 if self.conductivity is None else self.conductivity)
+        uD = self.value() if callable(self.value) else self.value
+        self.add_residual(-weak(k * dot(grad(u), n), v) - weak(u - uD, k * dot(grad(v), n)) + weak(self.penalty * (u - uD), v))

@@ -113,7 +113,7 @@ def var(arg: Union[str, Sequence[str]]):
     if arg == "time":
         return TIME
     if arg == "normal":
-        if code.etype.elem_dim >= code.nodal_dim:
+        if code.etype.elem_dim >= code.nodal_dim and not code.etype.name.startswith("QuadFace"):
             raise RuntimeError("var(\"normal\") is defined on interface elements only")
         return sp.Matrix(list(NORMAL[:code.nodal_dim]) + _padding(code, NORMAL[:code.nodal_dim]))
     comps = _vector_components(code, arg)

@@ -168,6 +168,32 @@ def RectangularTriangleMesh(N=10, size=1.0, lower_left=(0.0, 0.0)) -> Structured
     return m
 
 
+def boundary_face_mesh(mesh: StructuredMesh, names: Sequence[str]) -> InterfaceMesh:
+    """The boundary edges of a RectangularQuadMesh as FACES OF THEIR BULK ELEMENTS (element type QuadFace2dC2): per edge the nine nodes
+    of the bulk element, rotated (orientation preserved) so that the edge is the local face s1 = -1 traversed in the direction of
+    increasing s0; the outer normal is then (t_y, -t_x)/|t|.  Rotations of the 3x3 node grid: right face (i, j) <- (2 - j, i), top face
+    (i, j) <- (2 - i, 2 - j), left face (i, j) <- (j, 2 - i)."""
+    if mesh.dim != 2 or mesh.element_type != "Quad2dC2":
+        raise NotImplementedError("bulk faces: Q9 meshes only")
+    Nx, Ny = mesh.N
+    rot = {"bottom": [i + 3 * j for j in range(3) for i in range(3)],
+           "right": [(2 - j) + 3 * i for j in range(3) for i in range(3)],
+           "top": [(2 - i) + 3 * (2 - j) for j in range(3) for i in range(3)],
+           "left": [j + 3 * (2 - i) for j in range(3) for i in range(3)]}
+    elems = {"bottom": [ex * Ny for ex in range(Nx)], "top": [ex * Ny + Ny - 1 for ex in range(Nx)],
+             "left": list(range(Ny)), "right": [(Nx - 1) * Ny + ey for ey in range(Ny)]}
+    en, be, fi = [], [], []
+    face_id = {"left": -1, "right": 1, "bottom": -2, "top": 2}
+    for name in names:
+        for e in elems[name]:
+            en.append(mesh.elem_nodes[e][rot[name]])
+            be.append(e)
+            fi.append(face_id[name])
+    en = np.ascontiguousarray(np.stack(en), dtype=np.int32)
+    return InterfaceMesh(2, mesh.N, en, mesh.node_pos, mesh.node_lattice, mesh.boundaries, "QuadFace2dC2", np.array(be, dtype=np.int64),
+                         np.array(fi, dtype=np.int32), mesh.is_vertex())
+
+
 def CuboidTetraMesh(N=4, size=1.0, lower_left=(0.0, 0.0, 0.0)) -> StructuredMesh:
     """Ten-node tetrahedra (BulkElementTetra3dC2 = oomph TElement<3,3>, src/elements.cpp:11397) on the node set of the Q27 mesh: every
     cell is cut into the six Kuhn tetrahedra around its main diagonal (one per order in which the three axes are walked from the

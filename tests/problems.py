@@ -76,6 +76,23 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             return _variant(_mk["brick"](n))
     else:
         from pyoomph_b200.meshes import CuboidBrickMesh, RectangularQuadMesh
+    if kind == "nitsche_face":
+        # interface class that reaches into its BULK element (normal derivatives of the field and of the test function on the face):
+        # element type QuadFace2dC2 on two boundaries of a (distorted) Q9 mesh, Nitsche's method for a nonlinear diffusion problem
+        import pyoomph_b200.meshes as _mm
+        from pyoomph_b200.equations import NitscheDirichletBC
+        from pyoomph_b200.expressions import var as _var
+        bulk = _mm.RectangularQuadMesh(N)
+        if distortion:
+            bulk = distort(bulk, distortion, seed)
+        mesh = _mm.boundary_face_mesh(bulk, ["right", "top", "bottom"])
+        code = FiniteElementCode("QuadFace2dC2", NitscheDirichletBC("u", value=lambda: 0.3 + _var("coordinate_x") * _var("coordinate_y"),
+                                                                     conductivity=lambda u: 1 + 0.5 * u * u, penalty=40.0), name="nitscheface")
+        bulk_code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")
+        dofmap = assign_equation_numbers(bulk, bulk_code, {"u": bulk.boundaries["left"]}, None)
+        vals = np.zeros((1, bulk.n_node, 1))
+        vals[0, :, 0] = smooth_field(bulk.node_pos, 0, seed)
+        return dict(kind=kind, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=None, unsteady=False, params={}, bulk_mesh=bulk, bulk_code=bulk_code)
     if kind in ("robin_if", "freesurf_if", "freesurf_mov_if"):
         # interface element classes (InterfaceElementLine1dC2) on boundary edges of a (distorted) Q9 mesh, on the bulk's nodes, nodal
         # values and equation numbers: a Robin condition for the Poisson field of config 1, and the free-surface terms of config 4

@@ -557,7 +557,9 @@ def test_point_expressions_parity(kind, N, distortion, unstructured):
 
 INTERFACES = [("robin_if", 6, 0.12), ("robin_if", 9, 0.0), ("freesurf_if", 5, 0.1), ("freesurf_if", 24, 0.05),
               # config 4's interface class on a MOVING mesh: kinematic condition with the mesh velocity, position dofs in the Jacobian
-              ("freesurf_mov_if", 5, 0.1), ("freesurf_mov_if", 20, 0.06)]
+              ("freesurf_mov_if", 5, 0.1), ("freesurf_mov_if", 20, 0.06),
+              # faces seen through their bulk elements (bulk_eleminfo access): Nitsche's method with normal derivatives of field and test function
+              ("nitsche_face", 5, 0.12), ("nitsche_face", 16, 0.0)]
 
 
 @pytest.mark.gpu
@@ -591,7 +593,7 @@ def test_interface_element_classes_parity(kind, N, distortion):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,N,distortion", [("robin_if", 7, 0.1), ("freesurf_if", 6, 0.1), ("freesurf_if", 40, 0.0), ("freesurf_mov_if", 6, 0.08)])
+@pytest.mark.parametrize("kind,N,distortion", [("robin_if", 7, 0.1), ("freesurf_if", 6, 0.1), ("freesurf_if", 40, 0.0), ("freesurf_mov_if", 6, 0.08), ("nitsche_face", 7, 0.1)])
 def test_interface_class_assembled_into_the_matrix_of_its_bulk_class(kind, N, distortion):
     """A child problem (pb2_problem_create_child): the interface class scatters into the CSR matrix and residual its bulk class just
     wrote, on the device; the sum equals the oracle's two classes assembled into one matrix (oomph assembles all element classes of a

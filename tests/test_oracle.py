@@ -531,3 +531,54 @@ def test_moving_free_surface_of_the_oracle_matches_finite_differences():
             checked_pos += 1
     assert checked_pos >= 8
     op.close()
+
+
+def test_bulk_face_elements_of_the_oracle():
+    """Faces seen through their bulk elements (QuadFace2dC2: the reference's bulk_eleminfo access of an interface element): on a distorted
+    Q9 mesh the bulk gradient of a linear field is exact on the face, only the three face nodes carry values there, the measure adds up
+    to the boundary length, the normal is unit, orthogonal to the face tangent and leaves the bulk element; the analytic Jacobian of
+    Nitsche's method (normal derivatives of field and test function, nonlinear conductivity) agrees with finite differences."""
+    from problems import csr_to_sorted, make_oracle, make_problem
+    from pyoomph_b200.cuda_emitter import gauss_rule_1d
+    pb = make_problem("nitsche_face", 4, distortion=0.12)
+    im, bulk = pb["mesh"], pb["bulk_mesh"]
+    op = make_oracle(pb)
+    a = np.array([0.7, -1.3])
+    kn, w1 = gauss_rule_1d()
+    length = 0.0
+    for e in range(im.n_elem):
+        xe = bulk.node_pos[im.elem_nodes[e]]
+        centroid = xe.mean(axis=0)
+        for ipt in range(3):
+            wts, sh, dx, _, _, _ = op.point_shapes(e, ipt, flag=0)
+            assert np.abs((xe @ a) @ dx - a).max() <= 1e-12                      # bulk gradient, both components
+            assert np.abs(sh[3:]).max() <= 1e-15 and abs(sh[:3].sum() - 1.0) <= 1e-15
+            s = kn[ipt][0]
+            t = np.array([s - 0.5, -2.0 * s, s + 0.5]) @ xe[:3]                   # tangent from the three face nodes
+            assert abs(wts[0] - np.hypot(*t) * w1[ipt]) <= 1e-14
+            length += wts[0]
+            nrm = np.array([t[1], -t[0]]) / np.hypot(*t)
+            assert nrm @ (sh @ xe - centroid) > 0.0                               # outward
+    # boundary length of the three sides: sum of the parabola arcs ~ their chord polygon (loose), and equal to the line-element measure
+    pbl = make_problem("robin_if", 4, distortion=0.12)
+    assert length > 2.5
+    n = pb["dofmap"].n_dof
+    r, mats = op.assemble(flag=1)
+    A = csr_to_sorted(n, *mats[0]).toarray()
+    eq, eps = pb["dofmap"].node_eqn, 1e-6
+    for node in np.unique(im.elem_nodes)[::2]:
+        g = eq[node, 0]
+        if g < 0:
+            continue
+        v = pb["vals"][0].copy()
+        v[node, 0] += eps
+        op.update_values(0, v)
+        rp, _ = op.assemble(flag=0)
+        v[node, 0] -= 2 * eps
+        op.update_values(0, v)
+        rm, _ = op.assemble(flag=0)
+        op.update_values(0, pb["vals"][0])
+        assert np.abs((rp - rm) / (2 * eps) - A[:, g]).max() <= 1e-8 * np.abs(A).max()
+    # the Jacobian couples the face to the interior nodes of its bulk element (normal derivative): more than the 3x3 face block
+    assert np.count_nonzero(A) > 9 * im.n_elem
+    op.close()
