@@ -794,6 +794,29 @@ static void element_rjm_bound(ThreadState *ts, int which, int param, unsigned fl
   prepare_shape_buffer(ts);
   ts->si.jacobian_size = ts->ei.ndof;
   ts->si.mass_matrix_size = ts->ei.ndof;
+  /* fill_shape_info_element_sizes (src/elements.cpp:3527-3568): sum over all integration points of w * J, times the coordinate
+   * system's JacobianForElementSize at the point for the non-Cartesian size */
+  const JITFuncSpec_RequiredShapes_FiniteElement_t *rq = &o->ft->shapes_required_ResJac[which];
+  if (rq->elemsize_Eulerian_Pos || rq->elemsize_Eulerian_cartesian_Pos)
+  {
+    double esz = 0.0, esz_cart = 0.0;
+    for (int q = 0; q < o->et.n_int; q++)
+    {
+      double s[MAXD], w;
+      if (o->et.tri && o->et.dim == 3) oracle_gauss_tet(q, s, &w);
+      else if (o->et.tri) oracle_gauss_tri(q, s, &w);
+      else if (o->et.edim == 1) oracle_gauss_1d(q, s, &w);
+      else oracle_gauss(o->et.dim, q, s, &w);
+      fill_shape_info_at_s(ts, s, w, 0u, NULL);
+      double x[MAXD] = {0, 0, 0};
+      for (int l = 0; l < o->et.nnode; l++)
+        for (int i = 0; i < o->et.dim; i++) x[i] += ts->ei.nodal_coords[l][i][0] * ts->si.shape_C2[l];
+      esz_cart += ts->si.int_pt_weight;
+      esz += ts->si.int_pt_weight * o->ft->JacobianForElementSize(&ts->ei, x);
+    }
+    ts->si.elemsize_Eulerian = esz;
+    ts->si.elemsize_Eulerian_cartesian = esz_cart;
+  }
   JITFuncSpec_ResidualAndJacobian_FiniteElement func;
   if (param >= 0)
     func = o->ft->ParameterDerivative[which][param];

@@ -121,7 +121,8 @@ class CEmitter:
             if t.field not in test_fields:
                 test_fields.append(t.field)
         names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi",
-                                       ex.NORMAL[0]: "shapeinfo->normal[0]", ex.NORMAL[1]: "shapeinfo->normal[1]", ex.NORMAL[2]: "shapeinfo->normal[2]"}
+                                       ex.NORMAL[0]: "shapeinfo->normal[0]", ex.NORMAL[1]: "shapeinfo->normal[1]", ex.NORMAL[2]: "shapeinfo->normal[2]",
+                                       ex.ELEMSIZE_EUL: "shapeinfo->elemsize_Eulerian", ex.ELEMSIZE_EUL_CART: "shapeinfo->elemsize_Eulerian_cartesian"}
         for a in atoms:
             names[code.atom_symbol(a)] = "this_" + a.cname
         for k, p in enumerate(code.global_params):
@@ -305,7 +306,8 @@ class CEmitter:
             used |= {s_ for s_ in e.free_symbols if s_ in code._atom_syms}
         atoms = sorted([code._atom_syms[s_] for s_ in used], key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
         names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi",
-                                       ex.NORMAL[0]: "shapeinfo->normal[0]", ex.NORMAL[1]: "shapeinfo->normal[1]", ex.NORMAL[2]: "shapeinfo->normal[2]"}
+                                       ex.NORMAL[0]: "shapeinfo->normal[0]", ex.NORMAL[1]: "shapeinfo->normal[1]", ex.NORMAL[2]: "shapeinfo->normal[2]",
+                                       ex.ELEMSIZE_EUL: "shapeinfo->elemsize_Eulerian", ex.ELEMSIZE_EUL_CART: "shapeinfo->elemsize_Eulerian_cartesian"}
         for a in atoms:
             names[code.atom_symbol(a)] = "this_" + a.cname
         for k, p in enumerate(code.global_params):
@@ -453,7 +455,8 @@ class CEmitter:
             if t.field not in test_fields:
                 test_fields.append(t.field)
         names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi",
-                                       ex.NORMAL[0]: "shapeinfo->normal[0]", ex.NORMAL[1]: "shapeinfo->normal[1]", ex.NORMAL[2]: "shapeinfo->normal[2]"}
+                                       ex.NORMAL[0]: "shapeinfo->normal[0]", ex.NORMAL[1]: "shapeinfo->normal[1]", ex.NORMAL[2]: "shapeinfo->normal[2]",
+                                       ex.ELEMSIZE_EUL: "shapeinfo->elemsize_Eulerian", ex.ELEMSIZE_EUL_CART: "shapeinfo->elemsize_Eulerian_cartesian"}
         for a in atoms:
             names[code.atom_symbol(a)] = "this_" + a.cname
         for k, p in enumerate(code.global_params):
@@ -602,6 +605,13 @@ class CEmitter:
         w('#include "oracle_jit_hang.h"')
         w("")
         resnames = code.residual_names()
+        # src/codegen.cpp:5762-5772: the coordinate system's geometric Jacobian as a function of the position, used for elemsize_Eulerian
+        w("// Used for elemsize_Eulerian etc")
+        w("static double JacobianForElementSize(const JITElementInfo_t * eleminfo, const double * _x)")
+        w("{")
+        w("  return %s;" % ("2*Pi*_x[0]" if code.coordinate_system.get_id_name() == "Axisymmetric" else "1.0"))
+        w("}")
+        w("")
         for i, rn in enumerate(resnames):
             w(self.routine("ResidualAndJacobian%d" % i, rn, i, None))
             for p in code.global_params:
@@ -649,6 +659,12 @@ class CEmitter:
         for i, rn in enumerate(resnames):
             w(' SET_INTERNAL_NAME(functable->res_jac_names[%d],"%s");' % (i, rn))
         w(" functable->shapes_required_ResJac=(JITFuncSpec_RequiredShapes_FiniteElement_t *)calloc(%d,sizeof(JITFuncSpec_RequiredShapes_FiniteElement_t));" % max(1, len(resnames)))
+        for i, rn in enumerate(resnames):
+            if code.residuals[rn].has(ex.ELEMSIZE_EUL):
+                w(" functable->shapes_required_ResJac[%d].elemsize_Eulerian_Pos=true;" % i)
+            if code.residuals[rn].has(ex.ELEMSIZE_EUL_CART):
+                w(" functable->shapes_required_ResJac[%d].elemsize_Eulerian_cartesian_Pos=true;" % i)
+        w(" functable->JacobianForElementSize=&JacobianForElementSize;")
         w(" functable->numglobal_params=%d;" % len(code.global_params))
         w(" functable->global_parameters=(double **)calloc(%d,sizeof(double*));" % max(1, len(code.global_params)))
         w(" functable->ResidualAndJacobian=(JITFuncSpec_ResidualAndJacobian_FiniteElement *)calloc(%d,sizeof(JITFuncSpec_ResidualAndJacobian_FiniteElement));" % max(1, len(resnames)))

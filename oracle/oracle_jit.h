@@ -54,6 +54,7 @@ typedef struct JITShapeInfo
 {
   unsigned int n_int_pt;
   double int_pt_weight, int_pt_weight_Lagrangian, int_pt_weight_unity;
+  double elemsize_Eulerian, elemsize_Eulerian_cartesian; /* jitbridge.h:178 */
   double **int_pt_weights_d_coords;      /* [dim][node] */
   double ****int_pt_weights_d2_coords;   /* [dim][dim][node][node] */
   double *shape_C2, **dx_shape_C2, **dX_shape_C2, **dS_shape_C2;
@@ -82,6 +83,7 @@ typedef struct JITFuncSpec_RequiredShapes_FiniteElement
 {
   bool psi_C1, psi_C2, dx_psi_C1, dx_psi_C2, dX_psi_C1, dX_psi_C2;
   bool psi_Pos, dx_psi_Pos, dX_psi_Pos;
+  bool elemsize_Eulerian_Pos, elemsize_Eulerian_cartesian_Pos; /* jitbridge.h:305-306 */
 } JITFuncSpec_RequiredShapes_FiniteElement_t;
 
 typedef void (*JITFuncSpec_GetZ2Fluxes_FiniteElement)(const JITElementInfo_t *, const JITShapeInfo_t *, double *); /* jitbridge.h:287 */
@@ -124,6 +126,7 @@ typedef struct JITFuncSpec_Table_FiniteElement
   char *domain_name;
   void (*check_compiler_size)(unsigned long long, unsigned long long, char *);
   void (*fill_shape_buffer_for_point)(unsigned, JITFuncSpec_RequiredShapes_FiniteElement_t *, int);
+  double (*JacobianForElementSize)(const JITElementInfo_t *, const double *); /* jitbridge.h:484 */
   void (*clean_up)(struct JITFuncSpec_Table_FiniteElement *functable);
 } JITFuncSpec_Table_FiniteElement_t;
 

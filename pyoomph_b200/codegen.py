@@ -463,6 +463,8 @@ class FiniteElementCode:
         return form
 
     def _coefficient_form(self, E: sp.Expr, name: str) -> ResidualForm:
+        if self.coordinates_as_dofs and (E.has(ex.ELEMSIZE_EUL) or E.has(ex.ELEMSIZE_EUL_CART)):
+            raise NotImplementedError("element sizes on a moving mesh (elemsize_d_coords, src/jitbridge.h:180)")
         tests = sorted([s for s in E.free_symbols if s in self._test_syms], key=lambda s: s.name)
         slots: List[TestSlot] = []
         R: List[sp.Expr] = []

@@ -1296,11 +1296,35 @@ class CudaEmitter:
         if plan["need_lagr"]:
             w("      const double dX = c_w[ipt] * detL;")
         # interpolation
-        names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "a.ti.t[0]", ex.pi: "3.14159265359"}
+        names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "a.ti.t[0]", ex.pi: "3.14159265359",
+                                       ex.ELEMSIZE_EUL: "esz_eul", ex.ELEMSIZE_EUL_CART: "esz_cart"}
         for i_, ns_ in enumerate(ex.NORMAL):
             names[ns_] = "nrm%d" % i_          # computed by _emit_geometry on interface elements
         for k, p in enumerate(code.global_params):
             names[code._param_syms[p]] = "a.params[%d]" % k
+        all_exprs = list(form.R) + list(form.J.values()) + list(form.M.values())
+        if any(e_.has(ex.ELEMSIZE_EUL) or e_.has(ex.ELEMSIZE_EUL_CART) for e_ in all_exprs if hasattr(e_, "has")):
+            # element sizes (fill_shape_info_element_sizes, src/elements.cpp:3527-3568): sum over ALL integration points of w * J, with the
+            # coordinate system's JacobianForElementSize (2 Pi r when axisymmetric) at the point for the non-Cartesian one; every
+            # (element, point) thread forms the sum itself (a few hundred flops; only classes that use the symbols pay)
+            if edim != 2 or dim != 2:
+                raise NotImplementedError("element sizes: two-dimensional bulk elements only")
+            axi = code.coordinate_system.get_id_name() == "Axisymmetric"
+            w("      double esz_cart = 0.0, esz_eul = 0.0;")
+            w("      for (int q = 0; q < %d; ++q)" % NIPT)
+            w("      {")
+            w("        const double* dq = s_dpsi2 + q * %d; const double* pq = s_psi2 + q * %d; (void)pq;" % (NN * edim, NN))
+            w("        double e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0, ex0 = 0.0;")
+            w("        for (int l = 0; l < %d; ++l)" % NN)
+            w("        {")
+            w("          const double X0 = E[%d + l * 2], X1 = E[%d + l * 2 + 1];" % (plan["xpos"], plan["xpos"]))
+            w("          e00 += X0 * dq[l * 2]; e01 += X1 * dq[l * 2]; e10 += X0 * dq[l * 2 + 1]; e11 += X1 * dq[l * 2 + 1]; ex0 += X0 * pq[l];")
+            w("        }")
+            w("        const double a00 = e00 * e00 + e01 * e01, a01 = e00 * e10 + e01 * e11, a11 = e10 * e10 + e11 * e11;")
+            w("        const double Jq = c_w[q] * sqrt(a00 * a11 - a01 * a01);")
+            w("        esz_cart += Jq; esz_eul += Jq * %s;" % ("(2.0 * 3.14159265359 * ex0)" if axi else "1.0"))
+            w("      }")
+            w("      (void)esz_cart; (void)esz_eul;")
         # local-derivative sums per (field, kind)
         for (f, kind), derivs in needed.items():
             fld = code.fields[f]

@@ -316,3 +316,32 @@ class NitscheDirichletBC(Equations):
         k = self.conductivity(u) if callable(self.conductivity) else (1 if self.conductivity is None else self.conductivity)
         uD = self.value() if callable(self.value) else self.value
         self.add_residual(-weak(k * dot(grad(u), n), v) - weak(u - uD, k * dot(grad(v), n)) + weak(self.penalty * (u - uD), v))
+
+
+class StreamlineDiffusionAdvection(Equations):
+    """Advection-diffusion with a streamline-upwind (SUPG) term scaled by the element length h = sqrt(element size)
+    (pyoomph/equations/advection_diffusion.py; `var("element_length_h")`, pyoomph/expressions/generic.py:178):
+
+        weak(partial_t(c) + w.grad(c), v) + weak(D grad(c), grad(v)) + weak(tau h (w.grad(c)), w.grad(v))
+
+    One number per element -- the integral of the measure over ALL its integration points -- enters every point of the element."""
+
+    def __init__(self, name: str = "c", wind=(1.0, 0.5), diffusivity=0.01, tau=0.5, cartesian_size: bool = False):
+        super().__init__()
+        self.name, self.wind, self.D, self.tau, self.cartesian_size = name, wind, diffusivity, tau, cartesian_size
+
+    def define_fields(self):
+        self.define_scalar_field(self.name, "C2")
+
+    def define_residuals(self):
+        c, v = var_and_test(self.name)
+        gc, gv = grad(c), grad(v)
+        wc = sum(self.wind[i] * gc[i, 0] for i in range(2))
+        wv = sum(self.wind[i] * gv[i, 0] for i in range(2))
+        if self.cartesian_size:
+            from .expressions import ELEMSIZE_EUL_CART
+            import sympy as sp
+            h = sp.sqrt(var("cartesian_element_size_Eulerian"))
+        else:
+            h = var("element_length_h")
+        self.add_residual(weak(partial_t(c) + wc, v) + weak(self.D * gc, gv) + weak(self.tau * h * wc, wv))

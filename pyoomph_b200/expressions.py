@@ -30,6 +30,10 @@ DX_LAG = sp.Symbol("M__dX", real=True)
 # unit normal of an interface element at the integration point (var("normal"); GiNaCNormalSymbol, src/codegen.cpp:7780-7823; printed as
 # shapeinfo->normal[i] by the reference)
 NORMAL = sp.symbols("NRM__0 NRM__1 NRM__2", real=True)
+# element sizes (JITShapeInfo_t::elemsize_Eulerian / elemsize_Eulerian_cartesian, src/jitbridge.h:178): the integral of the (coordinate
+# system's / Cartesian) measure over the element, one number per element
+ELEMSIZE_EUL = sp.Symbol("ESZ__eulerian", positive=True)
+ELEMSIZE_EUL_CART = sp.Symbol("ESZ__eulerian_cartesian", positive=True)
 
 DIRS = ("x", "y", "z")
 
@@ -112,6 +116,15 @@ def var(arg: Union[str, Sequence[str]]):
     code = _Context.current()
     if arg == "time":
         return TIME
+    if arg in ("element_size_Eulerian", "cartesian_element_size_Eulerian", "element_length_h"):
+        # pyoomph/expressions/generic.py:174-178; stabilisation terms (SUPG / PSPG, artificial diffusion) are built on them
+        if code.etype.elem_dim != 2 or code.nodal_dim != 2:
+            raise NotImplementedError("element sizes: two-dimensional bulk elements only")
+        if arg == "cartesian_element_size_Eulerian":
+            return ELEMSIZE_EUL_CART
+        return ELEMSIZE_EUL if arg == "element_size_Eulerian" else ELEMSIZE_EUL ** sp.Rational(1, code.etype.elem_dim)
+    if arg in ("element_size_Lagrangian", "cartesian_element_size_Lagrangian"):
+        raise NotImplementedError("Lagrangian element sizes are outside the GPU path")
     if arg == "normal":
         if code.etype.elem_dim >= code.nodal_dim and not code.etype.name.startswith("QuadFace"):
             raise RuntimeError("var(\"normal\") is defined on interface elements only")

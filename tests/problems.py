@@ -212,6 +212,16 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "right", "bottom", "top")]))
             pinned = {"velocity_x": wall, "velocity_y": wall, "pressure": np.array([0])}
             unsteady = kind == "ns_unsteady_hang"
+    elif kind in ("supg", "supg_axi"):
+        # element sizes (var("element_length_h"), "cartesian_element_size_Eulerian"): one number per element, the integral of the measure
+        # over all of its integration points (with 2 pi r when axisymmetric), in a streamline-upwind term
+        from pyoomph_b200.equations import StreamlineDiffusionAdvection
+        mesh = RectangularQuadMesh(N)
+        axi = kind == "supg_axi"
+        code = FiniteElementCode("Quad2dC2", StreamlineDiffusionAdvection(cartesian_size=axi), name="supgaxi" if axi else "supg",
+                                 coordinate_system="axisymmetric" if axi else "cartesian")
+        pinned = {"c": mesh.boundaries["left"]}
+        unsteady = True
     elif kind == "poisson":          # config 1
         mesh = RectangularQuadMesh(N)
         code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")

@@ -35,12 +35,15 @@ TRIANGLES = [("poisson_tri", 9, 0.0, False), ("poisson_tri", 8, 0.12, False), ("
 # ten-node tetrahedra (BulkElementTetra3dC2 = TElement<3,3>, TGauss<3,3> with its negative weight): Poisson, transient heat, 3D P2/P1 NS
 TETRAHEDRA = [("poisson_tet", 3, 0.0, False), ("poisson_tet", 3, 0.1, False), ("heat3d_tet", 3, 0.1, False), ("ns_tet", 2, 0.1, False)]
 
+# element sizes (one number per element from all of its integration points) in a streamline-upwind term; axisymmetric: the Cartesian size
+ELEMENT_SIZES = [("supg", 9, 0.0, False), ("supg", 8, 0.12, False), ("supg_axi", 7, 0.1, False)]
+
 VARIANTS = [("ns", 11, 0.12, False), ("ns_unsteady", 10, 0.1, True), ("heat3d", 3, 0.1, True), ("ale", 6, 0.08, True), ("poisson", 33, 0.15, True),
             ("ns_axi_swirl", 6, 0.1, True), ("ale_axi", 6, 0.08, True)]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,N,distortion,unstructured", [(k, n, 0.0, False) for k, n in CASES] + VARIANTS + TRIANGLES + TETRAHEDRA)
+@pytest.mark.parametrize("kind,N,distortion,unstructured", [(k, n, 0.0, False) for k, n in CASES] + VARIANTS + TRIANGLES + TETRAHEDRA + ELEMENT_SIZES)
 def test_residual_jacobian_mass_parity(kind, N, distortion, unstructured):
     pb = make_problem(kind, N, distortion=distortion, unstructured=unstructured)
     op = make_oracle(pb)

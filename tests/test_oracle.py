@@ -582,3 +582,57 @@ def test_bulk_face_elements_of_the_oracle():
     # the Jacobian couples the face to the interior nodes of its bulk element (normal derivative): more than the 3x3 face block
     assert np.count_nonzero(A) > 9 * im.n_elem
     op.close()
+
+
+def test_element_sizes_of_the_oracle():
+    """var("element_length_h") / "cartesian_element_size_Eulerian" (fill_shape_info_element_sizes, src/elements.cpp:3527-3568): on a uniform
+    N x N mesh the element length is 1/N, so the streamline-upwind residual equals the one written with that constant; on a distorted
+    mesh (axisymmetric: Cartesian size, the measure's 2 pi r not included) the analytic Jacobian agrees with finite differences."""
+    from problems import csr_to_sorted, make_oracle, make_problem
+    from pyoomph_b200.codegen import FiniteElementCode
+    from pyoomph_b200.equations import StreamlineDiffusionAdvection
+    import pyoomph_b200.expressions as ex_
+    N = 5
+    pb = make_problem("supg", N)
+
+    class _ConstH(StreamlineDiffusionAdvection):
+        def define_residuals(self):
+            real_var = ex_.var
+            try:
+                ex_.var = lambda a: (1.0 / N if a == "element_length_h" else real_var(a))
+                import pyoomph_b200.equations as eqm
+                saved = eqm.var
+                eqm.var = ex_.var
+                super().define_residuals()
+            finally:
+                ex_.var = real_var
+                eqm.var = saved
+    pbc = dict(pb, code=FiniteElementCode("Quad2dC2", _ConstH(), name="supgconst"))
+    a, b = make_oracle(pb), make_oracle(pbc)
+    ra, ma = a.assemble(flag=2)
+    rb, mb = b.assemble(flag=2)
+    assert np.abs(ra - rb).max() <= 1e-13 * np.abs(rb).max()
+    n = pb["dofmap"].n_dof
+    assert abs(csr_to_sorted(n, *ma[0]) - csr_to_sorted(n, *mb[0])).max() <= 1e-13 * abs(csr_to_sorted(n, *mb[0])).max()
+    a.close(); b.close()
+    for kind in ("supg", "supg_axi"):
+        pb = make_problem(kind, 4, distortion=0.12)
+        op = make_oracle(pb)
+        n = pb["dofmap"].n_dof
+        _, mats = op.assemble(flag=1)
+        A = csr_to_sorted(n, *mats[0]).toarray()
+        eq, eps = pb["dofmap"].node_eqn, 1e-6
+        for node in range(0, pb["mesh"].n_node, 4):
+            g = eq[node, 0]
+            if g < 0:
+                continue
+            v = pb["vals"][0].copy()
+            v[node, 0] += eps
+            op.update_values(0, v)
+            rp, _ = op.assemble(flag=0)
+            v[node, 0] -= 2 * eps
+            op.update_values(0, v)
+            rm, _ = op.assemble(flag=0)
+            op.update_values(0, pb["vals"][0])
+            assert np.abs((rp - rm) / (2 * eps) - A[:, g]).max() <= 1e-8 * np.abs(A).max()
+        op.close()
