@@ -401,6 +401,96 @@ def refine_quad_mesh(mesh: StructuredMesh, refine: np.ndarray) -> RefinedQuadMes
     return RefinedQuadMesh(2, elem_nodes, node_pos, node_lat, boundaries, "Quad2dC2", vertex, HangingNodes(hang_C2, hang_C1), np.array(parent, dtype=np.int64))
 
 
+def refine_brick_mesh(mesh: StructuredMesh, refine: np.ndarray) -> RefinedQuadMesh:
+    """One level of octree refinement of the flagged Q27 elements (RefineableQElement<3>: eight sons).  New nodes are placed by the father's
+    Q27 mapping.  A coarse FACE or EDGE that is shared by at least one refined and one unrefined element is constrained: the new nodes on
+    it hang on the coarse nodes of that entity -- the nine nodes of a face with the weights L_i(s_a) L_j(s_b), the three nodes of an edge
+    with L_i(s) (oomph-lib refineable_brick_element.cc, oc_hang_helper; zero weights dropped).  Only the C2 / position hang infos are
+    generated (element classes with C1 fields are refused by the equation numbering on these meshes)."""
+    if mesh.dim != 3 or mesh.element_type != "Brick3dC2":
+        raise NotImplementedError("octree refinement: Q27 meshes only")
+    refine = np.asarray(refine, dtype=bool)
+    Nx, Ny, Nz = mesh.N
+    assert refine.shape == (mesh.n_elem,)
+    rgrid = refine.reshape(Nx, Ny, Nz)
+    lat = mesh.node_lattice.astype(np.int64) * 2
+    key_of = {tuple(int(v) for v in lat[n]): n for n in range(mesh.n_node)}
+    pos = [mesh.node_pos[n].copy() for n in range(mesh.n_node)]
+    flat = [tuple(int(v) for v in lat[n]) for n in range(mesh.n_node)]
+    psi1 = {k: _lag3(0.5 * k - 1.0) for k in range(5)}
+    elems, parent = [], []
+    for e in range(mesh.n_elem):
+        en = mesh.elem_nodes[e]
+        if not refine[e]:
+            elems.append(en.copy())
+            parent.append(e)
+            continue
+        ex, ey, ez = e // (Ny * Nz), (e // Nz) % Ny, e % Nz
+        X = mesh.node_pos[en]                      # [27, 3], local index i + 3 j + 9 k
+        grid = np.empty((5, 5, 5), dtype=np.int64)
+        for fk in range(5):
+            for fj in range(5):
+                for fi in range(5):
+                    key = (4 * ex + fi, 4 * ey + fj, 4 * ez + fk)
+                    if key not in key_of:
+                        w = np.einsum("k,j,i->kji", psi1[fk], psi1[fj], psi1[fi]).ravel()
+                        key_of[key] = len(pos)
+                        pos.append(w @ X)
+                        flat.append(key)
+                    grid[fi, fj, fk] = key_of[key]
+        for c in range(2):
+            for b in range(2):
+                for a in range(2):
+                    elems.append(np.array([grid[2 * a + i, 2 * b + j, 2 * c + k] for k in range(3) for j in range(3) for i in range(3)], dtype=np.int32))
+                    parent.append(e)
+
+    def is_refined(cx, cy, cz):
+        return None if not (0 <= cx < Nx and 0 <= cy < Ny and 0 <= cz < Nz) else bool(rgrid[cx, cy, cz])
+    hang_C2 = {}
+    for key, n in key_of.items():
+        if all(k % 2 == 0 for k in key):
+            continue                                   # a node of the coarse level (vertex, mid-edge, mid-face, centre): never C2-hanging
+        on = [k % 4 == 0 for k in key]                 # lies on a coarse lattice plane in that direction
+        if sum(on) == 0:
+            continue                                   # interior of a coarse element
+        # the coarse elements sharing the entity (face: 2, edge: 4)
+        cells = [[]]
+        for d in range(3):
+            opts = [key[d] // 4 - 1, key[d] // 4] if on[d] else [key[d] // 4]
+            cells = [c + [o] for c in cells for o in opts]
+        states = [is_refined(*c) for c in cells]
+        if not (any(s_ is False for s_ in states) and any(s_ is True for s_ in states)):
+            continue
+        # masters: the coarse nodes of the entity; local coordinate of the node in every free direction
+        free = [d for d in range(3) if not on[d]]
+        base = [key[d] - (key[d] % 4) if not on[d] else key[d] for d in range(3)]
+        masters, weights = [], []
+        import itertools
+        for idx in itertools.product(range(3), repeat=len(free)):
+            mk = list(base)
+            wgt = 1.0
+            for d, i in zip(free, idx):
+                mk[d] = base[d] + 2 * i
+                wgt *= psi1[key[d] - base[d]][i]
+            if wgt != 0.0:
+                masters.append(key_of[tuple(mk)])
+                weights.append(wgt)
+        hang_C2[n] = (np.array(masters, dtype=np.int64), np.array(weights))
+    elem_nodes = np.ascontiguousarray(np.stack(elems), dtype=np.int32)
+    node_pos = np.ascontiguousarray(np.stack(pos), dtype=np.float64)
+    for n, (m, w) in hang_C2.items():
+        node_pos[n] = w @ node_pos[m]
+    node_lat = np.array(flat, dtype=np.int32)
+    vertex = np.zeros(node_pos.shape[0], dtype=bool)
+    vertex[elem_nodes[:, [0, 2, 6, 8, 18, 20, 24, 26]].ravel()] = True
+    names = [("left", "right"), ("bottom", "top"), ("back", "front")]
+    boundaries = {}
+    for d, nd in enumerate((Nx, Ny, Nz)):
+        boundaries[names[d][0]] = np.nonzero(node_lat[:, d] == 0)[0]
+        boundaries[names[d][1]] = np.nonzero(node_lat[:, d] == 4 * nd)[0]
+    return RefinedQuadMesh(3, elem_nodes, node_pos, node_lat, boundaries, "Brick3dC2", vertex, HangingNodes(hang_C2, {}), np.array(parent, dtype=np.int64))
+
+
 @dataclasses.dataclass
 class DofMap:
     node_eqn: np.ndarray             # [n_node, nval] int32, -1 pinned
@@ -425,6 +515,8 @@ def assign_equation_numbers(mesh: StructuredMesh, code: FiniteElementCode,
         if code.coordinates_as_dofs:
             raise NotImplementedError("hanging nodes on a moving mesh (hanging position dofs)")
         for f in code.nodal_fields():
+            if f.space == "C1" and mesh.dim == 3:
+                raise NotImplementedError("C1 fields on octree-refined meshes (only the C2 hang infos are generated in 3D)")
             hn = np.fromiter(hanging.of_space(f.space).keys(), dtype=np.int64)
             if hn.size:
                 free[hn, f.index] = False

@@ -212,6 +212,19 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "right", "bottom", "top")]))
             pinned = {"velocity_x": wall, "velocity_y": wall, "pressure": np.array([0])}
             unsteady = kind == "ns_unsteady_hang"
+    elif kind == "heat3d_hang":
+        # one level of octree refinement of some Q27 elements: hanging nodes on the faces AND edges between refined and unrefined elements
+        import pyoomph_b200.meshes as _mm
+        base = _mm.CuboidBrickMesh(N)
+        if distortion:
+            base = distort(base, distortion, seed)
+        flags = np.zeros((N, N, N), dtype=bool)
+        flags[N // 2, N // 2, N // 2] = flags[0, 0, 0] = flags[-1, -1, 0] = True
+        flags[N // 2, N // 2, min(N - 1, N // 2 + 1)] = True                       # two refined neighbours: a shared face without hanging nodes
+        mesh = _mm.refine_brick_mesh(base, flags.ravel())
+        code = FiniteElementCode("Brick3dC2", TransientHeatEquation(), name="heat3d")
+        pinned = {"u": mesh.boundaries["left"]}
+        unsteady = True
     elif kind in ("supg", "supg_axi"):
         # element sizes (var("element_length_h"), "cartesian_element_size_Eulerian"): one number per element, the integral of the measure
         # over all of its integration points (with 2 pi r when axisymmetric), in a streamline-upwind term

@@ -634,7 +634,8 @@ def test_interface_class_assembled_into_the_matrix_of_its_bulk_class(kind, N, di
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,N,distortion", [("poisson_hang", 8, 0.12), ("ns_hang", 6, 0.1), ("ns_unsteady_hang", 6, 0.08), ("ns_hang", 24, 0.05)])
+@pytest.mark.parametrize("kind,N,distortion", [("poisson_hang", 8, 0.12), ("ns_hang", 6, 0.1), ("ns_unsteady_hang", 6, 0.08), ("ns_hang", 24, 0.05),
+                                                ("heat3d_hang", 3, 0.08), ("heat3d_hang", 5, 0.0)])
 def test_hanging_nodes_parity(kind, N, distortion):
     """a14: a mesh with hanging nodes (one quadtree level).  Oracle: the reference's hang macros inside the element routine with its
     local numbering of the master values.  Product: the unchanged element kernel over virtual equations for the hanging values, then
@@ -662,7 +663,7 @@ def test_hanging_nodes_parity(kind, N, distortion):
         for vals, ref in zip((jac, mass), mats):
             err, missing = compare_matrix(csr_to_sorted(n, asm.indptr, asm.indices, vals), csr_to_sorted(n, *ref))
             assert missing == 0 and err <= TOL, (kind, rep, err, missing)
-    st = assert_csr_parity(asm.indptr, asm.indices, jac, mats[0], TOL, label="%s N=%d" % (kind, N), max_cancel_fraction=0.02)
+    st = assert_csr_parity(asm.indptr, asm.indices, jac, mats[0], TOL, label="%s N=%d" % (kind, N), max_cancel_fraction=0.02 if distortion > 0 else 0.30)
     _record(kind, N, distortion, False, st)
     # the device holds J (+) I over the extended equations: virtual rows / columns cleared, unit diagonal, zero residual
     r_ext, j_ext, _ = asm.fetch_extended(True, False)

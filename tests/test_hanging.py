@@ -45,7 +45,7 @@ def test_refined_mesh_is_conforming():
     assert mesh.n_elem == 36 + 3 * int((mesh.parent_element[1:] == mesh.parent_element[:-1]).sum() // 3)
 
 
-@pytest.mark.parametrize("kind,N,distortion", [("poisson_hang", 6, 0.12), ("ns_hang", 5, 0.1)])
+@pytest.mark.parametrize("kind,N,distortion", [("poisson_hang", 6, 0.12), ("ns_hang", 5, 0.1), ("heat3d_hang", 3, 0.08)])
 def test_oracle_jacobian_with_hanging_nodes_matches_finite_differences(kind, N, distortion):
     """the reference's own check (src/elements.cpp:5880 analytic vs FD) with the hanging values following their masters"""
     pb = make_problem(kind, N, distortion=distortion)
@@ -118,7 +118,7 @@ def test_patch_test_with_hanging_nodes():
     op.close()
 
 
-@pytest.mark.parametrize("kind,N,distortion", [("poisson_hang", 6, 0.12), ("ns_hang", 5, 0.1), ("ns_unsteady_hang", 5, 0.08)])
+@pytest.mark.parametrize("kind,N,distortion", [("poisson_hang", 6, 0.12), ("ns_hang", 5, 0.1), ("ns_unsteady_hang", 5, 0.08), ("heat3d_hang", 3, 0.08)])
 def test_global_reduction_equals_the_element_level_treatment(kind, N, distortion):
     """Route 1 (the reference's): hang macros inside the element routine.  Route 2 (the product's): virtual equations for the hanging
     values, the plain element routine, then P^T J_ext P -- by scipy and by the reduction lists the device kernels run."""
@@ -207,3 +207,32 @@ def test_host_side_of_the_hanging_node_assembly():
     _, missing = compare_matrix(ones, csr_to_sorted(n, *mats[0]))
     assert missing == 0
     asm.close()
+
+
+def test_octree_refinement_is_conforming():
+    """3D: faces AND edges between refined and unrefined elements are constrained (an edge is shared by up to four elements); masters never
+    hang themselves; weights are the tensor products of the quadratic 1D weights with the zeros dropped (3 masters on edges and face
+    mid-lines, 9 inside faces); hanging nodes lie on the coarse entity's surface; the shared face of two refined neighbours has none."""
+    pb = make_problem("heat3d_hang", 3, distortion=0.08)
+    mesh = pb["mesh"]
+    h = mesh.hanging.C2
+    assert len(h) > 100 and not mesh.hanging.C1
+    masters_all = set(int(x) for m, _ in h.values() for x in m)
+    sizes = set()
+    for n, (m, w) in h.items():
+        assert abs(w.sum() - 1.0) < 1e-14 and n not in masters_all
+        assert np.allclose(mesh.node_pos[n], w @ mesh.node_pos[m], atol=1e-15)
+        sizes.add(len(m))
+    assert sizes == {3, 9}
+    assert np.all(pb["dofmap"].node_eqn[list(h), 0] < 0)
+    # the patch test in 3D: constants are in the kernel of the stiffness part (J - weight * M) of every row
+    from pyoomph_b200.meshes import assign_equation_numbers
+    pb["dofmap"] = assign_equation_numbers(mesh, pb["code"], {}, None)
+    op = make_oracle(pb)
+    n = pb["dofmap"].n_dof
+    _, mats = op.assemble(flag=2)
+    J, M = csr_to_sorted(n, *mats[0]), csr_to_sorted(n, *mats[1])
+    one = np.ones(n)
+    ratio = (J @ one) / (M @ one)                   # J 1 = w0 M 1 (the time weight) when K 1 = 0
+    assert np.abs(ratio - ratio[0]).max() < 1e-9 * abs(ratio[0])
+    op.close()
