@@ -452,6 +452,16 @@ class B200Assembly(CustomAssemblyBase):
         n = self.n_dof
         return csr_matrix((mass, self.indices, self.indptr), shape=(n, n)), csr_matrix((jac, self.indices, self.indptr), shape=(n, n))
 
+    def integral_gradient(self, name: str) -> np.ndarray:
+        """c_j = d(integral expression `name`)/dU_j at the current state: the residual vector of the contribution "d_integral_<name>"
+        (registered with ``add_integral_function(..., with_gradient=True)``): the dense row of a global constraint in bordered form"""
+        rn = self.code.INTEGRAL_GRADIENT_PREFIX + name
+        if rn not in self.residual_names:
+            raise RuntimeError("integral expression '%s' was registered without its gradient" % name)
+        self.assemble(flag=0, residual=rn)
+        r, _, _ = self.fetch(False, False)
+        return r
+
     def assemble_azimuthal_eigenproblem_matrices(self, m: float, sigma_r: float = 0.0, residual: str = ""):
         """Complex (M, J - sigma_r M) of the azimuthal mode m about the current axisymmetric base state: two flag-2 launches (real and
         imaginary contribution, pyoomph/generic/problem.py:4543-4558 and the normal-mode eigensolve of problem.py) combined as

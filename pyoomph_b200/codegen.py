@@ -246,6 +246,29 @@ class FiniteElementCode:
     def integral_expression_names(self) -> List[str]:
         return list(self.integral_expressions.keys())
 
+    INTEGRAL_GRADIENT_PREFIX = "d_integral_"
+
+    def add_integral_gradient(self, name: str):
+        """Register the residual contribution  "d_integral_<name>":  c_j = d/dU_j (integral expression <name>)  -- the Gateaux derivative
+        of the integrand in the direction of the test functions.  Its residual vector (flag 0) is the dense ROW a global constraint
+        g(U) = integral - target = 0 adds to the system, its Jacobian (flag 1) the constraint's second derivative, and the dense COLUMN of
+        the multiplier is a parameter derivative dR/d(lambda) -- the bordered form of pyoomph's GlobalLagrangeMultiplier
+        (pyoomph/generic/codegen.py:2927; SURVEY 8e: such rows are not sharded, their vectors are reduced over the ranks).  Fixed meshes,
+        integrands without time derivatives."""
+        if self.coordinates_as_dofs:
+            raise NotImplementedError("gradient of an integral expression on a moving mesh")
+        I = self.integral_expressions[name]
+        eps = sp.Symbol("EPS__gateaux", real=True)
+        repl = {}
+        for f in self.nodal_fields():
+            F = sp.Function("F__" + f.name, real=True)(*ex._args(self.nodal_dim))
+            T = sp.Function("T__" + f.name, real=True)(*ex._args(self.nodal_dim))
+            repl[F] = F + eps * T
+        if any(isinstance(d, sp.Derivative) and ex.TIME in [v for v, _ in d.variable_count] for d in I.atoms(sp.Derivative)):
+            raise NotImplementedError("gradient of an integral expression with time derivatives")
+        g = sp.diff(I.subs(repl).doit(), eps).subs(eps, 0).doit()
+        self.residuals[self.INTEGRAL_GRADIENT_PREFIX + name] = sp.expand(g)
+
     # -- local / extremum expressions and Z2 fluxes (src/codegen.cpp:4366-4453; pyoomph/generic/codegen.py:1213, :2126) -----------------
     def _register_components(self, dest: Dict[str, sp.Expr], name: str, expr):
         if isinstance(expr, sp.MatrixBase):
@@ -775,9 +798,12 @@ class Equations:
         """integral / local expressions (pyoomph/generic/codegen.py Equations.define_additional_functions)"""
         pass
 
-    def add_integral_function(self, name: str, expr):
-        """pyoomph/generic/codegen.py:1251: the integrand carries its own measure (multiply by ``self.get_dx()``)"""
+    def add_integral_function(self, name: str, expr, with_gradient: bool = False):
+        """pyoomph/generic/codegen.py:1251: the integrand carries its own measure (multiply by ``self.get_dx()``); with_gradient also
+        registers the residual contribution "d_integral_<name>" (FiniteElementCode.add_integral_gradient)"""
         self._code.add_integral_function(name, expr)
+        if with_gradient:
+            self._code.add_integral_gradient(name)
 
     def add_local_function(self, name: str, expr):
         """pyoomph/generic/codegen.py:1213: quantity evaluated node-wise on output"""

@@ -135,16 +135,16 @@ class IntegralObservables(Equations):
     (pyoomph/equations/generic.py:684-699): every integrand is multiplied by the measure of the coordinate system (or of
     ``_coordinate_system``; Lagrangian if ``_lagrangian``) and registered with ``add_integral_function``."""
 
-    def __init__(self, _coordinate_system=None, _lagrangian: bool = False, **integral_observables):
+    def __init__(self, _coordinate_system=None, _lagrangian: bool = False, _with_gradients: bool = False, **integral_observables):
         super().__init__()
-        self._coordinate_system, self._lagrangian = _coordinate_system, _lagrangian
+        self._coordinate_system, self._lagrangian, self._with_gradients = _coordinate_system, _lagrangian, _with_gradients
         self.integral_observables = dict(integral_observables)
 
     def define_additional_functions(self):
         dx = self.get_dx(lagrangian=self._lagrangian, coordsys=self._coordinate_system)
         for k, v in self.integral_observables.items():
             v = v() if callable(v) else v
-            self.add_integral_function(k, v * dx)
+            self.add_integral_function(k, v * dx, with_gradient=self._with_gradients)
 
 
 class LocalExpressions(Equations):

@@ -225,6 +225,19 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
         code = FiniteElementCode("Brick3dC2", TransientHeatEquation(), name="heat3d")
         pinned = {"u": mesh.boundaries["left"]}
         unsteady = True
+    elif kind == "ns_constraint":
+        # integral expressions WITH their gradients with respect to the dofs (the dense rows of global constraints in bordered form):
+        # mean pressure, kinetic energy, flux through the domain
+        from pyoomph_b200.equations import IntegralObservables
+        from pyoomph_b200.expressions import dot, grad, var
+        mesh = RectangularQuadMesh(N)
+        obs = IntegralObservables(_with_gradients=True, pressure_integral=lambda: var("pressure"),
+                                  kinetic_energy=lambda: dot(var("velocity"), var("velocity")) / 2,
+                                  enstrophy=lambda: (grad(var("velocity_y"))[0] - grad(var("velocity_x"))[1]) ** 2)
+        code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + obs, name="nsconstraint")
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
+        pinned = {"velocity_x": wall, "velocity_y": wall}
+        unsteady = False
     elif kind in ("supg", "supg_axi"):
         # element sizes (var("element_length_h"), "cartesian_element_size_Eulerian"): one number per element, the integral of the measure
         # over all of its integration points (with 2 pi r when axisymmetric), in a streamline-upwind term

@@ -893,3 +893,49 @@ def test_newton_iterations_of_the_coupled_free_surface_problem():
     for o in (ob, oi):
         o.close()
     bulk.close()
+
+
+@pytest.mark.gpu
+def test_integral_gradients_for_global_constraints():
+    """Dense rows of global constraints in bordered form (pyoomph's GlobalLagrangeMultiplier): c = d(integral expression)/dU as
+    the residual vector of an automatically generated contribution, its second derivative as that contribution's Jacobian; against the
+    oracle's routine and against central differences of the oracle's integral values."""
+    pb = make_problem("ns_constraint", 7, distortion=0.1)
+    asm = make_gpu(pb)
+    op = make_oracle(pb)
+    n = pb["dofmap"].n_dof
+    eq = pb["dofmap"].node_eqn
+    names = pb["code"].residual_names()
+    vals_gpu = asm.evaluate_integral_expressions()
+    vals_ref = op.evaluate_integral_expressions()
+    for iname in pb["code"].integral_expression_names():
+        assert abs(vals_gpu[iname] - vals_ref[iname]) <= TOL * abs(vals_ref[iname])
+        which = names.index("d_integral_" + iname)
+        c = asm.integral_gradient(iname)
+        c_ref, mats = op.assemble(which=which, flag=1)
+        assert np.abs(c - c_ref).max() <= TOL * np.abs(c_ref).max()
+        asm.assemble(flag=1, residual="d_integral_" + iname)
+        _, H, _ = asm.fetch(True, False)
+        B = csr_to_sorted(n, *mats[0])
+        if abs(B).max() > 0:
+            err, missing = compare_matrix(csr_to_sorted(n, asm.indptr, asm.indices, H), B)
+            assert missing == 0 and err <= TOL
+        else:
+            assert np.abs(H).max() == 0.0                       # a linear functional (the pressure integral) has no second derivative
+        eps = 1e-6
+        for node in range(0, pb["mesh"].n_node, 23):
+            for f in range(eq.shape[1]):
+                g = eq[node, f]
+                if g < 0:
+                    continue
+                v = pb["vals"][0].copy()
+                v[node, f] += eps
+                op.update_values(0, v)
+                ip = op.evaluate_integral_expressions()[iname]
+                v[node, f] -= 2 * eps
+                op.update_values(0, v)
+                im = op.evaluate_integral_expressions()[iname]
+                op.update_values(0, pb["vals"][0])
+                assert abs((ip - im) / (2 * eps) - c[g]) <= 1e-7 * max(np.abs(c).max(), 1e-300)
+    op.close()
+    asm.close()

@@ -636,3 +636,38 @@ def test_element_sizes_of_the_oracle():
             op.update_values(0, pb["vals"][0])
             assert np.abs((rp - rm) / (2 * eps) - A[:, g]).max() <= 1e-8 * np.abs(A).max()
         op.close()
+
+
+def test_integral_gradient_contributions_match_finite_differences_of_the_integrals():
+    """add_integral_function(..., with_gradient=True): the residual vector of "d_integral_<name>" is d(integral)/dU (checked against
+    central differences of EvalIntegralExpression), a linear functional has a vanishing second derivative, a quadratic one a symmetric one"""
+    from problems import csr_to_sorted, make_oracle, make_problem
+    pb = make_problem("ns_constraint", 4, distortion=0.1)
+    code = pb["code"]
+    assert code.residual_names() == [""] + ["d_integral_" + k for k in code.integral_expression_names()]
+    op = make_oracle(pb)
+    n, eq = pb["dofmap"].n_dof, pb["dofmap"].node_eqn
+    for iname in code.integral_expression_names():
+        which = code.residual_names().index("d_integral_" + iname)
+        c, mats = op.assemble(which=which, flag=1)
+        H = csr_to_sorted(n, *mats[0])
+        if iname == "pressure_integral":
+            assert H.nnz == 0 or abs(H).max() == 0.0
+        else:
+            assert abs(H - H.T).max() <= 1e-13 * abs(H).max()
+        eps = 1e-6
+        for node in range(0, pb["mesh"].n_node, 7):
+            for f in range(eq.shape[1]):
+                g = eq[node, f]
+                if g < 0:
+                    continue
+                v = pb["vals"][0].copy()
+                v[node, f] += eps
+                op.update_values(0, v)
+                ip = op.evaluate_integral_expressions()[iname]
+                v[node, f] -= 2 * eps
+                op.update_values(0, v)
+                im = op.evaluate_integral_expressions()[iname]
+                op.update_values(0, pb["vals"][0])
+                assert abs((ip - im) / (2 * eps) - c[g]) <= 1e-8 * np.abs(c).max()
+    op.close()
