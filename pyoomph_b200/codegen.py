@@ -683,8 +683,8 @@ class FiniteElementCode:
         key = resname + ("|hessianT" if transposed else "|hessian")
         if key in self._forms:
             return self._forms[key]
-        if self.coordinates_as_dofs and not transposed:
-            hf = self._hessian_form_moving_mesh(resname, key)
+        if self.coordinates_as_dofs:
+            hf = self._hessian_form_moving_mesh(resname, key, transposed)
             self._forms[key] = hf
             return hf
         if transposed:
@@ -715,22 +715,25 @@ class FiniteElementCode:
         self._forms[key] = hf
         return hf
 
-    def _hessian_form_moving_mesh(self, resname: str, key: str) -> ResidualForm:
+    def _hessian_form_moving_mesh(self, resname: str, key: str, transposed: bool = False) -> ResidualForm:
         """d((J.Y))/dU and d((M.Y))/dU when the nodal positions are unknowns (the reference's second-order tensors d2_dx2_shape_dcoord,
         int_pt_weights_d2_coords, src/elements.cpp:3163-3217, src/codegen.cpp:1500-1881).  (A.Y)_i = sum_s T_s[l_i] sum_(G,a) C_{s,(G,a)} Yhat_{G,a}
         is itself a weak form that is linear in the test functions, with Y interpolated like the unknowns (values, gradients, and the
         POSITION columns of A contracted with the position part of Y).  Its derivative with respect to every unknown -- fields and
         positions, through the measure, the Eulerian gradients of fields, of Y and of the test functions, and the radius of an
-        axisymmetric system -- is what `_coefficient_form` computes for any such form: the first-order identities applied once more."""
+        axisymmetric system -- is what `_coefficient_form` computes for any such form: the first-order identities applied once more.
+        Transposed (flags 4 / 5): (A^T.Y)_i = sum_(s,G,a) S_a[l_i] C_{s,(G,a)} Yhat_{F_s,b_s} -- the former column (G, a) is the test slot, Y is
+        interpolated like the tested field with the slot's derivative."""
         form = self.derive(resname)
 
         def contracted(coefs) -> sp.Expr:
             E = sp.Integer(0)
             for (si, G, a), c in coefs.items():
-                yf = "Y__" + G
+                yfield, yderiv, slot = (form.slots[si].field, form.slots[si].deriv, TestSlot(G, a)) if transposed else (G, a, form.slots[si])
+                yf = "Y__" + yfield
                 if yf not in self.fields:
-                    self.fields[yf] = Field(yf, self.fields[G].space, -1, aux_of=G)
-                E = E + self._test_atom(form.slots[si]) * c * self._atom(AtomInfo(yf, 0, "", a, 0))
+                    self.fields[yf] = Field(yf, self.fields[yfield].space, -1, aux_of=yfield)
+                E = E + self._test_atom(slot) * c * self._atom(AtomInfo(yf, 0, "", yderiv, 0))
             return E
         fJ = self._coefficient_form(contracted(form.J), key + "|J")
         slots = list(fJ.slots)

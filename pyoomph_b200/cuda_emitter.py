@@ -275,9 +275,8 @@ class CudaEmitter:
         if self.hessian:
             for i, rn in enumerate(code.residual_names()):
                 self.hroutines.append(RoutinePlan("h%d" % i, code.hessian_form(rn), i, -1))
-                if not code.coordinates_as_dofs:
-                    # transposed contraction (flags 4 / 5 of HessianVectorProduct, src/jitbridge.h:637-691): plugin query kind 3
-                    self.hroutines.append(RoutinePlan("ht%d" % i, code.hessian_form(rn, transposed=True), i, -1))
+                # transposed contraction (flags 4 / 5 of HessianVectorProduct, src/jitbridge.h:637-691): plugin query kind 3
+                self.hroutines.append(RoutinePlan("ht%d" % i, code.hessian_form(rn, transposed=True), i, -1))
         self.T_val = code.history_levels()
         self.T_pos = self.T_val if code.coordinates_as_dofs else 1
         self._plan_groups()

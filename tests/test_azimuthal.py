@@ -62,3 +62,23 @@ def test_navier_stokes_with_swirl_mode_zero_is_the_axisymmetric_operator():
     # Hessian routines of the contributions exist (the azimuthal Hopf / fold trackers contract them with the eigenvector)
     h = code.hessian_form(cs.real_contribution_name)
     assert len(h.J) > 0
+
+
+def test_generic_second_derivative_route_reproduces_the_fixed_mesh_hessian_forms():
+    """`_hessian_form_moving_mesh` (the contracted form (A.Y) / (A^T.Y) differentiated once more by `_coefficient_form`) against the
+    dedicated fixed-mesh derivations `derive_hessian` / `derive_hessian_transposed`: identical coefficients in every field column"""
+    from problems import make_problem
+    c = make_problem("ns_unsteady", 2)["code"]
+    for tr in (False, True):
+        a = c.hessian_form("", transposed=tr)
+        c.coordinates_as_dofs = True
+        try:
+            b = c._hessian_form_moving_mesh("", "|generic%d" % tr, tr)
+        finally:
+            c.coordinates_as_dofs = False
+        for A, B in ((a.J, b.J), (a.M, b.M)):
+            da = {(a.slots[k[0]], k[1], k[2]): v for k, v in A.items()}
+            db = {(b.slots[k[0]], k[1], k[2]): v for k, v in B.items() if not k[1].startswith("coordinate")}
+            assert set(da) == set(db) and len(da) == 8 * (A is a.J)
+            for k in da:
+                assert sp.simplify(da[k] - db[k]) == 0, k

@@ -785,10 +785,17 @@ def test_moving_mesh_hessian_vector_products(kind, N, distortion):
     HJ, HM = asm.assemble_hessian(Y[None, :], flag=2)
     A = csr_matrix((HJ[0], asm.indices, asm.indptr), shape=(n, n)).toarray()
     AM = csr_matrix((HM[0], asm.indices, asm.indptr), shape=(n, n)).toarray()
+    TJ, TM = asm.assemble_hessian(Y[None, :], flag=2, transposed=True)            # flags 4 / 5: d(J^T.Y)/dU, d(M^T.Y)/dU
+    AT = csr_matrix((TJ[0], asm.indices, asm.indptr), shape=(n, n)).toarray()
+    ATM = csr_matrix((TM[0], asm.indices, asm.indptr), shape=(n, n)).toarray()
+    refT, refTM = np.zeros((n, n)), np.zeros((n, n))
+    cols_T = {}
 
     def JY_MY():
         _, mats = op.assemble(flag=2)
-        return csr_to_sorted(n, *mats[0]) @ Y, csr_to_sorted(n, *mats[1]) @ Y
+        Jm, Mm = csr_to_sorted(n, *mats[0]), csr_to_sorted(n, *mats[1])
+        cols_T["J"], cols_T["M"] = Jm.T @ Y, Mm.T @ Y
+        return Jm @ Y, Mm @ Y
     eps = 1e-6
     ref, refM = np.zeros((n, n)), np.zeros((n, n))
     vals0, pos0 = pb["vals"][0], pb["pos_hist"][0]
@@ -801,10 +808,12 @@ def test_moving_mesh_hessian_vector_products(kind, N, distortion):
             v[node, f] += eps
             op.update_values(0, v)
             jp, mp = JY_MY()
+            tp = dict(cols_T)
             v[node, f] -= 2 * eps
             op.update_values(0, v)
             jm, mm = JY_MY()
             ref[:, g], refM[:, g] = (jp - jm) / (2 * eps), (mp - mm) / (2 * eps)
+            refT[:, g], refTM[:, g] = (tp["J"] - cols_T["J"]) / (2 * eps), (tp["M"] - cols_T["M"]) / (2 * eps)
         op.update_values(0, vals0)
         for d in range(pos0.shape[1]):
             g = pb["dofmap"].pos_eqn[node, d]
@@ -814,15 +823,19 @@ def test_moving_mesh_hessian_vector_products(kind, N, distortion):
             x[node, d] += eps
             op.update_values(0, None, x)
             jp, mp = JY_MY()
+            tp = dict(cols_T)
             x[node, d] -= 2 * eps
             op.update_values(0, None, x)
             jm, mm = JY_MY()
             ref[:, g], refM[:, g] = (jp - jm) / (2 * eps), (mp - mm) / (2 * eps)
+            refT[:, g], refTM[:, g] = (tp["J"] - cols_T["J"]) / (2 * eps), (tp["M"] - cols_T["M"]) / (2 * eps)
         op.update_values(0, None, pos0)
     pos_cols = pb["dofmap"].pos_eqn[pb["dofmap"].pos_eqn >= 0]
     assert np.abs(ref[:, pos_cols]).max() > 1e-3 * np.abs(ref).max()          # the position columns are not a side show
     assert np.abs(A - ref).max() <= 2e-6 * np.abs(ref).max(), (np.abs(A - ref).max(), np.abs(ref).max())
     assert np.abs(AM - refM).max() <= 2e-6 * max(np.abs(refM).max(), 1e-300), (np.abs(AM - refM).max(), np.abs(refM).max())
+    assert np.abs(AT - refT).max() <= 2e-6 * np.abs(refT).max(), (np.abs(AT - refT).max(), np.abs(refT).max())
+    assert np.abs(ATM - refTM).max() <= 2e-6 * max(np.abs(refTM).max(), 1e-300), (np.abs(ATM - refTM).max(), np.abs(refTM).max())
     op.close()
     asm.close()
 
