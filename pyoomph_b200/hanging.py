@@ -141,26 +141,6 @@ def constraint_lists(indptr: np.ndarray, indices: np.ndarray, ext: ExtendedNumbe
                 clear_pos=i32(src), diag_pos=i32(diag_pos), virt_rows=i32(virt_rows))
 
 
-def apply_constraints_numpy(lists, jac: np.ndarray, res: Optional[np.ndarray], diag_value: float = 1.0):
-    """what the reduction kernels do, in numpy (the CPU tests compare it with scipy's P^T J P; the product never calls it)"""
-    jac = jac.copy()
-    for k, t in enumerate(lists["target_pos"]):
-        a, b = lists["src_start"][k], lists["src_start"][k + 1]
-        s = 0.0
-        for i in range(a, b):
-            s += lists["src_w"][i] * jac[lists["src_pos"][i]]
-        jac[t] += s
-    jac[lists["clear_pos"]] = 0.0
-    jac[lists["diag_pos"]] = diag_value
-    if res is not None:
-        res = res.copy()
-        for k, r in enumerate(lists["res_row"]):
-            a, b = lists["res_start"][k], lists["res_start"][k + 1]
-            res[r] += float(np.dot(lists["res_w"][a:b], res[lists["res_src"][a:b]]))
-        res[lists["virt_rows"]] = 0.0
-    return jac, res
-
-
 def extra_pattern_for_constraints(code: FiniteElementCode, mesh, ext: ExtendedNumbering):
     """(rows, cols) of the entries of P^T S P (S = the element pattern of the extended system) that S does not hold: the master-master
     couplings the hanging contributions are redirected to"""

@@ -6,7 +6,28 @@ import numpy as np
 import pytest
 
 from problems import compare_matrix, csr_to_sorted, make_oracle, make_problem
-from pyoomph_b200.hanging import (apply_constraints_numpy, constraint_lists, extend_numbering, extra_pattern_for_constraints)
+from pyoomph_b200.hanging import constraint_lists, extend_numbering, extra_pattern_for_constraints
+
+
+def apply_constraints_numpy(lists, jac: np.ndarray, res: np.ndarray, diag_value: float = 1.0):
+    """what the reduction kernels of pb2_core.cu do with the lists, restated in numpy (test infrastructure: compared with scipy's P^T J P)"""
+    jac = jac.copy()
+    for k, t in enumerate(lists["target_pos"]):
+        a, b = lists["src_start"][k], lists["src_start"][k + 1]
+        s = 0.0
+        for i in range(a, b):
+            s += lists["src_w"][i] * jac[lists["src_pos"][i]]
+        jac[t] += s
+    jac[lists["clear_pos"]] = 0.0
+    jac[lists["diag_pos"]] = diag_value
+    if res is not None:
+        res = res.copy()
+        for k, r in enumerate(lists["res_row"]):
+            a, b = lists["res_start"][k], lists["res_start"][k + 1]
+            res[r] += float(np.dot(lists["res_w"][a:b], res[lists["res_src"][a:b]]))
+        res[lists["virt_rows"]] = 0.0
+    return jac, res
+
 
 
 def _vals_from_dofs(pb, u):
