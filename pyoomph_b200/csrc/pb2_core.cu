@@ -925,6 +925,13 @@ static int create_impl(pb2_class *cls, int device, const pb2_mesh_desc *m, pb2_p
 extern "C" void pb2_problem_free(pb2_problem *p)
 {
   if (!p) return;
+  if (p->n_children > 0)
+  {
+    // child problems alias this problem's device buffers: releasing it now would leave them dangling.  Keep it (the caller releases the
+    // children first and calls again); pb2_last_error says why nothing happened.
+    fail("pb2_problem_free: " + std::to_string(p->n_children) + " child problem(s) still alive; release them first");
+    return;
+  }
   if (p->parent) p->parent->n_children--; // children are released before their parent
   if (p->device < 0)
   {

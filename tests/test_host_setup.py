@@ -124,3 +124,15 @@ def test_child_problem_maps_point_into_the_parents_pattern(kind, N):
     child.close()
     bulk.close()
     far.close()
+
+
+def test_parent_is_not_released_under_its_children():
+    """pb2_problem_free on a parent with live children does nothing (the children alias its buffers) and says so"""
+    pb = make_problem("robin_if", 4, distortion=0.1)
+    bulk = B200Assembly(pb["bulk_code"], pb["bulk_mesh"], pb["dofmap"], name=pb["bulk_code"].name, device=-1)
+    child = B200Assembly(pb["code"], pb["mesh"], pb["dofmap"], name=pb["code"].name, parent=bulk)
+    bulk.lib.pb2_problem_free(bulk.prob)                    # refused
+    assert b"child problem" in bulk.lib.pb2_last_error()
+    assert np.array_equal(child.indptr, bulk.indptr)         # still usable
+    bulk.close()                                             # releases the child first, then itself
+    assert child.prob is None and bulk.prob is None
