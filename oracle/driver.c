@@ -271,9 +271,9 @@ typedef struct
   int eqn_of_local[MAXN * (MAXD + 16)];
   JITHangInfo_t nohang[MAXN];
 #define MAXM 9
-  JITHangInfo_t hang_C2[MAXN], hang_C1[8];
-  JITHangInfoEntry_t hang_entries_C2[MAXN][MAXM], hang_entries_C1[8][MAXM];
-  int hang_eqn_C2[MAXN][MAXM][32], hang_eqn_C1[8][MAXM][32];
+  JITHangInfo_t hang_C2[MAXN], hang_C1[8], hang_Pos[MAXN];
+  JITHangInfoEntry_t hang_entries_C2[MAXN][MAXM], hang_entries_C1[8][MAXM], hang_entries_Pos[MAXN][MAXM];
+  int hang_eqn_C2[MAXN][MAXM][32], hang_eqn_C1[8][MAXM][32], hang_eqn_Pos[MAXN][MAXM][MAXD];
   /* backing storage */
   double **coord_ptr[MAXN], **data_ptr[MAXN];
   double *coord_slots[MAXN][2 * MAXD], *data_slots[MAXN][32];
@@ -656,13 +656,47 @@ static void bind_element(ThreadState *ts, int e)
   si->hanginfo_Pos = ts->nohang;
   if (o->hang_start[0] || o->hang_start[1])
   {
-    if (o->pos_eqn)
-    {
-      fprintf(stderr, "oracle: hanging nodes on a moving mesh are not restated\n");
-      abort();
-    }
     si->hanginfo_C2 = ts->hang_C2;
     si->hanginfo_C1 = ts->hang_C1;
+    if (o->pos_eqn)
+    {
+      /* moving mesh: the POSITIONS of a (geometrically) hanging node hang on the positions of its masters (hanginfo_Pos,
+       * src/elements.cpp:820-862; local_position_hang_eqn of oomph-lib's RefineableSolidElement) */
+      si->hanginfo_Pos = ts->hang_Pos;
+      for (int l = 0; l < nn; l++)
+      {
+        const int node = en[l];
+        JITHangInfo_t *hi = &ts->hang_Pos[l];
+        JITHangInfoEntry_t *ent = ts->hang_entries_Pos[l];
+        hi->nummaster = 0;
+        hi->masters = ent;
+        if (!o->hang_start[0]) continue;
+        const int h0 = o->hang_start[0][node], h1 = o->hang_start[0][node + 1];
+        if (h1 == h0) continue;
+        hi->nummaster = h1 - h0;
+        for (int m = 0; m < h1 - h0; m++)
+        {
+          ent[m].weight = o->hang_weight[0][h0 + m];
+          ent[m].local_eqn = ts->hang_eqn_Pos[l][m];
+          for (int d = 0; d < dim; d++)
+          {
+            const int g = o->pos_eqn[(size_t)o->hang_master[0][h0 + m] * dim + d];
+            int loc = -1;
+            if (g >= 0)
+            {
+              for (int k = 0; k < nloc; k++)
+                if (ts->eqn_of_local[k] == g) loc = k;
+              if (loc < 0)
+              {
+                loc = nloc;
+                ts->eqn_of_local[nloc++] = g;
+              }
+            }
+            ent[m].local_eqn[d] = loc;
+          }
+        }
+      }
+    }
     for (int sp = 0; sp < 2; sp++)
     {
       const int nl = sp == 0 ? nn : o->et.nnode_C1, f0 = sp == 0 ? 0 : nC2, f1 = sp == 0 ? nC2 : nC2 + nC1;

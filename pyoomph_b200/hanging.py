@@ -51,34 +51,44 @@ class ExtendedNumbering:
 def extend_numbering(code: FiniteElementCode, dofmap: DofMap, hanging: HangingNodes) -> ExtendedNumbering:
     """virtual equations n_dof, n_dof+1, ... for the hanging values (node order, then value index); values whose masters are all pinned
     stay without an equation (they contribute to nothing)"""
-    if dofmap.pos_eqn is not None:
-        raise NotImplementedError("hanging nodes on a moving mesh (hanging position dofs)")
     node_eqn = dofmap.node_eqn.copy()
+    pos_eqn = None if dofmap.pos_eqn is None else dofmap.pos_eqn.copy()
     n = dofmap.n_dof
+    nval = node_eqn.shape[1]
     todo = []
     for f in code.nodal_fields():
         for node, (masters, weights) in hanging.of_space(f.space).items():
             todo.append((int(node), f.index, masters, weights))
+    if pos_eqn is not None:
+        # moving mesh: the position dofs of a geometrically hanging node (C2 hang info) hang on its masters' position dofs; they are
+        # addressed here as value indices nval, nval + 1, ... of the node
+        for node, (masters, weights) in hanging.C2.items():
+            for d in range(pos_eqn.shape[1]):
+                todo.append((int(node), nval + d, masters, weights))
     todo.sort(key=lambda t: (t[0], t[1]))
+    all_eqn = node_eqn if pos_eqn is None else np.concatenate([dofmap.node_eqn, dofmap.pos_eqn], axis=1)
+    ext_eqn = all_eqn.copy()
     hang_by_field = {}
     for node, fi, _, _ in todo:
         hang_by_field.setdefault(fi, set()).add(node)
     pr, pc, pv = [], [], []
     nxt = n
     for node, fi, masters, weights in todo:
-        assert node_eqn[node, fi] < 0, "a hanging value must not have an equation of its own"
+        assert all_eqn[node, fi] < 0, "a hanging value must not have an equation of its own"
         if any(int(m) in hang_by_field[fi] for m in masters):
             raise NotImplementedError("masters that hang themselves (more than one refinement level across an edge)")
-        meq = dofmap.node_eqn[np.asarray(masters), fi]
+        meq = all_eqn[np.asarray(masters), fi]
         live = meq >= 0
         if not live.any():
             continue
-        node_eqn[node, fi] = nxt
+        ext_eqn[node, fi] = nxt
         pr += [nxt] * int(live.sum())
         pc += [int(g) for g in meq[live]]
         pv += [float(w) for w in np.asarray(weights)[live]]
         nxt += 1
-    return ExtendedNumbering(DofMap(node_eqn, None, nxt), n, np.array(pr, dtype=np.int64), np.array(pc, dtype=np.int64), np.array(pv))
+    node_eqn = np.ascontiguousarray(ext_eqn[:, :nval])
+    pos_ext = None if pos_eqn is None else np.ascontiguousarray(ext_eqn[:, nval:])
+    return ExtendedNumbering(DofMap(node_eqn, pos_ext, nxt), n, np.array(pr, dtype=np.int64), np.array(pc, dtype=np.int64), np.array(pv))
 
 
 def constraint_lists(indptr: np.ndarray, indices: np.ndarray, ext: ExtendedNumbering):
@@ -171,6 +181,7 @@ class HangingNodeAssembly:
         self.code, self.mesh, self.dofmap, self.hanging = code, mesh, dofmap, hanging
         self.ext = extend_numbering(code, dofmap, hanging)
         self._pinned_offset = {}
+        self._pinned_pos_offset = {}
         self.P = self.ext.prolongation()
         extra = extra_pattern_for_constraints(code, mesh, self.ext)
         if "patch_hint" not in kw and not hasattr(mesh, "element_patches"):
@@ -217,10 +228,36 @@ class HangingNodeAssembly:
                     off[g] = float(np.dot(np.asarray(w)[pinned], v[np.asarray(m)[pinned], f.index]))
         self._pinned_offset[t] = off
 
+    def set_nodal_positions(self, t: int, pos: np.ndarray):
+        """positions of level t; (geometrically) hanging nodes are placed on their masters' interpolation
+        (BulkElementBase::interpolate_hang_values, src/elements.cpp:448)"""
+        x = np.array(pos, dtype=np.float64, copy=True)
+        for n, (m, w) in self.hanging.C2.items():
+            x[n] = np.asarray(w) @ x[np.asarray(m)]
+        self.asm.set_nodal_positions(t, x)
+        if self.dofmap.pos_eqn is not None:
+            off = np.zeros(self.n_ext)
+            pe = self.ext.dofmap.pos_eqn
+            for n, (m, w) in self.hanging.C2.items():
+                for d in range(x.shape[1]):
+                    g = pe[n, d]
+                    if g >= 0:
+                        pinned = self.dofmap.pos_eqn[np.asarray(m), d] < 0
+                        off[g] = float(np.dot(np.asarray(w)[pinned], x[np.asarray(m)[pinned], d]))
+            self._pinned_pos_offset[t] = off
+
+    def set_lagrangian_positions(self, pos: np.ndarray):
+        x = np.array(pos, dtype=np.float64, copy=True)
+        for n, (m, w) in self.hanging.C2.items():
+            x[n] = np.asarray(w) @ x[np.asarray(m)]
+        self.asm.set_lagrangian_positions(x)
+
     def set_dofs(self, dofs: np.ndarray, t: int = 0):
         u = self.P @ np.asarray(dofs, dtype=np.float64)
         if t in self._pinned_offset:
             u = u + self._pinned_offset[t]
+        if t in self._pinned_pos_offset:
+            u = u + self._pinned_pos_offset[t]
         self.asm.set_dofs(u, t)
 
     def set_parameters(self, **values: float):

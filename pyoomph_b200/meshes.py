@@ -512,8 +512,6 @@ def assign_equation_numbers(mesh: StructuredMesh, code: FiniteElementCode,
             free[~vertex, f.index] = False     # dummy values on non-vertex nodes (src/elements.cpp:2235-2271)
     hanging = getattr(mesh, "hanging", None)
     if hanging is not None:
-        if code.coordinates_as_dofs:
-            raise NotImplementedError("hanging nodes on a moving mesh (hanging position dofs)")
         for f in code.nodal_fields():
             if f.space == "C1" and mesh.dim == 3:
                 raise NotImplementedError("C1 fields on octree-refined meshes (only the C2 hang infos are generated in 3D)")
@@ -524,6 +522,8 @@ def assign_equation_numbers(mesh: StructuredMesh, code: FiniteElementCode,
         free[np.asarray(list(nodes) if not isinstance(nodes, np.ndarray) else nodes, dtype=np.int64), code.fields[name].index] = False
     if code.coordinates_as_dofs:
         pfree = np.ones((n_node, dim), dtype=bool)
+        if hanging is not None and hanging.C2:
+            pfree[np.fromiter(hanging.C2.keys(), dtype=np.int64), :] = False       # hanging positions follow their masters
         for name, nodes in (pinned_positions or {}).items():
             d = "xyz".index(name[-1])
             pfree[np.asarray(list(nodes) if not isinstance(nodes, np.ndarray) else nodes, dtype=np.int64), d] = False

@@ -190,7 +190,7 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
             pinned = {"velocity_x": wall, "velocity_y": wall}
             unsteady = True
-    elif kind in ("poisson_hang", "ns_hang", "ns_unsteady_hang"):
+    elif kind in ("poisson_hang", "ns_hang", "ns_unsteady_hang", "ale_hang"):
         # one level of quadtree refinement of some elements of a (distorted) Q9 mesh: hanging nodes on the edges between refined and
         # unrefined elements (a14; the same element classes -- hanging is a property of the mesh, the generated code is the same)
         import pyoomph_b200.meshes as _mm
@@ -207,6 +207,12 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")
             pinned = {"u": np.concatenate([mesh.boundaries["left"], mesh.boundaries["right"]])}
             unsteady = False
+        elif kind == "ale_hang":
+            # hanging nodes on a MOVING mesh: the positions of the hanging nodes hang on their masters' position dofs
+            code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + PseudoElasticMesh(), name="ale")
+            wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
+            pinned = {"velocity_x": wall, "velocity_y": wall}
+            unsteady = True
         else:
             code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0), name="ns")
             wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "right", "bottom", "top")]))
@@ -405,6 +411,9 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
     if code.coordinates_as_dofs:
         pos_hist = np.stack([mesh.node_pos + 1e-3 * (1 + 0.3 * t) * np.stack(
             [smooth_field(mesh.node_pos, 10 + d + 2 * t, seed) for d in range(mesh.dim)], axis=1) for t in range(T)])
+        if hanging is not None:
+            for n, (m, w) in hanging.C2.items():         # hanging nodes sit on their masters' interpolation, at every history level
+                pos_hist[:, n, :] = np.einsum("k,tkd->td", w, pos_hist[:, m, :])
     return dict(kind=kind, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=pos_hist, unsteady=unsteady, params=params)
 
 

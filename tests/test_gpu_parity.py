@@ -635,7 +635,7 @@ def test_interface_class_assembled_into_the_matrix_of_its_bulk_class(kind, N, di
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,N,distortion", [("poisson_hang", 8, 0.12), ("ns_hang", 6, 0.1), ("ns_unsteady_hang", 6, 0.08), ("ns_hang", 24, 0.05),
-                                                ("heat3d_hang", 3, 0.08), ("heat3d_hang", 5, 0.0)])
+                                                ("heat3d_hang", 3, 0.08), ("heat3d_hang", 5, 0.0), ("ale_hang", 6, 0.08)])
 def test_hanging_nodes_parity(kind, N, distortion):
     """a14: a mesh with hanging nodes (one quadtree level).  Oracle: the reference's hang macros inside the element routine with its
     local numbering of the master values.  Product: the unchanged element kernel over virtual equations for the hanging values, then
@@ -652,6 +652,9 @@ def test_hanging_nodes_parity(kind, N, distortion):
     assert asm.n_dof == n and asm.n_ext > n
     for t in range(pb["vals"].shape[0]):
         asm.set_nodal_values(t, pb["vals"][t])
+    if pb["pos_hist"] is not None:         # moving mesh: the positions of the hanging nodes hang on their masters' position dofs
+        for t in range(pb["pos_hist"].shape[0]):
+            asm.set_nodal_positions(t, pb["pos_hist"][t])
     if pb["unsteady"]:
         asm.set_unsteady(TIME["t"], TIME["dt"], TIME["dtprev"], TIME["unsteady_steps_done"])
     else:
@@ -675,6 +678,9 @@ def test_hanging_nodes_parity(kind, N, distortion):
     ne = pb["dofmap"].node_eqn
     u = np.zeros(n)
     u[ne[ne >= 0]] = pb["vals"][0][ne >= 0]
+    if pb["pos_hist"] is not None:
+        pe = pb["dofmap"].pos_eqn
+        u[pe[pe >= 0]] = pb["pos_hist"][0][pe >= 0]
     asm.set_dofs(u)
     asm.assemble(flag=1)
     r2, jac2, _ = asm.fetch(True, False)

@@ -139,7 +139,7 @@ def test_patch_test_with_hanging_nodes():
     op.close()
 
 
-@pytest.mark.parametrize("kind,N,distortion", [("poisson_hang", 6, 0.12), ("ns_hang", 5, 0.1), ("ns_unsteady_hang", 5, 0.08), ("heat3d_hang", 3, 0.08)])
+@pytest.mark.parametrize("kind,N,distortion", [("poisson_hang", 6, 0.12), ("ns_hang", 5, 0.1), ("ns_unsteady_hang", 5, 0.08), ("heat3d_hang", 3, 0.08), ("ale_hang", 4, 0.08)])
 def test_global_reduction_equals_the_element_level_treatment(kind, N, distortion):
     """Route 1 (the reference's): hang macros inside the element routine.  Route 2 (the product's): virtual equations for the hanging
     values, the plain element routine, then P^T J_ext P -- by scipy and by the reduction lists the device kernels run."""
@@ -256,4 +256,45 @@ def test_octree_refinement_is_conforming():
     one = np.ones(n)
     ratio = (J @ one) / (M @ one)                   # J 1 = w0 M 1 (the time weight) when K 1 = 0
     assert np.abs(ratio - ratio[0]).max() < 1e-9 * abs(ratio[0])
+    op.close()
+
+
+def test_oracle_jacobian_with_hanging_positions_matches_finite_differences():
+    """hanging nodes on a MOVING mesh: the position dofs of the masters move the hanging nodes (hanginfo_Pos, src/elements.cpp:820-862);
+    analytic Jacobian columns of master positions and of ordinary dofs against central differences with the hanging nodes re-placed"""
+    pb = make_problem("ale_hang", 5, distortion=0.08)
+    n = pb["dofmap"].n_dof
+    eq, peq = pb["dofmap"].node_eqn, pb["dofmap"].pos_eqn
+    hang = pb["mesh"].hanging
+    assert np.all(peq[list(hang.C2)] < 0)                      # hanging positions are no dofs
+    op = make_oracle(pb)
+    _, mats = op.assemble(flag=1)
+    A = csr_to_sorted(n, *mats[0]).toarray()
+
+    def set_state(U):
+        v, x = pb["vals"][0].copy(), pb["pos_hist"][0].copy()
+        v[eq >= 0] = U[eq[eq >= 0]]
+        x[peq >= 0] = U[peq[peq >= 0]]
+        for f in pb["code"].nodal_fields():
+            for nn_, (ms, w) in hang.of_space(f.space).items():
+                v[nn_, f.index] = v[ms, f.index] @ w
+        for nn_, (ms, w) in hang.C2.items():
+            x[nn_] = w @ x[ms]
+        op.update_values(0, v, x)
+    U0 = np.zeros(n)
+    U0[eq[eq >= 0]] = pb["vals"][0][eq >= 0]
+    U0[peq[peq >= 0]] = pb["pos_hist"][0][peq >= 0]
+    masters = [g for _, (ms, _) in hang.C2.items() for g in peq[ms].ravel() if g >= 0]
+    cols = np.unique(np.array(masters[:40] + list(np.random.default_rng(0).choice(n, 20, replace=False))))
+    eps, worst = 1e-6, 0.0
+    for c in cols:
+        up, um = U0.copy(), U0.copy()
+        up[c] += eps
+        um[c] -= eps
+        set_state(up)
+        rp, _ = op.assemble(flag=0)
+        set_state(um)
+        rm, _ = op.assemble(flag=0)
+        worst = max(worst, np.abs((rp - rm) / (2 * eps) - A[:, c]).max() / np.abs(A).max())
+    assert worst < 5e-8, worst
     op.close()
