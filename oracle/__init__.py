@@ -63,17 +63,26 @@ def build_plugin(code, name: str, *, reference_headers: bool = False, fast_math:
     sofile = os.path.join(outdir, "%s_%s%s.so" % (name, tag, "_ref" if reference_headers else ""))
     if os.path.exists(sofile) and not force:
         return sofile
-    with open(cfile, "w") as f:
+    # several processes (the ranks of a multi-process test) may build the same plugin at once: everyone compiles into files of its own
+    # and renames the finished library into place, so that nobody ever loads a half-written one
+    tmp = "%s.%d.tmp" % (sofile, os.getpid())
+    ctmp = "%s.%d.c" % (cfile[:-2], os.getpid())
+    with open(ctmp, "w") as f:
         f.write(src)
     cmd = ["gcc", "-std=gnu99"] + cpu_flags(fast_math) + ["-fopenmp", "-shared", "-I", HERE]
     if reference_headers:
         if not os.path.isdir(REFERENCE_SRC):
             raise RuntimeError("reference tree not present")
         cmd += ["-DORACLE_USE_REFERENCE_HEADERS", "-I", REFERENCE_SRC]
-    cmd += [os.path.join(HERE, "driver.c"), cfile, "-o", sofile, "-lm"]
+    cmd += [os.path.join(HERE, "driver.c"), ctmp, "-o", tmp, "-lm"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        for f_ in (tmp, ctmp):
+            if os.path.exists(f_):
+                os.remove(f_)
         raise RuntimeError("oracle plugin compilation failed:\n" + r.stderr[-4000:])
+    os.replace(ctmp, cfile)
+    os.replace(tmp, sofile)
     return sofile
 
 
