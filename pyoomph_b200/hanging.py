@@ -263,6 +263,9 @@ class HangingNodeAssembly:
     def set_parameters(self, **values: float):
         self.asm.set_parameters(**values)
 
+    def shift_time_values(self):
+        self.asm.shift_time_values()
+
     def set_steady(self):
         self.asm.set_steady()
 

@@ -958,3 +958,86 @@ def test_integral_gradients_for_global_constraints():
                 assert abs((ip - im) / (2 * eps) - c[g]) <= 1e-7 * max(np.abs(c).max(), 1e-300)
     op.close()
     asm.close()
+
+
+@pytest.mark.gpu
+def test_newton_and_time_step_drivers():
+    """pyoomph_b200.newton: Problem::newton_solve / unsteady_newton_solve on top of the assembly path.  (1) the lid-driven cavity: the
+    same iterates as the oracle-driven loop with the same SuperLU, quadratic convergence; (2) the same solve with the matrix staying on
+    the device (solver plugin); (3) one BDF2 step of config 3 against the oracle-assembled step; (4) a mesh with hanging nodes."""
+    from scipy.sparse.linalg import splu
+    from problems import TIME
+    from test_oracle import _cavity, newton_cavity
+    from pyoomph_b200.hanging import HangingNodeAssembly
+    from pyoomph_b200.newton import newton_solve, unsteady_newton_solve
+    from pyoomph_b200.solvers import GenericLinearSystemSolver
+    pb = _cavity(8)
+    n = pb["dofmap"].n_dof
+    eq = pb["dofmap"].node_eqn
+    m = eq >= 0
+    op = make_oracle(pb)
+
+    def set_cpu(U):
+        v = pb["vals"][0].copy()
+        v[m] = U[eq[m]]
+        op.update_values(0, v)
+
+    def assemble_cpu():
+        r, mats = op.assemble(flag=1)
+        return r, csr_to_sorted(n, *mats[0])
+    U_ref, hist_ref = newton_cavity(pb, assemble_cpu, set_cpu)
+    asm = make_gpu(pb)
+    U0 = np.zeros(n)
+    U0[eq[m]] = pb["vals"][0][m]
+    U, hist = newton_solve(asm, U0, tol=1e-10, max_iter=12)
+    assert len(hist) == len(hist_ref) and np.abs(U - U_ref).max() <= 1e-9 * np.abs(U_ref).max()
+    assert hist[-1] < 1e-10 and hist[-2] < 1e-4 and hist[-3] > hist[-2] ** 0.75          # quadratic tail
+    Ud, histd = newton_solve(asm, U0, tol=1e-9, max_iter=12, device_solver=GenericLinearSystemSolver.factory_solver("torch_krylov"))
+    assert np.abs(Ud - U_ref).max() <= 1e-7 * np.abs(U_ref).max() and histd[-1] < 1e-9
+    op.close()
+    asm.close()
+    # (3) one implicit step of the Q27 heat equation
+    pb = make_problem("heat3d", 3)
+    n = pb["dofmap"].n_dof
+    eq = pb["dofmap"].node_eqn[:, 0]
+    asm = make_gpu(pb)
+    op = make_oracle(pb)
+    U0 = np.zeros(n)
+    U0[eq[eq >= 0]] = pb["vals"][0][eq >= 0, 0]
+    dt, dtprev = 0.02, TIME["dt"]
+    U1, h1 = unsteady_newton_solve(asm, U0, TIME["t"], dt, dtprev, 3, tol=1e-11)
+    vals = pb["vals"].copy()
+    vals[2], vals[1] = vals[1], vals[0]                       # shift_time_values
+    for t_ in range(3):
+        op.update_values(t_, vals[t_])
+    op.set_unsteady(TIME["t"] + dt, dt, dtprev, 3)
+    U = U0.copy()
+    for _ in range(4):
+        v = vals[0].copy()
+        v[eq >= 0, 0] = U[eq[eq >= 0]]
+        op.update_values(0, v)
+        r, mats = op.assemble(flag=1)
+        if np.abs(r).max() < 1e-11:
+            break
+        U = U - splu(csr_to_sorted(n, *mats[0]).tocsc()).solve(r)
+    assert len(h1) == 2 and np.abs(U1 - U).max() <= 1e-10 * np.abs(U).max()          # a linear problem: one Newton step
+    op.close()
+    asm.close()
+    # (4) hanging nodes: the driver works on the real equations, the virtual ones stay inside
+    pb = make_problem("poisson_hang", 6, distortion=0.1)
+    n = pb["dofmap"].n_dof
+    h = HangingNodeAssembly(pb["code"], pb["mesh"], pb["dofmap"], name=pb["code"].name)
+    h.set_nodal_values(0, pb["vals"][0])
+    h.set_steady()
+    Uh, hh = newton_solve(h, np.zeros(n), tol=1e-11)
+    op = make_oracle(pb)
+    ne = pb["dofmap"].node_eqn[:, 0]
+    v = pb["vals"][0].copy()
+    v[ne >= 0, 0] = Uh[ne[ne >= 0]]
+    for nn_, (ms, w) in pb["mesh"].hanging.C2.items():
+        v[nn_, 0] = v[ms, 0] @ w
+    op.update_values(0, v)
+    r, _ = op.assemble(flag=0)
+    assert np.abs(r).max() < 1e-10 and len(hh) == 2
+    op.close()
+    h.close()
