@@ -10,6 +10,8 @@ Scaling/non-dimensionalisation factors of the reference are all 1 here (no units
 """
 from __future__ import annotations
 
+from typing import Optional
+
 from .codegen import Equations
 from .expressions import (Weak, cartesian, div, dot, grad, identity_matrix, material_derivative, mesh_velocity, partial_t, rational_num, sym, trace, var,
                           var_and_test, weak)
@@ -345,3 +347,29 @@ class StreamlineDiffusionAdvection(Equations):
         else:
             h = var("element_length_h")
         self.add_residual(weak(partial_t(c) + wc, v) + weak(self.D * gc, gv) + weak(self.tau * h * wc, wv))
+
+
+class IntegralConstraint(Equations):
+    """A global constraint  integral(expr) = target  enforced by ONE Lagrange multiplier that is a global parameter of the element class
+    (the bordered form of pyoomph's GlobalLagrangeMultiplier + WeakContribution, pyoomph/generic/codegen.py:2927): the class gets
+
+      * the residual term  lambda * d(integral)/dU  (written by the caller as  weak(lambda * d expr/d field, test)  for the field(s) the
+        expression depends on: here the common case expr = field),
+      * the integral expression itself with its gradient contribution (the dense row), and
+      * the multiplier's dense column as the parameter derivative dR/d(lambda).
+
+    The solver then works on [[J, b], [c^T, 0]] with b = dR/dlambda and c = integral_gradient: two vectors per Newton step, reduced over
+    the ranks on several GPUs, no dense row inside the CSR matrix."""
+
+    def __init__(self, field: str, name: Optional[str] = None, multiplier: Optional[str] = None):
+        super().__init__()
+        self.field, self.name = field, name or ("integral_" + field)
+        self.multiplier = multiplier or ("lambda_" + field)
+
+    def define_residuals(self):
+        from .expressions import global_parameter
+        _, test = var_and_test(self.field)
+        self.add_residual(weak(global_parameter(self.multiplier), test))
+
+    def define_additional_functions(self):
+        self.add_integral_function(self.name, var(self.field) * self.get_dx(), with_gradient=True)

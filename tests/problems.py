@@ -231,6 +231,17 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
         code = FiniteElementCode("Brick3dC2", TransientHeatEquation(), name="heat3d")
         pinned = {"u": mesh.boundaries["left"]}
         unsteady = True
+    elif kind == "ns_mean_pressure":
+        # the pressure level fixed by the global constraint  integral(p) = 0  with a Lagrange multiplier (bordered system) instead of a
+        # pinned pressure value
+        from pyoomph_b200.equations import IntegralConstraint
+        mesh = RectangularQuadMesh(N)
+        code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + IntegralConstraint("pressure"),
+                                 name="nsmeanp")
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "right", "bottom", "top")]))
+        pinned = {"velocity_x": wall, "velocity_y": wall}
+        unsteady = False
+        params = {"lambda_pressure": 0.0}
     elif kind == "ns_constraint":
         # integral expressions WITH their gradients with respect to the dofs (the dense rows of global constraints in bordered form):
         # mean pressure, kinetic energy, flux through the domain

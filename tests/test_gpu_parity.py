@@ -1041,3 +1041,66 @@ def test_newton_and_time_step_drivers():
     assert np.abs(r).max() < 1e-10 and len(hh) == 2
     op.close()
     h.close()
+
+
+@pytest.mark.gpu
+def test_global_constraint_with_a_lagrange_multiplier_in_bordered_form():
+    """The pressure level of the lid-driven cavity fixed by  integral(p) = 0  through one global Lagrange multiplier (pyoomph's
+    GlobalLagrangeMultiplier; SURVEY 8e: such dense rows are not part of the CSR matrix): Newton's method on [[J, b], [c^T, 0]] with
+    b = dR/d(lambda) (parameter-derivative routine) and c = d(integral)/dU (gradient contribution), every piece assembled on the GPU,
+    against the same loop on oracle-assembled pieces."""
+    from scipy.sparse import bmat, csr_matrix
+    from scipy.sparse.linalg import splu
+    pb = make_problem("ns_mean_pressure", 6, distortion=0.05)
+    code = pb["code"]
+    n = pb["dofmap"].n_dof
+    eq = pb["dofmap"].node_eqn
+    m = eq >= 0
+    pb["vals"][0][:] = 0.0
+    pb["vals"][0][pb["mesh"].boundaries["top"], code.fields["velocity_x"].index] = 1.0          # the lid
+    wg = code.residual_names().index("d_integral_integral_pressure")
+
+    def bordered_newton(pieces):
+        U, lam, hist = np.zeros(n), 0.0, []
+        for _ in range(10):
+            r, J, b, c, g = pieces(U, lam)
+            hist.append(max(float(np.abs(r).max()), abs(g)))
+            if hist[-1] < 1e-10:
+                break
+            K = bmat([[J, csr_matrix(b[:, None])], [csr_matrix(c[None, :]), None]]).tocsc()
+            d = splu(K).solve(np.concatenate([r, [g]]))
+            U, lam = U - d[:n], lam - d[n]
+        return U, lam, hist
+
+    op = make_oracle(pb)
+
+    def cpu(U, lam):
+        v = pb["vals"][0].copy()
+        v[m] = U[eq[m]]
+        op.update_values(0, v)
+        op.set_params([lam])
+        r, mats = op.assemble(flag=1)
+        b, _ = op.assemble(which=0, param=0, flag=0)
+        c, _ = op.assemble(which=wg, flag=0)
+        return r, csr_to_sorted(n, *mats[0]), b, c, op.evaluate_integral_expressions()["integral_pressure"]
+    U_ref, lam_ref, hist_ref = bordered_newton(cpu)
+
+    asm = make_gpu(pb)
+
+    def gpu(U, lam):
+        asm.set_dofs(U)
+        asm.set_parameters(lambda_pressure=lam)
+        asm.assemble(flag=1)
+        r, jac, _ = asm.fetch(True, False)
+        asm.assemble(flag=0, parameter="lambda_pressure")
+        b, _, _ = asm.fetch(False, False)
+        c = asm.integral_gradient("integral_pressure")
+        return r, csr_matrix((jac, asm.indices, asm.indptr), shape=(n, n)), b, c, asm.evaluate_integral_expressions()["integral_pressure"]
+    U, lam, hist = bordered_newton(gpu)
+    assert hist_ref[-1] < 1e-10 and len(hist) == len(hist_ref) <= 8
+    assert np.abs(U - U_ref).max() <= 1e-9 * np.abs(U_ref).max() and abs(lam - lam_ref) <= 1e-9 * max(abs(lam_ref), 1e-3)
+    r, J, b, c, g = gpu(U, lam)
+    assert np.array_equal(b, c) or np.abs(b - c).max() <= 1e-15 * np.abs(c).max()             # dR/d(lambda) IS the constraint's gradient here
+    assert abs(g) < 1e-12
+    op.close()
+    asm.close()
