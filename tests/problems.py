@@ -93,7 +93,7 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
         vals = np.zeros((1, bulk.n_node, 1))
         vals[0, :, 0] = smooth_field(bulk.node_pos, 0, seed)
         return dict(kind=kind, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=None, unsteady=False, params={}, bulk_mesh=bulk, bulk_code=bulk_code)
-    if kind in ("robin_if", "freesurf_if", "freesurf_mov_if"):
+    if kind in ("robin_if", "freesurf_if", "freesurf_mov_if", "freesurf_mov_axi_if"):
         # interface element classes (InterfaceElementLine1dC2) on boundary edges of a (distorted) Q9 mesh, on the bulk's nodes, nodal
         # values and equation numbers: a Robin condition for the Poisson field of config 1, and the free-surface terms of config 4
         # (surface tension, no-penetration through a Lagrange multiplier field on the interface) on a mesh that does not move
@@ -103,11 +103,21 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
         bulk = _mm.RectangularQuadMesh(N)
         if distortion:
             bulk = distort(bulk, distortion, seed)
-        mesh = _mm.boundary_line_mesh(bulk, ["right", "top"] if kind == "robin_if" else ["top", "left"])
+        mesh = _mm.boundary_line_mesh(bulk, ["right", "top"] if kind in ("robin_if", "freesurf_mov_axi_if") else ["top", "left"])
         if kind == "robin_if":
             code = FiniteElementCode("Line1dC2", RobinBC("u", alpha=2.5, external=lambda: _var("coordinate_x") * _var("coordinate_y"), flux=0.3), name="robinif")
             bulk_code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")
             pinned = {"u": bulk.boundaries["left"]}
+        elif kind == "freesurf_mov_axi_if":
+            # ... and AXISYMMETRIC, as BASELINE config 4 is (a droplet: r = x, the interface away from the axis): measure 2 pi r ds, surface
+            # divergence with its v_r / r term, all of it depending on the position dofs
+            code = FiniteElementCode("Line1dC2", NavierStokesFreeSurface(surface_tension=0.7, static_interface=False), name="freesurfmovaxi",
+                                     coordinate_system="axisymmetric")
+            bulk_code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + PseudoElasticMesh() +
+                                          DeclareFields(_kin_bc="C2"), name="aleaxiif", coordinate_system="axisymmetric")
+            wall = np.unique(np.concatenate([bulk.boundaries[b] for b in ("bottom", "left")]))
+            off_interface = np.setdiff1d(np.arange(bulk.n_node), np.unique(mesh.elem_nodes))
+            pinned = {"velocity_x": wall, "velocity_y": wall, "_kin_bc": off_interface}
         elif kind == "freesurf_mov_if":
             # config 4 as BASELINE names it: the free surface of a MOVING mesh (kinematic condition with the mesh velocity, the multiplier
             # acting on the position equations; normal, surface divergence and line measure depend on the position dofs)
@@ -123,10 +133,10 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             wall = np.unique(np.concatenate([bulk.boundaries[b] for b in ("bottom", "right")]))
             off_interface = np.setdiff1d(np.arange(bulk.n_node), np.unique(mesh.elem_nodes))
             pinned = {"velocity_x": wall, "velocity_y": wall, "_kin_bc": off_interface}     # the multiplier exists on the interface nodes only
-        unsteady = kind == "freesurf_mov_if"
+        unsteady = kind in ("freesurf_mov_if", "freesurf_mov_axi_if")
         pinned_pos = None
         if bulk_code.coordinates_as_dofs:
-            pinned_pos = {"coordinate_x": bulk.boundaries["right"], "coordinate_y": bulk.boundaries["bottom"]}
+            pinned_pos = {"coordinate_x": bulk.boundaries["left" if kind == "freesurf_mov_axi_if" else "right"], "coordinate_y": bulk.boundaries["bottom"]}
         dofmap = assign_equation_numbers(bulk, bulk_code, pinned, pinned_pos)
         assert [f.name for f in code.nodal_fields()] == [f.name for f in bulk_code.nodal_fields()]
         assert code.coordinates_as_dofs == bulk_code.coordinates_as_dofs

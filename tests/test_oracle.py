@@ -491,7 +491,13 @@ def test_moving_free_surface_of_the_oracle_matches_finite_differences():
     gradients of the test functions (the el_dim x nodal_dim tensors of src/elements.cpp:3051-3155) -- against central differences of the
     residual, BDF2 step with mesh velocity"""
     from problems import csr_to_sorted, make_oracle, make_problem
-    pb = make_problem("freesurf_mov_if", 4, distortion=0.12)
+    _check_moving_free_surface("freesurf_mov_if")
+    _check_moving_free_surface("freesurf_mov_axi_if")         # config 4 is axisymmetric: 2 pi r in the measure, v_r / r in the surface divergence
+
+
+def _check_moving_free_surface(kind):
+    from problems import csr_to_sorted, make_oracle, make_problem
+    pb = make_problem(kind, 4, distortion=0.12)
     assert pb["code"].coordinates_as_dofs and pb["unsteady"]
     op = make_oracle(pb)
     _, mats = op.assemble(flag=1)
