@@ -146,19 +146,21 @@ def build_workload(workload, n, seed=0):
         unsteady = False
         label = "2D Poisson QUAD2 %dx%d" % (n, n)
     elif workload == "ale_freesurface":
-        # BASELINE config 4's element classes: NS Taylor-Hood on a pseudo-elastic moving mesh (40 dofs per element) + the free-surface
+        # BASELINE config 4's element classes: axisymmetric NS Taylor-Hood on a pseudo-elastic moving mesh (49 dofs per element) + the free-surface
         # interface class on the top boundary, assembled into the same matrix (child problem)
         from pyoomph_b200.equations import DeclareFields, NavierStokesFreeSurface, PseudoElasticMesh
         from pyoomph_b200.meshes import boundary_line_mesh
         mesh = RectangularQuadMesh(n)
-        code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + PseudoElasticMesh() + DeclareFields(_kin_bc="C2"), name="aleif")
+        code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + PseudoElasticMesh() + DeclareFields(_kin_bc="C2"),
+                                 name="aleaxiif", coordinate_system="axisymmetric")
         imesh = boundary_line_mesh(mesh, ["top"])
-        icode = FiniteElementCode("Line1dC2", NavierStokesFreeSurface(surface_tension=0.7, static_interface=False), name="freesurfmov")
+        icode = FiniteElementCode("Line1dC2", NavierStokesFreeSurface(surface_tension=0.7, static_interface=False), name="freesurfmovaxi",
+                                  coordinate_system="axisymmetric")
         wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("bottom", "left", "right")]))
         pinned = {"velocity_x": wall, "velocity_y": wall, "_kin_bc": np.setdiff1d(np.arange(mesh.n_node), np.unique(imesh.elem_nodes))}
         pinned_pos = {"coordinate_x": np.unique(np.concatenate([mesh.boundaries["left"], mesh.boundaries["right"]])), "coordinate_y": mesh.boundaries["bottom"]}
         unsteady = True
-        label = "2D NS Taylor-Hood on a pseudo-elastic moving mesh %dx%d + free-surface interface class (%d line elements) in one matrix, BDF2" % (n, n, imesh.n_elem)
+        label = "axisymmetric NS Taylor-Hood on a pseudo-elastic moving mesh %dx%d + free-surface interface class (%d line elements) in one matrix, BDF2" % (n, n, imesh.n_elem)
         extra = dict(interface_mesh=imesh, interface_code=icode)
     elif workload in ("ns_swirl_hvp", "ns_azimuthal"):
         # BASELINE config 5's element class: axisymmetric NS Taylor-Hood with swirl (31 dofs per element); timed: one Hessian-vector
