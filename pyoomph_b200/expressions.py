@@ -351,6 +351,57 @@ class AxisymmetryBreakingCoordinateSystem(AxisymmetricCoordinateSystem):
         return sp.expand(self._first_order(residual).coeff(sp.I))
 
 
+class CartesianCoordinateSystemWithAdditionalNormalMode(CartesianCoordinateSystem):
+    """Normal-mode expansion exp(i k z) in the direction a two-dimensional Cartesian domain does not resolve
+    (pyoomph/expressions/coordsys.py:574-760; `Problem.setup_for_stability_analysis(additional_cartesian_mode=True)`): fields
+    U_base(x, y) + eps * U_mode(x, y) * exp(i k z), tests with exp(-i k z), vectors with three components (x, y, z), the gradient's third
+    entry d/dz, the divergence's d v_z / dz.  Contributions "real_contrib_normal_mode_stability" / "imag_contrib_normal_mode_stability"
+    (pyoomph/generic/problem.py:108-109); k is the global parameter "normal_mode_k".  Same machinery as the azimuthal expansion."""
+    has_normal_mode_expansion = True
+    real_contribution_name = "real_contrib_normal_mode_stability"
+    imag_contribution_name = "imag_contrib_normal_mode_stability"
+
+    def __init__(self, normal_mode="normal_mode_k"):
+        self.angular_mode = normal_mode if isinstance(normal_mode, str) else sp.sympify(normal_mode)
+        self.expansion_eps = sp.Symbol("EPS__mode_expansion", real=True)
+        self.m_angular_symbol = sp.Symbol("K__normal_mode", real=True)
+        self.phi = sp.Symbol("XADD__normal_mode", real=True)          # the additional coordinate
+        self.field_mode = sp.exp(sp.I * self.m_angular_symbol * self.phi)
+        self.test_mode = sp.exp(-sp.I * self.m_angular_symbol * self.phi)
+
+    expands = AxisymmetryBreakingCoordinateSystem.expands
+    map_residual_on_base_mode = AxisymmetryBreakingCoordinateSystem.map_residual_on_base_mode
+    _first_order = AxisymmetryBreakingCoordinateSystem._first_order
+    map_residual_on_angular_eigenproblem_real = AxisymmetryBreakingCoordinateSystem.map_residual_on_angular_eigenproblem_real
+    map_residual_on_angular_eigenproblem_imag = AxisymmetryBreakingCoordinateSystem.map_residual_on_angular_eigenproblem_imag
+
+    def vector_dimension(self, nodal_dim: int) -> int:
+        if nodal_dim != 2:
+            raise RuntimeError("the additional normal mode is built for 2d meshes")
+        return 3
+
+    def scalar_gradient(self, arg, lagrangian: bool):
+        cs = _coords(lagrangian)
+        return sp.Matrix([sp.diff(arg, cs[0]), sp.diff(arg, cs[1]), sp.Integer(0) if lagrangian else sp.diff(arg, self.phi)])
+
+    def vector_gradient(self, arg, lagrangian: bool):
+        cs = _coords(lagrangian)
+        n = arg.shape[0]
+        return sp.Matrix(n, 3, lambda i, j: sp.diff(arg[i, 0], cs[j]) if j < 2 else (sp.Integer(0) if lagrangian else sp.diff(arg[i, 0], self.phi)))
+
+    def vector_divergence(self, arg, lagrangian: bool):
+        cs = _coords(lagrangian)
+        d = sp.diff(arg[0, 0], cs[0]) + sp.diff(arg[1, 0], cs[1])
+        if arg.shape[0] > 2 and not lagrangian:
+            d += sp.diff(arg[2, 0], self.phi)
+        return d
+
+    def tensor_divergence(self, arg, lagrangian: bool):
+        cs = _coords(lagrangian)
+        return sp.Matrix([sum(sp.diff(arg[i, j], cs[j]) for j in range(2)) + (sp.Integer(0) if (lagrangian or arg.shape[1] < 3) else sp.diff(arg[i, 2], self.phi))
+                          for i in range(arg.shape[0])])
+
+
 cartesian = CartesianCoordinateSystem()
 axisymmetric = AxisymmetricCoordinateSystem()
 

@@ -376,6 +376,22 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("left", "bottom")]))
             pinned = {"velocity_x": wall, "velocity_y": wall}
         unsteady = True
+    elif kind in ("ns_kz", "ns_kz_ext"):
+        # the Cartesian sibling: normal mode exp(i k z) normal to a 2D Cartesian domain (three velocity components x, y, z)
+        from pyoomph_b200.equations import DeclareFields
+        from pyoomph_b200.expressions import MODE_SUFFIX, CartesianCoordinateSystemWithAdditionalNormalMode
+        mesh = RectangularQuadMesh(N)
+        eqs = NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0, with_azimuthal_velocity=True)
+        base_names = ["velocity_x", "velocity_y", "velocity_z", "pressure"]
+        if kind == "ns_kz_ext":
+            eqs = eqs + DeclareFields(**{n + MODE_SUFFIX: ("C1" if n == "pressure" else "C2") for n in base_names})
+        code = FiniteElementCode("Quad2dC2", eqs, name="nskz" if kind == "ns_kz" else "nskzext", coordinate_system=CartesianCoordinateSystemWithAdditionalNormalMode("normal_mode_k"))
+        wall = np.unique(np.concatenate([mesh.boundaries[b] for b in ("right", "bottom", "top", "left")]))
+        pinned = {"velocity_x": wall, "velocity_y": wall, "velocity_z": wall}
+        if kind == "ns_kz_ext":
+            pinned.update({n + MODE_SUFFIX: v for n, v in list(pinned.items())})
+        unsteady = True
+        params = {"normal_mode_k": 1.0}
     elif kind in ("ns_azi", "ns_azi_ext"):
         # config 5 as BASELINE names it: azimuthal normal-mode expansion exp(i m phi) about the axisymmetric NS base flow with swirl.
         # "ns_azi": the product's class -- base residual + real / imaginary contribution of the angular eigenproblem, the mode fields
@@ -415,10 +431,10 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
     for t in range(T):
         for f in range(nval):
             vals[t, :, f] = smooth_field(mesh.node_pos, f + 3 * t, seed) * (1.0 - 0.05 * t)
-    if kind == "ns_azi_ext":
+    if kind in ("ns_azi_ext", "ns_kz_ext"):
         # base and mode fields carry the values the product's class has in its base fields (the contributions are evaluated at the base state)
         from pyoomph_b200.expressions import MODE_SUFFIX
-        base = make_problem("ns_azi", N, seed, distortion, unstructured)
+        base = make_problem(kind[:-4], N, seed, distortion, unstructured)
         for f in base["code"].nodal_fields():
             vals[:, :, code.fields[f.name].index] = base["vals"][:, :, f.index]
             vals[:, :, code.fields[f.name + MODE_SUFFIX].index] = base["vals"][:, :, f.index]

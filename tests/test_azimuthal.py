@@ -82,3 +82,22 @@ def test_generic_second_derivative_route_reproduces_the_fixed_mesh_hessian_forms
             assert set(da) == set(db) and len(da) == 8 * (A is a.J)
             for k in da:
                 assert sp.simplify(da[k] - db[k]) == 0, k
+
+
+def test_cartesian_normal_mode_expansion():
+    """exp(i k z) normal to a 2D Cartesian domain (CartesianCoordinateSystemWithAdditionalNormalMode, coordsys.py:574): k = 0 gives the
+    base operator and no imaginary part; the viscous term gains mu k^2; continuity couples to v_z through i k"""
+    from problems import make_problem
+    c = make_problem("ns_kz", 2)["code"]
+    cs = c.coordinate_system
+    assert c.residual_names() == ["", "real_contrib_normal_mode_stability", "imag_contrib_normal_mode_stability"] and c.global_params == ["normal_mode_k"]
+    fb, fr, fi = c.derive(""), c.derive(cs.real_contribution_name), c.derive(cs.imag_contribution_name)
+    k = c._param_syms["normal_mode_k"]
+    b, r, i = _by_slot(fb), _by_slot(fr), _by_slot(fi)
+    for key in set(b) | set(r):
+        assert sp.simplify(r.get(key, 0).subs(k, 0) - b.get(key, 0)) == 0, key
+    assert all(sp.simplify(v.subs(k, 0)) == 0 for v in i.values()) and len(i) > 5
+    d = sp.factor(r[("velocity_x", "d0", "velocity_x", "d0")] - b[("velocity_x", "d0", "velocity_x", "d0")])
+    dx = [s for s in d.free_symbols if s.name == "M__dx"][0]
+    assert sp.simplify(d - sp.Float(0.01) * dx * k ** 2) == 0
+    assert sp.simplify(i[("pressure", "d0", "velocity_z", "d0")] ** 2 - (dx * k) ** 2) == 0
