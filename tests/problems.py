@@ -93,7 +93,7 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
         vals = np.zeros((1, bulk.n_node, 1))
         vals[0, :, 0] = smooth_field(bulk.node_pos, 0, seed)
         return dict(kind=kind, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=None, unsteady=False, params={}, bulk_mesh=bulk, bulk_code=bulk_code)
-    if kind in ("robin_if", "freesurf_if", "freesurf_mov_if", "freesurf_mov_axi_if"):
+    if kind in ("robin_if", "robin_if_obs", "freesurf_if", "freesurf_mov_if", "freesurf_mov_axi_if"):
         # interface element classes (InterfaceElementLine1dC2) on boundary edges of a (distorted) Q9 mesh, on the bulk's nodes, nodal
         # values and equation numbers: a Robin condition for the Poisson field of config 1, and the free-surface terms of config 4
         # (surface tension, no-penetration through a Lagrange multiplier field on the interface) on a mesh that does not move
@@ -103,8 +103,18 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
         bulk = _mm.RectangularQuadMesh(N)
         if distortion:
             bulk = distort(bulk, distortion, seed)
-        mesh = _mm.boundary_line_mesh(bulk, ["right", "top"] if kind in ("robin_if", "freesurf_mov_axi_if") else ["top", "left"])
-        if kind == "robin_if":
+        mesh = _mm.boundary_line_mesh(bulk, ["right", "top"] if kind in ("robin_if", "robin_if_obs", "freesurf_mov_axi_if") else ["top", "left"])
+        if kind == "robin_if_obs":
+            # integral expressions over an INTERFACE (boundary length, mean value, the flux the Robin condition exchanges, the tangential
+            # variation of the field, the outward normal integrated along the boundary)
+            from pyoomph_b200.equations import IntegralObservables
+            from pyoomph_b200.expressions import dot, grad
+            obs = IntegralObservables(length=1, mean_u=lambda: _var("u"), exchange=lambda: 2.5 * (_var("u") - _var("coordinate_x") * _var("coordinate_y")),
+                                      tangential_variation=lambda: dot(grad(_var("u")), grad(_var("u"))), normal=lambda: _var("normal"))
+            code = FiniteElementCode("Line1dC2", RobinBC("u", alpha=2.5, external=lambda: _var("coordinate_x") * _var("coordinate_y"), flux=0.3) + obs, name="robinifobs")
+            bulk_code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")
+            pinned = {"u": bulk.boundaries["left"]}
+        elif kind == "robin_if":
             code = FiniteElementCode("Line1dC2", RobinBC("u", alpha=2.5, external=lambda: _var("coordinate_x") * _var("coordinate_y"), flux=0.3), name="robinif")
             bulk_code = FiniteElementCode("Quad2dC2", PoissonEquation(source=poisson_source), name="poisson")
             pinned = {"u": bulk.boundaries["left"]}
