@@ -3,7 +3,7 @@ tag=${1:-r02y}
 out=gpurun_out/$tag
 mkdir -p $out
 rm -f gpurun_out/csr_parity_stats.jsonl
-( time timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "azimuthal" ) > $out/pytest_new.log 2>&1
+( time timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "integral_expressions" ) > $out/pytest_new.log 2>&1
 echo "rc=$?" >> $out/pytest_new.log
 ( time timeout 1200 python -m pytest tests -m gpu -q ) > $out/pytest.log 2>&1
 echo "pytest rc=$?" >> $out/pytest.log
