@@ -48,6 +48,22 @@ def cpu_flags(fast_math: bool = False):
     return fl
 
 
+_CPU_TAG = None
+
+
+def _cpu_tag() -> str:
+    """fingerprint of the host CPU's instruction-set flags: the plugins are compiled with -march=native (the reference's SystemCCompiler
+    flags), so a library built on one host must not be reused on a host with another instruction set (it is rebuilt there instead)"""
+    global _CPU_TAG
+    if _CPU_TAG is None:
+        try:
+            flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+            _CPU_TAG = hashlib.sha1(" ".join(sorted(flags.split(":", 1)[1].split())).encode()).hexdigest()[:8]
+        except Exception:
+            _CPU_TAG = "unknown"
+    return _CPU_TAG
+
+
 def build_plugin(code, name: str, *, reference_headers: bool = False, fast_math: bool = False, force: bool = False) -> str:
     """Emit the generated-format C for `code`, compile it with the restated driver, return the .so path.
 
@@ -58,7 +74,7 @@ def build_plugin(code, name: str, *, reference_headers: bool = False, fast_math:
     os.makedirs(outdir, exist_ok=True)
     driver = open(os.path.join(HERE, "driver.c")).read()
     hdrs = open(os.path.join(HERE, "oracle_jit.h")).read() + open(os.path.join(HERE, "oracle_jit_hang.h")).read()
-    tag = hashlib.sha1((src + driver + hdrs + str(fast_math)).encode()).hexdigest()[:12]
+    tag = hashlib.sha1((src + driver + hdrs + str(fast_math) + _cpu_tag()).encode()).hexdigest()[:12]
     cfile = os.path.join(outdir, "%s_%s.c" % (name, tag))
     sofile = os.path.join(outdir, "%s_%s%s.so" % (name, tag, "_ref" if reference_headers else ""))
     if os.path.exists(sofile) and not force:
