@@ -1306,21 +1306,40 @@ class CudaEmitter:
             # element sizes (fill_shape_info_element_sizes, src/elements.cpp:3527-3568): sum over ALL integration points of w * J, with the
             # coordinate system's JacobianForElementSize (2 Pi r when axisymmetric) at the point for the non-Cartesian one; every
             # (element, point) thread forms the sum itself (a few hundred flops; only classes that use the symbols pay)
-            if edim != 2 or dim != 2:
-                raise NotImplementedError("element sizes: two-dimensional bulk elements only")
+            if edim != dim or dim not in (2, 3):
+                raise NotImplementedError("element sizes: bulk elements (two- or three-dimensional) only")
             axi = code.coordinate_system.get_id_name() == "Axisymmetric"
             w("      double esz_cart = 0.0, esz_eul = 0.0;")
             w("      for (int q = 0; q < %d; ++q)" % NIPT)
             w("      {")
             w("        const double* dq = s_dpsi2 + q * %d; const double* pq = s_psi2 + q * %d; (void)pq;" % (NN * edim, NN))
-            w("        double e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0, ex0 = 0.0;")
-            w("        for (int l = 0; l < %d; ++l)" % NN)
-            w("        {")
-            w("          const double X0 = E[%d + l * 2], X1 = E[%d + l * 2 + 1];" % (plan["xpos"], plan["xpos"]))
-            w("          e00 += X0 * dq[l * 2]; e01 += X1 * dq[l * 2]; e10 += X0 * dq[l * 2 + 1]; e11 += X1 * dq[l * 2 + 1]; ex0 += X0 * pq[l];")
-            w("        }")
-            w("        const double a00 = e00 * e00 + e01 * e01, a01 = e00 * e10 + e01 * e11, a11 = e10 * e10 + e11 * e11;")
-            w("        const double Jq = c_w[q] * sqrt(a00 * a11 - a01 * a01);")
+            if dim == 2:
+                w("        double e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0, ex0 = 0.0;")
+                w("        for (int l = 0; l < %d; ++l)" % NN)
+                w("        {")
+                w("          const double X0 = E[%d + l * 2], X1 = E[%d + l * 2 + 1];" % (plan["xpos"], plan["xpos"]))
+                w("          e00 += X0 * dq[l * 2]; e01 += X1 * dq[l * 2]; e10 += X0 * dq[l * 2 + 1]; e11 += X1 * dq[l * 2 + 1]; ex0 += X0 * pq[l];")
+                w("        }")
+                w("        const double a00 = e00 * e00 + e01 * e01, a01 = e00 * e10 + e01 * e11, a11 = e10 * e10 + e11 * e11;")
+                w("        const double Jq = c_w[q] * sqrt(a00 * a11 - a01 * a01);")
+            else:
+                # three dimensions: the metric a_ab = t_a . t_b of the three tangents and the root of its determinant, as
+                # fill_shape_info_at_s forms it (src/elements.cpp:3801)
+                w("        double e[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}}; const double ex0 = 0.0; (void)ex0;")
+                w("        for (int l = 0; l < %d; ++l)" % NN)
+                w("        {")
+                w("          const double X0 = E[%d + l * 3], X1 = E[%d + l * 3 + 1], X2 = E[%d + l * 3 + 2];" % ((plan["xpos"],) * 3))
+                w("          #pragma unroll")
+                w("          for (int b = 0; b < 3; ++b) { const double d = dq[l * 3 + b]; e[b][0] += X0 * d; e[b][1] += X1 * d; e[b][2] += X2 * d; }")
+                w("        }")
+                w("        double m[3][3];")
+                w("        #pragma unroll")
+                w("        for (int a_ = 0; a_ < 3; ++a_)")
+                w("          #pragma unroll")
+                w("          for (int b = 0; b < 3; ++b) m[a_][b] = e[a_][0] * e[b][0] + e[a_][1] * e[b][1] + e[a_][2] * e[b][2];")
+                w("        const double detm = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0])")
+                w("                          + m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);")
+                w("        const double Jq = c_w[q] * sqrt(detm);")
             w("        esz_cart += Jq; esz_eul += Jq * %s;" % ("(2.0 * 3.14159265359 * ex0)" if axi else "1.0"))
             w("      }")
             w("      (void)esz_cart; (void)esz_eul;")

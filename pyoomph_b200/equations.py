@@ -338,8 +338,8 @@ class StreamlineDiffusionAdvection(Equations):
     def define_residuals(self):
         c, v = var_and_test(self.name)
         gc, gv = grad(c), grad(v)
-        wc = sum(self.wind[i] * gc[i, 0] for i in range(2))
-        wv = sum(self.wind[i] * gv[i, 0] for i in range(2))
+        wc = sum(self.wind[i] * gc[i, 0] for i in range(len(self.wind)))
+        wv = sum(self.wind[i] * gv[i, 0] for i in range(len(self.wind)))
         if self.cartesian_size:
             from .expressions import ELEMSIZE_EUL_CART
             import sympy as sp

@@ -118,8 +118,8 @@ def var(arg: Union[str, Sequence[str]]):
         return TIME
     if arg in ("element_size_Eulerian", "cartesian_element_size_Eulerian", "element_length_h"):
         # pyoomph/expressions/generic.py:174-178; stabilisation terms (SUPG / PSPG, artificial diffusion) are built on them
-        if code.etype.elem_dim != 2 or code.nodal_dim != 2:
-            raise NotImplementedError("element sizes: two-dimensional bulk elements only")
+        if code.etype.elem_dim != code.nodal_dim or code.nodal_dim not in (2, 3):
+            raise NotImplementedError("element sizes: bulk elements (two- or three-dimensional) only")
         if arg == "cartesian_element_size_Eulerian":
             return ELEMSIZE_EUL_CART
         return ELEMSIZE_EUL if arg == "element_size_Eulerian" else ELEMSIZE_EUL ** sp.Rational(1, code.etype.elem_dim)

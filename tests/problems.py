@@ -319,6 +319,15 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
         code = FiniteElementCode("Quad2dC2", NonlinearHeatEquation(), name="nlheat")
         pinned = {"u": mesh.boundaries["left"]}
         unsteady = True
+    elif kind in ("supg3d", "supg_tet"):
+        # element sizes in three dimensions (element_length_h = cube root of the element volume) on bricks and tetrahedra
+        from pyoomph_b200.equations import StreamlineDiffusionAdvection
+        import pyoomph_b200.meshes as _mm
+        mesh = CuboidBrickMesh(N) if kind == "supg3d" else _mm.CuboidTetraMesh(N)
+        code = FiniteElementCode("Brick3dC2" if kind == "supg3d" else "Tetra3dC2", StreamlineDiffusionAdvection(wind=(1.0, 0.5, -0.25)),
+                                 name=kind.replace("_", ""))
+        pinned = {"c": mesh.boundaries["left"]}
+        unsteady = True
     elif kind == "heat3d":         # config 3
         mesh = CuboidBrickMesh(N)
         code = FiniteElementCode("Brick3dC2", TransientHeatEquation(), name="heat3d")

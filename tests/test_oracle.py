@@ -621,8 +621,20 @@ def test_element_sizes_of_the_oracle():
     n = pb["dofmap"].n_dof
     assert abs(csr_to_sorted(n, *ma[0]) - csr_to_sorted(n, *mb[0])).max() <= 1e-13 * abs(csr_to_sorted(n, *mb[0])).max()
     a.close(); b.close()
-    for kind in ("supg", "supg_axi"):
-        pb = make_problem(kind, 4, distortion=0.12)
+    # three dimensions: h = (element volume)^(1/3) = 1/N on uniform bricks
+    pb3 = make_problem("supg3d", 3)
+
+    class _ConstH3(_ConstH):
+        pass
+    N = 3           # read by _ConstH when the class is built
+    pbc3 = dict(pb3, code=FiniteElementCode("Brick3dC2", _ConstH3(wind=(1.0, 0.5, -0.25)), name="supg3dconst"))
+    a, b = make_oracle(pb3), make_oracle(pbc3)
+    ra, _ = a.assemble(flag=0)
+    rb, _ = b.assemble(flag=0)
+    assert np.abs(ra - rb).max() <= 1e-13 * np.abs(rb).max()
+    a.close(); b.close()
+    for kind in ("supg", "supg_axi", "supg3d", "supg_tet"):
+        pb = make_problem(kind, 2 if kind == "supg_tet" else (3 if kind == "supg3d" else 4), distortion=0.12)
         op = make_oracle(pb)
         n = pb["dofmap"].n_dof
         _, mats = op.assemble(flag=1)
