@@ -189,7 +189,7 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             for f in range(nval):
                 vals[t, :, f] = smooth_field(mesh.node_pos, f + 3 * t, seed) * (1.0 - 0.05 * t)
         return dict(kind=kind, code=code, mesh=mesh, dofmap=dofmap, vals=vals, pos_hist=None, unsteady=unsteady, params=params)
-    if kind in ("poisson_tri", "ns_tri", "ale_tri"):
+    if kind in ("poisson_tri", "ns_tri", "ale_tri", "supg_tri"):
         # six-node triangles (the element class of the reference's gmsh droplet meshes): Poisson, Taylor-Hood P2/P1 Navier-Stokes,
         # and NS on a pseudo-elastic moving mesh
         import pyoomph_b200.meshes as _mm
@@ -198,7 +198,12 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             raise NotImplementedError
         if distortion:
             mesh = distort(mesh, distortion, seed)
-        if kind == "poisson_tri":
+        if kind == "supg_tri":                    # element sizes on triangles
+            from pyoomph_b200.equations import StreamlineDiffusionAdvection
+            code = FiniteElementCode("Tri2dC2", StreamlineDiffusionAdvection(), name="supgtri")
+            pinned = {"c": mesh.boundaries["left"]}
+            unsteady = True
+        elif kind == "poisson_tri":
             code = FiniteElementCode("Tri2dC2", PoissonEquation(source=poisson_source), name="poissontri")
             pinned = {"u": np.concatenate([mesh.boundaries["left"], mesh.boundaries["right"]])}
             unsteady = False

@@ -633,7 +633,7 @@ def test_element_sizes_of_the_oracle():
     rb, _ = b.assemble(flag=0)
     assert np.abs(ra - rb).max() <= 1e-13 * np.abs(rb).max()
     a.close(); b.close()
-    for kind in ("supg", "supg_axi", "supg3d", "supg_tet"):
+    for kind in ("supg", "supg_axi", "supg3d", "supg_tet", "supg_tri"):
         pb = make_problem(kind, 2 if kind == "supg_tet" else (3 if kind == "supg3d" else 4), distortion=0.12)
         op = make_oracle(pb)
         n = pb["dofmap"].n_dof
