@@ -831,9 +831,9 @@ static void element_rjm_bound(ThreadState *ts, int which, int param, unsigned fl
   /* fill_shape_info_element_sizes (src/elements.cpp:3527-3568): sum over all integration points of w * J, times the coordinate
    * system's JacobianForElementSize at the point for the non-Cartesian size */
   const JITFuncSpec_RequiredShapes_FiniteElement_t *rq = &o->ft->shapes_required_ResJac[which];
-  if (rq->elemsize_Eulerian_Pos || rq->elemsize_Eulerian_cartesian_Pos)
+  if (rq->elemsize_Eulerian_Pos || rq->elemsize_Eulerian_cartesian_Pos || rq->elemsize_Lagrangian_Pos || rq->elemsize_Lagrangian_cartesian_Pos)
   {
-    double esz = 0.0, esz_cart = 0.0;
+    double esz = 0.0, esz_cart = 0.0, eszL = 0.0, eszL_cart = 0.0;
     for (int q = 0; q < o->et.n_int; q++)
     {
       double s[MAXD], w;
@@ -847,9 +847,17 @@ static void element_rjm_bound(ThreadState *ts, int which, int param, unsigned fl
         for (int i = 0; i < o->et.dim; i++) x[i] += ts->ei.nodal_coords[l][i][0] * ts->si.shape_C2[l];
       esz_cart += ts->si.int_pt_weight;
       esz += ts->si.int_pt_weight * o->ft->JacobianForElementSize(&ts->ei, x);
+      /* the Lagrangian sizes: interpolated_xi and J_lagrangian_at_knot (src/elements.cpp:3546-3551, :3569-3574) */
+      double xi[MAXD] = {0, 0, 0};
+      for (int l = 0; l < o->et.nnode; l++)
+        for (int i = 0; i < o->et.dim; i++) xi[i] += ts->ei.nodal_coords[l][o->et.dim + i][0] * ts->si.shape_C2[l];
+      eszL_cart += ts->si.int_pt_weight_Lagrangian;
+      eszL += ts->si.int_pt_weight_Lagrangian * o->ft->JacobianForElementSize(&ts->ei, xi);
     }
     ts->si.elemsize_Eulerian = esz;
     ts->si.elemsize_Eulerian_cartesian = esz_cart;
+    ts->si.elemsize_Lagrangian = eszL;
+    ts->si.elemsize_Lagrangian_cartesian = eszL_cart;
   }
   JITFuncSpec_ResidualAndJacobian_FiniteElement func;
   if (param >= 0)

@@ -122,7 +122,8 @@ class CEmitter:
                 test_fields.append(t.field)
         names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi",
                                        ex.NORMAL[0]: "shapeinfo->normal[0]", ex.NORMAL[1]: "shapeinfo->normal[1]", ex.NORMAL[2]: "shapeinfo->normal[2]",
-                                       ex.ELEMSIZE_EUL: "shapeinfo->elemsize_Eulerian", ex.ELEMSIZE_EUL_CART: "shapeinfo->elemsize_Eulerian_cartesian"}
+                                       ex.ELEMSIZE_EUL: "shapeinfo->elemsize_Eulerian", ex.ELEMSIZE_EUL_CART: "shapeinfo->elemsize_Eulerian_cartesian",
+                                       ex.ELEMSIZE_LAG: "shapeinfo->elemsize_Lagrangian", ex.ELEMSIZE_LAG_CART: "shapeinfo->elemsize_Lagrangian_cartesian"}
         for a in atoms:
             names[code.atom_symbol(a)] = "this_" + a.cname
         for k, p in enumerate(code.global_params):
@@ -307,7 +308,8 @@ class CEmitter:
         atoms = sorted([code._atom_syms[s_] for s_ in used], key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
         names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi",
                                        ex.NORMAL[0]: "shapeinfo->normal[0]", ex.NORMAL[1]: "shapeinfo->normal[1]", ex.NORMAL[2]: "shapeinfo->normal[2]",
-                                       ex.ELEMSIZE_EUL: "shapeinfo->elemsize_Eulerian", ex.ELEMSIZE_EUL_CART: "shapeinfo->elemsize_Eulerian_cartesian"}
+                                       ex.ELEMSIZE_EUL: "shapeinfo->elemsize_Eulerian", ex.ELEMSIZE_EUL_CART: "shapeinfo->elemsize_Eulerian_cartesian",
+                                       ex.ELEMSIZE_LAG: "shapeinfo->elemsize_Lagrangian", ex.ELEMSIZE_LAG_CART: "shapeinfo->elemsize_Lagrangian_cartesian"}
         for a in atoms:
             names[code.atom_symbol(a)] = "this_" + a.cname
         for k, p in enumerate(code.global_params):
@@ -456,7 +458,8 @@ class CEmitter:
                 test_fields.append(t.field)
         names: Dict[sp.Symbol, str] = {ex.DX_EUL: "dx", ex.DX_LAG: "dX", ex.TIME: "t[0]", ex.pi: "Pi",
                                        ex.NORMAL[0]: "shapeinfo->normal[0]", ex.NORMAL[1]: "shapeinfo->normal[1]", ex.NORMAL[2]: "shapeinfo->normal[2]",
-                                       ex.ELEMSIZE_EUL: "shapeinfo->elemsize_Eulerian", ex.ELEMSIZE_EUL_CART: "shapeinfo->elemsize_Eulerian_cartesian"}
+                                       ex.ELEMSIZE_EUL: "shapeinfo->elemsize_Eulerian", ex.ELEMSIZE_EUL_CART: "shapeinfo->elemsize_Eulerian_cartesian",
+                                       ex.ELEMSIZE_LAG: "shapeinfo->elemsize_Lagrangian", ex.ELEMSIZE_LAG_CART: "shapeinfo->elemsize_Lagrangian_cartesian"}
         for a in atoms:
             names[code.atom_symbol(a)] = "this_" + a.cname
         for k, p in enumerate(code.global_params):
@@ -664,6 +667,10 @@ class CEmitter:
                 w(" functable->shapes_required_ResJac[%d].elemsize_Eulerian_Pos=true;" % i)
             if code.residuals[rn].has(ex.ELEMSIZE_EUL_CART):
                 w(" functable->shapes_required_ResJac[%d].elemsize_Eulerian_cartesian_Pos=true;" % i)
+            if code.residuals[rn].has(ex.ELEMSIZE_LAG):
+                w(" functable->shapes_required_ResJac[%d].elemsize_Lagrangian_Pos=true;" % i)
+            if code.residuals[rn].has(ex.ELEMSIZE_LAG_CART):
+                w(" functable->shapes_required_ResJac[%d].elemsize_Lagrangian_cartesian_Pos=true;" % i)
         w(" functable->JacobianForElementSize=&JacobianForElementSize;")
         w(" functable->numglobal_params=%d;" % len(code.global_params))
         w(" functable->global_parameters=(double **)calloc(%d,sizeof(double*));" % max(1, len(code.global_params)))

@@ -55,6 +55,7 @@ typedef struct JITShapeInfo
   unsigned int n_int_pt;
   double int_pt_weight, int_pt_weight_Lagrangian, int_pt_weight_unity;
   double elemsize_Eulerian, elemsize_Eulerian_cartesian; /* jitbridge.h:178 */
+  double elemsize_Lagrangian, elemsize_Lagrangian_cartesian; /* jitbridge.h:179 */
   double **int_pt_weights_d_coords;      /* [dim][node] */
   double ****int_pt_weights_d2_coords;   /* [dim][dim][node][node] */
   double *shape_C2, **dx_shape_C2, **dX_shape_C2, **dS_shape_C2;
@@ -83,7 +84,7 @@ typedef struct JITFuncSpec_RequiredShapes_FiniteElement
 {
   bool psi_C1, psi_C2, dx_psi_C1, dx_psi_C2, dX_psi_C1, dX_psi_C2;
   bool psi_Pos, dx_psi_Pos, dX_psi_Pos;
-  bool elemsize_Eulerian_Pos, elemsize_Eulerian_cartesian_Pos; /* jitbridge.h:305-306 */
+  bool elemsize_Eulerian_Pos, elemsize_Lagrangian_Pos, elemsize_Eulerian_cartesian_Pos, elemsize_Lagrangian_cartesian_Pos; /* jitbridge.h:305-306 */
 } JITFuncSpec_RequiredShapes_FiniteElement_t;
 
 typedef void (*JITFuncSpec_GetZ2Fluxes_FiniteElement)(const JITElementInfo_t *, const JITShapeInfo_t *, double *); /* jitbridge.h:287 */

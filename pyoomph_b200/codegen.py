@@ -323,7 +323,7 @@ class FiniteElementCode:
             used |= {s_ for s_ in e.free_symbols if s_ in self._atom_syms}
         atoms = sorted((self._atom_syms[s_] for s_ in used), key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
         allsyms = set().union(*[e.free_symbols for e in R]) if R else set()
-        form = ResidualForm("|points", slots, R, {}, {}, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=ex.DX_LAG in allsyms)
+        form = ResidualForm("|points", slots, R, {}, {}, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=(ex.DX_LAG in allsyms or ex.ELEMSIZE_LAG in allsyms or ex.ELEMSIZE_LAG_CART in allsyms))
         self._forms["|points"] = form
         return form
 
@@ -345,7 +345,7 @@ class FiniteElementCode:
             used |= {s for s in e.free_symbols if s in self._atom_syms}
         atoms = sorted((self._atom_syms[s] for s in used), key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
         allsyms = set().union(*[e.free_symbols for e in R]) if R else set()
-        form = ResidualForm("|integrals", slots, R, {}, {}, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=ex.DX_LAG in allsyms)
+        form = ResidualForm("|integrals", slots, R, {}, {}, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=(ex.DX_LAG in allsyms or ex.ELEMSIZE_LAG in allsyms or ex.ELEMSIZE_LAG_CART in allsyms))
         self._forms["|integrals"] = form
         return form
 
@@ -600,7 +600,7 @@ class FiniteElementCode:
             used |= {s for s in e.free_symbols if s in self._atom_syms}
         atoms = sorted((self._atom_syms[s] for s in used), key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
         allsyms = set().union(*[e.free_symbols for e in list(R) + list(J.values()) + list(M.values())]) if R else set()
-        return ResidualForm(name, slots, R, J, M, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=ex.DX_LAG in allsyms)
+        return ResidualForm(name, slots, R, J, M, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=(ex.DX_LAG in allsyms or ex.ELEMSIZE_LAG in allsyms or ex.ELEMSIZE_LAG_CART in allsyms))
 
     # -- Hessian (second derivatives), fixed meshes ------------------------------------------------
     def derive_hessian(self, resname: str = ""):
@@ -711,7 +711,7 @@ class FiniteElementCode:
         atoms = sorted((self._atom_syms[s_] for s_ in used), key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
         allsyms = set().union(*[e.free_symbols for e in list(J.values()) + list(M.values())]) if (J or M) else set()
         hf = ResidualForm(key, list(form.slots), [sp.Integer(0)] * len(form.slots), J, M, atoms,
-                          uses_dx=ex.DX_EUL in allsyms, uses_dX=ex.DX_LAG in allsyms)
+                          uses_dx=ex.DX_EUL in allsyms, uses_dX=(ex.DX_LAG in allsyms or ex.ELEMSIZE_LAG in allsyms or ex.ELEMSIZE_LAG_CART in allsyms))
         self._forms[key] = hf
         return hf
 
@@ -751,7 +751,7 @@ class FiniteElementCode:
             used |= {s_ for s_ in e.free_symbols if s_ in self._atom_syms}
         atoms = sorted((self._atom_syms[s_] for s_ in used), key=lambda a: (a.field, a.dt_order, a.deriv, a.past))
         allsyms = set().union(*[e.free_symbols for e in list(J.values()) + list(M.values())]) if (J or M) else set()
-        return ResidualForm(key, slots, [sp.Integer(0)] * len(slots), J, M, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=ex.DX_LAG in allsyms)
+        return ResidualForm(key, slots, [sp.Integer(0)] * len(slots), J, M, atoms, uses_dx=ex.DX_EUL in allsyms, uses_dX=(ex.DX_LAG in allsyms or ex.ELEMSIZE_LAG in allsyms or ex.ELEMSIZE_LAG_CART in allsyms))
 
     def atom_symbol(self, info: AtomInfo) -> sp.Symbol:
         return self._atom(info)

@@ -1302,14 +1302,18 @@ class CudaEmitter:
         for k, p in enumerate(code.global_params):
             names[code._param_syms[p]] = "a.params[%d]" % k
         all_exprs = list(form.R) + list(form.J.values()) + list(form.M.values())
-        if any(e_.has(ex.ELEMSIZE_EUL) or e_.has(ex.ELEMSIZE_EUL_CART) for e_ in all_exprs if hasattr(e_, "has")):
+        names[ex.ELEMSIZE_LAG], names[ex.ELEMSIZE_LAG_CART] = "eszL_eul", "eszL_cart"
+        for (sym_e, sym_c, xkey, v_e, v_c) in ((ex.ELEMSIZE_EUL, ex.ELEMSIZE_EUL_CART, "xpos", "esz_eul", "esz_cart"),
+                                               (ex.ELEMSIZE_LAG, ex.ELEMSIZE_LAG_CART, "xlag", "eszL_eul", "eszL_cart")):
+            if not any(e_.has(sym_e) or e_.has(sym_c) for e_ in all_exprs if hasattr(e_, "has")):
+                continue
             # element sizes (fill_shape_info_element_sizes, src/elements.cpp:3527-3568): sum over ALL integration points of w * J, with the
             # coordinate system's JacobianForElementSize (2 Pi r when axisymmetric) at the point for the non-Cartesian one; every
             # (element, point) thread forms the sum itself (a few hundred flops; only classes that use the symbols pay)
             if edim != dim or dim not in (2, 3):
                 raise NotImplementedError("element sizes: bulk elements (two- or three-dimensional) only")
             axi = code.coordinate_system.get_id_name() == "Axisymmetric"
-            w("      double esz_cart = 0.0, esz_eul = 0.0;")
+            w("      double %s = 0.0, %s = 0.0;" % (v_c, v_e))
             w("      for (int q = 0; q < %d; ++q)" % NIPT)
             w("      {")
             w("        const double* dq = s_dpsi2 + q * %d; const double* pq = s_psi2 + q * %d; (void)pq;" % (NN * edim, NN))
@@ -1317,7 +1321,7 @@ class CudaEmitter:
                 w("        double e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0, ex0 = 0.0;")
                 w("        for (int l = 0; l < %d; ++l)" % NN)
                 w("        {")
-                w("          const double X0 = E[%d + l * 2], X1 = E[%d + l * 2 + 1];" % (plan["xpos"], plan["xpos"]))
+                w("          const double X0 = E[%d + l * 2], X1 = E[%d + l * 2 + 1];" % (plan[xkey], plan[xkey]))
                 w("          e00 += X0 * dq[l * 2]; e01 += X1 * dq[l * 2]; e10 += X0 * dq[l * 2 + 1]; e11 += X1 * dq[l * 2 + 1]; ex0 += X0 * pq[l];")
                 w("        }")
                 w("        const double a00 = e00 * e00 + e01 * e01, a01 = e00 * e10 + e01 * e11, a11 = e10 * e10 + e11 * e11;")
@@ -1328,7 +1332,7 @@ class CudaEmitter:
                 w("        double e[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}}; const double ex0 = 0.0; (void)ex0;")
                 w("        for (int l = 0; l < %d; ++l)" % NN)
                 w("        {")
-                w("          const double X0 = E[%d + l * 3], X1 = E[%d + l * 3 + 1], X2 = E[%d + l * 3 + 2];" % ((plan["xpos"],) * 3))
+                w("          const double X0 = E[%d + l * 3], X1 = E[%d + l * 3 + 1], X2 = E[%d + l * 3 + 2];" % ((plan[xkey],) * 3))
                 w("          #pragma unroll")
                 w("          for (int b = 0; b < 3; ++b) { const double d = dq[l * 3 + b]; e[b][0] += X0 * d; e[b][1] += X1 * d; e[b][2] += X2 * d; }")
                 w("        }")
@@ -1340,9 +1344,9 @@ class CudaEmitter:
                 w("        const double detm = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0])")
                 w("                          + m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);")
                 w("        const double Jq = c_w[q] * sqrt(detm);")
-            w("        esz_cart += Jq; esz_eul += Jq * %s;" % ("(2.0 * 3.14159265359 * ex0)" if axi else "1.0"))
+            w("        %s += Jq; %s += Jq * %s;" % (v_c, v_e, "(2.0 * 3.14159265359 * ex0)" if axi else "1.0"))
             w("      }")
-            w("      (void)esz_cart; (void)esz_eul;")
+            w("      (void)%s; (void)%s;" % (v_c, v_e))
         # local-derivative sums per (field, kind)
         for (f, kind), derivs in needed.items():
             fld = code.fields[f]

@@ -328,9 +328,10 @@ class StreamlineDiffusionAdvection(Equations):
 
     One number per element -- the integral of the measure over ALL its integration points -- enters every point of the element."""
 
-    def __init__(self, name: str = "c", wind=(1.0, 0.5), diffusivity=0.01, tau=0.5, cartesian_size: bool = False):
+    def __init__(self, name: str = "c", wind=(1.0, 0.5), diffusivity=0.01, tau=0.5, cartesian_size: bool = False, lagrangian_size: bool = False):
         super().__init__()
         self.name, self.wind, self.D, self.tau, self.cartesian_size = name, wind, diffusivity, tau, cartesian_size
+        self.lagrangian_size = lagrangian_size      # h from the Lagrangian element size: independent of the position dofs of a moving mesh
 
     def define_fields(self):
         self.define_scalar_field(self.name, "C2")
@@ -340,8 +341,10 @@ class StreamlineDiffusionAdvection(Equations):
         gc, gv = grad(c), grad(v)
         wc = sum(self.wind[i] * gc[i, 0] for i in range(len(self.wind)))
         wv = sum(self.wind[i] * gv[i, 0] for i in range(len(self.wind)))
-        if self.cartesian_size:
-            from .expressions import ELEMSIZE_EUL_CART
+        if self.lagrangian_size:
+            import sympy as sp
+            h = var("cartesian_element_size_Lagrangian" if self.cartesian_size else "element_size_Lagrangian") ** sp.Rational(1, len(self.wind))
+        elif self.cartesian_size:
             import sympy as sp
             h = sp.sqrt(var("cartesian_element_size_Eulerian"))
         else:

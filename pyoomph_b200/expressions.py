@@ -34,6 +34,10 @@ NORMAL = sp.symbols("NRM__0 NRM__1 NRM__2", real=True)
 # system's / Cartesian) measure over the element, one number per element
 ELEMSIZE_EUL = sp.Symbol("ESZ__eulerian", positive=True)
 ELEMSIZE_EUL_CART = sp.Symbol("ESZ__eulerian_cartesian", positive=True)
+# ... and their Lagrangian siblings (src/jitbridge.h:179): integrated over the Lagrangian coordinates, so constants with respect to every dof
+# (usable on moving meshes, where the Eulerian sizes would need elemsize_d_coords)
+ELEMSIZE_LAG = sp.Symbol("ESZ__lagrangian", positive=True)
+ELEMSIZE_LAG_CART = sp.Symbol("ESZ__lagrangian_cartesian", positive=True)
 
 DIRS = ("x", "y", "z")
 
@@ -116,15 +120,20 @@ def var(arg: Union[str, Sequence[str]]):
     code = _Context.current()
     if arg == "time":
         return TIME
-    if arg in ("element_size_Eulerian", "cartesian_element_size_Eulerian", "element_length_h"):
-        # pyoomph/expressions/generic.py:174-178; stabilisation terms (SUPG / PSPG, artificial diffusion) are built on them
+    if arg in ("element_size_Eulerian", "cartesian_element_size_Eulerian", "element_length_h", "cartesian_element_length_h",
+               "element_size_Lagrangian", "cartesian_element_size_Lagrangian"):
+        # pyoomph/expressions/generic.py:174-180; stabilisation terms (SUPG / PSPG, artificial diffusion) are built on them
         if code.etype.elem_dim != code.nodal_dim or code.nodal_dim not in (2, 3):
             raise NotImplementedError("element sizes: bulk elements (two- or three-dimensional) only")
         if arg == "cartesian_element_size_Eulerian":
             return ELEMSIZE_EUL_CART
+        if arg == "element_size_Lagrangian":
+            return ELEMSIZE_LAG
+        if arg == "cartesian_element_size_Lagrangian":
+            return ELEMSIZE_LAG_CART
+        if arg == "cartesian_element_length_h":
+            return ELEMSIZE_EUL_CART ** sp.Rational(1, code.etype.elem_dim)
         return ELEMSIZE_EUL if arg == "element_size_Eulerian" else ELEMSIZE_EUL ** sp.Rational(1, code.etype.elem_dim)
-    if arg in ("element_size_Lagrangian", "cartesian_element_size_Lagrangian"):
-        raise NotImplementedError("Lagrangian element sizes are outside the GPU path")
     if arg == "normal":
         if code.etype.elem_dim >= code.nodal_dim and not code.etype.name.startswith("QuadFace"):
             raise RuntimeError("var(\"normal\") is defined on interface elements only")

@@ -436,6 +436,16 @@ def make_problem(kind: str, N: int, seed: int = 0, distortion: float = 0.0, unst
             pinned.update({n + MODE_SUFFIX: v for n, v in list(pinned.items())})
         unsteady = True
         params = {"azimuthal_m": 1.0}
+    elif kind in ("supg_ale", "supg_ale_axi"):
+        # Lagrangian element sizes on a MOVING mesh (element_size_Lagrangian: constants with respect to the position dofs); axisymmetric:
+        # the coordinate system's 2 pi R at the Lagrangian position enters the size
+        from pyoomph_b200.equations import StreamlineDiffusionAdvection
+        mesh = RectangularQuadMesh(N)
+        axi = kind == "supg_ale_axi"
+        code = FiniteElementCode("Quad2dC2", StreamlineDiffusionAdvection(lagrangian_size=True, cartesian_size=not axi) + PseudoElasticMesh(),
+                                 name=kind.replace("_", ""), coordinate_system="axisymmetric" if axi else "cartesian")
+        pinned = {"c": mesh.boundaries["left"]}
+        unsteady = True
     elif kind == "ale_axi":        # config 4 bulk part as BASELINE names it: axisymmetric NS-TH on a pseudo-elastic moving mesh
         mesh = RectangularQuadMesh(N)
         code = FiniteElementCode("Quad2dC2", NavierStokesEquations(dynamic_viscosity=0.01, mass_density=1.0) + PseudoElasticMesh(),

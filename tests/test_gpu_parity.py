@@ -36,7 +36,8 @@ TRIANGLES = [("poisson_tri", 9, 0.0, False), ("poisson_tri", 8, 0.12, False), ("
 TETRAHEDRA = [("poisson_tet", 3, 0.0, False), ("poisson_tet", 3, 0.1, False), ("heat3d_tet", 3, 0.1, False), ("ns_tet", 2, 0.1, False)]
 
 # element sizes (one number per element from all of its integration points) in a streamline-upwind term; axisymmetric: the Cartesian size
-ELEMENT_SIZES = [("supg", 9, 0.0, False), ("supg", 8, 0.12, False), ("supg_axi", 7, 0.1, False), ("supg3d", 3, 0.1, False), ("supg_tet", 2, 0.1, False), ("supg_tri", 6, 0.1, False)]
+ELEMENT_SIZES = [("supg", 9, 0.0, False), ("supg", 8, 0.12, False), ("supg_axi", 7, 0.1, False), ("supg3d", 3, 0.1, False), ("supg_tet", 2, 0.1, False), ("supg_tri", 6, 0.1, False),
+                 ("supg_ale", 6, 0.1, False), ("supg_ale_axi", 5, 0.1, False)]   # Lagrangian sizes on moving meshes
 
 VARIANTS = [("ns", 11, 0.12, False), ("ns_unsteady", 10, 0.1, True), ("heat3d", 3, 0.1, True), ("ale", 6, 0.08, True), ("poisson", 33, 0.15, True),
             ("ns_axi_swirl", 6, 0.1, True), ("ale_axi", 6, 0.08, True)]

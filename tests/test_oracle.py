@@ -656,6 +656,58 @@ def test_element_sizes_of_the_oracle():
         op.close()
 
 
+def test_lagrangian_element_sizes_of_the_oracle():
+    """var("element_size_Lagrangian") / "cartesian_element_size_Lagrangian" (src/elements.cpp:3546-3551, :3569-3574; jitbridge.h:179) on a
+    MOVING mesh: on a uniform N x N Lagrangian mesh the Cartesian size is 1/N^2 whatever the current positions are, so the residual
+    equals the one written with h = 1/N; the analytic Jacobian (value and position columns) agrees with finite differences on a
+    distorted mesh, Cartesian and axisymmetric (2 pi R at the Lagrangian position)."""
+    from problems import csr_to_sorted, make_oracle, make_problem
+    from pyoomph_b200.codegen import FiniteElementCode
+    from pyoomph_b200.equations import PseudoElasticMesh, StreamlineDiffusionAdvection
+    import pyoomph_b200.expressions as ex_
+    import pyoomph_b200.equations as eqm
+    N = 4
+    pb = make_problem("supg_ale", N)
+
+    class _ConstH(StreamlineDiffusionAdvection):
+        def define_residuals(self):
+            saved = eqm.var
+            eqm.var = lambda a: (1.0 / N ** 2 if a == "cartesian_element_size_Lagrangian" else saved(a))
+            try:
+                super().define_residuals()
+            finally:
+                eqm.var = saved
+    pbc = dict(pb, code=FiniteElementCode("Quad2dC2", _ConstH(lagrangian_size=True, cartesian_size=True) + PseudoElasticMesh(), name="supgaleconst"))
+    a, b = make_oracle(pb), make_oracle(pbc)
+    ra, ma = a.assemble(flag=1)
+    rb, mb = b.assemble(flag=1)
+    assert np.abs(ra - rb).max() <= 1e-13 * np.abs(rb).max()
+    n = pb["dofmap"].n_dof
+    assert abs(csr_to_sorted(n, *ma[0]) - csr_to_sorted(n, *mb[0])).max() <= 1e-13 * abs(csr_to_sorted(n, *mb[0])).max()
+    a.close(); b.close()
+    for kind in ("supg_ale", "supg_ale_axi"):
+        pb = make_problem(kind, 3, distortion=0.12)
+        op = make_oracle(pb)
+        n = pb["dofmap"].n_dof
+        _, mats = op.assemble(flag=1)
+        A = csr_to_sorted(n, *mats[0]).toarray()
+        eps = 1e-6
+        for node in range(0, pb["mesh"].n_node, 5):
+            for (arr, eqs, key) in ((pb["vals"][0], pb["dofmap"].node_eqn, "node_val"), (pb["pos_hist"][0], pb["dofmap"].pos_eqn, "node_pos")):
+                g = eqs[node, 0]
+                if g < 0:
+                    continue
+                res = []
+                for sgn in (+1, -1):
+                    v = arr.copy()
+                    v[node, 0] += sgn * eps
+                    op.update_values(0, **{key: v})
+                    res.append(op.assemble(flag=0)[0])
+                op.update_values(0, **{key: arr})
+                assert np.abs((res[0] - res[1]) / (2 * eps) - A[:, g]).max() <= 2e-7 * np.abs(A).max(), (kind, key, node)
+        op.close()
+
+
 def test_integral_gradient_contributions_match_finite_differences_of_the_integrals():
     """add_integral_function(..., with_gradient=True): the residual vector of "d_integral_<name>" is d(integral)/dU (checked against
     central differences of EvalIntegralExpression), a linear functional has a vanishing second derivative, a quadratic one a symmetric one"""
